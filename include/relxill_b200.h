@@ -1,0 +1,108 @@
+/* relxill_b200.h — C ABI of librelxill_b200.so, the B200 (sm_100a) implementation of relxill's
+ * spectrum-evaluation hot path.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) the XSPEC/ISIS local-model functions, drop-in for the symbols the reference's generated
+ *      wrapper exports (reference src/create_wrapper_xspec.py:153-162, one per block of
+ *      src/modelfiles/lmodel_relxill_public.dat, dispatched by xspec_C_wrapper_eval_model,
+ *      src/LocalModel.cpp:143-160).  Same signature, same parameter order, same units.
+ *
+ *  (2) the batched entry points (new; north_star): N parameter vectors on one shared energy grid.
+ *
+ * There is no CPU fallback: every entry point runs the CUDA kernels and fails (non-zero return,
+ * message on stderr, flux zeroed) if no device / tables are available.
+ */
+#ifndef RELXILL_B200_H_
+#define RELXILL_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- (1) XSPEC local models
+ * energy[Nflux+1] ascending bin edges (keV); parameter[] in lmodel.dat order including the
+ * $switch entries, excluding norm; flux[Nflux] out (photons/cm^2/s/bin).  For the convolution
+ * models ("con") flux is input and output.  spectrum, fluxError and init are ignored, as in the
+ * reference.  Tables are read from $RELXILL_TABLE_PATH (or ./) on first use, like the reference
+ * (src/relutility.c:320-328). */
+#define RELXILL_B200_LMOD(name)                                                                            \
+  void name(const double *energy, int Nflux, const double *parameter, int spectrum, double *flux,         \
+            double *fluxError, const char *init)
+
+RELXILL_B200_LMOD(lmodrelline);              /* lmodel_relxill_public.dat:1   relline      (10 par) */
+RELXILL_B200_LMOD(lmodrelconv);              /* :13  relconv      (8)  */
+RELXILL_B200_LMOD(lmodrellinelp);            /* :23  relline_lp   (10) */
+RELXILL_B200_LMOD(lmodrelconvlp);            /* :35  relconv_lp   (9)  */
+RELXILL_B200_LMOD(lmodrelxill);              /* :46  relxill      (13) */
+RELXILL_B200_LMOD(lmodrelxilllp);            /* :61  relxilllp    (14) */
+RELXILL_B200_LMOD(lmodrelxilldensnthcomp);   /* :96  relxillCp    (14) */
+RELXILL_B200_LMOD(lmodrelxilllpdensnthcomp); /* :112 relxilllpCp  (17) */
+
+/* ---------------------------------------------------------------- library state */
+/* Select the CUDA device and load the tables from `table_dir` (NULL: $RELXILL_TABLE_PATH or "./").
+ * Optional: the first evaluation does it lazily on the current device.  Returns 0 on success. */
+int relxill_b200_init(const char *table_dir, int device);
+/* Free all device memory (tables, scratch). */
+void relxill_b200_shutdown(void);
+/* Equivalent of the reference's RELXILL_NUM_RZONES environment variable
+ * (src/relutility.c:506-544); 0 restores the defaults (1 / 10 / 25).  The env var itself is read
+ * once at init. */
+void relxill_b200_set_num_zones(int n);
+/* Number of parameters of a model ("relxilllp", ...; XSPEC names), -1 if unknown. */
+int relxill_b200_num_params(const char *model);
+/* Default parameter vector (lmodel.dat column 3); returns the count or -1. */
+int relxill_b200_default_params(const char *model, double *out);
+/* Last error message of this thread ("" if none). */
+const char *relxill_b200_last_error(void);
+
+/* ---------------------------------------------------------------- (2) batched evaluation
+ * model   XSPEC model name.
+ * energy  [n_flux+1] shared bin edges (keV), host memory.
+ * params  [n_vec][npar] row-major, host memory.
+ * flux    [n_vec][n_flux] row-major, host memory (input as well for convolution models).
+ * status  [n_vec] or NULL: 0 = ok, >0 = this vector's parameters were rejected / evaluation
+ *         failed (its flux row is zeroed), mirroring the reference's per-call failure.
+ * Returns 0 if the batch ran (individual vectors may still carry a status), <0 on a library
+ * error (no device, tables missing, unknown model). */
+int relxill_batch_eval(const char *model, const double *energy, int n_flux, const double *params, long n_vec,
+                       double *flux, int *status);
+
+/* Same, but the result stays on the device: d_flux is a device pointer to [n_vec][n_flux]
+ * doubles (e.g. a torch tensor's data_ptr) and the work is enqueued on `stream`
+ * (a cudaStream_t passed as void*, NULL = default stream).  Used for the multi-GPU gather. */
+int relxill_batch_eval_device(const char *model, const double *energy, int n_flux, const double *params,
+                              long n_vec, double *d_flux, int *status, void *stream);
+
+/* Prepared batches: interpret + upload once, evaluate many times with everything resident in
+ * HBM (what bench.py times as `value`). */
+typedef struct relxill_b200_batch relxill_b200_batch;
+relxill_b200_batch *relxill_b200_prepare(const char *model, const double *energy, int n_flux,
+                                         const double *params, long n_vec);
+int relxill_b200_run(relxill_b200_batch *b, double *d_flux, void *stream);
+/* per-vector status after prepare/run (host copy), length n_vec */
+int relxill_b200_batch_status(relxill_b200_batch *b, int *status);
+void relxill_b200_free_batch(relxill_b200_batch *b);
+
+/* ---------------------------------------------------------------- measurement support */
+/* Exact algorithmic byte count of the last run of `b`: distinct xillver corner
+ * rows per vector (U, host-counted from the zone indices the kernels produced) and the other
+ * table/IO terms.  out[0]=bytes total, out[1]=sum of U over vectors, out[2]=xillver bytes,
+ * out[3]=upper bound without cross-zone sharing. */
+int relxill_b200_algorithmic_bytes(relxill_b200_batch *b, double *out4);
+/* Number of kernel launches issued by the last relxill_b200_run of `b`. */
+long relxill_b200_last_launches(relxill_b200_batch *b);
+/* Time (ms, CUDA events on the run's stream) spent in each kernel family during the last run when
+ * profiling is enabled with relxill_b200_set_profiling(1); names[] receives static strings.
+ * Returns the number of entries written (<= max). */
+void relxill_b200_set_profiling(int on);
+int relxill_b200_kernel_times(relxill_b200_batch *b, const char **names, double *ms, long *launches, int max);
+
+/* Stage probes for the parity tests (device -> host copies of intermediates of vector `iv` of
+ * the last run; sizes as in oracle/relxill_oracle.h).  Return 0 on success. */
+int relxill_b200_probe(relxill_b200_batch *b, long iv, const char *what, double *out, long max_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

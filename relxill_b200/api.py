@@ -1,0 +1,195 @@
+"""Host-side mirror of the reference's local-model interface on top of the C ABI.
+
+The reference's in-process API is `LocalModel(ModelName).set_par(XPar, v).eval_model(spectrum)`
+(reference test/speed/speed_test.cpp:30-44, src/LocalModel.h:62-128); XSPEC calls the generated
+`lmod*` C functions (src/create_wrapper_xspec.py:153-162).  Both are mirrored here with the same
+names, parameter order and failure behaviour, plus the batched entry point.  All numerical work
+happens in librelxill_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+
+# parameter names in lmodel.dat order (reference src/modelfiles/lmodel_relxill_public.dat)
+PARAM_NAMES = {
+    "relline": ["lineE", "Index1", "Index2", "Rbr", "a", "Incl", "Rin", "Rout", "z", "limb"],
+    "relconv": ["Index1", "Index2", "Rbr", "a", "Incl", "Rin", "Rout", "limb"],
+    "relline_lp": ["lineE", "h", "a", "Incl", "Rin", "Rout", "z", "limb", "gamma", "switch_returnrad"],
+    "relconv_lp": ["h", "beta", "a", "Incl", "Rin", "Rout", "limb", "gamma", "switch_returnrad"],
+    "relxill": ["Index1", "Index2", "Rbr", "a", "Incl", "Rin", "Rout", "z", "gamma", "logxi", "Afe", "Ecut",
+                "refl_frac"],
+    "relxilllp": ["h", "beta", "a", "Incl", "Rin", "Rout", "z", "gamma", "logxi", "Afe", "Ecut", "refl_frac",
+                  "switch_returnrad", "switch_reflfrac_boost"],
+    "relxillCp": ["Incl", "a", "Rin", "Rout", "Rbr", "Index1", "Index2", "z", "gamma", "logxi", "logN", "Afe", "kTe",
+                  "refl_frac"],
+    "relxilllpCp": ["Incl", "a", "Rin", "Rout", "h", "beta", "gamma", "logxi", "logN", "Afe", "kTe", "refl_frac", "z",
+                    "iongrad_index", "iongrad_type", "switch_returnrad", "switch_reflfrac_boost"],
+}
+
+
+class ModelEvalFailed(RuntimeError):
+    """Same role as the reference's ModelEvalFailed (src/LocalModel.h:37-52)."""
+
+
+class ModelNotFound(KeyError):
+    """Same role as the reference's ModelNotFound (src/ModelDatabase.h:33-48)."""
+
+
+def init(table_dir: str | None = None, device: int = -1) -> None:
+    rc = _lib.lib().relxill_b200_init(table_dir.encode() if table_dir else None, device)
+    if rc != 0:
+        raise RuntimeError("relxill_b200 initialisation failed: " + _lib.last_error())
+
+
+def shutdown() -> None:
+    _lib.lib().relxill_b200_shutdown()
+
+
+def set_num_zones(n: int | None) -> None:
+    """RELXILL_NUM_RZONES of the reference (src/relutility.c:506-544); None/0 = defaults."""
+    _lib.lib().relxill_b200_set_num_zones(int(n) if n else 0)
+
+
+def num_params(model: str) -> int:
+    n = _lib.lib().relxill_b200_num_params(model.encode())
+    if n < 0:
+        raise ModelNotFound(model)
+    return n
+
+
+def default_params(model: str) -> np.ndarray:
+    out = np.zeros(32)
+    n = _lib.lib().relxill_b200_default_params(model.encode(), out)
+    if n < 0:
+        raise ModelNotFound(model)
+    return out[:n].copy()
+
+
+def default_energy_grid(n: int = 3000, emin: float = 0.1, emax: float = 1000.0) -> np.ndarray:
+    """DefaultSpec grid (reference src/XspecSpectrum.h:121,143-149)."""
+    i = np.arange(n + 1, dtype=np.float64)
+    e = np.exp(i / float(n) * (np.log(emax) - np.log(emin)) + np.log(emin))
+    e[-1] = emax
+    return e
+
+
+def batch_eval(model: str, energy, params, flux_in=None, return_status: bool = False):
+    """N parameter vectors on one energy grid -> flux [N, n_flux] (host arrays in, host arrays out).
+    For convolution models pass the input spectra as `flux_in` [N, n_flux]."""
+    energy = np.ascontiguousarray(energy, np.float64)
+    params = np.ascontiguousarray(np.atleast_2d(params), np.float64)
+    npar = num_params(model)
+    if params.shape[1] != npar:
+        raise ValueError(f"{model} takes {npar} parameters, got {params.shape[1]}")
+    n, n_flux = params.shape[0], energy.size - 1
+    if flux_in is not None:
+        flux = np.ascontiguousarray(np.broadcast_to(np.asarray(flux_in, np.float64), (n, n_flux))).copy()
+    else:
+        flux = np.zeros((n, n_flux))
+    status = np.zeros(n, np.int32)
+    rc = _lib.lib().relxill_batch_eval(model.encode(), energy, n_flux, params, n, flux, status)
+    if rc != 0:
+        raise ModelEvalFailed(f"batched evaluation of {model} failed: {_lib.last_error()}")
+    return (flux, status) if return_status else flux
+
+
+class Batch:
+    """A prepared batch: parameters interpreted and resident in HBM; `run` only launches kernels."""
+
+    def __init__(self, model: str, energy, params):
+        self.model = model
+        self.energy = np.ascontiguousarray(energy, np.float64)
+        self.params = np.ascontiguousarray(np.atleast_2d(params), np.float64)
+        self.n, self.n_flux = self.params.shape[0], self.energy.size - 1
+        if self.params.shape[1] != num_params(model):
+            raise ValueError("wrong parameter count")
+        self._h = _lib.lib().relxill_b200_prepare(model.encode(), self.energy, self.n_flux, self.params, self.n)
+        if not self._h:
+            raise ModelEvalFailed(f"prepare({model}) failed: {_lib.last_error()}")
+
+    def run(self, d_flux_ptr: int, stream_ptr: int = 0) -> None:
+        rc = _lib.lib().relxill_b200_run(self._h, C.c_void_p(d_flux_ptr), C.c_void_p(stream_ptr))
+        if rc != 0:
+            raise ModelEvalFailed(f"run({self.model}) failed: {_lib.last_error()}")
+
+    def status(self) -> np.ndarray:
+        st = np.zeros(self.n, np.int32)
+        _lib.lib().relxill_b200_batch_status(self._h, st)
+        return st
+
+    def launches(self) -> int:
+        return int(_lib.lib().relxill_b200_last_launches(self._h))
+
+    def algorithmic_bytes(self) -> dict:
+        out = np.zeros(4)
+        _lib.lib().relxill_b200_algorithmic_bytes(self._h, out)
+        return dict(total=out[0], distinct_rows=out[1], xillver=out[2], xillver_upper_bound=out[3])
+
+    def kernel_times(self) -> dict:
+        names = (C.c_char_p * 16)()
+        ms = np.zeros(16)
+        cnt = np.zeros(16, np.int64)
+        n = _lib.lib().relxill_b200_kernel_times(self._h, names, ms, cnt, 16)
+        return {names[i].decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
+    def probe(self, iv: int, what: str, max_len: int = 50 * 4096) -> np.ndarray:
+        out = np.zeros(max_len)
+        n = _lib.lib().relxill_b200_probe(self._h, iv, what.encode(), out, max_len)
+        if n < 0:
+            raise RuntimeError(f"probe({what}) failed: {_lib.last_error()}")
+        return out[:n].copy()
+
+    def close(self) -> None:
+        if self._h:
+            _lib.lib().relxill_b200_free_batch(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def lmod(model: str, energy, parameter, flux_in=None) -> np.ndarray:
+    """Calls the XSPEC C symbol of `model` (lmodrelxilllp, ...) exactly as XSPEC would."""
+    if model not in _lib.LMOD_SYMBOLS:
+        raise ModelNotFound(model)
+    energy = np.ascontiguousarray(energy, np.float64)
+    parameter = np.ascontiguousarray(parameter, np.float64)
+    flux = np.zeros(energy.size - 1) if flux_in is None else np.array(flux_in, np.float64)
+    getattr(_lib.lib(), _lib.LMOD_SYMBOLS[model])(energy, energy.size - 1, parameter, 1, flux, None, b"")
+    return flux
+
+
+class LocalModel:
+    """`LocalModel(name).set_par(par, value).eval_model(energy)` as in the reference (src/LocalModel.h)."""
+
+    def __init__(self, model: str, params: Sequence[float] | None = None):
+        if model not in PARAM_NAMES:
+            raise ModelNotFound(model)
+        self.model = model
+        self.names = PARAM_NAMES[model]
+        self._lower = [n.lower() for n in self.names]
+        self.values = default_params(model) if params is None else np.array(params, np.float64)
+
+    def set_par(self, name: str, value: float) -> "LocalModel":
+        try:
+            self.values[self._lower.index(name.lower())] = value
+        except ValueError:
+            raise KeyError(f"parameter not found: {name}")
+        return self
+
+    def get_par(self, name: str) -> float:
+        return float(self.values[self._lower.index(name.lower())])
+
+    def eval_model(self, energy, flux_in=None) -> np.ndarray:
+        flux, status = batch_eval(self.model, energy, self.values[None, :], flux_in, return_status=True)
+        if status[0] != 0:
+            raise ModelEvalFailed(f"model evaluation failed (status {int(status[0])})")
+        return flux[0]

@@ -1,0 +1,537 @@
+// api.cu — runtime + C ABI of librelxill_b200.so (see include/relxill_b200.h).
+//
+// Engine: one per process (one process per GPU); owns the HBM-resident tables, a scratch arena
+// sized for one chunk of parameter vectors, and the kernel sequence.  Batches larger than the
+// chunk capacity are streamed through the arena chunk by chunk on the caller's stream.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/relxill_b200.h"
+#include "common.h"
+#include "kernels.h"
+#include "models.h"
+#include "tables.h"
+
+using namespace rx;
+
+namespace {
+
+thread_local std::string g_err;
+void set_err(const std::string &s) {
+  g_err = s;
+  if (!s.empty()) fprintf(stderr, " *** relxill_b200 error: %s\n", s.c_str());
+}
+
+#define CK(call)                                                            \
+  do {                                                                      \
+    cudaError_t e_ = (call);                                                \
+    if (e_ != cudaSuccess) {                                                \
+      set_err(std::string(#call) + ": " + cudaGetErrorString(e_));          \
+      return -2;                                                            \
+    }                                                                       \
+  } while (0)
+
+enum KFam { KF_SYSPAR, KF_ZONE, KF_FINE, KF_DIST, KF_LINE, KF_XILL, KF_CONV, KF_FINISH, KF_MEMSET, KF_COUNT };
+const char *KF_NAMES[KF_COUNT] = {"k_syspar", "k_zone", "k_fine", "k_dist", "k_line", "k_xill", "k_conv", "k_linefinish", "memset"};
+
+struct Engine {
+  std::mutex mu;
+  bool inited = false;
+  int device = 0;
+  Tables *tables = nullptr;
+  HostConfig cfg;
+  Scratch S{};
+  std::vector<void *> scratch_allocs;
+  double *d_total = nullptr;  // [cap][NCONV]
+  double *d_io = nullptr;     // staging for host-buffer calls
+  size_t d_io_cap = 0;
+  long max_chunk = 4096;
+  bool profiling = false;
+};
+Engine g_eng;
+
+void free_scratch(Engine &E) {
+  for (void *p : E.scratch_allocs) cudaFree(p);
+  E.scratch_allocs.clear();
+  E.S = Scratch{};
+  E.d_total = nullptr;
+}
+
+template <class T> bool salloc(Engine &E, T *&p, size_t n) {
+  void *d = nullptr;
+  if (cudaMalloc(&d, n * sizeof(T)) != cudaSuccess) return false;
+  E.scratch_allocs.push_back(d);
+  p = (T *) d;
+  return true;
+}
+
+int ensure_scratch(Engine &E, long cap, int nz_cap, int ne_cap, int nex_stride) {
+  Scratch &S = E.S;
+  if (S.cap >= cap && S.nz_cap >= nz_cap && S.ne_line_cap >= ne_cap && S.nex_stride >= nex_stride) return 0;
+  cap = std::max(cap, S.cap);
+  nz_cap = std::max(nz_cap, S.nz_cap);
+  ne_cap = std::max(ne_cap, S.ne_line_cap);
+  nex_stride = std::max(nex_stride, S.nex_stride);
+  free_scratch(E);
+  bool ok = true;
+  const size_t c = (size_t) cap;
+  ok &= salloc(E, S.re, c * NR) && salloc(E, S.gmin, c * NR) && salloc(E, S.gmax, c * NR) && salloc(E, S.emis, c * NR);
+  ok &= salloc(E, S.del_emit, c * NR) && salloc(E, S.del_inc, c * NR) && salloc(E, S.fr, c * NR);
+  ok &= salloc(E, S.it, c * NR) && salloc(E, S.izone, c * NR) && salloc(E, S.glim, c * 2) && salloc(E, S.reflfrac, c * 8);
+  ok &= salloc(E, S.trff, c * NR * NG * 2) && salloc(E, S.cosne, c * NR * NG * 2);
+  ok &= salloc(E, S.eshift, c * NZMAX) && salloc(E, S.zlxi, c * NZMAX) && salloc(E, S.zdens, c * NZMAX);
+  ok &= salloc(E, S.zect, c * NZMAX) && salloc(E, S.normch, c * NZMAX) && salloc(E, S.corr_flux, c * NZMAX);
+  ok &= salloc(E, S.corr_gshift, c * NZMAX) && salloc(E, S.nsrc, c);
+  ok &= salloc(E, S.xrow, c * NZMAX * 32) && salloc(E, S.xw, c * NZMAX * 32);
+  ok &= salloc(E, S.relflux, c * nz_cap * ne_cap) && salloc(E, S.dist, c * NZMAX * MAX_INCL);
+  ok &= salloc(E, S.xillz, c * nz_cap * (size_t) std::max(nex_stride, 1)) && salloc(E, S.status, c);
+  ok &= salloc(E, E.d_total, c * NCONV);
+  if (!ok) {
+    free_scratch(E);
+    set_err("out of device memory for the scratch arena");
+    return -2;
+  }
+  S.cap = cap; S.nz_cap = nz_cap; S.ne_line_cap = ne_cap; S.nex_stride = nex_stride;
+  return 0;
+}
+
+int engine_init(Engine &E, const char *dir, int device) {
+  if (E.inited) return 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_err("no CUDA device available (this library has no CPU fallback)");
+    return -1;
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  CK(cudaSetDevice(device));
+  E.device = device;
+  std::string d;
+  if (dir && *dir) d = dir;
+  else if (const char *env = getenv("RELXILL_TABLE_PATH")) d = env;  // src/relutility.c:320-328
+  else d = "./";
+  if (const char *env = getenv("RELXILL_NUM_RZONES")) E.cfg.env_num_zones = (int) atof(env);
+  if (const char *env = getenv("RELXILL_RETURNRAD_SWITCH")) E.cfg.env_returnrad = (int) atof(env);
+  if (const char *env = getenv("RELLINE_PHYSICAL_NORM")) E.cfg.env_phys_norm = ((int) strtod(env, nullptr) == 1) ? 1 : 0;
+  if (const char *env = getenv("RELXILL_B200_CHUNK")) E.max_chunk = std::max(1L, atol(env));
+  if (kernels_init() != 0) {
+    set_err("kernel attribute setup failed (is this an sm_100a device?)");
+    return -1;
+  }
+  E.tables = new Tables();
+  const std::string err = E.tables->load(d);
+  if (!err.empty()) {
+    set_err(err);
+    delete E.tables;
+    E.tables = nullptr;
+    return -1;
+  }
+  E.inited = true;
+  return 0;
+}
+
+}  // namespace
+
+struct relxill_b200_batch {
+  const ModelDef *m = nullptr;
+  long n = 0;
+  int n_flux = 0;
+  int nz_max = 1;
+  bool any_corr = false;
+  std::vector<VPar> vps;
+  std::vector<int> status;
+  VPar *d_vps = nullptr;
+  double *d_energy = nullptr;
+  long launches = 0;
+  long last_chunk0 = 0, last_chunk_n = 0;
+  double kt_ms[KF_COUNT] = {0};
+  long kt_n[KF_COUNT] = {0};
+};
+
+namespace {
+
+struct Timer {
+  Engine &E;
+  relxill_b200_batch *b;
+  cudaStream_t st;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  Timer(Engine &E_, relxill_b200_batch *b_, cudaStream_t s) : E(E_), b(b_), st(s) {
+    if (E.profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+  }
+  ~Timer() {
+    if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+  }
+  void begin() { if (E.profiling) cudaEventRecord(e0, st); }
+  void end(int fam, bool is_kernel = true) {
+    if (is_kernel) b->launches++;
+    b->kt_n[fam]++;
+    if (E.profiling) {
+      cudaEventRecord(e1, st);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      b->kt_ms[fam] += ms;
+    }
+  }
+};
+
+int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st) {
+  const ModelDef &m = *b->m;
+  const DevTables &T = E.tables->dev();
+  const int which = (m.prim == PRIM_NTHCOMP) ? 1 : 0;
+  const bool relxill = (m.type == T_RELXILL);
+  const int ne_line = (m.type == T_LINE) ? b->n_flux : NCONV;
+  const int nex_stride = relxill ? E.tables->xill_host(m.prim).stride : 1;
+  const int n_incl = relxill ? E.tables->xill_host(m.prim).n_incl : 0;
+  const long cap = std::min(b->n, E.max_chunk);
+  if (ensure_scratch(E, cap, b->nz_max, ne_line, nex_stride)) return -2;
+  const Scratch &S = E.S;
+  b->launches = 0;
+  for (int k = 0; k < KF_COUNT; k++) { b->kt_ms[k] = 0; b->kt_n[k] = 0; }
+  Timer tm(E, b, st);
+  const std::vector<double> &econv = E.tables->econv();
+  for (long c0 = 0; c0 < b->n; c0 += S.cap) {
+    const long nc = std::min(S.cap, b->n - c0);
+    const VPar *vps = b->d_vps + c0;
+    double *out = d_flux + (size_t) c0 * b->n_flux;
+    tm.begin();
+    CK(cudaMemsetAsync(S.relflux, 0, (size_t) nc * S.nz_cap * S.ne_line_cap * sizeof(double), st));
+    tm.end(KF_MEMSET, false);
+    tm.begin(); launch_syspar(vps, T, S, nc, 1, st); tm.end(KF_SYSPAR);
+    if (relxill) {
+      tm.begin(); launch_zone(vps, T, S, nc, st); tm.end(KF_ZONE);
+      if (b->any_corr) { tm.begin(); launch_syspar(vps, T, S, nc, 2, st); tm.end(KF_SYSPAR); }
+    }
+    tm.begin(); launch_fine(vps, T, S, nc, st); tm.end(KF_FINE);
+    if (relxill) {
+      tm.begin(); launch_dist(vps, T, S, nc, n_incl, econv[0], econv[NCONV], st); tm.end(KF_DIST);
+    }
+    if (m.type == T_LINE) {
+      tm.begin(); launch_line(vps, T, S, nc, b->d_energy, b->n_flux, 1, st); tm.end(KF_LINE);
+      tm.begin(); launch_linefinish(vps, S, nc, b->n_flux, out, st); tm.end(KF_FINISH);
+    } else {
+      tm.begin(); launch_line(vps, T, S, nc, T.econv, NCONV, 0, st); tm.end(KF_LINE);
+      if (relxill) {
+        tm.begin(); launch_xill(vps, T, S, nc, which, b->nz_max, st); tm.end(KF_XILL);
+        tm.begin(); launch_conv(vps, T, S, nc, b->d_energy, b->n_flux, out, E.d_total, which, 0, st); tm.end(KF_CONV);
+      } else {
+        tm.begin(); launch_conv(vps, T, S, nc, b->d_energy, b->n_flux, out, nullptr, 0, 1, st); tm.end(KF_CONV);
+      }
+    }
+    CK(cudaMemcpyAsync(b->status.data() + c0, S.status, nc * sizeof(int), cudaMemcpyDeviceToHost, st));
+    b->last_chunk0 = c0;
+    b->last_chunk_n = nc;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================== C ABI
+extern "C" {
+
+const char *relxill_b200_last_error(void) { return g_err.c_str(); }
+
+int relxill_b200_init(const char *table_dir, int device) {
+  std::lock_guard<std::mutex> lk(g_eng.mu);
+  return engine_init(g_eng, table_dir, device);
+}
+
+void relxill_b200_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_eng.mu);
+  free_scratch(g_eng);
+  if (g_eng.d_io) cudaFree(g_eng.d_io);
+  g_eng.d_io = nullptr;
+  g_eng.d_io_cap = 0;
+  delete g_eng.tables;
+  g_eng.tables = nullptr;
+  g_eng.inited = false;
+}
+
+void relxill_b200_set_num_zones(int n) { g_eng.cfg.env_num_zones = n; }
+void relxill_b200_set_profiling(int on) { g_eng.profiling = on != 0; }
+
+int relxill_b200_num_params(const char *model) {
+  const ModelDef *m = find_model(model);
+  return m ? m->npar : -1;
+}
+int relxill_b200_default_params(const char *model, double *out) {
+  const ModelDef *m = find_model(model);
+  if (!m) return -1;
+  for (int i = 0; i < m->npar; i++) out[i] = m->def[i];
+  return m->npar;
+}
+
+relxill_b200_batch *relxill_b200_prepare(const char *model, const double *energy, int n_flux, const double *params,
+                                         long n_vec) {
+  Engine &E = g_eng;
+  std::lock_guard<std::mutex> lk(E.mu);
+  g_err.clear();
+  if (engine_init(E, nullptr, -1)) return nullptr;
+  const ModelDef *m = find_model(model);
+  if (!m) { set_err(std::string("unknown model ") + model); return nullptr; }
+  if (n_vec < 1 || n_flux < 1) { set_err("empty batch or energy grid"); return nullptr; }
+  if (m->prim == PRIM_NTHCOMP) { set_err("nthcomp models are not implemented on the device yet"); return nullptr; }
+  // tables this flavour needs; returning radiation can be switched per vector -> load if the table exists
+  bool want_rr = (m->irrad == EMIS_LP) || E.cfg.env_returnrad == 1;
+  std::string err = E.tables->require(m->irrad == EMIS_LP, false, m->type == T_RELXILL ? m->prim : PRIM_NONE);
+  if (!err.empty()) { set_err(err); return nullptr; }
+  if (want_rr) {
+    err = E.tables->require(false, true, PRIM_NONE);
+    // missing table is only an error for the vectors that switch returning radiation on
+  }
+  auto *b = new relxill_b200_batch();
+  b->m = m;
+  b->n = n_vec;
+  b->n_flux = n_flux;
+  b->vps.resize(n_vec);
+  b->status.assign(n_vec, 0);
+  const std::vector<double> &sp = E.tables->rr_spins();
+  for (long i = 0; i < n_vec; i++) {
+    interpret_params(*m, params + (size_t) i * m->npar, E.cfg, sp.empty() ? nullptr : sp.data(), (int) sp.size(), b->vps[i]);
+    if (b->vps[i].status == ST_OK) {
+      b->nz_max = std::max(b->nz_max, b->vps[i].nz);
+      if (b->vps[i].do_corr) b->any_corr = true;
+    }
+  }
+  if (cudaMalloc((void **) &b->d_vps, n_vec * sizeof(VPar)) != cudaSuccess ||
+      cudaMalloc((void **) &b->d_energy, (n_flux + 1) * sizeof(double)) != cudaSuccess) {
+    set_err("out of device memory (batch)");
+    relxill_b200_free_batch(b);
+    return nullptr;
+  }
+  cudaMemcpy(b->d_vps, b->vps.data(), n_vec * sizeof(VPar), cudaMemcpyHostToDevice);
+  cudaMemcpy(b->d_energy, energy, (n_flux + 1) * sizeof(double), cudaMemcpyHostToDevice);
+  return b;
+}
+
+void relxill_b200_free_batch(relxill_b200_batch *b) {
+  if (!b) return;
+  if (b->d_vps) cudaFree(b->d_vps);
+  if (b->d_energy) cudaFree(b->d_energy);
+  delete b;
+}
+
+int relxill_b200_run(relxill_b200_batch *b, double *d_flux, void *stream) {
+  Engine &E = g_eng;
+  std::lock_guard<std::mutex> lk(E.mu);
+  if (!b || !E.inited) { set_err("run: library not initialised or null batch"); return -1; }
+  return run_batch(E, b, d_flux, (cudaStream_t) stream);
+}
+
+int relxill_b200_batch_status(relxill_b200_batch *b, int *status) {
+  if (!b) return -1;
+  cudaDeviceSynchronize();
+  for (long i = 0; i < b->n; i++) status[i] = b->status[i];
+  return 0;
+}
+
+long relxill_b200_last_launches(relxill_b200_batch *b) { return b ? b->launches : 0; }
+
+int relxill_b200_kernel_times(relxill_b200_batch *b, const char **names, double *ms, long *launches, int max) {
+  if (!b) return 0;
+  int n = 0;
+  for (int k = 0; k < KF_COUNT && n < max; k++) {
+    if (b->kt_n[k] == 0) continue;
+    names[n] = KF_NAMES[k];
+    ms[n] = b->kt_ms[k];
+    launches[n] = b->kt_n[k];
+    n++;
+  }
+  return n;
+}
+
+int relxill_batch_eval_device(const char *model, const double *energy, int n_flux, const double *params, long n_vec,
+                              double *d_flux, int *status, void *stream) {
+  relxill_b200_batch *b = relxill_b200_prepare(model, energy, n_flux, params, n_vec);
+  if (!b) return -1;
+  int rc = relxill_b200_run(b, d_flux, stream);
+  cudaStreamSynchronize((cudaStream_t) stream);
+  if (status) for (long i = 0; i < n_vec; i++) status[i] = b->status[i];
+  relxill_b200_free_batch(b);
+  return rc;
+}
+
+int relxill_batch_eval(const char *model, const double *energy, int n_flux, const double *params, long n_vec,
+                       double *flux, int *status) {
+  relxill_b200_batch *b = relxill_b200_prepare(model, energy, n_flux, params, n_vec);
+  if (!b) {
+    if (flux && n_vec > 0 && n_flux > 0) memset(flux, 0, sizeof(double) * (size_t) n_vec * n_flux);
+    if (status) for (long i = 0; i < n_vec; i++) status[i] = ST_BAD_PARAM;
+    return -1;
+  }
+  Engine &E = g_eng;
+  const size_t need = (size_t) n_vec * n_flux;
+  {
+    std::lock_guard<std::mutex> lk(E.mu);
+    if (E.d_io_cap < need) {
+      if (E.d_io) cudaFree(E.d_io);
+      E.d_io = nullptr;
+      E.d_io_cap = 0;
+      if (cudaMalloc((void **) &E.d_io, need * sizeof(double)) != cudaSuccess) {
+        set_err("out of device memory (output staging)");
+        relxill_b200_free_batch(b);
+        return -2;
+      }
+      E.d_io_cap = need;
+    }
+  }
+  if (b->m->type == T_CONV) {
+    // convolution models: flux is the input spectrum; a non-positive total is rejected (src/LocalModel.cpp:84-86)
+    for (long i = 0; i < n_vec; i++) {
+      double s = 0.0;
+      for (int j = 0; j < n_flux; j++) s += flux[(size_t) i * n_flux + j];
+      if (s <= 0.0 && b->vps[i].status == ST_OK) b->vps[i].status = ST_CONV_INPUT;
+    }
+    cudaMemcpy(b->d_vps, b->vps.data(), n_vec * sizeof(VPar), cudaMemcpyHostToDevice);
+    cudaMemcpy(E.d_io, flux, need * sizeof(double), cudaMemcpyHostToDevice);
+  }
+  int rc = relxill_b200_run(b, E.d_io, nullptr);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpy(flux, E.d_io, need * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_err(std::string("D2H copy: ") + cudaGetErrorString(e)); rc = -2; }
+  }
+  if (status) for (long i = 0; i < n_vec; i++) status[i] = b->status[i];
+  relxill_b200_free_batch(b);
+  return rc;
+}
+
+int relxill_b200_algorithmic_bytes(relxill_b200_batch *b, double *out4) {
+  Engine &E = g_eng;
+  if (!b || !E.inited) return -1;
+  cudaDeviceSynchronize();
+  const ModelDef &m = *b->m;
+  const long nc = b->last_chunk_n;
+  double sumU = 0, bound = 0;
+  double xbytes = 0;
+  if (m.type == T_RELXILL && nc > 0) {
+    const XillHost &xh = E.tables->xill_host(m.prim);
+    const int ncorn = (xh.npar == 6) ? 32 : 16;
+    std::vector<int> rows((size_t) nc * NZMAX * 32);
+    cudaMemcpy(rows.data(), E.S.xrow, rows.size() * sizeof(int), cudaMemcpyDeviceToHost);
+    const double row_bytes = (double) xh.n_incl * xh.n_ener * 4.0;
+    for (long i = 0; i < nc; i++) {
+      const VPar &vp = b->vps[b->last_chunk0 + i];
+      if (b->status[b->last_chunk0 + i] != ST_OK) continue;
+      std::set<int> u;
+      for (int z = 0; z < vp.nz; z++)
+        for (int c = 0; c < ncorn; c++) u.insert(rows[((size_t) i * NZMAX + z) * 32 + c]);
+      sumU += (double) u.size();
+      bound += (double) vp.nz * ncorn * row_bytes;
+    }
+    const double scale = (double) b->n / (double) nc;  // chunks beyond the last are assumed alike
+    sumU *= scale;
+    bound *= scale;
+    xbytes = sumU * row_bytes;
+  }
+  // rel table 4 corners + lp + rrad + params in + spectrum out (+ shared grid once)
+  double per_vec = 4.0 * (3 * 100 + 4 * 100 * 40) * 4.0 + m.npar * 8.0 + b->n_flux * 8.0;
+  if (m.irrad == EMIS_LP) per_vec += 2 * 2 * 3 * 100 * 4.0;
+  double rr = 0;
+  for (long i = 0; i < b->n; i++)
+    if (b->vps[i].status == ST_OK && b->vps[i].return_rad != 0) rr += (3 * 50 * 50 + 50 * 50 * 20) * 8.0;
+  out4[0] = xbytes + per_vec * (double) b->n + rr + (b->n_flux + 1) * 8.0;
+  out4[1] = sumU;
+  out4[2] = xbytes;
+  out4[3] = bound;
+  return 0;
+}
+
+int relxill_b200_probe(relxill_b200_batch *b, long iv, const char *what, double *out, long max_len) {
+  Engine &E = g_eng;
+  if (!b || !E.inited) return -1;
+  cudaDeviceSynchronize();
+  if (iv < b->last_chunk0 || iv >= b->last_chunk0 + b->last_chunk_n) { set_err("probe: vector not in the last chunk"); return -1; }
+  const size_t v = (size_t) (iv - b->last_chunk0);
+  const Scratch &S = E.S;
+  const VPar &vp = b->vps[iv];
+  const std::string w = what;
+  const double *src = nullptr;
+  size_t n = 0;
+  std::vector<double> tmp;
+  if (w == "re") { src = S.re + v * NR; n = NR; }
+  else if (w == "gmin") { src = S.gmin + v * NR; n = NR; }
+  else if (w == "gmax") { src = S.gmax + v * NR; n = NR; }
+  else if (w == "emis") { src = S.emis + v * NR; n = NR; }
+  else if (w == "del_emit") { src = S.del_emit + v * NR; n = NR; }
+  else if (w == "del_inc") { src = S.del_inc + v * NR; n = NR; }
+  else if (w == "trff") { src = S.trff + v * NR * NG * 2; n = (size_t) NR * NG * 2; }
+  else if (w == "cosne") { src = S.cosne + v * NR * NG * 2; n = (size_t) NR * NG * 2; }
+  else if (w == "reflfrac") { src = S.reflfrac + v * 8; n = 5; }
+  else if (w == "lxi") { src = S.zlxi + v * NZMAX; n = vp.nz; }
+  else if (w == "dens") { src = S.zdens + v * NZMAX; n = vp.nz; }
+  else if (w == "ect") { src = S.zect + v * NZMAX; n = vp.nz; }
+  else if (w == "eshift") { src = S.eshift + v * NZMAX; n = vp.nz; }
+  else if (w == "normch") { src = S.normch + v * NZMAX; n = vp.nz; }
+  else if (w == "corr_flux") { src = S.corr_flux + v * NZMAX; n = vp.nz; }
+  else if (w == "corr_gshift") { src = S.corr_gshift + v * NZMAX; n = vp.nz; }
+  else if (w == "total") { src = E.d_total + v * NCONV; n = NCONV; }
+  else if (w == "zone") {
+    n = vp.nz + 1;
+    if ((long) n > max_len) return -1;
+    for (size_t i = 0; i < n; i++) out[i] = vp.zone[i];
+    return (int) n;
+  } else if (w == "relflux" || w == "xill" || w == "dist") {
+    const int nz = vp.nz;
+    const size_t len = (w == "relflux") ? (size_t) ((b->m->type == T_LINE) ? b->n_flux : NCONV)
+                       : (w == "xill")  ? (size_t) E.tables->xill_host(b->m->prim).n_ener
+                                        : (size_t) E.tables->xill_host(b->m->prim).n_incl;
+    if ((long) (len * nz) > max_len) return -1;
+    for (int z = 0; z < nz; z++) {
+      const double *p = (w == "relflux") ? S.relflux + (v * S.nz_cap + z) * S.ne_line_cap
+                        : (w == "xill")  ? S.xillz + (v * S.nz_cap + z) * S.nex_stride
+                                         : S.dist + (v * NZMAX + z) * MAX_INCL;
+      cudaMemcpy(out + z * len, p, len * sizeof(double), cudaMemcpyDeviceToHost);
+    }
+    return (int) (len * nz);
+  } else {
+    set_err("probe: unknown quantity " + w);
+    return -1;
+  }
+  if ((long) n > max_len) return -1;
+  cudaMemcpy(out, src, n * sizeof(double), cudaMemcpyDeviceToHost);
+  return (int) n;
+}
+
+// ---------------------------------------------------------------- XSPEC local-model entry points
+static void lmod_call(const char *name, const double *energy, int Nflux, const double *parameter, double *flux) {
+  static bool warned = false;
+  int st = 0;
+  const int rc = relxill_batch_eval(name, energy, Nflux, parameter, 1, flux, &st);
+  if (rc != 0 || st != 0) {
+    for (int i = 0; i < Nflux; i++) flux[i] = 0.0;
+    if (!warned) {
+      fprintf(stderr, " *** relxill_b200: evaluation of %s failed (rc=%d, status=%d); returning zeros\n", name, rc, st);
+      warned = true;
+    }
+  }
+}
+
+#define DEF_LMOD(sym, name)                                                                              \
+  void sym(const double *energy, int Nflux, const double *parameter, int spectrum, double *flux,        \
+           double *fluxError, const char *init) {                                                        \
+    (void) spectrum; (void) fluxError; (void) init;                                                      \
+    lmod_call(name, energy, Nflux, parameter, flux);                                                     \
+  }
+
+DEF_LMOD(lmodrelline, "relline")
+DEF_LMOD(lmodrelconv, "relconv")
+DEF_LMOD(lmodrellinelp, "relline_lp")
+DEF_LMOD(lmodrelconvlp, "relconv_lp")
+DEF_LMOD(lmodrelxill, "relxill")
+DEF_LMOD(lmodrelxilllp, "relxilllp")
+DEF_LMOD(lmodrelxilldensnthcomp, "relxillCp")
+DEF_LMOD(lmodrelxilllpdensnthcomp, "relxilllpCp")
+
+}  // extern "C"

@@ -1,0 +1,121 @@
+// common.h — data layout shared by the host runtime and the sm_100a kernels.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace rx {
+
+// sizes fixed by the table formats / the reference (src/common.h:69-81,127-136; src/Xillspec.h:28-38)
+constexpr int NR = 1000;       // fine radial grid
+constexpr int NG = 40;         // g* grid
+constexpr int NCONV = 4096;    // convolution grid bins
+constexpr int NCOARSE = 500;   // xillver-normalisation grid bins
+constexpr int NZMAX = 50;      // radial zones
+constexpr int REL_NA = 25, REL_NMU = 30, REL_NRT = 100;
+constexpr int LP_NA = 20, LP_NH = 250, LP_NRT = 100;
+constexpr int RR_NR = 50, RR_NG = 20;
+constexpr int MAX_INCL = 16;
+constexpr int NTH_MAX = 900;   // nthcomp photon grid (src/donthcomp.c)
+
+enum { EMIS_BKN = 1, EMIS_LP = 2 };
+enum { PRIM_NONE = 0, PRIM_ECUT = 1, PRIM_NTHCOMP = 2 };
+enum { T_LINE = 0, T_CONV = 1, T_XILL = 2, T_RELXILL = 3 };
+enum { ION_CONST = 0, ION_PL = 1, ION_ALPHA = 2 };
+
+// per-vector status codes (0 = ok)
+enum {
+  ST_OK = 0,
+  ST_BAD_PARAM = 1,      // rejected by the parameter checks (reference: ParamInputException)
+  ST_TABLE_RANGE = 2,    // radial grid outside the rel table
+  ST_RRAD = 3,           // returning-radiation setup failed
+  ST_ZONE = 4,           // degenerate zone grid
+  ST_NAN = 5,            // NaN in the angular distribution
+  ST_CONV_INPUT = 6      // convolution model with non-positive input flux
+};
+
+// One parameter vector after host-side interpretation (reference get_rel_params/get_xill_params/
+// check_parameter_bounds, src/ModelDefinition.cpp:168-385).  Values that feed discrete decisions
+// (zone grid, ISCO) are computed on the host with the host libm so they carry the same bits as
+// the reference's.
+struct VPar {
+  double a, incl, emis1, emis2, rbr, rin, rout, lineE, z, height, gamma, beta;
+  double gam, afe, lxi, ect, dens, refl_frac, iongrad_index;
+  double eshift_obs;            // energy shift source -> observer (1 unless lamp post)
+  double doppler_obs;           // doppler_factor_source_obs (lamp post, beta > 1e-4), else 1
+  double rms;                   // ISCO
+  double relline_norm;          // 0.5 cos(incl) for relxill+BKN, else 1
+  double zone[NZMAX + 1];       // radial zone grid
+  int model_type, emis_type, prim_type, type;
+  int limb, nz, return_rad, ion_grad_type, boost;
+  int renorm;                   // do_renorm_model
+  int do_corr;                  // returning-radiation correction factors are computed
+  int rr_spin;                  // index into the returning-radiation table (spin >= a), -1 = none
+  int status;
+  int pad_;
+};
+
+struct XillDev {
+  int npar;               // 5 or 6
+  int nvals[6];
+  int pindex[6];          // global parameter id of each table axis (0 gam,1 afe,2 lxi,3 ect/kte,4 dens,7 incl)
+  const float *vals[6];   // device pointers to axis values
+  int n_ener, n_incl, stride;  // stride = padded row length in floats
+  long nnodes;            // rows / n_incl
+  const float *data;      // [nnodes][n_incl][stride], renormalised like the reference does at load
+  const double *ener;     // [n_ener+1] bin edges (float table values promoted)
+  const float *incl;      // [n_incl] degrees
+  // per-node scalars for the returning-radiation correction factors (linear functionals of the spectra)
+  const double *node_ef, *node_p1, *node_p2;
+  // fixed rebin map xillver grid -> convolution grid (same imin/imax/weights as _rebin_spectrum)
+  const int *rb_imin, *rb_imax;   // [NCONV], imin = -1: output bin outside the source grid
+  const double *rb_dmin, *rb_dmax;
+};
+
+struct DevTables {
+  // relline table (src/reltable.h:24-48); r/gmin/gmax [na][nmu][100], tc [na][nmu][100][40] float4
+  const float *rel_a, *rel_mu0, *rel_r, *rel_gmin, *rel_gmax;
+  const float *rel_tc;  // float4 {trff1, trff2, cosne1, cosne2}
+  // lamp-post table (src/reltable.h:51-69)
+  const float *lp_a, *lp_h, *lp_rad, *lp_int, *lp_del, *lp_dinc;
+  // returning radiation (src/Relreturn_Table.h:23-84) + ln of the g grid (precomputed)
+  int rr_nspin;
+  const double *rr_spin, *rr_rlo, *rr_rhi, *rr_tf, *rr_gmin, *rr_gmax, *rr_fg, *rr_lng;
+  // xillver tables, index 0 = cutoff power law, 1 = nthcomp
+  XillDev xill[2];
+  // fixed grids
+  const double *econv;      // [NCONV+1]
+  const double *conv_cf;    // [NCONV] E_mid / dE
+  const unsigned char *conv_band;  // [NCONV] 1 if 0.01 <= E_lo and E_hi < 1000
+  int conv_i1kev;
+  const double *ecoarse;    // [NCOARSE+1]
+  const unsigned char *coarse_m1, *coarse_m2;  // masks of the two band conditions on the coarse grid
+  const double *gstar, *d_gstar;  // [NG]
+  const double *tw_re, *tw_im;    // FFT twiddles exp(-2 pi i k / NCONV), k < NCONV/2
+  // nthcomp: arrays that depend only on the photon grid (kT_bb is fixed at 0.05 keV)
+  const double *nth_x, *nth_c2, *nth_rel, *nth_x3, *nth_w, *nth_dphdot;
+  int nth_jnr, nth_jrel, nth_jmaxth;
+  double nth_xmin, nth_deltal;
+};
+
+// per-chunk device scratch (struct of arrays, vector-major)
+struct Scratch {
+  long cap;          // vectors
+  int nz_cap;        // zones per vector allocated
+  int ne_line_cap;   // bins of the line-profile grid allocated
+  int nex_stride;    // xillver row stride
+  double *re, *gmin, *gmax, *emis, *del_emit, *del_inc, *fr;  // [cap][NR]
+  int *it, *izone;                                            // [cap][NR]
+  double *glim;                                               // [cap][2] min gmin / max gmax over radii
+  double *reflfrac;                                           // [cap][8]
+  double *trff, *cosne;                                       // [cap][NR][NG][2]
+  double *eshift, *zlxi, *zdens, *zect, *normch, *corr_flux, *corr_gshift;  // [cap][NZMAX]
+  double *nsrc;                                               // [cap] source normalisation factor
+  int *xrow;                                                  // [cap][NZMAX][32] node index of each corner
+  double *xw;                                                 // [cap][NZMAX][32] corner weights
+  double *relflux;                                            // [cap][nz_cap][ne_line_cap]
+  double *dist;                                               // [cap][NZMAX][MAX_INCL]
+  double *xillz;                                              // [cap][nz_cap][nex_stride]
+  int *status;                                                // [cap]
+};
+
+}  // namespace rx

@@ -1,0 +1,1304 @@
+// kernels.cu — hand-written sm_100a kernels of the relxill spectrum-evaluation hot path.
+//
+// One batch chunk = C parameter vectors.  Kernel sequence (see DESIGN.md for the data flow):
+//   k_syspar   1 CTA / vector : (a,mu0) table interpolation of the 100 table radii, fine radial grid,
+//                               emissivity (broken power law | lamp post [+ returning radiation])
+//   k_zone     1 CTA / vector : per-zone ionisation / density / Ecut, xillver corner indices+weights,
+//                               primary-spectrum normalisations, returning-radiation correction factors
+//   k_fine     (vector, 8 radii): transfer function + emission-angle tables on the fine radial grid
+//   k_dist     1 CTA / vector : emission-angle distribution per zone
+//   k_line     (vector, 256 energy bins): relline profile, bin-stationary: every thread owns one energy
+//                               bin and walks the 1000 radii -> no atomics, reference summation order
+//   k_xill     (vector, zone) : 16/32-corner xillver gather-blend, angle-weighted
+//   k_conv     1 CTA / vector : rebin, shared-memory FFT convolution per zone, primary spectrum,
+//                               rebin to the output grid
+// Reference code each kernel replaces is cited at the kernel.  FP64 throughout where the reference
+// uses double; float where it uses float (interpolation factors).  No tensor cores: no stage is a
+// dense contraction.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <cstdio>
+
+#include "common.h"
+#include "kernels.h"
+
+namespace rx {
+
+#define PI 3.14159265358979323846
+#define GFAC_H 5e-3
+
+// ---------------------------------------------------------------------------------- device helpers
+__device__ __forceinline__ double lin1d(double f, double lo, double hi) { return f * hi + (1.0 - f) * lo; }
+
+__device__ __forceinline__ double lin2d_f(double f1, double f2, float r11, float r12, float r21, float r22) {
+  return (1.0 - f1) * (1.0 - f2) * r11 + (f1) * (1.0 - f2) * r12 + (1.0 - f1) * (f2) * r21 + (f1) * (f2) * r22;
+}
+
+// arr ascending: k with arr[k] <= val < arr[k+1], clamped to [0, n-2]  (src/relutility.c:135-171)
+template <class T> __device__ __forceinline__ int bsearch_asc(const T *arr, int n, T val) {
+  int klo = 0, khi = n - 1;
+  while (khi - klo > 1) {
+    const int k = (khi + klo) >> 1;
+    if (arr[k] > val) khi = k; else klo = k;
+  }
+  return klo;
+}
+// arr descending (src/relutility.c:195-211)
+__device__ __forceinline__ int bsearch_desc(const double *arr, int n, double val) {
+  int klo = 0, khi = n - 1;
+  while (khi - klo > 1) {
+    const int k = (khi + klo) >> 1;
+    if (arr[k] < val) khi = k; else klo = k;
+  }
+  return klo;
+}
+// number of entries of ascending arr[0..n) that are <= val
+__device__ __forceinline__ int count_le_asc(const double *arr, int n, double val) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int m = (lo + hi) >> 1;
+    if (arr[m] <= val) lo = m + 1; else hi = m;
+  }
+  return lo;
+}
+// number of entries of descending arr[0..n) that are > val
+__device__ __forceinline__ int count_gt_desc(const double *arr, int n, double val) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int m = (lo + hi) >> 1;
+    if (arr[m] > val) lo = m + 1; else hi = m;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ double trapez_single(const double *re, int i, int nr) {  // src/relutility.c:233-244
+  double dr;
+  if (i == 0) dr = 0.5 * (re[i] - re[i + 1]);
+  else if (i == nr - 1) dr = 0.5 * (re[i - 1] - re[i]);
+  else dr = 0.5 * (re[i - 1] - re[i + 1]);
+  return re[i] * dr * PI;
+}
+
+__device__ __forceinline__ double doppler_factor(double del, double bet) {  // src/Relphysics.cpp:158-160
+  return sqrt(1.0 - bet * bet) / (1.0 + bet * cos(del));
+}
+__device__ __forceinline__ double relat_abberation(double del, double beta) {  // src/Relphysics.cpp:127-129
+  return acos((cos(del) - beta) / (1 - beta * cos(del)));
+}
+__device__ double gi_potential_lp(double r, double a, double h, double bet, double del) {  // src/Relphysics.cpp:163-207
+  const double ut_d = ((r * sqrt(r) + a) / (sqrt(r) * sqrt(r * r - 3 * r + 2 * a * sqrt(r))));
+  const double ut_h = sqrt((h * h + a * a) / (h * h - 2 * h + a * a));
+  const double gi = ut_d / ut_h;
+  if (fabs(bet) < 1e-6) return gi;
+  const double gam = 1.0 / sqrt(1.0 - bet * bet);
+  const double sign = (del > PI / 2) ? -1.0 : 1.0;
+  const double delta_eq = h * h - 2 * h + a * a;
+  const double sd = sin(del);
+  const double hh = (h * h + a * a);
+  const double q2 = (sd * sd) * ((hh * hh) / delta_eq) - a * a;
+  double beta_fac = sqrt(hh * hh - delta_eq * (q2 + a * a));
+  beta_fac = gam * (1.0 + sign * beta_fac / (h * h + a * a) * bet);
+  return gi / beta_fac;
+}
+__device__ __forceinline__ double density_ss73_zone_a(double radius, double rms) {  // src/Relphysics.cpp:123-125
+  const double t = (1 - sqrt(rms / radius));
+  return pow((radius / rms), (3. / 2)) * (1.0 / (t * t));
+}
+
+// fixed-order block reduction (deterministic); all threads must call; result broadcast
+template <int NT> __device__ double block_sum(double v, double *red) {
+  const int t = threadIdx.x;
+  red[t] = v;
+  __syncthreads();
+#pragma unroll
+  for (int s = NT / 2; s > 0; s >>= 1) {
+    if (t < s) red[t] += red[t + s];
+    __syncthreads();
+  }
+  const double r = red[0];
+  __syncthreads();
+  return r;
+}
+
+// ---------------------------------------------------------------------------------- k_syspar
+// Replaces interpol_relTable (src/Relprofile.cpp:141-303, the parts that do not need the g* axis),
+// get_fine_radial_grid (src/relutility.c:666-677), calc_emis_profile (src/Rellp.cpp:518-564) with
+// get_emis_bkn (:421-437), the lamp-post branch (:36-89,:120-285) and the returning-radiation
+// emissivity (src/Relreturn_Corona.cpp:39-171,263-321; src/Relreturn_Table.cpp:396-611).
+struct SysSmem {
+  double rt[REL_NRT], gmin_t[REL_NRT], gmax_t[REL_NRT];
+  double lrad[LP_NRT], let[LP_NRT], ldet[LP_NRT], ldit[LP_NRT];
+  double re[NR], emis[NR], del_emit[NR];
+  double red[256];
+  double rad[RR_NR], rlo[RR_NR], rhi[RR_NR], emis_in[RR_NR], emis_ret[RR_NR], cflux[RR_NR], cgsh[RR_NR];
+  double prod[RR_NR * RR_NR];
+  double scal[8];
+  int irad[RR_NR];
+  int ints[8];
+};
+
+__device__ double gshift_fluxboost(double xill_gshift_fac, double g, double lng, double gamma) {  // Relreturn_Corona.cpp:39-83
+  const double g0 = 2. / 3;
+  double corr;
+  if (xill_gshift_fac < 1) {
+    const double a = (xill_gshift_fac / g0 - 1) / (g0 - 1);
+    const double b = 1 - a;
+    corr = (g >= 1) ? 1. / g * (1. / g * a + b) : g * (g * a + b);
+  } else {
+    const double alin = (xill_gshift_fac - 1) / (g0 - 1);
+    const double blin = 1 - alin;
+    corr = (g >= 1) ? (1. / g * alin + blin) : (g * alin + blin);
+  }
+  double fb = exp(gamma * lng) * corr;   // pow(g, gamma) with ln g tabulated at load
+  if (g < 1 && fb > 1) fb = 1;
+  if (fb < 0) fb = 0;
+  return fb;
+}
+
+__global__ void __launch_bounds__(256) k_syspar(const VPar *__restrict__ vps, DevTables T, Scratch S, int pass) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  SysSmem &sm = *reinterpret_cast<SysSmem *>(smraw);
+  const int v = blockIdx.x, t = threadIdx.x;
+  const VPar &vp = vps[v];
+  if (pass == 1) {
+    if (t == 0) S.status[v] = vp.status;
+    if (vp.status != ST_OK) return;
+  } else {
+    if (!vp.do_corr || S.status[v] != ST_OK) return;
+  }
+  const double a = vp.a, rin = vp.rin, rout = vp.rout;
+  double *g_re = S.re + (size_t) v * NR, *g_gmin = S.gmin + (size_t) v * NR, *g_gmax = S.gmax + (size_t) v * NR;
+  double *g_emis = S.emis + (size_t) v * NR, *g_de = S.del_emit + (size_t) v * NR, *g_di = S.del_inc + (size_t) v * NR;
+
+  // ---- (a, mu0) bracket: float arithmetic exactly like src/Relprofile.cpp:171-177
+  const double mu0 = cos(vp.incl);
+  const int ia = bsearch_asc<float>(T.rel_a, REL_NA, (float) a);
+  const int im = bsearch_asc<float>(T.rel_mu0, REL_NMU, (float) mu0);
+  const float ifac_a = ((float) a - T.rel_a[ia]) / (T.rel_a[ia + 1] - T.rel_a[ia]);
+  const float ifac_mu = ((float) mu0 - T.rel_mu0[im]) / (T.rel_mu0[im + 1] - T.rel_mu0[im]);
+  const size_t o00 = ((size_t) ia * REL_NMU + im) * REL_NRT, o10 = ((size_t) (ia + 1) * REL_NMU + im) * REL_NRT;
+  const size_t o01 = o00 + REL_NRT, o11 = o10 + REL_NRT;
+
+  if (t < REL_NRT) {
+    sm.rt[t] = lin1d(ifac_a, T.rel_r[o00 + t], T.rel_r[o10 + t]);
+    sm.gmin_t[t] = lin2d_f(ifac_a, ifac_mu, T.rel_gmin[o00 + t], T.rel_gmin[o10 + t], T.rel_gmin[o01 + t], T.rel_gmin[o11 + t]);
+    sm.gmax_t[t] = lin2d_f(ifac_a, ifac_mu, T.rel_gmax[o00 + t], T.rel_gmax[o10 + t], T.rel_gmax[o01 + t], T.rel_gmax[o11 + t]);
+  }
+  __syncthreads();
+  if (t == 0) {
+    const double rms = vp.rms;
+    double last = sm.rt[REL_NRT - 1];
+    if ((last > rms) && ((last - rms) / last < 1e-3)) sm.rt[REL_NRT - 1] = rms;
+    const int ind_rmin = bsearch_desc(sm.rt, REL_NRT, rin);
+    const int ind_rmax = bsearch_desc(sm.rt, REL_NRT, rout);
+    if (sm.rt[ind_rmax] < 1000.0 && sm.rt[ind_rmax] * 1.01 > 1000.0) sm.rt[ind_rmax] = 1000.0;
+    sm.ints[0] = ind_rmin;
+    sm.ints[1] = 0;  // error flag
+  }
+  __syncthreads();
+  const int ind_rmin = sm.ints[0];
+
+  // ---- fine radial grid + radial bracket in the table
+  const double r1 = 1.0 / sqrt(rout), r2 = 1.0 / sqrt(rin);
+  double lmin = CUDART_INF, lmax = -CUDART_INF;
+  for (int i = t; i < NR; i += 256) {
+    double x = ((double) (i)) * (r2 - r1) / (NR - 1) + r1;
+    x = 1.0 / x;
+    const double re = x * x;
+    sm.re[i] = re;
+    const int K = count_gt_desc(sm.rt, REL_NRT, re) - 1;
+    int it = (K < ind_rmin) ? K : ind_rmin;
+    if (it < 0) {
+      if (re - 1000.0 <= 1e-6) it = 0; else sm.ints[1] = ST_TABLE_RANGE;
+      if (it < 0) it = 0;
+    }
+    const double fr = (re - sm.rt[it + 1]) / (sm.rt[it] - sm.rt[it + 1]);
+    if (fr > 1.0 && it > 0) sm.ints[1] = ST_TABLE_RANGE;
+    const double gmn = lin1d(fr, sm.gmin_t[it + 1], sm.gmin_t[it]);
+    const double gmx = lin1d(fr, sm.gmax_t[it + 1], sm.gmax_t[it]);
+    if (pass == 1) {
+      g_re[i] = re;
+      g_gmin[i] = gmn;
+      g_gmax[i] = gmx;
+      S.fr[(size_t) v * NR + i] = fr;
+      S.it[(size_t) v * NR + i] = it;
+      S.izone[(size_t) v * NR + i] = bsearch_asc<double>(vp.zone, vp.nz + 1, re);
+    }
+    lmin = fmin(lmin, gmn);
+    lmax = fmax(lmax, gmx);
+  }
+  __syncthreads();
+  if (pass == 1) {  // extent of the line in energy (used to skip empty blocks of k_line)
+    sm.red[t] = lmin;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if (t < s) sm.red[t] = fmin(sm.red[t], sm.red[t + s]); __syncthreads(); }
+    if (t == 0) S.glim[2 * v] = sm.red[0];
+    __syncthreads();
+    sm.red[t] = lmax;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if (t < s) sm.red[t] = fmax(sm.red[t], sm.red[t + s]); __syncthreads(); }
+    if (t == 0) S.glim[2 * v + 1] = sm.red[0];
+    __syncthreads();
+  }
+  if (sm.ints[1] != 0) {
+    if (t == 0) S.status[v] = sm.ints[1];
+    return;
+  }
+
+  // ---- emissivity
+  if (vp.emis_type == EMIS_BKN) {
+    double part = 0.0;
+    for (int i = t; i < NR; i += 256) {
+      const double re = sm.re[i];
+      double alpha = vp.emis1;
+      if (re > vp.rbr) alpha = vp.emis2;
+      const double e = pow(re / vp.rbr, -alpha);
+      sm.emis[i] = e;
+      sm.del_emit[i] = -1.0;
+    }
+    __syncthreads();
+    for (int i = t; i < NR; i += 256) part += sm.emis[i] * (trapez_single(sm.re, i, NR) * 2);
+    const double integ = block_sum<256>(part, sm.red);
+    for (int i = t; i < NR; i += 256) {
+      sm.emis[i] = sm.emis[i] / integ;
+      g_di[i] = -1.0;
+    }
+    __syncthreads();
+  } else {
+    // lamp post: (a, h) interpolation on the table's 100 radii, src/Rellp.cpp:190-247
+    const int la = bsearch_asc<float>(T.lp_a, LP_NA, (float) a);
+    const double fa = (double) (((float) a - T.lp_a[la]) / (T.lp_a[la + 1] - T.lp_a[la]));
+    const float hf = (float) vp.height;
+    const float *h0 = T.lp_h + (size_t) la * LP_NH, *h1 = h0 + LP_NH;
+    const int ih0 = bsearch_asc<float>(h0, LP_NH, hf), ih1 = bsearch_asc<float>(h1, LP_NH, hf);
+    const double fh0 = (double) ((hf - h0[ih0]) / (h0[ih0 + 1] - h0[ih0]));
+    const double fh1 = (double) ((hf - h1[ih1]) / (h1[ih1 + 1] - h1[ih1]));
+    if (t < LP_NRT) {
+      const size_t q0 = ((size_t) la * LP_NH + ih0) * LP_NRT + t, q1 = ((size_t) (la + 1) * LP_NH + ih1) * LP_NRT + t;
+      sm.lrad[t] = lin1d(fa, T.lp_rad[(size_t) la * LP_NRT + t], T.lp_rad[(size_t) (la + 1) * LP_NRT + t]);
+      sm.let[t] = (1.0 - fa) * lin1d(fh0, T.lp_int[q0], T.lp_int[q0 + LP_NRT]) + (fa) * lin1d(fh1, T.lp_int[q1], T.lp_int[q1 + LP_NRT]);
+      sm.ldet[t] = (1.0 - fa) * lin1d(fh0, T.lp_del[q0], T.lp_del[q0 + LP_NRT]) + (fa) * lin1d(fh1, T.lp_del[q1], T.lp_del[q1 + LP_NRT]);
+      sm.ldit[t] = (1.0 - fa) * lin1d(fh0, T.lp_dinc[q0], T.lp_dinc[q0 + LP_NRT]) + (fa) * lin1d(fh1, T.lp_dinc[q1], T.lp_dinc[q1 + LP_NRT]);
+    }
+    __syncthreads();
+    // re-grid onto the fine radii, src/Rellp.cpp:120-175
+    const int kk0 = bsearch_asc<double>(sm.lrad, LP_NRT, sm.re[NR - 1]);
+    for (int i = t; i < NR; i += 256) {
+      const double re = sm.re[i];
+      int kk = count_le_asc(sm.lrad, LP_NRT, re) - 1;
+      if (kk < kk0) kk = kk0;
+      if (kk >= LP_NRT - 1) {
+        if (!(re - 1000.0 <= 1e-6)) sm.ints[1] = ST_TABLE_RANGE;
+        kk = LP_NRT - 2;
+      }
+      double f;
+      if (sm.ldet[kk] / PI * 180.0 <= 75.0) f = (re - sm.lrad[kk]) / (sm.lrad[kk + 1] - sm.lrad[kk]);
+      else f = (log(re) - log(sm.lrad[kk])) / (log(sm.lrad[kk + 1]) - log(sm.lrad[kk]));
+      sm.emis[i] = exp(f * log(sm.let[kk + 1]) + (1.0 - f) * log(sm.let[kk]));
+      sm.del_emit[i] = lin1d(f, sm.ldet[kk], sm.ldet[kk + 1]);
+      g_di[i] = lin1d(f, sm.ldit[kk], sm.ldit[kk + 1]);
+    }
+    __syncthreads();
+    if (t == 0 && pass == 1) {  // photon fate fractions, src/Rellp.cpp:36-89
+      double del_ad_max = sm.ldet[LP_NRT - 1];
+      double del_bh = sm.del_emit[bsearch_desc(sm.re, NR, rin)];
+      double del_ad = sm.del_emit[bsearch_desc(sm.re, NR, rout)];
+      if (del_ad_max < PI / 2.0) del_ad_max = PI / 2.0;
+      if (vp.beta > 1e-6) {
+        del_bh = relat_abberation(del_bh, -1. * vp.beta);
+        del_ad = relat_abberation(del_ad, -1. * vp.beta);
+      }
+      const double f_bh = 0.5 * (1.0 - cos(del_bh));
+      const double f_ad = 0.5 * (cos(del_bh) - cos(del_ad));
+      const double f_inf_rest = 0.5 * (1.0 + cos(del_ad_max));
+      double f_inf = f_inf_rest;
+      if (vp.beta > 1e-6) f_inf = 0.5 * (1.0 + cos(relat_abberation(del_ad_max, -1. * vp.beta)));
+      double *rf = S.reflfrac + (size_t) v * 8;
+      rf[0] = f_ad / f_inf; rf[1] = f_bh; rf[2] = f_ad; rf[3] = f_inf; rf[4] = f_inf_rest;
+    }
+    for (int i = t; i < NR; i += 256) {  // flux boost source -> disk, src/Relphysics.cpp:301-311
+      double boost = pow(gi_potential_lp(sm.re[i], a, vp.height, vp.beta, sm.del_emit[i]), vp.gamma);
+      if (vp.beta > 1e-6) {
+        const double d = doppler_factor(sm.del_emit[i], vp.beta);
+        boost *= d * d;
+      }
+      sm.emis[i] *= boost;
+    }
+    __syncthreads();
+  }
+
+  // ---- returning radiation
+  if (vp.return_rad != 0) {
+    const int is = vp.rr_spin;
+    const size_t n2 = (size_t) RR_NR * RR_NR;
+    const double *rlo_t = T.rr_rlo + (size_t) is * RR_NR, *rhi_t = T.rr_rhi + (size_t) is * RR_NR;
+    const bool have_corr = (pass == 2);
+    if (t == 0) {
+      const double rlo_e = sm.re[NR - 1], rhi_e = sm.re[0];
+      int klo = bsearch_asc<double>(rlo_t, RR_NR, rlo_e);
+      int khi = bsearch_asc<double>(rhi_t, RR_NR, rhi_e);
+      if (fabs(rhi_e - rhi_t[RR_NR - 1]) < 1e-6) khi = RR_NR - 1; else khi++;
+      if (fabs(rlo_e - rlo_t[0]) < 1e-6) klo = 0;
+      int nrad = (khi + 1) - klo;
+      int err = 0;
+      if (nrad < 2 || nrad > RR_NR) { err = ST_RRAD; nrad = 2; }
+      for (int i = 0; i < nrad; i++) {
+        sm.irad[i] = klo + i;
+        sm.rlo[i] = rlo_t[klo + i];
+        sm.rhi[i] = rhi_t[klo + i];
+      }
+      sm.rlo[0] = rlo_e;
+      sm.rhi[nrad - 1] = rhi_e;
+      for (int i = 0; i < nrad; i++) { sm.rad[i] = 0.5 * (sm.rlo[i] + sm.rhi[i]); sm.emis_in[i] = 0.0; }
+      for (int s = 0; s < 2; s++) {  // ring-area correction of the two partially covered edge rings
+        const int idx = s == 0 ? 0 : nrad - 1;
+        double rlo_tab = rlo_t[sm.irad[idx]];
+        if (sm.irad[idx] == 0 && rlo_tab > vp.rms) rlo_tab = vp.rms;
+        const double rhi_tab = rhi_t[sm.irad[idx]];
+        const double area_table = 0.5 * (rlo_tab + rhi_tab) * (rhi_tab - rlo_tab);
+        const double area_model = 0.5 * (sm.rlo[idx] + sm.rhi[idx]) * (sm.rhi[idx] - sm.rlo[idx]);
+        sm.scal[s] = area_model / area_table;
+      }
+      // emissivity at the ring centres: inv_rebin_mean (src/relutility.c:636-663), cursor semantics kept
+      if (sm.rad[0] > sm.rad[nrad - 1] || sm.re[nrad - 1] > sm.re[0]) err = ST_RRAD;
+      if (sm.rad[0] < sm.re[NR - 1] || sm.rad[nrad - 1] > sm.re[0]) err = ST_RRAD;
+      if (!err) {
+        int in = nrad - 1;
+        for (int ii = 0; ii < NR - 1; ii++) {
+          if (sm.re[ii] > sm.rad[in] && sm.re[ii + 1] <= sm.rad[in]) {
+            const double f = (sm.rad[in] - sm.re[ii + 1]) / (sm.re[ii] - sm.re[ii + 1]);
+            sm.emis_in[in] = lin1d(f, sm.emis[ii + 1], sm.emis[ii]);
+            in--;
+            if (in < 0) break;
+          }
+        }
+      }
+      if (have_corr) {  // correction factors by zone membership of the ring centre, Relreturn_Corona.cpp:233-247
+        const double *cf = S.corr_flux + (size_t) v * NZMAX, *cg = S.corr_gshift + (size_t) v * NZMAX;
+        for (int i = 0; i < nrad; i++) {
+          int ind = bsearch_asc<double>(vp.zone, vp.nz + 1, sm.rad[i]);
+          if (sm.rad[i] < vp.zone[0]) ind = 0;
+          else if (sm.rad[i] > vp.zone[vp.nz]) ind = vp.nz;  // (one past the end in the reference as well)
+          if (ind >= vp.nz) ind = vp.nz - 1;
+          sm.cflux[i] = cf[ind];
+          sm.cgsh[i] = cg[ind];
+        }
+      }
+      sm.ints[2] = nrad;
+      if (err) sm.ints[1] = err;
+    }
+    __syncthreads();
+    const int nrad = sm.ints[2];
+    const double *tf_t = T.rr_tf + is * n2, *gmin_t = T.rr_gmin + is * n2, *gmax_t = T.rr_gmax + is * n2;
+    const double *fg_t = T.rr_fg + is * n2 * RR_NG, *lng_t = T.rr_lng + is * n2 * RR_NG;
+    for (int pr = t; pr < nrad * nrad; pr += 256) {
+      const int io = pr / nrad, ie = pr - io * nrad;
+      const size_t q = (size_t) sm.irad[io] * RR_NR + sm.irad[ie];
+      const double cg = have_corr ? sm.cgsh[ie] : 1.0;
+      const double gmn = gmin_t[q], gmx = gmax_t[q];
+      double ez = 0.0;
+      for (int jj = 0; jj < RR_NG; jj++) {
+        const double g = ((jj + 0.5) / RR_NG) * (gmx - gmn) + gmn;
+        double e1 = fg_t[q * RR_NG + jj];
+        if (fabs(cg - 1) > 1e-3) e1 *= gshift_fluxboost(cg, g, lng_t[q * RR_NG + jj], vp.gamma) / g;
+        else if (fabs(g - 1) > 1e-3) e1 *= exp((vp.gamma - 1) * lng_t[q * RR_NG + jj]);
+        ez += e1;
+      }
+      double tfr = tf_t[q];
+      if (ie == 0 && io < nrad - 1) tfr *= sm.scal[0];
+      if (ie == nrad - 1 && io < nrad - 2) tfr *= sm.scal[1];
+      sm.prod[io * RR_NR + ie] = ez * tfr * sm.emis_in[ie];
+    }
+    __syncthreads();
+    if (t < nrad) {
+      double sum = 0.0;
+      for (int ie = 0; ie < nrad; ie++) sum += sm.prod[t * RR_NR + ie];
+      if (have_corr) sum *= sm.cflux[t];
+      sm.emis_ret[t] = sum;
+    }
+    __syncthreads();
+    // back onto the fine grid (log interpolation in emissivity, linear in radius), add
+    const int kk0 = bsearch_asc<double>(sm.rad, nrad, sm.re[NR - 1]);
+    for (int i = t; i < NR; i += 256) {
+      const double re = sm.re[i];
+      int kk = count_le_asc(sm.rad, nrad, re) - 1;
+      if (kk < kk0) kk = kk0;
+      if (kk >= nrad - 1) {
+        if (!(re - 1000.0 <= 1e-6)) sm.ints[1] = ST_TABLE_RANGE;
+        kk = nrad - 2;
+      }
+      const double f = (re - sm.rad[kk]) / (sm.rad[kk + 1] - sm.rad[kk]);
+      const double er = exp(f * log(sm.emis_ret[kk + 1]) + (1.0 - f) * log(sm.emis_ret[kk]));
+      if (vp.return_rad == 1) sm.emis[i] += er; else sm.emis[i] = er;
+    }
+    __syncthreads();
+  }
+  for (int i = t; i < NR; i += 256) {
+    g_emis[i] = sm.emis[i];
+    if (pass == 1) g_de[i] = sm.del_emit[i];
+  }
+  if (t == 0 && sm.ints[1] != 0) S.status[v] = sm.ints[1];
+}
+
+// ---------------------------------------------------------------------------------- k_zone
+// Replaces IonGradient::calculate_gradient (src/IonGradient.cpp:128-211,340-390,421-430),
+// get_xilltab_indices_for_paramvals + the interpolation-factor part of interp_xill_table
+// (src/xilltable.c:297-323,1054-1136), calc_xillver_normalization_change_source_to_disk and
+// calc_normalization_factor_source (src/Xillspec.cpp:179-233,408-440; src/PrimarySource.h:279-293) and
+// calc_rrad_corr_factors (src/Relxill.cpp:164-182; src/Xillspec.cpp:344-362,457-526).
+struct ZoneSmem {
+  double re[NR], y1[NR], y2[NR], y3[NR];
+  double powtab[NCOARSE];
+  double rmean[NZMAX], del_emit[NZMAX], irr[NZMAX], dinc[NZMAX], lxi[NZMAX], dens[NZMAX], ect[NZMAX], eshift[NZMAX];
+  double nfac[NZMAX + 1], s2[NZMAX + 1];
+  int b[NZMAX];
+  int ints[4];
+};
+
+// cutoff power law on the coarse grid (src/Xillspec.cpp:215-233) reduced to the two band sums; warp-cooperative
+__device__ void ecut_band_sums(const DevTables &T, const double *powtab, double ecut, double &S1, double &S2) {
+  const int lane = threadIdx.x & 31;
+  double a1 = 0.0, a2 = 0.0;
+  const double ex0 = exp(1.0 / ecut);
+  for (int i = lane; i < NCOARSE; i += 32) {
+    const double e0 = T.ecoarse[i], e1 = T.ecoarse[i + 1];
+    const double en = 0.5 * (e0 + e1);
+    const double fl = ex0 * powtab[i] * exp(-en / ecut) * (e1 - e0);
+    const double w = fl * 0.5 * (e0 + e1);
+    if (T.coarse_m1[i]) a1 += w * 1e20 * 1.602177e-09;
+    if (T.coarse_m2[i]) a2 += w;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  S1 = a1;
+  S2 = a2;
+}
+
+__global__ void __launch_bounds__(128) k_zone(const VPar *__restrict__ vps, DevTables T, Scratch S) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  ZoneSmem &sm = *reinterpret_cast<ZoneSmem *>(smraw);
+  const int v = blockIdx.x, t = threadIdx.x;
+  const VPar &vp = vps[v];
+  if (S.status[v] != ST_OK) return;
+  const int nz = vp.nz;
+  const bool alpha = (vp.ion_grad_type == ION_ALPHA);
+  for (int i = t; i < NR; i += 128) {
+    sm.re[i] = S.re[(size_t) v * NR + i];
+    sm.y1[i] = S.del_emit[(size_t) v * NR + i];
+    if (alpha) {
+      sm.y2[i] = S.emis[(size_t) v * NR + i];
+      sm.y3[i] = S.del_inc[(size_t) v * NR + i];
+    }
+  }
+  if (t == 0) sm.ints[0] = 0;
+  __syncthreads();
+  // brackets of the zone centres in the (descending) fine grid
+  if (t < nz) {
+    const double x = 0.5 * (vp.zone[t] + vp.zone[t + 1]);
+    sm.rmean[t] = x;
+    const int c = count_gt_desc(sm.re, NR, x);
+    sm.b[t] = (c >= 1 && c <= NR - 1) ? c - 1 : -1;
+  }
+  __syncthreads();
+  if (t == 0) {  // inv_rebin_mean's cursor semantics: brackets must be found in strictly increasing order
+    bool ok = true;
+    if (sm.rmean[0] > sm.rmean[nz - 1] || sm.re[nz - 1] > sm.re[0]) ok = false;
+    if (sm.rmean[0] < sm.re[NR - 1] || sm.rmean[nz - 1] > sm.re[0]) ok = false;
+    int prev = -1;
+    for (int in = nz - 1; in >= 0 && ok; in--) {
+      if (sm.b[in] < 0 || sm.b[in] <= prev) ok = false;
+      prev = sm.b[in];
+    }
+    if (!ok) sm.ints[0] = ST_ZONE;
+  }
+  __syncthreads();
+  if (sm.ints[0] != 0) {
+    if (t == 0) S.status[v] = sm.ints[0];
+    return;
+  }
+  if (t < nz) {
+    const int ii = sm.b[t];
+    const double f = (sm.rmean[t] - sm.re[ii + 1]) / (sm.re[ii] - sm.re[ii + 1]);
+    sm.del_emit[t] = lin1d(f, sm.y1[ii + 1], sm.y1[ii]);
+    if (alpha) {
+      sm.irr[t] = lin1d(f, sm.y2[ii + 1], sm.y2[ii]);
+      sm.dinc[t] = lin1d(f, sm.y3[ii + 1], sm.y3[ii]);
+    }
+    sm.eshift[t] = (vp.emis_type == EMIS_LP) ? gi_potential_lp(sm.rmean[t], vp.a, vp.height, vp.beta, sm.del_emit[t]) : 1.0;
+  }
+  __syncthreads();
+  if (t < nz) {
+    double lxi, dens;
+    if (vp.ion_grad_type == ION_PL) {  // src/IonGradient.cpp:174-182 (natural log/exp as written there)
+      lxi = (exp(vp.lxi)) * pow((sm.rmean[t] / sm.rmean[0]), -1.0 * vp.iongrad_index);
+      lxi = log(lxi);
+      dens = vp.dens;
+    } else if (alpha) {  // src/IonGradient.cpp:108-171
+      const double rin = vp.zone[0];
+      const double rad_lxi = ((11. / 9.) * (11. / 9.)) * rin;
+      const int kk = bsearch_desc(sm.re, NR, rad_lxi);
+      const double interp = (rad_lxi - sm.re[kk + 1]) / (sm.re[kk] - sm.re[kk + 1]);
+      const double e_at = lin1d(interp, sm.y2[kk + 1], sm.y2[kk]);
+      const double di_at = lin1d(interp, sm.y3[kk + 1], sm.y3[kk]);
+      const double lxi_max = log10(4.0 * PI * e_at / density_ss73_zone_a(rad_lxi, rin) * (cos(PI / 4) / cos(di_at)));
+      const double fac_lxi_norm = vp.lxi - lxi_max;
+      const double density_min = density_ss73_zone_a((25. / 9.) * rin, rin);
+      const double dn = density_ss73_zone_a(sm.rmean[t], rin) / density_min;
+      dens = log10(dn) + vp.dens;
+      lxi = log10(4.0 * PI * sm.irr[t] / dn * (cos(PI / 4) / cos(sm.dinc[t])));
+      lxi += fac_lxi_norm;
+    } else {
+      lxi = vp.lxi;
+      dens = vp.dens;
+    }
+    if (lxi < 0.0) lxi = 0.0; else if (lxi > 4.7) lxi = 4.7;  // src/IonGradient.cpp:388
+    sm.lxi[t] = lxi;
+    sm.dens[t] = dens;
+    sm.ect[t] = vp.ect * sm.eshift[t];
+    S.eshift[(size_t) v * NZMAX + t] = sm.eshift[t];
+    S.zlxi[(size_t) v * NZMAX + t] = lxi;
+    S.zdens[(size_t) v * NZMAX + t] = dens;
+    S.zect[(size_t) v * NZMAX + t] = sm.ect[t];
+
+    // xillver corner nodes + weights of this zone
+    const XillDev &X = T.xill[vp.prim_type == PRIM_NTHCOMP ? 1 : 0];
+    float inp[8];
+    inp[0] = (float) vp.gam; inp[1] = (float) vp.afe; inp[2] = (float) lxi; inp[3] = (float) sm.ect[t];
+    inp[4] = (float) dens; inp[5] = 0.f; inp[6] = 0.f; inp[7] = 0.f;
+    int ind[6];
+    double fac[6];
+    const int nax = X.npar - 1;  // all axes but the inclination
+    for (int i = 0; i < nax; i++) {
+      const int pind = X.pindex[i];
+      const int n = X.nvals[i];
+      int k = bsearch_asc<float>(X.vals[i], n, inp[pind]);
+      if (k < 0) k = 0; else if (k > n - 2) k = n - 2;
+      ind[i] = k;
+      float val = inp[pind];
+      const float lo = X.vals[i][0], hi = X.vals[i][n - 1];
+      if (val < lo) val = lo; else if (val > hi) val = hi;
+      fac[i] = (double) ((val - X.vals[i][k]) / (X.vals[i][k + 1] - X.vals[i][k]));
+      if (pind == 3) {  // ensure_ecut_within_boundarys
+        if (sm.ect[t] <= (double) lo) fac[i] = 0.0;
+        if (sm.ect[t] >= (double) hi) fac[i] = 1.0;
+      }
+    }
+    const int off = (X.npar == 6) ? 1 : 0;
+    const double f1 = fac[off], f2 = fac[off + 1], f3 = fac[off + 2], f4 = fac[off + 3];
+    int *xr = S.xrow + ((size_t) v * NZMAX + t) * 32;
+    double *xw = S.xw + ((size_t) v * NZMAX + t) * 32;
+    // corner order of interp_5d_tab_incl (src/xilltable.c:836-873)
+    const int bits[16] = {0x0, 0x1, 0x2, 0x4, 0x3, 0x5, 0x6, 0x7, 0x8, 0x9, 0xA, 0xC, 0xB, 0xD, 0xE, 0xF};
+    for (int half = 0; half < (X.npar == 6 ? 2 : 1); half++) {
+      for (int c = 0; c < 16; c++) {
+        const int b1 = bits[c] & 1, b2 = (bits[c] >> 1) & 1, b3 = (bits[c] >> 2) & 1, b4 = (bits[c] >> 3) & 1;
+        double w = (b1 ? f1 : (1.0 - f1)) * (b2 ? f2 : (1.0 - f2)) * (b3 ? f3 : (1.0 - f3)) * (b4 ? f4 : (1 - f4));
+        long node;
+        const int i1 = ind[off] + b1, i2 = ind[off + 1] + b2, i3 = ind[off + 2] + b3, i4 = ind[off + 3] + b4;
+        if (X.npar == 5) node = (((long) i1 * X.nvals[1] + i2) * X.nvals[2] + i3) * X.nvals[3] + i4;
+        else node = ((((long) (ind[0] + half) * X.nvals[1] + i1) * X.nvals[2] + i2) * X.nvals[3] + i3) * X.nvals[4] + i4;
+        if (X.npar == 6) w = half ? fac[0] * w : (1.0 - fac[0]) * w;
+        xr[half * 16 + c] = (int) node;
+        xw[half * 16 + c] = w;
+      }
+    }
+  }
+  __syncthreads();
+  // primary-spectrum normalisations: one warp per (zone | source); cutoff power law only here,
+  // the nthcomp variant lives in k_zone_nthcomp
+  if (vp.prim_type == PRIM_ECUT) {
+    for (int i = t; i < NCOARSE; i += 128) {
+      const double en = 0.5 * (T.ecoarse[i] + T.ecoarse[i + 1]);
+      sm.powtab[i] = pow(en, -vp.gam);
+    }
+    __syncthreads();
+    const int warp = t >> 5, lane = t & 31;
+    for (int job = warp; job <= nz; job += 4) {
+      const double ecut = (job < nz) ? sm.ect[job] : vp.ect;
+      double S1, S2;
+      ecut_band_sums(T, sm.powtab, ecut, S1, S2);
+      if (lane == 0) {
+        const double norm = S1 / (1e15 / 4.0 / PI);
+        sm.nfac[job] = 1. / norm;
+        sm.s2[job] = S2;
+      }
+    }
+    __syncthreads();
+    if (t == 0) S.nsrc[v] = sm.nfac[nz];
+    if (t < nz) {
+      S.normch[(size_t) v * NZMAX + t] = sm.nfac[t] / sm.nfac[nz];
+      if (vp.do_corr) {
+        const XillDev &X = T.xill[0];
+        const int *xr = S.xrow + ((size_t) v * NZMAX + t) * 32;
+        const double *xw = S.xw + ((size_t) v * NZMAX + t) * 32;
+        double ef = 0.0, p1 = 0.0, p2 = 0.0;
+        const int nc = (X.npar == 6) ? 32 : 16;
+        for (int c = 0; c < nc; c++) {
+          ef += xw[c] * X.node_ef[xr[c]];
+          p1 += xw[c] * X.node_p1[xr[c]];
+          p2 += xw[c] * X.node_p2[xr[c]];
+        }
+        const double direct = sm.s2[t] * sm.nfac[t];
+        S.corr_flux[(size_t) v * NZMAX + t] = ef / direct;
+        S.corr_gshift[(size_t) v * NZMAX + t] = (p1 / p2) / pow(1.5, vp.gam);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- k_fine
+// The g*-dependent half of interpol_relTable (src/Relprofile.cpp:39-80,280-293): bilinear (a, mu0) blend of
+// the four table corners at the two bracketing table radii, then the radial lerp, for trff1/2 and cosne1/2.
+__global__ void __launch_bounds__(320) k_fine(const VPar *__restrict__ vps, DevTables T, Scratch S) {
+  const int v = blockIdx.y;
+  if (S.status[v] != ST_OK) return;
+  const VPar &vp = vps[v];
+  const int j = threadIdx.x % NG;
+  const int i = blockIdx.x * 8 + threadIdx.x / NG;
+  const double mu0 = cos(vp.incl);
+  const int ia = bsearch_asc<float>(T.rel_a, REL_NA, (float) vp.a);
+  const int im = bsearch_asc<float>(T.rel_mu0, REL_NMU, (float) mu0);
+  const double fa = (double) (((float) vp.a - T.rel_a[ia]) / (T.rel_a[ia + 1] - T.rel_a[ia]));
+  const double fm = (double) (((float) mu0 - T.rel_mu0[im]) / (T.rel_mu0[im + 1] - T.rel_mu0[im]));
+  const int it = S.it[(size_t) v * NR + i];
+  const double fr = S.fr[(size_t) v * NR + i];
+  const float4 *tc = reinterpret_cast<const float4 *>(T.rel_tc);
+  const size_t o00 = (((size_t) ia * REL_NMU + im) * REL_NRT + it) * NG + j;
+  const size_t o10 = (((size_t) (ia + 1) * REL_NMU + im) * REL_NRT + it) * NG + j;
+  const size_t o01 = (((size_t) ia * REL_NMU + im + 1) * REL_NRT + it) * NG + j;
+  const size_t o11 = (((size_t) (ia + 1) * REL_NMU + im + 1) * REL_NRT + it) * NG + j;
+  const float4 a00 = __ldg(tc + o00), a10 = __ldg(tc + o10), a01 = __ldg(tc + o01), a11 = __ldg(tc + o11);
+  const float4 b00 = __ldg(tc + o00 + NG), b10 = __ldg(tc + o10 + NG), b01 = __ldg(tc + o01 + NG), b11 = __ldg(tc + o11 + NG);
+  // row `it` (larger radius) and row `it+1` (smaller radius)
+  const double t1_hi = lin2d_f(fa, fm, a00.x, a10.x, a01.x, a11.x), t1_lo = lin2d_f(fa, fm, b00.x, b10.x, b01.x, b11.x);
+  const double t2_hi = lin2d_f(fa, fm, a00.y, a10.y, a01.y, a11.y), t2_lo = lin2d_f(fa, fm, b00.y, b10.y, b01.y, b11.y);
+  const double c1_hi = lin2d_f(fa, fm, a00.z, a10.z, a01.z, a11.z), c1_lo = lin2d_f(fa, fm, b00.z, b10.z, b01.z, b11.z);
+  const double c2_hi = lin2d_f(fa, fm, a00.w, a10.w, a01.w, a11.w), c2_lo = lin2d_f(fa, fm, b00.w, b10.w, b01.w, b11.w);
+  double2 tr, co;
+  tr.x = lin1d(fr, t1_lo, t1_hi);
+  tr.y = lin1d(fr, t2_lo, t2_hi);
+  co.x = lin1d(fr, c1_lo, c1_hi);
+  co.y = lin1d(fr, c2_lo, c2_hi);
+  const size_t o = ((size_t) v * NR + i) * NG + j;
+  reinterpret_cast<double2 *>(S.trff)[o] = tr;
+  reinterpret_cast<double2 *>(S.cosne)[o] = co;
+}
+
+// ---------------------------------------------------------------------------------- k_dist
+// Emission-angle distribution per zone: the rel_cosne part of calc_relline_profile
+// (src/Relprofile.cpp:907-938, get_cosne_bin :799-801) and its normalisation (:783-795).
+__global__ void __launch_bounds__(256) k_dist(const VPar *__restrict__ vps, DevTables T, Scratch S, int n_incl,
+                                              double e_first, double e_last) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double *part = reinterpret_cast<double *>(smraw);        // [NR][n_incl]
+  double *re = part + (size_t) NR * n_incl;                // [NR]
+  int *flags = reinterpret_cast<int *>(re + NR);
+  const int v = blockIdx.x, t = threadIdx.x;
+  if (S.status[v] != ST_OK) return;
+  const VPar &vp = vps[v];
+  for (int i = t; i < NR; i += 256) re[i] = S.re[(size_t) v * NR + i];
+  if (t == 0) flags[0] = 0;
+  __syncthreads();
+  for (int i = t; i < NR; i += 256) {
+    double *p = part + (size_t) i * n_incl;
+    for (int m = 0; m < n_incl; m++) p[m] = 0.0;
+    const double gmin = S.gmin[(size_t) v * NR + i], gmax = S.gmax[(size_t) v * NR + i];
+    if (!((gmax > e_first) && (gmin < e_last))) continue;
+    const double emis = S.emis[(size_t) v * NR + i];
+    const double weight = trapez_single(re, i, NR) / 2;
+    const double r = re[i];
+    const double2 *tr = reinterpret_cast<const double2 *>(S.trff) + ((size_t) v * NR + i) * NG;
+    const double2 *co = reinterpret_cast<const double2 *>(S.cosne) + ((size_t) v * NR + i) * NG;
+    for (int jj = 0; jj < NG; jj++) {
+      const double gs = T.gstar[jj];
+      const double g = gs * (gmax - gmin) + gmin;
+      const double2 trv = tr[jj], cov = co[jj];
+      const double x = 2 * PI * g * r;
+      const double base = r * (x * x) / sqrt(gs - gs * gs);
+      for (int kk = 0; kk < 2; kk++) {
+        const double mu = kk ? cov.y : cov.x;
+        const double tf = kk ? trv.y : trv.x;
+        const int imu = ((int) (n_incl * (1 - mu) + 1)) - 1;
+        const double tmp = base * tf * emis * weight * T.d_gstar[jj];
+        if (tmp != tmp) flags[0] = ST_NAN;
+        if (imu < 0 || imu >= n_incl) flags[0] = ST_NAN; else p[imu] += tmp;
+      }
+    }
+  }
+  __syncthreads();
+  if (flags[0] != 0) {
+    if (t == 0) S.status[v] = flags[0];
+    return;
+  }
+  const int *izone = S.izone + (size_t) v * NR;
+  const int nz = vp.nz;
+  for (int job = t; job < nz * n_incl; job += 256) {
+    const int z = job / n_incl, m = job - z * n_incl;
+    double s = 0.0;
+    for (int i = 0; i < NR; i++)
+      if (izone[i] == z) s += part[(size_t) i * n_incl + m];
+    S.dist[((size_t) v * NZMAX + z) * MAX_INCL + m] = s;
+  }
+  __syncthreads();
+  if (t < nz) {
+    double *d = S.dist + ((size_t) v * NZMAX + t) * MAX_INCL;
+    double s = 0.0;
+    for (int m = 0; m < n_incl; m++) s += d[m];
+    if (!(s > 1e-8)) S.status[v] = ST_ZONE;  // the reference asserts here (src/Relprofile.cpp:790)
+    for (int m = 0; m < n_incl; m++) d[m] /= s;
+  }
+}
+
+// ---------------------------------------------------------------------------------- k_line
+// Relline profile: calc_relline_profile + integ_relline_bin + int_edge + int_romb + romberg_integration +
+// relb_func (src/Relprofile.cpp:489-726,835-905) and the division by the bin energy of
+// renorm_relline_profile (:757-762).
+//
+// Bin-stationary mapping: thread = one energy bin, loop over the 1000 radii (descending radius = the
+// reference's loop order), accumulating in a register; a zone change flushes the register to
+// flux[zone][bin].  No atomics, no cross-thread reduction, reference summation order.
+struct LineRad {        // per-radius scalars staged in shared memory
+  double gmin, gmax, del_g, emis, weight;
+  int zone, active;
+};
+constexpr int LINE_TILE = 8;
+
+struct RelbCtx {
+  double gmin, gmax, del_g, emis;
+  const double2 *trff;   // [NG] {branch 0, branch 1}
+  const double2 *cosne;
+  const double *gstar;
+  int limb;
+};
+
+__device__ __forceinline__ double relb_func(double eg, int k, const RelbCtx &c) {  // src/Relprofile.cpp:489-521
+  const double egstar = (eg - c.gmin) * c.del_g;
+  // bracket in the (uniform up to rounding) g* grid: same result as binary_search(gstar, 40, egstar)
+  int ind = (int) ((egstar - GFAC_H) * ((NG - 1) / (1.0 - 2 * GFAC_H)));
+  ind = ind < 0 ? 0 : (ind > NG - 2 ? NG - 2 : ind);
+  while (ind > 0 && c.gstar[ind] > egstar) ind--;
+  while (ind < NG - 2 && c.gstar[ind + 1] <= egstar) ind++;
+  const double inte = (egstar - c.gstar[ind]) / (c.gstar[ind + 1] - c.gstar[ind]);
+  const double inte1 = 1.0 - inte;
+  const double2 t0 = c.trff[ind], t1 = c.trff[ind + 1];
+  const double ftrf = inte * (k ? t0.y : t0.x) + inte1 * (k ? t1.y : t1.x);
+  const double val = (eg * eg * eg) / ((c.gmax - c.gmin) * sqrt(egstar - egstar * egstar)) * ftrf * c.emis;
+  if (c.limb == 0) return val;
+  const double2 c0 = c.cosne[ind], c1 = c.cosne[ind + 1];
+  const double fmu0 = inte * (k ? c0.y : c0.x) + inte1 * (k ? c1.y : c1.x);
+  double limb = 1.0;
+  if (c.limb == 1) limb = (1.0 + 2.06 * fmu0);
+  else if (c.limb == 2) limb = log(1.0 + 1.0 / fmu0);
+  return val * limb;
+}
+
+__device__ double romberg(double a, double b, int k, const RelbCtx &c) {  // src/Relprofile.cpp:524-579
+  const double prec = 0.02;
+  double obtprec = 1.0;
+  double prev[7], cur[7];
+  int niter = 0;
+  const double r0 = relb_func(a, k, c);
+  const double rb = relb_func(b, k, c);
+  const double ta = (r0 + rb) / 2.0;
+  double pas = b - a;
+  prev[0] = ta * pas;
+  double last_diag = prev[0];
+  while ((obtprec > prec) && (niter <= 5)) {
+    niter++;
+    pas = pas / 2.0;
+    double s = ta;
+    const int npts = (1 << niter) - 1;
+    for (int ii = 1; ii <= npts; ii++) s += relb_func(a + pas * ii, k, c);
+    cur[0] = s * pas;
+    double r = 1.0;
+#pragma unroll
+    for (int ii = 1; ii <= 6; ii++) {
+      if (ii <= niter) {
+        r *= 4.0;
+        cur[ii] = (r * cur[ii - 1] - prev[ii - 1]) / (r - 1.0);
+      }
+    }
+    double diag = cur[0];
+#pragma unroll
+    for (int ii = 1; ii <= 6; ii++) if (ii == niter) diag = cur[ii];
+    obtprec = fabs(diag - last_diag) / diag;
+    last_diag = diag;
+#pragma unroll
+    for (int ii = 0; ii < 7; ii++) prev[ii] = cur[ii];
+  }
+  return last_diag;
+}
+
+__device__ __forceinline__ double gstar2ener(double g, double gmin, double gmax) { return (g * (gmax - gmin) + gmin) * 1.0; }
+
+__device__ double int_edge(double blo, double bhi, const RelbCtx &c) {  // src/Relprofile.cpp:585-621 (h = GFAC_H)
+  double hex, lo, hi;
+  if (blo <= 0.5) { hex = GFAC_H; lo = blo; hi = bhi; }
+  else { hex = 1.0 - GFAC_H; lo = 1.0 - bhi; hi = 1.0 - blo; }
+  double norm = 0.0;
+  const double eh = gstar2ener(hex, c.gmin, c.gmax);
+  norm = norm + relb_func(eh, 0, c);
+  norm = norm + relb_func(eh, 1, c);
+  norm = norm * sqrt(GFAC_H);
+  return 2 * norm * (sqrt(hi) - sqrt(lo)) * 1.0 * (c.gmax - c.gmin);
+}
+
+__device__ double integ_relline_bin(const RelbCtx &c, double rlo0, double rhi0) {  // src/Relprofile.cpp:650-726
+  double flu = 0.0;
+  double gblo = (rlo0 / 1.0 - c.gmin) * c.del_g;
+  if (gblo < 0.0) gblo = 0.0; else if (gblo > 1.0) gblo = 1.0;
+  double gbhi = (rhi0 / 1.0 - c.gmin) * c.del_g;
+  if (gbhi < 0.0) gbhi = 0.0; else if (gbhi > 1.0) gbhi = 1.0;
+  if (gbhi == 0) return 0.0;
+  double rlo = rlo0, rhi = rhi0, hlo, hhi;
+  if (gblo <= GFAC_H) {
+    hlo = gblo;
+    hhi = GFAC_H;
+    rlo = gstar2ener(GFAC_H, c.gmin, c.gmax);
+    if (gbhi <= GFAC_H) { hhi = gbhi; rlo = -1.0; }
+    flu = flu + int_edge(hlo, hhi, c);
+  }
+  if (gbhi >= (1.0 - GFAC_H)) {
+    hhi = gbhi;
+    hlo = 1.0 - GFAC_H;
+    rhi = gstar2ener(1 - GFAC_H, c.gmin, c.gmax);
+    if (gblo >= (1.0 - GFAC_H)) { hlo = gblo; rhi = -1.0; }
+    flu = flu + int_edge(hlo, hhi, c);
+  }
+  if ((rhi >= 0) && (rlo >= 0)) {
+    double f2 = 0.0;
+    if (rlo >= 1.0 * 0.95) {  // src/Relprofile.cpp:628-647
+      f2 += romberg(rlo, rhi, 0, c);
+      f2 += romberg(rlo, rhi, 1, c);
+    } else {
+      const double mid = (rhi + rlo) / 2.0;
+      f2 += relb_func(mid, 0, c) * (rhi - rlo);
+      f2 += relb_func(mid, 1, c) * (rhi - rlo);
+    }
+    flu = flu + f2;
+  }
+  return flu;
+}
+
+// grid_mode 0: the fixed convolution grid; 1: the caller's grid shifted by (1+z) and divided by lineE
+// per vector (XspecSpectrum::shift_energy_grid_redshift / _1keV, src/XspecSpectrum.h:61-76)
+__device__ __forceinline__ double line_edge(const double *egrid, int j, int grid_mode, double z, double lineE) {
+  double e = egrid[j];
+  if (grid_mode) {
+    if (z > 0) e *= (1 + z);
+    e /= lineE;
+  }
+  return e;
+}
+
+__global__ void __launch_bounds__(256) k_line(const VPar *__restrict__ vps, DevTables T, Scratch S,
+                                              const double *__restrict__ egrid, int n_ener, int grid_mode,
+                                              int ne_stride, int nz_stride) {
+  __shared__ double2 s_trff[LINE_TILE][NG];
+  __shared__ double2 s_cosne[LINE_TILE][NG];
+  __shared__ LineRad s_rad[LINE_TILE];
+  __shared__ double s_gstar[NG];
+  __shared__ double s_re[NR];
+  const int v = blockIdx.y, t = threadIdx.x;
+  if (S.status[v] != ST_OK) return;
+  const VPar &vp = vps[v];
+  const int j = blockIdx.x * 256 + t;
+  const bool in_grid = j < n_ener;
+  const double e_first = line_edge(egrid, 0, grid_mode, vp.z, vp.lineE);
+  const double e_last = line_edge(egrid, n_ener, grid_mode, vp.z, vp.lineE);
+  const int jlo_b = blockIdx.x * 256, jhi_b = min(jlo_b + 256, n_ener);
+  {  // whole block outside the line?  (flux was zero-filled)
+    const double blo = line_edge(egrid, jlo_b, grid_mode, vp.z, vp.lineE);
+    const double bhi = line_edge(egrid, jhi_b, grid_mode, vp.z, vp.lineE);
+    if (bhi <= S.glim[2 * v] || blo > S.glim[2 * v + 1]) return;
+  }
+  const double elo = in_grid ? line_edge(egrid, j, grid_mode, vp.z, vp.lineE) : 0.0;
+  const double ehi = in_grid ? line_edge(egrid, j + 1, grid_mode, vp.z, vp.lineE) : 0.0;
+  if (t < NG) s_gstar[t] = T.gstar[t];
+  for (int i = t; i < NR; i += 256) s_re[i] = S.re[(size_t) v * NR + i];
+  __syncthreads();
+  const double2 *g_trff = reinterpret_cast<const double2 *>(S.trff) + (size_t) v * NR * NG;
+  const double2 *g_cosne = reinterpret_cast<const double2 *>(S.cosne) + (size_t) v * NR * NG;
+  double *flux = S.relflux + (size_t) v * nz_stride * ne_stride;
+  const double inv_emid = 0.5 * (elo + ehi);
+  double acc = 0.0;
+  int cur_zone = -1;
+  const int limb = vp.limb;
+  for (int i0 = 0; i0 < NR; i0 += LINE_TILE) {
+    __syncthreads();
+    // stage a tile of radii
+    for (int q = t; q < LINE_TILE * NG; q += 256) {
+      const int r = q / NG, g = q - r * NG;
+      s_trff[r][g] = g_trff[(size_t) (i0 + r) * NG + g];
+      if (limb != 0) s_cosne[r][g] = g_cosne[(size_t) (i0 + r) * NG + g];
+    }
+    if (t < LINE_TILE) {
+      const int i = i0 + t;
+      LineRad lr;
+      lr.gmin = S.gmin[(size_t) v * NR + i];
+      lr.gmax = S.gmax[(size_t) v * NR + i];
+      lr.del_g = 1. / (lr.gmax - lr.gmin);
+      lr.emis = S.emis[(size_t) v * NR + i];
+      lr.weight = trapez_single(s_re, i, NR) / 2;
+      lr.zone = S.izone[(size_t) v * NR + i];
+      lr.active = ((lr.gmax > e_first) && (lr.gmin < e_last)) ? 1 : 0;
+      s_rad[t] = lr;
+    }
+    __syncthreads();
+    if (!in_grid) continue;
+#pragma unroll 1
+    for (int r = 0; r < LINE_TILE; r++) {
+      const LineRad lr = s_rad[r];
+      if (!lr.active) continue;
+      double egmin = lr.gmin, egmax = lr.gmax;
+      if (egmin < e_first) egmin = e_first;
+      if (egmax > e_last) egmax = e_last;
+      // bin j is inside [ielo, iehi] of the reference's two binary searches
+      if (!(ehi > egmin) || !(elo <= egmax)) continue;
+      if (lr.zone != cur_zone) {
+        if (cur_zone >= 0) flux[(size_t) cur_zone * ne_stride + j] = acc / inv_emid;
+        acc = 0.0;
+        cur_zone = lr.zone;
+      }
+      RelbCtx c;
+      c.gmin = lr.gmin; c.gmax = lr.gmax; c.del_g = lr.del_g; c.emis = lr.emis;
+      c.trff = s_trff[r]; c.cosne = s_cosne[r]; c.gstar = s_gstar; c.limb = limb;
+      const double tmp = integ_relline_bin(c, elo, ehi);
+      acc += tmp * lr.weight;
+    }
+  }
+  if (in_grid && cur_zone >= 0) flux[(size_t) cur_zone * ne_stride + j] = acc / inv_emid;
+}
+
+// ---------------------------------------------------------------------------------- k_linefinish
+// renorm_relline_profile for one-zone line models (src/Relprofile.cpp:749-781) + copy to the output
+__global__ void __launch_bounds__(256) k_linefinish(const VPar *__restrict__ vps, Scratch S, int n_ener, int ne_stride,
+                                                    int nz_stride, double *__restrict__ out) {
+  __shared__ double red[256];
+  const int v = blockIdx.x, t = threadIdx.x;
+  double *o = out + (size_t) v * n_ener;
+  if (S.status[v] != ST_OK) {
+    for (int j = t; j < n_ener; j += 256) o[j] = 0.0;
+    return;
+  }
+  const VPar &vp = vps[v];
+  const double *flux = S.relflux + (size_t) v * nz_stride * ne_stride;
+  double part = 0.0;
+  for (int j = t; j < n_ener; j += 256) part += flux[j];
+  const double sum = block_sum<256>(part, red);
+  const double scale = vp.renorm ? vp.relline_norm / sum : 1.0;
+  for (int j = t; j < n_ener; j += 256) o[j] = vp.renorm ? flux[j] * scale : flux[j];
+}
+
+// ---------------------------------------------------------------------------------- k_xill
+// interp_5d_tab_incl / interp_6d_tab_incl for every inclination (src/xilltable.c:812-876,999-1019) fused
+// with calc_xillver_angdep (src/Xillspec.cpp:557-573) and the division by the normalisation change
+// (src/Relxill.cpp:380-385): xill[z][e] = sum_m dist[z][m] * sum_c w_c * tab[node_c][m][e] / normch[z].
+// One CTA per (vector, zone); threads stride the energy axis so every corner row is a coalesced stream.
+__global__ void __launch_bounds__(256) k_xill(const VPar *__restrict__ vps, DevTables T, Scratch S, int which,
+                                              int nz_stride) {
+  __shared__ double s_w[32];
+  __shared__ double s_d[MAX_INCL];
+  __shared__ const float *s_row[32];
+  const int v = blockIdx.y, z = blockIdx.x, t = threadIdx.x;
+  if (S.status[v] != ST_OK) return;
+  const VPar &vp = vps[v];
+  if (z >= vp.nz) return;
+  const XillDev &X = T.xill[which];
+  const int nc = (X.npar == 6) ? 32 : 16;
+  const int ni = X.n_incl, st = X.stride, ne = X.n_ener;
+  if (t < nc) {
+    s_w[t] = S.xw[((size_t) v * NZMAX + z) * 32 + t];
+    s_row[t] = X.data + (size_t) S.xrow[((size_t) v * NZMAX + z) * 32 + t] * ni * st;
+  }
+  if (t < ni) s_d[t] = S.dist[((size_t) v * NZMAX + z) * MAX_INCL + t];
+  __syncthreads();
+  const double inv_norm = S.normch[(size_t) v * NZMAX + z];
+  double *out = S.xillz + ((size_t) v * nz_stride + z) * st;
+  for (int e = t; e < ne; e += 256) {
+    double acc = 0.0;
+    for (int m = 0; m < ni; m++) {
+      double f = 0.0;
+      if (nc == 16) {
+#pragma unroll
+        for (int c = 0; c < 16; c++) f += s_w[c] * (double) __ldg(s_row[c] + (size_t) m * st + e);
+      } else {
+        double f1 = 0.0, f2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+          f1 += s_w[c] * (double) __ldg(s_row[c] + (size_t) m * st + e);
+          f2 += s_w[16 + c] * (double) __ldg(s_row[16 + c] + (size_t) m * st + e);
+        }
+        f = f1 + f2;
+      }
+      acc += s_d[m] * f;
+    }
+    out[e] = acc / inv_norm;
+  }
+}
+
+// ---------------------------------------------------------------------------------- k_conv
+// relxill_convolution_multizone (src/Relxill.cpp:432-482) with fftw_conv_spectrum + calcFFTNormFactor
+// (src/Relbase.cpp:119-213), PrimarySource::add_primary_spectrum (src/PrimarySource.cpp:66-125) and
+// rebin_and_normalize_relxill_for_xspec (src/Relxill.cpp:261-278).  One CTA per vector; the 4096-point
+// FFTs run in shared memory (radix-2, the two real inputs packed into one complex transform).
+constexpr int CONV_NT = 512;
+
+__device__ void fft4096(double *xr, double *xi, const double *__restrict__ twr, const double *__restrict__ twi,
+                        double sign) {
+  const int t = threadIdx.x;
+  for (int i = t; i < NCONV; i += CONV_NT) {
+    const int j = (int) (__brev((unsigned) i) >> 20);
+    if (i < j) {
+      double a = xr[i]; xr[i] = xr[j]; xr[j] = a;
+      a = xi[i]; xi[i] = xi[j]; xi[j] = a;
+    }
+  }
+  __syncthreads();
+  for (int lg = 1; lg <= 12; lg++) {
+    const int half = 1 << (lg - 1);
+    const int step = NCONV >> lg;
+    for (int b = t; b < NCONV / 2; b += CONV_NT) {
+      const int k = b & (half - 1);
+      const int i = ((b >> (lg - 1)) << lg) + k;
+      const int j = i + half;
+      const double c = __ldg(twr + k * step), s = sign * __ldg(twi + k * step);
+      const double vr = xr[j] * c - xi[j] * s, vi = xr[j] * s + xi[j] * c;
+      const double ur = xr[i], ui = xi[i];
+      xr[i] = ur + vr; xi[i] = ui + vi;
+      xr[j] = ur - vr; xi[j] = ui - vi;
+    }
+    __syncthreads();
+  }
+}
+
+// _rebin_spectrum (src/relutility.c:549-601) for one output bin, source spectrum in memory `flu0`
+__device__ double rebin_bin(double elo_out, double ehi_out, const double *__restrict__ e0, const double *flu0, int n0) {
+  if (!((e0[0] <= ehi_out) && (e0[n0] >= elo_out))) return 0.0;
+  int imin = count_le_asc(e0, n0 + 1, elo_out) - 1;
+  if (imin < 0) imin = 0;
+  int imax = count_le_asc(e0, n0 + 1, ehi_out);
+  if (imax > n0) imax = n0;
+  imax -= 1;
+  if (imax < 0) imax = 0;
+  double elo = elo_out, ehi = ehi_out;
+  if (elo < e0[imin]) elo = e0[imin];
+  if (ehi > e0[imax + 1]) ehi = e0[imax + 1];
+  if (imax == imin) return (ehi - elo) / (e0[imin + 1] - e0[imin]) * flu0[imin];
+  const double dmin = (e0[imin + 1] - elo) / (e0[imin + 1] - e0[imin]);
+  const double dmax = (ehi - e0[imax]) / (e0[imax + 1] - e0[imax]);
+  double f = 0.0;
+  f += flu0[imin] * dmin + flu0[imax] * dmax;
+  for (int jj = imin + 1; jj <= imax - 1; jj++) f += flu0[jj];
+  return f;
+}
+
+struct ConvArgs {
+  const double *user_e;   // [n_flux+1] device
+  int n_flux;
+  double *out;            // [C][n_flux] device
+  double *total;          // [C][NCONV] device (probe; may be null)
+  int which;              // xillver table index
+  int nz_stride, ne_stride;
+  int mode;               // 0 relxill, 1 convolution model (input spectrum in `out`)
+};
+
+__global__ void __launch_bounds__(CONV_NT) k_conv(const VPar *__restrict__ vps, DevTables T, Scratch S, ConvArgs A) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double *xr = reinterpret_cast<double *>(smraw);
+  double *xi = xr + NCONV;
+  double *acc = xi + NCONV;
+  double *fx = acc + NCONV;    // rebinned xillver spectrum of the zone (needed again for the norm)
+  double *red = fx + NCONV;    // [CONV_NT]
+  const int v = blockIdx.x, t = threadIdx.x;
+  double *o = A.out + (size_t) v * A.n_flux;
+  const VPar &vp = vps[v];
+  if (S.status[v] != ST_OK) {
+    for (int j = t; j < A.n_flux; j += CONV_NT) o[j] = 0.0;
+    return;
+  }
+  const int nz = (A.mode == 0) ? vp.nz : 1;
+  const XillDev &X = T.xill[A.which];
+  const int i1 = T.conv_i1kev;
+  for (int i = t; i < NCONV; i += CONV_NT) acc[i] = 0.0;
+  for (int z = 0; z < nz; z++) {
+    const double *rel = S.relflux + ((size_t) v * A.nz_stride + z) * A.ne_stride;
+    double part = 0.0;
+    for (int i = t; i < NCONV; i += CONV_NT) part += rel[i];
+    const double srel_all = block_sum<CONV_NT>(part, red);
+    double rscale = 1.0;
+    if (vp.renorm) rscale = vp.relline_norm / srel_all;   // renorm_relline_profile (single-zone models)
+    {
+      double chk = vp.renorm ? srel_all * rscale : srel_all;
+      if (chk < 1e-12) continue;                          // src/Relxill.cpp:455-457
+    }
+    // rebin the zone's spectrum onto the convolution grid; pack x + i y
+    double p_x = 0.0, p_r = 0.0;
+    if (A.mode == 0) {
+      const double *xz = S.xillz + ((size_t) v * A.nz_stride + z) * X.stride;
+      for (int i = t; i < NCONV; i += CONV_NT) {
+        const int imin = X.rb_imin[i];
+        double f = 0.0;
+        if (imin >= 0) {
+          const int imax = X.rb_imax[i];
+          if (imax == imin) f = X.rb_dmin[i] * xz[imin];
+          else {
+            f += xz[imin] * X.rb_dmin[i] + xz[imax] * X.rb_dmax[i];
+            for (int jj = imin + 1; jj <= imax - 1; jj++) f += xz[jj];
+          }
+        }
+        fx[i] = f;
+      }
+    } else {
+      for (int i = t; i < NCONV; i += CONV_NT) {
+        double elo = T.econv[i], ehi = T.econv[i + 1];
+        fx[i] = rebin_bin(elo, ehi, A.user_e, o, A.n_flux);   // user grid already shifted by the host for mode 1
+      }
+    }
+    __syncthreads();
+    // The two real inputs share one complex transform; bring them to the same scale first so that the
+    // split does not lose the smaller one to rounding.  Any positive factor cancels in the normalisation
+    // (norm = s_rel * s_xill / s_conv is computed from the scaled output).
+    double p_ax = 0.0;
+    for (int i = t; i < NCONV; i += CONV_NT) p_ax += fabs(fx[i]);
+    const double s_ax = block_sum<CONV_NT>(p_ax, red);
+    const double bal = (s_ax > 0.0 && srel_all > 0.0) ? s_ax / (vp.renorm ? srel_all * rscale : srel_all) : 1.0;
+    for (int i = t; i < NCONV; i += CONV_NT) {
+      const double cf = T.conv_cf[i];
+      const double r = vp.renorm ? rel[i] * rscale : rel[i];
+      xr[i] = fx[i] * cf;
+      xi[(i - i1 + NCONV) % NCONV] = (r * cf) * bal;
+      if (T.conv_band[i]) { p_x += fx[i]; p_r += r; }
+    }
+    const double s_xill = block_sum<CONV_NT>(p_x, red);
+    const double s_rel = block_sum<CONV_NT>(p_r, red);
+    fft4096(xr, xi, T.tw_re, T.tw_im, 1.0);
+    // split into the two real transforms, multiply, rebuild the Hermitian product
+    for (int k = t; k <= NCONV / 2; k += CONV_NT) {
+      const int nk = (NCONV - k) & (NCONV - 1);
+      const double a = xr[k], b = xi[k], c = xr[nk], d = xi[nk];
+      const double Xr = 0.5 * (a + c), Xi = 0.5 * (b - d);
+      const double Yr = 0.5 * (b + d), Yi = 0.5 * (c - a);
+      const double Pr = Xr * Yr - Xi * Yi, Pi = Xr * Yi + Xi * Yr;
+      xr[k] = Pr; xi[k] = Pi;
+      xr[nk] = Pr; xi[nk] = -Pi;
+    }
+    __syncthreads();
+    if (t == 0) { xi[0] = 0.0; xi[NCONV / 2] = 0.0; }
+    __syncthreads();
+    fft4096(xr, xi, T.tw_re, T.tw_im, -1.0);
+    double p_c = 0.0;
+    for (int i = t; i < NCONV; i += CONV_NT) {
+      const double fo = xr[i] / T.conv_cf[i];
+      xr[i] = fo;
+      if (T.conv_band[i]) p_c += fo;
+    }
+    const double s_conv = block_sum<CONV_NT>(p_c, red);
+    const double norm = s_rel * s_xill / s_conv;
+    for (int i = t; i < NCONV; i += CONV_NT) acc[i] += xr[i] * norm;
+    __syncthreads();
+  }
+  if (A.mode == 0) {
+    // primary spectrum on the convolution grid (cutoff power law here; nthcomp is added by k_prim_nthcomp)
+    double refl_scale, prim_scale;
+    if (vp.emis_type != EMIS_LP) {
+      refl_scale = fabs(vp.refl_frac);
+      prim_scale = 1.0;
+    } else {
+      const double *rf = S.reflfrac + (size_t) v * 8;
+      double rfi = vp.refl_frac;
+      if (vp.boost) rfi *= rf[0];
+      prim_scale = rf[4] / 0.5 * pow(vp.eshift_obs, vp.gam);
+      if (vp.beta > 1e-4) prim_scale *= vp.doppler_obs * vp.doppler_obs;
+      refl_scale = (fabs(rfi)) / rf[0];
+    }
+    const double nsrc = S.nsrc[v];
+    const bool add_prim = (vp.refl_frac >= 0);
+    if (vp.prim_type == PRIM_ECUT) {
+      const double ecut = vp.ect * vp.eshift_obs;
+      const double ex0 = exp(1.0 / ecut);
+      for (int i = t; i < NCONV; i += CONV_NT) {
+        const double e0 = T.econv[i], e1 = T.econv[i + 1];
+        const double en = 0.5 * (e0 + e1);
+        double pr = ex0 * pow(en, -vp.gam) * exp(-en / ecut) * (e1 - e0);
+        pr *= nsrc;
+        if (vp.emis_type == EMIS_LP) pr *= prim_scale;
+        double tot = acc[i] * refl_scale;
+        if (add_prim) tot += pr;
+        acc[i] = tot;
+      }
+    } else {
+      for (int i = t; i < NCONV; i += CONV_NT) acc[i] = acc[i] * refl_scale;  // primary added afterwards
+    }
+    __syncthreads();
+    if (A.total) for (int i = t; i < NCONV; i += CONV_NT) A.total[(size_t) v * NCONV + i] = acc[i];
+  }
+  __syncthreads();
+  // rebin to the caller's grid (shifted by 1+z), src/Relxill.cpp:261-278
+  for (int j = t; j < A.n_flux; j += CONV_NT) {
+    double elo = A.user_e[j], ehi = A.user_e[j + 1];
+    if (A.mode == 0 && vp.z > 0) { elo *= (1 + vp.z); ehi *= (1 + vp.z); }
+    double f = rebin_bin(elo, ehi, T.econv, acc, NCONV);
+    if (A.mode == 1 && (ehi < 0.01 || elo > 1000.0)) f = 0;   // src/Relbase.cpp:233-246
+    o[j] = f;
+  }
+}
+
+// ---------------------------------------------------------------------------------- launchers
+static size_t g_smem_sys = 0, g_smem_zone = 0;
+
+int kernels_init() {
+  g_smem_sys = sizeof(SysSmem);
+  g_smem_zone = sizeof(ZoneSmem);
+  cudaError_t e;
+  e = cudaFuncSetAttribute(k_syspar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) g_smem_sys);
+  if (e != cudaSuccess) return 1;
+  e = cudaFuncSetAttribute(k_zone, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) g_smem_zone);
+  if (e != cudaSuccess) return 1;
+  e = cudaFuncSetAttribute(k_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ((NR * MAX_INCL + NR + 4) * sizeof(double)));
+  if (e != cudaSuccess) return 1;
+  e = cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ((4 * NCONV + CONV_NT) * sizeof(double)));
+  if (e != cudaSuccess) return 1;
+  return 0;
+}
+
+void launch_syspar(const VPar *vps, const DevTables &T, const Scratch &S, long n, int pass, cudaStream_t st) {
+  k_syspar<<<(unsigned) n, 256, g_smem_sys, st>>>(vps, T, S, pass);
+}
+void launch_zone(const VPar *vps, const DevTables &T, const Scratch &S, long n, cudaStream_t st) {
+  k_zone<<<(unsigned) n, 128, g_smem_zone, st>>>(vps, T, S);
+}
+void launch_fine(const VPar *vps, const DevTables &T, const Scratch &S, long n, cudaStream_t st) {
+  dim3 grid(NR / 8, (unsigned) n);
+  k_fine<<<grid, 320, 0, st>>>(vps, T, S);
+}
+void launch_dist(const VPar *vps, const DevTables &T, const Scratch &S, long n, int n_incl, double e_first,
+                 double e_last, cudaStream_t st) {
+  const size_t sm = ((size_t) NR * n_incl + NR + 4) * sizeof(double);
+  k_dist<<<(unsigned) n, 256, sm, st>>>(vps, T, S, n_incl, e_first, e_last);
+}
+void launch_line(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *egrid, int n_ener,
+                 int grid_mode, cudaStream_t st) {
+  dim3 grid((n_ener + 255) / 256, (unsigned) n);
+  k_line<<<grid, 256, 0, st>>>(vps, T, S, egrid, n_ener, grid_mode, S.ne_line_cap, S.nz_cap);
+}
+void launch_linefinish(const VPar *vps, const Scratch &S, long n, int n_ener, double *out, cudaStream_t st) {
+  k_linefinish<<<(unsigned) n, 256, 0, st>>>(vps, S, n_ener, S.ne_line_cap, S.nz_cap, out);
+}
+void launch_xill(const VPar *vps, const DevTables &T, const Scratch &S, long n, int which, int nz_max, cudaStream_t st) {
+  dim3 grid(nz_max, (unsigned) n);
+  k_xill<<<grid, 256, 0, st>>>(vps, T, S, which, S.nz_cap);
+}
+void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
+                 double *out, double *total, int which, int mode, cudaStream_t st) {
+  ConvArgs A;
+  A.user_e = user_e; A.n_flux = n_flux; A.out = out; A.total = total; A.which = which;
+  A.nz_stride = S.nz_cap; A.ne_stride = S.ne_line_cap; A.mode = mode;
+  const size_t sm = (4 * NCONV + CONV_NT) * sizeof(double);
+  k_conv<<<(unsigned) n, CONV_NT, sm, st>>>(vps, T, S, A);
+}
+
+}  // namespace rx

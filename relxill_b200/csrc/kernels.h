@@ -1,0 +1,23 @@
+// kernels.h — launchers of the sm_100a kernels (kernels.cu, nthcomp.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.h"
+
+namespace rx {
+
+int kernels_init();  // opt-in shared-memory sizes; returns 0 on success
+
+void launch_syspar(const VPar *vps, const DevTables &T, const Scratch &S, long n, int pass, cudaStream_t st);
+void launch_zone(const VPar *vps, const DevTables &T, const Scratch &S, long n, cudaStream_t st);
+void launch_fine(const VPar *vps, const DevTables &T, const Scratch &S, long n, cudaStream_t st);
+void launch_dist(const VPar *vps, const DevTables &T, const Scratch &S, long n, int n_incl, double e_first,
+                 double e_last, cudaStream_t st);
+void launch_line(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *egrid, int n_ener,
+                 int grid_mode, cudaStream_t st);
+void launch_linefinish(const VPar *vps, const Scratch &S, long n, int n_ener, double *out, cudaStream_t st);
+void launch_xill(const VPar *vps, const DevTables &T, const Scratch &S, long n, int which, int nz_max, cudaStream_t st);
+void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
+                 double *out, double *total, int which, int mode, cudaStream_t st);
+
+}  // namespace rx

@@ -1,0 +1,43 @@
+// models.h — host-side mirror of the reference's model database and parameter layer
+// (src/ModelDatabase.h, src/ModelDefinition.{h,cpp}, src/modelfiles/lmodel_relxill_public.dat).
+#pragma once
+#include "common.h"
+
+namespace rx {
+
+enum XPar {
+  P_LINEE, P_INDEX1, P_INDEX2, P_RBR, P_A, P_RIN, P_ROUT, P_INCL, P_Z, P_LIMB, P_GAMMA, P_LOGXI, P_LOGN, P_AFE,
+  P_ECUT, P_KTE, P_REFLFRAC, P_H, P_BETA, P_IONGRAD_INDEX, P_IONGRAD_TYPE, P_SWITCH_RETURNRAD,
+  P_SWITCH_REFLFRAC_BOOST, P_COUNT
+};
+
+struct ModelDef {
+  const char *name;      // XSPEC name (lmodel.dat column 1)
+  const char *symbol;    // C symbol after "c_" (lmodel.dat column 5)
+  int type, irrad, prim; // T_Model / T_Irrad / T_PrimSpec of src/ModelDatabase.h:136-165
+  int model_type;        // integer model type, src/ModelDefinition.cpp:35-61
+  int npar;
+  int ids[20];
+  double def[20];
+};
+
+struct HostConfig {
+  int env_num_zones = 0;     // RELXILL_NUM_RZONES (0 = unset)
+  int env_returnrad = -1;    // RELXILL_RETURNRAD_SWITCH (-1 = unset)
+  int env_phys_norm = 0;     // RELLINE_PHYSICAL_NORM
+};
+
+const ModelDef *find_model(const char *name);
+int num_models();
+const ModelDef *model_at(int i);
+
+// reference kerr_rms / kerr_rplus (src/Relphysics.cpp:139-155)
+double kerr_rms(double a);
+double kerr_rplus(double a);
+
+// Fill a VPar from one raw parameter vector.  `rr_spins` = spin axis of the returning-radiation
+// table (may be null if that table is not loaded).  Sets vp.status (ST_OK / ST_BAD_PARAM).
+void interpret_params(const ModelDef &m, const double *par, const HostConfig &cfg, const double *rr_spins,
+                      int rr_nspin, VPar &vp);
+
+}  // namespace rx

@@ -1,0 +1,432 @@
+// tables.cu — read the relxill FITS tables and lay them out in HBM.
+//
+// File layouts are the reference's (src/reltable.c:171-448, src/xilltable.c:169-276,513-564,
+// src/Relreturn_Table.cpp:289-361).  What changes is the residency and layout:
+//   * everything is loaded eagerly and stays resident on the device (the reference loads
+//     xillver rows lazily per interpolation corner, src/xilltable.c:575-635);
+//   * the four transfer-function columns are interleaved as float4 per (a, mu0, r, g*) so one
+//     16-byte load fetches trff1/trff2/cosne1/cosne2 of a corner;
+//   * xillver rows are padded to a 128-byte multiple for aligned vector loads and are
+//     renormalised once at load exactly like renorm_xill_spec (src/xilltable.c:478-485);
+//   * linear functionals of the xillver spectra that the returning-radiation correction needs
+//     (band energy flux, band photon flux before/after the g=2/3 shift) are reduced to three
+//     scalars per table node at load, so the kernels never re-read the spectra for them.
+#include "tables.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "minifits.h"
+
+namespace rx {
+
+#define CUDA_OK(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) return std::string("CUDA error: ") + cudaGetErrorString(e_);       \
+  } while (0)
+
+Tables::~Tables() {
+  for (void *p : allocs_) cudaFree(p);
+}
+
+template <class T> const T *Tables::upload(const T *p, size_t n) {
+  void *d = nullptr;
+  if (cudaMalloc(&d, n * sizeof(T) + 256) != cudaSuccess) return nullptr;
+  cudaMemcpy(d, p, n * sizeof(T), cudaMemcpyHostToDevice);
+  allocs_.push_back(d);
+  dev_bytes_ += n * sizeof(T);
+  return (const T *) d;
+}
+template <class T> const T *Tables::upload(const std::vector<T> &v) { return upload(v.data(), v.size()); }
+
+static void log_grid(std::vector<double> &e, int n, double emin, double emax) {  // src/relutility.c:399-405
+  e.resize(n);
+  for (int i = 0; i < n; i++) {
+    e[i] = 1.0 * i / (n - 1) * (std::log(emax) - std::log(emin)) + std::log(emin);
+    e[i] = std::exp(e[i]);
+  }
+}
+
+static int lower_index(const double *arr, int n, double val) {
+  int klo = 0, khi = n - 1;
+  while (khi - klo > 1) {
+    const int k = (khi + klo) / 2;
+    if (arr[k] > val) khi = k; else klo = k;
+  }
+  return klo;
+}
+
+// Flux-conserving rebin between monotone grids, same bin selection and arithmetic as
+// _rebin_spectrum (src/relutility.c:549-601).  Host version (table preprocessing only).
+static void rebin_host(const double *ener, double *flu, int nbins, const double *ener0, const double *flu0, int nbins0) {
+  int imin = 0, imax = 0;
+  for (int ii = 0; ii < nbins; ii++) {
+    flu[ii] = 0.0;
+    if ((ener0[0] <= ener[ii + 1]) && (ener0[nbins0] >= ener[ii])) {
+      while (imin <= nbins0 && ener0[imin] <= ener[ii]) imin++;
+      if (imin > 0) imin--;
+      while (imax < nbins0 && ener0[imax] <= ener[ii + 1]) imax++;
+      if (imax > 0) imax--;
+      double elo = ener[ii], ehi = ener[ii + 1];
+      if (elo < ener0[imin]) elo = ener0[imin];
+      if (ehi > ener0[imax + 1]) ehi = ener0[imax + 1];
+      if (imax == imin) {
+        flu[ii] = (ehi - elo) / (ener0[imin + 1] - ener0[imin]) * flu0[imin];
+      } else {
+        const double dmin = (ener0[imin + 1] - elo) / (ener0[imin + 1] - ener0[imin]);
+        const double dmax = (ehi - ener0[imax]) / (ener0[imax + 1] - ener0[imax]);
+        flu[ii] += flu0[imin] * dmin + flu0[imax] * dmax;
+        for (int jj = imin + 1; jj <= imax - 1; jj++) flu[ii] += flu0[jj];
+      }
+    }
+  }
+}
+
+void Tables::load_fixed() {
+  if (have_fixed_) return;
+  log_grid(econv_, NCONV + 1, 0.00035, 2000.0);   // src/Xillspec.h:36-38
+  log_grid(ecoarse_, NCOARSE + 1, 0.1, 1000.0);   // src/Xillspec.h:28-32
+  std::vector<double> cf(NCONV);
+  std::vector<unsigned char> band(NCONV), m1(NCOARSE), m2(NCOARSE);
+  for (int i = 0; i < NCONV; i++) {
+    cf[i] = 0.5 * (econv_[i] + econv_[i + 1]) / (econv_[i + 1] - econv_[i]);        // src/Relbase.cpp:93-103
+    band[i] = (econv_[i] >= 0.01 && econv_[i + 1] < 1000.0) ? 1 : 0;               // src/Relbase.cpp:205
+  }
+  for (int i = 0; i < NCOARSE; i++) {
+    m1[i] = (ecoarse_[i] >= 0.1 && ecoarse_[i] <= 1000.0) ? 1 : 0;                 // src/Xillspec.cpp:199
+    m2[i] = (ecoarse_[i] >= 0.1 && ecoarse_[i + 1] <= 1000) ? 1 : 0;               // src/Xillspec.cpp:139
+  }
+  std::vector<double> gstar(NG), dg(NG);
+  const double H = 5e-3;
+  for (int i = 0; i < NG; i++) gstar[i] = H + (1.0 - 2 * H) / (NG - 1) * ((float) (i));  // src/Relprofile.cpp:104-106
+  for (int i = 0; i < NG; i++)
+    dg[i] = (i == 0 || i == NG - 1) ? 0.5 * (gstar[1] - gstar[0]) + H : gstar[1] - gstar[0];
+  std::vector<double> twr(NCONV / 2), twi(NCONV / 2);
+  for (int k = 0; k < NCONV / 2; k++) {
+    const double ang = -2.0 * M_PI * k / NCONV;
+    twr[k] = std::cos(ang);
+    twi[k] = std::sin(ang);
+  }
+  dt_.econv = upload(econv_);
+  dt_.conv_cf = upload(cf);
+  dt_.conv_band = upload(band);
+  dt_.conv_i1kev = lower_index(econv_.data(), NCONV + 1, 1.0);                      // src/Relbase.cpp:133-137
+  dt_.ecoarse = upload(ecoarse_);
+  dt_.coarse_m1 = upload(m1);
+  dt_.coarse_m2 = upload(m2);
+  dt_.gstar = upload(gstar);
+  dt_.d_gstar = upload(dg);
+  dt_.tw_re = upload(twr);
+  dt_.tw_im = upload(twi);
+  have_fixed_ = true;
+}
+
+std::string Tables::load_rel() {
+  if (have_rel_) return "";
+  const std::string path = dir_ + "/rel_table_v0.5a.fits";
+  mf_file *f = mf_open(path.c_str());
+  if (!f) return "cannot open " + path;
+  std::vector<float> a(REL_NA), mu(REL_NMU);
+  int h = mf_find_hdu(f, "a");
+  int hm = mf_find_hdu(f, "mu0");
+  if (!h || !hm || f->nhdu < 3 + REL_NA * REL_NMU) { mf_close(f); return "rel table: unexpected layout in " + path; }
+  mf_read(&f->hdus[h - 1], mf_find_col(&f->hdus[h - 1], "a"), 1, 1, REL_NA, 'f', a.data());
+  mf_read(&f->hdus[hm - 1], mf_find_col(&f->hdus[hm - 1], "mu0"), 1, 1, REL_NMU, 'f', mu.data());
+  const size_t n1 = (size_t) REL_NA * REL_NMU * REL_NRT;
+  std::vector<float> r(n1), gmin(n1), gmax(n1), tc(n1 * NG * 4), col((size_t) REL_NRT * NG);
+  const char *names[4] = {"trff1", "trff2", "cosne1", "cosne2"};
+  for (int ia = 0; ia < REL_NA; ia++)
+    for (int im = 0; im < REL_NMU; im++) {
+      const mf_hdu *hd = &f->hdus[ia * REL_NMU + im + 4 - 1];  // by HDU number, src/reltable.c:290
+      const size_t o1 = ((size_t) ia * REL_NMU + im) * REL_NRT;
+      int rc = 0;
+      rc |= mf_read(hd, mf_find_col(hd, "r"), 1, 1, REL_NRT, 'f', r.data() + o1);
+      rc |= mf_read(hd, mf_find_col(hd, "gmin"), 1, 1, REL_NRT, 'f', gmin.data() + o1);
+      rc |= mf_read(hd, mf_find_col(hd, "gmax"), 1, 1, REL_NRT, 'f', gmax.data() + o1);
+      for (int q = 0; q < 4; q++) {
+        rc |= mf_read(hd, mf_find_col(hd, names[q]), 1, 1, REL_NRT * NG, 'f', col.data());
+        for (size_t k = 0; k < (size_t) REL_NRT * NG; k++) tc[(o1 * NG + k) * 4 + q] = col[k];
+      }
+      if (rc) { mf_close(f); return "rel table: read error in " + path; }
+    }
+  mf_close(f);
+  dt_.rel_a = upload(a);
+  dt_.rel_mu0 = upload(mu);
+  dt_.rel_r = upload(r);
+  dt_.rel_gmin = upload(gmin);
+  dt_.rel_gmax = upload(gmax);
+  dt_.rel_tc = upload(tc);
+  if (!dt_.rel_tc) return "out of device memory (rel table)";
+  have_rel_ = true;
+  return "";
+}
+
+std::string Tables::load_lp() {
+  if (have_lp_) return "";
+  const std::string path = dir_ + "/rel_lp_table_v0.5b.fits";
+  mf_file *f = mf_open(path.c_str());
+  if (!f) return "cannot open " + path;
+  const int h = mf_find_hdu(f, "I_h");
+  if (!h) { mf_close(f); return "lp table: no I_h extension in " + path; }
+  const mf_hdu *hd = &f->hdus[h - 1];
+  std::vector<float> a(LP_NA), hh((size_t) LP_NA * LP_NH), rad((size_t) LP_NA * LP_NRT);
+  const size_t n3 = (size_t) LP_NA * LP_NH * LP_NRT;
+  std::vector<float> in(n3), de(n3), di(n3);
+  int rc = mf_read(hd, mf_find_col(hd, "a"), 1, 1, LP_NA, 'f', a.data());
+  const int c_hg = mf_find_col(hd, "hgrid"), c_r = mf_find_col(hd, "r");
+  for (int ia = 0; ia < LP_NA && !rc; ia++) {
+    rc |= mf_read(hd, c_hg, ia + 1, 1, LP_NH, 'f', hh.data() + (size_t) ia * LP_NH);
+    rc |= mf_read(hd, c_r, ia + 1, 1, LP_NRT, 'f', rad.data() + (size_t) ia * LP_NRT);
+  }
+  for (int ih = 0; ih < LP_NH && !rc; ih++) {
+    char nm[32];
+    snprintf(nm, sizeof(nm), "h%i", ih + 1);
+    const int c1 = mf_find_col(hd, nm);
+    snprintf(nm, sizeof(nm), "del%i", ih + 1);
+    const int c2 = mf_find_col(hd, nm);
+    snprintf(nm, sizeof(nm), "del_inc%i", ih + 1);
+    const int c3 = mf_find_col(hd, nm);
+    for (int ia = 0; ia < LP_NA; ia++) {
+      const size_t o = ((size_t) ia * LP_NH + ih) * LP_NRT;
+      rc |= mf_read(hd, c1, ia + 1, 1, LP_NRT, 'f', in.data() + o);
+      rc |= mf_read(hd, c2, ia + 1, 1, LP_NRT, 'f', de.data() + o);
+      rc |= mf_read(hd, c3, ia + 1, 1, LP_NRT, 'f', di.data() + o);
+    }
+  }
+  mf_close(f);
+  if (rc) return "lp table: read error in " + path;
+  for (size_t k = 0; k < n3; k++) {  // the sign of the angles is dropped at load, src/reltable.c:370-377
+    de[k] = fabsf(de[k]);
+    di[k] = fabsf(di[k]);
+  }
+  dt_.lp_a = upload(a);
+  dt_.lp_h = upload(hh);
+  dt_.lp_rad = upload(rad);
+  dt_.lp_int = upload(in);
+  dt_.lp_del = upload(de);
+  dt_.lp_dinc = upload(di);
+  if (!dt_.lp_dinc) return "out of device memory (lp table)";
+  have_lp_ = true;
+  return "";
+}
+
+std::string Tables::load_rrad() {
+  if (have_rr_) return "";
+  const std::string path = dir_ + "/table_returnRad_v20220301.fits";
+  mf_file *f = mf_open(path.c_str());
+  if (!f) return "cannot open " + path;
+  const int hs = mf_find_hdu(f, "SPIN");
+  if (!hs) { mf_close(f); return "returnRad table: no SPIN extension"; }
+  const int ns = (int) f->hdus[hs - 1].nrows;
+  rr_spin_.resize(ns);
+  mf_read(&f->hdus[hs - 1], mf_find_col(&f->hdus[hs - 1], "a"), 1, 1, ns, 'd', rr_spin_.data());
+  const size_t n2 = (size_t) RR_NR * RR_NR;
+  std::vector<double> rlo((size_t) ns * RR_NR), rhi((size_t) ns * RR_NR), tf(ns * n2), gmin(ns * n2), gmax(ns * n2),
+      fg(ns * n2 * RR_NG), lng(ns * n2 * RR_NG);
+  int rc = 0;
+  for (int s = 0; s < ns; s++) {
+    char nm[32];
+    snprintf(nm, sizeof(nm), "FRAC%02i", s + 1);
+    const int h = mf_find_hdu(f, nm);
+    if (!h) { mf_close(f); return std::string("returnRad table: missing extension ") + nm; }
+    const mf_hdu *hd = &f->hdus[h - 1];
+    rc |= mf_read(hd, mf_find_col(hd, "rlo"), 1, 1, RR_NR, 'd', rlo.data() + (size_t) s * RR_NR);
+    rc |= mf_read(hd, mf_find_col(hd, "rhi"), 1, 1, RR_NR, 'd', rhi.data() + (size_t) s * RR_NR);
+    rc |= mf_read(hd, mf_find_col(hd, "tf_r"), 1, 1, n2, 'd', tf.data() + s * n2);
+    rc |= mf_read(hd, mf_find_col(hd, "gmin"), 1, 1, n2, 'd', gmin.data() + s * n2);
+    rc |= mf_read(hd, mf_find_col(hd, "gmax"), 1, 1, n2, 'd', gmax.data() + s * n2);
+    rc |= mf_read(hd, mf_find_col(hd, "frac_g"), 1, 1, n2 * RR_NG, 'd', fg.data() + s * n2 * RR_NG);
+  }
+  mf_close(f);
+  if (rc) return "returnRad table: read error";
+  for (size_t q = 0; q < ns * n2; q++)  // g grid of src/Relreturn_Datastruct.cpp:51-59, stored as ln g
+    for (int j = 0; j < RR_NG; j++) {
+      const double g = ((j + 0.5) / RR_NG) * (gmax[q] - gmin[q]) + gmin[q];
+      lng[q * RR_NG + j] = std::log(g);
+    }
+  dt_.rr_nspin = ns;
+  dt_.rr_spin = upload(rr_spin_);
+  dt_.rr_rlo = upload(rlo);
+  dt_.rr_rhi = upload(rhi);
+  dt_.rr_tf = upload(tf);
+  dt_.rr_gmin = upload(gmin);
+  dt_.rr_gmax = upload(gmax);
+  dt_.rr_fg = upload(fg);
+  dt_.rr_lng = upload(lng);
+  if (!dt_.rr_lng) return "out of device memory (returnRad table)";
+  have_rr_ = true;
+  return "";
+}
+
+static int xill_param_id(const char *name) {  // src/common.h:141-161
+  if (!strcmp(name, "Gamma")) return 0;
+  if (!strcmp(name, "A_Fe")) return 1;
+  if (!strcmp(name, "logXi")) return 2;
+  if (!strcmp(name, "Ecut") || !strcmp(name, "kTe")) return 3;
+  if (!strcmp(name, "Dens")) return 4;
+  if (!strcmp(name, "Incl")) return 7;
+  return -1;
+}
+
+std::string Tables::load_xill(int which) {
+  XillHost &xh = xh_[which];
+  if (xh.loaded) return "";
+  load_fixed();
+  const std::string path = dir_ + (which == 1 ? "/xillverCp_v3.4.fits" : "/xillver-a-Ec5.fits");
+  mf_file *f = mf_open(path.c_str());
+  if (!f) return "cannot open " + path;
+  const int hp = mf_find_hdu(f, "PARAMETERS"), he = mf_find_hdu(f, "ENERGIES"), hs = mf_find_hdu(f, "SPECTRA");
+  if (!hp || !he || !hs) { mf_close(f); return "xillver table: missing extension in " + path; }
+  const mf_hdu *P = &f->hdus[hp - 1], *E = &f->hdus[he - 1], *S = &f->hdus[hs - 1];
+  xh.npar = (int) P->nrows;
+  if (xh.npar != 5 && xh.npar != 6) { mf_close(f); return "xillver table: wrong dimensionality"; }
+  mf_read(P, 9, 1, 1, xh.npar, 'i', xh.nvals);
+  long nrows = 1;
+  int ax_lxi = -1, ax_dns = -1;
+  for (int i = 0; i < xh.npar; i++) {
+    char nm[16];
+    mf_read_str(P, 1, i + 1, nm, 8);
+    xh.pindex[i] = xill_param_id(nm);
+    if (xh.pindex[i] < 0) { mf_close(f); return std::string("xillver table: unknown parameter ") + nm; }
+    xh.vals[i].resize(xh.nvals[i]);
+    mf_read(P, 10, i + 1, 1, xh.nvals[i], 'f', xh.vals[i].data());
+    nrows *= xh.nvals[i];
+    if (xh.pindex[i] == 2) ax_lxi = i;
+    if (xh.pindex[i] == 4) ax_dns = i;
+  }
+  if (xh.pindex[xh.npar - 1] != 7 || S->nrows != nrows) { mf_close(f); return "xillver table: Incl must be the last axis"; }
+  // the kernels assume the reference's standard axis order: [Gamma,] A_Fe, logXi, Ecut|kTe, [Dens,] Incl
+  xh.n_incl = xh.nvals[xh.npar - 1];
+  if (xh.n_incl > MAX_INCL) { mf_close(f); return "xillver table: too many inclinations"; }
+  xh.n_ener = (int) E->nrows;
+  xh.stride = ((xh.n_ener + 31) / 32) * 32;
+  xh.nnodes = nrows / xh.n_incl;
+  std::vector<float> elo(xh.n_ener), ehi(xh.n_ener);
+  mf_read(E, 1, 1, 1, xh.n_ener, 'f', elo.data());
+  mf_read(E, 2, 1, 1, xh.n_ener, 'f', ehi.data());
+  xh.ener.resize(xh.n_ener + 1);
+  for (int i = 0; i < xh.n_ener; i++) xh.ener[i] = elo[i];                         // src/xilltable.c:1105-1109
+  xh.ener[xh.n_ener] = ehi[xh.n_ener - 1];
+
+  const mf_col *sc = &S->cols[1];  // column 2 = INTPSPEC, src/xilltable.c:544
+  if (sc->code != 'E' || sc->width != xh.n_ener) { mf_close(f); return "xillver table: INTPSPEC column has the wrong shape"; }
+  const int ne = xh.n_ener, ni = xh.n_incl, st = xh.stride;
+  std::vector<double> ef(xh.nnodes), p1(xh.nnodes), p2(xh.nnodes);
+  std::vector<double> w(ni), avg(ne), ez(ne + 1), fz(ne);
+  for (int m = 0; m < ni; m++) {  // angle-average weights, src/Xillspec.cpp:109-126 (degrees passed through *180/pi)
+    const double incl_deg = ((double) xh.vals[xh.npar - 1][m]) * 180 / M_PI;
+    w[m] = 0.5 * std::cos(incl_deg * M_PI / 180) / ni;
+  }
+  const double gref = 2. / 3.;
+  for (int i = 0; i <= ne; i++) ez[i] = xh.ener[i] / gref;
+
+  float *d_data = nullptr;
+  const size_t total = (size_t) nrows * st;
+  if (cudaMalloc((void **) &d_data, total * sizeof(float)) != cudaSuccess) { mf_close(f); return "out of device memory (xillver table)"; }
+  allocs_.push_back(d_data);
+  dev_bytes_ += total * sizeof(float);
+  xh.bytes = total * sizeof(float);
+  // stream node blocks through a staging buffer
+  const long nodes_per_blk = 256;
+  std::vector<float> stage((size_t) nodes_per_blk * ni * st, 0.f);
+  for (long n0 = 0; n0 < xh.nnodes; n0 += nodes_per_blk) {
+    const long nb = std::min(nodes_per_blk, xh.nnodes - n0);
+    for (long nd = 0; nd < nb; nd++) {
+      const long node = n0 + nd;
+      long rem = node;
+      int idx[6] = {0};
+      for (int i = xh.npar - 2; i >= 0; i--) { idx[i] = (int) (rem % xh.nvals[i]); rem /= xh.nvals[i]; }
+      const double lxi = (ax_lxi >= 0) ? (double) xh.vals[ax_lxi][idx[ax_lxi]] : 0.0;
+      const double dens = (ax_dns >= 0) ? (double) xh.vals[ax_dns][idx[ax_dns]] : 15.0;
+      const double pl = std::pow(10, lxi), pd = std::pow(10, dens - 15);
+      const bool do_d = std::fabs(dens - 15) > 1e-6;
+      for (int e = 0; e < ne; e++) avg[e] = 0.0;
+      for (int m = 0; m < ni; m++) {
+        float *dst = stage.data() + ((size_t) nd * ni + m) * st;
+        const long row = node * ni + m;
+        mf_copy_f32(S->data + (size_t) row * S->rowbytes + sc->offset, dst, ne);
+        for (int e = 0; e < ne; e++) {  // renorm_xill_spec: float /= double, twice
+          dst[e] /= pl;
+          if (do_d) dst[e] /= pd;
+          avg[e] += w[m] * (double) dst[e];
+        }
+      }
+      double s_ef = 0.0, s_p1 = 0.0, s_p2 = 0.0;
+      rebin_host(ez.data(), fz.data(), ne, xh.ener.data(), avg.data(), ne);       // src/Xillspec.cpp:457-487
+      for (int e = 0; e < ne; e++) {
+        if (xh.ener[e] >= 0.1 && xh.ener[e + 1] <= 1000) s_ef += avg[e] * 0.5 * (xh.ener[e] + xh.ener[e + 1]);
+        if (xh.ener[e] >= 0.15 && xh.ener[e + 1] <= 500.0) { s_p1 += avg[e]; s_p2 += fz[e] * gref; }
+      }
+      ef[node] = s_ef; p1[node] = s_p1; p2[node] = s_p2;
+    }
+    cudaMemcpy(d_data + (size_t) n0 * ni * st, stage.data(), (size_t) nb * ni * st * sizeof(float), cudaMemcpyHostToDevice);
+  }
+  mf_close(f);
+
+  // fixed rebin map xillver grid -> convolution grid
+  std::vector<int> imin_v(NCONV), imax_v(NCONV);
+  std::vector<double> dmin_v(NCONV), dmax_v(NCONV);
+  {
+    const double *e0 = xh.ener.data(), *e = econv_.data();
+    int imin = 0, imax = 0;
+    for (int ii = 0; ii < NCONV; ii++) {
+      imin_v[ii] = -1; imax_v[ii] = -1; dmin_v[ii] = 0; dmax_v[ii] = 0;
+      if ((e0[0] <= e[ii + 1]) && (e0[ne] >= e[ii])) {
+        while (imin <= ne && e0[imin] <= e[ii]) imin++;
+        if (imin > 0) imin--;
+        while (imax < ne && e0[imax] <= e[ii + 1]) imax++;
+        if (imax > 0) imax--;
+        double elo_ = e[ii], ehi_ = e[ii + 1];
+        if (elo_ < e0[imin]) elo_ = e0[imin];
+        if (ehi_ > e0[imax + 1]) ehi_ = e0[imax + 1];
+        imin_v[ii] = imin; imax_v[ii] = imax;
+        if (imax == imin) {
+          dmin_v[ii] = (ehi_ - elo_) / (e0[imin + 1] - e0[imin]);
+        } else {
+          dmin_v[ii] = (e0[imin + 1] - elo_) / (e0[imin + 1] - e0[imin]);
+          dmax_v[ii] = (ehi_ - e0[imax]) / (e0[imax + 1] - e0[imax]);
+        }
+      }
+    }
+  }
+  XillDev &xd = dt_.xill[which];
+  xd.npar = xh.npar;
+  for (int i = 0; i < 6; i++) { xd.nvals[i] = xh.nvals[i]; xd.pindex[i] = xh.pindex[i]; xd.vals[i] = nullptr; }
+  for (int i = 0; i < xh.npar; i++) xd.vals[i] = upload(xh.vals[i]);
+  xd.n_ener = ne; xd.n_incl = ni; xd.stride = st; xd.nnodes = xh.nnodes;
+  xd.data = d_data;
+  xd.ener = upload(xh.ener);
+  xd.incl = xd.vals[xh.npar - 1];
+  xd.node_ef = upload(ef);
+  xd.node_p1 = upload(p1);
+  xd.node_p2 = upload(p2);
+  xd.rb_imin = upload(imin_v);
+  xd.rb_imax = upload(imax_v);
+  xd.rb_dmin = upload(dmin_v);
+  xd.rb_dmax = upload(dmax_v);
+  if (!xd.rb_dmax) return "out of device memory (xillver table)";
+  xh.loaded = true;
+  return "";
+}
+
+std::string Tables::load(const std::string &dir) {
+  dir_ = dir;
+  load_fixed();
+  return load_rel();
+}
+
+std::string Tables::require(bool lp, bool rrad, int prim_type) {
+  std::string err = load_rel();
+  if (!err.empty()) return err;
+  if (lp && !(err = load_lp()).empty()) return err;
+  if (rrad && !(err = load_rrad()).empty()) return err;
+  if (prim_type == PRIM_ECUT && !(err = load_xill(0)).empty()) return err;
+  if (prim_type == PRIM_NTHCOMP && !(err = load_xill(1)).empty()) return err;
+  return "";
+}
+
+}  // namespace rx

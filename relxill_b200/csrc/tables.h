@@ -1,0 +1,51 @@
+// tables.h — FITS tables -> host arrays -> HBM-resident DevTables.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "common.h"
+
+namespace rx {
+
+struct XillHost {
+  bool loaded = false;
+  int npar = 0, nvals[6] = {0}, pindex[6] = {0}, n_ener = 0, n_incl = 0, stride = 0;
+  long nnodes = 0;
+  std::vector<float> vals[6];
+  std::vector<double> ener;
+  size_t bytes = 0;
+};
+
+class Tables {
+ public:
+  ~Tables();
+  // loads rel + (optionally) lp / rrad / xillver tables that exist in dir; returns "" or an error message
+  std::string load(const std::string &dir);
+  // lazily make sure the table needed by a model flavour is there
+  std::string require(bool lp, bool rrad, int prim_type);
+  const DevTables &dev() const { return dt_; }
+  const std::vector<double> &rr_spins() const { return rr_spin_; }
+  const XillHost &xill_host(int prim_type) const { return xh_[prim_type == PRIM_NTHCOMP ? 1 : 0]; }
+  bool has_rel() const { return have_rel_; }
+  const std::vector<double> &econv() const { return econv_; }
+  size_t device_bytes() const { return dev_bytes_; }
+
+ private:
+  std::string dir_;
+  DevTables dt_{};
+  bool have_rel_ = false, have_lp_ = false, have_rr_ = false, have_fixed_ = false;
+  XillHost xh_[2];
+  std::vector<double> rr_spin_, econv_, ecoarse_;
+  std::vector<void *> allocs_;
+  size_t dev_bytes_ = 0;
+
+  template <class T> const T *upload(const std::vector<T> &v);
+  template <class T> const T *upload(const T *p, size_t n);
+  void load_fixed();
+  std::string load_rel();
+  std::string load_lp();
+  std::string load_rrad();
+  std::string load_xill(int which);
+};
+
+}  // namespace rx
