@@ -21,8 +21,8 @@ def available() -> bool:
     return os.path.exists(REF_SO)
 
 
-class Ref:
-    """The reference is full of process-global state (tables, caches, env reads on
+class RefLocal:
+    """In-process binding.  The reference is full of process-global state (tables, caches, env reads on
     every call), so: one table directory per process, set before the first call."""
 
     def __init__(self, table_dir: str, num_zones: int | None = None):
@@ -166,6 +166,99 @@ class Ref:
         out = np.zeros(ener.size - 1)
         self.lib.ref_nthcomp(ener, ener.size - 1, gamma, kte, z, out)
         return out
+
+
+def _worker(conn, table_dir, num_zones):
+    ref = RefLocal(table_dir, num_zones)
+    while True:
+        msg = conn.recv()
+        if msg is None:
+            break
+        name, args = msg
+        try:
+            conn.send(("ok", getattr(ref, name)(*args)))
+        except Exception as exc:  # noqa: BLE001
+            conn.send(("err", repr(exc)))
+
+
+class Ref:
+    """Process-isolated binding used by the tests.  The reference keeps linked-list / deque caches in
+    file-scope globals and is not robust when many different models and zone counts are evaluated in one
+    process (it can segfault after a few dozen mixed evaluations), so each model gets its own worker
+    process, recycled every `max_calls` calls.  Results do not depend on the caches (they are
+    result-transparent), only the crash behaviour does."""
+
+    def __init__(self, table_dir: str, num_zones: int | None = None, max_calls: int = 40):
+        self.table_dir, self.num_zones, self.max_calls = table_dir, num_zones, max_calls
+        self._workers = {}
+
+    def set_num_zones(self, n):
+        if n != self.num_zones:
+            self.close()
+        self.num_zones = n
+
+    def _call(self, key, name, *args):
+        import multiprocessing as mp
+        w = self._workers.get(key)
+        if w is not None and (w[2] >= self.max_calls or not w[0].is_alive()):
+            self._stop(key)
+            w = None
+        if w is None:
+            ctx = mp.get_context("spawn")
+            parent, child = ctx.Pipe()
+            proc = ctx.Process(target=_worker, args=(child, self.table_dir, self.num_zones), daemon=True)
+            proc.start()
+            w = [proc, parent, 0]
+            self._workers[key] = w
+        w[2] += 1
+        w[1].send((name, args))
+        if not w[1].poll(600):
+            self._stop(key)
+            raise RuntimeError("reference worker timed out")
+        try:
+            tag, val = w[1].recv()
+        except EOFError:
+            self._stop(key)
+            raise RuntimeError(f"reference worker died in {name}{args[:1]}")
+        if tag == "err":
+            raise RuntimeError(val)
+        return val
+
+    def _stop(self, key):
+        w = self._workers.pop(key, None)
+        if w is None:
+            return
+        try:
+            w[1].send(None)
+        except Exception:  # noqa: BLE001
+            pass
+        w[0].join(2)
+        if w[0].is_alive():
+            w[0].kill()
+
+    def close(self):
+        for k in list(self._workers):
+            self._stop(k)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def num_params(self, model): return self._call(model, "num_params", model)
+    def default_params(self, model): return self._call(model, "default_params", model)
+    def eval(self, model, energy, par): return self._call(model, "eval", model, energy, par)
+    def eval_conv(self, model, energy, par, flux_in): return self._call(model, "eval_conv", model, energy, par, flux_in)
+    def eval_batch(self, model, energy, params): return self._call(model, "eval_batch", model, energy, params)
+    def rel_params(self, model, par): return self._call(model, "rel_params", model, par)
+    def syspar(self, model, par): return self._call(model, "syspar", model, par)
+    def relbase(self, model, par, ener): return self._call(model, "relbase", model, par, ener)
+    def stages(self, model, par): return self._call(model, "stages", model, par)
+    def conv_grid(self): return self._call("_util", "conv_grid")
+    def rebin(self, ener, ener0, flu0): return self._call("_util", "rebin", ener, ener0, flu0)
+    def fft_conv(self, fxill, frel): return self._call("_util", "fft_conv", fxill, frel)
+    def nthcomp(self, ener, gamma, kte, z): return self._call("_util", "nthcomp", ener, gamma, kte, z)
 
 
 def default_grid(n=3000, emin=0.1, emax=1000.0):

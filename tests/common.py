@@ -1,0 +1,88 @@
+"""Shared by the tests and tests/golden/make_golden.py: seeded parameter samplers and the parity metric."""
+import numpy as np
+
+MODELS = ["relline", "relline_lp", "relconv", "relconv_lp", "relxill", "relxilllp", "relxillCp", "relxilllpCp"]
+# north_star tolerance: relative error <= 1e-5 per bin on bins above 1e-6 of the spectrum peak
+RTOL = 1e-5
+PEAK_FLOOR = 1e-6
+
+
+def default_grid(n=3000, emin=0.1, emax=1000.0):
+    i = np.arange(n + 1, dtype=np.float64)
+    e = np.exp(i / float(n) * (np.log(emax) - np.log(emin)) + np.log(emin))
+    e[-1] = emax
+    return e
+
+
+def relerr(a, b, floor=PEAK_FLOOR):
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    peak = np.abs(b).max()
+    if peak == 0:
+        return float(np.abs(a).max())
+    m = np.abs(b) > floor * peak
+    return float(np.max(np.abs(a[m] - b[m]) / np.abs(b[m])))
+
+
+def sample_params(model, n, seed):
+    """n random parameter vectors inside the lmodel.dat soft ranges, row 0 = defaults-like."""
+    rng = np.random.default_rng(seed)
+    U = rng.uniform
+    rows = []
+    for _ in range(n):
+        z = U(0, .3) * (rng.random() < .5)
+        a = U(-0.998, 0.998)
+        incl = U(5, 85)
+        rin = -U(1, 5)
+        rout = U(50, 1000)
+        h = U(1.5, 100)
+        beta = U(0, .5) * (rng.random() < .5)
+        if model == "relline":
+            r = [U(1, 8), U(0, 6), U(0, 6), U(2, 100), a, incl, rin, rout, z, rng.integers(0, 3)]
+        elif model == "relconv":
+            r = [U(0, 6), U(0, 6), U(2, 100), a, incl, rin, rout, rng.integers(0, 3)]
+        elif model == "relline_lp":
+            r = [U(1, 8), h, a, incl, rin, rout, z, rng.integers(0, 3), U(1, 3.4), rng.integers(0, 2)]
+        elif model == "relconv_lp":
+            r = [h, beta, a, incl, rin, rout, rng.integers(0, 3), U(1, 3.4), rng.integers(0, 2)]
+        elif model == "relxill":
+            r = [U(0, 6), U(0, 6), U(2, 100), a, incl, rin, rout, z, U(1, 3.4), U(0, 4.7), U(.5, 10), U(5, 1000), U(-2, 10)]
+        elif model == "relxilllp":
+            r = [h, beta, a, incl, rin, rout, z, U(1, 3.4), U(0, 4.7), U(.5, 10), U(5, 1000), U(-2, 10),
+                 rng.integers(0, 2), rng.integers(0, 2)]
+        elif model == "relxillCp":
+            r = [incl, a, rin, rout, U(2, 100), U(0, 6), U(0, 6), z, U(1.2, 3.4), U(0, 4.7), U(15, 20), U(.5, 10),
+                 U(1, 400), U(-2, 10)]
+        elif model == "relxilllpCp":
+            r = [incl, a, rin, rout, h, beta, U(1.2, 3.4), U(0, 4.7), U(15, 20), U(.5, 10), U(1, 400), U(-2, 10), z,
+                 U(0, 3), rng.integers(0, 3), rng.integers(0, 2), rng.integers(0, 2)]
+        else:
+            raise KeyError(model)
+        rows.append([float(x) for x in r])
+    return np.array(rows, np.float64)
+
+
+def walker_ball(model, n, seed=4321):
+    """BASELINE config 3: Gaussian ball of MCMC walkers around the defaults, clipped to the hard limits."""
+    rng = np.random.default_rng(seed)
+    if model == "relxilllp":
+        #            h    beta  a     Incl Rin  Rout  z  gamma logxi Afe Ecut  refl rr boost
+        c = np.array([6.0, 0.0, 0.9, 30., -1., 400., 0., 2.0, 3.1, 1.0, 300., 1.0, 1, 0])
+        s = np.array([0.5, 0.0, 0.03, 3.0, 0., 0., 0., 0.05, 0.1, 0.2, 30., 0.2, 0, 0])
+        lo = np.array([2.0, 0, -0.998, 3, -100, 1, 0, 1.0, 0, 0.5, 5, 0, 0, 0])
+        hi = np.array([500, .99, 0.998, 87, -1, 1000, 10, 3.4, 4.7, 10, 1000, 10, 1, 1])
+    elif model == "relxilllpCp":
+        #            Incl a    Rin Rout  h   beta gamma logxi logN Afe kTe refl z idx type rr boost
+        c = np.array([30., 0.9, -1., 400., 6.0, 0.0, 2.0, 3.1, 16., 1.0, 60., 1.0, 0., 1.0, 1, 1, 0])
+        s = np.array([3.0, 0.03, 0., 0., 0.5, 0.0, 0.05, 0.1, 0.3, 0.2, 6.0, 0.2, 0., 0.2, 0, 0, 0])
+        lo = np.array([3, -0.998, -100, 1, 2.0, 0, 1.2, 0, 15, 0.5, 1, 0, 0, 0, 0, 0, 0])
+        hi = np.array([87, 0.998, -1, 1000, 500, .99, 3.4, 4.7, 20, 10, 400, 10, 10, 3, 2, 1, 1])
+    elif model == "relxill":
+        c = np.array([3., 3., 15., 0.9, 30., -1., 400., 0., 2.0, 3.1, 1.0, 300., 1.0])
+        s = np.array([0.3, 0.3, 2., 0.03, 3., 0., 0., 0., 0.05, 0.1, 0.2, 30., 0.2])
+        lo = np.array([0, 0, 1, -0.998, 3, -100, 1, 0, 1.0, 0, 0.5, 5, 0])
+        hi = np.array([10, 10, 1000, 0.998, 87, -1, 1000, 10, 3.4, 4.7, 10, 1000, 10])
+    else:
+        raise KeyError(model)
+    p = c[None, :] + s[None, :] * rng.standard_normal((n, c.size))
+    return np.clip(p, lo, hi)

@@ -1,0 +1,59 @@
+"""Generates tests/golden/golden_v1.npz from the UNMODIFIED reference (oracle/_ref) on the synthetic
+'test' tables.  Run in the build container (needs /root/reference to have been compiled by
+`make -C oracle ref`):   python tests/golden/make_golden.py
+The fixture pins the oracle restatement and the CUDA path on machines without the reference."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from common import MODELS, default_grid, sample_params  # noqa: E402
+from oracle.pyref import Ref  # noqa: E402  (process-isolated)
+from relxill_b200.tables import synth  # noqa: E402
+
+
+def table_digest(d):
+    h = hashlib.sha256()
+    for key in ("rel", "lp", "xill", "xillcp", "rrad"):
+        with open(os.path.join(d, synth.FILES[key]), "rb") as f:
+            while True:
+                blk = f.read(1 << 24)
+                if not blk:
+                    break
+                h.update(blk)
+    return h.hexdigest()
+
+
+def main():
+    tdir = synth.generate(synth.default_table_dir("test"), "test")
+    os.environ.pop("RELXILL_NUM_RZONES", None)
+    ref = Ref(tdir)
+    e = default_grid(600)  # 600 bins keep the fixture small; the grid is arbitrary for every model
+    out = {"energy": e, "table_digest": np.array(table_digest(tdir))}
+    conv_in = np.exp(-0.5 * ((np.log(0.5 * (e[1:] + e[:-1])) - np.log(6.4)) / 0.02) ** 2) + 1e-3
+    out["conv_input"] = conv_in
+    for m in MODELS:
+        P = np.vstack([ref.default_params(m)[None, :], sample_params(m, 5, seed=1000 + len(m))])
+        if m.startswith("relconv"):
+            F = np.stack([ref.eval_conv(m, e, p, conv_in) for p in P])
+        else:
+            F = ref.eval_batch(m, e, P)
+        out[f"{m}_params"] = P
+        out[f"{m}_flux"] = F
+        print(m, P.shape, F.shape, float(F.sum()))
+    # 50-zone variants of the lamp-post models (metric config)
+    ref.set_num_zones(50)
+    for m in ("relxilllp", "relxilllpCp"):
+        P = sample_params(m, 3, seed=77)
+        out[f"{m}_z50_params"] = P
+        out[f"{m}_z50_flux"] = ref.eval_batch(m, e, P)
+    ref.set_num_zones(None)
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_v1.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

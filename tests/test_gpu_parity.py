@@ -1,0 +1,189 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> librelxill_b200.so), against the
+oracle on the same seeded inputs, against the golden vectors generated from the unmodified reference, and
+through size-independent properties at full batch size.
+
+Tolerance (north_star): relative error <= 1e-5 per bin on bins above 1e-6 of the spectrum peak."""
+import os
+
+import numpy as np
+import pytest
+
+from common import PEAK_FLOOR, RTOL, default_grid, relerr, sample_params, walker_ball
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz")
+GPU_MODELS = ["relline", "relline_lp", "relconv", "relconv_lp", "relxill", "relxilllp"]
+
+
+def _conv_input(e):
+    return np.exp(-0.5 * ((np.log(0.5 * (e[1:] + e[:-1])) - np.log(6.4)) / 0.03) ** 2) + 1e-3
+
+
+@pytest.mark.parametrize("model", GPU_MODELS)
+def test_vs_golden_reference_vectors(rx, model):
+    g = np.load(GOLDEN)
+    e, P, F = g["energy"], g[f"{model}_params"], g[f"{model}_flux"]
+    rx.set_num_zones(None)
+    fin = g["conv_input"] if model.startswith("relconv") else None
+    got, st = rx.batch_eval(model, e, P, fin, return_status=True)
+    assert (st == 0).all()
+    for a, b in zip(got, F):
+        assert relerr(a, b) < RTOL
+
+
+def test_vs_golden_50_zones(rx):
+    g = np.load(GOLDEN)
+    rx.set_num_zones(50)
+    try:
+        got = rx.batch_eval("relxilllp", g["energy"], g["relxilllp_z50_params"])
+        for a, b in zip(got, g["relxilllp_z50_flux"]):
+            assert relerr(a, b) < RTOL
+    finally:
+        rx.set_num_zones(None)
+
+
+@pytest.mark.parametrize("model", GPU_MODELS)
+def test_vs_oracle_random(rx, oracle, model):
+    e = default_grid(3000)
+    P = sample_params(model, 24, seed=2024 + len(model))
+    rx.set_num_zones(None)
+    oracle.set_num_zones(None)
+    fin = _conv_input(e) if model.startswith("relconv") else None
+    got, st = rx.batch_eval(model, e, P, fin, return_status=True)
+    assert (st == 0).all()
+    worst = 0.0
+    for a, p in zip(got, P):
+        b = oracle.eval_conv(model, e, p, fin) if fin is not None else oracle.eval(model, e, p)
+        worst = max(worst, relerr(a, b))
+    assert worst < RTOL, worst
+
+
+def test_metric_config_vs_oracle(rx, oracle):
+    """relxilllp, RELXILL_NUM_RZONES=50, MCMC-walker ball (BASELINE config 3), 3000-bin grid."""
+    e = default_grid(3000)
+    P = walker_ball("relxilllp", 12)
+    rx.set_num_zones(50)
+    oracle.set_num_zones(50)
+    try:
+        got = rx.batch_eval("relxilllp", e, P)
+        for a, p in zip(got, P):
+            assert relerr(a, oracle.eval("relxilllp", e, p)) < RTOL
+    finally:
+        rx.set_num_zones(None)
+        oracle.set_num_zones(None)
+
+
+def test_stage_parity(rx, oracle):
+    """Intermediates of the pipeline against the oracle's (tight tolerances: same arithmetic)."""
+    import torch
+    e = default_grid(3000)
+    P = sample_params("relxilllp", 4, seed=11)
+    P[:, 12] = 1  # returning radiation on: exercises the second system-parameter pass
+    P[:, 2] = np.abs(P[:, 2])
+    b = rx.Batch("relxilllp", e, P)
+    out = torch.zeros((4, 3000), dtype=torch.float64, device="cuda")
+    b.run(out.data_ptr())
+    torch.cuda.synchronize()
+    for i, p in enumerate(P):
+        sp, sg = oracle.syspar("relxilllp", p), oracle.stages("relxilllp", p)
+        for k in ("re", "gmin", "gmax", "del_emit", "del_inc"):
+            np.testing.assert_allclose(b.probe(i, k), sp[k], rtol=1e-13, err_msg=k)
+        np.testing.assert_allclose(b.probe(i, "trff"), sp["trff"].ravel(), rtol=1e-13)
+        np.testing.assert_allclose(b.probe(i, "cosne"), sp["cosne"].ravel(), rtol=1e-13)
+        np.testing.assert_allclose(b.probe(i, "emis"), sg["emis2"], rtol=1e-12)
+        for k in ("lxi", "ect", "eshift", "normch", "corr_flux", "corr_gshift"):
+            np.testing.assert_allclose(b.probe(i, k), sg[k], rtol=1e-12, err_msg=k)
+        assert relerr(b.probe(i, "relflux"), sg["relflux"]) < 1e-11
+        np.testing.assert_allclose(b.probe(i, "dist"), sg["dist"].ravel(), rtol=1e-11)
+        assert relerr(b.probe(i, "xill"), sg["xill"]) < 1e-11
+        assert relerr(b.probe(i, "total"), sg["total"]) < RTOL
+    b.close()
+
+
+def test_lmod_symbols_match_batch(rx):
+    e = default_grid(500)
+    for model in GPU_MODELS:
+        p = rx.default_params(model)
+        fin = _conv_input(e) if model.startswith("relconv") else None
+        a = rx.lmod(model, e, p, fin)
+        b = rx.batch_eval(model, e, p[None, :], fin)[0]
+        np.testing.assert_array_equal(a, b)
+        assert np.isfinite(a).all() and a.sum() > 0
+
+
+def test_local_model_interface(rx, oracle):
+    e = default_grid(800)
+    lm = rx.LocalModel("relxilllp").set_par("h", 4.0).set_par("a", 0.5).set_par("Incl", 55.0)
+    got = lm.eval_model(e)
+    p = rx.default_params("relxilllp")
+    p[0], p[2], p[3] = 4.0, 0.5, 55.0
+    assert relerr(got, oracle.eval("relxilllp", e, p)) < RTOL
+
+
+def test_invalid_parameters_are_reported_per_vector(rx):
+    e = default_grid(300)
+    P = np.tile(rx.default_params("relxill"), (4, 1))
+    P[1, 3] = 0.9999      # spin above 0.9982 -> rejected by the reference's check_parameter_bounds
+    P[2, 4] = 89.5        # inclination outside 3..87 deg
+    flux, st = rx.batch_eval("relxill", e, P, return_status=True)
+    assert st[0] == 0 and st[3] == 0 and st[1] != 0 and st[2] != 0
+    assert (flux[1] == 0).all() and (flux[2] == 0).all() and flux[0].sum() > 0
+    np.testing.assert_array_equal(flux[0], flux[3])
+    with pytest.raises(rx.ModelEvalFailed):
+        rx.LocalModel("relxill", P[1]).eval_model(e)
+
+
+def test_ragged_and_tiny_grids(rx, oracle):
+    rng = np.random.default_rng(5)
+    e = np.sort(np.concatenate([[0.05, 2500.0], rng.uniform(0.2, 80.0, 57)]))  # irregular, beyond the conv grid
+    p = rx.default_params("relxilllp")
+    assert relerr(rx.batch_eval("relxilllp", e, p[None, :])[0], oracle.eval("relxilllp", e, p)) < RTOL
+    e1 = np.array([3.0, 7.0])  # a single bin
+    np.testing.assert_allclose(rx.batch_eval("relline", e1, rx.default_params("relline")[None, :])[0],
+                               oracle.eval("relline", e1, rx.default_params("relline")), rtol=1e-12)
+
+
+def test_redshift_and_negative_refl_frac(rx, oracle):
+    e = default_grid(1000)
+    p = rx.default_params("relxilllp")
+    p[6] = 0.4          # z
+    p[11] = -1.5        # reflection only
+    assert relerr(rx.batch_eval("relxilllp", e, p[None, :])[0], oracle.eval("relxilllp", e, p)) < RTOL
+
+
+# ---------------------------------------------------------------- properties at BASELINE batch sizes
+def test_full_batch_properties(rx):
+    """4096 walkers x 50 zones x 3000 bins (the metric configuration): order invariance, chunk invariance,
+    linearity in refl_frac and flux conservation of the output rebin."""
+    e = default_grid(3000)
+    n = 4096
+    P = walker_ball("relxilllp", n)
+    rx.set_num_zones(50)
+    try:
+        f = rx.batch_eval("relxilllp", e, P)
+        assert np.isfinite(f).all() and (f.sum(axis=1) > 0).all()
+        # (1) a permuted batch gives the permuted result, bit for bit (vectors are independent)
+        perm = np.random.default_rng(1).permutation(n)[:512]
+        np.testing.assert_array_equal(rx.batch_eval("relxilllp", e, P[perm]), f[perm])
+        # (2) refl_frac enters linearly: f(rf) = |rf| R + primary for rf >= 0 and no boost switch
+        sub = P[:256].copy()
+        sub[:, 13] = 0
+        f1, f2, f3 = (rx.batch_eval("relxilllp", e, np.column_stack([sub[:, :11], np.full(256, rf), sub[:, 12:]]))
+                      for rf in (1.0, 2.0, 3.0))
+        np.testing.assert_allclose(f3 - f2, f2 - f1, rtol=1e-9, atol=1e-12 * f1.max())
+        # (3) the output rebin conserves flux: a 2x coarser grid holds the pairwise sums
+        fc = rx.batch_eval("relxilllp", e[::2], P[:256])
+        np.testing.assert_allclose(fc, f[:256, 0::2] + f[:256, 1::2], rtol=1e-10)
+    finally:
+        rx.set_num_zones(None)
+
+
+def test_relline_normalisation_full_batch(rx):
+    """relline is normalised to unit photon flux (reference test/unit/test-relxill.cpp:29-40 checks the same
+    integral on the published tables)."""
+    e = default_grid(3000, 0.05, 12.0)
+    P = sample_params("relline", 1024, seed=9)
+    P[:, 0] = 1.0
+    P[:, 8] = 0.0
+    f = rx.batch_eval("relline", e, P)
+    np.testing.assert_allclose(f.sum(axis=1), 1.0, rtol=1e-12)

@@ -1,0 +1,133 @@
+"""CPU tests of the oracle: reference known-answer tests, golden vectors generated from the unmodified
+reference, and (when oracle/_ref is built) fresh reference runs, whole-model and stage by stage."""
+import os
+
+import numpy as np
+import pytest
+
+from common import MODELS, default_grid, relerr, sample_params
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz")
+
+
+# ---------------------------------------------------------------- table-independent KATs of the reference
+def test_rebin_spectrum_kat(oracle):
+    # reference test/unit/test-stdfunctions.cpp:129-152
+    ener0 = np.array([1, 3, 4, 5, 6, 7, 9], float)
+    val0 = np.array([1, 1, 1, 2, 1, 1], float)
+    ener = np.array([0.5, 2, 4, 5.5, 7.5, 8], float)
+    val = oracle.rebin(ener, ener0, val0)
+    np.testing.assert_allclose(val, [0.5, 1.5, 2.0, 2.25, 0.25], atol=1e-12)
+
+
+def test_default_grid_endpoints():
+    # reference test/unit/tests-execmodel.cpp:44-61
+    e = default_grid(100, 0.5, 10.0)
+    assert e[0] == 0.5 and e[-1] == 10.0 and e[1] > e[0] and e.size == 101
+
+
+def test_kerr_rms(oracle):
+    assert abs(oracle.lib.orc_kerr_rms(0.0) - 6.0) < 1e-12
+    assert abs(oracle.lib.orc_kerr_rms(0.998) - 1.2369706551751847) < 1e-9
+    assert abs(oracle.lib.orc_kerr_rms(-0.998) - 8.994376) < 1e-5
+
+
+def test_fft_convolution_normalisation(oracle):
+    # reference test/unit/test-stdfunctions.cpp:253-298: the convolution keeps the 0.01-1000 keV sum
+    e = oracle.conv_grid()
+    emid = 0.5 * (e[1:] + e[:-1])
+    xill = emid ** -2.0 * np.exp(-emid / 300.0) * np.diff(e)
+    xill[(e[:-1] < 0.08) | (e[1:] > 900)] = 0.0
+    rel = np.exp(-0.5 * ((np.log(emid) - np.log(0.9)) / 0.1) ** 2)
+    band = (e[:-1] >= 0.01) & (e[1:] < 1000.0)
+    rel /= rel[band].sum()
+    out = oracle.fft_conv(xill, rel)
+    assert abs(out[band].sum() - xill[band].sum()) < 1e-8 * xill[band].sum()
+    rel2 = rel.copy()
+    rel2[1000] = 1000.0
+    out2 = oracle.fft_conv(xill, rel2)
+    assert abs(out2[band].sum() - xill[band].sum()) > 1e-8 * xill[band].sum()
+
+
+def test_model_database(oracle):
+    counts = dict(relline=10, relconv=8, relline_lp=10, relconv_lp=9, relxill=13, relxilllp=14, relxillCp=14,
+                  relxilllpCp=17)
+    for m, n in counts.items():
+        assert oracle.num_params(m) == n
+    assert oracle.default_params("relxilllp")[10] == 300.0
+
+
+# ---------------------------------------------------------------- golden vectors (from the unmodified reference)
+@pytest.mark.parametrize("model", MODELS)
+def test_oracle_vs_golden(oracle, model):
+    g = np.load(GOLDEN)
+    e = g["energy"]
+    P, F = g[f"{model}_params"], g[f"{model}_flux"]
+    oracle.set_num_zones(None)
+    for p, f in zip(P, F):
+        if model.startswith("relconv"):
+            got = oracle.eval_conv(model, e, p, g["conv_input"])
+        else:
+            got = oracle.eval(model, e, p)
+        assert relerr(got, f) < 1e-8, (model, p)
+
+
+@pytest.mark.parametrize("model", ["relxilllp", "relxilllpCp"])
+def test_oracle_vs_golden_50_zones(oracle, model):
+    g = np.load(GOLDEN)
+    oracle.set_num_zones(50)
+    try:
+        for p, f in zip(g[f"{model}_z50_params"], g[f"{model}_z50_flux"]):
+            assert relerr(oracle.eval(model, g["energy"], p), f) < 1e-8
+    finally:
+        oracle.set_num_zones(None)
+
+
+def test_golden_tables_match(table_dir):
+    import hashlib
+    from relxill_b200.tables import synth
+    h = hashlib.sha256()
+    for key in ("rel", "lp", "xill", "xillcp", "rrad"):
+        with open(os.path.join(table_dir, synth.FILES[key]), "rb") as f:
+            h.update(f.read())
+    assert h.hexdigest() == str(np.load(GOLDEN)["table_digest"]), "synthetic tables changed: regenerate the golden file"
+
+
+# ---------------------------------------------------------------- fresh runs of the unmodified reference
+@pytest.mark.parametrize("model", MODELS)
+def test_oracle_vs_reference_random(oracle, ref, model):
+    e = default_grid(1200)
+    P = sample_params(model, 3, seed=31 + len(model))
+    conv_in = np.exp(-0.5 * ((np.log(0.5 * (e[1:] + e[:-1])) - np.log(6.4)) / 0.03) ** 2) + 1e-3
+    ref.set_num_zones(None)
+    oracle.set_num_zones(None)
+    for p in P:
+        if model.startswith("relconv"):
+            a, b = oracle.eval_conv(model, e, p, conv_in), ref.eval_conv(model, e, p, conv_in)
+        else:
+            a, b = oracle.eval(model, e, p), ref.eval(model, e, p)
+        assert relerr(a, b) < 1e-8, (model, p)
+
+
+@pytest.mark.parametrize("model", ["relxill", "relxilllp", "relxilllpCp"])
+def test_oracle_stages_vs_reference(oracle, ref, model):
+    ref.set_num_zones(None)
+    oracle.set_num_zones(None)
+    for p in sample_params(model, 2, seed=5):
+        a, b = oracle.stages(model, p), ref.stages(model, p)
+        assert a["nz"] == b["nz"]
+        np.testing.assert_array_equal(a["zone"], b["zone"])
+        for k in ("lxi", "dens", "ect", "eshift", "normch", "corr_flux", "corr_gshift", "emis2", "dist"):
+            np.testing.assert_allclose(a[k], b[k], rtol=1e-11, atol=0, err_msg=k)
+        assert relerr(a["relflux"], b["relflux"]) < 1e-11
+        assert relerr(a["xill"], b["xill"]) < 1e-11
+        assert relerr(a["total"], b["total"]) < 1e-8
+        sa, sb = oracle.syspar(model, p), ref.syspar(model, p)
+        for k in ("re", "gmin", "gmax", "trff", "cosne", "del_emit", "del_inc"):
+            np.testing.assert_allclose(sa[k], sb[k], rtol=1e-13, atol=0, err_msg=k)
+
+
+def test_nthcomp_vs_reference(oracle, ref):
+    e = default_grid(500)
+    for gam, kte, z in [(2.0, 60.0, 0.0), (1.4, 5.0, 0.3), (3.2, 350.0, 1.5)]:
+        np.testing.assert_allclose(oracle.nthcomp(e, gam, kte, z), ref.nthcomp(e, gam, kte, z), rtol=1e-12)
