@@ -204,9 +204,6 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st)
     const long nc = std::min(S.cap, b->n - c0);
     const VPar *vps = b->d_vps + c0;
     double *out = d_flux + (size_t) c0 * b->n_flux;
-    tm.begin();
-    CK(cudaMemsetAsync(S.relflux, 0, (size_t) nc * S.nz_cap * S.ne_line_cap * sizeof(double), st));
-    tm.end(KF_MEMSET, false);
     tm.begin(); launch_syspar(vps, T, S, nc, 1, st); tm.end(KF_SYSPAR);
     if (relxill) {
       tm.begin(); launch_zone(vps, T, S, nc, st); tm.end(KF_ZONE);
@@ -217,10 +214,10 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st)
       tm.begin(); launch_dist(vps, T, S, nc, n_incl, econv[0], econv[NCONV], st); tm.end(KF_DIST);
     }
     if (m.type == T_LINE) {
-      tm.begin(); launch_line(vps, T, S, nc, b->d_energy, b->n_flux, 1, st); tm.end(KF_LINE);
+      tm.begin(); launch_line(vps, T, S, nc, b->d_energy, b->n_flux, 1, 1, st); tm.end(KF_LINE);
       tm.begin(); launch_linefinish(vps, S, nc, b->n_flux, out, st); tm.end(KF_FINISH);
     } else {
-      tm.begin(); launch_line(vps, T, S, nc, T.econv, NCONV, 0, st); tm.end(KF_LINE);
+      tm.begin(); launch_line(vps, T, S, nc, T.econv, NCONV, 0, relxill ? b->nz_max : 1, st); tm.end(KF_LINE);
       if (relxill) {
         tm.begin(); launch_xill(vps, T, S, nc, which, b->nz_max, st); tm.end(KF_XILL);
         tm.begin(); launch_conv(vps, T, S, nc, b->d_energy, b->n_flux, out, E.d_total, which, 0, st); tm.end(KF_CONV);
@@ -283,6 +280,10 @@ relxill_b200_batch *relxill_b200_prepare(const char *model, const double *energy
   if (!m) { set_err(std::string("unknown model ") + model); return nullptr; }
   if (n_vec < 1 || n_flux < 1) { set_err("empty batch or energy grid"); return nullptr; }
   if (m->prim == PRIM_NTHCOMP) { set_err("nthcomp models are not implemented on the device yet"); return nullptr; }
+  if (m->type == T_LINE && n_flux > line_max_bins()) {
+    set_err("line models: energy grids above " + std::to_string(line_max_bins()) + " bins are not supported yet");
+    return nullptr;
+  }
   // tables this flavour needs; returning radiation can be switched per vector -> load if the table exists
   bool want_rr = (m->irrad == EMIS_LP) || E.cfg.env_returnrad == 1;
   std::string err = E.tables->require(m->irrad == EMIS_LP, false, m->type == T_RELXILL ? m->prim : PRIM_NONE);

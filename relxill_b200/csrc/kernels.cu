@@ -21,105 +21,10 @@
 #include <cstdio>
 
 #include "common.h"
+#include "devutil.cuh"
 #include "kernels.h"
 
 namespace rx {
-
-#define PI 3.14159265358979323846
-#define GFAC_H 5e-3
-
-// ---------------------------------------------------------------------------------- device helpers
-__device__ __forceinline__ double lin1d(double f, double lo, double hi) { return f * hi + (1.0 - f) * lo; }
-
-__device__ __forceinline__ double lin2d_f(double f1, double f2, float r11, float r12, float r21, float r22) {
-  return (1.0 - f1) * (1.0 - f2) * r11 + (f1) * (1.0 - f2) * r12 + (1.0 - f1) * (f2) * r21 + (f1) * (f2) * r22;
-}
-
-// arr ascending: k with arr[k] <= val < arr[k+1], clamped to [0, n-2]  (src/relutility.c:135-171)
-template <class T> __device__ __forceinline__ int bsearch_asc(const T *arr, int n, T val) {
-  int klo = 0, khi = n - 1;
-  while (khi - klo > 1) {
-    const int k = (khi + klo) >> 1;
-    if (arr[k] > val) khi = k; else klo = k;
-  }
-  return klo;
-}
-// arr descending (src/relutility.c:195-211)
-__device__ __forceinline__ int bsearch_desc(const double *arr, int n, double val) {
-  int klo = 0, khi = n - 1;
-  while (khi - klo > 1) {
-    const int k = (khi + klo) >> 1;
-    if (arr[k] < val) khi = k; else klo = k;
-  }
-  return klo;
-}
-// number of entries of ascending arr[0..n) that are <= val
-__device__ __forceinline__ int count_le_asc(const double *arr, int n, double val) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int m = (lo + hi) >> 1;
-    if (arr[m] <= val) lo = m + 1; else hi = m;
-  }
-  return lo;
-}
-// number of entries of descending arr[0..n) that are > val
-__device__ __forceinline__ int count_gt_desc(const double *arr, int n, double val) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int m = (lo + hi) >> 1;
-    if (arr[m] > val) lo = m + 1; else hi = m;
-  }
-  return lo;
-}
-
-__device__ __forceinline__ double trapez_single(const double *re, int i, int nr) {  // src/relutility.c:233-244
-  double dr;
-  if (i == 0) dr = 0.5 * (re[i] - re[i + 1]);
-  else if (i == nr - 1) dr = 0.5 * (re[i - 1] - re[i]);
-  else dr = 0.5 * (re[i - 1] - re[i + 1]);
-  return re[i] * dr * PI;
-}
-
-__device__ __forceinline__ double doppler_factor(double del, double bet) {  // src/Relphysics.cpp:158-160
-  return sqrt(1.0 - bet * bet) / (1.0 + bet * cos(del));
-}
-__device__ __forceinline__ double relat_abberation(double del, double beta) {  // src/Relphysics.cpp:127-129
-  return acos((cos(del) - beta) / (1 - beta * cos(del)));
-}
-__device__ double gi_potential_lp(double r, double a, double h, double bet, double del) {  // src/Relphysics.cpp:163-207
-  const double ut_d = ((r * sqrt(r) + a) / (sqrt(r) * sqrt(r * r - 3 * r + 2 * a * sqrt(r))));
-  const double ut_h = sqrt((h * h + a * a) / (h * h - 2 * h + a * a));
-  const double gi = ut_d / ut_h;
-  if (fabs(bet) < 1e-6) return gi;
-  const double gam = 1.0 / sqrt(1.0 - bet * bet);
-  const double sign = (del > PI / 2) ? -1.0 : 1.0;
-  const double delta_eq = h * h - 2 * h + a * a;
-  const double sd = sin(del);
-  const double hh = (h * h + a * a);
-  const double q2 = (sd * sd) * ((hh * hh) / delta_eq) - a * a;
-  double beta_fac = sqrt(hh * hh - delta_eq * (q2 + a * a));
-  beta_fac = gam * (1.0 + sign * beta_fac / (h * h + a * a) * bet);
-  return gi / beta_fac;
-}
-__device__ __forceinline__ double density_ss73_zone_a(double radius, double rms) {  // src/Relphysics.cpp:123-125
-  const double t = (1 - sqrt(rms / radius));
-  return pow((radius / rms), (3. / 2)) * (1.0 / (t * t));
-}
-
-// fixed-order block reduction (deterministic); all threads must call; result broadcast
-template <int NT> __device__ double block_sum(double v, double *red) {
-  const int t = threadIdx.x;
-  red[t] = v;
-  __syncthreads();
-#pragma unroll
-  for (int s = NT / 2; s > 0; s >>= 1) {
-    if (t < s) red[t] += red[t + s];
-    __syncthreads();
-  }
-  const double r = red[0];
-  __syncthreads();
-  return r;
-}
 
 // ---------------------------------------------------------------------------------- k_syspar
 // Replaces interpol_relTable (src/Relprofile.cpp:141-303, the parts that do not need the g* axis),
@@ -752,227 +657,6 @@ __global__ void __launch_bounds__(256) k_dist(const VPar *__restrict__ vps, DevT
   }
 }
 
-// ---------------------------------------------------------------------------------- k_line
-// Relline profile: calc_relline_profile + integ_relline_bin + int_edge + int_romb + romberg_integration +
-// relb_func (src/Relprofile.cpp:489-726,835-905) and the division by the bin energy of
-// renorm_relline_profile (:757-762).
-//
-// Bin-stationary mapping: thread = one energy bin, loop over the 1000 radii (descending radius = the
-// reference's loop order), accumulating in a register; a zone change flushes the register to
-// flux[zone][bin].  No atomics, no cross-thread reduction, reference summation order.
-struct LineRad {        // per-radius scalars staged in shared memory
-  double gmin, gmax, del_g, emis, weight;
-  int zone, active;
-};
-constexpr int LINE_TILE = 8;
-
-struct RelbCtx {
-  double gmin, gmax, del_g, emis;
-  const double2 *trff;   // [NG] {branch 0, branch 1}
-  const double2 *cosne;
-  const double *gstar;
-  int limb;
-};
-
-__device__ __forceinline__ double relb_func(double eg, int k, const RelbCtx &c) {  // src/Relprofile.cpp:489-521
-  const double egstar = (eg - c.gmin) * c.del_g;
-  // bracket in the (uniform up to rounding) g* grid: same result as binary_search(gstar, 40, egstar)
-  int ind = (int) ((egstar - GFAC_H) * ((NG - 1) / (1.0 - 2 * GFAC_H)));
-  ind = ind < 0 ? 0 : (ind > NG - 2 ? NG - 2 : ind);
-  while (ind > 0 && c.gstar[ind] > egstar) ind--;
-  while (ind < NG - 2 && c.gstar[ind + 1] <= egstar) ind++;
-  const double inte = (egstar - c.gstar[ind]) / (c.gstar[ind + 1] - c.gstar[ind]);
-  const double inte1 = 1.0 - inte;
-  const double2 t0 = c.trff[ind], t1 = c.trff[ind + 1];
-  const double ftrf = inte * (k ? t0.y : t0.x) + inte1 * (k ? t1.y : t1.x);
-  const double val = (eg * eg * eg) / ((c.gmax - c.gmin) * sqrt(egstar - egstar * egstar)) * ftrf * c.emis;
-  if (c.limb == 0) return val;
-  const double2 c0 = c.cosne[ind], c1 = c.cosne[ind + 1];
-  const double fmu0 = inte * (k ? c0.y : c0.x) + inte1 * (k ? c1.y : c1.x);
-  double limb = 1.0;
-  if (c.limb == 1) limb = (1.0 + 2.06 * fmu0);
-  else if (c.limb == 2) limb = log(1.0 + 1.0 / fmu0);
-  return val * limb;
-}
-
-__device__ double romberg(double a, double b, int k, const RelbCtx &c) {  // src/Relprofile.cpp:524-579
-  const double prec = 0.02;
-  double obtprec = 1.0;
-  double prev[7], cur[7];
-  int niter = 0;
-  const double r0 = relb_func(a, k, c);
-  const double rb = relb_func(b, k, c);
-  const double ta = (r0 + rb) / 2.0;
-  double pas = b - a;
-  prev[0] = ta * pas;
-  double last_diag = prev[0];
-  while ((obtprec > prec) && (niter <= 5)) {
-    niter++;
-    pas = pas / 2.0;
-    double s = ta;
-    const int npts = (1 << niter) - 1;
-    for (int ii = 1; ii <= npts; ii++) s += relb_func(a + pas * ii, k, c);
-    cur[0] = s * pas;
-    double r = 1.0;
-#pragma unroll
-    for (int ii = 1; ii <= 6; ii++) {
-      if (ii <= niter) {
-        r *= 4.0;
-        cur[ii] = (r * cur[ii - 1] - prev[ii - 1]) / (r - 1.0);
-      }
-    }
-    double diag = cur[0];
-#pragma unroll
-    for (int ii = 1; ii <= 6; ii++) if (ii == niter) diag = cur[ii];
-    obtprec = fabs(diag - last_diag) / diag;
-    last_diag = diag;
-#pragma unroll
-    for (int ii = 0; ii < 7; ii++) prev[ii] = cur[ii];
-  }
-  return last_diag;
-}
-
-__device__ __forceinline__ double gstar2ener(double g, double gmin, double gmax) { return (g * (gmax - gmin) + gmin) * 1.0; }
-
-__device__ double int_edge(double blo, double bhi, const RelbCtx &c) {  // src/Relprofile.cpp:585-621 (h = GFAC_H)
-  double hex, lo, hi;
-  if (blo <= 0.5) { hex = GFAC_H; lo = blo; hi = bhi; }
-  else { hex = 1.0 - GFAC_H; lo = 1.0 - bhi; hi = 1.0 - blo; }
-  double norm = 0.0;
-  const double eh = gstar2ener(hex, c.gmin, c.gmax);
-  norm = norm + relb_func(eh, 0, c);
-  norm = norm + relb_func(eh, 1, c);
-  norm = norm * sqrt(GFAC_H);
-  return 2 * norm * (sqrt(hi) - sqrt(lo)) * 1.0 * (c.gmax - c.gmin);
-}
-
-__device__ double integ_relline_bin(const RelbCtx &c, double rlo0, double rhi0) {  // src/Relprofile.cpp:650-726
-  double flu = 0.0;
-  double gblo = (rlo0 / 1.0 - c.gmin) * c.del_g;
-  if (gblo < 0.0) gblo = 0.0; else if (gblo > 1.0) gblo = 1.0;
-  double gbhi = (rhi0 / 1.0 - c.gmin) * c.del_g;
-  if (gbhi < 0.0) gbhi = 0.0; else if (gbhi > 1.0) gbhi = 1.0;
-  if (gbhi == 0) return 0.0;
-  double rlo = rlo0, rhi = rhi0, hlo, hhi;
-  if (gblo <= GFAC_H) {
-    hlo = gblo;
-    hhi = GFAC_H;
-    rlo = gstar2ener(GFAC_H, c.gmin, c.gmax);
-    if (gbhi <= GFAC_H) { hhi = gbhi; rlo = -1.0; }
-    flu = flu + int_edge(hlo, hhi, c);
-  }
-  if (gbhi >= (1.0 - GFAC_H)) {
-    hhi = gbhi;
-    hlo = 1.0 - GFAC_H;
-    rhi = gstar2ener(1 - GFAC_H, c.gmin, c.gmax);
-    if (gblo >= (1.0 - GFAC_H)) { hlo = gblo; rhi = -1.0; }
-    flu = flu + int_edge(hlo, hhi, c);
-  }
-  if ((rhi >= 0) && (rlo >= 0)) {
-    double f2 = 0.0;
-    if (rlo >= 1.0 * 0.95) {  // src/Relprofile.cpp:628-647
-      f2 += romberg(rlo, rhi, 0, c);
-      f2 += romberg(rlo, rhi, 1, c);
-    } else {
-      const double mid = (rhi + rlo) / 2.0;
-      f2 += relb_func(mid, 0, c) * (rhi - rlo);
-      f2 += relb_func(mid, 1, c) * (rhi - rlo);
-    }
-    flu = flu + f2;
-  }
-  return flu;
-}
-
-// grid_mode 0: the fixed convolution grid; 1: the caller's grid shifted by (1+z) and divided by lineE
-// per vector (XspecSpectrum::shift_energy_grid_redshift / _1keV, src/XspecSpectrum.h:61-76)
-__device__ __forceinline__ double line_edge(const double *egrid, int j, int grid_mode, double z, double lineE) {
-  double e = egrid[j];
-  if (grid_mode) {
-    if (z > 0) e *= (1 + z);
-    e /= lineE;
-  }
-  return e;
-}
-
-__global__ void __launch_bounds__(256) k_line(const VPar *__restrict__ vps, DevTables T, Scratch S,
-                                              const double *__restrict__ egrid, int n_ener, int grid_mode,
-                                              int ne_stride, int nz_stride) {
-  __shared__ double2 s_trff[LINE_TILE][NG];
-  __shared__ double2 s_cosne[LINE_TILE][NG];
-  __shared__ LineRad s_rad[LINE_TILE];
-  __shared__ double s_gstar[NG];
-  __shared__ double s_re[NR];
-  const int v = blockIdx.y, t = threadIdx.x;
-  if (S.status[v] != ST_OK) return;
-  const VPar &vp = vps[v];
-  const int j = blockIdx.x * 256 + t;
-  const bool in_grid = j < n_ener;
-  const double e_first = line_edge(egrid, 0, grid_mode, vp.z, vp.lineE);
-  const double e_last = line_edge(egrid, n_ener, grid_mode, vp.z, vp.lineE);
-  const int jlo_b = blockIdx.x * 256, jhi_b = min(jlo_b + 256, n_ener);
-  {  // whole block outside the line?  (flux was zero-filled)
-    const double blo = line_edge(egrid, jlo_b, grid_mode, vp.z, vp.lineE);
-    const double bhi = line_edge(egrid, jhi_b, grid_mode, vp.z, vp.lineE);
-    if (bhi <= S.glim[2 * v] || blo > S.glim[2 * v + 1]) return;
-  }
-  const double elo = in_grid ? line_edge(egrid, j, grid_mode, vp.z, vp.lineE) : 0.0;
-  const double ehi = in_grid ? line_edge(egrid, j + 1, grid_mode, vp.z, vp.lineE) : 0.0;
-  if (t < NG) s_gstar[t] = T.gstar[t];
-  for (int i = t; i < NR; i += 256) s_re[i] = S.re[(size_t) v * NR + i];
-  __syncthreads();
-  const double2 *g_trff = reinterpret_cast<const double2 *>(S.trff) + (size_t) v * NR * NG;
-  const double2 *g_cosne = reinterpret_cast<const double2 *>(S.cosne) + (size_t) v * NR * NG;
-  double *flux = S.relflux + (size_t) v * nz_stride * ne_stride;
-  const double inv_emid = 0.5 * (elo + ehi);
-  double acc = 0.0;
-  int cur_zone = -1;
-  const int limb = vp.limb;
-  for (int i0 = 0; i0 < NR; i0 += LINE_TILE) {
-    __syncthreads();
-    // stage a tile of radii
-    for (int q = t; q < LINE_TILE * NG; q += 256) {
-      const int r = q / NG, g = q - r * NG;
-      s_trff[r][g] = g_trff[(size_t) (i0 + r) * NG + g];
-      if (limb != 0) s_cosne[r][g] = g_cosne[(size_t) (i0 + r) * NG + g];
-    }
-    if (t < LINE_TILE) {
-      const int i = i0 + t;
-      LineRad lr;
-      lr.gmin = S.gmin[(size_t) v * NR + i];
-      lr.gmax = S.gmax[(size_t) v * NR + i];
-      lr.del_g = 1. / (lr.gmax - lr.gmin);
-      lr.emis = S.emis[(size_t) v * NR + i];
-      lr.weight = trapez_single(s_re, i, NR) / 2;
-      lr.zone = S.izone[(size_t) v * NR + i];
-      lr.active = ((lr.gmax > e_first) && (lr.gmin < e_last)) ? 1 : 0;
-      s_rad[t] = lr;
-    }
-    __syncthreads();
-    if (!in_grid) continue;
-#pragma unroll 1
-    for (int r = 0; r < LINE_TILE; r++) {
-      const LineRad lr = s_rad[r];
-      if (!lr.active) continue;
-      double egmin = lr.gmin, egmax = lr.gmax;
-      if (egmin < e_first) egmin = e_first;
-      if (egmax > e_last) egmax = e_last;
-      // bin j is inside [ielo, iehi] of the reference's two binary searches
-      if (!(ehi > egmin) || !(elo <= egmax)) continue;
-      if (lr.zone != cur_zone) {
-        if (cur_zone >= 0) flux[(size_t) cur_zone * ne_stride + j] = acc / inv_emid;
-        acc = 0.0;
-        cur_zone = lr.zone;
-      }
-      RelbCtx c;
-      c.gmin = lr.gmin; c.gmax = lr.gmax; c.del_g = lr.del_g; c.emis = lr.emis;
-      c.trff = s_trff[r]; c.cosne = s_cosne[r]; c.gstar = s_gstar; c.limb = limb;
-      const double tmp = integ_relline_bin(c, elo, ehi);
-      acc += tmp * lr.weight;
-    }
-  }
-  if (in_grid && cur_zone >= 0) flux[(size_t) cur_zone * ne_stride + j] = acc / inv_emid;
-}
-
 // ---------------------------------------------------------------------------------- k_linefinish
 // renorm_relline_profile for one-zone line models (src/Relprofile.cpp:749-781) + copy to the output
 __global__ void __launch_bounds__(256) k_linefinish(const VPar *__restrict__ vps, Scratch S, int n_ener, int ne_stride,
@@ -1250,6 +934,8 @@ __global__ void __launch_bounds__(CONV_NT) k_conv(const VPar *__restrict__ vps, 
 // ---------------------------------------------------------------------------------- launchers
 static size_t g_smem_sys = 0, g_smem_zone = 0;
 
+int line_kernel_init();
+
 int kernels_init() {
   g_smem_sys = sizeof(SysSmem);
   g_smem_zone = sizeof(ZoneSmem);
@@ -1260,6 +946,7 @@ int kernels_init() {
   if (e != cudaSuccess) return 1;
   e = cudaFuncSetAttribute(k_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ((NR * MAX_INCL + NR + 4) * sizeof(double)));
   if (e != cudaSuccess) return 1;
+  if (line_kernel_init() != 0) return 1;
   e = cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ((4 * NCONV + CONV_NT) * sizeof(double)));
   if (e != cudaSuccess) return 1;
   return 0;
@@ -1279,11 +966,6 @@ void launch_dist(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
                  double e_last, cudaStream_t st) {
   const size_t sm = ((size_t) NR * n_incl + NR + 4) * sizeof(double);
   k_dist<<<(unsigned) n, 256, sm, st>>>(vps, T, S, n_incl, e_first, e_last);
-}
-void launch_line(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *egrid, int n_ener,
-                 int grid_mode, cudaStream_t st) {
-  dim3 grid((n_ener + 255) / 256, (unsigned) n);
-  k_line<<<grid, 256, 0, st>>>(vps, T, S, egrid, n_ener, grid_mode, S.ne_line_cap, S.nz_cap);
 }
 void launch_linefinish(const VPar *vps, const Scratch &S, long n, int n_ener, double *out, cudaStream_t st) {
   k_linefinish<<<(unsigned) n, 256, 0, st>>>(vps, S, n_ener, S.ne_line_cap, S.nz_cap, out);

@@ -14,7 +14,8 @@ void launch_fine(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
 void launch_dist(const VPar *vps, const DevTables &T, const Scratch &S, long n, int n_incl, double e_first,
                  double e_last, cudaStream_t st);
 void launch_line(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *egrid, int n_ener,
-                 int grid_mode, cudaStream_t st);
+                 int grid_mode, int nz_max, cudaStream_t st);
+int line_max_bins();  // largest energy grid the line kernel handles in one pass
 void launch_linefinish(const VPar *vps, const Scratch &S, long n, int n_ener, double *out, cudaStream_t st);
 void launch_xill(const VPar *vps, const DevTables &T, const Scratch &S, long n, int which, int nz_max, cudaStream_t st);
 void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,

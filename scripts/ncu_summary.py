@@ -1,0 +1,26 @@
+"""Prints the metrics we track from an .ncu-rep (run in the CPU container)."""
+import csv, subprocess, sys
+rep = sys.argv[1]
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr, units = rows[0], rows[1]
+KEYS = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__occupancy_limit",
+        "launch__grid_size", "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.sum",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+        "smsp__inst_executed.sum", "smsp__average_warps_issue_stalled", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "sm__inst_executed_pipe_xu.avg.pct", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+        "smsp__cycles_active.avg", "sm__cycles_elapsed.max"]
+for r in rows[2:]:
+    print("-" * 60)
+    for h, u, v in zip(hdr, units, r):
+        if any(h.startswith(k) or k in h for k in KEYS):
+            if "issue_stalled" in h and "per_issue_active" not in h:
+                continue
+            if "pipe_xu" in h and "avg.pct_of_peak_sustained_active" not in h:
+                continue
+            if h.endswith(".max") or h.endswith(".min") or ".max." in h or ".min." in h or ".sum." in h and "bytes" not in h:
+                continue
+            print(f"{h:85s} {u:12s} {v}")
