@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -13,6 +14,8 @@
 #include <mutex>
 #include <set>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/relxill_b200.h"
@@ -56,8 +59,31 @@ struct Engine {
   size_t d_io_cap = 0;
   long max_chunk = 4096;
   bool profiling = false;
+  // device buffers recycled between batches (cudaMalloc/cudaFree synchronise and cost milliseconds)
+  std::vector<std::pair<size_t, void *>> pool;
 };
 Engine g_eng;
+
+void *pool_get(Engine &E, size_t bytes) {
+  for (size_t i = 0; i < E.pool.size(); i++) {
+    if (E.pool[i].first >= bytes && E.pool[i].first <= 2 * bytes + 4096) {
+      void *p = E.pool[i].second;
+      E.pool.erase(E.pool.begin() + i);
+      return p;
+    }
+  }
+  void *d = nullptr;
+  if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
+  return d;
+}
+void pool_put(Engine &E, void *p, size_t bytes) {
+  if (!p) return;
+  if (E.pool.size() >= 8) {
+    cudaFree(E.pool.front().second);
+    E.pool.erase(E.pool.begin());
+  }
+  E.pool.emplace_back(bytes, p);
+}
 
 void free_scratch(Engine &E) {
   for (void *p : E.scratch_allocs) cudaFree(p);
@@ -152,6 +178,7 @@ struct relxill_b200_batch {
   std::vector<int> status;
   VPar *d_vps = nullptr;
   double *d_energy = nullptr;
+  size_t vps_bytes = 0, energy_bytes = 0;
   long launches = 0;
   long last_chunk0 = 0, last_chunk_n = 0;
   double kt_ms[KF_COUNT] = {0};
@@ -251,6 +278,8 @@ void relxill_b200_shutdown(void) {
   if (g_eng.d_io) cudaFree(g_eng.d_io);
   g_eng.d_io = nullptr;
   g_eng.d_io_cap = 0;
+  for (auto &pr : g_eng.pool) cudaFree(pr.second);
+  g_eng.pool.clear();
   delete g_eng.tables;
   g_eng.tables = nullptr;
   g_eng.inited = false;
@@ -299,17 +328,35 @@ relxill_b200_batch *relxill_b200_prepare(const char *model, const double *energy
   b->vps.resize(n_vec);
   b->status.assign(n_vec, 0);
   const std::vector<double> &sp = E.tables->rr_spins();
+  {  // host-side interpretation, spread over a few threads for large batches
+    const int nthr = (int) std::max<long>(1, std::min<long>({(long) std::thread::hardware_concurrency(), 16L, n_vec / 256}));
+    auto work = [&](long lo, long hi) {
+      for (long i = lo; i < hi; i++)
+        interpret_params(*m, params + (size_t) i * m->npar, E.cfg, sp.empty() ? nullptr : sp.data(), (int) sp.size(), b->vps[i]);
+    };
+    if (nthr <= 1) {
+      work(0, n_vec);
+    } else {
+      std::vector<std::thread> th;
+      for (int k = 0; k < nthr; k++) th.emplace_back(work, n_vec * k / nthr, n_vec * (k + 1) / nthr);
+      for (auto &x : th) x.join();
+    }
+  }
   for (long i = 0; i < n_vec; i++) {
-    interpret_params(*m, params + (size_t) i * m->npar, E.cfg, sp.empty() ? nullptr : sp.data(), (int) sp.size(), b->vps[i]);
     if (b->vps[i].status == ST_OK) {
       b->nz_max = std::max(b->nz_max, b->vps[i].nz);
       if (b->vps[i].do_corr) b->any_corr = true;
     }
   }
-  if (cudaMalloc((void **) &b->d_vps, n_vec * sizeof(VPar)) != cudaSuccess ||
-      cudaMalloc((void **) &b->d_energy, (n_flux + 1) * sizeof(double)) != cudaSuccess) {
+  b->vps_bytes = n_vec * sizeof(VPar);
+  b->energy_bytes = (n_flux + 1) * sizeof(double);
+  b->d_vps = (VPar *) pool_get(E, b->vps_bytes);
+  b->d_energy = (double *) pool_get(E, b->energy_bytes);
+  if (!b->d_vps || !b->d_energy) {
     set_err("out of device memory (batch)");
-    relxill_b200_free_batch(b);
+    pool_put(E, b->d_vps, b->vps_bytes);
+    pool_put(E, b->d_energy, b->energy_bytes);
+    delete b;
     return nullptr;
   }
   cudaMemcpy(b->d_vps, b->vps.data(), n_vec * sizeof(VPar), cudaMemcpyHostToDevice);
@@ -319,8 +366,11 @@ relxill_b200_batch *relxill_b200_prepare(const char *model, const double *energy
 
 void relxill_b200_free_batch(relxill_b200_batch *b) {
   if (!b) return;
-  if (b->d_vps) cudaFree(b->d_vps);
-  if (b->d_energy) cudaFree(b->d_energy);
+  {
+    std::lock_guard<std::mutex> lk(g_eng.mu);
+    pool_put(g_eng, b->d_vps, b->vps_bytes);
+    pool_put(g_eng, b->d_energy, b->energy_bytes);
+  }
   delete b;
 }
 
@@ -366,7 +416,12 @@ int relxill_batch_eval_device(const char *model, const double *energy, int n_flu
 
 int relxill_batch_eval(const char *model, const double *energy, int n_flux, const double *params, long n_vec,
                        double *flux, int *status) {
+  static const bool dbg = getenv("RELXILL_B200_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t0 = now();
   relxill_b200_batch *b = relxill_b200_prepare(model, energy, n_flux, params, n_vec);
+  const auto t1 = now();
   if (!b) {
     if (flux && n_vec > 0 && n_flux > 0) memset(flux, 0, sizeof(double) * (size_t) n_vec * n_flux);
     if (status) for (long i = 0; i < n_vec; i++) status[i] = ST_BAD_PARAM;
@@ -374,19 +429,21 @@ int relxill_batch_eval(const char *model, const double *energy, int n_flux, cons
   }
   Engine &E = g_eng;
   const size_t need = (size_t) n_vec * n_flux;
+  bool io_ok = true;
   {
     std::lock_guard<std::mutex> lk(E.mu);
     if (E.d_io_cap < need) {
       if (E.d_io) cudaFree(E.d_io);
       E.d_io = nullptr;
       E.d_io_cap = 0;
-      if (cudaMalloc((void **) &E.d_io, need * sizeof(double)) != cudaSuccess) {
-        set_err("out of device memory (output staging)");
-        relxill_b200_free_batch(b);
-        return -2;
-      }
-      E.d_io_cap = need;
+      if (cudaMalloc((void **) &E.d_io, need * sizeof(double)) != cudaSuccess) io_ok = false;
+      else E.d_io_cap = need;
     }
+  }
+  if (!io_ok) {
+    set_err("out of device memory (output staging)");
+    relxill_b200_free_batch(b);
+    return -2;
   }
   if (b->m->type == T_CONV) {
     // convolution models: flux is the input spectrum; a non-positive total is rejected (src/LocalModel.cpp:84-86)
@@ -398,13 +455,20 @@ int relxill_batch_eval(const char *model, const double *energy, int n_flux, cons
     cudaMemcpy(b->d_vps, b->vps.data(), n_vec * sizeof(VPar), cudaMemcpyHostToDevice);
     cudaMemcpy(E.d_io, flux, need * sizeof(double), cudaMemcpyHostToDevice);
   }
+  const auto t2 = now();
   int rc = relxill_b200_run(b, E.d_io, nullptr);
+  if (dbg) cudaDeviceSynchronize();
+  const auto t3 = now();
   if (rc == 0) {
     cudaError_t e = cudaMemcpy(flux, E.d_io, need * sizeof(double), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { set_err(std::string("D2H copy: ") + cudaGetErrorString(e)); rc = -2; }
   }
+  const auto t4 = now();
   if (status) for (long i = 0; i < n_vec; i++) status[i] = b->status[i];
   relxill_b200_free_batch(b);
+  if (dbg)
+    fprintf(stderr, "relxill_batch_eval timing: prepare %.2f ms, staging %.2f ms, run %.2f ms, D2H %.2f ms, free %.2f ms\n",
+            ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, now()));
   return rc;
 }
 

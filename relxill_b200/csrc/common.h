@@ -90,7 +90,8 @@ struct DevTables {
   const double *ecoarse;    // [NCOARSE+1]
   const unsigned char *coarse_m1, *coarse_m2;  // masks of the two band conditions on the coarse grid
   const double *gstar, *d_gstar;  // [NG]
-  const double *tw_re, *tw_im;    // FFT twiddles exp(-2 pi i k / NCONV), k < NCONV/2
+  const double *tw;               // FFT twiddles exp(-2 pi i m / NCONV), m < NCONV, interleaved (re, im)
+  const double *conv_wr, *conv_wi; // DFT of band/cf, k <= NCONV/2 (frequency-domain band sum of a convolution)
   // nthcomp: arrays that depend only on the photon grid (kT_bb is fixed at 0.05 keV)
   const double *nth_x, *nth_c2, *nth_rel, *nth_x3, *nth_w, *nth_dphdot;
   int nth_jnr, nth_jrel, nth_jmaxth;

@@ -727,33 +727,122 @@ __global__ void __launch_bounds__(256) k_xill(const VPar *__restrict__ vps, DevT
 // ---------------------------------------------------------------------------------- k_conv
 // relxill_convolution_multizone (src/Relxill.cpp:432-482) with fftw_conv_spectrum + calcFFTNormFactor
 // (src/Relbase.cpp:119-213), PrimarySource::add_primary_spectrum (src/PrimarySource.cpp:66-125) and
-// rebin_and_normalize_relxill_for_xspec (src/Relxill.cpp:261-278).  One CTA per vector; the 4096-point
-// FFTs run in shared memory (radix-2, the two real inputs packed into one complex transform).
+// rebin_and_normalize_relxill_for_xspec (src/Relxill.cpp:261-278).  One CTA per vector.
+//
+// FFT work per zone is cut from three transforms (reference) to one:
+//   * the two real inputs (xillver spectrum, rotated line profile) share one complex forward transform;
+//   * the band sum of the convolved zone that the normalisation needs is a linear functional of the
+//     product spectrum, sum_i w_i out_i = sum_k P[k] conj(W[k]) with W = DFT(band/cf) tabulated at
+//     load, so it is taken in the frequency domain and no per-zone inverse transform is needed;
+//   * the normalised product spectra of all zones are accumulated in the frequency domain and one inverse
+//     transform per vector brings the sum back (inverse = forward transform of the conjugate).
+// The transform is a 4096-point radix-8 Stockham autosort FFT in shared memory: 4 passes, one butterfly per
+// thread per pass, padded to keep the stride-8 scatter of the first passes off the same banks.
 constexpr int CONV_NT = 512;
+constexpr int CV_PADN = NCONV + NCONV / 8;
+__device__ __forceinline__ int cv_pad(int i) { return i + (i >> 3); }
 
-__device__ void fft4096(double *xr, double *xi, const double *__restrict__ twr, const double *__restrict__ twi,
-                        double sign) {
-  const int t = threadIdx.x;
-  for (int i = t; i < NCONV; i += CONV_NT) {
-    const int j = (int) (__brev((unsigned) i) >> 20);
-    if (i < j) {
-      double a = xr[i]; xr[i] = xr[j]; xr[j] = a;
-      a = xi[i]; xi[i] = xi[j]; xi[j] = a;
-    }
+struct ConvSmem {
+  double zr[CV_PADN], zi[CV_PADN];
+  double ar[NCONV / 2 + 1], ai[NCONV / 2 + 1];   // accumulated spectrum; reused as the final 4096-bin result
+  double red[4 * (CONV_NT / 32)];
+  double bc[4];
+};
+
+// sums four values over the block (fixed order: shuffle tree inside warps, then over the warps)
+__device__ void block_sum4(double (&v)[4], ConvSmem &sm) {
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+#pragma unroll
+  for (int q = 0; q < 4; q++)
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) sm.red[q * (CONV_NT / 32) + w] = v[q];
   }
   __syncthreads();
-  for (int lg = 1; lg <= 12; lg++) {
-    const int half = 1 << (lg - 1);
-    const int step = NCONV >> lg;
-    for (int b = t; b < NCONV / 2; b += CONV_NT) {
-      const int k = b & (half - 1);
-      const int i = ((b >> (lg - 1)) << lg) + k;
-      const int j = i + half;
-      const double c = __ldg(twr + k * step), s = sign * __ldg(twi + k * step);
-      const double vr = xr[j] * c - xi[j] * s, vi = xr[j] * s + xi[j] * c;
-      const double ur = xr[i], ui = xi[i];
-      xr[i] = ur + vr; xi[i] = ui + vi;
-      xr[j] = ur - vr; xi[j] = ui - vi;
+  if (t < 4) {
+    double s = 0.0;
+    for (int i = 0; i < CONV_NT / 32; i++) s += sm.red[t * (CONV_NT / 32) + i];
+    sm.bc[t] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; q++) v[q] = sm.bc[q];
+}
+
+__device__ __forceinline__ void cmul(double &xr, double &xi, double wr, double wi) {
+  const double a = xr * wr - xi * wi;
+  xi = xr * wi + xi * wr;
+  xr = a;
+}
+
+// 8-point DFT (forward sign), decimation in frequency, outputs in natural order
+__device__ __forceinline__ void fft8(double (&r)[8], double (&i)[8]) {
+  const double h = 0.70710678118654752440;
+  double ar[8], ai[8];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    ar[q] = r[q] + r[q + 4]; ai[q] = i[q] + i[q + 4];
+    ar[q + 4] = r[q] - r[q + 4]; ai[q + 4] = i[q] - i[q + 4];
+  }
+  {  // twiddles w8^1, w8^2 = -i, w8^3 on the odd half
+    double x = ar[5], y = ai[5];
+    ar[5] = (x + y) * h; ai[5] = (y - x) * h;
+    x = ar[6]; y = ai[6];
+    ar[6] = y; ai[6] = -x;
+    x = ar[7]; y = ai[7];
+    ar[7] = (y - x) * h; ai[7] = (-x - y) * h;
+  }
+  double br[8], bi[8];
+#pragma unroll
+  for (int g = 0; g < 8; g += 4) {
+    br[g] = ar[g] + ar[g + 2]; bi[g] = ai[g] + ai[g + 2];
+    br[g + 2] = ar[g] - ar[g + 2]; bi[g + 2] = ai[g] - ai[g + 2];
+    br[g + 1] = ar[g + 1] + ar[g + 3]; bi[g + 1] = ai[g + 1] + ai[g + 3];
+    const double dx = ar[g + 1] - ar[g + 3], dy = ai[g + 1] - ai[g + 3];
+    br[g + 3] = dy; bi[g + 3] = -dx;   // times -i
+  }
+  r[0] = br[0] + br[1]; i[0] = bi[0] + bi[1];
+  r[4] = br[0] - br[1]; i[4] = bi[0] - bi[1];
+  r[2] = br[2] + br[3]; i[2] = bi[2] + bi[3];
+  r[6] = br[2] - br[3]; i[6] = bi[2] - bi[3];
+  r[1] = br[4] + br[5]; i[1] = bi[4] + bi[5];
+  r[5] = br[4] - br[5]; i[5] = bi[4] - bi[5];
+  r[3] = br[6] + br[7]; i[3] = bi[6] + bi[7];
+  r[7] = br[6] - br[7]; i[7] = bi[6] - bi[7];
+}
+
+// in-place forward FFT of the padded arrays; tw[m] = exp(-2 pi i m / 4096); all CONV_NT threads call
+__device__ void fft4096(double *zr, double *zi, const double2 *__restrict__ tw) {
+  const int j = threadIdx.x;
+#pragma unroll 1
+  for (int pass = 0; pass < 4; pass++) {
+    const int ns = 1 << (3 * pass);          // 1, 8, 64, 512
+    const int k = j & (ns - 1);
+    double r[8], im[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int idx = cv_pad(j + q * (NCONV / 8));
+      r[q] = zr[idx];
+      im[q] = zi[idx];
+    }
+    if (pass > 0) {
+      const int mb = k * ((NCONV / 8) >> (3 * pass));   // k * 512 / ns
+#pragma unroll
+      for (int q = 1; q < 8; q++) {
+        const double2 w = __ldg(tw + q * mb);
+        cmul(r[q], im[q], w.x, w.y);
+      }
+    }
+    fft8(r, im);
+    __syncthreads();
+    const int j0 = ((j - k) << 3) + k;       // (j / ns) * ns * 8 + k
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int idx = cv_pad(j0 + q * ns);
+      zr[idx] = r[q];
+      zi[idx] = im[q];
     }
     __syncthreads();
   }
@@ -790,13 +879,9 @@ struct ConvArgs {
   int mode;               // 0 relxill, 1 convolution model (input spectrum in `out`)
 };
 
-__global__ void __launch_bounds__(CONV_NT) k_conv(const VPar *__restrict__ vps, DevTables T, Scratch S, ConvArgs A) {
+__global__ void __launch_bounds__(CONV_NT, 1) k_conv(const VPar *__restrict__ vps, DevTables T, Scratch S, ConvArgs A) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  double *xr = reinterpret_cast<double *>(smraw);
-  double *xi = xr + NCONV;
-  double *acc = xi + NCONV;
-  double *fx = acc + NCONV;    // rebinned xillver spectrum of the zone (needed again for the norm)
-  double *red = fx + NCONV;    // [CONV_NT]
+  ConvSmem &sm = *reinterpret_cast<ConvSmem *>(smraw);
   const int v = blockIdx.x, t = threadIdx.x;
   double *o = A.out + (size_t) v * A.n_flux;
   const VPar &vp = vps[v];
@@ -807,25 +892,17 @@ __global__ void __launch_bounds__(CONV_NT) k_conv(const VPar *__restrict__ vps, 
   const int nz = (A.mode == 0) ? vp.nz : 1;
   const XillDev &X = T.xill[A.which];
   const int i1 = T.conv_i1kev;
-  for (int i = t; i < NCONV; i += CONV_NT) acc[i] = 0.0;
+  const double2 *tw = reinterpret_cast<const double2 *>(T.tw);
+  for (int k = t; k <= NCONV / 2; k += CONV_NT) { sm.ar[k] = 0.0; sm.ai[k] = 0.0; }
   for (int z = 0; z < nz; z++) {
     const double *rel = S.relflux + ((size_t) v * A.nz_stride + z) * A.ne_stride;
-    double part = 0.0;
-    for (int i = t; i < NCONV; i += CONV_NT) part += rel[i];
-    const double srel_all = block_sum<CONV_NT>(part, red);
-    double rscale = 1.0;
-    if (vp.renorm) rscale = vp.relline_norm / srel_all;   // renorm_relline_profile (single-zone models)
-    {
-      double chk = vp.renorm ? srel_all * rscale : srel_all;
-      if (chk < 1e-12) continue;                          // src/Relxill.cpp:455-457
-    }
-    // rebin the zone's spectrum onto the convolution grid; pack x + i y
-    double p_x = 0.0, p_r = 0.0;
-    if (A.mode == 0) {
-      const double *xz = S.xillz + ((size_t) v * A.nz_stride + z) * X.stride;
-      for (int i = t; i < NCONV; i += CONV_NT) {
+    const double *xz = S.xillz + ((size_t) v * A.nz_stride + z) * X.stride;
+    // ---- rebin the zone's spectrum onto the convolution grid (x part of the packed transform) + sums
+    double sums[4] = {0.0, 0.0, 0.0, 0.0};   // all rel, |x|, band x, band rel
+    for (int i = t; i < NCONV; i += CONV_NT) {
+      double f = 0.0;
+      if (A.mode == 0) {
         const int imin = X.rb_imin[i];
-        double f = 0.0;
         if (imin >= 0) {
           const int imax = X.rb_imax[i];
           if (imax == imin) f = X.rb_dmin[i] * xz[imin];
@@ -834,57 +911,68 @@ __global__ void __launch_bounds__(CONV_NT) k_conv(const VPar *__restrict__ vps, 
             for (int jj = imin + 1; jj <= imax - 1; jj++) f += xz[jj];
           }
         }
-        fx[i] = f;
+      } else {
+        f = rebin_bin(T.econv[i], T.econv[i + 1], A.user_e, o, A.n_flux);
       }
-    } else {
-      for (int i = t; i < NCONV; i += CONV_NT) {
-        double elo = T.econv[i], ehi = T.econv[i + 1];
-        fx[i] = rebin_bin(elo, ehi, A.user_e, o, A.n_flux);   // user grid already shifted by the host for mode 1
-      }
+      const double r = rel[i];
+      sm.zr[cv_pad(i)] = f * T.conv_cf[i];
+      sums[0] += r;
+      sums[1] += fabs(f);
+      if (T.conv_band[i]) { sums[2] += f; sums[3] += r; }
+    }
+    block_sum4(sums, sm);
+    const double srel_all = sums[0];
+    const double rscale = vp.renorm ? vp.relline_norm / srel_all : 1.0;   // renorm_relline_profile (one-zone models)
+    const double srel_n = vp.renorm ? srel_all * rscale : srel_all;
+    if (srel_n < 1e-12) { __syncthreads(); continue; }                     // src/Relxill.cpp:455-457
+    // both real inputs ride one complex transform: bring them to the same scale (any factor cancels in the norm)
+    const double bal = (sums[1] > 0.0 && srel_n > 0.0) ? sums[1] / srel_n : 1.0;
+    const double s_xill = sums[2], s_rel = vp.renorm ? sums[3] * rscale : sums[3];
+    for (int i = t; i < NCONV; i += CONV_NT) {
+      const double r = vp.renorm ? rel[i] * rscale : rel[i];
+      sm.zi[cv_pad((i - i1 + NCONV) & (NCONV - 1))] = (r * T.conv_cf[i]) * bal;
     }
     __syncthreads();
-    // The two real inputs share one complex transform; bring them to the same scale first so that the
-    // split does not lose the smaller one to rounding.  Any positive factor cancels in the normalisation
-    // (norm = s_rel * s_xill / s_conv is computed from the scaled output).
-    double p_ax = 0.0;
-    for (int i = t; i < NCONV; i += CONV_NT) p_ax += fabs(fx[i]);
-    const double s_ax = block_sum<CONV_NT>(p_ax, red);
-    const double bal = (s_ax > 0.0 && srel_all > 0.0) ? s_ax / (vp.renorm ? srel_all * rscale : srel_all) : 1.0;
-    for (int i = t; i < NCONV; i += CONV_NT) {
-      const double cf = T.conv_cf[i];
-      const double r = vp.renorm ? rel[i] * rscale : rel[i];
-      xr[i] = fx[i] * cf;
-      xi[(i - i1 + NCONV) % NCONV] = (r * cf) * bal;
-      if (T.conv_band[i]) { p_x += fx[i]; p_r += r; }
-    }
-    const double s_xill = block_sum<CONV_NT>(p_x, red);
-    const double s_rel = block_sum<CONV_NT>(p_r, red);
-    fft4096(xr, xi, T.tw_re, T.tw_im, 1.0);
-    // split into the two real transforms, multiply, rebuild the Hermitian product
-    for (int k = t; k <= NCONV / 2; k += CONV_NT) {
-      const int nk = (NCONV - k) & (NCONV - 1);
-      const double a = xr[k], b = xi[k], c = xr[nk], d = xi[nk];
+    fft4096(sm.zr, sm.zi, tw);
+    // ---- split, product spectrum, band sum of the convolved zone in the frequency domain
+    double dot[4] = {0.0, 0.0, 0.0, 0.0};
+    double pr_[5], pi_[5];
+    int nk = 0;
+    for (int k = t; k <= NCONV / 2; k += CONV_NT, nk++) {
+      const int kk = (NCONV - k) & (NCONV - 1);
+      const double a = sm.zr[cv_pad(k)], b = sm.zi[cv_pad(k)], c = sm.zr[cv_pad(kk)], d = sm.zi[cv_pad(kk)];
       const double Xr = 0.5 * (a + c), Xi = 0.5 * (b - d);
       const double Yr = 0.5 * (b + d), Yi = 0.5 * (c - a);
       const double Pr = Xr * Yr - Xi * Yi, Pi = Xr * Yi + Xi * Yr;
-      xr[k] = Pr; xi[k] = Pi;
-      xr[nk] = Pr; xi[nk] = -Pi;
+      pr_[nk] = Pr;
+      pi_[nk] = Pi;
+      const double wgt = (k == 0 || k == NCONV / 2) ? 1.0 : 2.0;
+      dot[0] += wgt * (Pr * T.conv_wr[k] + Pi * T.conv_wi[k]);
     }
-    __syncthreads();
-    if (t == 0) { xi[0] = 0.0; xi[NCONV / 2] = 0.0; }
-    __syncthreads();
-    fft4096(xr, xi, T.tw_re, T.tw_im, -1.0);
-    double p_c = 0.0;
-    for (int i = t; i < NCONV; i += CONV_NT) {
-      const double fo = xr[i] / T.conv_cf[i];
-      xr[i] = fo;
-      if (T.conv_band[i]) p_c += fo;
+    block_sum4(dot, sm);
+    const double norm = s_rel * s_xill / dot[0];
+    nk = 0;
+    for (int k = t; k <= NCONV / 2; k += CONV_NT, nk++) {
+      sm.ar[k] += norm * pr_[nk];
+      sm.ai[k] += norm * pi_[nk];
     }
-    const double s_conv = block_sum<CONV_NT>(p_c, red);
-    const double norm = s_rel * s_xill / s_conv;
-    for (int i = t; i < NCONV; i += CONV_NT) acc[i] += xr[i] * norm;
     __syncthreads();
   }
+  // ---- one inverse transform for the whole vector: out = Re(FFT(conj(A)))
+  for (int k = t; k <= NCONV / 2; k += CONV_NT) {
+    const double ar = sm.ar[k], ai = (k == 0 || k == NCONV / 2) ? 0.0 : sm.ai[k];
+    sm.zr[cv_pad(k)] = ar;
+    sm.zi[cv_pad(k)] = -ai;
+    if (k > 0 && k < NCONV / 2) {
+      sm.zr[cv_pad(NCONV - k)] = ar;
+      sm.zi[cv_pad(NCONV - k)] = ai;
+    }
+  }
+  __syncthreads();
+  fft4096(sm.zr, sm.zi, tw);
+  double *acc = sm.ar;   // ar and ai are contiguous: 4098 doubles
+  for (int i = t; i < NCONV; i += CONV_NT) acc[i] = sm.zr[cv_pad(i)] / T.conv_cf[i];
+  __syncthreads();
   if (A.mode == 0) {
     // primary spectrum on the convolution grid (cutoff power law here; nthcomp is added by k_prim_nthcomp)
     double refl_scale, prim_scale;
@@ -947,7 +1035,9 @@ int kernels_init() {
   e = cudaFuncSetAttribute(k_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ((NR * MAX_INCL + NR + 4) * sizeof(double)));
   if (e != cudaSuccess) return 1;
   if (line_kernel_init() != 0) return 1;
-  e = cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ((4 * NCONV + CONV_NT) * sizeof(double)));
+  e = cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ConvSmem));
+  if (e != cudaSuccess) return 1;
+  e = cudaFuncSetAttribute(k_conv, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return 1;
   return 0;
 }
@@ -979,7 +1069,7 @@ void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
   ConvArgs A;
   A.user_e = user_e; A.n_flux = n_flux; A.out = out; A.total = total; A.which = which;
   A.nz_stride = S.nz_cap; A.ne_stride = S.ne_line_cap; A.mode = mode;
-  const size_t sm = (4 * NCONV + CONV_NT) * sizeof(double);
+  const size_t sm = sizeof(ConvSmem);
   k_conv<<<(unsigned) n, CONV_NT, sm, st>>>(vps, T, S, A);
 }
 

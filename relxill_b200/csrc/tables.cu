@@ -15,6 +15,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -105,12 +106,34 @@ void Tables::load_fixed() {
   for (int i = 0; i < NG; i++) gstar[i] = H + (1.0 - 2 * H) / (NG - 1) * ((float) (i));  // src/Relprofile.cpp:104-106
   for (int i = 0; i < NG; i++)
     dg[i] = (i == 0 || i == NG - 1) ? 0.5 * (gstar[1] - gstar[0]) + H : gstar[1] - gstar[0];
-  std::vector<double> twr(NCONV / 2), twi(NCONV / 2);
-  for (int k = 0; k < NCONV / 2; k++) {
+  std::vector<double> tw(2 * NCONV);
+  for (int k = 0; k < NCONV; k++) {
     const double ang = -2.0 * M_PI * k / NCONV;
-    twr[k] = std::cos(ang);
-    twi[k] = std::sin(ang);
+    tw[2 * k] = std::cos(ang);
+    tw[2 * k + 1] = std::sin(ang);
   }
+  // W = DFT(band / cf): sum over the band of a convolution = sum_k P[k] conj(W[k])  (host radix-2 FFT)
+  std::vector<double> wr(NCONV), wi(NCONV, 0.0);
+  for (int i = 0; i < NCONV; i++) wr[i] = band[i] ? 1.0 / cf[i] : 0.0;
+  for (int i = 1, j = 0; i < NCONV; i++) {
+    int bit = NCONV >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) { std::swap(wr[i], wr[j]); std::swap(wi[i], wi[j]); }
+  }
+  for (int len = 2; len <= NCONV; len <<= 1) {
+    const int half = len >> 1, step = NCONV / len;
+    for (int i = 0; i < NCONV; i += len)
+      for (int k = 0; k < half; k++) {
+        const double c = tw[2 * k * step], s = tw[2 * k * step + 1];
+        const double vr = wr[i + k + half] * c - wi[i + k + half] * s, vi = wr[i + k + half] * s + wi[i + k + half] * c;
+        const double ur = wr[i + k], ui = wi[i + k];
+        wr[i + k] = ur + vr; wi[i + k] = ui + vi;
+        wr[i + k + half] = ur - vr; wi[i + k + half] = ui - vi;
+      }
+  }
+  wr.resize(NCONV / 2 + 1);
+  wi.resize(NCONV / 2 + 1);
   dt_.econv = upload(econv_);
   dt_.conv_cf = upload(cf);
   dt_.conv_band = upload(band);
@@ -120,8 +143,9 @@ void Tables::load_fixed() {
   dt_.coarse_m2 = upload(m2);
   dt_.gstar = upload(gstar);
   dt_.d_gstar = upload(dg);
-  dt_.tw_re = upload(twr);
-  dt_.tw_im = upload(twi);
+  dt_.tw = upload(tw);
+  dt_.conv_wr = upload(wr);
+  dt_.conv_wi = upload(wi);
   have_fixed_ = true;
 }
 
