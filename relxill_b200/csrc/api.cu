@@ -118,6 +118,8 @@ int ensure_scratch(Engine &E, long cap, int nz_cap, int ne_cap, int nex_stride) 
   ok &= salloc(E, S.zect, c * NZMAX) && salloc(E, S.normch, c * NZMAX) && salloc(E, S.corr_flux, c * NZMAX);
   ok &= salloc(E, S.corr_gshift, c * NZMAX) && salloc(E, S.nsrc, c);
   ok &= salloc(E, S.xrow, c * NZMAX * 32) && salloc(E, S.xw, c * NZMAX * 32);
+  ok &= salloc(E, S.xkey, c * NZMAX * 32) && salloc(E, S.xwsort, c * NZMAX * 32) && salloc(E, S.xn, c);
+  ok &= salloc(E, S.xga_off, c * 4) && salloc(E, S.xga_w, c * 4);
   ok &= salloc(E, S.relflux, c * nz_cap * ne_cap) && salloc(E, S.dist, c * NZMAX * MAX_INCL);
   ok &= salloc(E, S.xillz, c * nz_cap * (size_t) std::max(nex_stride, 1)) && salloc(E, S.status, c);
   ok &= salloc(E, E.d_total, c * NCONV);
@@ -246,7 +248,7 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st)
     } else {
       tm.begin(); launch_line(vps, T, S, nc, T.econv, NCONV, 0, relxill ? b->nz_max : 1, st); tm.end(KF_LINE);
       if (relxill) {
-        tm.begin(); launch_xill(vps, T, S, nc, which, b->nz_max, st); tm.end(KF_XILL);
+        tm.begin(); launch_xill(vps, T, S, nc, which, b->nz_max, E.tables->xill_host(m.prim).n_ener, n_incl, st); tm.end(KF_XILL);
         tm.begin(); launch_conv(vps, T, S, nc, b->d_energy, b->n_flux, out, E.d_total, which, 0, st); tm.end(KF_CONV);
       } else {
         tm.begin(); launch_conv(vps, T, S, nc, b->d_energy, b->n_flux, out, nullptr, 0, 1, st); tm.end(KF_CONV);

@@ -113,6 +113,11 @@ struct Scratch {
   double *nsrc;                                               // [cap] source normalisation factor
   int *xrow;                                                  // [cap][NZMAX][32] node index of each corner
   double *xw;                                                 // [cap][NZMAX][32] corner weights
+  int *xkey;                                                  // [cap][NZMAX*32] (rest-corner node offset << 6 | zone), sorted
+  int *xga_off;                                               // [cap][4] node offsets of the (Gamma, A_Fe) corners
+  double *xga_w;                                              // [cap][4] their weights
+  double *xwsort;                                             // [cap][NZMAX*32] weights in xkey order
+  int *xn;                                                    // [cap] number of (zone, corner) pairs
   double *relflux;                                            // [cap][nz_cap][ne_line_cap]
   double *dist;                                               // [cap][NZMAX][MAX_INCL]
   double *xillz;                                              // [cap][nz_cap][nex_stride]

@@ -359,6 +359,8 @@ struct ZoneSmem {
   double nfac[NZMAX + 1], s2[NZMAX + 1];
   int b[NZMAX];
   int ints[4];
+  int skey[2048];      // (node << 6 | zone) of every (zone, corner) pair, sorted by node for k_xill
+  double sw[2048];
 };
 
 // cutoff power law on the coarse grid (src/Xillspec.cpp:215-233) reduced to the two band sums; warp-cooperative
@@ -390,6 +392,7 @@ __global__ void __launch_bounds__(128) k_zone(const VPar *__restrict__ vps, DevT
   if (S.status[v] != ST_OK) return;
   const int nz = vp.nz;
   const bool alpha = (vp.ion_grad_type == ION_ALPHA);
+  const int nc_all = (T.xill[vp.prim_type == PRIM_NTHCOMP ? 1 : 0].npar == 6) ? 32 : 16;
   for (int i = t; i < NR; i += 128) {
     sm.re[i] = S.re[(size_t) v * NR + i];
     sm.y1[i] = S.del_emit[(size_t) v * NR + i];
@@ -510,6 +513,93 @@ __global__ void __launch_bounds__(128) k_zone(const VPar *__restrict__ vps, DevT
         xw[half * 16 + c] = w;
       }
     }
+  }
+  __syncthreads();
+  // Factorised corner list for k_xill.  The multilinear weight of a corner is a product over the table
+  // axes; Gamma and A_Fe are the same for all zones of a vector, so the table is first contracted over
+  // those two axes (4 nodes, weights ga_w) and the zones only blend the remaining "rest" corners
+  // (logXi, Ecut|kTe[, Dens]: 4 or 8 per zone).  Entry key = (rest node offset << 6 | zone).
+  const int n_rest = nc_all / 4;
+  if (t < nz) {
+    const XillDev &X = T.xill[vp.prim_type == PRIM_NTHCOMP ? 1 : 0];
+    const int nax = X.npar - 1;
+    long stride[6];
+    long acc_s = 1;
+    for (int i = nax - 1; i >= 0; i--) { stride[i] = acc_s; acc_s *= X.nvals[i]; }
+    // recompute this zone's bracket (same arithmetic as above) for the zone-varying axes
+    float inp[8];
+    inp[0] = (float) vp.gam; inp[1] = (float) vp.afe; inp[2] = (float) sm.lxi[t]; inp[3] = (float) sm.ect[t];
+    inp[4] = (float) sm.dens[t]; inp[5] = 0.f; inp[6] = 0.f; inp[7] = 0.f;
+    int ind[6];
+    double fac[6];
+    for (int i = 0; i < nax; i++) {
+      const int pind = X.pindex[i];
+      const int n = X.nvals[i];
+      int k = bsearch_asc<float>(X.vals[i], n, inp[pind]);
+      if (k < 0) k = 0; else if (k > n - 2) k = n - 2;
+      ind[i] = k;
+      float val = inp[pind];
+      const float lo = X.vals[i][0], hi = X.vals[i][n - 1];
+      if (val < lo) val = lo; else if (val > hi) val = hi;
+      fac[i] = (double) ((val - X.vals[i][k]) / (X.vals[i][k + 1] - X.vals[i][k]));
+      if (pind == 3) {
+        if (sm.ect[t] <= (double) lo) fac[i] = 0.0;
+        if (sm.ect[t] >= (double) hi) fac[i] = 1.0;
+      }
+    }
+    // axes: the two vector-level ones (Gamma, A_Fe) and the zone-level rest
+    int ax_v[2], ax_r[3], nv = 0, nr = 0;
+    for (int i = 0; i < nax; i++) {
+      if (X.pindex[i] == 0 || X.pindex[i] == 1) ax_v[nv++] = i; else ax_r[nr++] = i;
+    }
+    for (int c = 0; c < n_rest; c++) {
+      long off = 0;
+      double w = 1.0;
+      for (int q = 0; q < nr; q++) {
+        const int bit = (c >> q) & 1;
+        off += (long) (ind[ax_r[q]] + bit) * stride[ax_r[q]];
+        w *= bit ? fac[ax_r[q]] : (1.0 - fac[ax_r[q]]);
+      }
+      sm.skey[t * n_rest + c] = ((int) off << 6) | t;
+      sm.sw[t * n_rest + c] = w;
+    }
+    if (t == 0) {
+      int *ga_off = S.xga_off + (size_t) v * 4;
+      double *ga_w = S.xga_w + (size_t) v * 4;
+      for (int c = 0; c < 4; c++) {
+        const int b0 = c & 1, b1 = (c >> 1) & 1;
+        ga_off[c] = (int) ((long) (ind[ax_v[0]] + b0) * stride[ax_v[0]] + (long) (ind[ax_v[1]] + b1) * stride[ax_v[1]]);
+        ga_w[c] = (b0 ? fac[ax_v[0]] : (1.0 - fac[ax_v[0]])) * (b1 ? fac[ax_v[1]] : (1.0 - fac[ax_v[1]]));
+      }
+    }
+  }
+  __syncthreads();
+  {  // sort the (rest node, zone, weight) triples by node: bitonic sort in shared memory
+    const int n_ent = nz * n_rest;
+    int npow = 1;
+    while (npow < n_ent) npow <<= 1;
+    for (int i = n_ent + t; i < npow; i += 128) { sm.skey[i] = 0x7fffffff; sm.sw[i] = 0.0; }
+    __syncthreads();
+    for (int k = 2; k <= npow; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = t; i < npow; i += 128) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const bool up = ((i & k) == 0);
+            const int a = sm.skey[i], b = sm.skey[ixj];
+            if ((a > b) == up) {
+              sm.skey[i] = b; sm.skey[ixj] = a;
+              const double wa = sm.sw[i]; sm.sw[i] = sm.sw[ixj]; sm.sw[ixj] = wa;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    int *gk = S.xkey + (size_t) v * NZMAX * 32;
+    double *gw = S.xwsort + (size_t) v * NZMAX * 32;
+    for (int i = t; i < n_ent; i += 128) { gk[i] = sm.skey[i]; gw[i] = sm.sw[i]; }
+    if (t == 0) S.xn[v] = n_ent;
   }
   __syncthreads();
   // primary-spectrum normalisations: one warp per (zone | source); cutoff power law only here,
@@ -675,53 +765,6 @@ __global__ void __launch_bounds__(256) k_linefinish(const VPar *__restrict__ vps
   const double sum = block_sum<256>(part, red);
   const double scale = vp.renorm ? vp.relline_norm / sum : 1.0;
   for (int j = t; j < n_ener; j += 256) o[j] = vp.renorm ? flux[j] * scale : flux[j];
-}
-
-// ---------------------------------------------------------------------------------- k_xill
-// interp_5d_tab_incl / interp_6d_tab_incl for every inclination (src/xilltable.c:812-876,999-1019) fused
-// with calc_xillver_angdep (src/Xillspec.cpp:557-573) and the division by the normalisation change
-// (src/Relxill.cpp:380-385): xill[z][e] = sum_m dist[z][m] * sum_c w_c * tab[node_c][m][e] / normch[z].
-// One CTA per (vector, zone); threads stride the energy axis so every corner row is a coalesced stream.
-__global__ void __launch_bounds__(256) k_xill(const VPar *__restrict__ vps, DevTables T, Scratch S, int which,
-                                              int nz_stride) {
-  __shared__ double s_w[32];
-  __shared__ double s_d[MAX_INCL];
-  __shared__ const float *s_row[32];
-  const int v = blockIdx.y, z = blockIdx.x, t = threadIdx.x;
-  if (S.status[v] != ST_OK) return;
-  const VPar &vp = vps[v];
-  if (z >= vp.nz) return;
-  const XillDev &X = T.xill[which];
-  const int nc = (X.npar == 6) ? 32 : 16;
-  const int ni = X.n_incl, st = X.stride, ne = X.n_ener;
-  if (t < nc) {
-    s_w[t] = S.xw[((size_t) v * NZMAX + z) * 32 + t];
-    s_row[t] = X.data + (size_t) S.xrow[((size_t) v * NZMAX + z) * 32 + t] * ni * st;
-  }
-  if (t < ni) s_d[t] = S.dist[((size_t) v * NZMAX + z) * MAX_INCL + t];
-  __syncthreads();
-  const double inv_norm = S.normch[(size_t) v * NZMAX + z];
-  double *out = S.xillz + ((size_t) v * nz_stride + z) * st;
-  for (int e = t; e < ne; e += 256) {
-    double acc = 0.0;
-    for (int m = 0; m < ni; m++) {
-      double f = 0.0;
-      if (nc == 16) {
-#pragma unroll
-        for (int c = 0; c < 16; c++) f += s_w[c] * (double) __ldg(s_row[c] + (size_t) m * st + e);
-      } else {
-        double f1 = 0.0, f2 = 0.0;
-#pragma unroll
-        for (int c = 0; c < 16; c++) {
-          f1 += s_w[c] * (double) __ldg(s_row[c] + (size_t) m * st + e);
-          f2 += s_w[16 + c] * (double) __ldg(s_row[16 + c] + (size_t) m * st + e);
-        }
-        f = f1 + f2;
-      }
-      acc += s_d[m] * f;
-    }
-    out[e] = acc / inv_norm;
-  }
 }
 
 // ---------------------------------------------------------------------------------- k_conv
@@ -1023,6 +1066,7 @@ __global__ void __launch_bounds__(CONV_NT, 1) k_conv(const VPar *__restrict__ vp
 static size_t g_smem_sys = 0, g_smem_zone = 0;
 
 int line_kernel_init();
+int xill_kernel_init();
 
 int kernels_init() {
   g_smem_sys = sizeof(SysSmem);
@@ -1035,6 +1079,7 @@ int kernels_init() {
   e = cudaFuncSetAttribute(k_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ((NR * MAX_INCL + NR + 4) * sizeof(double)));
   if (e != cudaSuccess) return 1;
   if (line_kernel_init() != 0) return 1;
+  if (xill_kernel_init() != 0) return 1;
   e = cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ConvSmem));
   if (e != cudaSuccess) return 1;
   e = cudaFuncSetAttribute(k_conv, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
@@ -1059,10 +1104,6 @@ void launch_dist(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
 }
 void launch_linefinish(const VPar *vps, const Scratch &S, long n, int n_ener, double *out, cudaStream_t st) {
   k_linefinish<<<(unsigned) n, 256, 0, st>>>(vps, S, n_ener, S.ne_line_cap, S.nz_cap, out);
-}
-void launch_xill(const VPar *vps, const DevTables &T, const Scratch &S, long n, int which, int nz_max, cudaStream_t st) {
-  dim3 grid(nz_max, (unsigned) n);
-  k_xill<<<grid, 256, 0, st>>>(vps, T, S, which, S.nz_cap);
 }
 void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
                  double *out, double *total, int which, int mode, cudaStream_t st) {

@@ -17,7 +17,8 @@ void launch_line(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
                  int grid_mode, int nz_max, cudaStream_t st);
 int line_max_bins();  // largest energy grid the line kernel handles in one pass
 void launch_linefinish(const VPar *vps, const Scratch &S, long n, int n_ener, double *out, cudaStream_t st);
-void launch_xill(const VPar *vps, const DevTables &T, const Scratch &S, long n, int which, int nz_max, cudaStream_t st);
+void launch_xill(const VPar *vps, const DevTables &T, const Scratch &S, long n, int which, int nz_max, int n_ener,
+                 int n_incl, cudaStream_t st);
 void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
                  double *out, double *total, int which, int mode, cudaStream_t st);
 
