@@ -119,7 +119,7 @@ int ensure_scratch(Engine &E, long cap, int nz_cap, int ne_cap, int nex_stride) 
   ok &= salloc(E, S.corr_gshift, c * NZMAX) && salloc(E, S.nsrc, c);
   ok &= salloc(E, S.xrow, c * NZMAX * 32) && salloc(E, S.xw, c * NZMAX * 32);
   ok &= salloc(E, S.xkey, c * NZMAX * 32) && salloc(E, S.xwsort, c * NZMAX * 32) && salloc(E, S.xn, c);
-  ok &= salloc(E, S.xga_off, c * 4) && salloc(E, S.xga_w, c * 4);
+  ok &= salloc(E, S.xga_off, c * 4) && salloc(E, S.xga_w, c * 4) && salloc(E, S.zrange, c * NZMAX * 2);
   ok &= salloc(E, S.relflux, c * nz_cap * ne_cap) && salloc(E, S.dist, c * NZMAX * MAX_INCL);
   ok &= salloc(E, S.xillz, c * nz_cap * (size_t) std::max(nex_stride, 1)) && salloc(E, S.status, c);
   ok &= salloc(E, E.d_total, c * NCONV);
@@ -560,6 +560,11 @@ int relxill_b200_probe(relxill_b200_batch *b, long iv, const char *what, double 
                         : (w == "xill")  ? S.xillz + (v * S.nz_cap + z) * S.nex_stride
                                          : S.dist + (v * NZMAX + z) * MAX_INCL;
       cudaMemcpy(out + z * len, p, len * sizeof(double), cudaMemcpyDeviceToHost);
+      if (w == "relflux") {  // rows are only written inside the zone's bin range
+        int rg[2];
+        cudaMemcpy(rg, S.zrange + (v * NZMAX + z) * 2, sizeof(rg), cudaMemcpyDeviceToHost);
+        for (long i = 0; i < (long) len; i++) if (i < rg[0] || i > rg[1]) out[z * len + i] = 0.0;
+      }
     }
     return (int) (len * nz);
   } else {

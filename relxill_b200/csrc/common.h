@@ -118,7 +118,8 @@ struct Scratch {
   double *xga_w;                                              // [cap][4] their weights
   double *xwsort;                                             // [cap][NZMAX*32] weights in xkey order
   int *xn;                                                    // [cap] number of (zone, corner) pairs
-  double *relflux;                                            // [cap][nz_cap][ne_line_cap]
+  double *relflux;                                            // [cap][nz_cap][ne_line_cap] (valid inside zrange only)
+  int *zrange;                                                // [cap][NZMAX][2] first/last bin written per zone (-1: none)
   double *dist;                                               // [cap][NZMAX][MAX_INCL]
   double *xillz;                                              // [cap][nz_cap][nex_stride]
   int *status;                                                // [cap]

@@ -760,11 +760,15 @@ __global__ void __launch_bounds__(256) k_linefinish(const VPar *__restrict__ vps
   }
   const VPar &vp = vps[v];
   const double *flux = S.relflux + (size_t) v * nz_stride * ne_stride;
+  const int jlo = S.zrange[(size_t) v * NZMAX * 2], jhi = S.zrange[(size_t) v * NZMAX * 2 + 1];
   double part = 0.0;
-  for (int j = t; j < n_ener; j += 256) part += flux[j];
+  for (int j = t; j < n_ener; j += 256) part += (j >= jlo && j <= jhi) ? flux[j] : 0.0;
   const double sum = block_sum<256>(part, red);
   const double scale = vp.renorm ? vp.relline_norm / sum : 1.0;
-  for (int j = t; j < n_ener; j += 256) o[j] = vp.renorm ? flux[j] * scale : flux[j];
+  for (int j = t; j < n_ener; j += 256) {
+    const double f = (j >= jlo && j <= jhi) ? flux[j] : 0.0;
+    o[j] = vp.renorm ? f * scale : f;
+  }
 }
 
 // ---------------------------------------------------------------------------------- k_conv
@@ -940,6 +944,7 @@ __global__ void __launch_bounds__(CONV_NT, 1) k_conv(const VPar *__restrict__ vp
   for (int z = 0; z < nz; z++) {
     const double *rel = S.relflux + ((size_t) v * A.nz_stride + z) * A.ne_stride;
     const double *xz = S.xillz + ((size_t) v * A.nz_stride + z) * X.stride;
+    const int rjlo = S.zrange[((size_t) v * NZMAX + z) * 2], rjhi = S.zrange[((size_t) v * NZMAX + z) * 2 + 1];
     // ---- rebin the zone's spectrum onto the convolution grid (x part of the packed transform) + sums
     double sums[4] = {0.0, 0.0, 0.0, 0.0};   // all rel, |x|, band x, band rel
     for (int i = t; i < NCONV; i += CONV_NT) {
@@ -957,7 +962,7 @@ __global__ void __launch_bounds__(CONV_NT, 1) k_conv(const VPar *__restrict__ vp
       } else {
         f = rebin_bin(T.econv[i], T.econv[i + 1], A.user_e, o, A.n_flux);
       }
-      const double r = rel[i];
+      const double r = (i >= rjlo && i <= rjhi) ? rel[i] : 0.0;
       sm.zr[cv_pad(i)] = f * T.conv_cf[i];
       sums[0] += r;
       sums[1] += fabs(f);
@@ -972,7 +977,8 @@ __global__ void __launch_bounds__(CONV_NT, 1) k_conv(const VPar *__restrict__ vp
     const double bal = (sums[1] > 0.0 && srel_n > 0.0) ? sums[1] / srel_n : 1.0;
     const double s_xill = sums[2], s_rel = vp.renorm ? sums[3] * rscale : sums[3];
     for (int i = t; i < NCONV; i += CONV_NT) {
-      const double r = vp.renorm ? rel[i] * rscale : rel[i];
+      const double r0 = (i >= rjlo && i <= rjhi) ? rel[i] : 0.0;
+      const double r = vp.renorm ? r0 * rscale : r0;
       sm.zi[cv_pad((i - i1 + NCONV) & (NCONV - 1))] = (r * T.conv_cf[i]) * bal;
     }
     __syncthreads();

@@ -1,6 +1,32 @@
 // line.cu — the relline profile kernel (the FP64 hot loop of the relativistic smearing).
 // Compiled with FMA contraction on (build.py): its results feed no discrete decision other than the
 // Romberg convergence test, which has a 2 % threshold.
+//
+// Replaces calc_relline_profile + integ_relline_bin + int_edge + int_romb + romberg_integration +
+// relb_func (src/Relprofile.cpp:489-726,835-905) and the division by the bin energy of
+// renorm_relline_profile (:757-762).
+//
+// Mapping.  One CTA per (vector, radial zone).  The zone's radii are processed in sub-batches; inside a
+// sub-batch all (radius, energy-bin) pairs that the reference's double loop visits are flattened into one
+// dense item list (the bins of one radius are contiguous: [ielo, iehi]), so lanes stay busy whatever the
+// line width is.
+//   phase 1  one thread per item.  Edge terms, midpoint bins and Romberg bins up to two halvings are
+//            finished here; a bin whose Romberg integral has not converged by then (the horns of the
+//            profile, a few per cent of the bins) is pushed on a shared-memory work list.
+//   phase 2  one WARP per listed bin: the dyadic abscissae of the deeper Romberg levels are evaluated
+//            in parallel across the lanes (17 points for levels <= 4, 65 for levels <= 6) and the
+//            tableau is built from masked warp sums.
+//   phase 3  per energy bin, the sub-batch's contributions are added in ascending-radius order into the
+//            zone accumulator -> no atomics on data, bit-reproducible, the reference's summation order.
+//
+// Arithmetic.  The two branches k = 0, 1 of the transfer function share everything but the interpolated
+// trff value, so one evaluation of the integrand returns both (the reference calls relb_func twice).
+// Romberg level n re-uses the function values of level n-1 (the reference re-evaluates them; the
+// abscissae a + ii * pas are bit-identical because pas is halved exactly).  The integrand
+//   pow(eg,3) / ((gmax-gmin) * sqrt(g* - g*^2)) * ftrf * emis          (src/Relprofile.cpp:506)
+// is evaluated as eg^3 * rsqrt(g* - g*^2) * ftrf * (emis / (gmax-gmin)); the g* bracket is computed
+// arithmetically (the grid is uniform), which can differ from the reference's binary search only when g*
+// sits within an ulp of a node, where the piecewise-linear interpolant is continuous.
 #include <cuda_runtime.h>
 
 #include "common.h"
@@ -9,92 +35,42 @@
 
 namespace rx {
 
-// ---------------------------------------------------------------------------------- k_line
-// Relline profile: calc_relline_profile + integ_relline_bin + int_edge + int_romb + romberg_integration +
-// relb_func (src/Relprofile.cpp:489-726,835-905) and the division by the bin energy of
-// renorm_relline_profile (:757-762).
-//
-// One CTA per (vector, radial zone).  The zone's radii are processed in sub-batches; inside a sub-batch all
-// (radius, energy-bin) pairs that the reference's double loop visits are flattened into one dense item list
-// (the bins of one radius are contiguous: [ielo, iehi]), so lanes stay busy whatever the line width is.
-//   phase 1  every item is integrated with the Romberg depth capped at 2; the few bins that have not
-//            converged by then (the horns of the profile) are pushed on a shared-memory work list
-//   phase 2  the work list is integrated densely with the full depth (same arithmetic from scratch)
-//   phase 3  per energy bin, the sub-batch's contributions are added in ascending-radius order into the
-//            zone accumulator -> no atomics on data, bit-reproducible, the reference's summation order
 struct RelbCtx {
-  double gmin, gmax, del_g, emis;
-  double scale;          // del_g * emis
+  double gmin, gmax, del_g;
+  double scale;          // emis / (gmax - gmin)
   const double2 *trff;   // [NG] {branch 0, branch 1} of this radius (global, L1-resident)
   const double2 *cosne;
-  const double *gstar;   // shared memory: g* nodes [NG] followed by the inverse node spacings [NG-1]
   int limb;
 };
 
-// The integrand (src/Relprofile.cpp:489-521):
-//   pow(eg,3) / ((gmax-gmin) * sqrt(g* - g*^2)) * ftrf * emis [* limb]
-// evaluated as eg^3 * rsqrt(g* - g*^2) * ftrf * (emis / (gmax-gmin)): one rsqrt instead of a sqrt and two
-// divisions (the node-spacing division becomes a multiplication by the tabulated inverse spacing).
-__device__ __forceinline__ double relb_func(double eg, int k, const RelbCtx &c) {
+#define GS_C ((1.0 - 2 * GFAC_H) / (NG - 1))
+#define GS_INVC ((NG - 1) / (1.0 - 2 * GFAC_H))
+
+// both branches of relb_func (src/Relprofile.cpp:489-521) at energy eg
+__device__ __forceinline__ void relb2(double eg, const RelbCtx &c, double &v0, double &v1) {
   const double egstar = (eg - c.gmin) * c.del_g;
-  // bracket in the (uniform up to rounding) g* grid: same result as binary_search(gstar, 40, egstar)
-  int ind = (int) ((egstar - GFAC_H) * ((NG - 1) / (1.0 - 2 * GFAC_H)));
+  int ind = (int) ((egstar - GFAC_H) * GS_INVC);
   ind = ind < 0 ? 0 : (ind > NG - 2 ? NG - 2 : ind);
-  if (ind > 0 && c.gstar[ind] > egstar) ind--;
-  else if (ind < NG - 2 && c.gstar[ind + 1] <= egstar) ind++;
-  const double inte = (egstar - c.gstar[ind]) * c.gstar[NG + ind];
+  const double inte = (egstar - (GFAC_H + GS_C * (double) ind)) * GS_INVC;
   const double inte1 = 1.0 - inte;
   const double2 t0 = __ldg(c.trff + ind), t1 = __ldg(c.trff + ind + 1);
-  const double ftrf = inte * (k ? t0.y : t0.x) + inte1 * (k ? t1.y : t1.x);
-  const double val = (eg * eg * eg) * rsqrt(egstar - egstar * egstar) * ftrf * c.scale;
-  if (c.limb == 0) return val;
-  const double2 c0 = __ldg(c.cosne + ind), c1 = __ldg(c.cosne + ind + 1);
-  const double fmu0 = inte * (k ? c0.y : c0.x) + inte1 * (k ? c1.y : c1.x);
-  double limb = 1.0;
-  if (c.limb == 1) limb = (1.0 + 2.06 * fmu0);
-  else if (c.limb == 2) limb = log(1.0 + 1.0 / fmu0);
-  return val * limb;
+  const double common = (eg * eg * eg) * rsqrt(egstar - egstar * egstar) * c.scale;
+  v0 = common * (inte * t0.x + inte1 * t1.x);   // (the reference's weights: inte on node ind, 1-inte on ind+1)
+  v1 = common * (inte * t0.y + inte1 * t1.y);
+  if (c.limb != 0) {
+    const double2 c0 = __ldg(c.cosne + ind), c1 = __ldg(c.cosne + ind + 1);
+    const double m0 = inte * c0.x + inte1 * c1.x, m1 = inte * c0.y + inte1 * c1.y;
+    if (c.limb == 1) { v0 *= (1.0 + 2.06 * m0); v1 *= (1.0 + 2.06 * m1); }
+    else if (c.limb == 2) { v0 *= log(1.0 + 1.0 / m0); v1 *= log(1.0 + 1.0 / m1); }
+  }
 }
 
-// Romberg integration, src/Relprofile.cpp:524-579.  itermax = 5 is the reference; a smaller cap returns
-// with converged = false when the precision goal has not been met yet.
-template <int ITERMAX>
-__device__ double romberg(double a, double b, int k, const RelbCtx &c, bool &converged) {
-  const double prec = 0.02;
-  double obtprec = 1.0;
-  double prev[ITERMAX + 2], cur[ITERMAX + 2];
-  int niter = 0;
-  const double r0 = relb_func(a, k, c);
-  const double rb = relb_func(b, k, c);
-  const double ta = (r0 + rb) / 2.0;
-  double pas = b - a;
-  prev[0] = ta * pas;
-  double last_diag = prev[0];
-  while ((obtprec > prec) && (niter <= ITERMAX)) {
-    niter++;
-    pas = pas / 2.0;
-    double s = ta;
-    const int npts = (1 << niter) - 1;
-    for (int ii = 1; ii <= npts; ii++) s += relb_func(a + pas * ii, k, c);
-    cur[0] = s * pas;
-    double r = 1.0;
-#pragma unroll
-    for (int ii = 1; ii <= ITERMAX + 1; ii++) {
-      if (ii <= niter) {
-        r *= 4.0;
-        cur[ii] = (r * cur[ii - 1] - prev[ii - 1]) / (r - 1.0);
-      }
-    }
-    double diag = cur[0];
-#pragma unroll
-    for (int ii = 1; ii <= ITERMAX + 1; ii++) if (ii == niter) diag = cur[ii];
-    obtprec = fabs(diag - last_diag) / diag;
-    last_diag = diag;
-#pragma unroll
-    for (int ii = 0; ii < ITERMAX + 2; ii++) prev[ii] = cur[ii];
-  }
-  converged = !(obtprec > prec);
-  return last_diag;
+// (obtprec > prec) of the reference, obtprec = fabs(t_new - t_old) / t_new  (src/Relprofile.cpp:575)
+__device__ __forceinline__ bool not_converged(double t_new, double t_old) {
+  const double d = fabs(t_new - t_old);
+  if (t_new > 0.0) return d > 0.02 * t_new;
+  if (t_new == 0.0) return d > 0.0;   // x/0 = inf > prec;  0/0 = NaN compares false
+  return false;                        // negative (or NaN) quotient ends the loop
 }
 
 __device__ __forceinline__ double gstar2ener(double g, double gmin, double gmax) { return (g * (gmax - gmin) + gmin) * 1.0; }
@@ -103,19 +79,150 @@ __device__ double int_edge(double blo, double bhi, const RelbCtx &c) {  // src/R
   double hex, lo, hi;
   if (blo <= 0.5) { hex = GFAC_H; lo = blo; hi = bhi; }
   else { hex = 1.0 - GFAC_H; lo = 1.0 - bhi; hi = 1.0 - blo; }
+  double n0, n1;
+  relb2(gstar2ener(hex, c.gmin, c.gmax), c, n0, n1);
   double norm = 0.0;
-  const double eh = gstar2ener(hex, c.gmin, c.gmax);
-  norm = norm + relb_func(eh, 0, c);
-  norm = norm + relb_func(eh, 1, c);
+  norm = norm + n0;
+  norm = norm + n1;
   norm = norm * sqrt(GFAC_H);
   return 2 * norm * (sqrt(hi) - sqrt(lo)) * 1.0 * (c.gmax - c.gmin);
 }
 
-// src/Relprofile.cpp:650-726.  ITERMAX < 5: `complete` tells whether the capped Romberg runs converged
-// (if not, the caller repeats the bin with ITERMAX = 5).
-template <int ITERMAX>
-__device__ double integ_relline_bin(const RelbCtx &c, double rlo0, double rhi0, bool &complete) {
-  complete = true;
+// Romberg on [a, b] for both branches, at most two halvings (src/Relprofile.cpp:524-579 with the loop cut
+// after niter = 2).  Returns true and the sum of the two integrals if both branches converged.
+__device__ bool romberg2_capped(double a, double b, const RelbCtx &c, double &out) {
+  double fa0, fa1, fb0, fb1, m0, m1;
+  relb2(a, c, fa0, fa1);
+  relb2(b, c, fb0, fb1);
+  const double ta0 = (fa0 + fb0) / 2.0, ta1 = (fa1 + fb1) / 2.0;
+  const double pas = b - a;
+  const double t00_0 = ta0 * pas, t00_1 = ta1 * pas;
+  const double pas1 = pas / 2.0;
+  relb2(a + pas1 * 1, c, m0, m1);
+  const double t01_0 = (ta0 + m0) * pas1, t01_1 = (ta1 + m1) * pas1;
+  const double t10_0 = (4.0 * t01_0 - t00_0) / 3.0, t10_1 = (4.0 * t01_1 - t00_1) / 3.0;
+  const bool nc0 = not_converged(t10_0, t00_0), nc1 = not_converged(t10_1, t00_1);
+  if (!nc0 && !nc1) { out = t10_0 + t10_1; return true; }
+  const double pas2 = pas1 / 2.0;
+  double q0, q1, u0, u1;
+  relb2(a + pas2 * 1, c, q0, q1);
+  relb2(a + pas2 * 3, c, u0, u1);
+  double r0 = t10_0, r1 = t10_1;
+  bool bad = false;
+  if (nc0) {
+    const double t02 = (((ta0 + q0) + m0) + u0) * pas2;
+    const double t11 = (4.0 * t02 - t01_0) / 3.0;
+    const double t20 = (16.0 * t11 - t10_0) / 15.0;
+    bad |= not_converged(t20, t10_0);
+    r0 = t20;
+  }
+  if (nc1) {
+    const double t02 = (((ta1 + q1) + m1) + u1) * pas2;
+    const double t11 = (4.0 * t02 - t01_1) / 3.0;
+    const double t20 = (16.0 * t11 - t10_1) / 15.0;
+    bad |= not_converged(t20, t10_1);
+    r1 = t20;
+  }
+  out = r0 + r1;
+  return !bad;
+}
+
+// sum over the lanes selected by `sel` (all lanes participate), fixed butterfly order
+__device__ __forceinline__ double warp_masked_sum(double v, bool sel) {
+  double x = sel ? v : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+// Full-depth Romberg of one bin by a whole warp (all lanes pass the same a, b, c; all lanes return the sum
+// of the two branch integrals).  Levels 1..4 use the 17 dyadic points of spacing (b-a)/16, levels 5..6 the
+// 65 points of spacing (b-a)/64.
+__device__ double romberg2_warp(double a, double b, const RelbCtx &c) {
+  const int lane = threadIdx.x & 31;
+  const double pas = b - a;
+  double res[2] = {0.0, 0.0};
+  bool done[2] = {false, false};
+  double tprev[2][7];   // previous tableau row per branch: tprev[k][ii] = t[ii][niter-1-ii]
+  double ta[2];
+  {  // ---- points of depth 4
+    const double pas4 = pas / 16.0;
+    double v0 = 0.0, v1 = 0.0;
+    if (lane <= 16) relb2(lane == 16 ? b : a + pas4 * lane, c, v0, v1);
+    const double va[2] = {v0, v1};
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const double fa = __shfl_sync(0xffffffffu, va[k], 0), fb = __shfl_sync(0xffffffffu, va[k], 16);
+      ta[k] = (fa + fb) / 2.0;
+      tprev[k][0] = ta[k] * pas;
+      double last = tprev[k][0];
+      double pasn = pas;
+#pragma unroll
+      for (int n = 1; n <= 4; n++) {
+        pasn = pasn / 2.0;
+        const int stride = 16 >> n;
+        const double s = ta[k] + warp_masked_sum(va[k], lane > 0 && lane < 16 && (lane & (stride - 1)) == 0);
+        if (!done[k]) {
+          double cur[7];
+          cur[0] = s * pasn;
+          double r = 1.0;
+#pragma unroll
+          for (int ii = 1; ii <= 4; ii++) {
+            if (ii <= n) { r *= 4.0; cur[ii] = (r * cur[ii - 1] - tprev[k][ii - 1]) / (r - 1.0); }
+          }
+          const double diag = cur[n];
+          res[k] = diag;
+          if (!not_converged(diag, last)) done[k] = true;
+          last = diag;
+#pragma unroll
+          for (int ii = 0; ii <= 4; ii++) if (ii <= n) tprev[k][ii] = cur[ii];
+        }
+      }
+    }
+  }
+  if (!(done[0] && done[1])) {  // ---- points of depth 6 (levels 5 and 6)
+    const double pas6 = pas / 64.0;
+    double w0[2], w1[2], e0 = 0.0, e1 = 0.0;
+    relb2(a + pas6 * lane, c, w0[0], w1[0]);          // points 0..31 (point 0 = a, unused in the sums)
+    relb2(a + pas6 * (lane + 32), c, w0[1], w1[1]);   // points 32..63
+    (void) e0; (void) e1;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      if (done[k]) continue;   // uniform across the warp
+      double last = res[k];
+      double pasn = pas / 16.0;
+#pragma unroll
+      for (int n = 5; n <= 6; n++) {
+        pasn = pasn / 2.0;
+        const int stride = 64 >> n;   // 2, 1
+        const double lo = k ? w1[0] : w0[0], hi = k ? w1[1] : w0[1];
+        const double s = ta[k] + warp_masked_sum(lo, lane > 0 && (lane & (stride - 1)) == 0)
+                         + warp_masked_sum(hi, (lane & (stride - 1)) == 0);
+        if (!done[k]) {
+          double cur[7];
+          cur[0] = s * pasn;
+          double r = 1.0;
+#pragma unroll
+          for (int ii = 1; ii <= 6; ii++) {
+            if (ii <= n) { r *= 4.0; cur[ii] = (r * cur[ii - 1] - tprev[k][ii - 1]) / (r - 1.0); }
+          }
+          const double diag = cur[n];
+          res[k] = diag;
+          if (!not_converged(diag, last)) done[k] = true;
+          last = diag;
+#pragma unroll
+          for (int ii = 0; ii <= 6; ii++) if (ii <= n) tprev[k][ii] = cur[ii];
+        }
+      }
+    }
+  }
+  return res[0] + res[1];
+}
+
+// integ_relline_bin (src/Relprofile.cpp:650-726) without the deep Romberg levels: returns the bin integral,
+// or (deferred = true) the edge terms only, with [ra, rb] the interval still to be integrated.
+__device__ double integ_bin_phase1(const RelbCtx &c, double rlo0, double rhi0, bool &deferred, double &ra, double &rb) {
+  deferred = false;
   double flu = 0.0;
   double gblo = (rlo0 / 1.0 - c.gmin) * c.del_g;
   if (gblo < 0.0) gblo = 0.0; else if (gblo > 1.0) gblo = 1.0;
@@ -123,43 +230,33 @@ __device__ double integ_relline_bin(const RelbCtx &c, double rlo0, double rhi0, 
   if (gbhi < 0.0) gbhi = 0.0; else if (gbhi > 1.0) gbhi = 1.0;
   if (gbhi == 0) return 0.0;
   double rlo = rlo0, rhi = rhi0, hlo, hhi;
-  const bool edge_lo = (gblo <= GFAC_H), edge_hi = (gbhi >= (1.0 - GFAC_H));
-  if (edge_lo) {
-    rlo = gstar2ener(GFAC_H, c.gmin, c.gmax);
-    if (gbhi <= GFAC_H) rlo = -1.0;
-  }
-  if (edge_hi) {
-    rhi = gstar2ener(1 - GFAC_H, c.gmin, c.gmax);
-    if (gblo >= (1.0 - GFAC_H)) rhi = -1.0;
-  }
-  const bool do_romb = (rhi >= 0) && (rlo >= 0) && (rlo >= 1.0 * 0.95);
-  double f2 = 0.0;
-  if (do_romb) {  // src/Relprofile.cpp:628-647
-    bool c0, c1;
-    f2 += romberg<ITERMAX>(rlo, rhi, 0, c, c0);
-    if (ITERMAX < 5 && !c0) { complete = false; return 0.0; }
-    f2 += romberg<ITERMAX>(rlo, rhi, 1, c, c1);
-    if (ITERMAX < 5 && !c1) { complete = false; return 0.0; }
-  }
-  if (edge_lo) {
+  if (gblo <= GFAC_H) {
     hlo = gblo;
     hhi = GFAC_H;
-    if (gbhi <= GFAC_H) hhi = gbhi;
+    rlo = gstar2ener(GFAC_H, c.gmin, c.gmax);
+    if (gbhi <= GFAC_H) { hhi = gbhi; rlo = -1.0; }
     flu = flu + int_edge(hlo, hhi, c);
   }
-  if (edge_hi) {
+  if (gbhi >= (1.0 - GFAC_H)) {
     hhi = gbhi;
     hlo = 1.0 - GFAC_H;
-    if (gblo >= (1.0 - GFAC_H)) hlo = gblo;
+    rhi = gstar2ener(1 - GFAC_H, c.gmin, c.gmax);
+    if (gblo >= (1.0 - GFAC_H)) { hlo = gblo; rhi = -1.0; }
     flu = flu + int_edge(hlo, hhi, c);
   }
   if ((rhi >= 0) && (rlo >= 0)) {
-    if (!do_romb) {
-      const double mid = (rhi + rlo) / 2.0;
-      f2 += relb_func(mid, 0, c) * (rhi - rlo);
-      f2 += relb_func(mid, 1, c) * (rhi - rlo);
+    if (rlo >= 1.0 * 0.95) {  // src/Relprofile.cpp:628-647
+      double f2;
+      if (romberg2_capped(rlo, rhi, c, f2)) flu = flu + f2;
+      else { deferred = true; ra = rlo; rb = rhi; }
+    } else {
+      double m0, m1;
+      relb2((rhi + rlo) / 2.0, c, m0, m1);
+      double f2 = 0.0;
+      f2 += m0 * (rhi - rlo);
+      f2 += m1 * (rhi - rlo);
+      flu = flu + f2;
     }
-    flu = flu + f2;
   }
   return flu;
 }
@@ -188,20 +285,27 @@ constexpr int LN_NT = 256;
 constexpr int LN_BUF = 2048;   // contribution slots per sub-batch
 constexpr int LN_MAXR = 64;    // radii per sub-batch
 struct LnRad {
-  double gmin, gmax, del_g, emis, weight;
+  double gmin, gmax, del_g, scale, weight;
   int ielo, iehi, off, gi;
 };
 struct LnSmem {
   double contrib[LN_BUF];
+  double def_a[LN_BUF / 4], def_b[LN_BUF / 4];   // work list of phase 2: interval still to integrate
   LnRad rad[LN_MAXR + 1];
-  double gstar[2 * NG];
-  unsigned short list[LN_BUF];
+  unsigned short def_item[LN_BUF / 4];
   int nrad, ndef, cursor, jlo, jhi, resume;   // resume: first bin still to do of radius `cursor` (-1 = all)
+  int zjlo, zjhi;
 };
+constexpr int LN_MAXDEF = LN_BUF / 4;
+
+__device__ __forceinline__ void ln_ctx(const LnRad &lr, const double2 *g_trff, const double2 *g_cosne, int limb, RelbCtx &c) {
+  c.gmin = lr.gmin; c.gmax = lr.gmax; c.del_g = lr.del_g; c.scale = lr.scale;
+  c.trff = g_trff + (size_t) lr.gi * NG; c.cosne = g_cosne + (size_t) lr.gi * NG; c.limb = limb;
+}
 
 __global__ void __launch_bounds__(LN_NT, 3) k_line(const VPar *__restrict__ vps, DevTables T, Scratch S,
-                                                const double *__restrict__ egrid, int n_ener, int grid_mode,
-                                                int ne_stride, int nz_stride, int n_acc) {
+                                                   const double *__restrict__ egrid, int n_ener, int grid_mode,
+                                                   int ne_stride, int nz_stride, int n_acc) {
   extern __shared__ __align__(16) unsigned char smraw[];
   LnSmem &sm = *reinterpret_cast<LnSmem *>(smraw);
   double *acc = reinterpret_cast<double *>(smraw + sizeof(LnSmem));   // [n_acc]
@@ -228,10 +332,8 @@ __global__ void __launch_bounds__(LN_NT, 3) k_line(const VPar *__restrict__ vps,
   const double *g_re = S.re + (size_t) v * NR;
   const double2 *g_trff = reinterpret_cast<const double2 *>(S.trff) + (size_t) v * NR * NG;
   const double2 *g_cosne = reinterpret_cast<const double2 *>(S.cosne) + (size_t) v * NR * NG;
-  if (t < NG) sm.gstar[t] = T.gstar[t];
-  if (t < NG - 1) sm.gstar[NG + t] = 1.0 / (T.gstar[t + 1] - T.gstar[t]);
   for (int j = t; j < n_acc; j += LN_NT) acc[j] = 0.0;
-  if (t == 0) { sm.cursor = ia; sm.resume = -1; }
+  if (t == 0) { sm.cursor = ia; sm.resume = -1; sm.zjlo = n_ener; sm.zjhi = -1; }
   __syncthreads();
 
   while (true) {
@@ -249,7 +351,7 @@ __global__ void __launch_bounds__(LN_NT, 3) k_line(const VPar *__restrict__ vps,
         lr.gmin = S.gmin[(size_t) v * NR + i];
         lr.gmax = S.gmax[(size_t) v * NR + i];
         lr.del_g = 1. / (lr.gmax - lr.gmin);
-        lr.emis = S.emis[(size_t) v * NR + i];
+        lr.scale = lr.del_g * S.emis[(size_t) v * NR + i];
         lr.weight = trapez_single(g_re, i, NR) / 2;
         if ((lr.gmax > e_first) && (lr.gmin < e_last)) {  // src/Relprofile.cpp:863-878
           double egmin = lr.gmin, egmax = lr.gmax;
@@ -284,42 +386,88 @@ __global__ void __launch_bounds__(LN_NT, 3) k_line(const VPar *__restrict__ vps,
       sm.ndef = 0;
       sm.jlo = jlo;
       sm.jhi = jhi;
+      sm.zjlo = min(sm.zjlo, jlo);
+      sm.zjhi = max(sm.zjhi, jhi);
       sm.resume = next_resume;
       sm.cursor = (next_resume >= 0) ? cur + n - 1 : cur + n;
     }
     __syncthreads();
     const int nrad = sm.nrad;
     const int nitems = sm.rad[nrad].off;
-    // ---- phase 1: all items, Romberg depth capped
+    // ---- phase 1: one thread per item
     for (int item = t; item < nitems; item += LN_NT) {
       int lo = 0, hi = nrad;   // radius of this item: last r with off[r] <= item
       while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (sm.rad[m].off <= item) lo = m; else hi = m; }
       const LnRad &lr = sm.rad[lo];
       const int j = lr.ielo + (item - lr.off);
       RelbCtx c;
-      c.gmin = lr.gmin; c.gmax = lr.gmax; c.del_g = lr.del_g; c.emis = lr.emis; c.scale = lr.del_g * lr.emis;
-      c.trff = g_trff + (size_t) lr.gi * NG; c.cosne = g_cosne + (size_t) lr.gi * NG; c.gstar = sm.gstar; c.limb = limb;
+      ln_ctx(lr, g_trff, g_cosne, limb, c);
       const double elo = line_edge(egrid, j, grid_mode, zred, lineE), ehi = line_edge(egrid, j + 1, grid_mode, zred, lineE);
-      bool complete;
-      const double val = integ_relline_bin<1>(c, elo, ehi, complete);
-      if (complete) sm.contrib[item] = val;
-      else sm.list[atomicAdd(&sm.ndef, 1)] = (unsigned short) item;
+      bool deferred;
+      double ra, rb;
+      double val = integ_bin_phase1(c, elo, ehi, deferred, ra, rb);
+      if (deferred) {
+        const int d = atomicAdd(&sm.ndef, 1);
+        if (d < LN_MAXDEF) {
+          sm.def_item[d] = (unsigned short) item;
+          sm.def_a[d] = ra;
+          sm.def_b[d] = rb;
+        } else {   // list full (does not happen for physical profiles): finish the bin right here
+          sm.contrib[item] = val;   // placeholder, fixed below by the owning thread
+          double f2 = 0.0;
+          {  // serial full-depth Romberg, same arithmetic as the warp version up to the summation order
+            const double pas = rb - ra;
+            double acc2 = 0.0;
+            for (int k = 0; k < 2; k++) {
+              double fa0, fa1, fb0, fb1;
+              relb2(ra, c, fa0, fa1);
+              relb2(rb, c, fb0, fb1);
+              const double ta = k ? (fa1 + fb1) / 2.0 : (fa0 + fb0) / 2.0;
+              double prev[7], curr[7];
+              prev[0] = ta * pas;
+              double last = prev[0], pasn = pas, res = prev[0];
+              int niter = 0;
+              bool go = true;
+              while (go && niter <= 5) {
+                niter++;
+                pasn = pasn / 2.0;
+                double s = ta;
+                for (int ii = 1; ii <= (1 << niter) - 1; ii++) {
+                  double x0, x1;
+                  relb2(ra + pasn * ii, c, x0, x1);
+                  s += k ? x1 : x0;
+                }
+                curr[0] = s * pasn;
+                double r = 1.0;
+                for (int ii = 1; ii <= niter; ii++) { r *= 4.0; curr[ii] = (r * curr[ii - 1] - prev[ii - 1]) / (r - 1.0); }
+                res = curr[niter];
+                go = not_converged(res, last);
+                last = res;
+                for (int ii = 0; ii <= niter; ii++) prev[ii] = curr[ii];
+              }
+              acc2 += res;
+            }
+            f2 = acc2;
+          }
+          val = val + f2;
+        }
+      }
+      sm.contrib[item] = val;
     }
     __syncthreads();
-    // ---- phase 2: the bins that need the full Romberg depth
-    const int ndef = sm.ndef;
-    for (int d = t; d < ndef; d += LN_NT) {
-      const int item = sm.list[d];
-      int lo = 0, hi = nrad;
-      while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (sm.rad[m].off <= item) lo = m; else hi = m; }
-      const LnRad &lr = sm.rad[lo];
-      const int j = lr.ielo + (item - lr.off);
-      RelbCtx c;
-      c.gmin = lr.gmin; c.gmax = lr.gmax; c.del_g = lr.del_g; c.emis = lr.emis; c.scale = lr.del_g * lr.emis;
-      c.trff = g_trff + (size_t) lr.gi * NG; c.cosne = g_cosne + (size_t) lr.gi * NG; c.gstar = sm.gstar; c.limb = limb;
-      const double elo = line_edge(egrid, j, grid_mode, zred, lineE), ehi = line_edge(egrid, j + 1, grid_mode, zred, lineE);
-      bool complete;
-      sm.contrib[item] = integ_relline_bin<5>(c, elo, ehi, complete);
+    // ---- phase 2: one warp per bin that needs the deeper Romberg levels
+    {
+      const int ndef = min(sm.ndef, LN_MAXDEF);
+      const int warp = t >> 5, lane = t & 31;
+      for (int d = warp; d < ndef; d += LN_NT / 32) {
+        const int item = sm.def_item[d];
+        int lo = 0, hi = nrad;
+        while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (sm.rad[m].off <= item) lo = m; else hi = m; }
+        RelbCtx c;
+        ln_ctx(sm.rad[lo], g_trff, g_cosne, limb, c);
+        const double f2 = romberg2_warp(sm.def_a[d], sm.def_b[d], c);
+        if (lane == 0) sm.contrib[item] = sm.contrib[item] + f2;
+      }
     }
     __syncthreads();
     // ---- phase 3: ordered accumulation (ascending radius index = the reference's loop order)
@@ -333,7 +481,13 @@ __global__ void __launch_bounds__(LN_NT, 3) k_line(const VPar *__restrict__ vps,
     }
     __syncthreads();
   }
-  for (int j = t; j < n_ener; j += LN_NT) {
+  // only the bins this zone touched are written; the range travels with the row
+  const int zjlo = sm.zjlo, zjhi = sm.zjhi;
+  if (t == 0) {
+    S.zrange[((size_t) v * NZMAX + z) * 2] = zjlo;
+    S.zrange[((size_t) v * NZMAX + z) * 2 + 1] = zjhi;
+  }
+  for (int j = zjlo + t; j <= zjhi; j += LN_NT) {
     const double elo = line_edge(egrid, j, grid_mode, zred, lineE), ehi = line_edge(egrid, j + 1, grid_mode, zred, lineE);
     flux[j] = acc[j] / (0.5 * (elo + ehi));
   }
