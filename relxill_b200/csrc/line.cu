@@ -13,9 +13,9 @@
 //   phase 1  one thread per item.  Edge terms, midpoint bins and Romberg bins up to two halvings are
 //            finished here; a bin whose Romberg integral has not converged by then (the horns of the
 //            profile, a few per cent of the bins) is pushed on a shared-memory work list.
-//   phase 2  one WARP per listed bin: the dyadic abscissae of the deeper Romberg levels are evaluated
-//            in parallel across the lanes (17 points for levels <= 4, 65 for levels <= 6) and the
-//            tableau is built from masked warp sums.
+//   phase 2  one HALF WARP per listed bin: the dyadic abscissae of the deeper Romberg levels are
+//            evaluated in parallel across the lanes (17 points for levels <= 4, 65 for levels <= 6) and
+//            the tableau is built from class sums of one xor-butterfly.
 //   phase 3  per energy bin, the sub-batch's contributions are added in ascending-radius order into the
 //            zone accumulator -> no atomics on data, bit-reproducible, the reference's summation order.
 //
@@ -127,89 +127,116 @@ __device__ bool romberg2_capped(double a, double b, const RelbCtx &c, double &ou
   return !bad;
 }
 
-// sum over the lanes selected by `sel` (all lanes participate), fixed butterfly order
-__device__ __forceinline__ double warp_masked_sum(double v, bool sel) {
-  double x = sel ? v : 0.0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-  return x;
+// Richardson step of the Romberg tableau, t[ii] = (4^ii t[ii-1] - tprev[ii-1]) / (4^ii - 1), with the
+// divisions replaced by the tabulated reciprocals
+__device__ __forceinline__ double richardson(int ii, double cur_lo, double prev_lo) {
+  const double r4[7] = {1.0, 4.0, 16.0, 64.0, 256.0, 1024.0, 4096.0};
+  const double inv[7] = {0.0, 1.0 / 3.0, 1.0 / 15.0, 1.0 / 63.0, 1.0 / 255.0, 1.0 / 1023.0, 1.0 / 4095.0};
+  return (r4[ii] * cur_lo - prev_lo) * inv[ii];
 }
 
-// Full-depth Romberg of one bin by a whole warp (all lanes pass the same a, b, c; all lanes return the sum
-// of the two branch integrals).  Levels 1..4 use the 17 dyadic points of spacing (b-a)/16, levels 5..6 the
-// 65 points of spacing (b-a)/64.
-__device__ double romberg2_warp(double a, double b, const RelbCtx &c) {
-  const int lane = threadIdx.x & 31;
+// Full-depth Romberg of one bin by a HALF warp (16 lanes; the two halves of a warp work on different bins;
+// `active` is uniform per half; all 32 lanes must call).  All lanes of the half return the sum of the two
+// branch integrals.  Levels 1..4 use the 17 dyadic points of spacing (b-a)/16 (lane h evaluates point h+1,
+// lane 0 also the lower end point), levels 5..6 the 65 points of spacing (b-a)/64.  The level sums come from
+// one xor-butterfly per depth: after the steps 8,4,2 the lanes whose index has the same low bits hold the sum
+// of their residue class, i.e. exactly the points that are new at one Romberg level.
+__device__ double romberg2_half(double a, double b, const RelbCtx &c, bool active) {
+  const unsigned FULL = 0xffffffffu;
+  const int h = threadIdx.x & 15;          // lane inside the half
+  const int base = threadIdx.x & 16;       // first lane of this half inside the warp
   const double pas = b - a;
   double res[2] = {0.0, 0.0};
-  bool done[2] = {false, false};
-  double tprev[2][7];   // previous tableau row per branch: tprev[k][ii] = t[ii][niter-1-ii]
-  double ta[2];
-  {  // ---- points of depth 4
-    const double pas4 = pas / 16.0;
-    double v0 = 0.0, v1 = 0.0;
-    if (lane <= 16) relb2(lane == 16 ? b : a + pas4 * lane, c, v0, v1);
-    const double va[2] = {v0, v1};
+  bool done[2] = {!active, !active};
+  double tprev[2][7], ta[2];
+  // ---- depth 4: point p = h + 1 (p = 16 is the upper end point), lane 0 additionally p = 0
+  const double pas4 = pas / 16.0;
+  double v[2] = {0.0, 0.0}, va0 = 0.0, va1 = 0.0;
+  if (active) {
+    relb2(h == 15 ? b : a + pas4 * (h + 1), c, v[0], v[1]);
+    if (h == 0) relb2(a, c, va0, va1);
+  }
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-      const double fa = __shfl_sync(0xffffffffu, va[k], 0), fb = __shfl_sync(0xffffffffu, va[k], 16);
-      ta[k] = (fa + fb) / 2.0;
-      tprev[k][0] = ta[k] * pas;
-      double last = tprev[k][0];
-      double pasn = pas;
+  for (int k = 0; k < 2; k++) {
+    const double fa = __shfl_sync(FULL, k ? va1 : va0, base), fb = __shfl_sync(FULL, v[k], base + 15);
+    // class sums over the interior points p = 1..15 (lane h = p - 1): odd p, p = 2 mod 4, p = 4 mod 8, p = 8
+    double x = (h == 15) ? 0.0 : v[k];
+    const double n1 = __shfl_sync(FULL, x, base + 7);                 // p = 8
+    x += __shfl_xor_sync(FULL, x, 8);
+    const double n2 = __shfl_sync(FULL, x, base + 3);                 // p = 4, 12
+    x += __shfl_xor_sync(FULL, x, 4);
+    const double n3 = __shfl_sync(FULL, x, base + 1);                 // p = 2, 6, 10, 14
+    x += __shfl_xor_sync(FULL, x, 2);
+    const double n4 = __shfl_sync(FULL, x, base + 0);                 // odd p
+    if (done[k]) continue;
+    ta[k] = (fa + fb) / 2.0;
+    tprev[k][0] = ta[k] * pas;
+    double last = tprev[k][0], pasn = pas, sum = ta[k];
+    const double newp[5] = {0.0, n1, n2, n3, n4};
 #pragma unroll
-      for (int n = 1; n <= 4; n++) {
-        pasn = pasn / 2.0;
-        const int stride = 16 >> n;
-        const double s = ta[k] + warp_masked_sum(va[k], lane > 0 && lane < 16 && (lane & (stride - 1)) == 0);
-        if (!done[k]) {
-          double cur[7];
-          cur[0] = s * pasn;
-          double r = 1.0;
+    for (int n = 1; n <= 4; n++) {
+      pasn = pasn * 0.5;
+      sum += newp[n];
+      if (!done[k]) {
+        double cur[7];
+        cur[0] = sum * pasn;
 #pragma unroll
-          for (int ii = 1; ii <= 4; ii++) {
-            if (ii <= n) { r *= 4.0; cur[ii] = (r * cur[ii - 1] - tprev[k][ii - 1]) / (r - 1.0); }
-          }
-          const double diag = cur[n];
-          res[k] = diag;
-          if (!not_converged(diag, last)) done[k] = true;
-          last = diag;
+        for (int ii = 1; ii <= 4; ii++) if (ii <= n) cur[ii] = richardson(ii, cur[ii - 1], tprev[k][ii - 1]);
+        res[k] = cur[n];
+        if (!not_converged(cur[n], last)) done[k] = true;
+        last = cur[n];
 #pragma unroll
-          for (int ii = 0; ii <= 4; ii++) if (ii <= n) tprev[k][ii] = cur[ii];
-        }
+        for (int ii = 0; ii <= 4; ii++) if (ii <= n) tprev[k][ii] = cur[ii];
       }
     }
   }
-  if (!(done[0] && done[1])) {  // ---- points of depth 6 (levels 5 and 6)
+  // ---- depth 6 (rare): 63 interior points, lane h takes p = h + 1 + 16 q, q = 0..3 (p = 64 is the end point)
+  const bool need6 = !(done[0] && done[1]);
+  if (__any_sync(FULL, need6)) {
     const double pas6 = pas / 64.0;
-    double w0[2], w1[2], e0 = 0.0, e1 = 0.0;
-    relb2(a + pas6 * lane, c, w0[0], w1[0]);          // points 0..31 (point 0 = a, unused in the sums)
-    relb2(a + pas6 * (lane + 32), c, w0[1], w1[1]);   // points 32..63
-    (void) e0; (void) e1;
+    double w0[4], w1[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      w0[q] = 0.0; w1[q] = 0.0;
+      const int pidx = h + 1 + 16 * q;
+      if (need6 && pidx < 64) relb2(a + pas6 * pidx, c, w0[q], w1[q]);
+    }
 #pragma unroll
     for (int k = 0; k < 2; k++) {
-      if (done[k]) continue;   // uniform across the warp
-      double last = res[k];
+      // new points of level 6: odd p; of level 5: p = 2 mod 4 (the others were used by levels <= 4)
+      double o6 = 0.0, o5 = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int pidx = h + 1 + 16 * q;
+        const double val = k ? w1[q] : w0[q];
+        if (pidx < 64) {
+          if (pidx & 1) o6 += val;
+          else if ((pidx & 3) == 2) o5 += val;
+        }
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        o6 += __shfl_xor_sync(FULL, o6, o);
+        o5 += __shfl_xor_sync(FULL, o5, o);
+      }
+      if (done[k]) continue;
+      // the level-4 trapezoid sum is recovered from the tableau row: cur[0] = sum * pasn
       double pasn = pas / 16.0;
+      double sum = tprev[k][0] / pasn;
+      double last = res[k];
+      const double newp[2] = {o5, o6};
 #pragma unroll
       for (int n = 5; n <= 6; n++) {
-        pasn = pasn / 2.0;
-        const int stride = 64 >> n;   // 2, 1
-        const double lo = k ? w1[0] : w0[0], hi = k ? w1[1] : w0[1];
-        const double s = ta[k] + warp_masked_sum(lo, lane > 0 && (lane & (stride - 1)) == 0)
-                         + warp_masked_sum(hi, (lane & (stride - 1)) == 0);
+        pasn = pasn * 0.5;
+        sum += newp[n - 5];
         if (!done[k]) {
           double cur[7];
-          cur[0] = s * pasn;
-          double r = 1.0;
+          cur[0] = sum * pasn;
 #pragma unroll
-          for (int ii = 1; ii <= 6; ii++) {
-            if (ii <= n) { r *= 4.0; cur[ii] = (r * cur[ii - 1] - tprev[k][ii - 1]) / (r - 1.0); }
-          }
-          const double diag = cur[n];
-          res[k] = diag;
-          if (!not_converged(diag, last)) done[k] = true;
-          last = diag;
+          for (int ii = 1; ii <= 6; ii++) if (ii <= n) cur[ii] = richardson(ii, cur[ii - 1], tprev[k][ii - 1]);
+          res[k] = cur[n];
+          if (!not_converged(cur[n], last)) done[k] = true;
+          last = cur[n];
 #pragma unroll
           for (int ii = 0; ii <= 6; ii++) if (ii <= n) tprev[k][ii] = cur[ii];
         }
@@ -293,6 +320,7 @@ struct LnSmem {
   double def_a[LN_BUF / 4], def_b[LN_BUF / 4];   // work list of phase 2: interval still to integrate
   LnRad rad[LN_MAXR + 1];
   unsigned short def_item[LN_BUF / 4];
+  unsigned char item_rad[LN_BUF];                 // sub-batch radius of every item
   int nrad, ndef, cursor, jlo, jhi, resume;   // resume: first bin still to do of radius `cursor` (-1 = all)
   int zjlo, zjhi;
 };
@@ -394,11 +422,12 @@ __global__ void __launch_bounds__(LN_NT, 3) k_line(const VPar *__restrict__ vps,
     __syncthreads();
     const int nrad = sm.nrad;
     const int nitems = sm.rad[nrad].off;
+    for (int r = t >> 5; r < nrad; r += LN_NT / 32)   // item -> radius map, one warp per radius
+      for (int q = sm.rad[r].off + (t & 31); q < sm.rad[r + 1].off; q += 32) sm.item_rad[q] = (unsigned char) r;
+    __syncthreads();
     // ---- phase 1: one thread per item
     for (int item = t; item < nitems; item += LN_NT) {
-      int lo = 0, hi = nrad;   // radius of this item: last r with off[r] <= item
-      while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (sm.rad[m].off <= item) lo = m; else hi = m; }
-      const LnRad &lr = sm.rad[lo];
+      const LnRad &lr = sm.rad[sm.item_rad[item]];
       const int j = lr.ielo + (item - lr.off);
       RelbCtx c;
       ln_ctx(lr, g_trff, g_cosne, limb, c);
@@ -455,18 +484,27 @@ __global__ void __launch_bounds__(LN_NT, 3) k_line(const VPar *__restrict__ vps,
       sm.contrib[item] = val;
     }
     __syncthreads();
-    // ---- phase 2: one warp per bin that needs the deeper Romberg levels
+    // ---- phase 2: one half warp per bin that needs the deeper Romberg levels
     {
       const int ndef = min(sm.ndef, LN_MAXDEF);
-      const int warp = t >> 5, lane = t & 31;
-      for (int d = warp; d < ndef; d += LN_NT / 32) {
-        const int item = sm.def_item[d];
-        int lo = 0, hi = nrad;
-        while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (sm.rad[m].off <= item) lo = m; else hi = m; }
+      const int half = t >> 4, hl = t & 15;
+      const int nloop = (ndef + LN_NT / 16 - 1) / (LN_NT / 16);
+      for (int it = 0; it < nloop; it++) {
+        const int d = it * (LN_NT / 16) + half;
+        const bool active = d < ndef;
         RelbCtx c;
-        ln_ctx(sm.rad[lo], g_trff, g_cosne, limb, c);
-        const double f2 = romberg2_warp(sm.def_a[d], sm.def_b[d], c);
-        if (lane == 0) sm.contrib[item] = sm.contrib[item] + f2;
+        double ra = 0.0, rb = 1.0;
+        int item = 0;
+        if (active) {
+          item = sm.def_item[d];
+          ln_ctx(sm.rad[sm.item_rad[item]], g_trff, g_cosne, limb, c);
+          ra = sm.def_a[d];
+          rb = sm.def_b[d];
+        } else {
+          ln_ctx(sm.rad[0], g_trff, g_cosne, limb, c);
+        }
+        const double f2 = romberg2_half(ra, rb, c, active);
+        if (active && hl == 0) sm.contrib[item] = sm.contrib[item] + f2;
       }
     }
     __syncthreads();
