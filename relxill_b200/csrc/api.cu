@@ -43,8 +43,8 @@ void set_err(const std::string &s) {
     }                                                                       \
   } while (0)
 
-enum KFam { KF_SYSPAR, KF_ZONE, KF_FINE, KF_DIST, KF_LINE, KF_XILL, KF_CONV, KF_FINISH, KF_MEMSET, KF_COUNT };
-const char *KF_NAMES[KF_COUNT] = {"k_syspar", "k_zone", "k_fine", "k_dist", "k_line", "k_xill", "k_conv", "k_linefinish", "memset"};
+enum KFam { KF_SYSPAR, KF_ZONE, KF_FINE, KF_DIST, KF_LINE, KF_XILL, KF_CONV, KF_FINISH, KF_NTH, KF_PRIMNTH, KF_COUNT };
+const char *KF_NAMES[KF_COUNT] = {"k_syspar", "k_zone", "k_fine", "k_dist", "k_line", "k_xill", "k_conv", "k_linefinish", "k_nth", "k_prim_nth"};
 
 struct Engine {
   std::mutex mu;
@@ -100,9 +100,10 @@ template <class T> bool salloc(Engine &E, T *&p, size_t n) {
   return true;
 }
 
-int ensure_scratch(Engine &E, long cap, int nz_cap, int ne_cap, int nex_stride) {
+int ensure_scratch(Engine &E, long cap, int nz_cap, int ne_cap, int nex_stride, bool nth) {
   Scratch &S = E.S;
-  if (S.cap >= cap && S.nz_cap >= nz_cap && S.ne_line_cap >= ne_cap && S.nex_stride >= nex_stride) return 0;
+  if (S.cap >= cap && S.nz_cap >= nz_cap && S.ne_line_cap >= ne_cap && S.nex_stride >= nex_stride && (!nth || S.nth_spt)) return 0;
+  nth = nth || S.nth_spt != nullptr;
   cap = std::max(cap, S.cap);
   nz_cap = std::max(nz_cap, S.nz_cap);
   ne_cap = std::max(ne_cap, S.ne_line_cap);
@@ -123,6 +124,10 @@ int ensure_scratch(Engine &E, long cap, int nz_cap, int ne_cap, int nex_stride) 
   ok &= salloc(E, S.relflux, c * nz_cap * ne_cap) && salloc(E, S.dist, c * NZMAX * MAX_INCL);
   ok &= salloc(E, S.xillz, c * nz_cap * (size_t) std::max(nex_stride, 1)) && salloc(E, S.status, c);
   ok &= salloc(E, E.d_total, c * NCONV);
+  if (nth) {
+    ok &= salloc(E, S.nth_gam, c * NTH_MAX * NTH_SOL) && salloc(E, S.nth_g, c * NTH_MAX * NTH_SOL);
+    ok &= salloc(E, S.nth_spt, c * NTH_MAX * NTH_SOL) && salloc(E, S.nth_jmax, c * NTH_SOL);
+  }
   if (!ok) {
     free_scratch(E);
     set_err("out of device memory for the scratch arena");
@@ -222,8 +227,10 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st)
   const int ne_line = (m.type == T_LINE) ? b->n_flux : NCONV;
   const int nex_stride = relxill ? E.tables->xill_host(m.prim).stride : 1;
   const int n_incl = relxill ? E.tables->xill_host(m.prim).n_incl : 0;
-  const long cap = std::min(b->n, E.max_chunk);
-  if (ensure_scratch(E, cap, b->nz_max, ne_line, nex_stride)) return -2;
+  const bool nth = relxill && m.prim == PRIM_NTHCOMP;
+  // the Kompaneets work arrays take 1.4 MB per vector: smaller chunks for the Cp models
+  const long cap = std::min(b->n, nth ? std::min<long>(E.max_chunk, 2048) : E.max_chunk);
+  if (ensure_scratch(E, cap, b->nz_max, ne_line, nex_stride, nth)) return -2;
   const Scratch &S = E.S;
   b->launches = 0;
   for (int k = 0; k < KF_COUNT; k++) { b->kt_ms[k] = 0; b->kt_n[k] = 0; }
@@ -236,6 +243,7 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st)
     tm.begin(); launch_syspar(vps, T, S, nc, 1, st); tm.end(KF_SYSPAR);
     if (relxill) {
       tm.begin(); launch_zone(vps, T, S, nc, st); tm.end(KF_ZONE);
+      if (nth) { tm.begin(); launch_nth(vps, T, S, nc, st); tm.end(KF_NTH); }
       if (b->any_corr) { tm.begin(); launch_syspar(vps, T, S, nc, 2, st); tm.end(KF_SYSPAR); }
     }
     tm.begin(); launch_fine(vps, T, S, nc, st); tm.end(KF_FINE);
@@ -250,6 +258,9 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st)
       if (relxill) {
         tm.begin(); launch_xill(vps, T, S, nc, which, b->nz_max, E.tables->xill_host(m.prim).n_ener, n_incl, st); tm.end(KF_XILL);
         tm.begin(); launch_conv(vps, T, S, nc, b->d_energy, b->n_flux, out, E.d_total, which, 0, st); tm.end(KF_CONV);
+        if (nth) {
+          tm.begin(); launch_prim_nth(vps, T, S, nc, E.d_total, b->d_energy, b->n_flux, out, st); tm.end(KF_PRIMNTH);
+        }
       } else {
         tm.begin(); launch_conv(vps, T, S, nc, b->d_energy, b->n_flux, out, nullptr, 0, 1, st); tm.end(KF_CONV);
       }
@@ -310,7 +321,6 @@ relxill_b200_batch *relxill_b200_prepare(const char *model, const double *energy
   const ModelDef *m = find_model(model);
   if (!m) { set_err(std::string("unknown model ") + model); return nullptr; }
   if (n_vec < 1 || n_flux < 1) { set_err("empty batch or energy grid"); return nullptr; }
-  if (m->prim == PRIM_NTHCOMP) { set_err("nthcomp models are not implemented on the device yet"); return nullptr; }
   if (m->type == T_LINE && n_flux > line_max_bins()) {
     set_err("line models: energy grids above " + std::to_string(line_max_bins()) + " bins are not supported yet");
     return nullptr;

@@ -16,6 +16,7 @@ constexpr int LP_NA = 20, LP_NH = 250, LP_NRT = 100;
 constexpr int RR_NR = 50, RR_NG = 20;
 constexpr int MAX_INCL = 16;
 constexpr int NTH_MAX = 900;   // nthcomp photon grid (src/donthcomp.c)
+constexpr int NTH_SOL = 64;    // Kompaneets solves per vector: one per zone + one for the source (<= NZMAX + 1)
 
 enum { EMIS_BKN = 1, EMIS_LP = 2 };
 enum { PRIM_NONE = 0, PRIM_ECUT = 1, PRIM_NTHCOMP = 2 };
@@ -123,6 +124,10 @@ struct Scratch {
   double *dist;                                               // [cap][NZMAX][MAX_INCL]
   double *xillz;                                              // [cap][nz_cap][nex_stride]
   int *status;                                                // [cap]
+  // nthcomp (allocated only for Cp models): Kompaneets work arrays and solutions, [cap][NTH_MAX][NTH_SOL]
+  // with the solve index fastest (coalesced across the threads of a vector's block)
+  double *nth_gam, *nth_g, *nth_spt;
+  int *nth_jmax;                                              // [cap][NTH_SOL]
 };
 
 }  // namespace rx

@@ -22,4 +22,8 @@ void launch_xill(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
 void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
                  double *out, double *total, int which, int mode, cudaStream_t st);
 
+void launch_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, cudaStream_t st);
+void launch_prim_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, double *total, const double *user_e,
+                     int n_flux, double *out, cudaStream_t st);
+
 }  // namespace rx

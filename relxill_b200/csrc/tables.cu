@@ -437,6 +437,112 @@ std::string Tables::load_xill(int which) {
   return "";
 }
 
+// Multicolour-disk photon spectrum shape used as the nthcomp seed (XSPEC diskbb interpolation formula as in
+// reference src/donthcomp.c:49-108, f_mcdint__).  Host only: evaluated once for the fixed kT_bb = 0.05 keV.
+static double mcd_value(double et) {
+  static const double gc[3] = {.078196667, -1.066202, 1.192418};
+  static const double gw[3] = {.5207874, .513457, .4077983};
+  static const double gn[3] = {.3728691, .039775528, .037766505};
+  static const double res[98] = {
+      9.6198382e-4, .0010901181, .0012310012, .0013841352, .0015481583, .0017210036, .0018988943, .002076939,
+      .0022484281, .0024049483, .0025366202, .0026316255, .0026774985, .0026613059, .0025708784, .0023962965,
+      .002130655, .0017725174, .0013268656, 8.0657672e-4, 2.3337584e-4, -3.6291778e-4, -9.4443569e-4,
+      -.0014678875, -.0018873741, -.0021588493, -.0022448371, -.0021198179, -.0017754602, -.0012246034,
+      -5.0414167e-4, 3.2507078e-4, .0011811065, .0019673402, .0025827094, .0029342526, .0029517083, .0026012166,
+      .0018959062, 9.0128649e-4, -2.6757144e-4, -.0014567885, -.002492855, -.0032079776, -.0034678637,
+      -.0031988217, -.0024080969, -.001193624, 2.6134145e-4, .0017117758, .0028906898, .0035614435, .0035711778,
+      .0028921374, .0016385898, 4.9857464e-5, -.0015572671, -.0028578151, -.0035924212, -.0036253044,
+      -.002975086, -.0018044436, -3.7796664e-4, .0010076215, .0020937327, .0027090854, .0028031667, .0024276576,
+      .0017175597, 8.1030795e-4, -1.2592304e-4, -9.4888491e-4, -.0015544816, -.0018831972, -.0019203142,
+      -.0016905849, -.0012487737, -6.6789911e-4, -2.7079461e-5, 5.9931935e-4, .0011499748, .0015816521,
+      .0018709224, .0020129966, .0020184702, .0019089181, .0017122289, .001458377, .0011760717, 8.9046768e-4,
+      6.2190822e-4, 3.8553762e-4, 1.9155022e-4, 4.5837109e-5, -4.9177834e-5, -9.3670762e-5, -8.9622968e-5,
+      -4.01538532e-5};
+  const double log10e = 0.43429448190325182765;
+  const double loget = log10e * std::log(et);
+  double pos = (loget - log10e * std::log(.001)) / .06 + 1;
+  int j = (int) pos;
+  double resfact;
+  if (j < 1) resfact = res[0];
+  else if (j >= 98) resfact = res[97];
+  else { pos -= j; resfact = res[j - 1] * (1. - pos) + res[j] * pos; }
+  double gaufact = 1.;
+  for (j = 1; j <= 3; ++j) {
+    const double z = (loget - gc[j - 1]) / gw[j - 1];
+    gaufact += gn[j - 1] * std::exp(-z * z / 2.);
+  }
+  return std::pow(et / .001, -.66666666666666663) * 193.21556 * (std::pow(et, 1.663753) * .52876731 + 1.) * std::exp(-et) * gaufact
+         * (resfact + 1.);
+}
+
+// Everything in the Kompaneets set-up that depends only on the photon grid, i.e. on the seed temperature,
+// which relxill fixes at kT_bb = 0.05 keV (reference src/relutility.c:625-632): the grid x, the Cooper
+// coefficient c2, the Klein-Nishina ratio, x^3 and the disk-blackbody photon production rate
+// (src/donthcomp.c:467-585).  Computed once on the host, kept in HBM.
+void Tables::load_nthcomp() {
+  if (have_nth_) return;
+  const double log10e = 0.43429448190325182765;
+  const double tempbb = 0.05 / 511.;
+  const double delta = .02;
+  const double xmin = tempbb * 1e-4;
+  const int N = NTH_MAX;
+  std::vector<double> x(N + 1), w(N), c2(N), rel(N), x3(N + 1), dph(N, 0.0);
+  for (int j = 0; j <= N; j++) x[j] = xmin * std::pow(10., j * delta);
+  for (int j = 0; j < N; j++) {
+    const double ww = x[j];
+    const double w1 = std::sqrt(x[j] * x[j + 1]);
+    w[j] = w1;
+    c2[j] = std::pow(w1, 4.) / (w1 * 4.6 + 1. + w1 * 1.1 * w1);
+    if (ww <= .05) {
+      rel[j] = 1 - ww * 2 + ww * 26 * ww / 5;
+    } else {
+      const double z1 = (ww + 1) / (ww * (ww * ww));
+      const double z2 = ww * 2 + 1;
+      const double z3 = std::log(z2);
+      const double z4 = ww * 2 * (ww + 1) / z2;
+      const double z5 = z3 / 2 / ww;
+      const double z6 = (ww * 3 + 1) / z2 / z2;
+      rel[j] = (z1 * (z4 - z3) + z5 - z6) * .75;
+    }
+  }
+  for (int j = 0; j <= N; j++) x3[j] = std::pow(x[j], 3.);
+  int jmaxth = (int) (log10e * std::log(tempbb * 50. / xmin) / delta);
+  if (jmaxth > 900) jmaxth = 900;
+  {  // disk-blackbody seed: 5-point Gauss integration per photon-grid cell (f_xsdskb__, :142-197)
+    static const double gw5[5] = {.236926885, .47862867, .568888888, .47862867, .236926885};
+    static const double gx5[5] = {-.906179846, -.53846931, 0., .53846931, .906179846};
+    std::vector<double> ear(jmaxth), photar(jmaxth, 0.0);
+    for (int j = 1; j <= jmaxth - 1; j++) ear[j - 1] = std::sqrt(x[j - 1] * x[j]) * 511.;
+    const double tin = tempbb * 511.;
+    const int ne = jmaxth - 2;
+    for (int i = 1; i <= ne; i++) {
+      const double xn = (ear[i] - ear[i - 1]) / 2.f;
+      const double xh = xn + ear[i - 1];
+      double ph = 0.f;
+      for (int j = 0; j < 5; j++) {
+        const double e = xn * gx5[j] + xh;
+        const double flux = mcd_value(e / tin) * tin * tin * 1. / 361.;
+        ph += gw5[j] * flux;
+      }
+      photar[i - 1] = ph * xn;
+    }
+    for (int j = 1; j <= ne; j++) dph[j] = photar[j - 1] * 511. / (ear[j] - ear[j - 1]);
+    dph[0] = dph[1];
+  }
+  dt_.nth_x = upload(x);
+  dt_.nth_w = upload(w);
+  dt_.nth_c2 = upload(c2);
+  dt_.nth_rel = upload(rel);
+  dt_.nth_x3 = upload(x3);
+  dt_.nth_dphdot = upload(dph);
+  dt_.nth_jnr = (int) (log10e * std::log(.1 / xmin) / delta + 1);
+  dt_.nth_jrel = (int) (log10e * std::log(1. / xmin) / delta + 1);
+  dt_.nth_jmaxth = jmaxth;
+  dt_.nth_xmin = xmin;
+  dt_.nth_deltal = delta * std::log(10.);
+  have_nth_ = true;
+}
+
 std::string Tables::load(const std::string &dir) {
   dir_ = dir;
   load_fixed();
@@ -450,6 +556,7 @@ std::string Tables::require(bool lp, bool rrad, int prim_type) {
   if (rrad && !(err = load_rrad()).empty()) return err;
   if (prim_type == PRIM_ECUT && !(err = load_xill(0)).empty()) return err;
   if (prim_type == PRIM_NTHCOMP && !(err = load_xill(1)).empty()) return err;
+  if (prim_type == PRIM_NTHCOMP) load_nthcomp();
   return "";
 }
 

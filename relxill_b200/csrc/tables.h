@@ -33,7 +33,7 @@ class Tables {
  private:
   std::string dir_;
   DevTables dt_{};
-  bool have_rel_ = false, have_lp_ = false, have_rr_ = false, have_fixed_ = false;
+  bool have_rel_ = false, have_lp_ = false, have_rr_ = false, have_fixed_ = false, have_nth_ = false;
   XillHost xh_[2];
   std::vector<double> rr_spin_, econv_, ecoarse_;
   std::vector<void *> allocs_;
@@ -42,6 +42,7 @@ class Tables {
   template <class T> const T *upload(const std::vector<T> &v);
   template <class T> const T *upload(const T *p, size_t n);
   void load_fixed();
+  void load_nthcomp();
   std::string load_rel();
   std::string load_lp();
   std::string load_rrad();

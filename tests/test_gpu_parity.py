@@ -12,7 +12,7 @@ from common import PEAK_FLOOR, RTOL, default_grid, relerr, sample_params, walker
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz")
-GPU_MODELS = ["relline", "relline_lp", "relconv", "relconv_lp", "relxill", "relxilllp"]
+GPU_MODELS = ["relline", "relline_lp", "relconv", "relconv_lp", "relxill", "relxilllp", "relxillCp", "relxilllpCp"]
 
 
 def _conv_input(e):
@@ -68,6 +68,27 @@ def test_metric_config_vs_oracle(rx, oracle):
         got = rx.batch_eval("relxilllp", e, P)
         for a, p in zip(got, P):
             assert relerr(a, oracle.eval("relxilllp", e, p)) < RTOL
+    finally:
+        rx.set_num_zones(None)
+        oracle.set_num_zones(None)
+
+
+def test_ion_gradient_50_zones(rx, oracle):
+    """relxilllpCp with iongrad_type 1 (power law) and 2 (alpha disk), RELXILL_NUM_RZONES=50 (BASELINE config 3)."""
+    e = default_grid(3000)
+    P = walker_ball("relxilllpCp", 8)
+    P[:, 14] = [1, 2, 1, 2, 1, 2, 1, 2]
+    rx.set_num_zones(50)
+    oracle.set_num_zones(50)
+    try:
+        got, st = rx.batch_eval("relxilllpCp", e, P, return_status=True)
+        assert (st == 0).all()
+        for a, p in zip(got, P):
+            assert relerr(a, oracle.eval("relxilllpCp", e, p)) < RTOL
+        g = np.load(GOLDEN)
+        got = rx.batch_eval("relxilllpCp", g["energy"], g["relxilllpCp_z50_params"])
+        for a, b in zip(got, g["relxilllpCp_z50_flux"]):
+            assert relerr(a, b) < RTOL
     finally:
         rx.set_num_zones(None)
         oracle.set_num_zones(None)
