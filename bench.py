@@ -317,14 +317,16 @@ def run_ours(args):
     dominant = max(ktimes, key=lambda k: ktimes[k][0])
     nz = args.zones
     nex = 2999
-    alg = {  # algorithmic bytes per launch of each kernel family (DESIGN.md §kernels)
-        "k_xill": ab["xillver"] + n * nz * nex * 8.0,
-        "k_line": n * (1000 * 40 * 2 * 8.0 + 1000 * 5 * 8.0 + nz * 4096 * 8.0),
-        "k_conv": n * (nz * 4096 * 8.0 + nz * nex * 8.0 + nb * 8.0),
-        "k_fine": n * (4 * 2 * 100 * 40 * 16.0 / 1.0 * 0 + 1000 * 40 * 4 * 8.0) + n * 4 * 100 * 40 * 16.0,
+    alg = {  # algorithmic bytes per launch of each kernel family (DESIGN.md §4)
+        "k_xill": ab["xillver"] + n * nz * nex * 8.0,                       # distinct table rows + zone spectra out
+        "k_line": n * (1000 * 40 * 2 * 8.0 + 1000 * 5 * 8.0 + nz * 4096 * 8.0),  # fine trff + radius scalars + profiles out (upper bound)
+        "k_conv": n * (nz * 4096 * 8.0 + nz * nex * 8.0 + nb * 8.0),        # profiles + zone spectra in, spectrum out
+        "k_fine": n * (2 * 4 * 40 * 16.0 * 100 + 1000 * 40 * 4 * 8.0),      # 4 corners x 100 radii x 40 g* float4 + fine tables out
         "k_dist": n * (1000 * 40 * 4 * 8.0),
-        "k_syspar": n * (4 * 3 * 100 * 4.0 + 2 * 2 * 3 * 100 * 4.0 + (3 * 2500 + 2 * 50000) * 8.0 + 7 * 1000 * 8.0),
+        "k_syspar": 2 * n * (4 * 3 * 100 * 4.0 + 2 * 2 * 3 * 100 * 4.0 + (3 * 2500 + 2 * 50000) * 8.0 + 7 * 1000 * 8.0),
         "k_zone": n * (4 * 1000 * 8.0),
+        "k_nth": n * (3 * 900 * 64 * 8.0),
+        "k_prim_nth": n * (2 * 4096 * 8.0 + nb * 8.0),
     }
     k_ms, k_cnt = ktimes[dominant]
     achieved = alg.get(dominant, 0.0) / (k_ms / max(k_cnt, 1) * 1e-3) / 1e9
