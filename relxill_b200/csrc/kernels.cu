@@ -926,7 +926,7 @@ struct ConvArgs {
   int mode;               // 0 relxill, 1 convolution model (input spectrum in `out`)
 };
 
-__global__ void __launch_bounds__(CONV_NT, 1) k_conv(const VPar *__restrict__ vps, DevTables T, Scratch S, ConvArgs A) {
+__global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vps, DevTables T, Scratch S, ConvArgs A) {
   extern __shared__ __align__(16) unsigned char smraw[];
   ConvSmem &sm = *reinterpret_cast<ConvSmem *>(smraw);
   const int v = blockIdx.x, t = threadIdx.x;

@@ -25,8 +25,8 @@
 
 namespace rx {
 
-constexpr int XL_NT = 256;
-constexpr int XL_CH = 128;   // entries staged per chunk
+constexpr int XL_NT = 128;
+constexpr int XL_CH = 64;    // entries staged per chunk
 
 template <int NI>   // NI = number of inclinations known at compile time (0: run-time)
 __global__ void __launch_bounds__(XL_NT) k_xill(const VPar *__restrict__ vps, DevTables T, Scratch S, int which,
