@@ -113,6 +113,7 @@ int ensure_scratch(Engine &E, long cap, int nz_cap, int ne_cap, int nex_stride, 
   const size_t c = (size_t) cap;
   ok &= salloc(E, S.re, c * NR) && salloc(E, S.gmin, c * NR) && salloc(E, S.gmax, c * NR) && salloc(E, S.emis, c * NR);
   ok &= salloc(E, S.del_emit, c * NR) && salloc(E, S.del_inc, c * NR) && salloc(E, S.fr, c * NR);
+  ok &= salloc(E, S.zfirst, c * (NZMAX + 1)) && salloc(E, S.brk_i, c * 2) && salloc(E, S.brk_f, c * 2);
   ok &= salloc(E, S.it, c * NR) && salloc(E, S.izone, c * NR) && salloc(E, S.glim, c * 2) && salloc(E, S.reflfrac, c * 8);
   ok &= salloc(E, S.trff, c * NR * NG * 2) && salloc(E, S.cosne, c * NR * NG * 2);
   ok &= salloc(E, S.eshift, c * NZMAX) && salloc(E, S.zlxi, c * NZMAX) && salloc(E, S.zdens, c * NZMAX);

@@ -107,6 +107,9 @@ struct Scratch {
   int nex_stride;    // xillver row stride
   double *re, *gmin, *gmax, *emis, *del_emit, *del_inc, *fr;  // [cap][NR]
   int *it, *izone;                                            // [cap][NR]
+  int *zfirst;                                                // [cap][NZMAX+1] first fine-grid index with zone < z
+  int *brk_i;                                                 // [cap][2] rel-table bracket (spin, mu0)
+  double *brk_f;                                              // [cap][2] its interpolation factors
   double *glim;                                               // [cap][2] min gmin / max gmax over radii
   double *reflfrac;                                           // [cap][8]
   double *trff, *cosne;                                       // [cap][NR][NG][2]

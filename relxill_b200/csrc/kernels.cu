@@ -100,6 +100,12 @@ __global__ void __launch_bounds__(256) k_syspar(const VPar *__restrict__ vps, De
     if (sm.rt[ind_rmax] < 1000.0 && sm.rt[ind_rmax] * 1.01 > 1000.0) sm.rt[ind_rmax] = 1000.0;
     sm.ints[0] = ind_rmin;
     sm.ints[1] = 0;  // error flag
+    if (pass == 1) {  // the (a, mu0) bracket, reused by k_fine
+      S.brk_i[2 * v] = ia;
+      S.brk_i[2 * v + 1] = im;
+      S.brk_f[2 * v] = (double) ifac_a;
+      S.brk_f[2 * v + 1] = (double) ifac_mu;
+    }
   }
   __syncthreads();
   const int ind_rmin = sm.ints[0];
@@ -149,6 +155,12 @@ __global__ void __launch_bounds__(256) k_syspar(const VPar *__restrict__ vps, De
   if (sm.ints[1] != 0) {
     if (t == 0) S.status[v] = sm.ints[1];
     return;
+  }
+  if (pass == 1 && t <= vp.nz) {  // zfirst[z] = first fine-grid index whose zone is < z (zone z owns [zfirst[z+1], zfirst[z]))
+    const int *iz = S.izone + (size_t) v * NR;
+    int lo = 0, hi = NR;
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (iz[m] >= t) lo = m + 1; else hi = m; }
+    S.zfirst[(size_t) v * (NZMAX + 1) + t] = lo;
   }
 
   // ---- emissivity
@@ -650,14 +662,10 @@ __global__ void __launch_bounds__(128) k_zone(const VPar *__restrict__ vps, DevT
 __global__ void __launch_bounds__(320) k_fine(const VPar *__restrict__ vps, DevTables T, Scratch S) {
   const int v = blockIdx.y;
   if (S.status[v] != ST_OK) return;
-  const VPar &vp = vps[v];
   const int j = threadIdx.x % NG;
   const int i = blockIdx.x * 8 + threadIdx.x / NG;
-  const double mu0 = cos(vp.incl);
-  const int ia = bsearch_asc<float>(T.rel_a, REL_NA, (float) vp.a);
-  const int im = bsearch_asc<float>(T.rel_mu0, REL_NMU, (float) mu0);
-  const double fa = (double) (((float) vp.a - T.rel_a[ia]) / (T.rel_a[ia + 1] - T.rel_a[ia]));
-  const double fm = (double) (((float) mu0 - T.rel_mu0[im]) / (T.rel_mu0[im + 1] - T.rel_mu0[im]));
+  const int ia = S.brk_i[2 * v], im = S.brk_i[2 * v + 1];
+  const double fa = S.brk_f[2 * v], fm = S.brk_f[2 * v + 1];
   const int it = S.it[(size_t) v * NR + i];
   const double fr = S.fr[(size_t) v * NR + i];
   const float4 *tc = reinterpret_cast<const float4 *>(T.rel_tc);

@@ -90,10 +90,11 @@ __device__ double int_edge(double blo, double bhi, const RelbCtx &c) {  // src/R
 
 // Romberg on [a, b] for both branches, at most two halvings (src/Relprofile.cpp:524-579 with the loop cut
 // after niter = 2).  Returns true and the sum of the two integrals if both branches converged.
-__device__ bool romberg2_capped(double a, double b, const RelbCtx &c, double &out) {
+__device__ bool romberg2_capped(double a, double b, const RelbCtx &c, double &out, double (&fend)[2]) {
   double fa0, fa1, fb0, fb1, m0, m1;
   relb2(a, c, fa0, fa1);
   relb2(b, c, fb0, fb1);
+  fend[0] = fa0; fend[1] = fa1;
   const double ta0 = (fa0 + fb0) / 2.0, ta1 = (fa1 + fb1) / 2.0;
   const double pas = b - a;
   const double t00_0 = ta0 * pas, t00_1 = ta1 * pas;
@@ -141,7 +142,7 @@ __device__ __forceinline__ double richardson(int ii, double cur_lo, double prev_
 // lane 0 also the lower end point), levels 5..6 the 65 points of spacing (b-a)/64.  The level sums come from
 // one xor-butterfly per depth: after the steps 8,4,2 the lanes whose index has the same low bits hold the sum
 // of their residue class, i.e. exactly the points that are new at one Romberg level.
-__device__ double romberg2_half(double a, double b, const RelbCtx &c, bool active) {
+__device__ double romberg2_half(double a, double b, const RelbCtx &c, bool active, const double *fend) {
   const unsigned FULL = 0xffffffffu;
   const int h = threadIdx.x & 15;          // lane inside the half
   const int base = threadIdx.x & 16;       // first lane of this half inside the warp
@@ -151,14 +152,11 @@ __device__ double romberg2_half(double a, double b, const RelbCtx &c, bool activ
   double tprev[2][7], ta[2];
   // ---- depth 4: point p = h + 1 (p = 16 is the upper end point), lane 0 additionally p = 0
   const double pas4 = pas / 16.0;
-  double v[2] = {0.0, 0.0}, va0 = 0.0, va1 = 0.0;
-  if (active) {
-    relb2(h == 15 ? b : a + pas4 * (h + 1), c, v[0], v[1]);
-    if (h == 0) relb2(a, c, va0, va1);
-  }
+  double v[2] = {0.0, 0.0};
+  if (active) relb2(h == 15 ? b : a + pas4 * (h + 1), c, v[0], v[1]);   // f(a) comes from phase 1
 #pragma unroll
   for (int k = 0; k < 2; k++) {
-    const double fa = __shfl_sync(FULL, k ? va1 : va0, base), fb = __shfl_sync(FULL, v[k], base + 15);
+    const double fa = active ? fend[k] : 0.0, fb = __shfl_sync(FULL, v[k], base + 15);
     // class sums over the interior points p = 1..15 (lane h = p - 1): odd p, p = 2 mod 4, p = 4 mod 8, p = 8
     double x = (h == 15) ? 0.0 : v[k];
     const double n1 = __shfl_sync(FULL, x, base + 7);                 // p = 8
@@ -248,7 +246,7 @@ __device__ double romberg2_half(double a, double b, const RelbCtx &c, bool activ
 
 // integ_relline_bin (src/Relprofile.cpp:650-726) without the deep Romberg levels: returns the bin integral,
 // or (deferred = true) the edge terms only, with [ra, rb] the interval still to be integrated.
-__device__ double integ_bin_phase1(const RelbCtx &c, double rlo0, double rhi0, bool &deferred, double &ra, double &rb) {
+__device__ double integ_bin_phase1(const RelbCtx &c, double rlo0, double rhi0, bool &deferred, double &ra, double &rb, double (&fend)[2]) {
   deferred = false;
   double flu = 0.0;
   double gblo = (rlo0 / 1.0 - c.gmin) * c.del_g;
@@ -274,7 +272,7 @@ __device__ double integ_bin_phase1(const RelbCtx &c, double rlo0, double rhi0, b
   if ((rhi >= 0) && (rlo >= 0)) {
     if (rlo >= 1.0 * 0.95) {  // src/Relprofile.cpp:628-647
       double f2;
-      if (romberg2_capped(rlo, rhi, c, f2)) flu = flu + f2;
+      if (romberg2_capped(rlo, rhi, c, f2, fend)) flu = flu + f2;
       else { deferred = true; ra = rlo; rb = rhi; }
     } else {
       double m0, m1;
@@ -318,10 +316,11 @@ struct LnRad {
 struct LnSmem {
   double contrib[LN_BUF];
   double def_a[LN_BUF / 4], def_b[LN_BUF / 4];   // work list of phase 2: interval still to integrate
+  double def_f[LN_BUF / 4][2];                    // ... and the integrand at its lower end (both branches)
   LnRad rad[LN_MAXR + 1];
   unsigned short def_item[LN_BUF / 4];
   unsigned char item_rad[LN_BUF];                 // sub-batch radius of every item
-  int nrad, ndef, cursor, jlo, jhi, resume;   // resume: first bin still to do of radius `cursor` (-1 = all)
+  int nrad, ndef, overflow, cursor, jlo, jhi, resume;   // resume: first bin still to do of radius `cursor` (-1 = all)
   int zjlo, zjhi;
 };
 constexpr int LN_MAXDEF = LN_BUF / 4;
@@ -345,17 +344,9 @@ __global__ void __launch_bounds__(LN_NT, 3) k_line(const VPar *__restrict__ vps,
   const int limb = vp.limb;
   const double e_first = line_edge(egrid, 0, grid_mode, zred, lineE);
   const double e_last = line_edge(egrid, n_ener, grid_mode, zred, lineE);
-  const int *izone = S.izone + (size_t) v * NR;
-  // radii of this zone: izone[] is non-increasing along the (descending-radius) fine grid
-  int ia, ib;
-  {
-    int lo = 0, hi = NR;
-    while (lo < hi) { const int m = (lo + hi) >> 1; if (izone[m] > z) lo = m + 1; else hi = m; }
-    ia = lo;
-    hi = NR;
-    while (lo < hi) { const int m = (lo + hi) >> 1; if (izone[m] >= z) lo = m + 1; else hi = m; }
-    ib = lo;
-  }
+  // radii of this zone (izone[] is non-increasing along the descending-radius fine grid; k_syspar tabulated
+  // the first index of every zone)
+  const int ia = S.zfirst[(size_t) v * (NZMAX + 1) + z + 1], ib = S.zfirst[(size_t) v * (NZMAX + 1) + z];
   double *flux = S.relflux + ((size_t) v * nz_stride + z) * ne_stride;
   const double *g_re = S.re + (size_t) v * NR;
   const double2 *g_trff = reinterpret_cast<const double2 *>(S.trff) + (size_t) v * NR * NG;
@@ -412,6 +403,7 @@ __global__ void __launch_bounds__(LN_NT, 3) k_line(const VPar *__restrict__ vps,
       sm.rad[n].off = off;
       sm.nrad = n;
       sm.ndef = 0;
+      sm.overflow = 0;
       sm.jlo = jlo;
       sm.jhi = jhi;
       sm.zjlo = min(sm.zjlo, jlo);
@@ -425,89 +417,67 @@ __global__ void __launch_bounds__(LN_NT, 3) k_line(const VPar *__restrict__ vps,
     for (int r = t >> 5; r < nrad; r += LN_NT / 32)   // item -> radius map, one warp per radius
       for (int q = sm.rad[r].off + (t & 31); q < sm.rad[r + 1].off; q += 32) sm.item_rad[q] = (unsigned char) r;
     __syncthreads();
-    // ---- phase 1: one thread per item
-    for (int item = t; item < nitems; item += LN_NT) {
-      const LnRad &lr = sm.rad[sm.item_rad[item]];
-      const int j = lr.ielo + (item - lr.off);
-      RelbCtx c;
-      ln_ctx(lr, g_trff, g_cosne, limb, c);
-      const double elo = line_edge(egrid, j, grid_mode, zred, lineE), ehi = line_edge(egrid, j + 1, grid_mode, zred, lineE);
-      bool deferred;
-      double ra, rb;
-      double val = integ_bin_phase1(c, elo, ehi, deferred, ra, rb);
-      if (deferred) {
-        const int d = atomicAdd(&sm.ndef, 1);
-        if (d < LN_MAXDEF) {
-          sm.def_item[d] = (unsigned short) item;
-          sm.def_a[d] = ra;
-          sm.def_b[d] = rb;
-        } else {   // list full (does not happen for physical profiles): finish the bin right here
-          sm.contrib[item] = val;   // placeholder, fixed below by the owning thread
-          double f2 = 0.0;
-          {  // serial full-depth Romberg, same arithmetic as the warp version up to the summation order
-            const double pas = rb - ra;
-            double acc2 = 0.0;
-            for (int k = 0; k < 2; k++) {
-              double fa0, fa1, fb0, fb1;
-              relb2(ra, c, fa0, fa1);
-              relb2(rb, c, fb0, fb1);
-              const double ta = k ? (fa1 + fb1) / 2.0 : (fa0 + fb0) / 2.0;
-              double prev[7], curr[7];
-              prev[0] = ta * pas;
-              double last = prev[0], pasn = pas, res = prev[0];
-              int niter = 0;
-              bool go = true;
-              while (go && niter <= 5) {
-                niter++;
-                pasn = pasn / 2.0;
-                double s = ta;
-                for (int ii = 1; ii <= (1 << niter) - 1; ii++) {
-                  double x0, x1;
-                  relb2(ra + pasn * ii, c, x0, x1);
-                  s += k ? x1 : x0;
-                }
-                curr[0] = s * pasn;
-                double r = 1.0;
-                for (int ii = 1; ii <= niter; ii++) { r *= 4.0; curr[ii] = (r * curr[ii - 1] - prev[ii - 1]) / (r - 1.0); }
-                res = curr[niter];
-                go = not_converged(res, last);
-                last = res;
-                for (int ii = 0; ii <= niter; ii++) prev[ii] = curr[ii];
-              }
-              acc2 += res;
-            }
-            f2 = acc2;
-          }
-          val = val + f2;
-        }
-      }
-      sm.contrib[item] = val;
-    }
-    __syncthreads();
-    // ---- phase 2: one half warp per bin that needs the deeper Romberg levels
-    {
-      const int ndef = min(sm.ndef, LN_MAXDEF);
-      const int half = t >> 4, hl = t & 15;
-      const int nloop = (ndef + LN_NT / 16 - 1) / (LN_NT / 16);
-      for (int it = 0; it < nloop; it++) {
-        const int d = it * (LN_NT / 16) + half;
-        const bool active = d < ndef;
+    // ---- phase 1: one thread per item.  A bin whose Romberg integral needs more than two halvings goes on
+    // the work list; if the list is full the item is flagged (bit 7 of item_rad) and retried after phase 2
+    // has drained the list, so the result never depends on the order in which threads reach the list.
+    for (int round = 0;; round++) {
+      for (int item = t; item < nitems; item += LN_NT) {
+        const int ir = sm.item_rad[item];
+        if (round > 0 && !(ir & 0x80)) continue;
+        const LnRad &lr = sm.rad[ir & 0x7f];
+        const int j = lr.ielo + (item - lr.off);
         RelbCtx c;
-        double ra = 0.0, rb = 1.0;
-        int item = 0;
-        if (active) {
-          item = sm.def_item[d];
-          ln_ctx(sm.rad[sm.item_rad[item]], g_trff, g_cosne, limb, c);
-          ra = sm.def_a[d];
-          rb = sm.def_b[d];
-        } else {
-          ln_ctx(sm.rad[0], g_trff, g_cosne, limb, c);
+        ln_ctx(lr, g_trff, g_cosne, limb, c);
+        const double elo = line_edge(egrid, j, grid_mode, zred, lineE), ehi = line_edge(egrid, j + 1, grid_mode, zred, lineE);
+        bool deferred;
+        double ra, rb, fend[2];
+        const double val = integ_bin_phase1(c, elo, ehi, deferred, ra, rb, fend);
+        sm.item_rad[item] = (unsigned char) (ir & 0x7f);
+        if (deferred) {
+          const int d = atomicAdd(&sm.ndef, 1);
+          if (d < LN_MAXDEF) {
+            sm.def_item[d] = (unsigned short) item;
+            sm.def_a[d] = ra;
+            sm.def_b[d] = rb;
+            sm.def_f[d][0] = fend[0];
+            sm.def_f[d][1] = fend[1];
+          } else {
+            sm.item_rad[item] = (unsigned char) (ir | 0x80);
+            sm.overflow = 1;
+          }
         }
-        const double f2 = romberg2_half(ra, rb, c, active);
-        if (active && hl == 0) sm.contrib[item] = sm.contrib[item] + f2;
+        sm.contrib[item] = val;
       }
+      __syncthreads();
+      // ---- phase 2: one half warp per listed bin
+      {
+        const int ndef = min(sm.ndef, LN_MAXDEF);
+        const int half = t >> 4, hl = t & 15;
+        const int nloop = (ndef + LN_NT / 16 - 1) / (LN_NT / 16);
+        for (int it = 0; it < nloop; it++) {
+          const int d = it * (LN_NT / 16) + half;
+          const bool active = d < ndef;
+          RelbCtx c;
+          double ra = 0.0, rb = 1.0;
+          int item = 0;
+          if (active) {
+            item = sm.def_item[d];
+            ln_ctx(sm.rad[sm.item_rad[item] & 0x7f], g_trff, g_cosne, limb, c);
+            ra = sm.def_a[d];
+            rb = sm.def_b[d];
+          } else {
+            ln_ctx(sm.rad[0], g_trff, g_cosne, limb, c);
+          }
+          const double f2 = romberg2_half(ra, rb, c, active, sm.def_f[active ? d : 0]);
+          if (active && hl == 0) sm.contrib[item] = sm.contrib[item] + f2;
+        }
+      }
+      const int again = sm.overflow;
+      __syncthreads();
+      if (!again) break;
+      if (t == 0) { sm.ndef = 0; sm.overflow = 0; }
+      __syncthreads();
     }
-    __syncthreads();
     // ---- phase 3: ordered accumulation (ascending radius index = the reference's loop order)
     for (int j = sm.jlo + t; j <= sm.jhi; j += LN_NT) {
       double a = acc[j];
