@@ -38,6 +38,8 @@ RELXILL_B200_LMOD(lmodrelxill);              /* :46  relxill      (13) */
 RELXILL_B200_LMOD(lmodrelxilllp);            /* :61  relxilllp    (14) */
 RELXILL_B200_LMOD(lmodrelxilldensnthcomp);   /* :96  relxillCp    (14) */
 RELXILL_B200_LMOD(lmodrelxilllpdensnthcomp); /* :112 relxilllpCp  (17) */
+RELXILL_B200_LMOD(lmodxillver);              /* :77  xillver      (7)  */
+RELXILL_B200_LMOD(lmodxillverdensnthcomp);   /* :86  xillverCp    (8)  */
 
 /* ---------------------------------------------------------------- library state */
 /* Select the CUDA device and load the tables from `table_dir` (NULL: $RELXILL_TABLE_PATH or "./").

@@ -1324,6 +1324,71 @@ static int xillver_spectra(const XPar *x, double *flu) {
   return 0;
 }
 
+/* Standalone xillver models: interpolation over ALL axes including the inclination, interp_5d_tab
+ * (src/xilltable.c:878-996) and interp_6d_tab (:1022-1044), bracket/factor code of interp_xill_table
+ * (:1090-1181).  flu[n_ener] */
+static int xillver_spectrum_incl(const XPar *x, double incl_deg, double *flu) {
+  if (!g_xill[x->prim_type] && load_xill(x->prim_type)) return 1;
+  const XillTab *t = g_xill[x->prim_type];
+  float inp[8];
+  inp[XP_GAM] = (float) x->gam; inp[XP_AFE] = (float) x->afe; inp[XP_LXI] = (float) x->lxi;
+  inp[XP_ECT] = (float) x->ect; inp[XP_DNS] = (float) x->dens; inp[XP_INC] = (float) incl_deg;
+  int ind[6];
+  double fac[6];
+  int ax_ect = -1;
+  for (int i = 0; i < t->npar; i++) {
+    ind[i] = bsearch_f(t->vals[i], t->nvals[i], inp[t->pindex[i]]);
+    if (ind[i] < 0) ind[i] = 0; else if (ind[i] > t->nvals[i] - 2) ind[i] = t->nvals[i] - 2;
+    if (t->pindex[i] == XP_ECT) ax_ect = i;
+  }
+  for (int i = 0; i < t->npar; i++) {
+    int pind = t->pindex[i];
+    float lo = t->vals[i][0], hi = t->vals[i][t->nvals[i] - 1];
+    if (inp[pind] < lo) inp[pind] = lo; else if (inp[pind] > hi) inp[pind] = hi;
+    fac[i] = (inp[pind] - t->vals[i][ind[i]]) / (t->vals[i][ind[i] + 1] - t->vals[i][ind[i]]);
+  }
+  if (ax_ect >= 0) {
+    if (x->ect <= t->vals[3][0]) fac[ax_ect] = 0.0;
+    if (x->ect >= t->vals[3][t->nvals[3] - 1]) fac[ax_ect] = 1.0;
+  }
+  int n_ener = t->n_ener;
+  int off = (t->npar == 6) ? 1 : 0;
+  const int *n = t->nvals;
+  double f[5] = {fac[off], fac[off + 1], fac[off + 2], fac[off + 3], fac[off + 4]};
+  /* term order of interp_5d_tab: the 16 patterns of interp_5d_tab_incl with the 5th bit 0, then with it 1 */
+  static const int b16[16][4] = {{0,0,0,0},{1,0,0,0},{0,1,0,0},{0,0,1,0},{1,1,0,0},{1,0,1,0},{0,1,1,0},{1,1,1,0},
+                                 {0,0,0,1},{1,0,0,1},{0,1,0,1},{0,0,1,1},{1,1,0,1},{1,0,1,1},{0,1,1,1},{1,1,1,1}};
+  double w[32];
+  for (int h5 = 0; h5 < 2; h5++)
+    for (int c = 0; c < 16; c++)
+      w[h5 * 16 + c] = (b16[c][0] ? f[0] : (1.0 - f[0])) * (b16[c][1] ? f[1] : (1.0 - f[1])) * (b16[c][2] ? f[2] : (1.0 - f[2]))
+                       * (b16[c][3] ? f[3] : (1 - f[3])) * (h5 ? f[4] : (1 - f[4]));
+  double *s2 = (t->npar == 6) ? (double *) malloc(sizeof(double) * n_ener) : NULL;
+  for (int half = 0; half < (t->npar == 6 ? 2 : 1); half++) {
+    const float *dat[32];
+    for (int h5 = 0; h5 < 2; h5++)
+      for (int c = 0; c < 16; c++) {
+        long row;
+        int i1 = ind[off] + b16[c][0], i2 = ind[off + 1] + b16[c][1], i3 = ind[off + 2] + b16[c][2],
+            i4 = ind[off + 3] + b16[c][3], i5 = ind[off + 4] + h5;
+        if (t->npar == 5) row = ((((long) i1 * n[1] + i2) * n[2] + i3) * n[3] + i4) * n[4] + i5;
+        else row = (((((long) (ind[0] + half) * n[1] + i1) * n[2] + i2) * n[3] + i3) * n[4] + i4) * n[5] + i5;
+        dat[h5 * 16 + c] = t->data + (size_t) row * n_ener;
+      }
+    double *dst = (half == 0) ? flu : s2;
+    for (int e = 0; e < n_ener; e++) {
+      double v = w[0] * (double) dat[0][e];
+      for (int c = 1; c < 32; c++) v += w[c] * (double) dat[c][e];
+      dst[e] = v;
+    }
+  }
+  if (t->npar == 6) {
+    for (int e = 0; e < n_ener; e++) flu[e] = lin1d(fac[0], flu[e], s2[e]);
+    free(s2);
+  }
+  return 0;
+}
+
 static void xill_energy_grid(int prim_type, double *ener) { /* xilltable.c:1105-1109 */
   const XillTab *t = g_xill[prim_type];
   for (int i = 0; i < t->n_ener; i++) ener[i] = t->elo[i];
@@ -1594,8 +1659,28 @@ int orc_eval_model(const char *model, const double *energy, int n_flux, const do
         if (e[i + 1] < 0.01 || e[i] > 1000.0) flux[i] = 0;
     }
     free_syspar(sp);
-  } else {
-    rc = -2; /* standalone xillver models: not restated yet */
+  } else { /* xillver_model, src/LocalModel.cpp:104-130, + add_primary_component, src/Relbase.cpp:294-351 */
+    XPar src = {p.gam, p.afe, p.lxi, p.ect, p.dens, p.prim_type};
+    if (!g_xill[p.prim_type] && load_xill(p.prim_type)) { free(e); return 3; }
+    int nex = g_xill[p.prim_type]->n_ener;
+    double *ex = (double *) malloc(sizeof(double) * (nex + 1));
+    double *fx = (double *) malloc(sizeof(double) * nex);
+    xill_energy_grid(p.prim_type, ex);
+    rc = xillver_spectrum_incl(&src, p.xincl, fx);
+    if (!rc) {
+      double nf = 0.5 * cos(p.xincl * M_PI / 180); /* norm_xillver_spec, src/Xillspec.cpp:528-545 */
+      for (int i = 0; i < nex; i++) fx[i] *= nf;
+      orc_rebin(e, flux, n_flux, ex, fx, nex);
+      double *pl = (double *) malloc(sizeof(double) * n_flux);
+      primary_spectrum(pl, e, n_flux, &src, 1.0);
+      double nsrc = norm_factor_source(&src);
+      for (int i = 0; i < n_flux; i++) pl[i] *= nsrc;
+      for (int i = 0; i < n_flux; i++) flux[i] *= fabs(p.refl_frac);
+      if (p.refl_frac >= 0)
+        for (int i = 0; i < n_flux; i++) flux[i] += pl[i];
+      free(pl);
+    }
+    free(ex); free(fx);
   }
   free(e);
   return rc;

@@ -23,6 +23,8 @@ LMOD_SYMBOLS = {
     "relxilllp": "lmodrelxilllp",
     "relxillCp": "lmodrelxilldensnthcomp",
     "relxilllpCp": "lmodrelxilllpdensnthcomp",
+    "xillver": "lmodxillver",
+    "xillverCp": "lmodxillverdensnthcomp",
 }
 
 ABI_SYMBOLS = [

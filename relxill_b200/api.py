@@ -27,6 +27,8 @@ PARAM_NAMES = {
                   "switch_returnrad", "switch_reflfrac_boost"],
     "relxillCp": ["Incl", "a", "Rin", "Rout", "Rbr", "Index1", "Index2", "z", "gamma", "logxi", "logN", "Afe", "kTe",
                   "refl_frac"],
+    "xillver": ["gamma", "Afe", "Ecut", "logxi", "z", "Incl", "refl_frac"],
+    "xillverCp": ["gamma", "Afe", "kTe", "logxi", "logN", "z", "Incl", "refl_frac"],
     "relxilllpCp": ["Incl", "a", "Rin", "Rout", "h", "beta", "gamma", "logxi", "logN", "Afe", "kTe", "refl_frac", "z",
                     "iongrad_index", "iongrad_type", "switch_returnrad", "switch_reflfrac_boost"],
 }

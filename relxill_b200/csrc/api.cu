@@ -43,8 +43,8 @@ void set_err(const std::string &s) {
     }                                                                       \
   } while (0)
 
-enum KFam { KF_SYSPAR, KF_ZONE, KF_FINE, KF_DIST, KF_LINE, KF_XILL, KF_CONV, KF_FINISH, KF_NTH, KF_PRIMNTH, KF_COUNT };
-const char *KF_NAMES[KF_COUNT] = {"k_syspar", "k_zone", "k_fine", "k_dist", "k_line", "k_xill", "k_conv", "k_linefinish", "k_nth", "k_prim_nth"};
+enum KFam { KF_SYSPAR, KF_ZONE, KF_FINE, KF_DIST, KF_LINE, KF_XILL, KF_CONV, KF_FINISH, KF_NTH, KF_PRIMNTH, KF_XILLVER, KF_COUNT };
+const char *KF_NAMES[KF_COUNT] = {"k_syspar", "k_zone", "k_fine", "k_dist", "k_line", "k_xill", "k_conv", "k_linefinish", "k_nth", "k_prim_nth", "k_xillver"};
 
 struct Engine {
   std::mutex mu;
@@ -226,9 +226,10 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st)
   const int which = (m.prim == PRIM_NTHCOMP) ? 1 : 0;
   const bool relxill = (m.type == T_RELXILL);
   const int ne_line = (m.type == T_LINE) ? b->n_flux : NCONV;
-  const int nex_stride = relxill ? E.tables->xill_host(m.prim).stride : 1;
+  const int nex_stride = (relxill || m.type == T_XILL) ? E.tables->xill_host(m.prim).stride : 1;
   const int n_incl = relxill ? E.tables->xill_host(m.prim).n_incl : 0;
-  const bool nth = relxill && m.prim == PRIM_NTHCOMP;
+  const bool xillver = (m.type == T_XILL);
+  const bool nth = (relxill || xillver) && m.prim == PRIM_NTHCOMP;
   // the Kompaneets work arrays take 1.4 MB per vector: smaller chunks for the Cp models
   const long cap = std::min(b->n, nth ? std::min<long>(E.max_chunk, 2048) : E.max_chunk);
   if (ensure_scratch(E, cap, b->nz_max, ne_line, nex_stride, nth)) return -2;
@@ -241,6 +242,17 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st)
     const long nc = std::min(S.cap, b->n - c0);
     const VPar *vps = b->d_vps + c0;
     double *out = d_flux + (size_t) c0 * b->n_flux;
+    if (xillver) {
+      tm.begin(); launch_xillver(vps, T, S, nc, which, b->d_energy, b->n_flux, out, nex_stride, st); tm.end(KF_XILLVER);
+      if (nth) {
+        tm.begin(); launch_nth(vps, T, S, nc, st); tm.end(KF_NTH);
+        tm.begin(); launch_xillver_prim_nth(vps, T, S, nc, b->d_energy, b->n_flux, out, st); tm.end(KF_PRIMNTH);
+      }
+      CK(cudaMemcpyAsync(b->status.data() + c0, S.status, nc * sizeof(int), cudaMemcpyDeviceToHost, st));
+      b->last_chunk0 = c0;
+      b->last_chunk_n = nc;
+      continue;
+    }
     tm.begin(); launch_syspar(vps, T, S, nc, 1, st); tm.end(KF_SYSPAR);
     if (relxill) {
       tm.begin(); launch_zone(vps, T, S, nc, st); tm.end(KF_ZONE);
@@ -328,7 +340,9 @@ relxill_b200_batch *relxill_b200_prepare(const char *model, const double *energy
   }
   // tables this flavour needs; returning radiation can be switched per vector -> load if the table exists
   bool want_rr = (m->irrad == EMIS_LP) || E.cfg.env_returnrad == 1;
-  std::string err = E.tables->require(m->irrad == EMIS_LP, false, m->type == T_RELXILL ? m->prim : PRIM_NONE);
+  std::string err = (m->type == T_XILL)
+                        ? E.tables->require_xill_only(m->prim)
+                        : E.tables->require(m->irrad == EMIS_LP, false, m->type == T_RELXILL ? m->prim : PRIM_NONE);
   if (!err.empty()) { set_err(err); return nullptr; }
   if (want_rr) {
     err = E.tables->require(false, true, PRIM_NONE);
@@ -616,5 +630,7 @@ DEF_LMOD(lmodrelxill, "relxill")
 DEF_LMOD(lmodrelxilllp, "relxilllp")
 DEF_LMOD(lmodrelxilldensnthcomp, "relxillCp")
 DEF_LMOD(lmodrelxilllpdensnthcomp, "relxilllpCp")
+DEF_LMOD(lmodxillver, "xillver")
+DEF_LMOD(lmodxillverdensnthcomp, "xillverCp")
 
 }  // extern "C"

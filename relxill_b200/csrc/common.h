@@ -45,6 +45,7 @@ struct VPar {
   double doppler_obs;           // doppler_factor_source_obs (lamp post, beta > 1e-4), else 1
   double rms;                   // ISCO
   double relline_norm;          // 0.5 cos(incl) for relxill+BKN, else 1
+  double xincl;                 // inclination in degrees (standalone xillver models interpolate over it)
   double zone[NZMAX + 1];       // radial zone grid
   int model_type, emis_type, prim_type, type;
   int limb, nz, return_rad, ion_grad_type, boost;

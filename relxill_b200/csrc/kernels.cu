@@ -1076,6 +1076,105 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
   }
 }
 
+// ---------------------------------------------------------------------------------- k_xillver
+// Standalone xillver / xillverCp (LocalModel::xillver_model, src/LocalModel.cpp:104-130): interpolation over
+// all table axes including the inclination (interp_5d_tab / interp_6d_tab, src/xilltable.c:878-1044),
+// semi-infinite-slab factor (norm_xillver_spec, src/Xillspec.cpp:528-545), rebin to the caller's grid and
+// add_primary_component (src/Relbase.cpp:294-351; the nthcomp primary is added by k_xillver_prim_nth).
+__global__ void __launch_bounds__(256) k_xillver(const VPar *__restrict__ vps, DevTables T, Scratch S, int which,
+                                                 const double *__restrict__ user_e, int n_flux, double *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double *fx = reinterpret_cast<double *>(smraw);   // [stride]
+  __shared__ double s_w[64], s_pow[NCOARSE], s_nsrc, s_fac0;
+  __shared__ const float *s_row[64];
+  const int v = blockIdx.x, t = threadIdx.x;
+  const VPar &vp = vps[v];
+  double *o = out + (size_t) v * n_flux;
+  if (t == 0) S.status[v] = vp.status;
+  if (vp.status != ST_OK) {
+    for (int j = t; j < n_flux; j += 256) o[j] = 0.0;
+    return;
+  }
+  const XillDev &X = T.xill[which];
+  const int ne = X.n_ener, st = X.stride;
+  const int ncorn = (X.npar == 6) ? 64 : 32;
+  if (t == 0) {
+    float inp[8];
+    inp[0] = (float) vp.gam; inp[1] = (float) vp.afe; inp[2] = (float) vp.lxi; inp[3] = (float) vp.ect;
+    inp[4] = (float) vp.dens; inp[5] = 0.f; inp[6] = 0.f; inp[7] = (float) vp.xincl;
+    int ind[6];
+    double fac[6];
+    for (int i = 0; i < X.npar; i++) {
+      const int pind = X.pindex[i];
+      const int n = X.nvals[i];
+      int k = bsearch_asc<float>(X.vals[i], n, inp[pind]);
+      if (k < 0) k = 0; else if (k > n - 2) k = n - 2;
+      ind[i] = k;
+      float val = inp[pind];
+      const float lo = X.vals[i][0], hi = X.vals[i][n - 1];
+      if (val < lo) val = lo; else if (val > hi) val = hi;
+      fac[i] = (double) ((val - X.vals[i][k]) / (X.vals[i][k + 1] - X.vals[i][k]));
+      if (pind == 3) {
+        if (vp.ect <= (double) lo) fac[i] = 0.0;
+        if (vp.ect >= (double) hi) fac[i] = 1.0;
+      }
+    }
+    const int off = (X.npar == 6) ? 1 : 0;
+    const int bits[16] = {0x0, 0x1, 0x2, 0x4, 0x3, 0x5, 0x6, 0x7, 0x8, 0x9, 0xA, 0xC, 0xB, 0xD, 0xE, 0xF};
+    for (int half = 0; half < (X.npar == 6 ? 2 : 1); half++)
+      for (int h5 = 0; h5 < 2; h5++)
+        for (int c = 0; c < 16; c++) {
+          const int b1 = bits[c] & 1, b2 = (bits[c] >> 1) & 1, b3 = (bits[c] >> 2) & 1, b4 = (bits[c] >> 3) & 1;
+          const double w = (b1 ? fac[off] : (1.0 - fac[off])) * (b2 ? fac[off + 1] : (1.0 - fac[off + 1]))
+                           * (b3 ? fac[off + 2] : (1.0 - fac[off + 2])) * (b4 ? fac[off + 3] : (1 - fac[off + 3]))
+                           * (h5 ? fac[off + 4] : (1 - fac[off + 4]));
+          const int i1 = ind[off] + b1, i2 = ind[off + 1] + b2, i3 = ind[off + 2] + b3, i4 = ind[off + 3] + b4,
+                    i5 = ind[off + 4] + h5;
+          long row;
+          if (X.npar == 5) row = ((((long) i1 * X.nvals[1] + i2) * X.nvals[2] + i3) * X.nvals[3] + i4) * X.nvals[4] + i5;
+          else row = (((((long) (ind[0] + half) * X.nvals[1] + i1) * X.nvals[2] + i2) * X.nvals[3] + i3) * X.nvals[4] + i4) * X.nvals[5] + i5;
+          s_w[half * 32 + h5 * 16 + c] = w;
+          s_row[half * 32 + h5 * 16 + c] = X.data + (size_t) row * st;
+        }
+    s_fac0 = fac[0];
+  }
+  if (vp.prim_type == PRIM_ECUT)
+    for (int i = t; i < NCOARSE; i += 256) s_pow[i] = pow(0.5 * (T.ecoarse[i] + T.ecoarse[i + 1]), -vp.gam);
+  __syncthreads();
+  if (vp.prim_type == PRIM_ECUT && t < 32) {
+    double S1, S2;
+    ecut_band_sums(T, s_pow, vp.ect, S1, S2);
+    if (t == 0) { s_nsrc = 1. / (S1 / (1e15 / 4.0 / PI)); S.nsrc[v] = s_nsrc; }
+  }
+  const double slab = 0.5 * cos(vp.xincl * PI / 180);
+  for (int e = t; e < ne; e += 256) {
+    double f1 = s_w[0] * (double) __ldg(s_row[0] + e);
+    for (int c = 1; c < 32; c++) f1 += s_w[c] * (double) __ldg(s_row[c] + e);
+    if (ncorn == 64) {
+      double f2 = s_w[32] * (double) __ldg(s_row[32] + e);
+      for (int c = 33; c < 64; c++) f2 += s_w[c] * (double) __ldg(s_row[c] + e);
+      f1 = lin1d(s_fac0, f1, f2);
+    }
+    fx[e] = f1 * slab;
+  }
+  __syncthreads();
+  const double rfa = fabs(vp.refl_frac);
+  const bool add_prim = (vp.refl_frac >= 0) && (vp.prim_type == PRIM_ECUT);
+  const double ex0 = exp(1.0 / vp.ect);
+  for (int j = t; j < n_flux; j += 256) {
+    double elo = user_e[j], ehi = user_e[j + 1];
+    if (vp.z > 0) { elo *= (1 + vp.z); ehi *= (1 + vp.z); }
+    double f = rebin_bin(elo, ehi, X.ener, fx, ne) * rfa;
+    if (add_prim) {
+      const double en = 0.5 * (elo + ehi);
+      double pr = ex0 * pow(en, -vp.gam) * exp(-en / vp.ect) * (ehi - elo);
+      pr *= s_nsrc;
+      f += pr;
+    }
+    o[j] = f;
+  }
+}
+
 // ---------------------------------------------------------------------------------- launchers
 static size_t g_smem_sys = 0, g_smem_zone = 0;
 
@@ -1118,6 +1217,10 @@ void launch_dist(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
 }
 void launch_linefinish(const VPar *vps, const Scratch &S, long n, int n_ener, double *out, cudaStream_t st) {
   k_linefinish<<<(unsigned) n, 256, 0, st>>>(vps, S, n_ener, S.ne_line_cap, S.nz_cap, out);
+}
+void launch_xillver(const VPar *vps, const DevTables &T, const Scratch &S, long n, int which, const double *user_e,
+                    int n_flux, double *out, int stride, cudaStream_t st) {
+  k_xillver<<<(unsigned) n, 256, (size_t) stride * sizeof(double), st>>>(vps, T, S, which, user_e, n_flux, out);
 }
 void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
                  double *out, double *total, int which, int mode, cudaStream_t st) {

@@ -22,6 +22,10 @@ void launch_xill(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
 void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
                  double *out, double *total, int which, int mode, cudaStream_t st);
 
+void launch_xillver(const VPar *vps, const DevTables &T, const Scratch &S, long n, int which, const double *user_e,
+                    int n_flux, double *out, int stride, cudaStream_t st);
+void launch_xillver_prim_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
+                             double *out, cudaStream_t st);
 void launch_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, cudaStream_t st);
 void launch_prim_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, double *total, const double *user_e,
                      int n_flux, double *out, cudaStream_t st);

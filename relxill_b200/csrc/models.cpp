@@ -34,6 +34,12 @@ static const ModelDef MODELS[] = {
      {P_H, P_BETA, P_A, P_INCL, P_RIN, P_ROUT, P_Z, P_GAMMA, P_LOGXI, P_AFE, P_ECUT, P_REFLFRAC,
       P_SWITCH_RETURNRAD, P_SWITCH_REFLFRAC_BOOST},
      {6.0, 0.0, 0.998, 30., -1., 400., 0., 2., 3.1, 1., 300., 1.0, 1., 0.}},
+    {"xillver", "lmodxillver", T_XILL, 0, PRIM_ECUT, 0, 7,
+     {P_GAMMA, P_AFE, P_ECUT, P_LOGXI, P_Z, P_INCL, P_REFLFRAC},
+     {2., 1., 300., 3.1, 0., 30., -1.}},
+    {"xillverCp", "lmodxillverdensnthcomp", T_XILL, 0, PRIM_NTHCOMP, 100, 8,
+     {P_GAMMA, P_AFE, P_KTE, P_LOGXI, P_LOGN, P_Z, P_INCL, P_REFLFRAC},
+     {2., 1., 60., 3.1, 15., 0., 30., -1.}},
     {"relxillCp", "lmodrelxilldensnthcomp", T_RELXILL, EMIS_BKN, PRIM_NTHCOMP, -1, 14,
      {P_INCL, P_A, P_RIN, P_ROUT, P_RBR, P_INDEX1, P_INDEX2, P_Z, P_GAMMA, P_LOGXI, P_LOGN, P_AFE, P_KTE,
       P_REFLFRAC},
@@ -130,6 +136,15 @@ void interpret_params(const ModelDef &m, const double *par, const HostConfig &cf
   vp.gam = v[P_GAMMA];
   vp.refl_frac = v[P_REFLFRAC];
   vp.boost = (int) std::lround(has[P_SWITCH_REFLFRAC_BOOST] ? v[P_SWITCH_REFLFRAC_BOOST] : 0.0);
+
+  vp.xincl = v[P_INCL];
+  vp.z = v[P_Z];
+  vp.eshift_obs = 1.0;
+  vp.doppler_obs = 1.0;
+  if (m.type == T_XILL) {  // no relativistic parameters (get_rel_params returns nullptr, src/ModelDefinition.cpp:281-283)
+    vp.nz = 0;
+    return;
+  }
 
   // relativistic parameters
   vp.a = v[P_A];

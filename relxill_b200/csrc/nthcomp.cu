@@ -267,6 +267,31 @@ __global__ void __launch_bounds__(256) k_prim_nth(const VPar *__restrict__ vps, 
   }
 }
 
+// nthcomp primary of the standalone xillverCp model on the caller's (redshifted) grid, added to k_xillver's
+// reflection spectrum (add_primary_component, src/Relbase.cpp:294-351 with energy shift 1)
+__global__ void __launch_bounds__(256) k_xillver_prim_nth(const VPar *__restrict__ vps, DevTables T, Scratch S,
+                                                          const double *__restrict__ user_e, int n_flux, double *out) {
+  const int v = blockIdx.x, t = threadIdx.x;
+  if (S.status[v] != ST_OK) return;
+  const VPar &vp = vps[v];
+  if (!(vp.refl_frac >= 0)) return;
+  const double *sp = S.nth_spt + (size_t) v * NTH_MAX * NTH_SOL;
+  const int nth = S.nth_jmax[(size_t) v * NTH_SOL];
+  const double normfac = nth_normfac(T, sp, nth, 1.0);
+  const double nsrc = S.nsrc[v];
+  double *o = out + (size_t) v * n_flux;
+  for (int j = t; j < n_flux; j += 256) {
+    double elo = user_e[j], ehi = user_e[j + 1];
+    if (vp.z > 0) { elo *= (1 + vp.z); ehi *= (1 + vp.z); }
+    o[j] += nth_bin(T, sp, nth, elo, ehi, 1.0, normfac) * nsrc;
+  }
+}
+
+void launch_xillver_prim_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
+                             double *out, cudaStream_t st) {
+  k_xillver_prim_nth<<<(unsigned) n, 256, 0, st>>>(vps, T, S, user_e, n_flux, out);
+}
+
 void launch_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, cudaStream_t st) {
   k_nth<<<(unsigned) n, 128, 0, st>>>(vps, T, S);
 }

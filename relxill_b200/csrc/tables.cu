@@ -546,7 +546,15 @@ void Tables::load_nthcomp() {
 std::string Tables::load(const std::string &dir) {
   dir_ = dir;
   load_fixed();
-  return load_rel();
+  return "";   // the tables themselves are loaded on first use by the model flavour that needs them
+}
+
+std::string Tables::require_xill_only(int prim_type) {
+  load_fixed();
+  std::string err = load_xill(prim_type == PRIM_NTHCOMP ? 1 : 0);
+  if (!err.empty()) return err;
+  if (prim_type == PRIM_NTHCOMP) load_nthcomp();
+  return "";
 }
 
 std::string Tables::require(bool lp, bool rrad, int prim_type) {

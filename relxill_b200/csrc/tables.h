@@ -23,6 +23,7 @@ class Tables {
   std::string load(const std::string &dir);
   // lazily make sure the table needed by a model flavour is there
   std::string require(bool lp, bool rrad, int prim_type);
+  std::string require_xill_only(int prim_type);  // standalone xillver models need no relativistic table
   const DevTables &dev() const { return dt_; }
   const std::vector<double> &rr_spins() const { return rr_spin_; }
   const XillHost &xill_host(int prim_type) const { return xh_[prim_type == PRIM_NTHCOMP ? 1 : 0]; }

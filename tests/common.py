@@ -1,7 +1,8 @@
 """Shared by the tests and tests/golden/make_golden.py: seeded parameter samplers and the parity metric."""
 import numpy as np
 
-MODELS = ["relline", "relline_lp", "relconv", "relconv_lp", "relxill", "relxilllp", "relxillCp", "relxilllpCp"]
+MODELS = ["relline", "relline_lp", "relconv", "relconv_lp", "relxill", "relxilllp", "relxillCp", "relxilllpCp",
+          "xillver", "xillverCp"]
 # north_star tolerance: relative error <= 1e-5 per bin on bins above 1e-6 of the spectrum peak
 RTOL = 1e-5
 PEAK_FLOOR = 1e-6
@@ -56,6 +57,10 @@ def sample_params(model, n, seed):
         elif model == "relxilllpCp":
             r = [incl, a, rin, rout, h, beta, U(1.2, 3.4), U(0, 4.7), U(15, 20), U(.5, 10), U(1, 400), U(-2, 10), z,
                  U(0, 3), rng.integers(0, 3), rng.integers(0, 2), rng.integers(0, 2)]
+        elif model == "xillver":
+            r = [U(1, 3.4), U(.5, 10), U(5, 1000), U(0, 4.7), z, U(3, 89), U(-2, 5)]
+        elif model == "xillverCp":
+            r = [U(1.2, 3.4), U(.5, 10), U(1, 400), U(0, 4.7), U(15, 20), z, U(3, 89), U(-2, 5)]
         else:
             raise KeyError(model)
         rows.append([float(x) for x in r])

@@ -12,7 +12,8 @@ from common import PEAK_FLOOR, RTOL, default_grid, relerr, sample_params, walker
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz")
-GPU_MODELS = ["relline", "relline_lp", "relconv", "relconv_lp", "relxill", "relxilllp", "relxillCp", "relxilllpCp"]
+GPU_MODELS = ["relline", "relline_lp", "relconv", "relconv_lp", "relxill", "relxilllp", "relxillCp", "relxilllpCp",
+              "xillver", "xillverCp"]
 
 
 def _conv_input(e):
