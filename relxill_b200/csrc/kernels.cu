@@ -39,26 +39,28 @@ struct SysSmem {
   double rad[RR_NR], rlo[RR_NR], rhi[RR_NR], emis_in[RR_NR], emis_ret[RR_NR], cflux[RR_NR], cgsh[RR_NR];
   double prod[RR_NR * RR_NR];
   double scal[8];
-  int irad[RR_NR];
+  int irad[RR_NR], irad2[RR_NR];
   int ints[8];
 };
 
-__device__ double gshift_fluxboost(double xill_gshift_fac, double g, double lng, double gamma) {  // Relreturn_Corona.cpp:39-83
+// corrected_gshift_fluxboost_factor / g (src/Relreturn_Corona.cpp:39-83), with 1/g computed once
+__device__ __forceinline__ double gshift_fluxboost_over_g(double xill_gshift_fac, double g, double lng, double gamma) {
   const double g0 = 2. / 3;
+  const double ig = 1. / g;
   double corr;
   if (xill_gshift_fac < 1) {
     const double a = (xill_gshift_fac / g0 - 1) / (g0 - 1);
     const double b = 1 - a;
-    corr = (g >= 1) ? 1. / g * (1. / g * a + b) : g * (g * a + b);
+    corr = (g >= 1) ? ig * (ig * a + b) : g * (g * a + b);
   } else {
     const double alin = (xill_gshift_fac - 1) / (g0 - 1);
     const double blin = 1 - alin;
-    corr = (g >= 1) ? (1. / g * alin + blin) : (g * alin + blin);
+    corr = (g >= 1) ? (ig * alin + blin) : (g * alin + blin);
   }
   double fb = exp(gamma * lng) * corr;   // pow(g, gamma) with ln g tabulated at load
   if (g < 1 && fb > 1) fb = 1;
   if (fb < 0) fb = 0;
-  return fb;
+  return fb * ig;
 }
 
 __global__ void __launch_bounds__(256) k_syspar(const VPar *__restrict__ vps, DevTables T, Scratch S, int pass) {
@@ -277,20 +279,8 @@ __global__ void __launch_bounds__(256) k_syspar(const VPar *__restrict__ vps, De
         const double area_model = 0.5 * (sm.rlo[idx] + sm.rhi[idx]) * (sm.rhi[idx] - sm.rlo[idx]);
         sm.scal[s] = area_model / area_table;
       }
-      // emissivity at the ring centres: inv_rebin_mean (src/relutility.c:636-663), cursor semantics kept
       if (sm.rad[0] > sm.rad[nrad - 1] || sm.re[nrad - 1] > sm.re[0]) err = ST_RRAD;
       if (sm.rad[0] < sm.re[NR - 1] || sm.rad[nrad - 1] > sm.re[0]) err = ST_RRAD;
-      if (!err) {
-        int in = nrad - 1;
-        for (int ii = 0; ii < NR - 1; ii++) {
-          if (sm.re[ii] > sm.rad[in] && sm.re[ii + 1] <= sm.rad[in]) {
-            const double f = (sm.rad[in] - sm.re[ii + 1]) / (sm.re[ii] - sm.re[ii + 1]);
-            sm.emis_in[in] = lin1d(f, sm.emis[ii + 1], sm.emis[ii]);
-            in--;
-            if (in < 0) break;
-          }
-        }
-      }
       if (have_corr) {  // correction factors by zone membership of the ring centre, Relreturn_Corona.cpp:233-247
         const double *cf = S.corr_flux + (size_t) v * NZMAX, *cg = S.corr_gshift + (size_t) v * NZMAX;
         for (int i = 0; i < nrad; i++) {
@@ -307,6 +297,28 @@ __global__ void __launch_bounds__(256) k_syspar(const VPar *__restrict__ vps, De
     }
     __syncthreads();
     const int nrad = sm.ints[2];
+    // emissivity at the ring centres: inv_rebin_mean (src/relutility.c:636-663).  Its cursor walk finds, for
+    // the ring centres in descending order, brackets in strictly ascending fine-grid index; a centre whose
+    // bracket does not advance (two centres in one fine bin) and all later ones stay unset (0).
+    if (t < nrad) {
+      const int c = count_gt_desc(sm.re, NR, sm.rad[t]);
+      sm.irad2[t] = (c >= 1 && c <= NR - 1) ? c - 1 : -1;
+    }
+    __syncthreads();
+    if (t < nrad && sm.ints[1] == 0) {
+      bool ok = true;
+      int prev = -1;
+      for (int in = nrad - 1; in >= t && ok; in--) {
+        if (sm.irad2[in] < 0 || sm.irad2[in] <= prev) ok = false;
+        prev = sm.irad2[in];
+      }
+      if (ok) {
+        const int ii = sm.irad2[t];
+        const double f = (sm.rad[t] - sm.re[ii + 1]) / (sm.re[ii] - sm.re[ii + 1]);
+        sm.emis_in[t] = lin1d(f, sm.emis[ii + 1], sm.emis[ii]);
+      }
+    }
+    __syncthreads();
     const double *tf_t = T.rr_tf + is * n2, *gmin_t = T.rr_gmin + is * n2, *gmax_t = T.rr_gmax + is * n2;
     const double *fg_t = T.rr_fg + is * n2 * RR_NG, *lng_t = T.rr_lng + is * n2 * RR_NG;
     for (int pr = t; pr < nrad * nrad; pr += 256) {
@@ -318,7 +330,7 @@ __global__ void __launch_bounds__(256) k_syspar(const VPar *__restrict__ vps, De
       for (int jj = 0; jj < RR_NG; jj++) {
         const double g = ((jj + 0.5) / RR_NG) * (gmx - gmn) + gmn;
         double e1 = fg_t[q * RR_NG + jj];
-        if (fabs(cg - 1) > 1e-3) e1 *= gshift_fluxboost(cg, g, lng_t[q * RR_NG + jj], vp.gamma) / g;
+        if (fabs(cg - 1) > 1e-3) e1 *= gshift_fluxboost_over_g(cg, g, lng_t[q * RR_NG + jj], vp.gamma);
         else if (fabs(g - 1) > 1e-3) e1 *= exp((vp.gamma - 1) * lng_t[q * RR_NG + jj]);
         ez += e1;
       }
@@ -736,13 +748,12 @@ __global__ void __launch_bounds__(256) k_dist(const VPar *__restrict__ vps, DevT
     if (t == 0) S.status[v] = flags[0];
     return;
   }
-  const int *izone = S.izone + (size_t) v * NR;
+  const int *zfirst = S.zfirst + (size_t) v * (NZMAX + 1);
   const int nz = vp.nz;
   for (int job = t; job < nz * n_incl; job += 256) {
     const int z = job / n_incl, m = job - z * n_incl;
     double s = 0.0;
-    for (int i = 0; i < NR; i++)
-      if (izone[i] == z) s += part[(size_t) i * n_incl + m];
+    for (int i = zfirst[z + 1]; i < zfirst[z]; i++) s += part[(size_t) i * n_incl + m];   // the zone's radii, ascending index
     S.dist[((size_t) v * NZMAX + z) * MAX_INCL + m] = s;
   }
   __syncthreads();
