@@ -1522,8 +1522,10 @@ static int relxill_pipeline(Par *p, Stages *st) {
     double lxi_max = log10(4.0 * M_PI * e_at / density_ss73_zone_a(rad_lxi, rin) * (cos(M_PI / 4) / cos(di_at)));
     double fac_lxi_norm = src.lxi - lxi_max;
     double density_min = density_ss73_zone_a((25. / 9.) * rin, rin);
+    const char *cd_env = getenv("RELXILL_CONSTANT_DENSITY"); /* constantDiskDensity(), src/relutility.c:372-382 */
+    int const_dens = (cd_env != NULL && (int) strtod(cd_env, NULL) == 1);
     for (int i = 0; i < nz; i++) {
-      double dn = density_ss73_zone_a(rmean[i], rin) / density_min;
+      double dn = const_dens ? 1.0 : density_ss73_zone_a(rmean[i], rin) / density_min; /* :155-158 */
       st->dens[i] = log10(dn) + src.dens;
       st->lxi[i] = log10(4.0 * M_PI * irr[i] / dn * (cos(M_PI / 4) / cos(dinc[i])));
       st->lxi[i] += fac_lxi_norm;

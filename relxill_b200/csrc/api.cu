@@ -157,6 +157,7 @@ int engine_init(Engine &E, const char *dir, int device) {
   if (const char *env = getenv("RELXILL_NUM_RZONES")) E.cfg.env_num_zones = (int) atof(env);
   if (const char *env = getenv("RELXILL_RETURNRAD_SWITCH")) E.cfg.env_returnrad = (int) atof(env);
   if (const char *env = getenv("RELLINE_PHYSICAL_NORM")) E.cfg.env_phys_norm = ((int) strtod(env, nullptr) == 1) ? 1 : 0;
+  if (const char *env = getenv("RELXILL_CONSTANT_DENSITY")) E.cfg.env_const_density = ((int) strtod(env, nullptr) == 1) ? 1 : 0;
   if (const char *env = getenv("RELXILL_B200_CHUNK")) E.max_chunk = std::max(1L, atol(env));
   if (kernels_init() != 0) {
     set_err("kernel attribute setup failed (is this an sm_100a device?)");
@@ -339,6 +340,10 @@ relxill_b200_batch *relxill_b200_prepare(const char *model, const double *energy
     return nullptr;
   }
   // tables this flavour needs; returning radiation can be switched per vector -> load if the table exists
+  {  // read per call, like the reference's constantDiskDensity() (src/relutility.c:372-382)
+    const char *env = getenv("RELXILL_CONSTANT_DENSITY");
+    E.cfg.env_const_density = (env && (int) strtod(env, nullptr) == 1) ? 1 : 0;
+  }
   bool want_rr = (m->irrad == EMIS_LP) || E.cfg.env_returnrad == 1;
   std::string err = (m->type == T_XILL)
                         ? E.tables->require_xill_only(m->prim)

@@ -53,7 +53,7 @@ struct VPar {
   int do_corr;                  // returning-radiation correction factors are computed
   int rr_spin;                  // index into the returning-radiation table (spin >= a), -1 = none
   int status;
-  int pad_;
+  int const_density;            // RELXILL_CONSTANT_DENSITY=1: alpha-disk ionisation gradient with constant density
 };
 
 struct XillDev {

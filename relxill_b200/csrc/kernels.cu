@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(128) k_zone(const VPar *__restrict__ vps, DevT
       const double lxi_max = log10(4.0 * PI * e_at / density_ss73_zone_a(rad_lxi, rin) * (cos(PI / 4) / cos(di_at)));
       const double fac_lxi_norm = vp.lxi - lxi_max;
       const double density_min = density_ss73_zone_a((25. / 9.) * rin, rin);
-      const double dn = density_ss73_zone_a(sm.rmean[t], rin) / density_min;
+      const double dn = vp.const_density ? 1.0 : density_ss73_zone_a(sm.rmean[t], rin) / density_min;   // src/IonGradient.cpp:155-158
       dens = log10(dn) + vp.dens;
       lxi = log10(4.0 * PI * sm.irr[t] / dn * (cos(PI / 4) / cos(sm.dinc[t])));
       lxi += fac_lxi_norm;

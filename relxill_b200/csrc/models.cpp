@@ -126,6 +126,7 @@ void interpret_params(const ModelDef &m, const double *par, const HostConfig &cf
   vp.prim_type = m.prim;
   vp.status = ST_OK;
   vp.rr_spin = -1;
+  vp.const_density = cfg.env_const_density;
 
   // xillver-side parameters
   vp.afe = v[P_AFE];

@@ -25,6 +25,7 @@ struct HostConfig {
   int env_num_zones = 0;     // RELXILL_NUM_RZONES (0 = unset)
   int env_returnrad = -1;    // RELXILL_RETURNRAD_SWITCH (-1 = unset)
   int env_phys_norm = 0;     // RELLINE_PHYSICAL_NORM
+  int env_const_density = 0; // RELXILL_CONSTANT_DENSITY (src/relutility.c:372-382)
 };
 
 const ModelDef *find_model(const char *name);

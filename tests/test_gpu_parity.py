@@ -95,6 +95,23 @@ def test_ion_gradient_50_zones(rx, oracle):
         oracle.set_num_zones(None)
 
 
+def test_constant_density_env(rx, oracle, monkeypatch):
+    """RELXILL_CONSTANT_DENSITY=1 (src/relutility.c:372-382, src/IonGradient.cpp:155-158): alpha-disk ionisation
+    gradient at constant density; read per call like the reference."""
+    e = default_grid(1500)
+    P = walker_ball("relxilllpCp", 4)
+    P[:, 14] = 2
+    base = rx.batch_eval("relxilllpCp", e, P)
+    monkeypatch.setenv("RELXILL_CONSTANT_DENSITY", "1")
+    got = rx.batch_eval("relxilllpCp", e, P)
+    assert max(relerr(a, b) for a, b in zip(got, base)) > 1e-4   # the switch changes the spectrum
+    for a, p in zip(got, P):
+        assert relerr(a, oracle.eval("relxilllpCp", e, p)) < RTOL
+    monkeypatch.delenv("RELXILL_CONSTANT_DENSITY")
+    again = rx.batch_eval("relxilllpCp", e, P)
+    assert np.array_equal(again, base)
+
+
 def test_stage_parity(rx, oracle):
     """Intermediates of the pipeline against the oracle's (tight tolerances: same arithmetic)."""
     import torch

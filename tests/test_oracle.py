@@ -131,3 +131,21 @@ def test_nthcomp_vs_reference(oracle, ref):
     e = default_grid(500)
     for gam, kte, z in [(2.0, 60.0, 0.0), (1.4, 5.0, 0.3), (3.2, 350.0, 1.5)]:
         np.testing.assert_allclose(oracle.nthcomp(e, gam, kte, z), ref.nthcomp(e, gam, kte, z), rtol=1e-12)
+
+
+def test_constant_density_env_vs_reference(oracle, ref, monkeypatch):
+    """RELXILL_CONSTANT_DENSITY=1 (src/relutility.c:372-382): alpha-disk gradient at constant density."""
+    e = default_grid(800)
+    p = sample_params("relxilllpCp", 1, seed=3)[0]
+    p[14] = 2
+    ref.set_num_zones(None)
+    oracle.set_num_zones(None)
+    base = oracle.eval("relxilllpCp", e, p)
+    ref.close()
+    monkeypatch.setenv("RELXILL_CONSTANT_DENSITY", "1")
+    try:
+        a, b = oracle.eval("relxilllpCp", e, p), ref.eval("relxilllpCp", e, p)
+    finally:
+        ref.close()                     # workers spawned with the switch set must not outlive this test
+    assert relerr(a, b) < 1e-8
+    assert relerr(a, base) > 1e-4
