@@ -319,8 +319,8 @@ def run_ours(args):
     nex = 2999
     alg = {  # algorithmic bytes per launch of each kernel family
         "k_xill": ab["xillver"] + n * nz * nex * 8.0,                       # distinct table rows + zone spectra out
-        "k_line": n * (1000 * 40 * 2 * 8.0 + 1000 * 5 * 8.0 + nz * 4096 * 8.0),  # fine trff + radius scalars + profiles out (upper bound)
-        "k_conv": n * (nz * 4096 * 8.0 + nz * nex * 8.0 + nb * 8.0),        # profiles + zone spectra in, spectrum out
+        "k_line": n * (1000 * 40 * 2 * 8.0 + 1000 * 5 * 8.0) + ab["line_profiles"],  # fine trff + radius scalars in, profiles out
+        "k_conv": ab["line_profiles"] + n * (nz * nex * 8.0 + nb * 8.0),     # profiles + zone spectra in, spectrum out
         "k_fine": n * (2 * 4 * 40 * 16.0 * 100 + 1000 * 40 * 4 * 8.0),      # 4 corners x 100 radii x 40 g* float4 + fine tables out
         "k_dist": n * (1000 * 40 * 4 * 8.0),
         "k_syspar": 2 * n * (4 * 3 * 100 * 4.0 + 2 * 2 * 3 * 100 * 4.0 + (3 * 2500 + 2 * 50000) * 8.0 + 7 * 1000 * 8.0),
@@ -330,8 +330,20 @@ def run_ours(args):
     }
     k_ms, k_cnt = ktimes[dominant]
     achieved = alg.get(dominant, 0.0) / (k_ms / max(k_cnt, 1) * 1e-3) / 1e9
+    traffic, compute = None, None   # dram bytes / pipe utilisation of this kernel from the committed ncu --set full capture
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        same = (prof["config"]["model"] == args.model and prof["config"]["batch"] == args.batch
+                and prof["config"]["zones"] == args.zones and prof["config"]["n_flux"] == nb)
+        if same and dominant in prof["kernels"]:
+            kk = prof["kernels"][dominant]
+            traffic = kk["dram_bytes_read"] + kk["dram_bytes_write"]
+            compute = {"fp64_pipe_pct": kk.get("fp64_pipe_pct"), "issue_active_pct": kk.get("issue_active_pct"),
+                       "source": prof.get("source")}
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "compute": compute, "peak_source": peak_src,
                 "share_of_step": ktimes[dominant][0] / tot_k,
                 "algorithmic_bytes_per_launch": alg.get(dominant, 0.0)}
     xk = ktimes.get("k_xill", (0.0, 1))

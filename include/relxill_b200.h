@@ -90,8 +90,9 @@ void relxill_b200_free_batch(relxill_b200_batch *b);
 /* Exact algorithmic byte count of the last run of `b`: distinct xillver corner
  * rows per vector (U, host-counted from the zone indices the kernels produced) and the other
  * table/IO terms.  out[0]=bytes total, out[1]=sum of U over vectors, out[2]=xillver bytes,
- * out[3]=upper bound without cross-zone sharing. */
-int relxill_b200_algorithmic_bytes(relxill_b200_batch *b, double *out4);
+ * out[3]=upper bound without cross-zone sharing, out[4]=bytes of the per-zone line profiles actually
+ * produced (first to last non-zero bin of every zone), out[5..7] reserved (0). */
+int relxill_b200_algorithmic_bytes(relxill_b200_batch *b, double *out8);
 /* Number of kernel launches issued by the last relxill_b200_run of `b`. */
 long relxill_b200_last_launches(relxill_b200_batch *b);
 /* Time (ms, CUDA events on the run's stream) spent in each kernel family during the last run when

@@ -128,9 +128,10 @@ class Batch:
         return int(_lib.lib().relxill_b200_last_launches(self._h))
 
     def algorithmic_bytes(self) -> dict:
-        out = np.zeros(4)
+        out = np.zeros(8)
         _lib.lib().relxill_b200_algorithmic_bytes(self._h, out)
-        return dict(total=out[0], distinct_rows=out[1], xillver=out[2], xillver_upper_bound=out[3])
+        return dict(total=out[0], distinct_rows=out[1], xillver=out[2], xillver_upper_bound=out[3],
+                    line_profiles=out[4])
 
     def kernel_times(self) -> dict:
         names = (C.c_char_p * 16)()

@@ -504,7 +504,8 @@ int relxill_batch_eval(const char *model, const double *energy, int n_flux, cons
   return rc;
 }
 
-int relxill_b200_algorithmic_bytes(relxill_b200_batch *b, double *out4) {
+int relxill_b200_algorithmic_bytes(relxill_b200_batch *b, double *out8) {
+  double *out4 = out8;
   Engine &E = g_eng;
   if (!b || !E.inited) return -1;
   cudaDeviceSynchronize();
@@ -542,6 +543,24 @@ int relxill_b200_algorithmic_bytes(relxill_b200_batch *b, double *out4) {
   out4[1] = sumU;
   out4[2] = xbytes;
   out4[3] = bound;
+  // bytes of the per-zone line profiles that exist (only the bins between a zone's first and last non-zero bin
+  // are written by k_line and read by k_conv)
+  double prof = 0;
+  if (nc > 0 && (m.type == T_RELXILL || m.type == T_LINE || m.type == T_CONV)) {
+    std::vector<int> zr((size_t) nc * NZMAX * 2);
+    cudaMemcpy(zr.data(), E.S.zrange, zr.size() * sizeof(int), cudaMemcpyDeviceToHost);
+    for (long i = 0; i < nc; i++) {
+      const VPar &vp = b->vps[b->last_chunk0 + i];
+      if (b->status[b->last_chunk0 + i] != ST_OK) continue;
+      for (int z = 0; z < vp.nz; z++) {
+        const int lo = zr[((size_t) i * NZMAX + z) * 2], hi = zr[((size_t) i * NZMAX + z) * 2 + 1];
+        if (hi >= lo) prof += (hi - lo + 1) * 8.0;
+      }
+    }
+    prof *= (double) b->n / (double) nc;
+  }
+  out8[4] = prof;
+  out8[5] = out8[6] = out8[7] = 0.0;
   return 0;
 }
 
