@@ -69,8 +69,8 @@ struct XillDev {
   // per-node scalars for the returning-radiation correction factors (linear functionals of the spectra)
   const double *node_ef, *node_p1, *node_p2;
   // fixed rebin map xillver grid -> convolution grid (same imin/imax/weights as _rebin_spectrum)
-  const int *rb_imin, *rb_imax;   // [NCONV], imin = -1: output bin outside the source grid
-  const double *rb_dmin, *rb_dmax;
+  const int *rb_ii;      // [NCONV][2] (imin, imax) of the rebin onto the convolution grid; imin = -1: outside the source grid
+  const double *rb_dd;   // [NCONV][2] (dmin, dmax) partial-overlap fractions of the first and last source bin
 };
 
 struct DevTables {
@@ -87,13 +87,13 @@ struct DevTables {
   // fixed grids
   const double *econv;      // [NCONV+1]
   const double *conv_cf;    // [NCONV] E_mid / dE
-  const unsigned char *conv_band;  // [NCONV] 1 if 0.01 <= E_lo and E_hi < 1000
+  int conv_b0, conv_b1;     // the normalisation band as a bin interval: 0.01 <= E_lo and E_hi < 1000 for b0 <= i <= b1
   int conv_i1kev;
   const double *ecoarse;    // [NCOARSE+1]
   const unsigned char *coarse_m1, *coarse_m2;  // masks of the two band conditions on the coarse grid
   const double *gstar, *d_gstar;  // [NG]
   const double *tw;               // FFT twiddles exp(-2 pi i m / NCONV), m < NCONV, interleaved (re, im)
-  const double *conv_wr, *conv_wi; // DFT of band/cf, k <= NCONV/2 (frequency-domain band sum of a convolution)
+  const double *conv_w;     // [NCONV/2+1][2] (re, im) DFT of band/cf (frequency-domain band sum of a convolution)
   // nthcomp: arrays that depend only on the photon grid (kT_bb is fixed at 0.05 keV)
   const double *nth_x, *nth_c2, *nth_rel, *nth_x3, *nth_w, *nth_dphdot;
   int nth_jnr, nth_jrel, nth_jmaxth;

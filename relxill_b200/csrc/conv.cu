@@ -1,0 +1,315 @@
+// conv.cu — k_conv: per-zone FFT convolution, primary spectrum and rebin to the caller's grid.
+// Compiled with FMA contraction on (build.py): butterflies and weighted sums only; the few discrete
+// decisions (zone skipped when its profile sums to < 1e-12, bin searches) compare sums / table values that
+// involve no multiply-add.
+//
+// relxill_convolution_multizone (src/Relxill.cpp:432-482) with fftw_conv_spectrum + calcFFTNormFactor
+// (src/Relbase.cpp:119-213), PrimarySource::add_primary_spectrum (src/PrimarySource.cpp:66-125) and
+// rebin_and_normalize_relxill_for_xspec (src/Relxill.cpp:261-278).  One CTA per vector.
+//
+// FFT work per zone is cut from three transforms (reference) to one:
+//   * the two real inputs (xillver spectrum, rotated line profile) share one complex forward transform;
+//   * the band sum of the convolved zone that the normalisation needs is a linear functional of the
+//     product spectrum, sum_i w_i out_i = sum_k P[k] conj(W[k]) with W = DFT(band/cf) tabulated at
+//     load, so it is taken in the frequency domain and no per-zone inverse transform is needed;
+//   * the normalised product spectra of all zones are accumulated in the frequency domain and one inverse
+//     transform per vector brings the sum back (inverse = forward transform of the conjugate).
+// The transform is a 4096-point radix-8 Stockham autosort FFT in shared memory: 4 passes, one butterfly per
+// thread per pass.  The work array is complex-interleaved (one 128-bit shared access per point) and padded by
+// one point every 8, which makes every pass's gather and scatter bank-conflict free per quarter-warp.
+#include <cuda_runtime.h>
+
+#include "common.h"
+#include "devutil.cuh"
+#include "kernels.h"
+
+namespace rx {
+
+constexpr int CONV_NT = 512;
+constexpr int CV_PADN = NCONV + NCONV / 8;
+__device__ __forceinline__ int cv_pad(int i) { return i + (i >> 3); }
+
+struct ConvSmem {
+  double2 z[CV_PADN];
+  double ar[NCONV / 2 + 1], ai[NCONV / 2 + 1];   // accumulated spectrum; reused as the final 4096-bin result
+  double red[4 * (CONV_NT / 32)];
+  double bc[4];
+};
+
+// sums NV values over the block (fixed order: shuffle tree inside warps, then over the warps)
+template <int NV>
+__device__ __forceinline__ void block_sum_n(double (&v)[NV], ConvSmem &sm) {
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; q++)
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; q++) sm.red[q * (CONV_NT / 32) + w] = v[q];
+  }
+  __syncthreads();
+  if (t < NV) {
+    double s = 0.0;
+    for (int i = 0; i < CONV_NT / 32; i++) s += sm.red[t * (CONV_NT / 32) + i];
+    sm.bc[t] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NV; q++) v[q] = sm.bc[q];
+}
+
+__device__ __forceinline__ void cmul(double &xr, double &xi, double wr, double wi) {
+  const double a = xr * wr - xi * wi;
+  xi = xr * wi + xi * wr;
+  xr = a;
+}
+__device__ __forceinline__ double2 cprod(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// 8-point DFT (forward sign), decimation in frequency, outputs in natural order
+__device__ __forceinline__ void fft8(double (&r)[8], double (&i)[8]) {
+  const double h = 0.70710678118654752440;
+  double ar[8], ai[8];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    ar[q] = r[q] + r[q + 4]; ai[q] = i[q] + i[q + 4];
+    ar[q + 4] = r[q] - r[q + 4]; ai[q + 4] = i[q] - i[q + 4];
+  }
+  {  // twiddles w8^1, w8^2 = -i, w8^3 on the odd half
+    double x = ar[5], y = ai[5];
+    ar[5] = (x + y) * h; ai[5] = (y - x) * h;
+    x = ar[6]; y = ai[6];
+    ar[6] = y; ai[6] = -x;
+    x = ar[7]; y = ai[7];
+    ar[7] = (y - x) * h; ai[7] = (-x - y) * h;
+  }
+  double br[8], bi[8];
+#pragma unroll
+  for (int g = 0; g < 8; g += 4) {
+    br[g] = ar[g] + ar[g + 2]; bi[g] = ai[g] + ai[g + 2];
+    br[g + 2] = ar[g] - ar[g + 2]; bi[g + 2] = ai[g] - ai[g + 2];
+    br[g + 1] = ar[g + 1] + ar[g + 3]; bi[g + 1] = ai[g + 1] + ai[g + 3];
+    const double dx = ar[g + 1] - ar[g + 3], dy = ai[g + 1] - ai[g + 3];
+    br[g + 3] = dy; bi[g + 3] = -dx;   // times -i
+  }
+  r[0] = br[0] + br[1]; i[0] = bi[0] + bi[1];
+  r[4] = br[0] - br[1]; i[4] = bi[0] - bi[1];
+  r[2] = br[2] + br[3]; i[2] = bi[2] + bi[3];
+  r[6] = br[2] - br[3]; i[6] = bi[2] - bi[3];
+  r[1] = br[4] + br[5]; i[1] = bi[4] + bi[5];
+  r[5] = br[4] - br[5]; i[5] = bi[4] - bi[5];
+  r[3] = br[6] + br[7]; i[3] = bi[6] + bi[7];
+  r[7] = br[6] - br[7]; i[7] = bi[6] - bi[7];
+}
+
+// in-place forward FFT of the padded array; tw[m] = exp(-2 pi i m / 4096); all CONV_NT threads call.
+// `yscale` multiplies the imaginary input (applied while the first pass loads it).
+__device__ void fft4096(double2 *z, const double2 *__restrict__ tw, double yscale) {
+  const int j = threadIdx.x;
+#pragma unroll 1
+  for (int pass = 0; pass < 4; pass++) {
+    const int ns = 1 << (3 * pass);          // 1, 8, 64, 512
+    const int k = j & (ns - 1);
+    double r[8], im[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const double2 c = z[cv_pad(j + q * (NCONV / 8))];
+      r[q] = c.x;
+      im[q] = c.y;
+    }
+    if (pass == 0) {
+#pragma unroll
+      for (int q = 0; q < 8; q++) im[q] *= yscale;
+    } else {
+      // twiddles w^q, w = tw[k * 512 / ns]: three table reads (w, w^2, w^4), the rest by products
+      const int mb = k * ((NCONV / 8) >> (3 * pass));
+      const double2 w1 = __ldg(tw + mb), w2 = __ldg(tw + 2 * mb), w4 = __ldg(tw + 4 * mb);
+      const double2 w3 = cprod(w1, w2), w5 = cprod(w4, w1), w6 = cprod(w4, w2);
+      const double2 w7 = cprod(w4, w3);
+      cmul(r[1], im[1], w1.x, w1.y);
+      cmul(r[2], im[2], w2.x, w2.y);
+      cmul(r[3], im[3], w3.x, w3.y);
+      cmul(r[4], im[4], w4.x, w4.y);
+      cmul(r[5], im[5], w5.x, w5.y);
+      cmul(r[6], im[6], w6.x, w6.y);
+      cmul(r[7], im[7], w7.x, w7.y);
+    }
+    fft8(r, im);
+    __syncthreads();
+    const int j0 = ((j - k) << 3) + k;       // (j / ns) * ns * 8 + k
+#pragma unroll
+    for (int q = 0; q < 8; q++) z[cv_pad(j0 + q * ns)] = make_double2(r[q], im[q]);
+    __syncthreads();
+  }
+}
+
+struct ConvArgs {
+  const double *user_e;   // [n_flux+1] device
+  int n_flux;
+  double *out;            // [C][n_flux] device
+  double *total;          // [C][NCONV] device (probe; may be null)
+  int which;              // xillver table index
+  int nz_stride, ne_stride;
+  int mode;               // 0 relxill, 1 convolution model (input spectrum in `out`)
+};
+
+__global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vps, DevTables T, Scratch S, ConvArgs A) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  ConvSmem &sm = *reinterpret_cast<ConvSmem *>(smraw);
+  const int v = blockIdx.x, t = threadIdx.x;
+  double *o = A.out + (size_t) v * A.n_flux;
+  const VPar &vp = vps[v];
+  if (S.status[v] != ST_OK) {
+    for (int j = t; j < A.n_flux; j += CONV_NT) o[j] = 0.0;
+    return;
+  }
+  const int nz = (A.mode == 0) ? vp.nz : 1;
+  const XillDev &X = T.xill[A.which];
+  const int i1 = T.conv_i1kev, b0 = T.conv_b0, b1 = T.conv_b1;
+  const double2 *tw = reinterpret_cast<const double2 *>(T.tw);
+  const double2 *cw = reinterpret_cast<const double2 *>(T.conv_w);
+  const int2 *rb_ii = reinterpret_cast<const int2 *>(X.rb_ii);
+  const double2 *rb_dd = reinterpret_cast<const double2 *>(X.rb_dd);
+  for (int k = t; k <= NCONV / 2; k += CONV_NT) { sm.ar[k] = 0.0; sm.ai[k] = 0.0; }
+  for (int z = 0; z < nz; z++) {
+    const double *rel = S.relflux + ((size_t) v * A.nz_stride + z) * A.ne_stride;
+    const double *xz = S.xillz + ((size_t) v * A.nz_stride + z) * X.stride;
+    const int rjlo = S.zrange[((size_t) v * NZMAX + z) * 2], rjhi = S.zrange[((size_t) v * NZMAX + z) * 2 + 1];
+    // ---- pack the zone's spectrum rebinned onto the convolution grid (real part) and its line profile, rotated so
+    //      that 1 keV sits at index 0 (imaginary part), both times E/dE; band and total sums on the way
+    double sums[4] = {0.0, 0.0, 0.0, 0.0};   // all rel, |x|, band x, band rel
+#pragma unroll 1
+    for (int i = t; i < NCONV; i += CONV_NT) {
+      double f = 0.0;
+      if (A.mode == 0) {
+        const int2 ii = __ldg(rb_ii + i);
+        if (ii.x >= 0) {
+          const double2 dd = __ldg(rb_dd + i);
+          if (ii.y == ii.x) f = dd.x * xz[ii.x];
+          else {
+            f += xz[ii.x] * dd.x + xz[ii.y] * dd.y;
+            for (int jj = ii.x + 1; jj <= ii.y - 1; jj++) f += xz[jj];
+          }
+        }
+      } else {
+        f = rebin_bin(T.econv[i], T.econv[i + 1], A.user_e, o, A.n_flux);
+      }
+      const int ri = (i + i1) & (NCONV - 1);
+      const double r = (ri >= rjlo && ri <= rjhi) ? rel[ri] : 0.0;
+      sm.z[cv_pad(i)] = make_double2(f * T.conv_cf[i], r * T.conv_cf[ri]);
+      sums[0] += r;
+      sums[1] += fabs(f);
+      if (i >= b0 && i <= b1) sums[2] += f;
+      if (ri >= b0 && ri <= b1) sums[3] += r;
+    }
+    block_sum_n<4>(sums, sm);
+    const double srel_all = sums[0];
+    const double rscale = vp.renorm ? vp.relline_norm / srel_all : 1.0;   // renorm_relline_profile (one-zone models)
+    const double srel_n = vp.renorm ? srel_all * rscale : srel_all;
+    if (srel_n < 1e-12) { __syncthreads(); continue; }                     // src/Relxill.cpp:455-457
+    // both real inputs ride one complex transform: bring them to the same scale (any factor cancels in the norm)
+    const double bal = (sums[1] > 0.0 && srel_n > 0.0) ? sums[1] / srel_n : 1.0;
+    const double s_xill = sums[2], s_rel = vp.renorm ? sums[3] * rscale : sums[3];
+    fft4096(sm.z, tw, rscale * bal);
+    // ---- split, product spectrum, band sum of the convolved zone in the frequency domain
+    double dot[1] = {0.0};
+    double pr_[5], pi_[5];
+    int nk = 0;
+    for (int k = t; k <= NCONV / 2; k += CONV_NT, nk++) {
+      const int kk = (NCONV - k) & (NCONV - 1);
+      const double2 p = sm.z[cv_pad(k)], q = sm.z[cv_pad(kk)];
+      const double a = p.x, b = p.y, c = q.x, d = q.y;
+      const double Xr = 0.5 * (a + c), Xi = 0.5 * (b - d);
+      const double Yr = 0.5 * (b + d), Yi = 0.5 * (c - a);
+      const double Pr = Xr * Yr - Xi * Yi, Pi = Xr * Yi + Xi * Yr;
+      pr_[nk] = Pr;
+      pi_[nk] = Pi;
+      const double wgt = (k == 0 || k == NCONV / 2) ? 1.0 : 2.0;
+      const double2 w = __ldg(cw + k);
+      dot[0] += wgt * (Pr * w.x + Pi * w.y);
+    }
+    block_sum_n<1>(dot, sm);
+    const double norm = s_rel * s_xill / dot[0];
+    nk = 0;
+    for (int k = t; k <= NCONV / 2; k += CONV_NT, nk++) {
+      sm.ar[k] += norm * pr_[nk];
+      sm.ai[k] += norm * pi_[nk];
+    }
+    __syncthreads();
+  }
+  // ---- one inverse transform for the whole vector: out = Re(FFT(conj(A)))
+  for (int k = t; k <= NCONV / 2; k += CONV_NT) {
+    const double ar = sm.ar[k], ai = (k == 0 || k == NCONV / 2) ? 0.0 : sm.ai[k];
+    sm.z[cv_pad(k)] = make_double2(ar, -ai);
+    if (k > 0 && k < NCONV / 2) sm.z[cv_pad(NCONV - k)] = make_double2(ar, ai);
+  }
+  __syncthreads();
+  fft4096(sm.z, tw, 1.0);
+  double *acc = sm.ar;   // ar and ai are contiguous: 4098 doubles
+  for (int i = t; i < NCONV; i += CONV_NT) acc[i] = sm.z[cv_pad(i)].x / T.conv_cf[i];
+  __syncthreads();
+  if (A.mode == 0) {
+    // primary spectrum on the convolution grid (cutoff power law here; nthcomp is added by k_prim_nthcomp)
+    double refl_scale, prim_scale;
+    if (vp.emis_type != EMIS_LP) {
+      refl_scale = fabs(vp.refl_frac);
+      prim_scale = 1.0;
+    } else {
+      const double *rf = S.reflfrac + (size_t) v * 8;
+      double rfi = vp.refl_frac;
+      if (vp.boost) rfi *= rf[0];
+      prim_scale = rf[4] / 0.5 * pow(vp.eshift_obs, vp.gam);
+      if (vp.beta > 1e-4) prim_scale *= vp.doppler_obs * vp.doppler_obs;
+      refl_scale = (fabs(rfi)) / rf[0];
+    }
+    const double nsrc = S.nsrc[v];
+    const bool add_prim = (vp.refl_frac >= 0);
+    if (vp.prim_type == PRIM_ECUT) {
+      const double ecut = vp.ect * vp.eshift_obs;
+      const double ex0 = exp(1.0 / ecut);
+      for (int i = t; i < NCONV; i += CONV_NT) {
+        const double e0 = T.econv[i], e1 = T.econv[i + 1];
+        const double en = 0.5 * (e0 + e1);
+        double pr = ex0 * pow(en, -vp.gam) * exp(-en / ecut) * (e1 - e0);
+        pr *= nsrc;
+        if (vp.emis_type == EMIS_LP) pr *= prim_scale;
+        double tot = acc[i] * refl_scale;
+        if (add_prim) tot += pr;
+        acc[i] = tot;
+      }
+    } else {
+      for (int i = t; i < NCONV; i += CONV_NT) acc[i] = acc[i] * refl_scale;  // primary added afterwards
+    }
+    __syncthreads();
+    if (A.total) for (int i = t; i < NCONV; i += CONV_NT) A.total[(size_t) v * NCONV + i] = acc[i];
+  }
+  __syncthreads();
+  // rebin to the caller's grid (shifted by 1+z), src/Relxill.cpp:261-278
+  for (int j = t; j < A.n_flux; j += CONV_NT) {
+    double elo = A.user_e[j], ehi = A.user_e[j + 1];
+    if (A.mode == 0 && vp.z > 0) { elo *= (1 + vp.z); ehi *= (1 + vp.z); }
+    double f = rebin_bin(elo, ehi, T.econv, acc, NCONV);
+    if (A.mode == 1 && (ehi < 0.01 || elo > 1000.0)) f = 0;   // src/Relbase.cpp:233-246
+    o[j] = f;
+  }
+}
+
+int conv_kernel_init() {
+  cudaError_t e = cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ConvSmem));
+  if (e != cudaSuccess) return 1;
+  e = cudaFuncSetAttribute(k_conv, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return 1;
+  return 0;
+}
+
+void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
+                 double *out, double *total, int which, int mode, cudaStream_t st) {
+  ConvArgs A;
+  A.user_e = user_e; A.n_flux = n_flux; A.out = out; A.total = total; A.which = which;
+  A.nz_stride = S.nz_cap; A.ne_stride = S.ne_line_cap; A.mode = mode;
+  k_conv<<<(unsigned) n, CONV_NT, sizeof(ConvSmem), st>>>(vps, T, S, A);
+}
+
+}  // namespace rx

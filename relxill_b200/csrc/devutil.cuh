@@ -103,5 +103,25 @@ template <int NT> __device__ double block_sum(double v, double *red) {
   return r;
 }
 
+// _rebin_spectrum (src/relutility.c:549-601) for one output bin, source spectrum in memory `flu0`
+static __device__ double rebin_bin(double elo_out, double ehi_out, const double *__restrict__ e0, const double *flu0, int n0) {
+  if (!((e0[0] <= ehi_out) && (e0[n0] >= elo_out))) return 0.0;
+  int imin = count_le_asc(e0, n0 + 1, elo_out) - 1;
+  if (imin < 0) imin = 0;
+  int imax = count_le_asc(e0, n0 + 1, ehi_out);
+  if (imax > n0) imax = n0;
+  imax -= 1;
+  if (imax < 0) imax = 0;
+  double elo = elo_out, ehi = ehi_out;
+  if (elo < e0[imin]) elo = e0[imin];
+  if (ehi > e0[imax + 1]) ehi = e0[imax + 1];
+  if (imax == imin) return (ehi - elo) / (e0[imin + 1] - e0[imin]) * flu0[imin];
+  const double dmin = (e0[imin + 1] - elo) / (e0[imin + 1] - e0[imin]);
+  const double dmax = (ehi - e0[imax]) / (e0[imax + 1] - e0[imax]);
+  double f = 0.0;
+  f += flu0[imin] * dmin + flu0[imax] * dmax;
+  for (int jj = imin + 1; jj <= imax - 1; jj++) f += flu0[jj];
+  return f;
+}
 
 }  // namespace rx

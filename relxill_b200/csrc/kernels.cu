@@ -790,303 +790,6 @@ __global__ void __launch_bounds__(256) k_linefinish(const VPar *__restrict__ vps
   }
 }
 
-// ---------------------------------------------------------------------------------- k_conv
-// relxill_convolution_multizone (src/Relxill.cpp:432-482) with fftw_conv_spectrum + calcFFTNormFactor
-// (src/Relbase.cpp:119-213), PrimarySource::add_primary_spectrum (src/PrimarySource.cpp:66-125) and
-// rebin_and_normalize_relxill_for_xspec (src/Relxill.cpp:261-278).  One CTA per vector.
-//
-// FFT work per zone is cut from three transforms (reference) to one:
-//   * the two real inputs (xillver spectrum, rotated line profile) share one complex forward transform;
-//   * the band sum of the convolved zone that the normalisation needs is a linear functional of the
-//     product spectrum, sum_i w_i out_i = sum_k P[k] conj(W[k]) with W = DFT(band/cf) tabulated at
-//     load, so it is taken in the frequency domain and no per-zone inverse transform is needed;
-//   * the normalised product spectra of all zones are accumulated in the frequency domain and one inverse
-//     transform per vector brings the sum back (inverse = forward transform of the conjugate).
-// The transform is a 4096-point radix-8 Stockham autosort FFT in shared memory: 4 passes, one butterfly per
-// thread per pass, padded to keep the stride-8 scatter of the first passes off the same banks.
-constexpr int CONV_NT = 512;
-constexpr int CV_PADN = NCONV + NCONV / 8;
-__device__ __forceinline__ int cv_pad(int i) { return i + (i >> 3); }
-
-struct ConvSmem {
-  double zr[CV_PADN], zi[CV_PADN];
-  double ar[NCONV / 2 + 1], ai[NCONV / 2 + 1];   // accumulated spectrum; reused as the final 4096-bin result
-  double red[4 * (CONV_NT / 32)];
-  double bc[4];
-};
-
-// sums four values over the block (fixed order: shuffle tree inside warps, then over the warps)
-__device__ void block_sum4(double (&v)[4], ConvSmem &sm) {
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-#pragma unroll
-  for (int q = 0; q < 4; q++)
-    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
-  __syncthreads();
-  if (lane == 0) {
-#pragma unroll
-    for (int q = 0; q < 4; q++) sm.red[q * (CONV_NT / 32) + w] = v[q];
-  }
-  __syncthreads();
-  if (t < 4) {
-    double s = 0.0;
-    for (int i = 0; i < CONV_NT / 32; i++) s += sm.red[t * (CONV_NT / 32) + i];
-    sm.bc[t] = s;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int q = 0; q < 4; q++) v[q] = sm.bc[q];
-}
-
-__device__ __forceinline__ void cmul(double &xr, double &xi, double wr, double wi) {
-  const double a = xr * wr - xi * wi;
-  xi = xr * wi + xi * wr;
-  xr = a;
-}
-
-// 8-point DFT (forward sign), decimation in frequency, outputs in natural order
-__device__ __forceinline__ void fft8(double (&r)[8], double (&i)[8]) {
-  const double h = 0.70710678118654752440;
-  double ar[8], ai[8];
-#pragma unroll
-  for (int q = 0; q < 4; q++) {
-    ar[q] = r[q] + r[q + 4]; ai[q] = i[q] + i[q + 4];
-    ar[q + 4] = r[q] - r[q + 4]; ai[q + 4] = i[q] - i[q + 4];
-  }
-  {  // twiddles w8^1, w8^2 = -i, w8^3 on the odd half
-    double x = ar[5], y = ai[5];
-    ar[5] = (x + y) * h; ai[5] = (y - x) * h;
-    x = ar[6]; y = ai[6];
-    ar[6] = y; ai[6] = -x;
-    x = ar[7]; y = ai[7];
-    ar[7] = (y - x) * h; ai[7] = (-x - y) * h;
-  }
-  double br[8], bi[8];
-#pragma unroll
-  for (int g = 0; g < 8; g += 4) {
-    br[g] = ar[g] + ar[g + 2]; bi[g] = ai[g] + ai[g + 2];
-    br[g + 2] = ar[g] - ar[g + 2]; bi[g + 2] = ai[g] - ai[g + 2];
-    br[g + 1] = ar[g + 1] + ar[g + 3]; bi[g + 1] = ai[g + 1] + ai[g + 3];
-    const double dx = ar[g + 1] - ar[g + 3], dy = ai[g + 1] - ai[g + 3];
-    br[g + 3] = dy; bi[g + 3] = -dx;   // times -i
-  }
-  r[0] = br[0] + br[1]; i[0] = bi[0] + bi[1];
-  r[4] = br[0] - br[1]; i[4] = bi[0] - bi[1];
-  r[2] = br[2] + br[3]; i[2] = bi[2] + bi[3];
-  r[6] = br[2] - br[3]; i[6] = bi[2] - bi[3];
-  r[1] = br[4] + br[5]; i[1] = bi[4] + bi[5];
-  r[5] = br[4] - br[5]; i[5] = bi[4] - bi[5];
-  r[3] = br[6] + br[7]; i[3] = bi[6] + bi[7];
-  r[7] = br[6] - br[7]; i[7] = bi[6] - bi[7];
-}
-
-// in-place forward FFT of the padded arrays; tw[m] = exp(-2 pi i m / 4096); all CONV_NT threads call
-__device__ void fft4096(double *zr, double *zi, const double2 *__restrict__ tw) {
-  const int j = threadIdx.x;
-#pragma unroll 1
-  for (int pass = 0; pass < 4; pass++) {
-    const int ns = 1 << (3 * pass);          // 1, 8, 64, 512
-    const int k = j & (ns - 1);
-    double r[8], im[8];
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-      const int idx = cv_pad(j + q * (NCONV / 8));
-      r[q] = zr[idx];
-      im[q] = zi[idx];
-    }
-    if (pass > 0) {
-      const int mb = k * ((NCONV / 8) >> (3 * pass));   // k * 512 / ns
-#pragma unroll
-      for (int q = 1; q < 8; q++) {
-        const double2 w = __ldg(tw + q * mb);
-        cmul(r[q], im[q], w.x, w.y);
-      }
-    }
-    fft8(r, im);
-    __syncthreads();
-    const int j0 = ((j - k) << 3) + k;       // (j / ns) * ns * 8 + k
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-      const int idx = cv_pad(j0 + q * ns);
-      zr[idx] = r[q];
-      zi[idx] = im[q];
-    }
-    __syncthreads();
-  }
-}
-
-// _rebin_spectrum (src/relutility.c:549-601) for one output bin, source spectrum in memory `flu0`
-__device__ double rebin_bin(double elo_out, double ehi_out, const double *__restrict__ e0, const double *flu0, int n0) {
-  if (!((e0[0] <= ehi_out) && (e0[n0] >= elo_out))) return 0.0;
-  int imin = count_le_asc(e0, n0 + 1, elo_out) - 1;
-  if (imin < 0) imin = 0;
-  int imax = count_le_asc(e0, n0 + 1, ehi_out);
-  if (imax > n0) imax = n0;
-  imax -= 1;
-  if (imax < 0) imax = 0;
-  double elo = elo_out, ehi = ehi_out;
-  if (elo < e0[imin]) elo = e0[imin];
-  if (ehi > e0[imax + 1]) ehi = e0[imax + 1];
-  if (imax == imin) return (ehi - elo) / (e0[imin + 1] - e0[imin]) * flu0[imin];
-  const double dmin = (e0[imin + 1] - elo) / (e0[imin + 1] - e0[imin]);
-  const double dmax = (ehi - e0[imax]) / (e0[imax + 1] - e0[imax]);
-  double f = 0.0;
-  f += flu0[imin] * dmin + flu0[imax] * dmax;
-  for (int jj = imin + 1; jj <= imax - 1; jj++) f += flu0[jj];
-  return f;
-}
-
-struct ConvArgs {
-  const double *user_e;   // [n_flux+1] device
-  int n_flux;
-  double *out;            // [C][n_flux] device
-  double *total;          // [C][NCONV] device (probe; may be null)
-  int which;              // xillver table index
-  int nz_stride, ne_stride;
-  int mode;               // 0 relxill, 1 convolution model (input spectrum in `out`)
-};
-
-__global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vps, DevTables T, Scratch S, ConvArgs A) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  ConvSmem &sm = *reinterpret_cast<ConvSmem *>(smraw);
-  const int v = blockIdx.x, t = threadIdx.x;
-  double *o = A.out + (size_t) v * A.n_flux;
-  const VPar &vp = vps[v];
-  if (S.status[v] != ST_OK) {
-    for (int j = t; j < A.n_flux; j += CONV_NT) o[j] = 0.0;
-    return;
-  }
-  const int nz = (A.mode == 0) ? vp.nz : 1;
-  const XillDev &X = T.xill[A.which];
-  const int i1 = T.conv_i1kev;
-  const double2 *tw = reinterpret_cast<const double2 *>(T.tw);
-  for (int k = t; k <= NCONV / 2; k += CONV_NT) { sm.ar[k] = 0.0; sm.ai[k] = 0.0; }
-  for (int z = 0; z < nz; z++) {
-    const double *rel = S.relflux + ((size_t) v * A.nz_stride + z) * A.ne_stride;
-    const double *xz = S.xillz + ((size_t) v * A.nz_stride + z) * X.stride;
-    const int rjlo = S.zrange[((size_t) v * NZMAX + z) * 2], rjhi = S.zrange[((size_t) v * NZMAX + z) * 2 + 1];
-    // ---- rebin the zone's spectrum onto the convolution grid (x part of the packed transform) + sums
-    double sums[4] = {0.0, 0.0, 0.0, 0.0};   // all rel, |x|, band x, band rel
-    for (int i = t; i < NCONV; i += CONV_NT) {
-      double f = 0.0;
-      if (A.mode == 0) {
-        const int imin = X.rb_imin[i];
-        if (imin >= 0) {
-          const int imax = X.rb_imax[i];
-          if (imax == imin) f = X.rb_dmin[i] * xz[imin];
-          else {
-            f += xz[imin] * X.rb_dmin[i] + xz[imax] * X.rb_dmax[i];
-            for (int jj = imin + 1; jj <= imax - 1; jj++) f += xz[jj];
-          }
-        }
-      } else {
-        f = rebin_bin(T.econv[i], T.econv[i + 1], A.user_e, o, A.n_flux);
-      }
-      const double r = (i >= rjlo && i <= rjhi) ? rel[i] : 0.0;
-      sm.zr[cv_pad(i)] = f * T.conv_cf[i];
-      sums[0] += r;
-      sums[1] += fabs(f);
-      if (T.conv_band[i]) { sums[2] += f; sums[3] += r; }
-    }
-    block_sum4(sums, sm);
-    const double srel_all = sums[0];
-    const double rscale = vp.renorm ? vp.relline_norm / srel_all : 1.0;   // renorm_relline_profile (one-zone models)
-    const double srel_n = vp.renorm ? srel_all * rscale : srel_all;
-    if (srel_n < 1e-12) { __syncthreads(); continue; }                     // src/Relxill.cpp:455-457
-    // both real inputs ride one complex transform: bring them to the same scale (any factor cancels in the norm)
-    const double bal = (sums[1] > 0.0 && srel_n > 0.0) ? sums[1] / srel_n : 1.0;
-    const double s_xill = sums[2], s_rel = vp.renorm ? sums[3] * rscale : sums[3];
-    for (int i = t; i < NCONV; i += CONV_NT) {
-      const double r0 = (i >= rjlo && i <= rjhi) ? rel[i] : 0.0;
-      const double r = vp.renorm ? r0 * rscale : r0;
-      sm.zi[cv_pad((i - i1 + NCONV) & (NCONV - 1))] = (r * T.conv_cf[i]) * bal;
-    }
-    __syncthreads();
-    fft4096(sm.zr, sm.zi, tw);
-    // ---- split, product spectrum, band sum of the convolved zone in the frequency domain
-    double dot[4] = {0.0, 0.0, 0.0, 0.0};
-    double pr_[5], pi_[5];
-    int nk = 0;
-    for (int k = t; k <= NCONV / 2; k += CONV_NT, nk++) {
-      const int kk = (NCONV - k) & (NCONV - 1);
-      const double a = sm.zr[cv_pad(k)], b = sm.zi[cv_pad(k)], c = sm.zr[cv_pad(kk)], d = sm.zi[cv_pad(kk)];
-      const double Xr = 0.5 * (a + c), Xi = 0.5 * (b - d);
-      const double Yr = 0.5 * (b + d), Yi = 0.5 * (c - a);
-      const double Pr = Xr * Yr - Xi * Yi, Pi = Xr * Yi + Xi * Yr;
-      pr_[nk] = Pr;
-      pi_[nk] = Pi;
-      const double wgt = (k == 0 || k == NCONV / 2) ? 1.0 : 2.0;
-      dot[0] += wgt * (Pr * T.conv_wr[k] + Pi * T.conv_wi[k]);
-    }
-    block_sum4(dot, sm);
-    const double norm = s_rel * s_xill / dot[0];
-    nk = 0;
-    for (int k = t; k <= NCONV / 2; k += CONV_NT, nk++) {
-      sm.ar[k] += norm * pr_[nk];
-      sm.ai[k] += norm * pi_[nk];
-    }
-    __syncthreads();
-  }
-  // ---- one inverse transform for the whole vector: out = Re(FFT(conj(A)))
-  for (int k = t; k <= NCONV / 2; k += CONV_NT) {
-    const double ar = sm.ar[k], ai = (k == 0 || k == NCONV / 2) ? 0.0 : sm.ai[k];
-    sm.zr[cv_pad(k)] = ar;
-    sm.zi[cv_pad(k)] = -ai;
-    if (k > 0 && k < NCONV / 2) {
-      sm.zr[cv_pad(NCONV - k)] = ar;
-      sm.zi[cv_pad(NCONV - k)] = ai;
-    }
-  }
-  __syncthreads();
-  fft4096(sm.zr, sm.zi, tw);
-  double *acc = sm.ar;   // ar and ai are contiguous: 4098 doubles
-  for (int i = t; i < NCONV; i += CONV_NT) acc[i] = sm.zr[cv_pad(i)] / T.conv_cf[i];
-  __syncthreads();
-  if (A.mode == 0) {
-    // primary spectrum on the convolution grid (cutoff power law here; nthcomp is added by k_prim_nthcomp)
-    double refl_scale, prim_scale;
-    if (vp.emis_type != EMIS_LP) {
-      refl_scale = fabs(vp.refl_frac);
-      prim_scale = 1.0;
-    } else {
-      const double *rf = S.reflfrac + (size_t) v * 8;
-      double rfi = vp.refl_frac;
-      if (vp.boost) rfi *= rf[0];
-      prim_scale = rf[4] / 0.5 * pow(vp.eshift_obs, vp.gam);
-      if (vp.beta > 1e-4) prim_scale *= vp.doppler_obs * vp.doppler_obs;
-      refl_scale = (fabs(rfi)) / rf[0];
-    }
-    const double nsrc = S.nsrc[v];
-    const bool add_prim = (vp.refl_frac >= 0);
-    if (vp.prim_type == PRIM_ECUT) {
-      const double ecut = vp.ect * vp.eshift_obs;
-      const double ex0 = exp(1.0 / ecut);
-      for (int i = t; i < NCONV; i += CONV_NT) {
-        const double e0 = T.econv[i], e1 = T.econv[i + 1];
-        const double en = 0.5 * (e0 + e1);
-        double pr = ex0 * pow(en, -vp.gam) * exp(-en / ecut) * (e1 - e0);
-        pr *= nsrc;
-        if (vp.emis_type == EMIS_LP) pr *= prim_scale;
-        double tot = acc[i] * refl_scale;
-        if (add_prim) tot += pr;
-        acc[i] = tot;
-      }
-    } else {
-      for (int i = t; i < NCONV; i += CONV_NT) acc[i] = acc[i] * refl_scale;  // primary added afterwards
-    }
-    __syncthreads();
-    if (A.total) for (int i = t; i < NCONV; i += CONV_NT) A.total[(size_t) v * NCONV + i] = acc[i];
-  }
-  __syncthreads();
-  // rebin to the caller's grid (shifted by 1+z), src/Relxill.cpp:261-278
-  for (int j = t; j < A.n_flux; j += CONV_NT) {
-    double elo = A.user_e[j], ehi = A.user_e[j + 1];
-    if (A.mode == 0 && vp.z > 0) { elo *= (1 + vp.z); ehi *= (1 + vp.z); }
-    double f = rebin_bin(elo, ehi, T.econv, acc, NCONV);
-    if (A.mode == 1 && (ehi < 0.01 || elo > 1000.0)) f = 0;   // src/Relbase.cpp:233-246
-    o[j] = f;
-  }
-}
-
 // ---------------------------------------------------------------------------------- k_xillver
 // Standalone xillver / xillverCp (LocalModel::xillver_model, src/LocalModel.cpp:104-130): interpolation over
 // all table axes including the inclination (interp_5d_tab / interp_6d_tab, src/xilltable.c:878-1044),
@@ -1191,6 +894,7 @@ static size_t g_smem_sys = 0, g_smem_zone = 0;
 
 int line_kernel_init();
 int xill_kernel_init();
+int conv_kernel_init();
 
 int kernels_init() {
   g_smem_sys = sizeof(SysSmem);
@@ -1204,10 +908,7 @@ int kernels_init() {
   if (e != cudaSuccess) return 1;
   if (line_kernel_init() != 0) return 1;
   if (xill_kernel_init() != 0) return 1;
-  e = cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ConvSmem));
-  if (e != cudaSuccess) return 1;
-  e = cudaFuncSetAttribute(k_conv, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
-  if (e != cudaSuccess) return 1;
+  if (conv_kernel_init() != 0) return 1;
   return 0;
 }
 
@@ -1233,13 +934,4 @@ void launch_xillver(const VPar *vps, const DevTables &T, const Scratch &S, long 
                     int n_flux, double *out, int stride, cudaStream_t st) {
   k_xillver<<<(unsigned) n, 256, (size_t) stride * sizeof(double), st>>>(vps, T, S, which, user_e, n_flux, out);
 }
-void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
-                 double *out, double *total, int which, int mode, cudaStream_t st) {
-  ConvArgs A;
-  A.user_e = user_e; A.n_flux = n_flux; A.out = out; A.total = total; A.which = which;
-  A.nz_stride = S.nz_cap; A.ne_stride = S.ne_line_cap; A.mode = mode;
-  const size_t sm = sizeof(ConvSmem);
-  k_conv<<<(unsigned) n, CONV_NT, sm, st>>>(vps, T, S, A);
-}
-
 }  // namespace rx

@@ -132,11 +132,15 @@ void Tables::load_fixed() {
         wr[i + k + half] = ur - vr; wi[i + k + half] = ui - vi;
       }
   }
-  wr.resize(NCONV / 2 + 1);
-  wi.resize(NCONV / 2 + 1);
+  std::vector<double> wpack(2 * (NCONV / 2 + 1));
+  for (int k = 0; k <= NCONV / 2; k++) { wpack[2 * k] = wr[k]; wpack[2 * k + 1] = wi[k]; }
+  int b0 = NCONV, b1 = -1;
+  for (int i = 0; i < NCONV; i++)
+    if (band[i]) { b0 = std::min(b0, i); b1 = std::max(b1, i); }
   dt_.econv = upload(econv_);
   dt_.conv_cf = upload(cf);
-  dt_.conv_band = upload(band);
+  dt_.conv_b0 = b0;
+  dt_.conv_b1 = b1;
   dt_.conv_i1kev = lower_index(econv_.data(), NCONV + 1, 1.0);                      // src/Relbase.cpp:133-137
   dt_.ecoarse = upload(ecoarse_);
   dt_.coarse_m1 = upload(m1);
@@ -144,8 +148,7 @@ void Tables::load_fixed() {
   dt_.gstar = upload(gstar);
   dt_.d_gstar = upload(dg);
   dt_.tw = upload(tw);
-  dt_.conv_wr = upload(wr);
-  dt_.conv_wi = upload(wi);
+  dt_.conv_w = upload(wpack);
   have_fixed_ = true;
 }
 
@@ -428,11 +431,15 @@ std::string Tables::load_xill(int which) {
   xd.node_ef = upload(ef);
   xd.node_p1 = upload(p1);
   xd.node_p2 = upload(p2);
-  xd.rb_imin = upload(imin_v);
-  xd.rb_imax = upload(imax_v);
-  xd.rb_dmin = upload(dmin_v);
-  xd.rb_dmax = upload(dmax_v);
-  if (!xd.rb_dmax) return "out of device memory (xillver table)";
+  std::vector<int> ii_v(2 * NCONV);
+  std::vector<double> dd_v(2 * NCONV);
+  for (int i = 0; i < NCONV; i++) {
+    ii_v[2 * i] = imin_v[i]; ii_v[2 * i + 1] = imax_v[i];
+    dd_v[2 * i] = dmin_v[i]; dd_v[2 * i + 1] = dmax_v[i];
+  }
+  xd.rb_ii = upload(ii_v);
+  xd.rb_dd = upload(dd_v);
+  if (!xd.rb_dd) return "out of device memory (xillver table)";
   xh.loaded = true;
   return "";
 }
