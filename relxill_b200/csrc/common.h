@@ -8,6 +8,7 @@ namespace rx {
 // sizes fixed by the table formats / the reference (src/common.h:69-81,127-136; src/Xillspec.h:28-38)
 constexpr int NR = 1000;       // fine radial grid
 constexpr int NG = 40;         // g* grid
+constexpr double CONV_EMIN = 0.00035, CONV_EMAX = 2000.0;   // convolution grid, src/Xillspec.h:36-38
 constexpr int NCONV = 4096;    // convolution grid bins
 constexpr int NCOARSE = 500;   // xillver-normalisation grid bins
 constexpr int NZMAX = 50;      // radial zones

@@ -6,18 +6,23 @@
 // relb_func (src/Relprofile.cpp:489-726,835-905) and the division by the bin energy of
 // renorm_relline_profile (:757-762).
 //
-// Mapping.  One CTA per (vector, radial zone).  The zone's radii are processed in sub-batches; inside a
-// sub-batch all (radius, energy-bin) pairs that the reference's double loop visits are flattened into one
+// Mapping.  One CTA (4 warps) per (vector, radial zone).  The zone's radii are processed in sub-batches; inside
+// a sub-batch all (radius, energy-bin) pairs that the reference's double loop visits are flattened into one
 // dense item list (the bins of one radius are contiguous: [ielo, iehi]), so lanes stay busy whatever the
-// line width is.
-//   phase 1  one thread per item.  Edge terms, midpoint bins and Romberg bins up to two halvings are
-//            finished here; a bin whose Romberg integral has not converged by then (the horns of the
-//            profile, a few per cent of the bins) is pushed on a shared-memory work list.
-//   phase 2  one HALF WARP per listed bin: the dyadic abscissae of the deeper Romberg levels are
-//            evaluated in parallel across the lanes (17 points for levels <= 4, 65 for levels <= 6) and
-//            the tableau is built from class sums of one xor-butterfly.
+// line width is.  The work is sorted by cost so that the lanes of a warp do the same thing:
+//   set-up   lane = radius, one warp per task: first bin, last bin (closed-form index on the logarithmic
+//            convolution grid, corrected against the tabulated edges) and the integrand at the two edge
+//            nodes g* = h, 1-h that int_edge needs (once per radius instead of once per edge bin);
+//            offsets by a warp scan.
+//   pass A   one thread per item: analytic edge terms and the midpoint-rule bins (E < 0.95) are finished;
+//            the bins that take the Romberg path are gathered in a dense list.
+//   pass B   one thread per Romberg bin: two halvings (five abscissae) unconditionally; a bin that has not
+//            converged by then (the horns of the profile, a few per cent of the bins) goes on a work list.
+//   phase 2  one HALF WARP per listed bin: the 16 new abscissae of levels <= 4 are evaluated in parallel
+//            across the lanes, the level sums come from one xor-butterfly, and the tableaus of 32 bins are
+//            then built in parallel, one per lane.  Levels 5-6 (rare) are finished by the owning lane.
 //   phase 3  per energy bin, the sub-batch's contributions are added in ascending-radius order into the
-//            zone accumulator -> no atomics on data, bit-reproducible, the reference's summation order.
+//            zone's output row -> no atomics on data, bit-reproducible, the reference's summation order.
 //
 // Arithmetic.  The two branches k = 0, 1 of the transfer function share everything but the interpolated
 // trff value, so one evaluation of the integrand returns both (the reference calls relb_func twice).
@@ -28,6 +33,8 @@
 // arithmetically (the grid is uniform), which can differ from the reference's binary search only when g*
 // sits within an ulp of a node, where the piecewise-linear interpolant is continuous.
 #include <cuda_runtime.h>
+
+#include <cmath>
 
 #include "common.h"
 #include "devutil.cuh"
@@ -75,215 +82,12 @@ __device__ __forceinline__ bool not_converged(double t_new, double t_old) {
 
 __device__ __forceinline__ double gstar2ener(double g, double gmin, double gmax) { return (g * (gmax - gmin) + gmin) * 1.0; }
 
-__device__ double int_edge(double blo, double bhi, const RelbCtx &c) {  // src/Relprofile.cpp:585-621 (h = GFAC_H)
-  double hex, lo, hi;
-  if (blo <= 0.5) { hex = GFAC_H; lo = blo; hi = bhi; }
-  else { hex = 1.0 - GFAC_H; lo = 1.0 - bhi; hi = 1.0 - blo; }
-  double n0, n1;
-  relb2(gstar2ener(hex, c.gmin, c.gmax), c, n0, n1);
-  double norm = 0.0;
-  norm = norm + n0;
-  norm = norm + n1;
-  norm = norm * sqrt(GFAC_H);
-  return 2 * norm * (sqrt(hi) - sqrt(lo)) * 1.0 * (c.gmax - c.gmin);
-}
-
-// Romberg on [a, b] for both branches, at most two halvings (src/Relprofile.cpp:524-579 with the loop cut
-// after niter = 2).  Returns true and the sum of the two integrals if both branches converged.
-__device__ bool romberg2_capped(double a, double b, const RelbCtx &c, double &out, double (&fend)[2]) {
-  double fa0, fa1, fb0, fb1, m0, m1;
-  relb2(a, c, fa0, fa1);
-  relb2(b, c, fb0, fb1);
-  fend[0] = fa0; fend[1] = fa1;
-  const double ta0 = (fa0 + fb0) / 2.0, ta1 = (fa1 + fb1) / 2.0;
-  const double pas = b - a;
-  const double t00_0 = ta0 * pas, t00_1 = ta1 * pas;
-  const double pas1 = pas / 2.0;
-  relb2(a + pas1 * 1, c, m0, m1);
-  const double t01_0 = (ta0 + m0) * pas1, t01_1 = (ta1 + m1) * pas1;
-  const double t10_0 = (4.0 * t01_0 - t00_0) / 3.0, t10_1 = (4.0 * t01_1 - t00_1) / 3.0;
-  const bool nc0 = not_converged(t10_0, t00_0), nc1 = not_converged(t10_1, t00_1);
-  if (!nc0 && !nc1) { out = t10_0 + t10_1; return true; }
-  const double pas2 = pas1 / 2.0;
-  double q0, q1, u0, u1;
-  relb2(a + pas2 * 1, c, q0, q1);
-  relb2(a + pas2 * 3, c, u0, u1);
-  double r0 = t10_0, r1 = t10_1;
-  bool bad = false;
-  if (nc0) {
-    const double t02 = (((ta0 + q0) + m0) + u0) * pas2;
-    const double t11 = (4.0 * t02 - t01_0) / 3.0;
-    const double t20 = (16.0 * t11 - t10_0) / 15.0;
-    bad |= not_converged(t20, t10_0);
-    r0 = t20;
-  }
-  if (nc1) {
-    const double t02 = (((ta1 + q1) + m1) + u1) * pas2;
-    const double t11 = (4.0 * t02 - t01_1) / 3.0;
-    const double t20 = (16.0 * t11 - t10_1) / 15.0;
-    bad |= not_converged(t20, t10_1);
-    r1 = t20;
-  }
-  out = r0 + r1;
-  return !bad;
-}
-
 // Richardson step of the Romberg tableau, t[ii] = (4^ii t[ii-1] - tprev[ii-1]) / (4^ii - 1), with the
 // divisions replaced by the tabulated reciprocals
 __device__ __forceinline__ double richardson(int ii, double cur_lo, double prev_lo) {
   const double r4[7] = {1.0, 4.0, 16.0, 64.0, 256.0, 1024.0, 4096.0};
   const double inv[7] = {0.0, 1.0 / 3.0, 1.0 / 15.0, 1.0 / 63.0, 1.0 / 255.0, 1.0 / 1023.0, 1.0 / 4095.0};
   return (r4[ii] * cur_lo - prev_lo) * inv[ii];
-}
-
-// Full-depth Romberg of one bin by a HALF warp (16 lanes; the two halves of a warp work on different bins;
-// `active` is uniform per half; all 32 lanes must call).  All lanes of the half return the sum of the two
-// branch integrals.  Levels 1..4 use the 17 dyadic points of spacing (b-a)/16 (lane h evaluates point h+1,
-// lane 0 also the lower end point), levels 5..6 the 65 points of spacing (b-a)/64.  The level sums come from
-// one xor-butterfly per depth: after the steps 8,4,2 the lanes whose index has the same low bits hold the sum
-// of their residue class, i.e. exactly the points that are new at one Romberg level.
-__device__ double romberg2_half(double a, double b, const RelbCtx &c, bool active, const double *fend) {
-  const unsigned FULL = 0xffffffffu;
-  const int h = threadIdx.x & 15;          // lane inside the half
-  const int base = threadIdx.x & 16;       // first lane of this half inside the warp
-  const double pas = b - a;
-  double res[2] = {0.0, 0.0};
-  bool done[2] = {!active, !active};
-  double tprev[2][7], ta[2];
-  // ---- depth 4: point p = h + 1 (p = 16 is the upper end point), lane 0 additionally p = 0
-  const double pas4 = pas / 16.0;
-  double v[2] = {0.0, 0.0};
-  if (active) relb2(h == 15 ? b : a + pas4 * (h + 1), c, v[0], v[1]);   // f(a) comes from phase 1
-#pragma unroll
-  for (int k = 0; k < 2; k++) {
-    const double fa = active ? fend[k] : 0.0, fb = __shfl_sync(FULL, v[k], base + 15);
-    // class sums over the interior points p = 1..15 (lane h = p - 1): odd p, p = 2 mod 4, p = 4 mod 8, p = 8
-    double x = (h == 15) ? 0.0 : v[k];
-    const double n1 = __shfl_sync(FULL, x, base + 7);                 // p = 8
-    x += __shfl_xor_sync(FULL, x, 8);
-    const double n2 = __shfl_sync(FULL, x, base + 3);                 // p = 4, 12
-    x += __shfl_xor_sync(FULL, x, 4);
-    const double n3 = __shfl_sync(FULL, x, base + 1);                 // p = 2, 6, 10, 14
-    x += __shfl_xor_sync(FULL, x, 2);
-    const double n4 = __shfl_sync(FULL, x, base + 0);                 // odd p
-    if (done[k]) continue;
-    ta[k] = (fa + fb) / 2.0;
-    tprev[k][0] = ta[k] * pas;
-    double last = tprev[k][0], pasn = pas, sum = ta[k];
-    const double newp[5] = {0.0, n1, n2, n3, n4};
-#pragma unroll
-    for (int n = 1; n <= 4; n++) {
-      pasn = pasn * 0.5;
-      sum += newp[n];
-      if (!done[k]) {
-        double cur[7];
-        cur[0] = sum * pasn;
-#pragma unroll
-        for (int ii = 1; ii <= 4; ii++) if (ii <= n) cur[ii] = richardson(ii, cur[ii - 1], tprev[k][ii - 1]);
-        res[k] = cur[n];
-        if (!not_converged(cur[n], last)) done[k] = true;
-        last = cur[n];
-#pragma unroll
-        for (int ii = 0; ii <= 4; ii++) if (ii <= n) tprev[k][ii] = cur[ii];
-      }
-    }
-  }
-  // ---- depth 6 (rare): 63 interior points, lane h takes p = h + 1 + 16 q, q = 0..3 (p = 64 is the end point)
-  const bool need6 = !(done[0] && done[1]);
-  if (__any_sync(FULL, need6)) {
-    const double pas6 = pas / 64.0;
-    double w0[4], w1[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      w0[q] = 0.0; w1[q] = 0.0;
-      const int pidx = h + 1 + 16 * q;
-      if (need6 && pidx < 64) relb2(a + pas6 * pidx, c, w0[q], w1[q]);
-    }
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-      // new points of level 6: odd p; of level 5: p = 2 mod 4 (the others were used by levels <= 4)
-      double o6 = 0.0, o5 = 0.0;
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const int pidx = h + 1 + 16 * q;
-        const double val = k ? w1[q] : w0[q];
-        if (pidx < 64) {
-          if (pidx & 1) o6 += val;
-          else if ((pidx & 3) == 2) o5 += val;
-        }
-      }
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-        o6 += __shfl_xor_sync(FULL, o6, o);
-        o5 += __shfl_xor_sync(FULL, o5, o);
-      }
-      if (done[k]) continue;
-      // the level-4 trapezoid sum is recovered from the tableau row: cur[0] = sum * pasn
-      double pasn = pas / 16.0;
-      double sum = tprev[k][0] / pasn;
-      double last = res[k];
-      const double newp[2] = {o5, o6};
-#pragma unroll
-      for (int n = 5; n <= 6; n++) {
-        pasn = pasn * 0.5;
-        sum += newp[n - 5];
-        if (!done[k]) {
-          double cur[7];
-          cur[0] = sum * pasn;
-#pragma unroll
-          for (int ii = 1; ii <= 6; ii++) if (ii <= n) cur[ii] = richardson(ii, cur[ii - 1], tprev[k][ii - 1]);
-          res[k] = cur[n];
-          if (!not_converged(cur[n], last)) done[k] = true;
-          last = cur[n];
-#pragma unroll
-          for (int ii = 0; ii <= 6; ii++) if (ii <= n) tprev[k][ii] = cur[ii];
-        }
-      }
-    }
-  }
-  return res[0] + res[1];
-}
-
-// integ_relline_bin (src/Relprofile.cpp:650-726) without the deep Romberg levels: returns the bin integral,
-// or (deferred = true) the edge terms only, with [ra, rb] the interval still to be integrated.
-__device__ double integ_bin_phase1(const RelbCtx &c, double rlo0, double rhi0, bool &deferred, double &ra, double &rb, double (&fend)[2]) {
-  deferred = false;
-  double flu = 0.0;
-  double gblo = (rlo0 / 1.0 - c.gmin) * c.del_g;
-  if (gblo < 0.0) gblo = 0.0; else if (gblo > 1.0) gblo = 1.0;
-  double gbhi = (rhi0 / 1.0 - c.gmin) * c.del_g;
-  if (gbhi < 0.0) gbhi = 0.0; else if (gbhi > 1.0) gbhi = 1.0;
-  if (gbhi == 0) return 0.0;
-  double rlo = rlo0, rhi = rhi0, hlo, hhi;
-  if (gblo <= GFAC_H) {
-    hlo = gblo;
-    hhi = GFAC_H;
-    rlo = gstar2ener(GFAC_H, c.gmin, c.gmax);
-    if (gbhi <= GFAC_H) { hhi = gbhi; rlo = -1.0; }
-    flu = flu + int_edge(hlo, hhi, c);
-  }
-  if (gbhi >= (1.0 - GFAC_H)) {
-    hhi = gbhi;
-    hlo = 1.0 - GFAC_H;
-    rhi = gstar2ener(1 - GFAC_H, c.gmin, c.gmax);
-    if (gblo >= (1.0 - GFAC_H)) { hlo = gblo; rhi = -1.0; }
-    flu = flu + int_edge(hlo, hhi, c);
-  }
-  if ((rhi >= 0) && (rlo >= 0)) {
-    if (rlo >= 1.0 * 0.95) {  // src/Relprofile.cpp:628-647
-      double f2;
-      if (romberg2_capped(rlo, rhi, c, f2, fend)) flu = flu + f2;
-      else { deferred = true; ra = rlo; rb = rhi; }
-    } else {
-      double m0, m1;
-      relb2((rhi + rlo) / 2.0, c, m0, m1);
-      double f2 = 0.0;
-      f2 += m0 * (rhi - rlo);
-      f2 += m1 * (rhi - rlo);
-      flu = flu + f2;
-    }
-  }
-  return flu;
 }
 
 // grid_mode 0: the fixed convolution grid; 1: the caller's grid shifted by (1+z) and divided by lineE
@@ -296,50 +100,135 @@ __device__ __forceinline__ double line_edge(const double *egrid, int j, int grid
   }
   return e;
 }
-// binary_search(ener, n+1, val) of the reference on the (possibly rescaled) grid
-__device__ int line_bsearch(const double *egrid, int n_edges, double val, int grid_mode, double z, double lineE) {
-  int klo = 0, khi = n_edges - 1;
+// binary_search(ener, n+1, val) of the reference on the (possibly rescaled) grid: the last index k <= n_edges-2
+// with edge[k] <= val (0 if none).  On the logarithmic convolution grid the index is computed in closed form
+// and then corrected against the tabulated edges, so the result is the search's, without its dependent loads.
+struct LineGrid {
+  const double *e;
+  int n_ener, mode;
+  double log_lo, inv_dlog;   // mode 0: edge[k] ~ exp(log_lo + k / inv_dlog)
+};
+__device__ int line_index(const LineGrid &G, double val, double z, double lineE) {
+  const int last = G.n_ener - 1;   // n_edges - 2
+  if (G.mode == 0) {
+    int k = (int) floor((log(val) - G.log_lo) * G.inv_dlog);
+    k = k < 0 ? 0 : (k > last ? last : k);
+    while (k < last && __ldg(G.e + k + 1) <= val) k++;
+    while (k > 0 && __ldg(G.e + k) > val) k--;
+    return k;
+  }
+  int klo = 0, khi = G.n_ener;
   while (khi - klo > 1) {
     const int k = (khi + klo) >> 1;
-    if (line_edge(egrid, k, grid_mode, z, lineE) > val) khi = k; else klo = k;
+    if (line_edge(G.e, k, 1, z, lineE) > val) khi = k; else klo = k;
   }
   return klo;
 }
 
-constexpr int LN_NT = 256;
-constexpr int LN_BUF = 2048;   // contribution slots per sub-batch
-constexpr int LN_MAXR = 64;    // radii per sub-batch
+constexpr int LN_NT = 128;
+constexpr int LN_BUF = 1024;     // contribution slots (items) per sub-batch
+constexpr int LN_MAXR = 32;      // radii per sub-batch: one lane each in the set-up warp
+constexpr int LN_MAXDEF = 256;   // work list of the deep Romberg bins
 struct LnRad {
   double gmin, gmax, del_g, scale, weight;
+  double nlo, nhi;               // `norm` of int_edge (src/Relprofile.cpp:585-621) at g* = h and g* = 1-h
   int ielo, iehi, off, gi;
 };
 struct LnSmem {
   double contrib[LN_BUF];
-  double def_a[LN_BUF / 4], def_b[LN_BUF / 4];   // work list of phase 2: interval still to integrate
-  double def_f[LN_BUF / 4][2];                    // ... and the integrand at its lower end (both branches)
+  double def_a[LN_MAXDEF], def_b[LN_MAXDEF];      // work list of phase 2: interval still to integrate
+  double def_f[LN_MAXDEF][2];                     // ... and the integrand at its lower end (both branches)
   LnRad rad[LN_MAXR + 1];
-  unsigned short def_item[LN_BUF / 4];
-  unsigned char item_rad[LN_BUF];                 // sub-batch radius of every item
-  int nrad, ndef, overflow, cursor, jlo, jhi, resume;   // resume: first bin still to do of radius `cursor` (-1 = all)
+  unsigned short rlist[LN_BUF];                   // items that take the Romberg path
+  unsigned short def_item[LN_MAXDEF];
+  unsigned char item_rad[LN_BUF];                 // sub-batch radius of every item (bit 7: retry flag)
+  int nrad, nrom, ndef, overflow, cursor, jlo, jhi, resume;   // resume: first bin still to do of radius `cursor` (-1 = all)
   int zjlo, zjhi;
 };
-constexpr int LN_MAXDEF = LN_BUF / 4;
 
 __device__ __forceinline__ void ln_ctx(const LnRad &lr, const double2 *g_trff, const double2 *g_cosne, int limb, RelbCtx &c) {
   c.gmin = lr.gmin; c.gmax = lr.gmax; c.del_g = lr.del_g; c.scale = lr.scale;
   c.trff = g_trff + (size_t) lr.gi * NG; c.cosne = g_cosne + (size_t) lr.gi * NG; c.limb = limb;
 }
 
-__global__ void __launch_bounds__(LN_NT, 3) k_line(const VPar *__restrict__ vps, DevTables T, Scratch S,
-                                                   const double *__restrict__ egrid, int n_ener, int grid_mode,
-                                                   int ne_stride, int nz_stride, int n_acc) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  LnSmem &sm = *reinterpret_cast<LnSmem *>(smraw);
-  double *acc = reinterpret_cast<double *>(smraw + sizeof(LnSmem));   // [n_acc]
+// int_edge (src/Relprofile.cpp:585-621) with the integrand at the edge node already summed into `norm`
+__device__ __forceinline__ double edge_term(double blo, double bhi, double norm, double gmin, double gmax) {
+  double lo, hi;
+  if (blo <= 0.5) { lo = blo; hi = bhi; }
+  else { lo = 1.0 - bhi; hi = 1.0 - blo; }
+  return 2 * norm * (sqrt(hi) - sqrt(lo)) * 1.0 * (gmax - gmin);
+}
+
+// The decision part of integ_relline_bin (src/Relprofile.cpp:650-726): the analytic edge terms of the bin
+// (returned in flu when EDGES) and the interval [rlo, rhi] left for quadrature.  Returns 0: nothing left,
+// 1: midpoint rule, 2: Romberg (int_romb, :628-647).
+template <bool EDGES>
+__device__ __forceinline__ int bin_split(const LnRad &lr, double rlo0, double rhi0, double &rlo, double &rhi, double &flu) {
+  flu = 0.0;
+  double gblo = (rlo0 / 1.0 - lr.gmin) * lr.del_g;
+  if (gblo < 0.0) gblo = 0.0; else if (gblo > 1.0) gblo = 1.0;
+  double gbhi = (rhi0 / 1.0 - lr.gmin) * lr.del_g;
+  if (gbhi < 0.0) gbhi = 0.0; else if (gbhi > 1.0) gbhi = 1.0;
+  if (gbhi == 0) return 0;
+  rlo = rlo0; rhi = rhi0;
+  if (gblo <= GFAC_H) {
+    double hhi = GFAC_H;
+    rlo = gstar2ener(GFAC_H, lr.gmin, lr.gmax);
+    if (gbhi <= GFAC_H) { hhi = gbhi; rlo = -1.0; }
+    if (EDGES) flu = flu + edge_term(gblo, hhi, lr.nlo, lr.gmin, lr.gmax);
+  }
+  if (gbhi >= (1.0 - GFAC_H)) {
+    double hlo = 1.0 - GFAC_H;
+    rhi = gstar2ener(1 - GFAC_H, lr.gmin, lr.gmax);
+    if (gblo >= (1.0 - GFAC_H)) { hlo = gblo; rhi = -1.0; }
+    if (EDGES) flu = flu + edge_term(hlo, gbhi, lr.nhi, lr.gmin, lr.gmax);
+  }
+  if ((rhi >= 0) && (rlo >= 0)) return (rlo >= 1.0 * 0.95) ? 2 : 1;
+  return 0;
+}
+
+// Romberg levels 5 and 6 of one bin (rare: a fraction of a per cent of the listed bins), by the thread that owns
+// the bin's tableau.  The new abscissae of a level are summed in ascending order like the reference's loop.
+__device__ __noinline__ void romberg_deep(double a, double pas, const RelbCtx &c, double (*tprev)[7], bool *done, double *res) {
+  const double pas6 = pas / 64.0;
+  double pasn = pas / 16.0;
+  double sum[2] = {tprev[0][0] / pasn, tprev[1][0] / pasn};   // level-4 trapezoid sums, from cur[0] = sum * pasn
+  double last[2] = {res[0], res[1]};
+  for (int n = 5; n <= 6; n++) {
+    if (done[0] && done[1]) break;
+    pasn = pasn * 0.5;
+    double o[2] = {0.0, 0.0};
+    const int step = (n == 5) ? 4 : 2, first = (n == 5) ? 2 : 1;   // level 5: p = 2 mod 4, level 6: odd p (of 64)
+    for (int p = first; p < 64; p += step) {
+      double w0, w1;
+      relb2(a + pas6 * p, c, w0, w1);
+      o[0] += w0;
+      o[1] += w1;
+    }
+    for (int k = 0; k < 2; k++) {
+      sum[k] += o[k];
+      if (done[k]) continue;
+      double cur[7];
+      cur[0] = sum[k] * pasn;
+      for (int ii = 1; ii <= n; ii++) cur[ii] = richardson(ii, cur[ii - 1], tprev[k][ii - 1]);
+      res[k] = cur[n];
+      if (!not_converged(cur[n], last[k])) done[k] = true;
+      last[k] = cur[n];
+      for (int ii = 0; ii <= n; ii++) tprev[k][ii] = cur[ii];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(LN_NT, 6) k_line(const VPar *__restrict__ vps, DevTables T, Scratch S, LineGrid G,
+                                                   int ne_stride, int nz_stride) {
+  __shared__ __align__(16) LnSmem sm;
+  const unsigned FULL = 0xffffffffu;
   const int v = blockIdx.y, z = blockIdx.x, t = threadIdx.x;
   if (S.status[v] != ST_OK) return;
   const VPar &vp = vps[v];
   if (z >= vp.nz) return;
+  const double *egrid = G.e;
+  const int n_ener = G.n_ener, grid_mode = G.mode;
   const double zred = vp.z, lineE = vp.lineE;
   const int limb = vp.limb;
   const double e_first = line_edge(egrid, 0, grid_mode, zred, lineE);
@@ -347,11 +236,10 @@ __global__ void __launch_bounds__(LN_NT, 3) k_line(const VPar *__restrict__ vps,
   // radii of this zone (izone[] is non-increasing along the descending-radius fine grid; k_syspar tabulated
   // the first index of every zone)
   const int ia = S.zfirst[(size_t) v * (NZMAX + 1) + z + 1], ib = S.zfirst[(size_t) v * (NZMAX + 1) + z];
-  double *flux = S.relflux + ((size_t) v * nz_stride + z) * ne_stride;
+  double *flux = S.relflux + ((size_t) v * nz_stride + z) * ne_stride;   // doubles as the zone accumulator
   const double *g_re = S.re + (size_t) v * NR;
   const double2 *g_trff = reinterpret_cast<const double2 *>(S.trff) + (size_t) v * NR * NG;
   const double2 *g_cosne = reinterpret_cast<const double2 *>(S.cosne) + (size_t) v * NR * NG;
-  for (int j = t; j < n_acc; j += LN_NT) acc[j] = 0.0;
   if (t == 0) { sm.cursor = ia; sm.resume = -1; sm.zjlo = n_ener; sm.zjhi = -1; }
   __syncthreads();
 
@@ -359,57 +247,90 @@ __global__ void __launch_bounds__(LN_NT, 3) k_line(const VPar *__restrict__ vps,
     const int cur = sm.cursor;
     if (cur >= ib) break;
     const int resume = sm.resume;
-    // ---- sub-batch set-up: one thread per radius
-    if (t < LN_MAXR) {
-      const int i = cur + t;
-      LnRad lr;
-      lr.gi = i;
-      lr.ielo = 0;
-      lr.iehi = -1;
+    const int zjlo_old = sm.zjlo, zjhi_old = sm.zjhi;
+    // ---- sub-batch set-up: radius r = lane, one warp per task (first bin | last bin | edge norm at g* = h | at 1-h)
+    {
+      const int r = t & 31, task = t >> 5;
+      const int i = cur + r;
+      LnRad &lr = sm.rad[r];
       if (i < ib) {
-        lr.gmin = S.gmin[(size_t) v * NR + i];
-        lr.gmax = S.gmax[(size_t) v * NR + i];
-        lr.del_g = 1. / (lr.gmax - lr.gmin);
-        lr.scale = lr.del_g * S.emis[(size_t) v * NR + i];
-        lr.weight = trapez_single(g_re, i, NR) / 2;
-        if ((lr.gmax > e_first) && (lr.gmin < e_last)) {  // src/Relprofile.cpp:863-878
-          double egmin = lr.gmin, egmax = lr.gmax;
-          if (egmin < e_first) egmin = e_first;
-          if (egmax > e_last) egmax = e_last;
-          lr.ielo = line_bsearch(egrid, n_ener + 1, egmin, grid_mode, zred, lineE);
-          lr.iehi = line_bsearch(egrid, n_ener + 1, egmax, grid_mode, zred, lineE);
-          if (t == 0 && resume >= 0) lr.ielo = resume;   // rest of a radius wider than the buffer
+        const double gmin = S.gmin[(size_t) v * NR + i], gmax = S.gmax[(size_t) v * NR + i];
+        const double del_g = 1. / (gmax - gmin);
+        const double scale = del_g * S.emis[(size_t) v * NR + i];
+        const bool on_grid = (gmax > e_first) && (gmin < e_last);  // src/Relprofile.cpp:863-878
+        if (task == 0) {
+          lr.gmin = gmin; lr.gmax = gmax; lr.del_g = del_g; lr.scale = scale;
+          lr.weight = trapez_single(g_re, i, NR) / 2;
+          lr.gi = i;
+          int ielo = 0;
+          if (on_grid) {
+            ielo = line_index(G, gmin < e_first ? e_first : gmin, zred, lineE);
+            if (r == 0 && resume >= 0) ielo = resume;   // rest of a radius wider than the buffer
+          }
+          lr.ielo = ielo;
+        } else if (task == 1) {
+          lr.iehi = on_grid ? line_index(G, gmax > e_last ? e_last : gmax, zred, lineE) : -1;
+        } else {
+          RelbCtx c;
+          c.gmin = gmin; c.gmax = gmax; c.del_g = del_g; c.scale = scale;
+          c.trff = g_trff + (size_t) i * NG; c.cosne = g_cosne + (size_t) i * NG; c.limb = limb;
+          double n0, n1;
+          relb2(gstar2ener(task == 2 ? GFAC_H : 1.0 - GFAC_H, gmin, gmax), c, n0, n1);
+          double norm = 0.0;
+          norm = norm + n0;
+          norm = norm + n1;
+          norm = norm * sqrt(GFAC_H);
+          if (task == 2) lr.nlo = norm; else lr.nhi = norm;
         }
+      } else if (task == 0) {
+        lr.gi = i; lr.ielo = 0;
+      } else if (task == 1) {
+        lr.iehi = -1;
       }
-      sm.rad[t] = lr;
     }
     __syncthreads();
-    if (t == 0) {
-      int off = 0, n = 0, jlo = n_ener, jhi = -1, next_resume = -1;
-      while (n < LN_MAXR && cur + n < ib) {
-        int w = sm.rad[n].iehi - sm.rad[n].ielo + 1;
-        if (off + w > LN_BUF) {
-          if (n > 0) break;
-          w = LN_BUF;                                   // a single radius wider than the buffer: take a piece
-          next_resume = sm.rad[n].ielo + w;
-          sm.rad[n].iehi = next_resume - 1;
-        }
-        sm.rad[n].off = off;
-        off += (w > 0 ? w : 0);
-        if (w > 0) { jlo = min(jlo, sm.rad[n].ielo); jhi = max(jhi, sm.rad[n].iehi); }
-        n++;
-        if (next_resume >= 0) break;
+    if (t < 32) {   // offsets of the radii that fit the buffer: warp scan over the bin counts
+      const int r = t;
+      const bool valid = cur + r < ib;
+      int ielo = sm.rad[r].ielo, iehi = sm.rad[r].iehi;
+      int w = valid ? max(iehi - ielo + 1, 0) : 0;
+      int next_resume = -1;
+      if (r == 0 && w > LN_BUF) {                       // a single radius wider than the buffer: take a piece
+        w = LN_BUF;
+        next_resume = ielo + w;
+        iehi = next_resume - 1;
+        sm.rad[0].iehi = iehi;
       }
-      sm.rad[n].off = off;
-      sm.nrad = n;
-      sm.ndef = 0;
-      sm.overflow = 0;
-      sm.jlo = jlo;
-      sm.jhi = jhi;
-      sm.zjlo = min(sm.zjlo, jlo);
-      sm.zjhi = max(sm.zjhi, jhi);
-      sm.resume = next_resume;
-      sm.cursor = (next_resume >= 0) ? cur + n - 1 : cur + n;
+      next_resume = __shfl_sync(FULL, next_resume, 0);
+      int cum = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(FULL, cum, o);
+        if (r >= o) cum += up;
+      }
+      const unsigned fits = __ballot_sync(FULL, valid && cum <= LN_BUF && (next_resume < 0 || r == 0));
+      const int n = __popc(fits);                       // `fits` is a prefix: cum is monotone, valid a prefix
+      const bool mine = r < n;
+      int jlo = (mine && w > 0) ? ielo : n_ener, jhi = (mine && w > 0) ? iehi : -1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        jlo = min(jlo, __shfl_xor_sync(FULL, jlo, o));
+        jhi = max(jhi, __shfl_xor_sync(FULL, jhi, o));
+      }
+      if (mine) sm.rad[r].off = cum - w;
+      if (r == n - 1) sm.rad[n].off = cum;
+      if (r == 0) {
+        sm.nrad = n;
+        sm.nrom = 0;
+        sm.ndef = 0;
+        sm.overflow = 0;
+        sm.jlo = jlo;
+        sm.jhi = jhi;
+        sm.zjlo = min(zjlo_old, jlo);
+        sm.zjhi = max(zjhi_old, jhi);
+        sm.resume = next_resume;
+        sm.cursor = (next_resume >= 0) ? cur + n - 1 : cur + n;
+      }
     }
     __syncthreads();
     const int nrad = sm.nrad;
@@ -417,59 +338,186 @@ __global__ void __launch_bounds__(LN_NT, 3) k_line(const VPar *__restrict__ vps,
     for (int r = t >> 5; r < nrad; r += LN_NT / 32)   // item -> radius map, one warp per radius
       for (int q = sm.rad[r].off + (t & 31); q < sm.rad[r + 1].off; q += 32) sm.item_rad[q] = (unsigned char) r;
     __syncthreads();
-    // ---- phase 1: one thread per item.  A bin whose Romberg integral needs more than two halvings goes on
-    // the work list; if the list is full the item is flagged (bit 7 of item_rad) and retried after phase 2
-    // has drained the list, so the result never depends on the order in which threads reach the list.
-    for (int round = 0;; round++) {
-      for (int item = t; item < nitems; item += LN_NT) {
-        const int ir = sm.item_rad[item];
-        if (round > 0 && !(ir & 0x80)) continue;
-        const LnRad &lr = sm.rad[ir & 0x7f];
+    // ---- pass A: one thread per item.  Edge terms and midpoint bins are finished here; the bins that take the
+    // Romberg path are gathered in a dense list (order irrelevant: every bin's value is computed on its own).
+    for (int base = 0; base < nitems; base += LN_NT) {
+      const int item = base + t;
+      int cls = 0;
+      if (item < nitems) {
+        const LnRad &lr = sm.rad[sm.item_rad[item]];
         const int j = lr.ielo + (item - lr.off);
-        RelbCtx c;
-        ln_ctx(lr, g_trff, g_cosne, limb, c);
         const double elo = line_edge(egrid, j, grid_mode, zred, lineE), ehi = line_edge(egrid, j + 1, grid_mode, zred, lineE);
-        bool deferred;
-        double ra, rb, fend[2];
-        const double val = integ_bin_phase1(c, elo, ehi, deferred, ra, rb, fend);
-        sm.item_rad[item] = (unsigned char) (ir & 0x7f);
-        if (deferred) {
-          const int d = atomicAdd(&sm.ndef, 1);
-          if (d < LN_MAXDEF) {
-            sm.def_item[d] = (unsigned short) item;
-            sm.def_a[d] = ra;
-            sm.def_b[d] = rb;
-            sm.def_f[d][0] = fend[0];
-            sm.def_f[d][1] = fend[1];
-          } else {
-            sm.item_rad[item] = (unsigned char) (ir | 0x80);
-            sm.overflow = 1;
+        double rlo, rhi, flu;
+        cls = bin_split<true>(lr, elo, ehi, rlo, rhi, flu);
+        if (cls == 1) {
+          RelbCtx c;
+          ln_ctx(lr, g_trff, g_cosne, limb, c);
+          double m0, m1;
+          relb2((rhi + rlo) / 2.0, c, m0, m1);
+          double f2 = 0.0;
+          f2 += m0 * (rhi - rlo);
+          f2 += m1 * (rhi - rlo);
+          flu = flu + f2;
+        }
+        sm.contrib[item] = flu;
+      }
+      const unsigned rom = __ballot_sync(FULL, cls == 2);
+      if (rom) {
+        int pos = 0;
+        if ((t & 31) == 0) pos = atomicAdd(&sm.nrom, __popc(rom));
+        pos = __shfl_sync(FULL, pos, 0);
+        if (cls == 2) sm.rlist[pos + __popc(rom & ((1u << (t & 31)) - 1))] = (unsigned short) item;
+      }
+    }
+    __syncthreads();
+    const int nrom = sm.nrom;
+    for (int round = 0;; round++) {
+      // ---- pass B: one thread per Romberg bin, two halvings (five abscissae) evaluated unconditionally.  A bin that
+      // has not converged by then (the horns of the profile) goes on the work list of phase 2; if the list is
+      // full the bin is flagged (bit 7 of item_rad) and retried after phase 2 has drained the list, so the
+      // result never depends on the order in which threads reach the list.
+      for (int base = 0; base < nrom; base += LN_NT) {
+        const int q = base + t;
+        bool defer = false;
+        int item = 0;
+        double ra = 0.0, rb = 0.0, fa0 = 0.0, fa1 = 0.0;
+        if (q < nrom) {
+          item = sm.rlist[q];
+          const int ir = sm.item_rad[item];
+          if (round == 0 || (ir & 0x80)) {
+            const LnRad &lr = sm.rad[ir & 0x7f];
+            const int j = lr.ielo + (item - lr.off);
+            const double elo = line_edge(egrid, j, grid_mode, zred, lineE), ehi = line_edge(egrid, j + 1, grid_mode, zred, lineE);
+            double flu;
+            bin_split<false>(lr, elo, ehi, ra, rb, flu);
+            RelbCtx c;
+            ln_ctx(lr, g_trff, g_cosne, limb, c);
+            // Romberg on [ra, rb] for both branches (src/Relprofile.cpp:524-579), levels 0..2
+            const double pas = rb - ra, pas1 = pas / 2.0, pas2 = pas1 / 2.0;
+            double fb0, fb1, m0, m1, q0, q1, u0, u1;
+            relb2(ra, c, fa0, fa1);
+            relb2(rb, c, fb0, fb1);
+            relb2(ra + pas1 * 1, c, m0, m1);
+            relb2(ra + pas2 * 1, c, q0, q1);
+            relb2(ra + pas2 * 3, c, u0, u1);
+            double rsum = 0.0;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+              const double fa = k ? fa1 : fa0, fb = k ? fb1 : fb0, m = k ? m1 : m0, qq = k ? q1 : q0, uu = k ? u1 : u0;
+              const double ta = (fa + fb) / 2.0;
+              const double t00 = ta * pas;
+              const double t01 = (ta + m) * pas1;
+              const double t10 = (4.0 * t01 - t00) / 3.0;
+              double r = t10;
+              if (not_converged(t10, t00)) {
+                const double t02 = (((ta + qq) + m) + uu) * pas2;
+                const double t11 = (4.0 * t02 - t01) / 3.0;
+                const double t20 = (16.0 * t11 - t10) / 15.0;
+                defer |= not_converged(t20, t10);
+                r = t20;
+              }
+              rsum += r;
+            }
+            sm.item_rad[item] = (unsigned char) (ir & 0x7f);
+            if (!defer) sm.contrib[item] = sm.contrib[item] + rsum;
           }
         }
-        sm.contrib[item] = val;
+        const unsigned dm = __ballot_sync(FULL, defer);
+        if (dm) {
+          int pos = 0;
+          if ((t & 31) == 0) pos = atomicAdd(&sm.ndef, __popc(dm));
+          pos = __shfl_sync(FULL, pos, 0);
+          if (defer) {
+            const int d = pos + __popc(dm & ((1u << (t & 31)) - 1));
+            if (d < LN_MAXDEF) {
+              sm.def_item[d] = (unsigned short) item;
+              sm.def_a[d] = ra;
+              sm.def_b[d] = rb;
+              sm.def_f[d][0] = fa0;
+              sm.def_f[d][1] = fa1;
+            } else {
+              sm.item_rad[item] |= 0x80;
+              sm.overflow = 1;
+            }
+          }
+        }
       }
       __syncthreads();
-      // ---- phase 2: one half warp per listed bin
+      // ---- phase 2: the listed bins at full Romberg depth.  One HALF WARP evaluates the 16 new abscissae of levels
+      // 1..4 of a bin in parallel (lane h takes point h+1 of 16; f(a) comes from pass B); one xor-butterfly
+      // gives the sums of the points that are new at each level.  The lane whose index equals the iteration
+      // keeps them, so after 16 iterations every lane owns one bin and all tableaus are built in parallel.
       {
         const int ndef = min(sm.ndef, LN_MAXDEF);
-        const int half = t >> 4, hl = t & 15;
-        const int nloop = (ndef + LN_NT / 16 - 1) / (LN_NT / 16);
-        for (int it = 0; it < nloop; it++) {
-          const int d = it * (LN_NT / 16) + half;
-          const bool active = d < ndef;
-          RelbCtx c;
-          double ra = 0.0, rb = 1.0;
-          int item = 0;
-          if (active) {
-            item = sm.def_item[d];
-            ln_ctx(sm.rad[sm.item_rad[item] & 0x7f], g_trff, g_cosne, limb, c);
-            ra = sm.def_a[d];
-            rb = sm.def_b[d];
-          } else {
-            ln_ctx(sm.rad[0], g_trff, g_cosne, limb, c);
+        constexpr int NH = LN_NT / 16;
+        const int half = t >> 4, h = t & 15, hb = t & 16;
+        for (int g0 = 0; g0 < ndef; g0 += 16 * NH) {
+          const int nit = min(16, (ndef - g0 + NH - 1) / NH);
+          double kn[2][4], kfb[2];
+#pragma unroll
+          for (int k = 0; k < 2; k++) { kfb[k] = 0.0; kn[k][0] = kn[k][1] = kn[k][2] = kn[k][3] = 0.0; }
+          for (int it = 0; it < nit; it++) {
+            const int d = g0 + it * NH + half;
+            double v0 = 0.0, v1 = 0.0;
+            if (d < ndef) {
+              RelbCtx c;
+              ln_ctx(sm.rad[sm.item_rad[sm.def_item[d]] & 0x7f], g_trff, g_cosne, limb, c);
+              const double a = sm.def_a[d], b = sm.def_b[d];
+              const double pas4 = (b - a) / 16.0;
+              relb2(h == 15 ? b : a + pas4 * (h + 1), c, v0, v1);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+              const double vv = k ? v1 : v0;
+              const double fb = __shfl_sync(FULL, vv, hb + 15);
+              // class sums over the interior points p = 1..15 (lane h = p - 1): p = 8; p = 4 mod 8; p = 2 mod 4; odd p
+              double x = (h == 15) ? 0.0 : vv;
+              const double n1 = __shfl_sync(FULL, x, hb + 7);
+              x += __shfl_xor_sync(FULL, x, 8);
+              const double n2 = __shfl_sync(FULL, x, hb + 3);
+              x += __shfl_xor_sync(FULL, x, 4);
+              const double n3 = __shfl_sync(FULL, x, hb + 1);
+              x += __shfl_xor_sync(FULL, x, 2);
+              const double n4 = __shfl_sync(FULL, x, hb + 0);
+              if (h == it) { kfb[k] = fb; kn[k][0] = n1; kn[k][1] = n2; kn[k][2] = n3; kn[k][3] = n4; }
+            }
           }
-          const double f2 = romberg2_half(ra, rb, c, active, sm.def_f[active ? d : 0]);
-          if (active && hl == 0) sm.contrib[item] = sm.contrib[item] + f2;
+          const int d = g0 + h * NH + half;   // the bin this lane kept
+          if (h < nit && d < ndef) {
+            const int item = sm.def_item[d];
+            const double a = sm.def_a[d], b = sm.def_b[d];
+            const double pas = b - a;
+            double tprev[2][7], res[2] = {0.0, 0.0};
+            bool done[2] = {false, false};
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+              const double ta = (sm.def_f[d][k] + kfb[k]) / 2.0;
+              tprev[k][0] = ta * pas;
+              double last = tprev[k][0], pasn = pas, sum = ta;
+#pragma unroll
+              for (int n = 1; n <= 4; n++) {
+                pasn = pasn * 0.5;
+                sum += kn[k][n - 1];
+                if (!done[k]) {
+                  double cur[5];
+                  cur[0] = sum * pasn;
+#pragma unroll
+                  for (int ii = 1; ii <= 4; ii++) if (ii <= n) cur[ii] = richardson(ii, cur[ii - 1], tprev[k][ii - 1]);
+                  res[k] = cur[n];
+                  if (!not_converged(cur[n], last)) done[k] = true;
+                  last = cur[n];
+#pragma unroll
+                  for (int ii = 0; ii <= 4; ii++) if (ii <= n) tprev[k][ii] = cur[ii];
+                }
+              }
+            }
+            if (!(done[0] && done[1])) {
+              RelbCtx c;
+              ln_ctx(sm.rad[sm.item_rad[item] & 0x7f], g_trff, g_cosne, limb, c);
+              romberg_deep(a, pas, c, tprev, done, res);
+            }
+            sm.contrib[item] = sm.contrib[item] + (res[0] + res[1]);
+          }
         }
       }
       const int again = sm.overflow;
@@ -478,14 +526,23 @@ __global__ void __launch_bounds__(LN_NT, 3) k_line(const VPar *__restrict__ vps,
       if (t == 0) { sm.ndef = 0; sm.overflow = 0; }
       __syncthreads();
     }
-    // ---- phase 3: ordered accumulation (ascending radius index = the reference's loop order)
-    for (int j = sm.jlo + t; j <= sm.jhi; j += LN_NT) {
-      double a = acc[j];
-      for (int r = 0; r < nrad; r++) {
-        const LnRad &lr = sm.rad[r];
-        if (j >= lr.ielo && j <= lr.iehi) a += sm.contrib[lr.off + (j - lr.ielo)] * lr.weight;
+    // ---- phase 3: ordered accumulation (ascending radius index = the reference's loop order) into the zone's
+    // row.  Bins joining the zone's range start from zero; bins the sub-batch does not touch stay as they are.
+    {
+      const int jlo = sm.jlo, jhi = sm.jhi;
+      const int nlo = min(zjlo_old, jlo), nhi = max(zjhi_old, jhi);
+      for (int j = nlo + t; j <= nhi; j += LN_NT) {
+        const bool was = (j >= zjlo_old && j <= zjhi_old), now = (j >= jlo && j <= jhi);
+        if (was && !now) continue;
+        double a = was ? flux[j] : 0.0;
+        if (now) {
+          for (int r = 0; r < nrad; r++) {
+            const LnRad &lr = sm.rad[r];
+            if (j >= lr.ielo && j <= lr.iehi) a += sm.contrib[lr.off + (j - lr.ielo)] * lr.weight;
+          }
+        }
+        flux[j] = a;
       }
-      acc[j] = a;
     }
     __syncthreads();
   }
@@ -497,25 +554,25 @@ __global__ void __launch_bounds__(LN_NT, 3) k_line(const VPar *__restrict__ vps,
   }
   for (int j = zjlo + t; j <= zjhi; j += LN_NT) {
     const double elo = line_edge(egrid, j, grid_mode, zred, lineE), ehi = line_edge(egrid, j + 1, grid_mode, zred, lineE);
-    flux[j] = acc[j] / (0.5 * (elo + ehi));
+    flux[j] = flux[j] / (0.5 * (elo + ehi));
   }
 }
 
 // ---------------------------------------------------------------------------------- launcher
 int line_kernel_init() {
-  cudaError_t e = cudaFuncSetAttribute(k_line, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (200 * 1024));
-  if (e != cudaSuccess) return 1;
-  e = cudaFuncSetAttribute(k_line, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
+  const cudaError_t e = cudaFuncSetAttribute(k_line, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
   return e == cudaSuccess ? 0 : 1;
 }
 
 void launch_line(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *egrid, int n_ener,
                  int grid_mode, int nz_max, cudaStream_t st) {
   dim3 grid(nz_max, (unsigned) n);
-  const int n_acc = ((n_ener + 31) / 32) * 32;
-  const size_t sm = sizeof(LnSmem) + (size_t) n_acc * sizeof(double);
-  k_line<<<grid, LN_NT, sm, st>>>(vps, T, S, egrid, n_ener, grid_mode, S.ne_line_cap, S.nz_cap, n_acc);
+  LineGrid G;
+  G.e = egrid; G.n_ener = n_ener; G.mode = grid_mode;
+  G.log_lo = std::log(CONV_EMIN);
+  G.inv_dlog = (double) NCONV / (std::log(CONV_EMAX) - std::log(CONV_EMIN));
+  k_line<<<grid, LN_NT, 0, st>>>(vps, T, S, G, S.ne_line_cap, S.nz_cap);
 }
-int line_max_bins() { return (int) ((200 * 1024 - sizeof(LnSmem)) / sizeof(double)); }
+int line_max_bins() { return 1 << 24; }   // the zone accumulator lives in the output row: no shared-memory limit
 
 }  // namespace rx

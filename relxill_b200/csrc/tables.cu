@@ -89,7 +89,7 @@ static void rebin_host(const double *ener, double *flu, int nbins, const double 
 
 void Tables::load_fixed() {
   if (have_fixed_) return;
-  log_grid(econv_, NCONV + 1, 0.00035, 2000.0);   // src/Xillspec.h:36-38
+  log_grid(econv_, NCONV + 1, CONV_EMIN, CONV_EMAX);   // src/Xillspec.h:36-38
   log_grid(ecoarse_, NCOARSE + 1, 0.1, 1000.0);   // src/Xillspec.h:28-32
   std::vector<double> cf(NCONV);
   std::vector<unsigned char> band(NCONV), m1(NCOARSE), m2(NCOARSE);
