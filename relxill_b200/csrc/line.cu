@@ -53,6 +53,17 @@ struct RelbCtx {
 #define GS_C ((1.0 - 2 * GFAC_H) / (NG - 1))
 #define GS_INVC ((NG - 1) / (1.0 - 2 * GFAC_H))
 
+// limb darkening / brightening factor of relb_func (src/Relprofile.cpp:508-518); out of line: the default
+// law is isotropic and the logarithm would otherwise be replicated into every copy of the integrand
+__device__ __noinline__ double2 relb2_limb(int ind, double inte, const double2 *cosne, int limb) {
+  const double inte1 = 1.0 - inte;
+  const double2 c0 = __ldg(cosne + ind), c1 = __ldg(cosne + ind + 1);
+  const double m0 = inte * c0.x + inte1 * c1.x, m1 = inte * c0.y + inte1 * c1.y;
+  if (limb == 1) return make_double2(1.0 + 2.06 * m0, 1.0 + 2.06 * m1);
+  if (limb == 2) return make_double2(log(1.0 + 1.0 / m0), log(1.0 + 1.0 / m1));
+  return make_double2(1.0, 1.0);
+}
+
 // both branches of relb_func (src/Relprofile.cpp:489-521) at energy eg
 __device__ __forceinline__ void relb2(double eg, const RelbCtx &c, double &v0, double &v1) {
   const double egstar = (eg - c.gmin) * c.del_g;
@@ -65,10 +76,9 @@ __device__ __forceinline__ void relb2(double eg, const RelbCtx &c, double &v0, d
   v0 = common * (inte * t0.x + inte1 * t1.x);   // (the reference's weights: inte on node ind, 1-inte on ind+1)
   v1 = common * (inte * t0.y + inte1 * t1.y);
   if (c.limb != 0) {
-    const double2 c0 = __ldg(c.cosne + ind), c1 = __ldg(c.cosne + ind + 1);
-    const double m0 = inte * c0.x + inte1 * c1.x, m1 = inte * c0.y + inte1 * c1.y;
-    if (c.limb == 1) { v0 *= (1.0 + 2.06 * m0); v1 *= (1.0 + 2.06 * m1); }
-    else if (c.limb == 2) { v0 *= log(1.0 + 1.0 / m0); v1 *= log(1.0 + 1.0 / m1); }
+    const double2 f = relb2_limb(ind, inte, c.cosne, c.limb);
+    v0 *= f.x;
+    v1 *= f.y;
   }
 }
 
@@ -108,9 +118,10 @@ struct LineGrid {
   int n_ener, mode;
   double log_lo, inv_dlog;   // mode 0: edge[k] ~ exp(log_lo + k / inv_dlog)
 };
+template <int GRID_MODE>
 __device__ int line_index(const LineGrid &G, double val, double z, double lineE) {
   const int last = G.n_ener - 1;   // n_edges - 2
-  if (G.mode == 0) {
+  if (GRID_MODE == 0) {
     int k = (int) floor((log(val) - G.log_lo) * G.inv_dlog);
     k = k < 0 ? 0 : (k > last ? last : k);
     while (k < last && __ldg(G.e + k + 1) <= val) k++;
@@ -171,17 +182,20 @@ __device__ __forceinline__ int bin_split(const LnRad &lr, double rlo0, double rh
   if (gbhi < 0.0) gbhi = 0.0; else if (gbhi > 1.0) gbhi = 1.0;
   if (gbhi == 0) return 0;
   rlo = rlo0; rhi = rhi0;
-  if (gblo <= GFAC_H) {
-    double hhi = GFAC_H;
+  const bool at_lo = gblo <= GFAC_H, at_hi = gbhi >= (1.0 - GFAC_H);
+  double lo_hhi = GFAC_H, hi_hlo = 1.0 - GFAC_H;
+  if (at_lo) {
     rlo = gstar2ener(GFAC_H, lr.gmin, lr.gmax);
-    if (gbhi <= GFAC_H) { hhi = gbhi; rlo = -1.0; }
-    if (EDGES) flu = flu + edge_term(gblo, hhi, lr.nlo, lr.gmin, lr.gmax);
+    if (gbhi <= GFAC_H) { lo_hhi = gbhi; rlo = -1.0; }
   }
-  if (gbhi >= (1.0 - GFAC_H)) {
-    double hlo = 1.0 - GFAC_H;
+  if (at_hi) {
     rhi = gstar2ener(1 - GFAC_H, lr.gmin, lr.gmax);
-    if (gblo >= (1.0 - GFAC_H)) { hlo = gblo; rhi = -1.0; }
-    if (EDGES) flu = flu + edge_term(hlo, gbhi, lr.nhi, lr.gmin, lr.gmax);
+    if (gblo >= (1.0 - GFAC_H)) { hi_hlo = gblo; rhi = -1.0; }
+  }
+  if (EDGES && (at_lo || at_hi)) {   // lower-edge term first, like the reference; one call unless the bin spans both edges
+    const double eb_lo = at_lo ? gblo : hi_hlo, eb_hi = at_lo ? lo_hhi : gbhi, e_norm = at_lo ? lr.nlo : lr.nhi;
+    flu = flu + edge_term(eb_lo, eb_hi, e_norm, lr.gmin, lr.gmax);
+    if (at_lo && at_hi) flu = flu + edge_term(hi_hlo, gbhi, lr.nhi, lr.gmin, lr.gmax);
   }
   if ((rhi >= 0) && (rlo >= 0)) return (rlo >= 1.0 * 0.95) ? 2 : 1;
   return 0;
@@ -189,7 +203,17 @@ __device__ __forceinline__ int bin_split(const LnRad &lr, double rlo0, double rh
 
 // Romberg levels 5 and 6 of one bin (rare: a fraction of a per cent of the listed bins), by the thread that owns
 // the bin's tableau.  The new abscissae of a level are summed in ascending order like the reference's loop.
-__device__ __noinline__ void romberg_deep(double a, double pas, const RelbCtx &c, double (*tprev)[7], bool *done, double *res) {
+// Everything is passed by value so that the caller's tableau stays in registers.
+struct DeepIn {
+  double tp[2][5];   // tableau rows after level 4
+  double res[2];
+  int done[2];
+};
+__device__ __noinline__ double romberg_deep(double a, double pas, RelbCtx c, DeepIn in) {
+  double tprev[2][7], res[2] = {in.res[0], in.res[1]};
+  bool done[2] = {in.done[0] != 0, in.done[1] != 0};
+  for (int k = 0; k < 2; k++)
+    for (int ii = 0; ii < 5; ii++) tprev[k][ii] = in.tp[k][ii];
   const double pas6 = pas / 64.0;
   double pasn = pas / 16.0;
   double sum[2] = {tprev[0][0] / pasn, tprev[1][0] / pasn};   // level-4 trapezoid sums, from cur[0] = sum * pasn
@@ -217,8 +241,10 @@ __device__ __noinline__ void romberg_deep(double a, double pas, const RelbCtx &c
       for (int ii = 0; ii <= n; ii++) tprev[k][ii] = cur[ii];
     }
   }
+  return res[0] + res[1];
 }
 
+template <int GRID_MODE>
 __global__ void __launch_bounds__(LN_NT, 6) k_line(const VPar *__restrict__ vps, DevTables T, Scratch S, LineGrid G,
                                                    int ne_stride, int nz_stride) {
   __shared__ __align__(16) LnSmem sm;
@@ -228,7 +254,8 @@ __global__ void __launch_bounds__(LN_NT, 6) k_line(const VPar *__restrict__ vps,
   const VPar &vp = vps[v];
   if (z >= vp.nz) return;
   const double *egrid = G.e;
-  const int n_ener = G.n_ener, grid_mode = G.mode;
+  const int n_ener = G.n_ener;
+  constexpr int grid_mode = GRID_MODE;
   const double zred = vp.z, lineE = vp.lineE;
   const int limb = vp.limb;
   const double e_first = line_edge(egrid, 0, grid_mode, zred, lineE);
@@ -264,12 +291,12 @@ __global__ void __launch_bounds__(LN_NT, 6) k_line(const VPar *__restrict__ vps,
           lr.gi = i;
           int ielo = 0;
           if (on_grid) {
-            ielo = line_index(G, gmin < e_first ? e_first : gmin, zred, lineE);
+            ielo = line_index<GRID_MODE>(G, gmin < e_first ? e_first : gmin, zred, lineE);
             if (r == 0 && resume >= 0) ielo = resume;   // rest of a radius wider than the buffer
           }
           lr.ielo = ielo;
         } else if (task == 1) {
-          lr.iehi = on_grid ? line_index(G, gmax > e_last ? e_last : gmax, zred, lineE) : -1;
+          lr.iehi = on_grid ? line_index<GRID_MODE>(G, gmax > e_last ? e_last : gmax, zred, lineE) : -1;
         } else {
           RelbCtx c;
           c.gmin = gmin; c.gmax = gmax; c.del_g = del_g; c.scale = scale;
@@ -394,25 +421,33 @@ __global__ void __launch_bounds__(LN_NT, 6) k_line(const VPar *__restrict__ vps,
             ln_ctx(lr, g_trff, g_cosne, limb, c);
             // Romberg on [ra, rb] for both branches (src/Relprofile.cpp:524-579), levels 0..2
             const double pas = rb - ra, pas1 = pas / 2.0, pas2 = pas1 / 2.0;
-            double fb0, fb1, m0, m1, q0, q1, u0, u1;
-            relb2(ra, c, fa0, fa1);
-            relb2(rb, c, fb0, fb1);
-            relb2(ra + pas1 * 1, c, m0, m1);
-            relb2(ra + pas2 * 1, c, q0, q1);
-            relb2(ra + pas2 * 3, c, u0, u1);
+            // abscissae in the order a, b, a+pas/4, a+pas/2, a+3pas/4: the level-2 trapezoid sum is built as
+            // ((ta + f(q1)) + f(mid)) + f(q3), the reference's ascending order.  Rolled: one copy of the integrand.
+            double ta[2] = {0.0, 0.0}, fm[2] = {0.0, 0.0}, x2[2] = {0.0, 0.0};
+#pragma unroll 1
+            for (int pt = 0; pt < 5; pt++) {
+              const double eg = (pt == 0) ? ra : (pt == 1) ? rb : (pt == 2) ? ra + pas2 * 1 : (pt == 3) ? ra + pas1 * 1 : ra + pas2 * 3;
+              double w0, w1;
+              relb2(eg, c, w0, w1);
+              if (pt == 0) { fa0 = w0; fa1 = w1; }
+              else if (pt == 1) { ta[0] = (fa0 + w0) / 2.0; ta[1] = (fa1 + w1) / 2.0; x2[0] = ta[0]; x2[1] = ta[1]; }
+              else {
+                if (pt == 3) { fm[0] = w0; fm[1] = w1; }
+                x2[0] += w0;
+                x2[1] += w1;
+              }
+            }
             double rsum = 0.0;
 #pragma unroll
             for (int k = 0; k < 2; k++) {
-              const double fa = k ? fa1 : fa0, fb = k ? fb1 : fb0, m = k ? m1 : m0, qq = k ? q1 : q0, uu = k ? u1 : u0;
-              const double ta = (fa + fb) / 2.0;
-              const double t00 = ta * pas;
-              const double t01 = (ta + m) * pas1;
-              const double t10 = (4.0 * t01 - t00) / 3.0;
+              const double t00 = ta[k] * pas;
+              const double t01 = (ta[k] + fm[k]) * pas1;
+              const double t10 = richardson(1, t01, t00);
               double r = t10;
               if (not_converged(t10, t00)) {
-                const double t02 = (((ta + qq) + m) + uu) * pas2;
-                const double t11 = (4.0 * t02 - t01) / 3.0;
-                const double t20 = (16.0 * t11 - t10) / 15.0;
+                const double t02 = x2[k] * pas2;
+                const double t11 = richardson(1, t02, t01);
+                const double t20 = richardson(2, t11, t10);
                 defer |= not_converged(t20, t10);
                 r = t20;
               }
@@ -487,7 +522,7 @@ __global__ void __launch_bounds__(LN_NT, 6) k_line(const VPar *__restrict__ vps,
             const int item = sm.def_item[d];
             const double a = sm.def_a[d], b = sm.def_b[d];
             const double pas = b - a;
-            double tprev[2][7], res[2] = {0.0, 0.0};
+            double tprev[2][5], res[2] = {0.0, 0.0};
             bool done[2] = {false, false};
 #pragma unroll
             for (int k = 0; k < 2; k++) {
@@ -511,12 +546,21 @@ __global__ void __launch_bounds__(LN_NT, 6) k_line(const VPar *__restrict__ vps,
                 }
               }
             }
+            double rtot = res[0] + res[1];
             if (!(done[0] && done[1])) {
               RelbCtx c;
               ln_ctx(sm.rad[sm.item_rad[item] & 0x7f], g_trff, g_cosne, limb, c);
-              romberg_deep(a, pas, c, tprev, done, res);
+              DeepIn in;
+#pragma unroll
+              for (int k = 0; k < 2; k++) {
+#pragma unroll
+                for (int ii = 0; ii < 5; ii++) in.tp[k][ii] = tprev[k][ii];
+                in.res[k] = res[k];
+                in.done[k] = done[k] ? 1 : 0;
+              }
+              rtot = romberg_deep(a, pas, c, in);
             }
-            sm.contrib[item] = sm.contrib[item] + (res[0] + res[1]);
+            sm.contrib[item] = sm.contrib[item] + rtot;
           }
         }
       }
@@ -560,7 +604,9 @@ __global__ void __launch_bounds__(LN_NT, 6) k_line(const VPar *__restrict__ vps,
 
 // ---------------------------------------------------------------------------------- launcher
 int line_kernel_init() {
-  const cudaError_t e = cudaFuncSetAttribute(k_line, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
+  cudaError_t e = cudaFuncSetAttribute(k_line<0>, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return 1;
+  e = cudaFuncSetAttribute(k_line<1>, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
   return e == cudaSuccess ? 0 : 1;
 }
 
@@ -571,7 +617,8 @@ void launch_line(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
   G.e = egrid; G.n_ener = n_ener; G.mode = grid_mode;
   G.log_lo = std::log(CONV_EMIN);
   G.inv_dlog = (double) NCONV / (std::log(CONV_EMAX) - std::log(CONV_EMIN));
-  k_line<<<grid, LN_NT, 0, st>>>(vps, T, S, G, S.ne_line_cap, S.nz_cap);
+  if (grid_mode == 0) k_line<0><<<grid, LN_NT, 0, st>>>(vps, T, S, G, S.ne_line_cap, S.nz_cap);
+  else k_line<1><<<grid, LN_NT, 0, st>>>(vps, T, S, G, S.ne_line_cap, S.nz_cap);
 }
 int line_max_bins() { return 1 << 24; }   // the zone accumulator lives in the output row: no shared-memory limit
 
