@@ -383,8 +383,6 @@ struct ZoneSmem {
   double nfac[NZMAX + 1], s2[NZMAX + 1];
   int b[NZMAX];
   int ints[4];
-  int skey[2048];      // (node << 6 | zone) of every (zone, corner) pair, sorted by node for k_xill
-  double sw[2048];
 };
 
 // cutoff power law on the coarse grid (src/Xillspec.cpp:215-233) reduced to the two band sums; warp-cooperative
@@ -542,7 +540,10 @@ __global__ void __launch_bounds__(128) k_zone(const VPar *__restrict__ vps, DevT
   // Factorised corner list for k_xill.  The multilinear weight of a corner is a product over the table
   // axes; Gamma and A_Fe are the same for all zones of a vector, so the table is first contracted over
   // those two axes (4 nodes, weights ga_w) and the zones only blend the remaining "rest" corners
-  // (logXi, Ecut|kTe[, Dens]: 4 or 8 per zone).  Entry key = (rest node offset << 6 | zone).
+  // (logXi, Ecut|kTe[, Dens]: 4 or 8 per zone).  A corner is filed under the slot given by the parities of
+  // its node indices (the two nodes of a bracket have different parity, so the corners of a zone occupy
+  // distinct slots, and a corner shared by neighbouring zones keeps its slot): xkey[zone][slot] = rest node
+  // offset, xwsort[zone][slot] = weight.
   const int n_rest = nc_all / 4;
   if (t < nz) {
     const XillDev &X = T.xill[vp.prim_type == PRIM_NTHCOMP ? 1 : 0];
@@ -584,8 +585,10 @@ __global__ void __launch_bounds__(128) k_zone(const VPar *__restrict__ vps, DevT
         off += (long) (ind[ax_r[q]] + bit) * stride[ax_r[q]];
         w *= bit ? fac[ax_r[q]] : (1.0 - fac[ax_r[q]]);
       }
-      sm.skey[t * n_rest + c] = ((int) off << 6) | t;
-      sm.sw[t * n_rest + c] = w;
+      int slot = 0;
+      for (int q = 0; q < nr; q++) slot |= ((ind[ax_r[q]] + ((c >> q) & 1)) & 1) << q;
+      S.xkey[((size_t) v * NZMAX + t) * 8 + slot] = (int) off;
+      S.xwsort[((size_t) v * NZMAX + t) * 8 + slot] = w;
     }
     if (t == 0) {
       int *ga_off = S.xga_off + (size_t) v * 4;
@@ -598,34 +601,7 @@ __global__ void __launch_bounds__(128) k_zone(const VPar *__restrict__ vps, DevT
     }
   }
   __syncthreads();
-  {  // sort the (rest node, zone, weight) triples by node: bitonic sort in shared memory
-    const int n_ent = nz * n_rest;
-    int npow = 1;
-    while (npow < n_ent) npow <<= 1;
-    for (int i = n_ent + t; i < npow; i += 128) { sm.skey[i] = 0x7fffffff; sm.sw[i] = 0.0; }
-    __syncthreads();
-    for (int k = 2; k <= npow; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = t; i < npow; i += 128) {
-          const int ixj = i ^ j;
-          if (ixj > i) {
-            const bool up = ((i & k) == 0);
-            const int a = sm.skey[i], b = sm.skey[ixj];
-            if ((a > b) == up) {
-              sm.skey[i] = b; sm.skey[ixj] = a;
-              const double wa = sm.sw[i]; sm.sw[i] = sm.sw[ixj]; sm.sw[ixj] = wa;
-            }
-          }
-        }
-        __syncthreads();
-      }
-    }
-    int *gk = S.xkey + (size_t) v * NZMAX * 32;
-    double *gw = S.xwsort + (size_t) v * NZMAX * 32;
-    for (int i = t; i < n_ent; i += 128) { gk[i] = sm.skey[i]; gw[i] = sm.sw[i]; }
-    if (t == 0) S.xn[v] = n_ent;
-  }
-  __syncthreads();
+  if (t == 0) S.xn[v] = n_rest;
   // primary-spectrum normalisations: one warp per (zone | source); cutoff power law only here,
   // the nthcomp variant lives in k_zone_nthcomp
   if (vp.prim_type == PRIM_ECUT) {

@@ -328,7 +328,7 @@ std::string Tables::load_xill(int which) {
   if (xh.pindex[xh.npar - 1] != 7 || S->nrows != nrows) { mf_close(f); return "xillver table: Incl must be the last axis"; }
   // the kernels assume the reference's standard axis order: [Gamma,] A_Fe, logXi, Ecut|kTe, [Dens,] Incl
   xh.n_incl = xh.nvals[xh.npar - 1];
-  if (xh.n_incl > MAX_INCL) { mf_close(f); return "xillver table: too many inclinations"; }
+  if (xh.n_incl > 10) { mf_close(f); return "xillver table: more than 10 inclinations are not supported"; }
   xh.n_ener = (int) E->nrows;
   xh.stride = ((xh.n_ener + 31) / 32) * 32;
   xh.nnodes = nrows / xh.n_incl;
