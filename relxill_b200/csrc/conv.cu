@@ -104,25 +104,26 @@ __device__ __forceinline__ void fft8(double (&r)[8], double (&i)[8]) {
   r[7] = br[6] - br[7]; i[7] = bi[6] - bi[7];
 }
 
-// in-place forward FFT of the padded array; tw[m] = exp(-2 pi i m / 4096); all CONV_NT threads call.
-// `yscale` multiplies the imaginary input (applied while the first pass loads it).
-__device__ void fft4096(double2 *z, const double2 *__restrict__ tw, double yscale) {
+// Forward FFT of 4096 points, tw[m] = exp(-2 pi i m / 4096); all CONV_NT threads call.  The input arrives in
+// registers: thread j holds the points j + 512 q, q = 0..7 (exactly what the first pass needs), so the packing
+// code hands its values over without a round trip through shared memory.  Result in the padded array z.
+__device__ void fft4096(double (&r)[8], double (&im)[8], double2 *z, const double2 *__restrict__ tw) {
   const int j = threadIdx.x;
+  fft8(r, im);
+#pragma unroll
+  for (int q = 0; q < 8; q++) z[cv_pad((j << 3) + q)] = make_double2(r[q], im[q]);
+  __syncthreads();
 #pragma unroll 1
-  for (int pass = 0; pass < 4; pass++) {
-    const int ns = 1 << (3 * pass);          // 1, 8, 64, 512
+  for (int pass = 1; pass < 4; pass++) {
+    const int ns = 1 << (3 * pass);          // 8, 64, 512
     const int k = j & (ns - 1);
-    double r[8], im[8];
 #pragma unroll
     for (int q = 0; q < 8; q++) {
       const double2 c = z[cv_pad(j + q * (NCONV / 8))];
       r[q] = c.x;
       im[q] = c.y;
     }
-    if (pass == 0) {
-#pragma unroll
-      for (int q = 0; q < 8; q++) im[q] *= yscale;
-    } else {
+    {
       // twiddles w^q, w = tw[k * 512 / ns]: three table reads (w, w^2, w^4), the rest by products
       const int mb = k * ((NCONV / 8) >> (3 * pass));
       const double2 w1 = __ldg(tw + mb), w2 = __ldg(tw + 2 * mb), w4 = __ldg(tw + 4 * mb);
@@ -180,29 +181,49 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
     // ---- pack the zone's spectrum rebinned onto the convolution grid (real part) and its line profile, rotated so
     //      that 1 keV sits at index 0 (imaginary part), both times E/dE; band and total sums on the way
     double sums[4] = {0.0, 0.0, 0.0, 0.0};   // all rel, |x|, band x, band rel
-#pragma unroll 1
-    for (int i = t; i < NCONV; i += CONV_NT) {
-      double f = 0.0;
-      if (A.mode == 0) {
+    double re[8], im[8];                      // bins t + 512 u: the first FFT pass takes them from here
+    if (A.mode == 0) {
+      // all loads of the 8 bins are independent: bins outside the table grid carry zero weights, the common
+      // spans (1-3 source bins) are branch-free
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int i = t + u * CONV_NT;
         const int2 ii = __ldg(rb_ii + i);
-        if (ii.x >= 0) {
-          const double2 dd = __ldg(rb_dd + i);
-          if (ii.y == ii.x) f = dd.x * xz[ii.x];
-          else {
-            f += xz[ii.x] * dd.x + xz[ii.y] * dd.y;
-            for (int jj = ii.x + 1; jj <= ii.y - 1; jj++) f += xz[jj];
-          }
+        const double2 dd = __ldg(rb_dd + i);
+        const int j0 = ii.x >= 0 ? ii.x : 0, j1 = ii.x >= 0 ? ii.y : 0;
+        double f = 0.0;
+        f += xz[j0] * dd.x + xz[j1] * dd.y;
+        if (j1 - j0 >= 2) {
+          f += xz[j0 + 1];
+          for (int jj = j0 + 2; jj <= j1 - 1; jj++) f += xz[jj];
         }
-      } else {
-        f = rebin_bin(T.econv[i], T.econv[i + 1], A.user_e, o, A.n_flux);
+        const int ri = (i + i1) & (NCONV - 1);
+        const double r = (ri >= rjlo && ri <= rjhi) ? rel[ri] : 0.0;
+        re[u] = f * T.conv_cf[i];
+        im[u] = r * T.conv_cf[ri];
+        sums[0] += r;
+        sums[1] += fabs(f);
+        if (i >= b0 && i <= b1) sums[2] += f;
+        if (ri >= b0 && ri <= b1) sums[3] += r;
       }
-      const int ri = (i + i1) & (NCONV - 1);
-      const double r = (ri >= rjlo && ri <= rjhi) ? rel[ri] : 0.0;
-      sm.z[cv_pad(i)] = make_double2(f * T.conv_cf[i], r * T.conv_cf[ri]);
-      sums[0] += r;
-      sums[1] += fabs(f);
-      if (i >= b0 && i <= b1) sums[2] += f;
-      if (ri >= b0 && ri <= b1) sums[3] += r;
+    } else {
+#pragma unroll 1
+      for (int i = t; i < NCONV; i += CONV_NT) {
+        const double f = rebin_bin(T.econv[i], T.econv[i + 1], A.user_e, o, A.n_flux);
+        const int ri = (i + i1) & (NCONV - 1);
+        const double r = (ri >= rjlo && ri <= rjhi) ? rel[ri] : 0.0;
+        sm.z[cv_pad(i)] = make_double2(f * T.conv_cf[i], r * T.conv_cf[ri]);
+        sums[0] += r;
+        sums[1] += fabs(f);
+        if (i >= b0 && i <= b1) sums[2] += f;
+        if (ri >= b0 && ri <= b1) sums[3] += r;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {   // the thread's own values
+        const double2 c = sm.z[cv_pad(t + u * CONV_NT)];
+        re[u] = c.x;
+        im[u] = c.y;
+      }
     }
     block_sum_n<4>(sums, sm);
     const double srel_all = sums[0];
@@ -212,7 +233,12 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
     // both real inputs ride one complex transform: bring them to the same scale (any factor cancels in the norm)
     const double bal = (sums[1] > 0.0 && srel_n > 0.0) ? sums[1] / srel_n : 1.0;
     const double s_xill = sums[2], s_rel = vp.renorm ? sums[3] * rscale : sums[3];
-    fft4096(sm.z, tw, rscale * bal);
+    {
+      const double yscale = rscale * bal;
+#pragma unroll
+      for (int u = 0; u < 8; u++) im[u] *= yscale;
+    }
+    fft4096(re, im, sm.z, tw);
     // ---- split, product spectrum, band sum of the convolved zone in the frequency domain
     double dot[1] = {0.0};
     double pr_[5], pi_[5];
@@ -240,13 +266,18 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
     __syncthreads();
   }
   // ---- one inverse transform for the whole vector: out = Re(FFT(conj(A)))
-  for (int k = t; k <= NCONV / 2; k += CONV_NT) {
-    const double ar = sm.ar[k], ai = (k == 0 || k == NCONV / 2) ? 0.0 : sm.ai[k];
-    sm.z[cv_pad(k)] = make_double2(ar, -ai);
-    if (k > 0 && k < NCONV / 2) sm.z[cv_pad(NCONV - k)] = make_double2(ar, ai);
+  {
+    double re[8], im[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {   // Hermitian extension of the accumulated half spectrum, conjugated
+      const int i = t + u * CONV_NT;
+      const int k = (i <= NCONV / 2) ? i : NCONV - i;
+      const double ai = (k == 0 || k == NCONV / 2) ? 0.0 : sm.ai[k];
+      re[u] = sm.ar[k];
+      im[u] = (i <= NCONV / 2) ? -ai : ai;
+    }
+    fft4096(re, im, sm.z, tw);
   }
-  __syncthreads();
-  fft4096(sm.z, tw, 1.0);
   double *acc = sm.ar;   // ar and ai are contiguous: 4098 doubles
   for (int i = t; i < NCONV; i += CONV_NT) acc[i] = sm.z[cv_pad(i)].x / T.conv_cf[i];
   __syncthreads();
