@@ -58,6 +58,8 @@ struct Engine {
   double *d_io = nullptr;     // staging for host-buffer calls
   size_t d_io_cap = 0;
   long max_chunk = 4096;
+  long pipe_piece = 2072;     // vectors per pipelined piece of a host-buffer call (RELXILL_B200_PIPE)
+  cudaStream_t stream_c = nullptr, stream_d = nullptr;   // compute / copy streams of host-buffer calls
   bool profiling = false;
   // device buffers recycled between batches (cudaMalloc/cudaFree synchronise and cost milliseconds)
   std::vector<std::pair<size_t, void *>> pool;
@@ -159,6 +161,9 @@ int engine_init(Engine &E, const char *dir, int device) {
   if (const char *env = getenv("RELLINE_PHYSICAL_NORM")) E.cfg.env_phys_norm = ((int) strtod(env, nullptr) == 1) ? 1 : 0;
   if (const char *env = getenv("RELXILL_CONSTANT_DENSITY")) E.cfg.env_const_density = ((int) strtod(env, nullptr) == 1) ? 1 : 0;
   if (const char *env = getenv("RELXILL_B200_CHUNK")) E.max_chunk = std::max(1L, atol(env));
+  if (const char *env = getenv("RELXILL_B200_PIPE")) E.pipe_piece = std::max(1L, atol(env));
+  if (!E.stream_c) cudaStreamCreateWithFlags(&E.stream_c, cudaStreamNonBlocking);
+  if (!E.stream_d) cudaStreamCreateWithFlags(&E.stream_d, cudaStreamNonBlocking);
   if (kernels_init() != 0) {
     set_err("kernel attribute setup failed (is this an sm_100a device?)");
     return -1;
@@ -221,7 +226,15 @@ struct Timer {
   }
 };
 
-int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st) {
+// Host-buffer calls overlap the device->host copy of the spectra with the kernels of the next piece of the
+// batch: pieces of `pipe_piece` vectors (a whole number of waves of the one-CTA-per-vector kernels), the odd
+// remainder first, so that only the copy of the last piece is exposed.
+struct PipeOut {
+  double *h_flux;
+  cudaStream_t copy_stream;
+};
+
+int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st, const PipeOut *pipe = nullptr) {
   const ModelDef &m = *b->m;
   const DevTables &T = E.tables->dev();
   const int which = (m.prim == PRIM_NTHCOMP) ? 1 : 0;
@@ -239,8 +252,32 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st)
   for (int k = 0; k < KF_COUNT; k++) { b->kt_ms[k] = 0; b->kt_n[k] = 0; }
   Timer tm(E, b, st);
   const std::vector<double> &econv = E.tables->econv();
-  for (long c0 = 0; c0 < b->n; c0 += S.cap) {
-    const long nc = std::min(S.cap, b->n - c0);
+  std::vector<long> piece_n;
+  {
+    long piece = S.cap;
+    if (pipe && b->n >= 2 * E.pipe_piece) piece = std::min(S.cap, E.pipe_piece);
+    long first = b->n % piece;
+    if (first == 0) first = std::min(piece, b->n);
+    for (long c0 = 0, nc = first; c0 < b->n; c0 += nc, nc = std::min(piece, b->n - c0)) piece_n.push_back(nc);
+  }
+  std::vector<cudaEvent_t> ev(pipe ? piece_n.size() : 0);
+  for (auto &e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  auto copy_piece = [&](size_t k, long c0, long nc) {
+    CK(cudaStreamWaitEvent(pipe->copy_stream, ev[k], 0));
+    CK(cudaMemcpyAsync(pipe->h_flux + (size_t) c0 * b->n_flux, d_flux + (size_t) c0 * b->n_flux,
+                       (size_t) nc * b->n_flux * sizeof(double), cudaMemcpyDeviceToHost, pipe->copy_stream));
+    return 0;
+  };
+  long c0 = 0, prev_c0 = 0;
+  for (size_t ip = 0; ip < piece_n.size(); c0 += piece_n[ip], ip++) {
+    const long nc = piece_n[ip];
+    if (pipe && ip > 0) {   // the previous piece's kernels are enqueued behind it: its copy overlaps this piece
+      if (copy_piece(ip - 1, prev_c0, piece_n[ip - 1])) return -2;
+    }
+    struct AtEnd {   // record the piece's completion event however the body is left
+      std::vector<cudaEvent_t> &ev; size_t ip; cudaStream_t st; bool on; long &prev, c0;
+      ~AtEnd() { if (on) cudaEventRecord(ev[ip], st); prev = c0; }
+    } at_end{ev, ip, st, pipe != nullptr, prev_c0, c0};
     const VPar *vps = b->d_vps + c0;
     double *out = d_flux + (size_t) c0 * b->n_flux;
     if (xillver) {
@@ -282,6 +319,12 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st)
     CK(cudaMemcpyAsync(b->status.data() + c0, S.status, nc * sizeof(int), cudaMemcpyDeviceToHost, st));
     b->last_chunk0 = c0;
     b->last_chunk_n = nc;
+  }
+  if (pipe) {
+    if (copy_piece(piece_n.size() - 1, prev_c0, piece_n.back())) return -2;
+    CK(cudaStreamSynchronize(pipe->copy_stream));
+    CK(cudaStreamSynchronize(st));
+    for (auto &e : ev) cudaEventDestroy(e);
   }
   CK(cudaGetLastError());
   return 0;
@@ -488,18 +531,19 @@ int relxill_batch_eval(const char *model, const double *energy, int n_flux, cons
     cudaMemcpy(E.d_io, flux, need * sizeof(double), cudaMemcpyHostToDevice);
   }
   const auto t2 = now();
-  int rc = relxill_b200_run(b, E.d_io, nullptr);
-  if (dbg) cudaDeviceSynchronize();
-  const auto t3 = now();
-  if (rc == 0) {
-    cudaError_t e = cudaMemcpy(flux, E.d_io, need * sizeof(double), cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) { set_err(std::string("D2H copy: ") + cudaGetErrorString(e)); rc = -2; }
+  int rc;
+  {
+    std::lock_guard<std::mutex> lk(E.mu);
+    PipeOut pipe{flux, E.stream_d};
+    rc = run_batch(E, b, E.d_io, E.stream_c, &pipe);   // kernels + pipelined D2H; returns with both streams drained
+    if (rc != 0) { cudaStreamSynchronize(E.stream_c); cudaStreamSynchronize(E.stream_d); }
   }
+  const auto t3 = now();
   const auto t4 = now();
   if (status) for (long i = 0; i < n_vec; i++) status[i] = b->status[i];
   relxill_b200_free_batch(b);
   if (dbg)
-    fprintf(stderr, "relxill_batch_eval timing: prepare %.2f ms, staging %.2f ms, run %.2f ms, D2H %.2f ms, free %.2f ms\n",
+    fprintf(stderr, "relxill_batch_eval timing: prepare %.2f ms, staging %.2f ms, run + D2H (pipelined) %.2f ms (+%.2f), free %.2f ms\n",
             ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, now()));
   return rc;
 }
