@@ -101,6 +101,10 @@ long relxill_b200_last_launches(relxill_b200_batch *b);
 void relxill_b200_set_profiling(int on);
 int relxill_b200_kernel_times(relxill_b200_batch *b, const char **names, double *ms, long *launches, int max);
 
+/* Keep the intermediates that only the probes read (the fine emission-angle tables are otherwise not stored
+ * unless a limb law needs them).  Off by default. */
+void relxill_b200_keep_intermediates(int on);
+
 /* Stage probes for the parity tests (device -> host copies of intermediates of vector `iv` of
  * the last run; sizes as in oracle/relxill_oracle.h).  Return 0 on success. */
 int relxill_b200_probe(relxill_b200_batch *b, long iv, const char *what, double *out, long max_len);

@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "relxill_b200_init", "relxill_b200_shutdown", "relxill_b200_set_num_zones", "relxill_b200_num_params",
     "relxill_b200_default_params", "relxill_b200_last_error", "relxill_batch_eval", "relxill_batch_eval_device",
     "relxill_b200_prepare", "relxill_b200_run", "relxill_b200_batch_status", "relxill_b200_free_batch",
-    "relxill_b200_algorithmic_bytes", "relxill_b200_last_launches", "relxill_b200_set_profiling",
+    "relxill_b200_algorithmic_bytes", "relxill_b200_last_launches", "relxill_b200_set_profiling", "relxill_b200_keep_intermediates",
     "relxill_b200_kernel_times", "relxill_b200_probe",
 ] + sorted(LMOD_SYMBOLS.values())
 
@@ -65,6 +65,7 @@ def lib() -> C.CDLL:
     L.relxill_b200_last_launches.argtypes = [C.c_void_p]
     L.relxill_b200_last_launches.restype = C.c_long
     L.relxill_b200_set_profiling.argtypes = [C.c_int]
+    L.relxill_b200_keep_intermediates.argtypes = [C.c_int]
     L.relxill_b200_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), _dp, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"), C.c_int]
     L.relxill_b200_kernel_times.restype = C.c_int
     L.relxill_b200_probe.argtypes = [C.c_void_p, C.c_long, C.c_char_p, _dp, C.c_long]

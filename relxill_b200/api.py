@@ -103,8 +103,10 @@ def batch_eval(model: str, energy, params, flux_in=None, return_status: bool = F
 class Batch:
     """A prepared batch: parameters interpreted and resident in HBM; `run` only launches kernels."""
 
-    def __init__(self, model: str, energy, params):
+    def __init__(self, model: str, energy, params, keep_intermediates: bool = False):
+        """keep_intermediates: also store what only `probe` reads (the fine emission-angle tables)."""
         self.model = model
+        self._keep = bool(keep_intermediates)
         self.energy = np.ascontiguousarray(energy, np.float64)
         self.params = np.ascontiguousarray(np.atleast_2d(params), np.float64)
         self.n, self.n_flux = self.params.shape[0], self.energy.size - 1
@@ -115,7 +117,13 @@ class Batch:
             raise ModelEvalFailed(f"prepare({model}) failed: {_lib.last_error()}")
 
     def run(self, d_flux_ptr: int, stream_ptr: int = 0) -> None:
-        rc = _lib.lib().relxill_b200_run(self._h, C.c_void_p(d_flux_ptr), C.c_void_p(stream_ptr))
+        if self._keep:
+            _lib.lib().relxill_b200_keep_intermediates(1)
+        try:
+            rc = _lib.lib().relxill_b200_run(self._h, C.c_void_p(d_flux_ptr), C.c_void_p(stream_ptr))
+        finally:
+            if self._keep:
+                _lib.lib().relxill_b200_keep_intermediates(0)
         if rc != 0:
             raise ModelEvalFailed(f"run({self.model}) failed: {_lib.last_error()}")
 

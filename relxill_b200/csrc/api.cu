@@ -61,6 +61,7 @@ struct Engine {
   long pipe_piece = 2072;     // vectors per pipelined piece of a host-buffer call (RELXILL_B200_PIPE)
   cudaStream_t stream_c = nullptr, stream_d = nullptr;   // compute / copy streams of host-buffer calls
   bool profiling = false;
+  bool keep_intermediates = false;   // store what only the test probes read (emission-angle tables)
   // device buffers recycled between batches (cudaMalloc/cudaFree synchronise and cost milliseconds)
   std::vector<std::pair<size_t, void *>> pool;
 };
@@ -124,7 +125,7 @@ int ensure_scratch(Engine &E, long cap, int nz_cap, int ne_cap, int nex_stride, 
   ok &= salloc(E, S.xrow, c * NZMAX * 32) && salloc(E, S.xw, c * NZMAX * 32);
   ok &= salloc(E, S.xkey, c * NZMAX * 32) && salloc(E, S.xwsort, c * NZMAX * 32) && salloc(E, S.xn, c);
   ok &= salloc(E, S.xga_off, c * 4) && salloc(E, S.xga_w, c * 4) && salloc(E, S.zrange, c * NZMAX * 2);
-  ok &= salloc(E, S.relflux, c * nz_cap * ne_cap) && salloc(E, S.dist, c * NZMAX * MAX_INCL);
+  ok &= salloc(E, S.relflux, c * nz_cap * ne_cap) && salloc(E, S.dist, c * NZMAX * MAX_INCL) && salloc(E, S.distpart, c * NR * 10);
   ok &= salloc(E, S.xillz, c * nz_cap * (size_t) std::max(nex_stride, 1)) && salloc(E, S.status, c);
   ok &= salloc(E, E.d_total, c * NCONV);
   if (nth) {
@@ -188,6 +189,7 @@ struct relxill_b200_batch {
   int n_flux = 0;
   int nz_max = 1;
   bool any_corr = false;
+  bool any_limb = false;      // some vector uses a limb law: k_fine must keep the emission angles for k_line
   std::vector<VPar> vps;
   std::vector<int> status;
   VPar *d_vps = nullptr;
@@ -297,9 +299,11 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
       if (nth) { tm.begin(); launch_nth(vps, T, S, nc, st); tm.end(KF_NTH); }
       if (b->any_corr) { tm.begin(); launch_syspar(vps, T, S, nc, 2, st); tm.end(KF_SYSPAR); }
     }
-    tm.begin(); launch_fine(vps, T, S, nc, st); tm.end(KF_FINE);
+    tm.begin();
+    launch_fine(vps, T, S, nc, relxill ? n_incl : 0, econv[0], econv[NCONV], (b->any_limb || E.keep_intermediates) ? 1 : 0, st);
+    tm.end(KF_FINE);
     if (relxill) {
-      tm.begin(); launch_dist(vps, T, S, nc, n_incl, econv[0], econv[NCONV], st); tm.end(KF_DIST);
+      tm.begin(); launch_dist(vps, T, S, nc, n_incl, st); tm.end(KF_DIST);
     }
     if (m.type == T_LINE) {
       tm.begin(); launch_line(vps, T, S, nc, b->d_energy, b->n_flux, 1, 1, st); tm.end(KF_LINE);
@@ -357,6 +361,7 @@ void relxill_b200_shutdown(void) {
 
 void relxill_b200_set_num_zones(int n) { g_eng.cfg.env_num_zones = n; }
 void relxill_b200_set_profiling(int on) { g_eng.profiling = on != 0; }
+void relxill_b200_keep_intermediates(int on) { g_eng.keep_intermediates = on != 0; }
 
 int relxill_b200_num_params(const char *model) {
   const ModelDef *m = find_model(model);
@@ -421,6 +426,7 @@ relxill_b200_batch *relxill_b200_prepare(const char *model, const double *energy
     if (b->vps[i].status == ST_OK) {
       b->nz_max = std::max(b->nz_max, b->vps[i].nz);
       if (b->vps[i].do_corr) b->any_corr = true;
+      if (b->vps[i].limb != 0) b->any_limb = true;
     }
   }
   b->vps_bytes = n_vec * sizeof(VPar);

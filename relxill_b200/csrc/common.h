@@ -93,6 +93,7 @@ struct DevTables {
   const double *ecoarse;    // [NCOARSE+1]
   const unsigned char *coarse_m1, *coarse_m2;  // masks of the two band conditions on the coarse grid
   const double *gstar, *d_gstar;  // [NG]
+  const double *gstar_w;          // [NG] dg* / sqrt(g* - g*^2)
   const double *tw;               // FFT twiddles exp(-2 pi i m / NCONV), m < NCONV, interleaved (re, im)
   const double *conv_w;     // [NCONV/2+1][2] (re, im) DFT of band/cf (frequency-domain band sum of a convolution)
   // nthcomp: arrays that depend only on the photon grid (kT_bb is fixed at 0.05 keV)
@@ -127,6 +128,7 @@ struct Scratch {
   double *relflux;                                            // [cap][nz_cap][ne_line_cap] (valid inside zrange only)
   int *zrange;                                                // [cap][NZMAX][2] first/last bin written per zone (-1: none)
   double *dist;                                               // [cap][NZMAX][MAX_INCL]
+  double *distpart;                                           // [cap][NR][10] per-radius parts of dist (k_fine -> k_dist)
   double *xillz;                                              // [cap][nz_cap][nex_stride]
   int *status;                                                // [cap]
   // nthcomp (allocated only for Cp models): Kompaneets work arrays and solutions, [cap][NTH_MAX][NTH_SOL]

@@ -647,11 +647,30 @@ __global__ void __launch_bounds__(128) k_zone(const VPar *__restrict__ vps, DevT
 // ---------------------------------------------------------------------------------- k_fine
 // The g*-dependent half of interpol_relTable (src/Relprofile.cpp:39-80,280-293): bilinear (a, mu0) blend of
 // the four table corners at the two bracketing table radii, then the radial lerp, for trff1/2 and cosne1/2.
-__global__ void __launch_bounds__(320) k_fine(const VPar *__restrict__ vps, DevTables T, Scratch S) {
+// Fused with the per-radius part of the emission-angle distribution (the rel_cosne part of
+// calc_relline_profile, src/Relprofile.cpp:907-938, get_cosne_bin :799-801) while the values are in registers:
+// every (radius, g*) thread files its two branch contributions, then one thread per (radius, angle bin) adds
+// them in the reference's order (g* ascending, branch 1 then 2).  The emission angles themselves are stored
+// only when a later stage needs them (limb darkening in k_line, or the test probes).
+__global__ void __launch_bounds__(320) k_fine(const VPar *__restrict__ vps, DevTables T, Scratch S, int n_incl,
+                                              double e_first, double e_last, int store_cosne) {
+  __shared__ __align__(16) double2 s_val[8][NG];   // the two branch contributions of every (radius, g*)
+  __shared__ int s_bin[8][NG];                      // their angle bins, 16 bits each (0xffff: none)
+  __shared__ double s_rad[8][3];                    // per radius: gmin, gmax - gmin, r (2 pi r)^2 emis weight (< 0: off the grid)
   const int v = blockIdx.y;
   if (S.status[v] != ST_OK) return;
-  const int j = threadIdx.x % NG;
-  const int i = blockIdx.x * 8 + threadIdx.x / NG;
+  const int j = threadIdx.x % NG, rl = threadIdx.x / NG;
+  const int i = blockIdx.x * 8 + rl;
+  if (n_incl > 0 && threadIdx.x < 8) {   // per-radius factors of the distribution
+    const int i2 = blockIdx.x * 8 + threadIdx.x;
+    const double *re = S.re + (size_t) v * NR;
+    const double gmin = S.gmin[(size_t) v * NR + i2], gmax = S.gmax[(size_t) v * NR + i2];
+    const double r = re[i2], x1 = 2 * PI * r;
+    s_rad[threadIdx.x][0] = gmin;
+    s_rad[threadIdx.x][1] = gmax - gmin;
+    s_rad[threadIdx.x][2] = ((gmax > e_first) && (gmin < e_last))
+                                ? r * (x1 * x1) * S.emis[(size_t) v * NR + i2] * (trapez_single(re, i2, NR) / 2) : -1.0;
+  }
   const int ia = S.brk_i[2 * v], im = S.brk_i[2 * v + 1];
   const double fa = S.brk_f[2 * v], fm = S.brk_f[2 * v + 1];
   const int it = S.it[(size_t) v * NR + i];
@@ -675,61 +694,62 @@ __global__ void __launch_bounds__(320) k_fine(const VPar *__restrict__ vps, DevT
   co.y = lin1d(fr, c2_lo, c2_hi);
   const size_t o = ((size_t) v * NR + i) * NG + j;
   reinterpret_cast<double2 *>(S.trff)[o] = tr;
-  reinterpret_cast<double2 *>(S.cosne)[o] = co;
+  if (store_cosne) reinterpret_cast<double2 *>(S.cosne)[o] = co;
+  if (n_incl <= 0) return;
+  __syncthreads();
+  // ---- emission-angle distribution, per-radius part: contribution = r (2 pi g r)^2 / sqrt(g* - g*^2) trff emis
+  //      weight dg*, grouped as [per radius] * g^2 * [per g*] * trff
+  {
+    int bins = 0xffffffff;
+    double2 val = make_double2(0.0, 0.0);
+    const double ar = s_rad[rl][2];
+    if (ar >= 0.0) {
+      const double g = T.gstar[j] * s_rad[rl][1] + s_rad[rl][0];
+      const double common = ar * (g * g) * T.gstar_w[j];
+      val.x = common * tr.x;
+      val.y = common * tr.y;
+      const int i0 = ((int) (n_incl * (1 - co.x) + 1)) - 1, i1 = ((int) (n_incl * (1 - co.y) + 1)) - 1;
+      const bool bad = (val.x != val.x) || (val.y != val.y) || i0 < 0 || i0 >= n_incl || i1 < 0 || i1 >= n_incl;
+      if (bad) S.status[v] = ST_NAN;   // any writer stores the same value
+      else bins = i0 | (i1 << 16);
+    }
+    s_bin[rl][j] = bins;
+    s_val[rl][j] = val;
+  }
+  __syncthreads();
+  {
+    // (radius, angle bin, quarter of the g* axis) per thread: 8 x 10 x 4 = 320; the quarters are then added in order
+    const int c = threadIdx.x & 3, rm = threadIdx.x >> 2;
+    const int r2 = rm / 10, m = rm - r2 * 10;
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < NG / 4; q++) {
+      const int jj = c * (NG / 4) + q;
+      const int b = s_bin[r2][jj];
+      const double2 w = s_val[r2][jj];
+      if ((b & 0xffff) == m) s += w.x;
+      if ((b >> 16) == m) s += w.y;
+    }
+    const double s1 = __shfl_down_sync(0xffffffffu, s, 1), s2 = __shfl_down_sync(0xffffffffu, s, 2),
+                 s3 = __shfl_down_sync(0xffffffffu, s, 3);
+    if (c == 0 && m < n_incl) S.distpart[((size_t) v * NR + blockIdx.x * 8 + r2) * 10 + m] = ((s + s1) + s2) + s3;
+  }
 }
 
 // ---------------------------------------------------------------------------------- k_dist
-// Emission-angle distribution per zone: the rel_cosne part of calc_relline_profile
-// (src/Relprofile.cpp:907-938, get_cosne_bin :799-801) and its normalisation (:783-795).
-__global__ void __launch_bounds__(256) k_dist(const VPar *__restrict__ vps, DevTables T, Scratch S, int n_incl,
-                                              double e_first, double e_last) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  double *part = reinterpret_cast<double *>(smraw);        // [NR][n_incl]
-  double *re = part + (size_t) NR * n_incl;                // [NR]
-  int *flags = reinterpret_cast<int *>(re + NR);
+// Emission-angle distribution per zone: sums of k_fine's per-radius parts over the zone's radii and the
+// normalisation (src/Relprofile.cpp:783-795).
+__global__ void __launch_bounds__(256) k_dist(const VPar *__restrict__ vps, DevTables T, Scratch S, int n_incl) {
   const int v = blockIdx.x, t = threadIdx.x;
   if (S.status[v] != ST_OK) return;
   const VPar &vp = vps[v];
-  for (int i = t; i < NR; i += 256) re[i] = S.re[(size_t) v * NR + i];
-  if (t == 0) flags[0] = 0;
-  __syncthreads();
-  for (int i = t; i < NR; i += 256) {
-    double *p = part + (size_t) i * n_incl;
-    for (int m = 0; m < n_incl; m++) p[m] = 0.0;
-    const double gmin = S.gmin[(size_t) v * NR + i], gmax = S.gmax[(size_t) v * NR + i];
-    if (!((gmax > e_first) && (gmin < e_last))) continue;
-    const double emis = S.emis[(size_t) v * NR + i];
-    const double weight = trapez_single(re, i, NR) / 2;
-    const double r = re[i];
-    const double2 *tr = reinterpret_cast<const double2 *>(S.trff) + ((size_t) v * NR + i) * NG;
-    const double2 *co = reinterpret_cast<const double2 *>(S.cosne) + ((size_t) v * NR + i) * NG;
-    for (int jj = 0; jj < NG; jj++) {
-      const double gs = T.gstar[jj];
-      const double g = gs * (gmax - gmin) + gmin;
-      const double2 trv = tr[jj], cov = co[jj];
-      const double x = 2 * PI * g * r;
-      const double base = r * (x * x) / sqrt(gs - gs * gs);
-      for (int kk = 0; kk < 2; kk++) {
-        const double mu = kk ? cov.y : cov.x;
-        const double tf = kk ? trv.y : trv.x;
-        const int imu = ((int) (n_incl * (1 - mu) + 1)) - 1;
-        const double tmp = base * tf * emis * weight * T.d_gstar[jj];
-        if (tmp != tmp) flags[0] = ST_NAN;
-        if (imu < 0 || imu >= n_incl) flags[0] = ST_NAN; else p[imu] += tmp;
-      }
-    }
-  }
-  __syncthreads();
-  if (flags[0] != 0) {
-    if (t == 0) S.status[v] = flags[0];
-    return;
-  }
+  const double *part = S.distpart + (size_t) v * NR * 10;
   const int *zfirst = S.zfirst + (size_t) v * (NZMAX + 1);
   const int nz = vp.nz;
   for (int job = t; job < nz * n_incl; job += 256) {
     const int z = job / n_incl, m = job - z * n_incl;
     double s = 0.0;
-    for (int i = zfirst[z + 1]; i < zfirst[z]; i++) s += part[(size_t) i * n_incl + m];   // the zone's radii, ascending index
+    for (int i = zfirst[z + 1]; i < zfirst[z]; i++) s += part[(size_t) i * 10 + m];   // the zone's radii, ascending index
     S.dist[((size_t) v * NZMAX + z) * MAX_INCL + m] = s;
   }
   __syncthreads();
@@ -880,8 +900,6 @@ int kernels_init() {
   if (e != cudaSuccess) return 1;
   e = cudaFuncSetAttribute(k_zone, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) g_smem_zone);
   if (e != cudaSuccess) return 1;
-  e = cudaFuncSetAttribute(k_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ((NR * MAX_INCL + NR + 4) * sizeof(double)));
-  if (e != cudaSuccess) return 1;
   if (line_kernel_init() != 0) return 1;
   if (xill_kernel_init() != 0) return 1;
   if (conv_kernel_init() != 0) return 1;
@@ -894,14 +912,13 @@ void launch_syspar(const VPar *vps, const DevTables &T, const Scratch &S, long n
 void launch_zone(const VPar *vps, const DevTables &T, const Scratch &S, long n, cudaStream_t st) {
   k_zone<<<(unsigned) n, 128, g_smem_zone, st>>>(vps, T, S);
 }
-void launch_fine(const VPar *vps, const DevTables &T, const Scratch &S, long n, cudaStream_t st) {
+void launch_fine(const VPar *vps, const DevTables &T, const Scratch &S, long n, int n_incl, double e_first,
+                 double e_last, int store_cosne, cudaStream_t st) {
   dim3 grid(NR / 8, (unsigned) n);
-  k_fine<<<grid, 320, 0, st>>>(vps, T, S);
+  k_fine<<<grid, 320, 0, st>>>(vps, T, S, n_incl, e_first, e_last, store_cosne);
 }
-void launch_dist(const VPar *vps, const DevTables &T, const Scratch &S, long n, int n_incl, double e_first,
-                 double e_last, cudaStream_t st) {
-  const size_t sm = ((size_t) NR * n_incl + NR + 4) * sizeof(double);
-  k_dist<<<(unsigned) n, 256, sm, st>>>(vps, T, S, n_incl, e_first, e_last);
+void launch_dist(const VPar *vps, const DevTables &T, const Scratch &S, long n, int n_incl, cudaStream_t st) {
+  k_dist<<<(unsigned) n, 256, 0, st>>>(vps, T, S, n_incl);
 }
 void launch_linefinish(const VPar *vps, const Scratch &S, long n, int n_ener, double *out, cudaStream_t st) {
   k_linefinish<<<(unsigned) n, 256, 0, st>>>(vps, S, n_ener, S.ne_line_cap, S.nz_cap, out);

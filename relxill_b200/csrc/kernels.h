@@ -10,9 +10,10 @@ int kernels_init();  // opt-in shared-memory sizes; returns 0 on success
 
 void launch_syspar(const VPar *vps, const DevTables &T, const Scratch &S, long n, int pass, cudaStream_t st);
 void launch_zone(const VPar *vps, const DevTables &T, const Scratch &S, long n, cudaStream_t st);
-void launch_fine(const VPar *vps, const DevTables &T, const Scratch &S, long n, cudaStream_t st);
-void launch_dist(const VPar *vps, const DevTables &T, const Scratch &S, long n, int n_incl, double e_first,
-                 double e_last, cudaStream_t st);
+// n_incl > 0: also file the per-radius parts of the emission-angle distribution (relxill models)
+void launch_fine(const VPar *vps, const DevTables &T, const Scratch &S, long n, int n_incl, double e_first,
+                 double e_last, int store_cosne, cudaStream_t st);
+void launch_dist(const VPar *vps, const DevTables &T, const Scratch &S, long n, int n_incl, cudaStream_t st);
 void launch_line(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *egrid, int n_ener,
                  int grid_mode, int nz_max, cudaStream_t st);
 int line_max_bins();  // largest energy grid the line kernel handles in one pass

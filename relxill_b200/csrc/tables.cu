@@ -147,6 +147,11 @@ void Tables::load_fixed() {
   dt_.coarse_m2 = upload(m2);
   dt_.gstar = upload(gstar);
   dt_.d_gstar = upload(dg);
+  {
+    std::vector<double> gw(NG);
+    for (int i = 0; i < NG; i++) gw[i] = dg[i] / std::sqrt(gstar[i] - gstar[i] * gstar[i]);
+    dt_.gstar_w = upload(gw);
+  }
   dt_.tw = upload(tw);
   dt_.conv_w = upload(wpack);
   have_fixed_ = true;

@@ -35,7 +35,7 @@ n = int(os.environ.get("N", "8"))
 for m in models:
     P = np.array([rx.default_params(m)] + [sample(m) for _ in range(n - 1)], float)
     t = time.time()
-    b = rx.Batch(m, e, P)
+    b = rx.Batch(m, e, P, keep_intermediates=True)
     import torch
     out = torch.zeros((n, e.size - 1), dtype=torch.float64, device="cuda")
     b.run(out.data_ptr())

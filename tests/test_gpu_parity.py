@@ -119,7 +119,7 @@ def test_stage_parity(rx, oracle):
     P = sample_params("relxilllp", 4, seed=11)
     P[:, 12] = 1  # returning radiation on: exercises the second system-parameter pass
     P[:, 2] = np.abs(P[:, 2])
-    b = rx.Batch("relxilllp", e, P)
+    b = rx.Batch("relxilllp", e, P, keep_intermediates=True)
     out = torch.zeros((4, 3000), dtype=torch.float64, device="cuda")
     b.run(out.data_ptr())
     torch.cuda.synchronize()
