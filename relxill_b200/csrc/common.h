@@ -82,7 +82,8 @@ struct DevTables {
   const float *lp_a, *lp_h, *lp_rad, *lp_int, *lp_del, *lp_dinc;
   // returning radiation (src/Relreturn_Table.h:23-84) + ln of the g grid (precomputed)
   int rr_nspin;
-  const double *rr_spin, *rr_rlo, *rr_rhi, *rr_tf, *rr_gmin, *rr_gmax, *rr_fg, *rr_lng;
+  const double *rr_spin, *rr_rlo, *rr_rhi, *rr_tf, *rr_gmin, *rr_gmax;
+  const double *rr_fgl;     // [nspin][RR_NG][RR_NR*RR_NR][2] {frac_g, ln g}
   // xillver tables, index 0 = cutoff power law, 1 = nthcomp
   XillDev xill[2];
   // fixed grids

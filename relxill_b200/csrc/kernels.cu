@@ -253,50 +253,54 @@ __global__ void __launch_bounds__(256) k_syspar(const VPar *__restrict__ vps, De
     const size_t n2 = (size_t) RR_NR * RR_NR;
     const double *rlo_t = T.rr_rlo + (size_t) is * RR_NR, *rhi_t = T.rr_rhi + (size_t) is * RR_NR;
     const bool have_corr = (pass == 2);
+    const double rlo_e = sm.re[NR - 1], rhi_e = sm.re[0];
     if (t == 0) {
-      const double rlo_e = sm.re[NR - 1], rhi_e = sm.re[0];
       int klo = bsearch_asc<double>(rlo_t, RR_NR, rlo_e);
       int khi = bsearch_asc<double>(rhi_t, RR_NR, rhi_e);
       if (fabs(rhi_e - rhi_t[RR_NR - 1]) < 1e-6) khi = RR_NR - 1; else khi++;
       if (fabs(rlo_e - rlo_t[0]) < 1e-6) klo = 0;
       int nrad = (khi + 1) - klo;
-      int err = 0;
-      if (nrad < 2 || nrad > RR_NR) { err = ST_RRAD; nrad = 2; }
-      for (int i = 0; i < nrad; i++) {
-        sm.irad[i] = klo + i;
-        sm.rlo[i] = rlo_t[klo + i];
-        sm.rhi[i] = rhi_t[klo + i];
-      }
-      sm.rlo[0] = rlo_e;
-      sm.rhi[nrad - 1] = rhi_e;
-      for (int i = 0; i < nrad; i++) { sm.rad[i] = 0.5 * (sm.rlo[i] + sm.rhi[i]); sm.emis_in[i] = 0.0; }
-      for (int s = 0; s < 2; s++) {  // ring-area correction of the two partially covered edge rings
-        const int idx = s == 0 ? 0 : nrad - 1;
-        double rlo_tab = rlo_t[sm.irad[idx]];
-        if (sm.irad[idx] == 0 && rlo_tab > vp.rms) rlo_tab = vp.rms;
-        const double rhi_tab = rhi_t[sm.irad[idx]];
-        const double area_table = 0.5 * (rlo_tab + rhi_tab) * (rhi_tab - rlo_tab);
-        const double area_model = 0.5 * (sm.rlo[idx] + sm.rhi[idx]) * (sm.rhi[idx] - sm.rlo[idx]);
-        sm.scal[s] = area_model / area_table;
-      }
-      if (sm.rad[0] > sm.rad[nrad - 1] || sm.re[nrad - 1] > sm.re[0]) err = ST_RRAD;
-      if (sm.rad[0] < sm.re[NR - 1] || sm.rad[nrad - 1] > sm.re[0]) err = ST_RRAD;
-      if (have_corr) {  // correction factors by zone membership of the ring centre, Relreturn_Corona.cpp:233-247
-        const double *cf = S.corr_flux + (size_t) v * NZMAX, *cg = S.corr_gshift + (size_t) v * NZMAX;
-        for (int i = 0; i < nrad; i++) {
-          int ind = bsearch_asc<double>(vp.zone, vp.nz + 1, sm.rad[i]);
-          if (sm.rad[i] < vp.zone[0]) ind = 0;
-          else if (sm.rad[i] > vp.zone[vp.nz]) ind = vp.nz;  // (one past the end in the reference as well)
-          if (ind >= vp.nz) ind = vp.nz - 1;
-          sm.cflux[i] = cf[ind];
-          sm.cgsh[i] = cg[ind];
-        }
-      }
+      if (nrad < 2 || nrad > RR_NR) { sm.ints[1] = ST_RRAD; nrad = 2; }
       sm.ints[2] = nrad;
-      if (err) sm.ints[1] = err;
+      sm.ints[3] = klo;
     }
     __syncthreads();
     const int nrad = sm.ints[2];
+    {
+      const int klo = sm.ints[3];
+      if (t < nrad) {   // one thread per ring
+        const double rlo = (t == 0) ? rlo_e : rlo_t[klo + t], rhi = (t == nrad - 1) ? rhi_e : rhi_t[klo + t];
+        sm.irad[t] = klo + t;
+        sm.rlo[t] = rlo;
+        sm.rhi[t] = rhi;
+        const double rad = 0.5 * (rlo + rhi);
+        sm.rad[t] = rad;
+        sm.emis_in[t] = 0.0;
+        if (have_corr) {  // correction factors by zone membership of the ring centre, Relreturn_Corona.cpp:233-247
+          int ind = bsearch_asc<double>(vp.zone, vp.nz + 1, rad);
+          if (rad < vp.zone[0]) ind = 0;
+          else if (rad > vp.zone[vp.nz]) ind = vp.nz;  // (one past the end in the reference as well)
+          if (ind >= vp.nz) ind = vp.nz - 1;
+          sm.cflux[t] = S.corr_flux[(size_t) v * NZMAX + ind];
+          sm.cgsh[t] = S.corr_gshift[(size_t) v * NZMAX + ind];
+        }
+      } else if (t >= 64 && t < 66) {  // ring-area correction of the two partially covered edge rings
+        const int s = t - 64;
+        const int idx = s == 0 ? 0 : nrad - 1;
+        const double rlo_m = (idx == 0) ? rlo_e : rlo_t[klo + idx], rhi_m = (idx == nrad - 1) ? rhi_e : rhi_t[klo + idx];
+        double rlo_tab = rlo_t[klo + idx];
+        if (klo + idx == 0 && rlo_tab > vp.rms) rlo_tab = vp.rms;
+        const double rhi_tab = rhi_t[klo + idx];
+        const double area_table = 0.5 * (rlo_tab + rhi_tab) * (rhi_tab - rlo_tab);
+        const double area_model = 0.5 * (rlo_m + rhi_m) * (rhi_m - rlo_m);
+        sm.scal[s] = area_model / area_table;
+      }
+    }
+    __syncthreads();
+    if (t == 0) {
+      if (sm.rad[0] > sm.rad[nrad - 1] || sm.re[nrad - 1] > sm.re[0]) sm.ints[1] = ST_RRAD;
+      if (sm.rad[0] < sm.re[NR - 1] || sm.rad[nrad - 1] > sm.re[0]) sm.ints[1] = ST_RRAD;
+    }
     // emissivity at the ring centres: inv_rebin_mean (src/relutility.c:636-663).  Its cursor walk finds, for
     // the ring centres in descending order, brackets in strictly ascending fine-grid index; a centre whose
     // bracket does not advance (two centres in one fine bin) and all later ones stay unset (0).
@@ -320,18 +324,21 @@ __global__ void __launch_bounds__(256) k_syspar(const VPar *__restrict__ vps, De
     }
     __syncthreads();
     const double *tf_t = T.rr_tf + is * n2, *gmin_t = T.rr_gmin + is * n2, *gmax_t = T.rr_gmax + is * n2;
-    const double *fg_t = T.rr_fg + is * n2 * RR_NG, *lng_t = T.rr_lng + is * n2 * RR_NG;
+    const double2 *fgl_t = reinterpret_cast<const double2 *>(T.rr_fgl) + (size_t) is * RR_NG * n2;
     for (int pr = t; pr < nrad * nrad; pr += 256) {
       const int io = pr / nrad, ie = pr - io * nrad;
       const size_t q = (size_t) sm.irad[io] * RR_NR + sm.irad[ie];
       const double cg = have_corr ? sm.cgsh[ie] : 1.0;
       const double gmn = gmin_t[q], gmx = gmax_t[q];
+      const bool corr = fabs(cg - 1) > 1e-3;
       double ez = 0.0;
+#pragma unroll 4
       for (int jj = 0; jj < RR_NG; jj++) {
         const double g = ((jj + 0.5) / RR_NG) * (gmx - gmn) + gmn;
-        double e1 = fg_t[q * RR_NG + jj];
-        if (fabs(cg - 1) > 1e-3) e1 *= gshift_fluxboost_over_g(cg, g, lng_t[q * RR_NG + jj], vp.gamma);
-        else if (fabs(g - 1) > 1e-3) e1 *= exp((vp.gamma - 1) * lng_t[q * RR_NG + jj]);
+        const double2 fl = __ldg(fgl_t + (size_t) jj * n2 + q);   // {frac_g, ln g}
+        double e1 = fl.x;
+        if (corr) e1 *= gshift_fluxboost_over_g(cg, g, fl.y, vp.gamma);
+        else if (fabs(g - 1) > 1e-3) e1 *= exp((vp.gamma - 1) * fl.y);
         ez += e1;
       }
       double tfr = tf_t[q];

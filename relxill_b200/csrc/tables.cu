@@ -287,9 +287,18 @@ std::string Tables::load_rrad() {
   dt_.rr_tf = upload(tf);
   dt_.rr_gmin = upload(gmin);
   dt_.rr_gmax = upload(gmax);
-  dt_.rr_fg = upload(fg);
-  dt_.rr_lng = upload(lng);
-  if (!dt_.rr_lng) return "out of device memory (returnRad table)";
+  {  // {frac_g, ln g} pairs, g-bin major: the (ring, ring) pairs of neighbouring threads are neighbours in memory
+    std::vector<double> fgl((size_t) ns * n2 * RR_NG * 2);
+    for (int s = 0; s < ns; s++)
+      for (size_t q = 0; q < n2; q++)
+        for (int j = 0; j < RR_NG; j++) {
+          const size_t o = (((size_t) s * RR_NG + j) * n2 + q) * 2;
+          fgl[o] = fg[(s * n2 + q) * RR_NG + j];
+          fgl[o + 1] = lng[(s * n2 + q) * RR_NG + j];
+        }
+    dt_.rr_fgl = upload(fgl);
+  }
+  if (!dt_.rr_fgl) return "out of device memory (returnRad table)";
   have_rr_ = true;
   return "";
 }
