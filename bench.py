@@ -168,21 +168,67 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (2 ms period, so that even
+    a 100 ms region gets tens of samples); `nvidia-smi -lms` is the fallback when NVML cannot be opened."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        self.path = tempfile.mktemp(suffix=".csv")
-        self.f = open(self.path, "w")
+        import threading
+        self.sm, self.mx, self.reasons = [], None, set()
+        self.p = self.thread = None
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                       "100", "-i", str(device)], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            try:
+                import torch
+                h = nv.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(device).uuid))
+            except Exception:  # noqa: BLE001
+                h = nv.nvmlDeviceGetHandleByIndex(device)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                     ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                     ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
+                     ("hw_power_brake_slowdown", nv.nvmlClocksEventReasonHwPowerBrakeSlowdown))
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        for nm, bit in names:
+                            if r & bit:
+                                self.reasons.add(nm)
+                    except Exception:  # noqa: BLE001
+                        pass
+                    self._stop.wait(0.002)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            self.how = "nvml, 2 ms period"
+        except Exception:  # noqa: BLE001
+            self.how = "nvidia-smi -lms 20"
+            self.path = tempfile.mktemp(suffix=".csv")
+            self.f = open(self.path, "w")
+            try:
+                self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                           "-lms", "20", "-i", str(device)], stdout=self.f, stderr=subprocess.DEVNULL)
+                time.sleep(0.5)   # let it print its first lines before the timed region starts
+            except OSError:
+                self.p = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "how": self.how}
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(1.0)
+            if self.sm:
+                out.update(sm_mhz=float(np.median(self.sm)), sm_max_mhz=self.mx, reasons=sorted(self.reasons),
+                           samples=len(self.sm))
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -205,8 +251,7 @@ class ClockSampler:
                     reasons.add(name)
         os.unlink(self.path)
         if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
         return out
 
 
