@@ -25,7 +25,8 @@
 
 /* ------------------------------------------------------------------ constants (src/common.h, src/Xillspec.h) */
 enum { EMIS_BKN = 1, EMIS_LP = 2 };
-enum { PRIM_NONE = 0, PRIM_ECUT = 1, PRIM_NTHCOMP = 2 };
+enum { PRIM_NONE = 0, PRIM_ECUT = 1, PRIM_NTHCOMP = 2, PRIM_BB = 3 };   /* src/common.h:57-59 */
+enum { XT_STD = 0, XT_CP = 1, XT_NS = 2, XT_CO = 3, XT_COUNT = 4 };
 enum { T_LINE, T_CONV, T_XILL, T_RELXILL };
 enum { ION_CONST = 0, ION_PL = 1, ION_ALPHA = 2 };
 #define REL_NA 25
@@ -43,6 +44,8 @@ enum { ION_CONST = 0, ION_PL = 1, ION_ALPHA = 2 };
 #define XP_LXI 2
 #define XP_ECT 3
 #define XP_DNS 4
+#define XP_KTB 5
+#define XP_FRA 6
 #define XP_INC 7
 
 /* ------------------------------------------------------------------ small utilities (src/relutility.c) */
@@ -173,7 +176,9 @@ typedef struct {
   int limb, num_zones, return_rad, ion_grad_type;
   /* xillver side */
   double gam, afe, lxi, ect, dens, refl_frac, iongrad_index, xincl;
+  double ktbb, frac_pl_bb;   /* xillverNS / xillverCO tables */
   int boost;
+  int xtab;                  /* xillver table: XT_STD, XT_CP, XT_NS, XT_CO (get_xilltable_id, src/xilltable.c:682-694) */
   /* returning-radiation correction factors (NULL = none), on the zone grid */
   const double *corr_rgrid, *corr_flux, *corr_gshift;
   int corr_nz;
@@ -181,7 +186,7 @@ typedef struct {
 
 enum {
   P_LINEE, P_INDEX1, P_INDEX2, P_RBR, P_A, P_RIN, P_ROUT, P_INCL, P_Z, P_LIMB, P_GAMMA, P_LOGXI, P_LOGN, P_AFE,
-  P_ECUT, P_KTE, P_REFLFRAC, P_H, P_BETA, P_IONIDX, P_IONTYPE, P_SWRET, P_SWBOOST, P_COUNT
+  P_ECUT, P_KTE, P_REFLFRAC, P_H, P_BETA, P_IONIDX, P_IONTYPE, P_SWRET, P_SWBOOST, P_KTBB, P_ACO, P_FRAC, P_COUNT
 };
 typedef struct {
   const char *name;
@@ -224,6 +229,19 @@ static const ModelDef MODELS[] = {
      {P_INCL, P_A, P_RIN, P_ROUT, P_H, P_BETA, P_GAMMA, P_LOGXI, P_LOGN, P_AFE, P_KTE, P_REFLFRAC, P_Z, P_IONIDX,
       P_IONTYPE, P_SWRET, P_SWBOOST},
      {30, 0.998, -1, 400, 6, 0, 2, 3.1, 15, 1, 60, 1, 0, 0, 0, 1, 0}},
+    /* neutron-star (blackbody-irradiated) and CO flavours: lmodel_relxill_public.dat:131-153, lmodel_relxill_devel.dat:1-25 */
+    {"xillverNS", T_XILL, 0, PRIM_BB, -101, 7,
+     {P_KTBB, P_AFE, P_LOGN, P_LOGXI, P_Z, P_INCL, P_REFLFRAC},
+     {2, 1, 15, 3.1, 0, 30, -1}},
+    {"relxillNS", T_RELXILL, EMIS_BKN, PRIM_BB, -30, 13,
+     {P_INDEX1, P_INDEX2, P_RBR, P_A, P_INCL, P_RIN, P_ROUT, P_Z, P_KTBB, P_LOGXI, P_AFE, P_LOGN, P_REFLFRAC},
+     {3, 3, 15, 0.998, 30, -1, 400, 0, 2, 3.1, 1, 15, 3}},
+    {"xillverCO", T_XILL, 0, PRIM_ECUT, -210, 8,
+     {P_GAMMA, P_ACO, P_KTBB, P_FRAC, P_ECUT, P_Z, P_INCL, P_REFLFRAC},
+     {2, 5, 0.1, 0.01, 300, 0, 45, -1}},
+    {"relxillCO", T_RELXILL, EMIS_BKN, PRIM_ECUT, -200, 14,
+     {P_INDEX1, P_INDEX2, P_RBR, P_A, P_INCL, P_RIN, P_ROUT, P_Z, P_GAMMA, P_ACO, P_KTBB, P_FRAC, P_ECUT, P_REFLFRAC},
+     {3, 3, 15, 0.998, 30, -1, 400, 0, 2, 5, 0.1, 0.01, 300, 3}},
 };
 #define N_MODELS ((int) (sizeof(MODELS) / sizeof(MODELS[0])))
 
@@ -275,11 +293,16 @@ static int interpret_params(const ModelDef *m, const double *par, Par *p) {
   p->emis_type = m->irrad;
   p->prim_type = m->prim;
   /* xillver-side values (get_xill_params) */
-  p->afe = v[P_AFE];
+  const int is_co = (m->model_type == -200 || m->model_type == -210);   /* is_co_model, src/relutility.c:103-109 */
+  const int is_ns = (m->model_type == -30 || m->model_type == -101);    /* is_ns_model, :95-101 */
+  p->xtab = is_ns ? XT_NS : is_co ? XT_CO : (m->prim == PRIM_NTHCOMP) ? XT_CP : XT_STD;
+  p->afe = is_co ? v[P_ACO] : v[P_AFE];                                  /* src/ModelDefinition.cpp:347-349 */
+  p->ktbb = v[P_KTBB];
+  p->frac_pl_bb = v[P_FRAC];
   p->xincl = v[P_INCL];
   p->ect = (m->prim == PRIM_NTHCOMP) ? (has[P_KTE] ? v[P_KTE] : 0.0) : (has[P_ECUT] ? v[P_ECUT] : 300.0);
   p->lxi = has[P_LOGXI] ? v[P_LOGXI] : 0.0;
-  p->dens = has[P_LOGN] ? v[P_LOGN] : 15.0;
+  p->dens = has[P_LOGN] ? v[P_LOGN] : (is_co ? 17.0 : 15.0);           /* :362-363 */
   p->iongrad_index = v[P_IONIDX];
   p->gam = v[P_GAMMA];
   p->refl_frac = v[P_REFLFRAC];
@@ -371,7 +394,7 @@ typedef struct {
 static char g_dir[1024];
 static RelTab *g_rel = NULL;
 static LpTab *g_lp = NULL;
-static XillTab *g_xill[3] = {NULL, NULL, NULL}; /* index by prim_type */
+static XillTab *g_xill[XT_COUNT]; /* index by table id */
 static RradTab *g_rr = NULL;
 static double g_econv[ORC_NCONV + 1], g_ecoarse[N_COARSE + 1];
 
@@ -450,14 +473,18 @@ static int xill_param_id(const char *name) { /* src/common.h:141-161 */
   if (!strcmp(name, "logXi")) return XP_LXI;
   if (!strcmp(name, "Ecut") || !strcmp(name, "kTe")) return XP_ECT;
   if (!strcmp(name, "Dens")) return XP_DNS;
+  if (!strcmp(name, "kTbb")) return XP_KTB;
+  if (!strcmp(name, "A_CO")) return XP_AFE;   /* PARAM_ACO == PARAM_AFE */
+  if (!strcmp(name, "Frac")) return XP_FRA;
   if (!strcmp(name, "Incl")) return XP_INC;
   return -1;
 }
 
 /* src/xilltable.c:169-276 (axes), :513-564 (rows; the reference loads them lazily — we load all of them
  * eagerly) and :478-511 (renormalisation at load, with its two float roundings) */
-static int load_xill(int prim_type) {
-  mf_file *f = open_tab(prim_type == PRIM_NTHCOMP ? "xillverCp_v3.4.fits" : "xillver-a-Ec5.fits");
+static int load_xill(int xtab) {
+  static const char *const names[XT_COUNT] = {"xillver-a-Ec5.fits", "xillverCp_v3.4.fits", "xillverNS-2.fits", "xillverCO.fits"};
+  mf_file *f = open_tab(names[xtab]);
   if (!f) return 1;
   XillTab *t = (XillTab *) calloc(1, sizeof(XillTab));
   const mf_hdu *hp = &f->hdus[mf_find_hdu(f, "PARAMETERS") - 1];
@@ -492,15 +519,17 @@ static int load_xill(int prim_type) {
     long rem = row;
     int idx[6];
     for (int i = t->npar - 1; i >= 0; i--) { idx[i] = (int) (rem % t->nvals[i]); rem /= t->nvals[i]; }
+    /* axes the table does not have take the model's fixed value (getDefaultLogxi / getDefaultDensity,
+     * src/xilltable.c:566-573): logxi 0; logN 17 for the CO table, 15 otherwise (src/ModelDefinition.cpp:361-363) */
     double lxi = (ax_lxi >= 0) ? t->vals[ax_lxi][idx[ax_lxi]] : 0.0;
-    double dens = (ax_dns >= 0) ? t->vals[ax_dns][idx[ax_dns]] : 15.0;
+    double dens = (ax_dns >= 0) ? t->vals[ax_dns][idx[ax_dns]] : (xtab == XT_CO ? 17.0 : 15.0);
     for (int k = 0; k < t->n_ener; k++) {
       spec[k] /= pow(10, lxi);
       if (fabs(dens - 15) > 1e-6) spec[k] /= pow(10, dens - 15);
     }
   }
   mf_close(f);
-  g_xill[prim_type] = t;
+  g_xill[xtab] = t;
   return 0;
 }
 
@@ -1228,7 +1257,7 @@ void orc_nthcomp(const double *ear, int ne, double gamma, double kte, double z_r
 }
 
 /* ------------------------------------------------------------------ primary spectrum + xillver normalisation */
-typedef struct { double gam, afe, lxi, ect, dens; int prim_type; } XPar;
+typedef struct { double gam, afe, lxi, ect, dens; int prim_type; int xtab; double ktbb, frac; } XPar;
 
 /* src/Xillspec.cpp:215-300 */
 static void primary_spectrum(double *out, const double *ener, int n, const XPar *x, double shift) {
@@ -1237,6 +1266,12 @@ static void primary_spectrum(double *out, const double *ener, int n, const XPar 
     for (int i = 0; i < n; i++) {
       double en = 0.5 * (ener[i] + ener[i + 1]);
       out[i] = exp(1.0 / ecut) * pow(en, -x->gam) * exp(-en / ecut) * (ener[i + 1] - ener[i]);
+    }
+  } else if (x->prim_type == PRIM_BB) { /* spec_blackbody, src/Xillspec.cpp:262-269 (not shifted) */
+    for (int i = 0; i < n; i++) {
+      double en = 0.5 * (ener[i] + ener[i + 1]);
+      out[i] = en * en / (pow(x->ktbb, 4) * (exp(en / x->ktbb) - 1));
+      out[i] *= (ener[i + 1] - ener[i]);
     }
   } else {
     orc_nthcomp(ener, n, x->gam, x->ect, 1 / shift - 1, out);
@@ -1260,11 +1295,12 @@ static double norm_factor_source(const XPar *x) { /* PrimarySource.h:279-293 */
 /* src/xilltable.c:297-323, :812-876, :999-1019, :1054-1181 — all inclinations, no interpolation over Incl.
  * flu[n_incl][n_ener] */
 static int xillver_spectra(const XPar *x, double *flu) {
-  if (!g_xill[x->prim_type] && load_xill(x->prim_type)) return 1;
-  const XillTab *t = g_xill[x->prim_type];
+  if (!g_xill[x->xtab] && load_xill(x->xtab)) return 1;
+  const XillTab *t = g_xill[x->xtab];
   float inp[8];
   inp[XP_GAM] = (float) x->gam; inp[XP_AFE] = (float) x->afe; inp[XP_LXI] = (float) x->lxi;
   inp[XP_ECT] = (float) x->ect; inp[XP_DNS] = (float) x->dens; inp[XP_INC] = 0.f;
+  inp[XP_KTB] = (float) x->ktbb; inp[XP_FRA] = (float) x->frac;
   int ind[6];
   double fac[6];
   int ax_ect = -1;
@@ -1328,11 +1364,12 @@ static int xillver_spectra(const XPar *x, double *flu) {
  * (src/xilltable.c:878-996) and interp_6d_tab (:1022-1044), bracket/factor code of interp_xill_table
  * (:1090-1181).  flu[n_ener] */
 static int xillver_spectrum_incl(const XPar *x, double incl_deg, double *flu) {
-  if (!g_xill[x->prim_type] && load_xill(x->prim_type)) return 1;
-  const XillTab *t = g_xill[x->prim_type];
+  if (!g_xill[x->xtab] && load_xill(x->xtab)) return 1;
+  const XillTab *t = g_xill[x->xtab];
   float inp[8];
   inp[XP_GAM] = (float) x->gam; inp[XP_AFE] = (float) x->afe; inp[XP_LXI] = (float) x->lxi;
   inp[XP_ECT] = (float) x->ect; inp[XP_DNS] = (float) x->dens; inp[XP_INC] = (float) incl_deg;
+  inp[XP_KTB] = (float) x->ktbb; inp[XP_FRA] = (float) x->frac;
   int ind[6];
   double fac[6];
   int ax_ect = -1;
@@ -1389,8 +1426,8 @@ static int xillver_spectrum_incl(const XPar *x, double incl_deg, double *flu) {
   return 0;
 }
 
-static void xill_energy_grid(int prim_type, double *ener) { /* xilltable.c:1105-1109 */
-  const XillTab *t = g_xill[prim_type];
+static void xill_energy_grid(int xtab, double *ener) { /* xilltable.c:1105-1109 */
+  const XillTab *t = g_xill[xtab];
   for (int i = 0; i < t->n_ener; i++) ener[i] = t->elo[i];
   ener[t->n_ener] = t->ehi[t->n_ener - 1];
 }
@@ -1487,7 +1524,7 @@ static void free_stages(Stages *s) { free(s->relflux); free(s->dist); free(s->xi
 static int relxill_pipeline(Par *p, Stages *st) {
   int rc;
   if (p->emis_type == EMIS_LP && p->prim_type == PRIM_ECUT) p->ect /= energy_shift_source_obs(p);
-  XPar src = {p->gam, p->afe, p->lxi, p->ect, p->dens, p->prim_type};
+  XPar src = {p->gam, p->afe, p->lxi, p->ect, p->dens, p->prim_type, p->xtab, p->ktbb, p->frac_pl_bb};
   double shift_obs = (p->emis_type == EMIS_LP) ? energy_shift_source_obs(p) : 1.0;
   SysPar *sp = new_syspar();
   p->corr_flux = NULL;
@@ -1539,22 +1576,22 @@ static int relxill_pipeline(Par *p, Stages *st) {
   }
 
   /* xillver spectra per zone */
-  if (!g_xill[p->prim_type] && load_xill(p->prim_type)) { free_syspar(sp); return 301; }
-  const XillTab *xt = g_xill[p->prim_type];
+  if (!g_xill[p->xtab] && load_xill(p->xtab)) { free_syspar(sp); return 301; }
+  const XillTab *xt = g_xill[p->xtab];
   int nex = xt->n_ener, ni = xt->n_incl;
   st->n_ener_x = nex; st->n_incl = ni;
   double *ex = (double *) malloc(sizeof(double) * (nex + 1));
-  xill_energy_grid(p->prim_type, ex);
+  xill_energy_grid(p->xtab, ex);
   double *flu = (double *) malloc(sizeof(double) * (size_t) nz * ni * nex);
   for (int i = 0; i < nz; i++) {
-    XPar xz = {src.gam, src.afe, st->lxi[i], st->ect[i], st->dens[i], p->prim_type};
+    XPar xz = {src.gam, src.afe, st->lxi[i], st->ect[i], st->dens[i], p->prim_type, p->xtab, p->ktbb, p->frac_pl_bb};
     xillver_spectra(&xz, flu + (size_t) i * ni * nex);
   }
   /* returning-radiation correction factors + second system-parameter pass (Relxill.cpp:337-344) */
   for (int i = 0; i < nz; i++) st->corr_flux[i] = st->corr_gshift[i] = 0.0;
   if (p->return_rad != 0 && p->a > 0.0) {
     for (int i = 0; i < nz; i++) {
-      XPar xz = {src.gam, src.afe, st->lxi[i], st->ect[i], st->dens[i], p->prim_type};
+      XPar xz = {src.gam, src.afe, st->lxi[i], st->ect[i], st->dens[i], p->prim_type, p->xtab, p->ktbb, p->frac_pl_bb};
       fluxcorr_factors(flu + (size_t) i * ni * nex, ni, nex, ex, xt->incl, &xz, &st->corr_flux[i], &st->corr_gshift[i]);
     }
     p->corr_rgrid = st->zone; p->corr_flux = st->corr_flux; p->corr_gshift = st->corr_gshift; p->corr_nz = nz;
@@ -1662,12 +1699,12 @@ int orc_eval_model(const char *model, const double *energy, int n_flux, const do
     }
     free_syspar(sp);
   } else { /* xillver_model, src/LocalModel.cpp:104-130, + add_primary_component, src/Relbase.cpp:294-351 */
-    XPar src = {p.gam, p.afe, p.lxi, p.ect, p.dens, p.prim_type};
-    if (!g_xill[p.prim_type] && load_xill(p.prim_type)) { free(e); return 3; }
-    int nex = g_xill[p.prim_type]->n_ener;
+    XPar src = {p.gam, p.afe, p.lxi, p.ect, p.dens, p.prim_type, p.xtab, p.ktbb, p.frac_pl_bb};
+    if (!g_xill[p.xtab] && load_xill(p.xtab)) { free(e); return 3; }
+    int nex = g_xill[p.xtab]->n_ener;
     double *ex = (double *) malloc(sizeof(double) * (nex + 1));
     double *fx = (double *) malloc(sizeof(double) * nex);
-    xill_energy_grid(p.prim_type, ex);
+    xill_energy_grid(p.xtab, ex);
     rc = xillver_spectrum_incl(&src, p.xincl, fx);
     if (!rc) {
       double nf = 0.5 * cos(p.xincl * M_PI / 180); /* norm_xillver_spec, src/Xillspec.cpp:528-545 */

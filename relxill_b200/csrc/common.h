@@ -96,7 +96,7 @@ struct DevTables {
   const double *gstar, *d_gstar;  // [NG]
   const double *gstar_w;          // [NG] dg* / sqrt(g* - g*^2)
   const double *tw;               // FFT twiddles exp(-2 pi i m / NCONV), m < NCONV, interleaved (re, im)
-  const double *conv_w;     // [NCONV/2+1][2] (re, im) DFT of band/cf (frequency-domain band sum of a convolution)
+  const double *conv_w;     // [NCONV/2+1][2] (re, im) DFT of the band mask (frequency-domain band sum of a convolution)
   // nthcomp: arrays that depend only on the photon grid (kT_bb is fixed at 0.05 keV)
   const double *nth_x, *nth_c2, *nth_rel, *nth_x3, *nth_w, *nth_dphdot;
   int nth_jnr, nth_jrel, nth_jmaxth;

@@ -104,16 +104,19 @@ __device__ __forceinline__ void fft8(double (&r)[8], double (&i)[8]) {
   r[7] = br[6] - br[7]; i[7] = bi[6] - bi[7];
 }
 
-// Forward FFT of 4096 points, tw[m] = exp(-2 pi i m / 4096); all CONV_NT threads call.  The input arrives in
-// registers: thread j holds the points j + 512 q, q = 0..7 (exactly what the first pass needs), so the packing
-// code hands its values over without a round trip through shared memory.  Result in the padded array z.
-__device__ void fft4096(double (&r)[8], double (&im)[8], double2 *z, const double2 *__restrict__ tw) {
+// Forward FFT of 4096 points; all CONV_NT threads call.  The input arrives in registers: thread j holds the points
+// j + 512 q, q = 0..7 (exactly what the first pass needs), so the packing code hands its values over without a
+// round trip through shared memory.  Result in the padded array z.
+// The twiddles of pass p are w^q with w = exp(-2 pi i k / (8 ns)), k = j mod ns: they depend on the thread only,
+// so the caller keeps the three w (one per pass) in registers for the whole kernel; w^2 and w^4 come from
+// squarings and the rest from products — no table reads inside the transform.
+__device__ __forceinline__ void fft4096(double (&r)[8], double (&im)[8], double2 *z, const double2 (&wreg)[3]) {
   const int j = threadIdx.x;
   fft8(r, im);
 #pragma unroll
   for (int q = 0; q < 8; q++) z[cv_pad((j << 3) + q)] = make_double2(r[q], im[q]);
   __syncthreads();
-#pragma unroll 1
+#pragma unroll
   for (int pass = 1; pass < 4; pass++) {
     const int ns = 1 << (3 * pass);          // 8, 64, 512
     const int k = j & (ns - 1);
@@ -124,9 +127,9 @@ __device__ void fft4096(double (&r)[8], double (&im)[8], double2 *z, const doubl
       im[q] = c.y;
     }
     {
-      // twiddles w^q, w = tw[k * 512 / ns]: three table reads (w, w^2, w^4), the rest by products
-      const int mb = k * ((NCONV / 8) >> (3 * pass));
-      const double2 w1 = __ldg(tw + mb), w2 = __ldg(tw + 2 * mb), w4 = __ldg(tw + 4 * mb);
+      const double2 w1 = wreg[pass - 1];
+      const double2 w2 = make_double2(w1.x * w1.x - w1.y * w1.y, 2.0 * w1.x * w1.y);
+      const double2 w4 = make_double2(w2.x * w2.x - w2.y * w2.y, 2.0 * w2.x * w2.y);
       const double2 w3 = cprod(w1, w2), w5 = cprod(w4, w1), w6 = cprod(w4, w2);
       const double2 w7 = cprod(w4, w3);
       cmul(r[1], im[1], w1.x, w1.y);
@@ -174,12 +177,16 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
   const int2 *rb_ii = reinterpret_cast<const int2 *>(X.rb_ii);
   const double2 *rb_dd = reinterpret_cast<const double2 *>(X.rb_dd);
   for (int k = t; k <= NCONV / 2; k += CONV_NT) { sm.ar[k] = 0.0; sm.ai[k] = 0.0; }
+  const double2 wreg[3] = {__ldg(tw + (t & 7) * 64), __ldg(tw + (t & 63) * 8), __ldg(tw + t)};   // tw[m] = exp(-2 pi i m / 4096)
   for (int z = 0; z < nz; z++) {
     const double *rel = S.relflux + ((size_t) v * A.nz_stride + z) * A.ne_stride;
     const double *xz = S.xillz + ((size_t) v * A.nz_stride + z) * X.stride;
     const int rjlo = S.zrange[((size_t) v * NZMAX + z) * 2], rjhi = S.zrange[((size_t) v * NZMAX + z) * 2 + 1];
     // ---- pack the zone's spectrum rebinned onto the convolution grid (real part) and its line profile, rotated so
-    //      that 1 keV sits at index 0 (imaginary part), both times E/dE; band and total sums on the way
+    //      that 1 keV sits at index 0 (imaginary part); band and total sums on the way.  The reference multiplies
+    //      both by E_mid/dE before the transform and divides the result by it afterwards (src/Relbase.cpp:93-103,
+    //      186-190); on the logarithmic convolution grid that factor is one constant (to 1e-13, checked at load,
+    //      tables.cu) and cancels against the normalisation, so it is left out
     double sums[4] = {0.0, 0.0, 0.0, 0.0};   // all rel, |x|, band x, band rel
     double re[8], im[8];                      // bins t + 512 u: the first FFT pass takes them from here
     if (A.mode == 0) {
@@ -199,8 +206,8 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
         }
         const int ri = (i + i1) & (NCONV - 1);
         const double r = (ri >= rjlo && ri <= rjhi) ? rel[ri] : 0.0;
-        re[u] = f * T.conv_cf[i];
-        im[u] = r * T.conv_cf[ri];
+        re[u] = f;
+        im[u] = r;
         sums[0] += r;
         sums[1] += fabs(f);
         if (i >= b0 && i <= b1) sums[2] += f;
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
         const double f = rebin_bin(T.econv[i], T.econv[i + 1], A.user_e, o, A.n_flux);
         const int ri = (i + i1) & (NCONV - 1);
         const double r = (ri >= rjlo && ri <= rjhi) ? rel[ri] : 0.0;
-        sm.z[cv_pad(i)] = make_double2(f * T.conv_cf[i], r * T.conv_cf[ri]);
+        sm.z[cv_pad(i)] = make_double2(f, r);
         sums[0] += r;
         sums[1] += fabs(f);
         if (i >= b0 && i <= b1) sums[2] += f;
@@ -238,7 +245,7 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
 #pragma unroll
       for (int u = 0; u < 8; u++) im[u] *= yscale;
     }
-    fft4096(re, im, sm.z, tw);
+    fft4096(re, im, sm.z, wreg);
     // ---- split, product spectrum, band sum of the convolved zone in the frequency domain
     double dot[1] = {0.0};
     double pr_[5], pi_[5];
@@ -276,10 +283,10 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
       re[u] = sm.ar[k];
       im[u] = (i <= NCONV / 2) ? -ai : ai;
     }
-    fft4096(re, im, sm.z, tw);
+    fft4096(re, im, sm.z, wreg);
   }
   double *acc = sm.ar;   // ar and ai are contiguous: 4098 doubles
-  for (int i = t; i < NCONV; i += CONV_NT) acc[i] = sm.z[cv_pad(i)].x / T.conv_cf[i];
+  for (int i = t; i < NCONV; i += CONV_NT) acc[i] = sm.z[cv_pad(i)].x;
   __syncthreads();
   if (A.mode == 0) {
     // primary spectrum on the convolution grid (cutoff power law here; nthcomp is added by k_prim_nthcomp)

@@ -112,9 +112,14 @@ void Tables::load_fixed() {
     tw[2 * k] = std::cos(ang);
     tw[2 * k + 1] = std::sin(ang);
   }
-  // W = DFT(band / cf): sum over the band of a convolution = sum_k P[k] conj(W[k])  (host radix-2 FFT)
+  // W = DFT(band): sum over the band of a convolution = sum_k P[k] conj(W[k])  (host radix-2 FFT).  The E_mid/dE
+  // weights of the reference (src/Relbase.cpp:93-103) are one constant on this grid — conv_cf_dev holds the
+  // largest relative deviation (~1e-13) — so the kernels convolve the plain spectra
   std::vector<double> wr(NCONV), wi(NCONV, 0.0);
-  for (int i = 0; i < NCONV; i++) wr[i] = band[i] ? 1.0 / cf[i] : 0.0;
+  for (int i = 0; i < NCONV; i++) {
+    wr[i] = band[i] ? 1.0 : 0.0;
+    conv_cf_dev_ = std::max(conv_cf_dev_, std::fabs(cf[i] / cf[NCONV / 2] - 1.0));
+  }
   for (int i = 1, j = 0; i < NCONV; i++) {
     int bit = NCONV >> 1;
     for (; j & bit; bit >>= 1) j ^= bit;
@@ -567,6 +572,7 @@ void Tables::load_nthcomp() {
 std::string Tables::load(const std::string &dir) {
   dir_ = dir;
   load_fixed();
+  if (conv_cf_dev_ > 1e-11) return "convolution grid: E_mid/dE is not constant (k_conv relies on it)";
   return "";   // the tables themselves are loaded on first use by the model flavour that needs them
 }
 

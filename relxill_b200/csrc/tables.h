@@ -30,6 +30,7 @@ class Tables {
   bool has_rel() const { return have_rel_; }
   const std::vector<double> &econv() const { return econv_; }
   size_t device_bytes() const { return dev_bytes_; }
+  double conv_cf_deviation() const { return conv_cf_dev_; }   // max |E_mid/dE / const - 1| on the convolution grid
 
  private:
   std::string dir_;
@@ -39,6 +40,7 @@ class Tables {
   std::vector<double> rr_spin_, econv_, ecoarse_;
   std::vector<void *> allocs_;
   size_t dev_bytes_ = 0;
+  double conv_cf_dev_ = 0.0;
 
   template <class T> const T *upload(const std::vector<T> &v);
   template <class T> const T *upload(const T *p, size_t n);

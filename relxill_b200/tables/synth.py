@@ -33,6 +33,11 @@ SIZES = {
     "test": dict(gam=5, afe=3, lxi=5, ect=5, kte=4, dens=3, gam_cp=4, n_ener=2999),
     "bench": dict(gam=13, afe=4, lxi=15, ect=11, kte=10, dens=6, gam_cp=12, n_ener=2999),
 }
+# the neutron-star (blackbody-irradiated) and CO flavours: same sizes for "test" and "bench"
+SIZES_NSCO = {
+    "ns": dict(ktbb=4, afe=3, lxi=4, dens=3),
+    "co": dict(gam=3, aco=3, ktbb=3, frac=3, ect=3),
+}
 
 
 def kerr_rms(a):
@@ -251,6 +256,78 @@ def write_xillver(path, size, nthcomp=False):
     w.close()
 
 
+def _bb_like(emid, ktbb):
+    x = np.minimum(emid / ktbb, 600.0)
+    return emid ** 2 / (ktbb ** 4 * np.expm1(x))
+
+
+def write_xillver_nsco(path, flavour, n_ener=2999):
+    """xillverNS-2.fits (5-D: kTbb, A_Fe, logXi, Dens, Incl; blackbody irradiation) and xillverCO.fits
+    (6-D: Gamma, A_CO, kTbb, Frac, Ecut, Incl), reference src/xilltable.c:682-760, common.h:141-168."""
+    cfg = SIZES_NSCO[flavour]
+    elo, ehi = _xill_energy(n_ener)
+    incl = _incl_axis()
+    mu = np.cos(np.radians(incl.astype(np.float64)))
+    e_lo, e_hi = elo.astype(np.float64), ehi.astype(np.float64)
+    emid, de = 0.5 * (e_lo + e_hi), e_hi - e_lo
+    n_incl = len(incl)
+    if flavour == "ns":
+        ktbb = np.geomspace(0.5, 10.0, cfg["ktbb"]).astype(np.float32)
+        afe = np.geomspace(0.5, 10.0, cfg["afe"]).astype(np.float32)
+        lxi = np.linspace(1.0, 4.7, cfg["lxi"]).astype(np.float32)
+        dens = np.linspace(15.0, 19.0, cfg["dens"]).astype(np.float32)
+        names, vals = ["kTbb", "A_Fe", "logXi", "Dens", "Incl"], [ktbb, afe, lxi, dens, incl]
+    else:
+        gam = np.linspace(1.0, 2.8, cfg["gam"]).astype(np.float32)
+        aco = np.geomspace(1.0, 1000.0, cfg["aco"]).astype(np.float32)
+        ktbb = np.geomspace(0.05, 0.5, cfg["ktbb"]).astype(np.float32)
+        frac = np.geomspace(0.01, 1.0, cfg["frac"]).astype(np.float32)
+        ect = np.geomspace(2.0, 1000.0, cfg["ect"]).astype(np.float32)
+        names, vals = ["Gamma", "A_CO", "kTbb", "Frac", "Ecut", "Incl"], [gam, aco, ktbb, frac, ect, incl]
+    w = FitsWriter(path)
+    _write_param_ext(w, names, vals)
+    w.add_table("ENERGIES", [Column("ENERG_LO", "E", elo), Column("ENERG_HI", "E", ehi)])
+    npar = len(names)
+    nrows = int(np.prod([len(v) for v in vals]))
+    w.begin_stream_table("SPECTRA", [("PARAMVAL", "E", npar), ("INTPSPEC", "E", n_ener)], nrows)
+    band = (emid >= 0.1) & (emid <= 1000)
+    if flavour == "ns":
+        for kt in ktbb:
+            bb = _bb_like(emid, float(kt))
+            for af in afe:
+                for lx in lxi:
+                    blk = np.zeros((len(dens), n_incl, npar + n_ener), ">f4")
+                    for idn, dn in enumerate(dens):
+                        sp = _xill_spec(emid, de, mu, 2.0, float(af), float(lx), 300.0, float(dn))
+                        refl = bb * (0.3 + 0.5 * float(lx) / 4.7) * de * 497.0 / np.sum(bb * de * emid * band)
+                        sp = 0.15 * sp + refl[None, :] * (0.5 + mu[:, None])
+                        sp = sp * 10.0 ** float(lx) * 10.0 ** (float(dn) - 15.0)
+                        blk[idn, :, npar:] = sp
+                        blk[idn, :, 0:4] = [kt, af, lx, dn]
+                        blk[idn, :, 4] = incl
+                    w.stream_rows(blk.reshape(-1, npar + n_ener))
+    else:
+        for g in gam:
+            for ac in aco:
+                for kt in ktbb:
+                    bb = _bb_like(emid, float(kt))
+                    bbn = bb * de * 497.0 / np.sum(bb * de * emid * band)
+                    blk = np.zeros((len(frac), len(ect), n_incl, npar + n_ener), ">f4")
+                    for ifr, fr in enumerate(frac):
+                        for ie, ec in enumerate(ect):
+                            sp = _xill_spec(emid, de, mu, float(g), 1.0, 1.0, float(ec))
+                            cline = 2.0 * np.log10(float(ac) + 1.0) * 0.28 ** (-float(g)) * _gauss(emid, 0.28, 0.02) \
+                                + np.log10(float(ac) + 1.0) * 0.53 ** (-float(g)) * _gauss(emid, 0.53, 0.03)
+                            mix = float(fr) * sp + (1.0 - float(fr)) * 0.3 * bbn[None, :] * (0.5 + mu[:, None])
+                            sp = mix + 0.05 * cline[None, :] * de[None, :] * (0.5 + mu[:, None])
+                            sp = sp * 100.0          # the table is computed for logN = 17 (src/ModelDefinition.cpp:362-363)
+                            blk[ifr, ie, :, npar:] = sp
+                            blk[ifr, ie, :, 0:5] = [g, ac, kt, fr, ec]
+                            blk[ifr, ie, :, 5] = incl
+                    w.stream_rows(blk.reshape(-1, npar + n_ener))
+    w.close()
+
+
 # --------------------------------------------------------------------------- returning radiation
 RR_SPINS = np.array([-0.5, 0.0, 0.5, 0.8, 0.9, 0.95, 0.99, 0.9982])
 
@@ -298,11 +375,13 @@ FILES = {
     "lp": "rel_lp_table_v0.5b.fits",
     "xill": "xillver-a-Ec5.fits",
     "xillcp": "xillverCp_v3.4.fits",
+    "xillns": "xillverNS-2.fits",
+    "xillco": "xillverCO.fits",
     "rrad": "table_returnRad_v20220301.fits",
 }
 
 
-def generate(outdir, size="test", which=("rel", "lp", "xill", "xillcp", "rrad"), force=False):
+def generate(outdir, size="test", which=("rel", "lp", "xill", "xillcp", "rrad", "xillns", "xillco"), force=False):
     """Writes the requested tables into `outdir` (skips files already stamped
     with the same size) and returns the directory."""
     os.makedirs(outdir, exist_ok=True)
@@ -325,6 +404,10 @@ def generate(outdir, size="test", which=("rel", "lp", "xill", "xillcp", "rrad"),
             write_xillver(tmp, size, nthcomp=False)
         elif key == "xillcp":
             write_xillver(tmp, size, nthcomp=True)
+        elif key == "xillns":
+            write_xillver_nsco(tmp, "ns")
+        elif key == "xillco":
+            write_xillver_nsco(tmp, "co")
         elif key == "rrad":
             write_rrad_table(tmp)
         os.replace(tmp, path)
@@ -345,7 +428,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("outdir")
     ap.add_argument("--size", default="test", choices=sorted(SIZES))
-    ap.add_argument("--which", default="rel,lp,xill,xillcp,rrad")
+    ap.add_argument("--which", default="rel,lp,xill,xillcp,rrad,xillns,xillco")
     ap.add_argument("--force", action="store_true")
     args = ap.parse_args()
     generate(args.outdir, args.size, tuple(args.which.split(",")), args.force)

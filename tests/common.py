@@ -3,6 +3,9 @@ import numpy as np
 
 MODELS = ["relline", "relline_lp", "relconv", "relconv_lp", "relxill", "relxilllp", "relxillCp", "relxilllpCp",
           "xillver", "xillverCp"]
+# neutron-star / CO table flavours; their golden vectors live in golden_v2_nsco.npz
+NSCO_MODELS = ["xillverNS", "relxillNS", "xillverCO", "relxillCO"]
+ALL_MODELS = MODELS + NSCO_MODELS
 # north_star tolerance: relative error <= 1e-5 per bin on bins above 1e-6 of the spectrum peak
 RTOL = 1e-5
 PEAK_FLOOR = 1e-6
@@ -61,6 +64,15 @@ def sample_params(model, n, seed):
             r = [U(1, 3.4), U(.5, 10), U(5, 1000), U(0, 4.7), z, U(3, 89), U(-2, 5)]
         elif model == "xillverCp":
             r = [U(1.2, 3.4), U(.5, 10), U(1, 400), U(0, 4.7), U(15, 20), z, U(3, 89), U(-2, 5)]
+        elif model == "xillverNS":
+            r = [U(.5, 10), U(.5, 10), U(15, 19), U(1, 4.7), z, U(3, 89), U(-2, 5)]
+        elif model == "relxillNS":
+            r = [U(0, 6), U(0, 6), U(2, 100), a, incl, rin, rout, z, U(.5, 10), U(1, 4.7), U(.5, 10), U(15, 19), U(-2, 10)]
+        elif model == "xillverCO":
+            r = [U(1, 2.8), U(1, 1000), U(.05, .5), U(.01, 1), U(2, 1000), z, U(18.2, 87), U(-2, 5)]
+        elif model == "relxillCO":
+            r = [U(0, 6), U(0, 6), U(2, 100), a, incl, rin, rout, z, U(1, 2.8), U(1, 1000), U(.05, .5), U(.01, 1),
+                 U(2, 1000), U(-2, 10)]
         else:
             raise KeyError(model)
         rows.append([float(x) for x in r])

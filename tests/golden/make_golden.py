@@ -1,4 +1,4 @@
-"""Generates tests/golden/golden_v1.npz from the UNMODIFIED reference (oracle/_ref) on the synthetic
+"""Generates tests/golden/golden_v1.npz (and golden_v2_nsco.npz with `nsco` as argument) from the UNMODIFIED reference (oracle/_ref) on the synthetic
 'test' tables.  Run in the build container (needs /root/reference to have been compiled by
 `make -C oracle ref`):   python tests/golden/make_golden.py
 The fixture pins the oracle restatement and the CUDA path on machines without the reference."""
@@ -11,14 +11,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from common import MODELS, default_grid, sample_params  # noqa: E402
+from common import MODELS, NSCO_MODELS, default_grid, sample_params  # noqa: E402
 from oracle.pyref import Ref  # noqa: E402  (process-isolated)
 from relxill_b200.tables import synth  # noqa: E402
 
 
-def table_digest(d):
+def table_digest(d, keys=("rel", "lp", "xill", "xillcp", "rrad")):
     h = hashlib.sha256()
-    for key in ("rel", "lp", "xill", "xillcp", "rrad"):
+    for key in keys:
         with open(os.path.join(d, synth.FILES[key]), "rb") as f:
             while True:
                 blk = f.read(1 << 24)
@@ -55,5 +55,24 @@ def main():
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_v1.npz"), **out)
 
 
+def main_nsco():
+    """xillverNS / relxillNS / xillverCO / relxillCO on the synthetic xillverNS-2.fits and xillverCO.fits"""
+    tdir = synth.generate(synth.default_table_dir("test"), "test")
+    os.environ.pop("RELXILL_NUM_RZONES", None)
+    ref = Ref(tdir)
+    e = default_grid(600)
+    out = {"energy": e, "table_digest": np.array(table_digest(tdir, ("rel", "xillns", "xillco")))}
+    for m in NSCO_MODELS:
+        P = np.vstack([ref.default_params(m)[None, :], sample_params(m, 5, seed=1000 + len(m))])
+        F = ref.eval_batch(m, e, P)
+        out[f"{m}_params"] = P
+        out[f"{m}_flux"] = F
+        print(m, P.shape, F.shape, float(F.sum()))
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_v2_nsco.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "nsco":
+        main_nsco()
+    else:
+        main()

@@ -5,9 +5,10 @@ import os
 import numpy as np
 import pytest
 
-from common import MODELS, default_grid, relerr, sample_params
+from common import ALL_MODELS, MODELS, NSCO_MODELS, default_grid, relerr, sample_params
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz")
+GOLDEN_NSCO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2_nsco.npz")
 
 
 # ---------------------------------------------------------------- table-independent KATs of the reference
@@ -58,9 +59,9 @@ def test_model_database(oracle):
 
 
 # ---------------------------------------------------------------- golden vectors (from the unmodified reference)
-@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("model", ALL_MODELS)
 def test_oracle_vs_golden(oracle, model):
-    g = np.load(GOLDEN)
+    g = np.load(GOLDEN_NSCO if model in NSCO_MODELS else GOLDEN)
     e = g["energy"]
     P, F = g[f"{model}_params"], g[f"{model}_flux"]
     oracle.set_num_zones(None)
@@ -91,10 +92,15 @@ def test_golden_tables_match(table_dir):
         with open(os.path.join(table_dir, synth.FILES[key]), "rb") as f:
             h.update(f.read())
     assert h.hexdigest() == str(np.load(GOLDEN)["table_digest"]), "synthetic tables changed: regenerate the golden file"
+    h = hashlib.sha256()
+    for key in ("rel", "xillns", "xillco"):
+        with open(os.path.join(table_dir, synth.FILES[key]), "rb") as f:
+            h.update(f.read())
+    assert h.hexdigest() == str(np.load(GOLDEN_NSCO)["table_digest"]), "synthetic NS/CO tables changed: regenerate golden_v2_nsco.npz"
 
 
 # ---------------------------------------------------------------- fresh runs of the unmodified reference
-@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("model", ALL_MODELS)
 def test_oracle_vs_reference_random(oracle, ref, model):
     e = default_grid(1200)
     P = sample_params(model, 3, seed=31 + len(model))
