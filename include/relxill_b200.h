@@ -40,6 +40,10 @@ RELXILL_B200_LMOD(lmodrelxilldensnthcomp);   /* :96  relxillCp    (14) */
 RELXILL_B200_LMOD(lmodrelxilllpdensnthcomp); /* :112 relxilllpCp  (17) */
 RELXILL_B200_LMOD(lmodxillver);              /* :77  xillver      (7)  */
 RELXILL_B200_LMOD(lmodxillverdensnthcomp);   /* :86  xillverCp    (8)  */
+RELXILL_B200_LMOD(lmodxillverns);            /* :131 xillverNS    (7)  blackbody-irradiated table xillverNS-2.fits */
+RELXILL_B200_LMOD(lmodrelxillns);            /* :140 relxillNS    (13) */
+RELXILL_B200_LMOD(lmodxillverco);            /* lmodel_relxill_devel.dat:1  xillverCO (8)  table xillverCO.fits */
+RELXILL_B200_LMOD(lmodrelxillco);            /* lmodel_relxill_devel.dat:11 relxillCO (14) */
 
 /* ---------------------------------------------------------------- library state */
 /* Select the CUDA device and load the tables from `table_dir` (NULL: $RELXILL_TABLE_PATH or "./").

@@ -25,6 +25,10 @@ LMOD_SYMBOLS = {
     "relxilllpCp": "lmodrelxilllpdensnthcomp",
     "xillver": "lmodxillver",
     "xillverCp": "lmodxillverdensnthcomp",
+    "xillverNS": "lmodxillverns",
+    "relxillNS": "lmodrelxillns",
+    "xillverCO": "lmodxillverco",
+    "relxillCO": "lmodrelxillco",
 }
 
 ABI_SYMBOLS = [

@@ -31,6 +31,13 @@ PARAM_NAMES = {
     "xillverCp": ["gamma", "Afe", "kTe", "logxi", "logN", "z", "Incl", "refl_frac"],
     "relxilllpCp": ["Incl", "a", "Rin", "Rout", "h", "beta", "gamma", "logxi", "logN", "Afe", "kTe", "refl_frac", "z",
                     "iongrad_index", "iongrad_type", "switch_returnrad", "switch_reflfrac_boost"],
+    # lmodel_relxill_public.dat:131-153 and lmodel_relxill_devel.dat:1-25
+    "xillverNS": ["kTbb", "Afe", "logN", "logxi", "z", "Incl", "refl_frac"],
+    "relxillNS": ["Index1", "Index2", "Rbr", "a", "Incl", "Rin", "Rout", "z", "kTbb", "logxi", "Afe", "logN",
+                  "refl_frac"],
+    "xillverCO": ["gamma", "A_CO", "kTbb", "frac_pl_bb", "Ecut", "z", "Incl", "refl_frac"],
+    "relxillCO": ["Index1", "Index2", "Rbr", "a", "Incl", "Rin", "Rout", "z", "gamma", "A_CO", "kTbb", "frac_pl_bb",
+                  "Ecut", "refl_frac"],
 }
 
 

@@ -239,11 +239,12 @@ struct PipeOut {
 int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st, const PipeOut *pipe = nullptr) {
   const ModelDef &m = *b->m;
   const DevTables &T = E.tables->dev();
-  const int which = (m.prim == PRIM_NTHCOMP) ? 1 : 0;
+  const int xtab = model_xtab(m);
+  const int which = xtab < 0 ? 0 : xtab;
   const bool relxill = (m.type == T_RELXILL);
   const int ne_line = (m.type == T_LINE) ? b->n_flux : NCONV;
-  const int nex_stride = (relxill || m.type == T_XILL) ? E.tables->xill_host(m.prim).stride : 1;
-  const int n_incl = relxill ? E.tables->xill_host(m.prim).n_incl : 0;
+  const int nex_stride = (relxill || m.type == T_XILL) ? E.tables->xill_host(xtab).stride : 1;
+  const int n_incl = relxill ? E.tables->xill_host(xtab).n_incl : 0;
   const bool xillver = (m.type == T_XILL);
   const bool nth = (relxill || xillver) && m.prim == PRIM_NTHCOMP;
   // the Kompaneets work arrays take 1.4 MB per vector: smaller chunks for the Cp models
@@ -311,7 +312,7 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
     } else {
       tm.begin(); launch_line(vps, T, S, nc, T.econv, NCONV, 0, relxill ? b->nz_max : 1, st); tm.end(KF_LINE);
       if (relxill) {
-        tm.begin(); launch_xill(vps, T, S, nc, which, b->nz_max, E.tables->xill_host(m.prim).n_ener, n_incl, st); tm.end(KF_XILL);
+        tm.begin(); launch_xill(vps, T, S, nc, which, b->nz_max, E.tables->xill_host(xtab).n_ener, n_incl, st); tm.end(KF_XILL);
         tm.begin(); launch_conv(vps, T, S, nc, b->d_energy, b->n_flux, out, E.d_total, which, 0, st); tm.end(KF_CONV);
         if (nth) {
           tm.begin(); launch_prim_nth(vps, T, S, nc, E.d_total, b->d_energy, b->n_flux, out, st); tm.end(KF_PRIMNTH);
@@ -394,11 +395,11 @@ relxill_b200_batch *relxill_b200_prepare(const char *model, const double *energy
   }
   bool want_rr = (m->irrad == EMIS_LP) || E.cfg.env_returnrad == 1;
   std::string err = (m->type == T_XILL)
-                        ? E.tables->require_xill_only(m->prim)
-                        : E.tables->require(m->irrad == EMIS_LP, false, m->type == T_RELXILL ? m->prim : PRIM_NONE);
+                        ? E.tables->require_xill_only(model_xtab(*m))
+                        : E.tables->require(m->irrad == EMIS_LP, false, model_xtab(*m));
   if (!err.empty()) { set_err(err); return nullptr; }
   if (want_rr) {
-    err = E.tables->require(false, true, PRIM_NONE);
+    err = E.tables->require(false, true, XT_NONE);
     // missing table is only an error for the vectors that switch returning radiation on
   }
   auto *b = new relxill_b200_batch();
@@ -564,7 +565,7 @@ int relxill_b200_algorithmic_bytes(relxill_b200_batch *b, double *out8) {
   double sumU = 0, bound = 0;
   double xbytes = 0;
   if (m.type == T_RELXILL && nc > 0) {
-    const XillHost &xh = E.tables->xill_host(m.prim);
+    const XillHost &xh = E.tables->xill_host(model_xtab(m));
     const int ncorn = (xh.npar == 6) ? 32 : 16;
     std::vector<int> rows((size_t) nc * NZMAX * 32);
     cudaMemcpy(rows.data(), E.S.xrow, rows.size() * sizeof(int), cudaMemcpyDeviceToHost);
@@ -651,8 +652,8 @@ int relxill_b200_probe(relxill_b200_batch *b, long iv, const char *what, double 
   } else if (w == "relflux" || w == "xill" || w == "dist") {
     const int nz = vp.nz;
     const size_t len = (w == "relflux") ? (size_t) ((b->m->type == T_LINE) ? b->n_flux : NCONV)
-                       : (w == "xill")  ? (size_t) E.tables->xill_host(b->m->prim).n_ener
-                                        : (size_t) E.tables->xill_host(b->m->prim).n_incl;
+                       : (w == "xill")  ? (size_t) E.tables->xill_host(model_xtab(*b->m)).n_ener
+                                        : (size_t) E.tables->xill_host(model_xtab(*b->m)).n_incl;
     if ((long) (len * nz) > max_len) return -1;
     for (int z = 0; z < nz; z++) {
       const double *p = (w == "relflux") ? S.relflux + (v * S.nz_cap + z) * S.ne_line_cap
@@ -706,5 +707,9 @@ DEF_LMOD(lmodrelxilldensnthcomp, "relxillCp")
 DEF_LMOD(lmodrelxilllpdensnthcomp, "relxilllpCp")
 DEF_LMOD(lmodxillver, "xillver")
 DEF_LMOD(lmodxillverdensnthcomp, "xillverCp")
+DEF_LMOD(lmodxillverns, "xillverNS")
+DEF_LMOD(lmodrelxillns, "relxillNS")
+DEF_LMOD(lmodxillverco, "xillverCO")
+DEF_LMOD(lmodrelxillco, "relxillCO")
 
 }  // extern "C"

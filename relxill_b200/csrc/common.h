@@ -20,9 +20,13 @@ constexpr int NTH_MAX = 900;   // nthcomp photon grid (src/donthcomp.c)
 constexpr int NTH_SOL = 64;    // Kompaneets solves per vector: one per zone + one for the source (<= NZMAX + 1)
 
 enum { EMIS_BKN = 1, EMIS_LP = 2 };
-enum { PRIM_NONE = 0, PRIM_ECUT = 1, PRIM_NTHCOMP = 2 };
+enum { PRIM_NONE = 0, PRIM_ECUT = 1, PRIM_NTHCOMP = 2, PRIM_BB = 3 };   // src/common.h:57-59
+// xillver table flavours (get_xilltable_id, src/xilltable.c:682-694)
+enum { XT_NONE = -1, XT_STD = 0, XT_CP = 1, XT_NS = 2, XT_CO = 3, XT_COUNT = 4 };
 enum { T_LINE = 0, T_CONV = 1, T_XILL = 2, T_RELXILL = 3 };
 enum { ION_CONST = 0, ION_PL = 1, ION_ALPHA = 2 };
+
+enum { REUSE_REL = 1, REUSE_ALL = 2 };
 
 // per-vector status codes (0 = ok)
 enum {
@@ -42,6 +46,7 @@ enum {
 struct VPar {
   double a, incl, emis1, emis2, rbr, rin, rout, lineE, z, height, gamma, beta;
   double gam, afe, lxi, ect, dens, refl_frac, iongrad_index;
+  double ktbb, frac_pl_bb;      // blackbody temperature / power-law fraction axes of the NS and CO tables
   double eshift_obs;            // energy shift source -> observer (1 unless lamp post)
   double doppler_obs;           // doppler_factor_source_obs (lamp post, beta > 1e-4), else 1
   double rms;                   // ISCO
@@ -55,12 +60,13 @@ struct VPar {
   int rr_spin;                  // index into the returning-radiation table (spin >= a), -1 = none
   int status;
   int const_density;            // RELXILL_CONSTANT_DENSITY=1: alpha-disk ionisation gradient with constant density
+  int xtab;                     // xillver table of this model (XT_*)
 };
 
 struct XillDev {
   int npar;               // 5 or 6
   int nvals[6];
-  int pindex[6];          // global parameter id of each table axis (0 gam,1 afe,2 lxi,3 ect/kte,4 dens,7 incl)
+  int pindex[6];          // global parameter id of each table axis (0 gam,1 afe|a_co,2 lxi,3 ect/kte,4 dens,5 kTbb,6 frac,7 incl)
   const float *vals[6];   // device pointers to axis values
   int n_ener, n_incl, stride;  // stride = padded row length in floats
   long nnodes;            // rows / n_incl
@@ -84,8 +90,8 @@ struct DevTables {
   int rr_nspin;
   const double *rr_spin, *rr_rlo, *rr_rhi, *rr_tf, *rr_gmin, *rr_gmax;
   const double *rr_fgl;     // [nspin][RR_NG][RR_NR*RR_NR][2] {frac_g, ln g}
-  // xillver tables, index 0 = cutoff power law, 1 = nthcomp
-  XillDev xill[2];
+  // xillver tables, indexed by XT_STD (cutoff power law), XT_CP (nthcomp), XT_NS, XT_CO
+  XillDev xill[XT_COUNT];
   // fixed grids
   const double *econv;      // [NCONV+1]
   const double *conv_cf;    // [NCONV] E_mid / dE
@@ -132,6 +138,10 @@ struct Scratch {
   double *distpart;                                           // [cap][NR][10] per-radius parts of dist (k_fine -> k_dist)
   double *xillz;                                              // [cap][nz_cap][nex_stride]
   int *status;                                                // [cap]
+  // Re-use of the previous run's device-resident state (api.cu: the arena still holds this batch): per vector,
+  // REUSE_REL = the relativistic half (k_syspar, k_fine, k_dist, k_line outputs) is still valid, REUSE_ALL = the
+  // whole convolution-grid spectrum is.  Null when nothing can be re-used.
+  const unsigned char *reuse;                                 // [cap]
   // nthcomp (allocated only for Cp models): Kompaneets work arrays and solutions, [cap][NTH_MAX][NTH_SOL]
   // with the solve index fastest (coalesced across the threads of a vector's block)
   double *nth_gam, *nth_g, *nth_spt;

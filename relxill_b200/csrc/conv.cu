@@ -317,6 +317,18 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
         if (add_prim) tot += pr;
         acc[i] = tot;
       }
+    } else if (vp.prim_type == PRIM_BB) {   // spec_blackbody (src/Xillspec.cpp:262-269); these flavours have no lamp post
+      const double kt4 = pow(vp.ktbb, 4);
+      for (int i = t; i < NCONV; i += CONV_NT) {
+        const double e0 = T.econv[i], e1 = T.econv[i + 1];
+        const double en = 0.5 * (e0 + e1);
+        double pr = en * en / (kt4 * (exp(en / vp.ktbb) - 1));
+        pr *= (e1 - e0);
+        pr *= nsrc;
+        double tot = acc[i] * refl_scale;
+        if (add_prim) tot += pr;
+        acc[i] = tot;
+      }
     } else {
       for (int i = t; i < NCONV; i += CONV_NT) acc[i] = acc[i] * refl_scale;  // primary added afterwards
     }

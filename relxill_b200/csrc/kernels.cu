@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(256) k_syspar(const VPar *__restrict__ vps, De
   SysSmem &sm = *reinterpret_cast<SysSmem *>(smraw);
   const int v = blockIdx.x, t = threadIdx.x;
   const VPar &vp = vps[v];
+  if (S.reuse && S.reuse[v]) return;   // emissivity, radial grid and status of the previous run stand
   if (pass == 1) {
     if (t == 0) S.status[v] = vp.status;
     if (vp.status != ST_OK) return;
@@ -413,15 +414,38 @@ __device__ void ecut_band_sums(const DevTables &T, const double *powtab, double 
   S2 = a2;
 }
 
+// blackbody primary of the NS flavours (spec_blackbody, src/Xillspec.cpp:262-269) reduced to the same two band sums
+__device__ void bb_band_sums(const DevTables &T, double ktbb, double &S1, double &S2) {
+  const int lane = threadIdx.x & 31;
+  double a1 = 0.0, a2 = 0.0;
+  const double kt4 = pow(ktbb, 4);
+  for (int i = lane; i < NCOARSE; i += 32) {
+    const double e0 = T.ecoarse[i], e1 = T.ecoarse[i + 1];
+    const double en = 0.5 * (e0 + e1);
+    double fl = en * en / (kt4 * (exp(en / ktbb) - 1));
+    fl *= (e1 - e0);
+    const double w = fl * 0.5 * (e0 + e1);
+    if (T.coarse_m1[i]) a1 += w * 1e20 * 1.602177e-09;
+    if (T.coarse_m2[i]) a2 += w;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  S1 = a1;
+  S2 = a2;
+}
+
 __global__ void __launch_bounds__(128) k_zone(const VPar *__restrict__ vps, DevTables T, Scratch S) {
   extern __shared__ __align__(16) unsigned char smraw[];
   ZoneSmem &sm = *reinterpret_cast<ZoneSmem *>(smraw);
   const int v = blockIdx.x, t = threadIdx.x;
   const VPar &vp = vps[v];
   if (S.status[v] != ST_OK) return;
+  if (S.reuse && (S.reuse[v] & REUSE_ALL)) return;
   const int nz = vp.nz;
   const bool alpha = (vp.ion_grad_type == ION_ALPHA);
-  const int nc_all = (T.xill[vp.prim_type == PRIM_NTHCOMP ? 1 : 0].npar == 6) ? 32 : 16;
+  const int nc_all = (T.xill[vp.xtab].npar == 6) ? 32 : 16;
   for (int i = t; i < NR; i += 128) {
     sm.re[i] = S.re[(size_t) v * NR + i];
     sm.y1[i] = S.del_emit[(size_t) v * NR + i];
@@ -501,10 +525,10 @@ __global__ void __launch_bounds__(128) k_zone(const VPar *__restrict__ vps, DevT
     S.zect[(size_t) v * NZMAX + t] = sm.ect[t];
 
     // xillver corner nodes + weights of this zone
-    const XillDev &X = T.xill[vp.prim_type == PRIM_NTHCOMP ? 1 : 0];
+    const XillDev &X = T.xill[vp.xtab];
     float inp[8];
     inp[0] = (float) vp.gam; inp[1] = (float) vp.afe; inp[2] = (float) lxi; inp[3] = (float) sm.ect[t];
-    inp[4] = (float) dens; inp[5] = 0.f; inp[6] = 0.f; inp[7] = 0.f;
+    inp[4] = (float) dens; inp[5] = (float) vp.ktbb; inp[6] = (float) vp.frac_pl_bb; inp[7] = 0.f;
     int ind[6];
     double fac[6];
     const int nax = X.npar - 1;  // all axes but the inclination
@@ -518,9 +542,10 @@ __global__ void __launch_bounds__(128) k_zone(const VPar *__restrict__ vps, DevT
       const float lo = X.vals[i][0], hi = X.vals[i][n - 1];
       if (val < lo) val = lo; else if (val > hi) val = hi;
       fac[i] = (double) ((val - X.vals[i][k]) / (X.vals[i][k + 1] - X.vals[i][k]));
-      if (pind == 3) {  // ensure_ecut_within_boundarys
-        if (sm.ect[t] <= (double) lo) fac[i] = 0.0;
-        if (sm.ect[t] >= (double) hi) fac[i] = 1.0;
+      if (pind == 3) {  // ensure_ecut_within_boundarys (src/xilltable.c:1054-1067): the reference looks the limits up on table
+                        // axis number 3 (the global Ecut id), which is the Ecut axis itself except in the CO table
+        if (sm.ect[t] <= (double) X.vals[3][0]) fac[i] = 0.0;
+        if (sm.ect[t] >= (double) X.vals[3][X.nvals[3] - 1]) fac[i] = 1.0;
       }
     }
     const int off = (X.npar == 6) ? 1 : 0;
@@ -553,7 +578,7 @@ __global__ void __launch_bounds__(128) k_zone(const VPar *__restrict__ vps, DevT
   // offset, xwsort[zone][slot] = weight.
   const int n_rest = nc_all / 4;
   if (t < nz) {
-    const XillDev &X = T.xill[vp.prim_type == PRIM_NTHCOMP ? 1 : 0];
+    const XillDev &X = T.xill[vp.xtab];
     const int nax = X.npar - 1;
     long stride[6];
     long acc_s = 1;
@@ -561,7 +586,7 @@ __global__ void __launch_bounds__(128) k_zone(const VPar *__restrict__ vps, DevT
     // recompute this zone's bracket (same arithmetic as above) for the zone-varying axes
     float inp[8];
     inp[0] = (float) vp.gam; inp[1] = (float) vp.afe; inp[2] = (float) sm.lxi[t]; inp[3] = (float) sm.ect[t];
-    inp[4] = (float) sm.dens[t]; inp[5] = 0.f; inp[6] = 0.f; inp[7] = 0.f;
+    inp[4] = (float) sm.dens[t]; inp[5] = (float) vp.ktbb; inp[6] = (float) vp.frac_pl_bb; inp[7] = 0.f;
     int ind[6];
     double fac[6];
     for (int i = 0; i < nax; i++) {
@@ -575,14 +600,16 @@ __global__ void __launch_bounds__(128) k_zone(const VPar *__restrict__ vps, DevT
       if (val < lo) val = lo; else if (val > hi) val = hi;
       fac[i] = (double) ((val - X.vals[i][k]) / (X.vals[i][k + 1] - X.vals[i][k]));
       if (pind == 3) {
-        if (sm.ect[t] <= (double) lo) fac[i] = 0.0;
-        if (sm.ect[t] >= (double) hi) fac[i] = 1.0;
+        if (sm.ect[t] <= (double) X.vals[3][0]) fac[i] = 0.0;
+        if (sm.ect[t] >= (double) X.vals[3][X.nvals[3] - 1]) fac[i] = 1.0;
       }
     }
-    // axes: the two vector-level ones (Gamma, A_Fe) and the zone-level rest
-    int ax_v[2], ax_r[3], nv = 0, nr = 0;
+    // axes: two vector-level ones (the first two whose parameter cannot change from zone to zone: Gamma and A_Fe,
+    // kTbb and A_Fe for the NS table, Gamma and A_CO for the CO table) and the rest (logXi, Ecut|kTe, Dens, ...)
+    int ax_v[2], ax_r[4], nv = 0, nr = 0;
     for (int i = 0; i < nax; i++) {
-      if (X.pindex[i] == 0 || X.pindex[i] == 1) ax_v[nv++] = i; else ax_r[nr++] = i;
+      const int pi = X.pindex[i];
+      if (nv < 2 && pi != 2 && pi != 3 && pi != 4) ax_v[nv++] = i; else ax_r[nr++] = i;
     }
     for (int c = 0; c < n_rest; c++) {
       long off = 0;
@@ -611,17 +638,18 @@ __global__ void __launch_bounds__(128) k_zone(const VPar *__restrict__ vps, DevT
   if (t == 0) S.xn[v] = n_rest;
   // primary-spectrum normalisations: one warp per (zone | source); cutoff power law only here,
   // the nthcomp variant lives in k_zone_nthcomp
-  if (vp.prim_type == PRIM_ECUT) {
+  if (vp.prim_type == PRIM_ECUT || vp.prim_type == PRIM_BB) {
+    const bool bb = (vp.prim_type == PRIM_BB);
     for (int i = t; i < NCOARSE; i += 128) {
       const double en = 0.5 * (T.ecoarse[i] + T.ecoarse[i + 1]);
-      sm.powtab[i] = pow(en, -vp.gam);
+      sm.powtab[i] = bb ? 0.0 : pow(en, -vp.gam);
     }
     __syncthreads();
     const int warp = t >> 5, lane = t & 31;
     for (int job = warp; job <= nz; job += 4) {
       const double ecut = (job < nz) ? sm.ect[job] : vp.ect;
       double S1, S2;
-      ecut_band_sums(T, sm.powtab, ecut, S1, S2);
+      if (bb) bb_band_sums(T, vp.ktbb, S1, S2); else ecut_band_sums(T, sm.powtab, ecut, S1, S2);
       if (lane == 0) {
         const double norm = S1 / (1e15 / 4.0 / PI);
         sm.nfac[job] = 1. / norm;
@@ -633,7 +661,7 @@ __global__ void __launch_bounds__(128) k_zone(const VPar *__restrict__ vps, DevT
     if (t < nz) {
       S.normch[(size_t) v * NZMAX + t] = sm.nfac[t] / sm.nfac[nz];
       if (vp.do_corr) {
-        const XillDev &X = T.xill[0];
+        const XillDev &X = T.xill[vp.xtab];
         const int *xr = S.xrow + ((size_t) v * NZMAX + t) * 32;
         const double *xw = S.xw + ((size_t) v * NZMAX + t) * 32;
         double ef = 0.0, p1 = 0.0, p2 = 0.0;
@@ -749,6 +777,7 @@ __global__ void __launch_bounds__(320) k_fine(const VPar *__restrict__ vps, DevT
 __global__ void __launch_bounds__(256) k_dist(const VPar *__restrict__ vps, DevTables T, Scratch S, int n_incl) {
   const int v = blockIdx.x, t = threadIdx.x;
   if (S.status[v] != ST_OK) return;
+  if (S.reuse && S.reuse[v]) return;
   const VPar &vp = vps[v];
   const double *part = S.distpart + (size_t) v * NR * 10;
   const int *zfirst = S.zfirst + (size_t) v * (NZMAX + 1);
@@ -818,7 +847,7 @@ __global__ void __launch_bounds__(256) k_xillver(const VPar *__restrict__ vps, D
   if (t == 0) {
     float inp[8];
     inp[0] = (float) vp.gam; inp[1] = (float) vp.afe; inp[2] = (float) vp.lxi; inp[3] = (float) vp.ect;
-    inp[4] = (float) vp.dens; inp[5] = 0.f; inp[6] = 0.f; inp[7] = (float) vp.xincl;
+    inp[4] = (float) vp.dens; inp[5] = (float) vp.ktbb; inp[6] = (float) vp.frac_pl_bb; inp[7] = (float) vp.xincl;
     int ind[6];
     double fac[6];
     for (int i = 0; i < X.npar; i++) {
@@ -831,9 +860,9 @@ __global__ void __launch_bounds__(256) k_xillver(const VPar *__restrict__ vps, D
       const float lo = X.vals[i][0], hi = X.vals[i][n - 1];
       if (val < lo) val = lo; else if (val > hi) val = hi;
       fac[i] = (double) ((val - X.vals[i][k]) / (X.vals[i][k + 1] - X.vals[i][k]));
-      if (pind == 3) {
-        if (vp.ect <= (double) lo) fac[i] = 0.0;
-        if (vp.ect >= (double) hi) fac[i] = 1.0;
+      if (pind == 3) {   // limits from table axis number 3, like the reference (see k_zone)
+        if (vp.ect <= (double) X.vals[3][0]) fac[i] = 0.0;
+        if (vp.ect >= (double) X.vals[3][X.nvals[3] - 1]) fac[i] = 1.0;
       }
     }
     const int off = (X.npar == 6) ? 1 : 0;
@@ -858,9 +887,9 @@ __global__ void __launch_bounds__(256) k_xillver(const VPar *__restrict__ vps, D
   if (vp.prim_type == PRIM_ECUT)
     for (int i = t; i < NCOARSE; i += 256) s_pow[i] = pow(0.5 * (T.ecoarse[i] + T.ecoarse[i + 1]), -vp.gam);
   __syncthreads();
-  if (vp.prim_type == PRIM_ECUT && t < 32) {
+  if ((vp.prim_type == PRIM_ECUT || vp.prim_type == PRIM_BB) && t < 32) {
     double S1, S2;
-    ecut_band_sums(T, s_pow, vp.ect, S1, S2);
+    if (vp.prim_type == PRIM_BB) bb_band_sums(T, vp.ktbb, S1, S2); else ecut_band_sums(T, s_pow, vp.ect, S1, S2);
     if (t == 0) { s_nsrc = 1. / (S1 / (1e15 / 4.0 / PI)); S.nsrc[v] = s_nsrc; }
   }
   const double slab = 0.5 * cos(vp.xincl * PI / 180);
@@ -876,15 +905,22 @@ __global__ void __launch_bounds__(256) k_xillver(const VPar *__restrict__ vps, D
   }
   __syncthreads();
   const double rfa = fabs(vp.refl_frac);
-  const bool add_prim = (vp.refl_frac >= 0) && (vp.prim_type == PRIM_ECUT);
-  const double ex0 = exp(1.0 / vp.ect);
+  const bool add_prim = (vp.refl_frac >= 0) && (vp.prim_type == PRIM_ECUT || vp.prim_type == PRIM_BB);
+  const bool bb = (vp.prim_type == PRIM_BB);
+  const double ex0 = exp(1.0 / vp.ect), kt4 = pow(vp.ktbb, 4);
   for (int j = t; j < n_flux; j += 256) {
     double elo = user_e[j], ehi = user_e[j + 1];
     if (vp.z > 0) { elo *= (1 + vp.z); ehi *= (1 + vp.z); }
     double f = rebin_bin(elo, ehi, X.ener, fx, ne) * rfa;
     if (add_prim) {
       const double en = 0.5 * (elo + ehi);
-      double pr = ex0 * pow(en, -vp.gam) * exp(-en / vp.ect) * (ehi - elo);
+      double pr;
+      if (bb) {
+        pr = en * en / (kt4 * (exp(en / vp.ktbb) - 1));
+        pr *= (ehi - elo);
+      } else {
+        pr = ex0 * pow(en, -vp.gam) * exp(-en / vp.ect) * (ehi - elo);
+      }
       pr *= s_nsrc;
       f += pr;
     }

@@ -48,6 +48,20 @@ static const ModelDef MODELS[] = {
      {P_INCL, P_A, P_RIN, P_ROUT, P_H, P_BETA, P_GAMMA, P_LOGXI, P_LOGN, P_AFE, P_KTE, P_REFLFRAC, P_Z,
       P_IONGRAD_INDEX, P_IONGRAD_TYPE, P_SWITCH_RETURNRAD, P_SWITCH_REFLFRAC_BOOST},
      {30., 0.998, -1., 400., 6.0, 0.0, 2., 3.1, 15., 1., 60., 1., 0., 0.0, 0., 1., 0.}},
+    // neutron-star (blackbody-irradiated) and CO flavours: lmodel_relxill_public.dat:131-153, lmodel_relxill_devel.dat:1-25
+    {"xillverNS", "lmodxillverns", T_XILL, 0, PRIM_BB, -101, 7,
+     {P_KTBB, P_AFE, P_LOGN, P_LOGXI, P_Z, P_INCL, P_REFLFRAC},
+     {2., 1., 15., 3.1, 0., 30., -1.}},
+    {"relxillNS", "lmodrelxillns", T_RELXILL, EMIS_BKN, PRIM_BB, -30, 13,
+     {P_INDEX1, P_INDEX2, P_RBR, P_A, P_INCL, P_RIN, P_ROUT, P_Z, P_KTBB, P_LOGXI, P_AFE, P_LOGN, P_REFLFRAC},
+     {3., 3., 15.0, 0.998, 30., -1., 400., 0., 2., 3.1, 1., 15., 3.}},
+    {"xillverCO", "lmodxillverco", T_XILL, 0, PRIM_ECUT, -210, 8,
+     {P_GAMMA, P_ACO, P_KTBB, P_FRAC_PL_BB, P_ECUT, P_Z, P_INCL, P_REFLFRAC},
+     {2., 5., 0.1, 0.01, 300., 0., 45., -1.}},
+    {"relxillCO", "lmodrelxillco", T_RELXILL, EMIS_BKN, PRIM_ECUT, -200, 14,
+     {P_INDEX1, P_INDEX2, P_RBR, P_A, P_INCL, P_RIN, P_ROUT, P_Z, P_GAMMA, P_ACO, P_KTBB, P_FRAC_PL_BB, P_ECUT,
+      P_REFLFRAC},
+     {3., 3., 15.0, 0.998, 30., -1., 400., 0., 2., 5., 0.1, 0.01, 300., 3.}},
 };
 
 int num_models() { return (int) (sizeof(MODELS) / sizeof(MODELS[0])); }
@@ -56,6 +70,15 @@ const ModelDef *find_model(const char *name) {
   for (int i = 0; i < num_models(); i++)
     if (std::strcmp(MODELS[i].name, name) == 0 || std::strcmp(MODELS[i].symbol, name) == 0) return &MODELS[i];
   return nullptr;
+}
+
+static bool is_ns_model(int model_type) { return model_type == -30 || model_type == -101; }    // src/relutility.c:95-101
+static bool is_co_model(int model_type) { return model_type == -200 || model_type == -210; }  // :103-109
+int model_xtab(const ModelDef &m) {
+  if (m.type != T_XILL && m.type != T_RELXILL) return XT_NONE;
+  if (is_ns_model(m.model_type)) return XT_NS;
+  if (is_co_model(m.model_type)) return XT_CO;
+  return (m.prim == PRIM_NTHCOMP) ? XT_CP : XT_STD;
 }
 
 double kerr_rms(double a) {
@@ -129,10 +152,13 @@ void interpret_params(const ModelDef &m, const double *par, const HostConfig &cf
   vp.const_density = cfg.env_const_density;
 
   // xillver-side parameters
-  vp.afe = v[P_AFE];
+  vp.xtab = model_xtab(m);
+  vp.afe = is_co_model(m.model_type) ? v[P_ACO] : v[P_AFE];   // src/ModelDefinition.cpp:347-349
+  vp.ktbb = v[P_KTBB];
+  vp.frac_pl_bb = v[P_FRAC_PL_BB];
   vp.ect = (m.prim == PRIM_NTHCOMP) ? (has[P_KTE] ? v[P_KTE] : 0.0) : (has[P_ECUT] ? v[P_ECUT] : 300.0);
   vp.lxi = has[P_LOGXI] ? v[P_LOGXI] : 0.0;
-  vp.dens = has[P_LOGN] ? v[P_LOGN] : 15.0;
+  vp.dens = has[P_LOGN] ? v[P_LOGN] : (is_co_model(m.model_type) ? 17.0 : 15.0);   // :362-363
   vp.iongrad_index = v[P_IONGRAD_INDEX];
   vp.gam = v[P_GAMMA];
   vp.refl_frac = v[P_REFLFRAC];

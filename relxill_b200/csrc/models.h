@@ -8,7 +8,7 @@ namespace rx {
 enum XPar {
   P_LINEE, P_INDEX1, P_INDEX2, P_RBR, P_A, P_RIN, P_ROUT, P_INCL, P_Z, P_LIMB, P_GAMMA, P_LOGXI, P_LOGN, P_AFE,
   P_ECUT, P_KTE, P_REFLFRAC, P_H, P_BETA, P_IONGRAD_INDEX, P_IONGRAD_TYPE, P_SWITCH_RETURNRAD,
-  P_SWITCH_REFLFRAC_BOOST, P_COUNT
+  P_SWITCH_REFLFRAC_BOOST, P_KTBB, P_ACO, P_FRAC_PL_BB, P_COUNT
 };
 
 struct ModelDef {
@@ -29,6 +29,8 @@ struct HostConfig {
 };
 
 const ModelDef *find_model(const char *name);
+// xillver table a model reads (XT_NONE for the line / convolution models)
+int model_xtab(const ModelDef &m);
 int num_models();
 const ModelDef *model_at(int i);
 

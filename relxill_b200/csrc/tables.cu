@@ -314,6 +314,9 @@ static int xill_param_id(const char *name) {  // src/common.h:141-161
   if (!strcmp(name, "logXi")) return 2;
   if (!strcmp(name, "Ecut") || !strcmp(name, "kTe")) return 3;
   if (!strcmp(name, "Dens")) return 4;
+  if (!strcmp(name, "kTbb")) return 5;
+  if (!strcmp(name, "A_CO")) return 1;   // PARAM_ACO == PARAM_AFE
+  if (!strcmp(name, "Frac")) return 6;
   if (!strcmp(name, "Incl")) return 7;
   return -1;
 }
@@ -322,7 +325,8 @@ std::string Tables::load_xill(int which) {
   XillHost &xh = xh_[which];
   if (xh.loaded) return "";
   load_fixed();
-  const std::string path = dir_ + (which == 1 ? "/xillverCp_v3.4.fits" : "/xillver-a-Ec5.fits");
+  static const char *const names[XT_COUNT] = {"/xillver-a-Ec5.fits", "/xillverCp_v3.4.fits", "/xillverNS-2.fits", "/xillverCO.fits"};   // src/common.h:165-168
+  const std::string path = dir_ + names[which];
   mf_file *f = mf_open(path.c_str());
   if (!f) return "cannot open " + path;
   const int hp = mf_find_hdu(f, "PARAMETERS"), he = mf_find_hdu(f, "ENERGIES"), hs = mf_find_hdu(f, "SPECTRA");
@@ -387,7 +391,9 @@ std::string Tables::load_xill(int which) {
       int idx[6] = {0};
       for (int i = xh.npar - 2; i >= 0; i--) { idx[i] = (int) (rem % xh.nvals[i]); rem /= xh.nvals[i]; }
       const double lxi = (ax_lxi >= 0) ? (double) xh.vals[ax_lxi][idx[ax_lxi]] : 0.0;
-      const double dens = (ax_dns >= 0) ? (double) xh.vals[ax_dns][idx[ax_dns]] : 15.0;
+      // an axis the table lacks takes the model's fixed value (getDefaultLogxi / getDefaultDensity, src/xilltable.c:566-573):
+      // logxi 0; logN 17 for the CO table, else 15 (src/ModelDefinition.cpp:361-363)
+      const double dens = (ax_dns >= 0) ? (double) xh.vals[ax_dns][idx[ax_dns]] : (which == XT_CO ? 17.0 : 15.0);
       const double pl = std::pow(10, lxi), pd = std::pow(10, dens - 15);
       const bool do_d = std::fabs(dens - 15) > 1e-6;
       for (int e = 0; e < ne; e++) avg[e] = 0.0;
@@ -576,22 +582,21 @@ std::string Tables::load(const std::string &dir) {
   return "";   // the tables themselves are loaded on first use by the model flavour that needs them
 }
 
-std::string Tables::require_xill_only(int prim_type) {
+std::string Tables::require_xill_only(int xtab) {
   load_fixed();
-  std::string err = load_xill(prim_type == PRIM_NTHCOMP ? 1 : 0);
+  std::string err = load_xill(xtab);
   if (!err.empty()) return err;
-  if (prim_type == PRIM_NTHCOMP) load_nthcomp();
+  if (xtab == XT_CP) load_nthcomp();
   return "";
 }
 
-std::string Tables::require(bool lp, bool rrad, int prim_type) {
+std::string Tables::require(bool lp, bool rrad, int xtab) {
   std::string err = load_rel();
   if (!err.empty()) return err;
   if (lp && !(err = load_lp()).empty()) return err;
   if (rrad && !(err = load_rrad()).empty()) return err;
-  if (prim_type == PRIM_ECUT && !(err = load_xill(0)).empty()) return err;
-  if (prim_type == PRIM_NTHCOMP && !(err = load_xill(1)).empty()) return err;
-  if (prim_type == PRIM_NTHCOMP) load_nthcomp();
+  if (xtab != XT_NONE && !(err = load_xill(xtab)).empty()) return err;
+  if (xtab == XT_CP) load_nthcomp();
   return "";
 }
 

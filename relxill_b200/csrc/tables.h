@@ -22,11 +22,11 @@ class Tables {
   // loads rel + (optionally) lp / rrad / xillver tables that exist in dir; returns "" or an error message
   std::string load(const std::string &dir);
   // lazily make sure the table needed by a model flavour is there
-  std::string require(bool lp, bool rrad, int prim_type);
-  std::string require_xill_only(int prim_type);  // standalone xillver models need no relativistic table
+  std::string require(bool lp, bool rrad, int xtab);   // xtab: XT_* or XT_NONE
+  std::string require_xill_only(int xtab);  // standalone xillver models need no relativistic table
   const DevTables &dev() const { return dt_; }
   const std::vector<double> &rr_spins() const { return rr_spin_; }
-  const XillHost &xill_host(int prim_type) const { return xh_[prim_type == PRIM_NTHCOMP ? 1 : 0]; }
+  const XillHost &xill_host(int xtab) const { return xh_[xtab]; }
   bool has_rel() const { return have_rel_; }
   const std::vector<double> &econv() const { return econv_; }
   size_t device_bytes() const { return dev_bytes_; }
@@ -36,7 +36,7 @@ class Tables {
   std::string dir_;
   DevTables dt_{};
   bool have_rel_ = false, have_lp_ = false, have_rr_ = false, have_fixed_ = false, have_nth_ = false;
-  XillHost xh_[2];
+  XillHost xh_[XT_COUNT];
   std::vector<double> rr_spin_, econv_, ecoarse_;
   std::vector<void *> allocs_;
   size_t dev_bytes_ = 0;

@@ -12,8 +12,10 @@ from common import PEAK_FLOOR, RTOL, default_grid, relerr, sample_params, walker
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz")
+GOLDEN_NSCO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2_nsco.npz")
+NSCO_MODELS = ["xillverNS", "relxillNS", "xillverCO", "relxillCO"]
 GPU_MODELS = ["relline", "relline_lp", "relconv", "relconv_lp", "relxill", "relxilllp", "relxillCp", "relxilllpCp",
-              "xillver", "xillverCp"]
+              "xillver", "xillverCp"] + NSCO_MODELS
 
 
 def _conv_input(e):
@@ -22,7 +24,7 @@ def _conv_input(e):
 
 @pytest.mark.parametrize("model", GPU_MODELS)
 def test_vs_golden_reference_vectors(rx, model):
-    g = np.load(GOLDEN)
+    g = np.load(GOLDEN_NSCO if model in NSCO_MODELS else GOLDEN)
     e, P, F = g["energy"], g[f"{model}_params"], g[f"{model}_flux"]
     rx.set_num_zones(None)
     fin = g["conv_input"] if model.startswith("relconv") else None
