@@ -61,6 +61,7 @@ def workload_config(args, world):
         "bins": args.bins, "tables": f"synthetic '{args.tables}' size",
         "parallelism": f"parameter-vector sharding x{world}, NCCL all-gather of the spectra",
         "l2": "flushed between timed steps (256 MiB write)",
+        "state_cache": "off (every step recomputes every vector)",
     }
 
 
@@ -273,6 +274,7 @@ def run_ours(args):
     tdir = make_tables(args, local)
     rx.init(tdir, local)
     rx.set_num_zones(args.zones)
+    rx.set_cache(False)   # every timed step recomputes every vector; the state cache is measured separately below
     energy = default_grid(args.bins)
     n, nb = args.batch, args.bins
     params = walker_ball(args.model, n, seed=4321 + rank)
@@ -399,6 +401,30 @@ def run_ours(args):
         hbm_stage["frac"] = hbm_stage["achieved"] / peak
         hbm_stage["frac_of_upper_bound_traffic"] = (ab["xillver_upper_bound"] + n * nz * nex * 8.0) / (xk[0] * 1e-3) / 1e9 / peak
 
+    # ---- supplemental: the device-resident state cache on an MCMC-like sequence in which half of the walkers stay where
+    #      they were (rejected proposals) from one step to the next.  Not the headline: `value`/`e2e` run with it off.
+    state_cache = None
+    try:
+        rx.set_cache(True)
+        moved = params.copy()
+        moved[::2] = walker_ball(args.model, n, seed=991 + rank)[::2]
+        seqs = [moved, params, moved, params]
+        batch.run(out.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for q in seqs:
+            batch.update_params(q)
+            batch.run(out.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        dt_c = time.perf_counter() - t0
+        state_cache = {"value": n * len(seqs) / dt_c, "unit": UNIT, "reuse_last_step": batch.reuse_counts(),
+                       "scenario": "update_params + run per step, every second walker unchanged since the previous step "
+                                   "(host interpretation and H2D of the parameters included)"}
+    except Exception as exc:  # noqa: BLE001
+        state_cache = {"error": str(exc)}
+    finally:
+        rx.set_cache(False)
+
     cpu = None
     if not args.no_cpu_baseline:
         from oracle import pyref
@@ -421,7 +447,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(n * nb * 8 + n * 4), "steps": e2e_steps,
                 "api": "relxill_batch_eval (C ABI) with pinned host buffers"},
         "gpu_launches": int(launches), "roofline": roofline, "hbm_stage": hbm_stage, "cpu_baseline": cpu,
-        "kernels_ms": {k: round(v[0], 3) for k, v in ktimes.items()},
+        "kernels_ms": {k: round(v[0], 3) for k, v in ktimes.items()}, "state_cache": state_cache,
     }
     print(json.dumps(line))
     if world > 1:

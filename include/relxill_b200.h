@@ -86,6 +86,21 @@ typedef struct relxill_b200_batch relxill_b200_batch;
 relxill_b200_batch *relxill_b200_prepare(const char *model, const double *energy, int n_flux,
                                          const double *params, long n_vec);
 int relxill_b200_run(relxill_b200_batch *b, double *d_flux, void *stream);
+/* Device-resident state cache (the reference's Relcache / specCache / RelxillCache, src/Relcache.cpp,
+ * src/Relbase.cpp:143-168, src/Relxill.cpp:296-300,405, as a device-resident re-use of the previous run):
+ * after a run the scratch arena still holds the batch's intermediates.  Update the parameters (same model,
+ * same n_vec) and/or the energy grid in place and run again: a vector whose whole parameter set is unchanged
+ * (z aside) only repeats the final rebin, one whose relativistic parameters are unchanged keeps its line
+ * profiles and emission-angle distribution and repeats only the xillver half.  The results are bit-identical
+ * to a fresh evaluation.  State survives only while no other batch has used the arena in between and the
+ * batch ran in one piece (n_vec <= the chunk capacity).  relxill_batch_eval and the lmod* symbols keep their
+ * last batch alive for the same purpose (an XSPEC fit varies one parameter at a time). */
+int relxill_b200_update_params(relxill_b200_batch *b, const double *params /* [n_vec][npar] */);
+int relxill_b200_update_energy(relxill_b200_batch *b, const double *energy, int n_flux);
+/* vectors of the last run that were {recomputed, re-used the relativistic half, re-used everything} */
+int relxill_b200_reuse_counts(relxill_b200_batch *b, long *out3);
+/* switch the re-use off (0) / on (1, default); measurements of the full path switch it off */
+void relxill_b200_set_cache(int on);
 /* per-vector status after prepare/run (host copy), length n_vec */
 int relxill_b200_batch_status(relxill_b200_batch *b, int *status);
 void relxill_b200_free_batch(relxill_b200_batch *b);

@@ -36,7 +36,8 @@ ABI_SYMBOLS = [
     "relxill_b200_default_params", "relxill_b200_last_error", "relxill_batch_eval", "relxill_batch_eval_device",
     "relxill_b200_prepare", "relxill_b200_run", "relxill_b200_batch_status", "relxill_b200_free_batch",
     "relxill_b200_algorithmic_bytes", "relxill_b200_last_launches", "relxill_b200_set_profiling", "relxill_b200_keep_intermediates",
-    "relxill_b200_kernel_times", "relxill_b200_probe",
+    "relxill_b200_kernel_times", "relxill_b200_probe", "relxill_b200_update_params", "relxill_b200_update_energy",
+    "relxill_b200_reuse_counts", "relxill_b200_set_cache",
 ] + sorted(LMOD_SYMBOLS.values())
 
 
@@ -74,6 +75,13 @@ def lib() -> C.CDLL:
     L.relxill_b200_kernel_times.restype = C.c_int
     L.relxill_b200_probe.argtypes = [C.c_void_p, C.c_long, C.c_char_p, _dp, C.c_long]
     L.relxill_b200_probe.restype = C.c_int
+    L.relxill_b200_update_params.argtypes = [C.c_void_p, _dp]
+    L.relxill_b200_update_params.restype = C.c_int
+    L.relxill_b200_update_energy.argtypes = [C.c_void_p, _dp, C.c_int]
+    L.relxill_b200_update_energy.restype = C.c_int
+    L.relxill_b200_reuse_counts.argtypes = [C.c_void_p, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]
+    L.relxill_b200_reuse_counts.restype = C.c_int
+    L.relxill_b200_set_cache.argtypes = [C.c_int]
     for sym in LMOD_SYMBOLS.values():
         f = getattr(L, sym)
         f.argtypes = [_dp, C.c_int, _dp, C.c_int, _dp, C.c_void_p, C.c_char_p]

@@ -64,6 +64,11 @@ def set_num_zones(n: int | None) -> None:
     _lib.lib().relxill_b200_set_num_zones(int(n) if n else 0)
 
 
+def set_cache(on: bool) -> None:
+    """Device-resident state cache (re-use of the previous run's intermediates, include/relxill_b200.h); on by default."""
+    _lib.lib().relxill_b200_set_cache(1 if on else 0)
+
+
 def num_params(model: str) -> int:
     n = _lib.lib().relxill_b200_num_params(model.encode())
     if n < 0:
@@ -133,6 +138,26 @@ class Batch:
                 _lib.lib().relxill_b200_keep_intermediates(0)
         if rc != 0:
             raise ModelEvalFailed(f"run({self.model}) failed: {_lib.last_error()}")
+
+    def update_params(self, params) -> None:
+        """New parameter vectors for the same model and batch size; the next run re-uses what they leave valid."""
+        params = np.ascontiguousarray(np.atleast_2d(params), np.float64)
+        if params.shape != self.params.shape:
+            raise ValueError("update_params: shape must stay the same")
+        self.params = params
+        if _lib.lib().relxill_b200_update_params(self._h, self.params) != 0:
+            raise ModelEvalFailed(f"update_params({self.model}) failed: {_lib.last_error()}")
+
+    def update_energy(self, energy) -> None:
+        self.energy = np.ascontiguousarray(energy, np.float64)
+        self.n_flux = self.energy.size - 1
+        if _lib.lib().relxill_b200_update_energy(self._h, self.energy, self.n_flux) != 0:
+            raise ModelEvalFailed(f"update_energy({self.model}) failed: {_lib.last_error()}")
+
+    def reuse_counts(self) -> dict:
+        out = np.zeros(3, np.int64)
+        _lib.lib().relxill_b200_reuse_counts(self._h, out)
+        return dict(recomputed=int(out[0]), reused_rel=int(out[1]), reused_all=int(out[2]))
 
     def status(self) -> np.ndarray:
         st = np.zeros(self.n, np.int32)

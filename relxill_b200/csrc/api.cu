@@ -26,6 +26,8 @@
 
 using namespace rx;
 
+struct relxill_b200_batch;
+
 namespace {
 
 thread_local std::string g_err;
@@ -64,6 +66,12 @@ struct Engine {
   bool keep_intermediates = false;   // store what only the test probes read (emission-angle tables)
   // device buffers recycled between batches (cudaMalloc/cudaFree synchronise and cost milliseconds)
   std::vector<std::pair<size_t, void *>> pool;
+  // Device-resident state cache.  The scratch arena keeps the intermediates of the batch that
+  // ran last in one piece (arena_owner = that batch's uid); when the same batch runs again with updated parameters,
+  // vectors whose relativistic half / whole parameter set is unchanged re-use their rows instead of recomputing them.
+  bool cache_on = true;
+  unsigned long arena_owner = 0, next_uid = 1;
+  relxill_b200_batch *retained = nullptr;   // the batch of the last host-buffer call (what an XSPEC fit re-evaluates)
 };
 Engine g_eng;
 
@@ -89,6 +97,7 @@ void pool_put(Engine &E, void *p, size_t bytes) {
 }
 
 void free_scratch(Engine &E) {
+  E.arena_owner = 0;   // whatever state the arena held is gone
   for (void *p : E.scratch_allocs) cudaFree(p);
   E.scratch_allocs.clear();
   E.S = Scratch{};
@@ -199,6 +208,14 @@ struct relxill_b200_batch {
   long last_chunk0 = 0, last_chunk_n = 0;
   double kt_ms[KF_COUNT] = {0};
   long kt_n[KF_COUNT] = {0};
+  // state cache: identity, the parameters the arena rows were computed from, per-vector re-use flags of the last run
+  unsigned long uid = 0;
+  std::vector<VPar> state_vps;
+  bool state_valid = false;
+  std::vector<unsigned char> reuse;
+  unsigned char *d_reuse = nullptr;
+  long n_reuse_rel = 0, n_reuse_all = 0;
+  std::vector<double> energy;   // host copy of the grid (retained batches compare it)
 };
 
 namespace {
@@ -250,7 +267,7 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
   // the Kompaneets work arrays take 1.4 MB per vector: smaller chunks for the Cp models
   const long cap = std::min(b->n, nth ? std::min<long>(E.max_chunk, 2048) : E.max_chunk);
   if (ensure_scratch(E, cap, b->nz_max, ne_line, nex_stride, nth)) return -2;
-  const Scratch &S = E.S;
+  Scratch S = E.S;
   b->launches = 0;
   for (int k = 0; k < KF_COUNT; k++) { b->kt_ms[k] = 0; b->kt_n[k] = 0; }
   Timer tm(E, b, st);
@@ -263,6 +280,28 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
     if (first == 0) first = std::min(piece, b->n);
     for (long c0 = 0, nc = first; c0 < b->n; c0 += nc, nc = std::min(piece, b->n - c0)) piece_n.push_back(nc);
   }
+  // ---- state cache: which vectors can keep the rows the arena still holds for them
+  const bool one_piece = piece_n.size() == 1;
+  b->n_reuse_rel = b->n_reuse_all = 0;
+  S.reuse = nullptr;
+  if (E.cache_on && one_piece && b->state_valid && E.arena_owner == b->uid && b->d_reuse && !E.keep_intermediates &&
+      (m.type == T_RELXILL || m.type == T_CONV || m.type == T_LINE)) {
+    b->reuse.resize(b->n);
+    long any = 0;
+    for (long i = 0; i < b->n; i++) {
+      int f = reusable_state(b->state_vps[i], b->vps[i]);
+      if (m.type != T_RELXILL) f &= REUSE_REL;
+      b->reuse[i] = (unsigned char) f;
+      if (f & REUSE_ALL) b->n_reuse_all++; else if (f & REUSE_REL) b->n_reuse_rel++;
+      any += f != 0;
+    }
+    if (any) {
+      CK(cudaMemcpyAsync(b->d_reuse, b->reuse.data(), b->n, cudaMemcpyHostToDevice, st));
+      S.reuse = b->d_reuse;
+    }
+  }
+  b->state_valid = false;   // until this run has been enqueued completely
+  E.arena_owner = 0;
   std::vector<cudaEvent_t> ev(pipe ? piece_n.size() : 0);
   for (auto &e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   auto copy_piece = [&](size_t k, long c0, long nc) {
@@ -332,7 +371,59 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
     for (auto &e : ev) cudaEventDestroy(e);
   }
   CK(cudaGetLastError());
+  if (one_piece && !xillver) {   // the arena now holds this batch's state
+    b->state_vps = b->vps;
+    b->state_valid = true;
+    E.arena_owner = b->uid;
+  }
   return 0;
+}
+
+}  // namespace
+
+namespace {
+
+// host-side interpretation of the raw parameter vectors (spread over a few threads for large batches) and the
+// batch-level switches derived from it
+void interpret_all(Engine &E, relxill_b200_batch *b, const double *params) {
+  const ModelDef *m = b->m;
+  const long n_vec = b->n;
+  const std::vector<double> &sp = E.tables->rr_spins();
+  const int nthr = (int) std::max<long>(1, std::min<long>({(long) std::thread::hardware_concurrency(), 16L, n_vec / 256}));
+  auto work = [&](long lo, long hi) {
+    for (long i = lo; i < hi; i++)
+      interpret_params(*m, params + (size_t) i * m->npar, E.cfg, sp.empty() ? nullptr : sp.data(), (int) sp.size(), b->vps[i]);
+  };
+  if (nthr <= 1) {
+    work(0, n_vec);
+  } else {
+    std::vector<std::thread> th;
+    for (int k = 0; k < nthr; k++) th.emplace_back(work, n_vec * k / nthr, n_vec * (k + 1) / nthr);
+    for (auto &x : th) x.join();
+  }
+  b->nz_max = 1;
+  b->any_corr = b->any_limb = false;
+  for (long i = 0; i < n_vec; i++) {
+    if (b->vps[i].status == ST_OK) {
+      b->nz_max = std::max(b->nz_max, b->vps[i].nz);
+      if (b->vps[i].do_corr) b->any_corr = true;
+      if (b->vps[i].limb != 0) b->any_limb = true;
+    }
+  }
+}
+
+void read_call_env(Engine &E) {   // read per call, like the reference's constantDiskDensity() (src/relutility.c:372-382)
+  const char *env = getenv("RELXILL_CONSTANT_DENSITY");
+  E.cfg.env_const_density = (env && (int) strtod(env, nullptr) == 1) ? 1 : 0;
+}
+
+void free_batch_locked(Engine &E, relxill_b200_batch *b) {
+  if (!b) return;
+  if (E.arena_owner == b->uid) E.arena_owner = 0;
+  pool_put(E, b->d_vps, b->vps_bytes);
+  pool_put(E, b->d_energy, b->energy_bytes);
+  pool_put(E, b->d_reuse, (size_t) b->n);
+  delete b;
 }
 
 }  // namespace
@@ -353,6 +444,8 @@ void relxill_b200_shutdown(void) {
   if (g_eng.d_io) cudaFree(g_eng.d_io);
   g_eng.d_io = nullptr;
   g_eng.d_io_cap = 0;
+  free_batch_locked(g_eng, g_eng.retained);
+  g_eng.retained = nullptr;
   for (auto &pr : g_eng.pool) cudaFree(pr.second);
   g_eng.pool.clear();
   delete g_eng.tables;
@@ -363,6 +456,7 @@ void relxill_b200_shutdown(void) {
 void relxill_b200_set_num_zones(int n) { g_eng.cfg.env_num_zones = n; }
 void relxill_b200_set_profiling(int on) { g_eng.profiling = on != 0; }
 void relxill_b200_keep_intermediates(int on) { g_eng.keep_intermediates = on != 0; }
+void relxill_b200_set_cache(int on) { g_eng.cache_on = on != 0; }
 
 int relxill_b200_num_params(const char *model) {
   const ModelDef *m = find_model(model);
@@ -389,10 +483,7 @@ relxill_b200_batch *relxill_b200_prepare(const char *model, const double *energy
     return nullptr;
   }
   // tables this flavour needs; returning radiation can be switched per vector -> load if the table exists
-  {  // read per call, like the reference's constantDiskDensity() (src/relutility.c:372-382)
-    const char *env = getenv("RELXILL_CONSTANT_DENSITY");
-    E.cfg.env_const_density = (env && (int) strtod(env, nullptr) == 1) ? 1 : 0;
-  }
+  read_call_env(E);
   bool want_rr = (m->irrad == EMIS_LP) || E.cfg.env_returnrad == 1;
   std::string err = (m->type == T_XILL)
                         ? E.tables->require_xill_only(model_xtab(*m))
@@ -408,37 +499,17 @@ relxill_b200_batch *relxill_b200_prepare(const char *model, const double *energy
   b->n_flux = n_flux;
   b->vps.resize(n_vec);
   b->status.assign(n_vec, 0);
-  const std::vector<double> &sp = E.tables->rr_spins();
-  {  // host-side interpretation, spread over a few threads for large batches
-    const int nthr = (int) std::max<long>(1, std::min<long>({(long) std::thread::hardware_concurrency(), 16L, n_vec / 256}));
-    auto work = [&](long lo, long hi) {
-      for (long i = lo; i < hi; i++)
-        interpret_params(*m, params + (size_t) i * m->npar, E.cfg, sp.empty() ? nullptr : sp.data(), (int) sp.size(), b->vps[i]);
-    };
-    if (nthr <= 1) {
-      work(0, n_vec);
-    } else {
-      std::vector<std::thread> th;
-      for (int k = 0; k < nthr; k++) th.emplace_back(work, n_vec * k / nthr, n_vec * (k + 1) / nthr);
-      for (auto &x : th) x.join();
-    }
-  }
-  for (long i = 0; i < n_vec; i++) {
-    if (b->vps[i].status == ST_OK) {
-      b->nz_max = std::max(b->nz_max, b->vps[i].nz);
-      if (b->vps[i].do_corr) b->any_corr = true;
-      if (b->vps[i].limb != 0) b->any_limb = true;
-    }
-  }
+  b->uid = E.next_uid++;
+  b->energy.assign(energy, energy + n_flux + 1);
+  interpret_all(E, b, params);
   b->vps_bytes = n_vec * sizeof(VPar);
   b->energy_bytes = (n_flux + 1) * sizeof(double);
   b->d_vps = (VPar *) pool_get(E, b->vps_bytes);
   b->d_energy = (double *) pool_get(E, b->energy_bytes);
-  if (!b->d_vps || !b->d_energy) {
+  b->d_reuse = (unsigned char *) pool_get(E, (size_t) n_vec);
+  if (!b->d_vps || !b->d_energy || !b->d_reuse) {
     set_err("out of device memory (batch)");
-    pool_put(E, b->d_vps, b->vps_bytes);
-    pool_put(E, b->d_energy, b->energy_bytes);
-    delete b;
+    free_batch_locked(E, b);
     return nullptr;
   }
   cudaMemcpy(b->d_vps, b->vps.data(), n_vec * sizeof(VPar), cudaMemcpyHostToDevice);
@@ -448,12 +519,48 @@ relxill_b200_batch *relxill_b200_prepare(const char *model, const double *energy
 
 void relxill_b200_free_batch(relxill_b200_batch *b) {
   if (!b) return;
-  {
-    std::lock_guard<std::mutex> lk(g_eng.mu);
-    pool_put(g_eng, b->d_vps, b->vps_bytes);
-    pool_put(g_eng, b->d_energy, b->energy_bytes);
+  std::lock_guard<std::mutex> lk(g_eng.mu);
+  free_batch_locked(g_eng, b);
+}
+
+int relxill_b200_update_params(relxill_b200_batch *b, const double *params) {
+  Engine &E = g_eng;
+  std::lock_guard<std::mutex> lk(E.mu);
+  if (!b || !E.inited || !params) { set_err("update_params: library not initialised or null argument"); return -1; }
+  read_call_env(E);
+  interpret_all(E, b, params);
+  CK(cudaMemcpy(b->d_vps, b->vps.data(), b->n * sizeof(VPar), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int relxill_b200_update_energy(relxill_b200_batch *b, const double *energy, int n_flux) {
+  Engine &E = g_eng;
+  std::lock_guard<std::mutex> lk(E.mu);
+  if (!b || !E.inited || !energy || n_flux < 1) { set_err("update_energy: library not initialised or bad argument"); return -1; }
+  if (b->m->type == T_LINE) {
+    if (n_flux > line_max_bins()) { set_err("line models: energy grid too long"); return -1; }
+    b->state_valid = false;   // the line models integrate on the caller's grid: nothing survives a new grid
   }
-  delete b;
+  const size_t bytes = (size_t) (n_flux + 1) * sizeof(double);
+  if (bytes > b->energy_bytes) {
+    double *d = (double *) pool_get(E, bytes);
+    if (!d) { set_err("out of device memory (energy grid)"); return -2; }
+    pool_put(E, b->d_energy, b->energy_bytes);
+    b->d_energy = d;
+    b->energy_bytes = bytes;
+  }
+  b->n_flux = n_flux;
+  b->energy.assign(energy, energy + n_flux + 1);
+  CK(cudaMemcpy(b->d_energy, energy, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int relxill_b200_reuse_counts(relxill_b200_batch *b, long *out3) {
+  if (!b || !out3) return -1;
+  out3[0] = b->n - b->n_reuse_rel - b->n_reuse_all;
+  out3[1] = b->n_reuse_rel;
+  out3[2] = b->n_reuse_all;
+  return 0;
 }
 
 int relxill_b200_run(relxill_b200_batch *b, double *d_flux, void *stream) {
@@ -502,7 +609,25 @@ int relxill_batch_eval(const char *model, const double *energy, int n_flux, cons
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
   const auto t0 = now();
-  relxill_b200_batch *b = relxill_b200_prepare(model, energy, n_flux, params, n_vec);
+  // An XSPEC fit (or any caller that re-evaluates the same vectors with a few parameters changed) comes back with the
+  // same model and batch size: the batch of the previous call was kept, so that the vectors whose relativistic half
+  // or whole parameter set is unchanged re-use the state still resident in the arena (run_batch).
+  relxill_b200_batch *b = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_eng.mu);
+    relxill_b200_batch *r = g_eng.retained;
+    g_eng.retained = nullptr;
+    if (r && g_eng.cache_on && g_eng.inited && r->m == find_model(model) && r->n == n_vec && n_flux >= 1 && energy && params) b = r;
+    else free_batch_locked(g_eng, r);
+  }
+  if (b) {
+    int rc = 0;
+    if (n_flux != b->n_flux || memcmp(energy, b->energy.data(), sizeof(double) * (size_t) (n_flux + 1)) != 0)
+      rc = relxill_b200_update_energy(b, energy, n_flux);
+    if (rc == 0) rc = relxill_b200_update_params(b, params);
+    if (rc != 0) { relxill_b200_free_batch(b); b = nullptr; }
+  }
+  if (!b) b = relxill_b200_prepare(model, energy, n_flux, params, n_vec);
   const auto t1 = now();
   if (!b) {
     if (flux && n_vec > 0 && n_flux > 0) memset(flux, 0, sizeof(double) * (size_t) n_vec * n_flux);
@@ -548,7 +673,12 @@ int relxill_batch_eval(const char *model, const double *energy, int n_flux, cons
   const auto t3 = now();
   const auto t4 = now();
   if (status) for (long i = 0; i < n_vec; i++) status[i] = b->status[i];
-  relxill_b200_free_batch(b);
+  if (rc == 0 && b->state_valid && E.cache_on) {
+    std::lock_guard<std::mutex> lk(E.mu);
+    E.retained = b;
+  } else {
+    relxill_b200_free_batch(b);
+  }
   if (dbg)
     fprintf(stderr, "relxill_batch_eval timing: prepare %.2f ms, staging %.2f ms, run + D2H (pipelined) %.2f ms (+%.2f), free %.2f ms\n",
             ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, now()));

@@ -169,7 +169,10 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
     for (int j = t; j < A.n_flux; j += CONV_NT) o[j] = 0.0;
     return;
   }
-  const int nz = (A.mode == 0) ? vp.nz : 1;
+  // the previous run's convolution-grid spectrum of this vector is still valid (same parameters up to z): only the
+  // rebin onto the caller's grid is left (the reference's RelxillCache hit, src/Relxill.cpp:296-300,405)
+  const bool reuse_all = (A.mode == 0) && A.total && S.reuse && (S.reuse[v] & REUSE_ALL);
+  const int nz = reuse_all ? 0 : (A.mode == 0) ? vp.nz : 1;
   const XillDev &X = T.xill[A.which];
   const int i1 = T.conv_i1kev, b0 = T.conv_b0, b1 = T.conv_b1;
   const double2 *tw = reinterpret_cast<const double2 *>(T.tw);
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
     __syncthreads();
   }
   // ---- one inverse transform for the whole vector: out = Re(FFT(conj(A)))
-  {
+  if (!reuse_all) {
     double re[8], im[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) {   // Hermitian extension of the accumulated half spectrum, conjugated
@@ -286,9 +289,14 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
     fft4096(re, im, sm.z, wreg);
   }
   double *acc = sm.ar;   // ar and ai are contiguous: 4098 doubles
-  for (int i = t; i < NCONV; i += CONV_NT) acc[i] = sm.z[cv_pad(i)].x;
+  if (reuse_all) {
+    __syncthreads();
+    for (int i = t; i < NCONV; i += CONV_NT) acc[i] = A.total[(size_t) v * NCONV + i];
+  } else {
+    for (int i = t; i < NCONV; i += CONV_NT) acc[i] = sm.z[cv_pad(i)].x;
+  }
   __syncthreads();
-  if (A.mode == 0) {
+  if (A.mode == 0 && !reuse_all) {
     // primary spectrum on the convolution grid (cutoff power law here; nthcomp is added by k_prim_nthcomp)
     double refl_scale, prim_scale;
     if (vp.emis_type != EMIS_LP) {

@@ -694,6 +694,7 @@ __global__ void __launch_bounds__(320) k_fine(const VPar *__restrict__ vps, DevT
   __shared__ double s_rad[8][3];                    // per radius: gmin, gmax - gmin, r (2 pi r)^2 emis weight (< 0: off the grid)
   const int v = blockIdx.y;
   if (S.status[v] != ST_OK) return;
+  if (S.reuse && S.reuse[v]) return;
   const int j = threadIdx.x % NG, rl = threadIdx.x / NG;
   const int i = blockIdx.x * 8 + rl;
   if (n_incl > 0 && threadIdx.x < 8) {   // per-radius factors of the distribution

@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(LN_NT, 6) k_line(const VPar *__restrict__ vps,
   const unsigned FULL = 0xffffffffu;
   const int v = blockIdx.y, z = blockIdx.x, t = threadIdx.x;
   if (S.status[v] != ST_OK) return;
+  if (S.reuse && S.reuse[v]) return;   // the zone profiles of the previous run stand
   const VPar &vp = vps[v];
   if (z >= vp.nz) return;
   const double *egrid = G.e;

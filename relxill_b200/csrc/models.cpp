@@ -271,4 +271,24 @@ void interpret_params(const ModelDef &m, const double *par, const HostConfig &cf
   vp.do_corr = (vp.type == T_RELXILL && vp.return_rad != 0 && vp.a > 0.0) ? 1 : 0;
 }
 
+int reusable_state(const VPar &p, const VPar &q) {
+  if (p.type != q.type || p.model_type != q.model_type || p.status != q.status || q.status != ST_OK) return 0;
+  if (p.type == T_XILL) return 0;
+  bool rel = p.emis_type == q.emis_type && p.a == q.a && p.incl == q.incl && p.emis1 == q.emis1 && p.emis2 == q.emis2 &&
+             p.rbr == q.rbr && p.rin == q.rin && p.rout == q.rout && p.lineE == q.lineE && p.height == q.height &&
+             p.gamma == q.gamma && p.beta == q.beta && p.rms == q.rms && p.limb == q.limb && p.nz == q.nz &&
+             p.return_rad == q.return_rad && p.rr_spin == q.rr_spin && p.do_corr == q.do_corr &&
+             p.eshift_obs == q.eshift_obs && p.doppler_obs == q.doppler_obs;
+  if (rel && p.type == T_LINE) rel = (p.z == q.z);   // the line models integrate on the caller's grid shifted by z
+  for (int i = 0; rel && i <= q.nz; i++) rel = (p.zone[i] == q.zone[i]);
+  if (!rel) return 0;
+  int out = (p.do_corr || q.do_corr) ? 0 : REUSE_REL;
+  if (p.type == T_RELXILL) {
+    VPar a = p, b = q;   // interpret_params zeroes the struct first, so the padding compares equal
+    a.z = b.z = 0.0;
+    if (std::memcmp(&a, &b, sizeof(VPar)) == 0) out |= REUSE_ALL | REUSE_REL;
+  }
+  return out;
+}
+
 }  // namespace rx

@@ -43,4 +43,14 @@ double kerr_rplus(double a);
 void interpret_params(const ModelDef &m, const double *par, const HostConfig &cfg, const double *rr_spins,
                       int rr_nspin, VPar &vp);
 
+// What of a vector's device-resident state survives a parameter change — the counterpart of the reference's
+// did_rel_param_change / did_xill_param_change logic (CachingStatus, src/Relxill.cpp:316; comp_rel_param and
+// comp_xill_param, src/Relbase.cpp:353-470):
+//   REUSE_ALL  every interpreted value that reaches the convolution-grid spectrum is unchanged (z may differ for the
+//              relxill flavours: it only enters the final rebin);
+//   REUSE_REL  the values read by the relativistic half (k_syspar, k_fine, k_dist, k_line) are unchanged and the
+//              emissivity does not depend on the xillver side (no returning-radiation correction factors).
+// Returns a combination of REUSE_REL / REUSE_ALL (0: recompute everything).
+int reusable_state(const VPar &prev, const VPar &now);
+
 }  // namespace rx

@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(128) k_nth(const VPar *__restrict__ vps, DevTa
   __shared__ int s_jmax[NZMAX + 1];
   const int v = blockIdx.x, t = threadIdx.x;
   if (S.status[v] != ST_OK) return;
+  if (S.reuse && (S.reuse[v] & REUSE_ALL)) return;
   const VPar &vp = vps[v];
   if (vp.prim_type != PRIM_NTHCOMP) return;
   const int nz = vp.nz;
@@ -213,6 +214,7 @@ __global__ void __launch_bounds__(256) k_prim_nth(const VPar *__restrict__ vps, 
   const int v = blockIdx.x, t = threadIdx.x;
   if (S.status[v] != ST_OK) return;
   const VPar &vp = vps[v];
+  const bool reuse_all = S.reuse && (S.reuse[v] & REUSE_ALL);   // `total` already holds reflection + primary
   const int nz = vp.nz;
   const double *sp = S.nth_spt + (size_t) v * NTH_MAX * NTH_SOL + nz;
   const int nth = S.nth_jmax[(size_t) v * NTH_SOL + nz];
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(256) k_prim_nth(const VPar *__restrict__ vps, 
     if (vp.beta > 1e-4) prim_scale *= vp.doppler_obs * vp.doppler_obs;
   }
   const double nsrc = S.nsrc[v];
-  const bool add_prim = (vp.refl_frac >= 0);
+  const bool add_prim = (vp.refl_frac >= 0) && !reuse_all;
   double *tot = total + (size_t) v * NCONV;
   for (int i = t; i < NCONV; i += 256) {
     double val = tot[i];

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(XL_NT, 4) k_xill(const VPar *__restrict__ vps,
   __shared__ int s_off[NZMAX * NS];
   const int v = blockIdx.y, t = threadIdx.x;
   if (S.status[v] != ST_OK) return;
+  if (S.reuse && (S.reuse[v] & REUSE_ALL)) return;
   const VPar &vp = vps[v];
   const int nz = vp.nz;
   const XillDev &X = T.xill[which];

@@ -228,3 +228,133 @@ def test_relline_normalisation_full_batch(rx):
     P[:, 8] = 0.0
     f = rx.batch_eval("relline", e, P)
     np.testing.assert_allclose(f.sum(axis=1), 1.0, rtol=1e-12)
+
+
+# ---------------------------------------------------------------- device-resident state cache
+def _run_batch(rx, model, e, P, flux_in=None):
+    import torch
+    b = rx.Batch(model, e, P)
+    out = torch.zeros((len(P), e.size - 1), dtype=torch.float64, device="cuda")
+    if flux_in is not None:
+        out.copy_(torch.from_numpy(np.broadcast_to(flux_in, out.shape).copy()))
+    b.run(out.data_ptr())
+    torch.cuda.synchronize()
+    return b, out
+
+
+# (model, index of a parameter that only the xillver half reads, index of a relativistic parameter)
+_CACHE_CASES = [("relxill", 9, 3), ("relxilllp", 8, 0), ("relxillCp", 9, 1), ("relxilllpCp", 7, 4), ("relxillNS", 9, 3)]
+
+
+@pytest.mark.parametrize("model,i_xill,i_rel", _CACHE_CASES)
+def test_state_cache_is_bit_identical(rx, model, i_xill, i_rel):
+    """Re-running a batch after update_params re-uses what is still valid (whole spectrum / relativistic half) and
+    must give the bits of a fresh evaluation — the reference's caches are result-transparent too."""
+    import torch
+    e = default_grid(1500)
+    P0 = sample_params(model, 12, seed=5)
+    if model == "relxilllp":
+        P0[:6, 12] = 0      # first half without returning radiation: their emissivity does not depend on xillver
+        P0[6:, 12] = 1
+        P0[6:, 2] = 0.5     # positive spin -> correction factors are on
+    if model == "relxilllpCp":
+        P0[:, 15] = 0
+    P1 = P0.copy()
+    chg_x, chg_r = [2, 3, 8, 9], [4, 5, 10, 11]
+    P1[chg_x, i_xill] *= 1.05
+    P1[chg_r, i_rel] *= 0.97
+    rx.set_cache(True)
+    b, out = _run_batch(rx, model, e, P0)
+    assert b.reuse_counts() == dict(recomputed=12, reused_rel=0, reused_all=0)
+    b.update_params(P1)
+    b.run(out.data_ptr())
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().copy()
+    cnt = b.reuse_counts()
+    st = b.status()
+    n_all = int(sum(1 for i in (0, 1, 6, 7) if st[i] == 0))
+    assert cnt["reused_all"] == n_all, cnt
+    if model == "relxilllp":   # rows 8, 9 carry correction factors: a xillver change reaches their emissivity
+        assert cnt["reused_rel"] == int(sum(1 for i in (2, 3) if st[i] == 0)), cnt
+    else:
+        assert cnt["reused_rel"] == int(sum(1 for i in chg_x if st[i] == 0)), cnt
+    # a new energy grid (and a redshift): only the final rebin is repeated
+    e2 = default_grid(700, 0.3, 200.0)
+    P2 = P1.copy()
+    P2[:, rx.PARAM_NAMES[model].index("z")] = 0.1
+    b.update_energy(e2)
+    b.update_params(P2)
+    out2 = torch.zeros((12, 700), dtype=torch.float64, device="cuda")
+    b.run(out2.data_ptr())
+    torch.cuda.synchronize()
+    assert b.reuse_counts()["reused_all"] == int((st == 0).sum())
+    # fresh evaluations (another batch takes the arena over: nothing to re-use)
+    rx.set_cache(False)
+    try:
+        fresh_b, fresh = _run_batch(rx, model, e, P1)
+        assert fresh_b.reuse_counts()["recomputed"] == 12
+        np.testing.assert_array_equal(got, fresh.cpu().numpy())
+        _, fresh2 = _run_batch(rx, model, e2, P2)
+        np.testing.assert_array_equal(out2.cpu().numpy(), fresh2.cpu().numpy())
+    finally:
+        rx.set_cache(True)
+    # the arena now belongs to the last fresh batch: the first batch recomputes everything
+    b.run(out2.data_ptr())
+    torch.cuda.synchronize()
+    assert b.reuse_counts()["recomputed"] == 12
+    np.testing.assert_array_equal(out2.cpu().numpy(), fresh2.cpu().numpy())
+
+
+def test_state_cache_line_and_conv_models(rx):
+    import torch
+    e = default_grid(1200)
+    fin = _conv_input(e)
+    rx.set_cache(True)
+    try:
+        # relconv: the input spectrum changes from call to call, the relativistic kernel does not
+        P = sample_params("relconv", 6, seed=3)
+        b, out = _run_batch(rx, "relconv", e, P, fin)
+        first = out.cpu().numpy().copy()
+        out.copy_(torch.from_numpy(np.broadcast_to(2.0 * fin, out.shape).copy()))
+        b.run(out.data_ptr())
+        torch.cuda.synchronize()
+        assert b.reuse_counts()["reused_rel"] == 6
+        np.testing.assert_allclose(out.cpu().numpy(), 2.0 * first, rtol=1e-13)
+        # relline: unchanged vectors keep their profile, changed ones are recomputed
+        P = sample_params("relline", 6, seed=4)
+        b, out = _run_batch(rx, "relline", e, P)
+        P1 = P.copy()
+        P1[3:, 4] *= 0.9
+        b.update_params(P1)
+        b.run(out.data_ptr())
+        torch.cuda.synchronize()
+        assert b.reuse_counts()["reused_rel"] == 3
+        rx.set_cache(False)
+        _, fresh = _run_batch(rx, "relline", e, P1)
+        np.testing.assert_array_equal(out.cpu().numpy(), fresh.cpu().numpy())
+    finally:
+        rx.set_cache(True)
+
+
+def test_state_cache_behind_the_xspec_symbols(rx):
+    """An XSPEC fit calls lmodrelxill again and again with one parameter changed: the retained batch must not change
+    any result."""
+    e = default_grid(800)
+    p = rx.default_params("relxill")
+    seq = []
+    for k, (i, fac) in enumerate([(0, 1.0), (9, 1.01), (9, 1.02), (3, 0.99), (7, 1.0), (12, 2.0), (12, 2.0)]):
+        q = p.copy()
+        q[i] *= fac
+        if i == 7:
+            q[7] = 0.05
+        seq.append(q)
+        p = q
+    rx.set_cache(True)
+    cached = [rx.lmod("relxill", e, q) for q in seq]
+    rx.set_cache(False)
+    try:
+        plain = [rx.lmod("relxill", e, q) for q in seq]
+    finally:
+        rx.set_cache(True)
+    for a, b in zip(cached, plain):
+        np.testing.assert_array_equal(a, b)
