@@ -358,3 +358,57 @@ def test_state_cache_behind_the_xspec_symbols(rx):
         rx.set_cache(True)
     for a, b in zip(cached, plain):
         np.testing.assert_array_equal(a, b)
+
+
+# ---------------------------------------------------------------- the other BASELINE.json configurations
+def test_config2_relxill_1024_random(rx, oracle):
+    """BASELINE config 2: relxill, 1024 random parameter vectors (seed 1234); a sample against the oracle, the
+    whole batch for status / finiteness / batch-order invariance."""
+    e = default_grid(3000)
+    P = sample_params("relxill", 1024, seed=1234)
+    f, st = rx.batch_eval("relxill", e, P, return_status=True)
+    assert (st == 0).all() and np.isfinite(f).all()
+    for i in (0, 17, 333, 1023):
+        assert relerr(f[i], oracle.eval("relxill", e, P[i])) < RTOL
+    np.testing.assert_array_equal(rx.batch_eval("relxill", e, P[::-1].copy())[::-1], f)
+
+
+def test_config4_cp_batch_streams_through_chunks(rx, oracle):
+    """BASELINE config 4 (relxillCp / relxilllpCp, uniform-random, one GPU's shard streamed through the scratch arena
+    in several chunks): chunking must not change a bit, and sampled rows agree with the oracle."""
+    e = default_grid(1000)
+    for model, n in (("relxillCp", 5000), ("relxilllpCp", 2500)):
+        P = sample_params(model, n, seed=99)
+        if model == "relxilllpCp":
+            P[:, 14] = 0          # iongrad_type 0, 10 zones (config 4)
+        rx.set_cache(False)
+        try:
+            f, st = rx.batch_eval(model, e, P, return_status=True)
+            ok = st == 0
+            assert ok.mean() > 0.95 and np.isfinite(f).all()
+            pick = [i for i in (1, n // 3, n // 2 + 7, n - 2) if ok[i]]
+            for i in pick:
+                assert relerr(f[i], oracle.eval(model, e, P[i])) < RTOL, (model, i)
+            # the same vectors in small batches (one chunk each)
+            sub = slice(n - 300, n)
+            np.testing.assert_array_equal(rx.batch_eval(model, e, P[sub]), f[sub])
+        finally:
+            rx.set_cache(True)
+
+
+def test_config5_returning_radiation_sweep(rx, oracle):
+    """BASELINE config 5: relxilllp with returning radiation on a spin x height x inclination grid."""
+    e = default_grid(1500)
+    base = rx.default_params("relxilllp")
+    rows = []
+    for a in np.linspace(0.0, 0.998, 8):
+        for h in np.geomspace(2.0, 100.0, 8):
+            for inc in np.linspace(5.0, 80.0, 4):
+                p = base.copy()
+                p[0], p[2], p[3], p[12] = h, a, inc, 1
+                rows.append(p)
+    P = np.array(rows)
+    f, st = rx.batch_eval("relxilllp", e, P, return_status=True)
+    assert (st == 0).all() and np.isfinite(f).all() and (f.sum(axis=1) > 0).all()
+    for i in (0, 37, 101, 200, 255):
+        assert relerr(f[i], oracle.eval("relxilllp", e, P[i])) < RTOL, i
