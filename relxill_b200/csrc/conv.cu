@@ -181,17 +181,6 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
   const double2 *rb_dd = reinterpret_cast<const double2 *>(X.rb_dd);
   for (int k = t; k <= NCONV / 2; k += CONV_NT) { sm.ar[k] = 0.0; sm.ai[k] = 0.0; }
   const double2 wreg[3] = {__ldg(tw + (t & 7) * 64), __ldg(tw + (t & 63) * 8), __ldg(tw + t)};   // tw[m] = exp(-2 pi i m / 4096)
-  // rebin map of the thread's 8 bins, 16 bits each: first source bin (12 bits) | bins spanned - 1 (0..2; 3 = look it up)
-  unsigned pk[4] = {0u, 0u, 0u, 0u};
-  if (A.mode == 0) {
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const int2 ii = __ldg(rb_ii + t + u * CONV_NT);
-      unsigned code = 0u;   // outside the table grid: source bin 0 with zero weights
-      if (ii.x >= 0) code = (ii.x < 4096 && ii.y - ii.x <= 2) ? ((unsigned) ii.x | ((unsigned) (ii.y - ii.x) << 12)) : (3u << 12);
-      pk[u >> 1] |= code << (16 * (u & 1));
-    }
-  }
   for (int z = 0; z < nz; z++) {
     const double *rel = S.relflux + ((size_t) v * A.nz_stride + z) * A.ne_stride;
     const double *xz = S.xillz + ((size_t) v * A.nz_stride + z) * X.stride;
@@ -204,22 +193,19 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
     double sums[4] = {0.0, 0.0, 0.0, 0.0};   // all rel, |x|, band x, band rel
     double re[8], im[8];                      // bins t + 512 u: the first FFT pass takes them from here
     if (A.mode == 0) {
-      // all loads of the 8 bins are independent: the first source bin and the span of every bin come from the
-      // thread's packed registers (pk), bins outside the table grid carry zero weights
+      // all loads of the 8 bins are independent: bins outside the table grid carry zero weights, the common
+      // spans (1-3 source bins) are branch-free
 #pragma unroll
       for (int u = 0; u < 8; u++) {
         const int i = t + u * CONV_NT;
-        const unsigned code = (pk[u >> 1] >> (16 * (u & 1))) & 0xffffu;
-        const int j0 = (int) (code & 0xfffu), sp = (int) ((code >> 12) & 3u);
+        const int2 ii = __ldg(rb_ii + i);
         const double2 dd = __ldg(rb_dd + i);
+        const int j0 = ii.x >= 0 ? ii.x : 0, j1 = ii.x >= 0 ? ii.y : 0;
         double f = 0.0;
-        if (sp != 3) {
-          f += xz[j0] * dd.x + xz[j0 + sp] * dd.y;
-          if (sp == 2) f += xz[j0 + 1];
-        } else {   // wide spans (a table grid much finer than the convolution grid): the general walk
-          const int2 ii = __ldg(rb_ii + i);
-          f += xz[ii.x] * dd.x + xz[ii.y] * dd.y;
-          for (int jj = ii.x + 1; jj <= ii.y - 1; jj++) f += xz[jj];
+        f += xz[j0] * dd.x + xz[j1] * dd.y;
+        if (j1 - j0 >= 2) {
+          f += xz[j0 + 1];
+          for (int jj = j0 + 2; jj <= j1 - 1; jj++) f += xz[jj];
         }
         const int ri = (i + i1) & (NCONV - 1);
         const double r = (ri >= rjlo && ri <= rjhi) ? rel[ri] : 0.0;
