@@ -103,28 +103,13 @@ __global__ void __launch_bounds__(XL_NT, 4) k_xill(const VPar *__restrict__ vps,
     double w[NS];
 #pragma unroll
     for (int s = 0; s < NS; s++) w[s] = s_w[z * NS + s];
-    // sum_s sum_m w_s d_m H[s][m], contracted first over whichever index leaves fewer multiply-adds:
-    // NS (NIT + 1) when the slots are the fewer (5-D: 44 instead of 50), NIT (NS + 1) otherwise (6-D: 45 instead of 48)
     double acc = 0.0;
-    if (NS < NIT) {
-      double d[NIT];
 #pragma unroll
-      for (int m = 0; m < NIT; m++) d[m] = s_dist[z * XL_NI + part * NIT + m];
+    for (int m = 0; m < NIT; m++) {
+      double g = w[0] * H[0][m];
 #pragma unroll
-      for (int s = 0; s < NS; s++) {
-        double g = d[0] * H[s][0];
-#pragma unroll
-        for (int m = 1; m < NIT; m++) g += d[m] * H[s][m];
-        acc += w[s] * g;
-      }
-    } else {
-#pragma unroll
-      for (int m = 0; m < NIT; m++) {
-        double g = w[0] * H[0][m];
-#pragma unroll
-        for (int s = 1; s < NS; s++) g += w[s] * H[s][m];
-        acc += s_dist[z * XL_NI + part * NIT + m] * g;
-      }
+      for (int s = 1; s < NS; s++) g += w[s] * H[s][m];
+      acc += s_dist[z * XL_NI + part * NIT + m] * g;
     }
     if (SPLIT == 2) acc += __shfl_xor_sync(0xffffffffu, acc, 16);
     if (live && part == 0) out[(size_t) z * st] = acc * s_rn[z];
