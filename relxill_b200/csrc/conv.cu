@@ -33,7 +33,8 @@ struct ConvSmem {
   double2 z[CV_PADN];
   double ar[NCONV / 2 + 1], ai[NCONV / 2 + 1];   // accumulated spectrum; reused as the final 4096-bin result
   double red[4 * (CONV_NT / 32)];
-  double bc[4];
+  double bc[8];
+  double part[4 * (CONV_NT / 32)];   // per-warp partial sums of the packing phase, finished after the transform
 };
 
 // sums NV values over the block (fixed order: shuffle tree inside warps, then over the warps)
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
   const double2 *rb_dd = reinterpret_cast<const double2 *>(X.rb_dd);
   for (int k = t; k <= NCONV / 2; k += CONV_NT) { sm.ar[k] = 0.0; sm.ai[k] = 0.0; }
   const double2 wreg[3] = {__ldg(tw + (t & 7) * 64), __ldg(tw + (t & 63) * 8), __ldg(tw + t)};   // tw[m] = exp(-2 pi i m / 4096)
+  double bal_prev = 0.0;   // ratio of the two input scales in the last zone that had one (0: none yet)
   for (int z = 0; z < nz; z++) {
     const double *rel = S.relflux + ((size_t) v * A.nz_stride + z) * A.ne_stride;
     const double *xz = S.xillz + ((size_t) v * A.nz_stride + z) * X.stride;
@@ -235,19 +237,35 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
         im[u] = c.y;
       }
     }
-    block_sum_n<4>(sums, sm);
-    const double srel_all = sums[0];
-    const double rscale = vp.renorm ? vp.relline_norm / srel_all : 1.0;   // renorm_relline_profile (one-zone models)
-    const double srel_n = vp.renorm ? srel_all * rscale : srel_all;
-    if (srel_n < 1e-12) { __syncthreads(); continue; }                     // src/Relxill.cpp:455-457
-    // both real inputs ride one complex transform: bring them to the same scale (any factor cancels in the norm)
-    const double bal = (sums[1] > 0.0 && srel_n > 0.0) ? sums[1] / srel_n : 1.0;
-    const double s_xill = sums[2], s_rel = vp.renorm ? sums[3] * rscale : sums[3];
-    {
-      const double yscale = rscale * bal;
+    // Both real inputs ride one complex transform, so they are brought to the same scale first (any factor cancels
+    // in the norm).  The exact ratio needs the block-wide sums; from the second zone on the previous zone's ratio
+    // is close enough (it only guards the rounding of the smaller input), and the sums are finished after the
+    // transform together with the band sum — one block reduction per zone instead of two.
+    const bool exact = (bal_prev == 0.0) || vp.renorm;   // uniform over the block
+    double rscale = 1.0, s_xill = 0.0, s_rel = 0.0, yscale;
+    if (exact) {
+      block_sum_n<4>(sums, sm);
+      const double srel_all = sums[0];
+      if (vp.renorm) rscale = vp.relline_norm / srel_all;                  // renorm_relline_profile (one-zone models)
+      const double srel_n = vp.renorm ? srel_all * rscale : srel_all;
+      if (srel_n < 1e-12) { __syncthreads(); continue; }                   // src/Relxill.cpp:455-457
+      const double bal = (sums[1] > 0.0 && srel_n > 0.0) ? sums[1] / srel_n : 1.0;
+      s_xill = sums[2];
+      s_rel = vp.renorm ? sums[3] * rscale : sums[3];
+      yscale = rscale * bal;
+      if (!vp.renorm) bal_prev = bal;
+    } else {
 #pragma unroll
-      for (int u = 0; u < 8; u++) im[u] *= yscale;
+      for (int q = 0; q < 4; q++)
+        for (int o = 16; o > 0; o >>= 1) sums[q] += __shfl_xor_sync(0xffffffffu, sums[q], o);
+      if ((t & 31) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) sm.part[q * (CONV_NT / 32) + (t >> 5)] = sums[q];
+      }
+      yscale = bal_prev;
     }
+#pragma unroll
+    for (int u = 0; u < 8; u++) im[u] *= yscale;
     fft4096(re, im, sm.z, wreg);
     // ---- split, product spectrum, band sum of the convolved zone in the frequency domain
     double dot[1] = {0.0};
@@ -266,7 +284,29 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
       const double2 w = __ldg(cw + k);
       dot[0] += wgt * (Pr * w.x + Pi * w.y);
     }
-    block_sum_n<1>(dot, sm);
+    if (exact) {
+      block_sum_n<1>(dot, sm);
+    } else {
+      // the band sum and, from the per-warp parts of the packing phase (visible: the transform's barriers lie in
+      // between), the four packing sums: five rows of 16 partials, one thread each
+      for (int o = 16; o > 0; o >>= 1) dot[0] += __shfl_xor_sync(0xffffffffu, dot[0], o);
+      __syncthreads();
+      if ((t & 31) == 0) sm.red[t >> 5] = dot[0];
+      __syncthreads();
+      if (t < 5) {
+        const double *row = (t == 0) ? sm.red : sm.part + (t - 1) * (CONV_NT / 32);
+        double a = 0.0;
+        for (int i = 0; i < CONV_NT / 32; i++) a += row[i];
+        sm.bc[t] = a;
+      }
+      __syncthreads();
+      dot[0] = sm.bc[0];
+      const double srel_all = sm.bc[1], sabs = sm.bc[2];
+      if (srel_all < 1e-12) { __syncthreads(); continue; }                 // src/Relxill.cpp:455-457
+      s_xill = sm.bc[3];
+      s_rel = sm.bc[4];
+      if (sabs > 0.0) bal_prev = sabs / srel_all;
+    }
     const double norm = s_rel * s_xill / dot[0];
     nk = 0;
     for (int k = t; k <= NCONV / 2; k += CONV_NT, nk++) {
