@@ -32,7 +32,10 @@ namespace rx {
 constexpr int XL_NT = 128;
 constexpr int XL_NI = 10;   // inclination nodes handled (all xillver tables have 10; fewer are padded with zero weight)
 
-template <int NS, int SPLIT>   // NS rest corners per zone, SPLIT lanes per energy bin
+// NS rest corners per zone, SPLIT lanes per energy bin; ST > 0: the table has XL_NI inclinations and rows of ST floats,
+// so the loads of a corner refresh address [pointer + immediate] (the refresh is a third of the kernel's instructions
+// when every row offset is 64-bit arithmetic on run-time strides); ST = 0: any table
+template <int NS, int SPLIT, int ST>
 __global__ void __launch_bounds__(XL_NT, 4) k_xill(const VPar *__restrict__ vps, DevTables T, Scratch S, int which,
                                                    int nz_stride) {
   constexpr int NIT = XL_NI / SPLIT;          // inclinations per lane
@@ -47,8 +50,8 @@ __global__ void __launch_bounds__(XL_NT, 4) k_xill(const VPar *__restrict__ vps,
   const VPar &vp = vps[v];
   const int nz = vp.nz;
   const XillDev &X = T.xill[which];
-  const int ni = X.n_incl;
-  const int st = X.stride, ne = X.n_ener;
+  const int ni = ST ? XL_NI : X.n_incl;
+  const int st = ST ? ST : X.stride, ne = X.n_ener;
   // lane -> (energy bin, inclination part): with SPLIT = 2 the two halves of a warp share 16 bins
   const int lane = t & 31, warp = t >> 5;
   const int part = (SPLIT == 2) ? (lane >> 4) : 0;
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(XL_NT, 4) k_xill(const VPar *__restrict__ vps,
   double gaw[4];
 #pragma unroll
   for (int q = 0; q < 4; q++) {
-    base[q] = X.data + (size_t) S.xga_off[(size_t) v * 4 + q] * ni * st + (live ? e : 0);
+    base[q] = X.data + (size_t) S.xga_off[(size_t) v * 4 + q] * ni * st + (live ? e : 0) + (size_t) (part * NIT) * st;
     gaw[q] = S.xga_w[(size_t) v * 4 + q];
   }
   __syncthreads();
@@ -89,13 +92,13 @@ __global__ void __launch_bounds__(XL_NT, 4) k_xill(const VPar *__restrict__ vps,
       if (off != cur[s]) {
         cur[s] = off;
         const size_t ro = (size_t) off * ni * st;
+        const float *p0 = base[0] + ro, *p1 = base[1] + ro, *p2 = base[2] + ro, *p3 = base[3] + ro;
 #pragma unroll
         for (int m = 0; m < NIT; m++) {
-          const int mg = part * NIT + m;
-          if (mg < ni) {
-            const size_t o = ro + (size_t) mg * st;
-            H[s][m] = gaw[0] * (double) __ldg(base[0] + o) + gaw[1] * (double) __ldg(base[1] + o)
-                      + gaw[2] * (double) __ldg(base[2] + o) + gaw[3] * (double) __ldg(base[3] + o);
+          if (ST || part * NIT + m < ni) {
+            const int o = m * st;
+            H[s][m] = gaw[0] * (double) __ldg(p0 + o) + gaw[1] * (double) __ldg(p1 + o)
+                      + gaw[2] * (double) __ldg(p2 + o) + gaw[3] * (double) __ldg(p3 + o);
           }
         }
       }
@@ -122,12 +125,16 @@ void launch_xill(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
                  int n_incl, cudaStream_t st) {
   (void) nz_max;
   (void) n_incl;   // tables with more than XL_NI inclinations are rejected at load (tables.cu)
-  if (T.xill[which].npar == 6) {
+  const XillDev &X = T.xill[which];
+  const bool std_rows = (X.stride == 3008 && X.n_incl == XL_NI);   // every table of the 2999-bin xillver grid
+  if (X.npar == 6) {
     dim3 grid((n_ener + XL_NT / 2 - 1) / (XL_NT / 2), (unsigned) n);
-    k_xill<8, 2><<<grid, XL_NT, 0, st>>>(vps, T, S, which, S.nz_cap);
+    if (std_rows) k_xill<8, 2, 3008><<<grid, XL_NT, 0, st>>>(vps, T, S, which, S.nz_cap);
+    else k_xill<8, 2, 0><<<grid, XL_NT, 0, st>>>(vps, T, S, which, S.nz_cap);
   } else {
     dim3 grid((n_ener + XL_NT - 1) / XL_NT, (unsigned) n);
-    k_xill<4, 1><<<grid, XL_NT, 0, st>>>(vps, T, S, which, S.nz_cap);
+    if (std_rows) k_xill<4, 1, 3008><<<grid, XL_NT, 0, st>>>(vps, T, S, which, S.nz_cap);
+    else k_xill<4, 1, 0><<<grid, XL_NT, 0, st>>>(vps, T, S, which, S.nz_cap);
   }
 }
 
