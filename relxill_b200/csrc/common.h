@@ -76,7 +76,7 @@ struct XillDev {
   // per-node scalars for the returning-radiation correction factors (linear functionals of the spectra)
   const double *node_ef, *node_p1, *node_p2;
   // fixed rebin map xillver grid -> convolution grid (same imin/imax/weights as _rebin_spectrum)
-  const int *rb_ii;      // [NCONV][2] (imin, imax) of the rebin onto the convolution grid; imin = -1: outside the source grid
+  const int *rb_ii;      // [NCONV][2] (imin, imax) of the rebin onto the convolution grid; (0, 0) with zero weights outside the source grid
   const double *rb_dd;   // [NCONV][2] (dmin, dmax) partial-overlap fractions of the first and last source bin
 };
 

@@ -183,10 +183,25 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
   for (int k = t; k <= NCONV / 2; k += CONV_NT) { sm.ar[k] = 0.0; sm.ai[k] = 0.0; }
   const double2 wreg[3] = {__ldg(tw + (t & 7) * 64), __ldg(tw + (t & 63) * 8), __ldg(tw + t)};   // tw[m] = exp(-2 pi i m / 4096)
   double bal_prev = 0.0;   // ratio of the two input scales in the last zone that had one (0: none yet)
+  // What does not change from zone to zone, per thread: the rotated bin of the line profile that goes with the
+  // thread's bin i(u) = t + 512 u is ri(u) = r0 + 512 ((c0 + u) mod 8), and whether i(u) (bits 0-7) and ri(u)
+  // (bits 8-15) lie in the normalisation band
+  const int r0 = (t + i1) & (CONV_NT - 1), c0 = (t + i1) >> 9;
+  unsigned band = 0u;
+#pragma unroll
+  for (int u = 0; u < 8; u++) {
+    const int i = t + u * CONV_NT, ri = r0 + (((c0 + u) & 7) << 9);
+    if (i >= b0 && i <= b1) band |= 1u << u;
+    if (ri >= b0 && ri <= b1) band |= 0x100u << u;
+  }
+  const double *rel_v = S.relflux + (size_t) v * A.nz_stride * A.ne_stride + r0;
+  const double *xz_v = S.xillz + (size_t) v * A.nz_stride * X.stride;
+  const int *zr_v = S.zrange + (size_t) v * NZMAX * 2;
   for (int z = 0; z < nz; z++) {
-    const double *rel = S.relflux + ((size_t) v * A.nz_stride + z) * A.ne_stride;
-    const double *xz = S.xillz + ((size_t) v * A.nz_stride + z) * X.stride;
-    const int rjlo = S.zrange[((size_t) v * NZMAX + z) * 2], rjhi = S.zrange[((size_t) v * NZMAX + z) * 2 + 1];
+    const double *relr = rel_v + (size_t) z * A.ne_stride;
+    const double *xz = xz_v + (size_t) z * X.stride;
+    int rjlo = zr_v[2 * z], rjw = zr_v[2 * z + 1] - rjlo;   // bins of the profile that were written: [rjlo, rjlo + rjw]
+    if (rjw < 0) { rjlo = 0x40000000; rjw = 0; }
     // ---- pack the zone's spectrum rebinned onto the convolution grid (real part) and its line profile, rotated so
     //      that 1 keV sits at index 0 (imaginary part); band and total sums on the way.  The reference multiplies
     //      both by E_mid/dE before the transform and divides the result by it afterwards (src/Relbase.cpp:93-103,
@@ -200,30 +215,29 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
 #pragma unroll
       for (int u = 0; u < 8; u++) {
         const int i = t + u * CONV_NT;
-        const int2 ii = __ldg(rb_ii + i);
+        const int2 ii = __ldg(rb_ii + i);      // (0, 0) with zero weights outside the table grid
         const double2 dd = __ldg(rb_dd + i);
-        const int j0 = ii.x >= 0 ? ii.x : 0, j1 = ii.x >= 0 ? ii.y : 0;
         double f = 0.0;
-        f += xz[j0] * dd.x + xz[j1] * dd.y;
-        if (j1 - j0 >= 2) {
-          f += xz[j0 + 1];
-          for (int jj = j0 + 2; jj <= j1 - 1; jj++) f += xz[jj];
+        f += xz[ii.x] * dd.x + xz[ii.y] * dd.y;
+        if (ii.y - ii.x >= 2) {
+          f += xz[ii.x + 1];
+          for (int jj = ii.x + 2; jj <= ii.y - 1; jj++) f += xz[jj];
         }
-        const int ri = (i + i1) & (NCONV - 1);
-        const double r = (ri >= rjlo && ri <= rjhi) ? rel[ri] : 0.0;
+        const int ku = ((c0 + u) & 7) << 9;
+        const double r = ((unsigned) (r0 + ku - rjlo) <= (unsigned) rjw) ? relr[ku] : 0.0;
         re[u] = f;
         im[u] = r;
         sums[0] += r;
         sums[1] += fabs(f);
-        if (i >= b0 && i <= b1) sums[2] += f;
-        if (ri >= b0 && ri <= b1) sums[3] += r;
+        if (band & (1u << u)) sums[2] += f;
+        if (band & (0x100u << u)) sums[3] += r;
       }
     } else {
 #pragma unroll 1
       for (int i = t; i < NCONV; i += CONV_NT) {
         const double f = rebin_bin(T.econv[i], T.econv[i + 1], A.user_e, o, A.n_flux);
         const int ri = (i + i1) & (NCONV - 1);
-        const double r = (ri >= rjlo && ri <= rjhi) ? rel[ri] : 0.0;
+        const double r = ((unsigned) (ri - rjlo) <= (unsigned) rjw) ? relr[ri - r0] : 0.0;
         sm.z[cv_pad(i)] = make_double2(f, r);
         sums[0] += r;
         sums[1] += fabs(f);

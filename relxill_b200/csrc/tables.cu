@@ -459,7 +459,7 @@ std::string Tables::load_xill(int which) {
   std::vector<int> ii_v(2 * NCONV);
   std::vector<double> dd_v(2 * NCONV);
   for (int i = 0; i < NCONV; i++) {
-    ii_v[2 * i] = imin_v[i]; ii_v[2 * i + 1] = imax_v[i];
+    ii_v[2 * i] = std::max(imin_v[i], 0); ii_v[2 * i + 1] = std::max(imax_v[i], 0);   // outside the table grid: bin 0, zero weights
     dd_v[2 * i] = dmin_v[i]; dd_v[2 * i + 1] = dmax_v[i];
   }
   xd.rb_ii = upload(ii_v);
