@@ -60,6 +60,8 @@ __device__ __forceinline__ void block_sum_n(double (&v)[NV], ConvSmem &sm) {
   for (int q = 0; q < NV; q++) v[q] = sm.bc[q];
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void cmul(double &xr, double &xi, double wr, double wi) {
   const double a = xr * wr - xi * wi;
   xi = xr * wi + xi * wr;
@@ -209,6 +211,18 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
     //      tables.cu) and cancels against the normalisation, so it is left out
     double sums[4] = {0.0, 0.0, 0.0, 0.0};   // all rel, |x|, band x, band rel
     double re[8], im[8];                      // bins t + 512 u: the first FFT pass takes them from here
+    if (A.mode == 0 && z + 1 < nz) {
+      // the next zone's two rows are pulled into L2 while this zone is transformed: the packing loads are the
+      // kernel's only DRAM accesses and there are too few warps to hide their latency (one 128-byte line per thread:
+      // 188 lines of the zone spectrum, up to 256 of the written part of the line profile)
+      if (t < 188) {
+        prefetch_l2(xz + X.stride + t * 16);
+      } else if (t >= 192 && t < 448) {
+        const int nlo = zr_v[2 * z + 2], nhi = zr_v[2 * z + 3];
+        const int l = (nlo & ~15) + (t - 192) * 16;
+        if (l <= nhi) prefetch_l2(relr - r0 + A.ne_stride + l);
+      }
+    }
     if (A.mode == 0) {
       // all loads of the 8 bins are independent: bins outside the table grid carry zero weights, the common
       // spans (1-3 source bins) are branch-free
