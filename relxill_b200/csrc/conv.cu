@@ -19,6 +19,8 @@
 // one point every 8, which makes every pass's gather and scatter bank-conflict free per quarter-warp.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "common.h"
 #include "devutil.cuh"
 #include "kernels.h"
@@ -35,6 +37,7 @@ struct ConvSmem {
   double red[4 * (CONV_NT / 32)];
   double bc[8];
   double part[4 * (CONV_NT / 32)];   // per-warp partial sums of the packing phase, finished after the transform
+  double2 tw12[8 + 64];              // twiddles of passes 1 and 2: exp(-2 pi i k / 64), k < 8; exp(-2 pi i k / 512), k < 64
 };
 
 // sums NV values over the block (fixed order: shuffle tree inside warps, then over the warps)
@@ -113,7 +116,7 @@ __device__ __forceinline__ void fft8(double (&r)[8], double (&i)[8]) {
 // The twiddles of pass p are w^q with w = exp(-2 pi i k / (8 ns)), k = j mod ns: they depend on the thread only,
 // so the caller keeps the three w (one per pass) in registers for the whole kernel; w^2 and w^4 come from
 // squarings and the rest from products — no table reads inside the transform.
-__device__ __forceinline__ void fft4096(double (&r)[8], double (&im)[8], double2 *z, const double2 (&wreg)[3]) {
+__device__ __forceinline__ void fft4096(double (&r)[8], double (&im)[8], double2 *z, const double2 *tw12, const double2 &w3) {
   const int j = threadIdx.x;
   fft8(r, im);
 #pragma unroll
@@ -130,7 +133,7 @@ __device__ __forceinline__ void fft4096(double (&r)[8], double (&im)[8], double2
       im[q] = c.y;
     }
     {
-      const double2 w1 = wreg[pass - 1];
+      const double2 w1 = (pass == 1) ? tw12[k] : (pass == 2) ? tw12[8 + k] : w3;
       const double2 w2 = make_double2(w1.x * w1.x - w1.y * w1.y, 2.0 * w1.x * w1.y);
       const double2 w4 = make_double2(w2.x * w2.x - w2.y * w2.y, 2.0 * w2.x * w2.y);
       const double2 w3 = cprod(w1, w2), w5 = cprod(w4, w1), w6 = cprod(w4, w2);
@@ -160,9 +163,14 @@ struct ConvArgs {
   int which;              // xillver table index
   int nz_stride, ne_stride;
   int mode;               // 0 relxill, 1 convolution model (input spectrum in `out`)
+  // resolved on the host so that the kernel reads them from the constant bank instead of keeping them in registers
+  const int2 *rb_ii;      // rebin map of the xillver table in use (XillDev::rb_ii / rb_dd)
+  const double2 *rb_dd;
+  int xstride;            // row stride of the zone spectra
 };
 
-__global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vps, DevTables T, Scratch S, ConvArgs A) {
+template <int MINB>
+__global__ void __launch_bounds__(CONV_NT, MINB) k_conv(const VPar *__restrict__ vps, DevTables T, Scratch S, ConvArgs A) {
   extern __shared__ __align__(16) unsigned char smraw[];
   ConvSmem &sm = *reinterpret_cast<ConvSmem *>(smraw);
   const int v = blockIdx.x, t = threadIdx.x;
@@ -176,14 +184,15 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
   // rebin onto the caller's grid is left (the reference's RelxillCache hit, src/Relxill.cpp:296-300,405)
   const bool reuse_all = (A.mode == 0) && A.total && S.reuse && (S.reuse[v] & REUSE_ALL);
   const int nz = reuse_all ? 0 : (A.mode == 0) ? vp.nz : 1;
-  const XillDev &X = T.xill[A.which];
   const int i1 = T.conv_i1kev, b0 = T.conv_b0, b1 = T.conv_b1;
   const double2 *tw = reinterpret_cast<const double2 *>(T.tw);
   const double2 *cw = reinterpret_cast<const double2 *>(T.conv_w);
-  const int2 *rb_ii = reinterpret_cast<const int2 *>(X.rb_ii);
-  const double2 *rb_dd = reinterpret_cast<const double2 *>(X.rb_dd);
   for (int k = t; k <= NCONV / 2; k += CONV_NT) { sm.ar[k] = 0.0; sm.ai[k] = 0.0; }
-  const double2 wreg[3] = {__ldg(tw + (t & 7) * 64), __ldg(tw + (t & 63) * 8), __ldg(tw + t)};   // tw[m] = exp(-2 pi i m / 4096)
+  // tw[m] = exp(-2 pi i m / 4096): the last pass's twiddle of this thread stays in registers, the 8 + 64 distinct
+  // ones of the two passes before it sit in shared memory (conflict-free: consecutive threads, consecutive entries)
+  const double2 w3 = __ldg(tw + t);
+  if (t < 8) sm.tw12[t] = __ldg(tw + t * 64);
+  else if (t < 72) sm.tw12[t] = __ldg(tw + (t - 8) * 8);
   double bal_prev = 0.0;   // ratio of the two input scales in the last zone that had one (0: none yet)
   // What does not change from zone to zone, per thread: the rotated bin of the line profile that goes with the
   // thread's bin i(u) = t + 512 u is ri(u) = r0 + 512 ((c0 + u) mod 8), and whether i(u) (bits 0-7) and ri(u)
@@ -197,11 +206,11 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
     if (ri >= b0 && ri <= b1) band |= 0x100u << u;
   }
   const double *rel_v = S.relflux + (size_t) v * A.nz_stride * A.ne_stride + r0;
-  const double *xz_v = S.xillz + (size_t) v * A.nz_stride * X.stride;
+  const double *xz_v = S.xillz + (size_t) v * A.nz_stride * A.xstride;
   const int *zr_v = S.zrange + (size_t) v * NZMAX * 2;
   for (int z = 0; z < nz; z++) {
     const double *relr = rel_v + (size_t) z * A.ne_stride;
-    const double *xz = xz_v + (size_t) z * X.stride;
+    const double *xz = xz_v + (size_t) z * A.xstride;
     int rjlo = zr_v[2 * z], rjw = zr_v[2 * z + 1] - rjlo;   // bins of the profile that were written: [rjlo, rjlo + rjw]
     if (rjw < 0) { rjlo = 0x40000000; rjw = 0; }
     // ---- pack the zone's spectrum rebinned onto the convolution grid (real part) and its line profile, rotated so
@@ -216,7 +225,7 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
       // kernel's only DRAM accesses and there are too few warps to hide their latency (one 128-byte line per thread:
       // 188 lines of the zone spectrum, up to 256 of the written part of the line profile)
       if (t < 188) {
-        prefetch_l2(xz + X.stride + t * 16);
+        prefetch_l2(xz + A.xstride + t * 16);
       } else if (t >= 192 && t < 448) {
         const int nlo = zr_v[2 * z + 2], nhi = zr_v[2 * z + 3];
         const int l = (nlo & ~15) + (t - 192) * 16;
@@ -229,8 +238,8 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
 #pragma unroll
       for (int u = 0; u < 8; u++) {
         const int i = t + u * CONV_NT;
-        const int2 ii = __ldg(rb_ii + i);      // (0, 0) with zero weights outside the table grid
-        const double2 dd = __ldg(rb_dd + i);
+        const int2 ii = __ldg(A.rb_ii + i);      // (0, 0) with zero weights outside the table grid
+        const double2 dd = __ldg(A.rb_dd + i);
         double f = 0.0;
         f += xz[ii.x] * dd.x + xz[ii.y] * dd.y;
         if (ii.y - ii.x >= 2) {
@@ -294,7 +303,7 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
     }
 #pragma unroll
     for (int u = 0; u < 8; u++) im[u] *= yscale;
-    fft4096(re, im, sm.z, wreg);
+    fft4096(re, im, sm.z, sm.tw12, w3);
     // ---- split, product spectrum, band sum of the convolved zone in the frequency domain
     double dot[1] = {0.0};
     double pr_[5], pi_[5];
@@ -354,7 +363,7 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
       re[u] = sm.ar[k];
       im[u] = (i <= NCONV / 2) ? -ai : ai;
     }
-    fft4096(re, im, sm.z, wreg);
+    fft4096(re, im, sm.z, sm.tw12, w3);
   }
   double *acc = sm.ar;   // ar and ai are contiguous: 4098 doubles
   if (reuse_all) {
@@ -422,12 +431,16 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
   }
 }
 
+static int g_conv_minb = 2;
+template <int MINB> static int conv_attr() {
+  cudaError_t e = cudaFuncSetAttribute(k_conv<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ConvSmem));
+  if (e != cudaSuccess) return 1;
+  e = cudaFuncSetAttribute(k_conv<MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
+  return e != cudaSuccess;
+}
 int conv_kernel_init() {
-  cudaError_t e = cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ConvSmem));
-  if (e != cudaSuccess) return 1;
-  e = cudaFuncSetAttribute(k_conv, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
-  if (e != cudaSuccess) return 1;
-  return 0;
+  if (const char *env = getenv("RELXILL_B200_CONV_MINB")) g_conv_minb = atoi(env);
+  return conv_attr<1>() || conv_attr<2>();
 }
 
 void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
@@ -435,7 +448,11 @@ void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
   ConvArgs A;
   A.user_e = user_e; A.n_flux = n_flux; A.out = out; A.total = total; A.which = which;
   A.nz_stride = S.nz_cap; A.ne_stride = S.ne_line_cap; A.mode = mode;
-  k_conv<<<(unsigned) n, CONV_NT, sizeof(ConvSmem), st>>>(vps, T, S, A);
+  A.rb_ii = reinterpret_cast<const int2 *>(T.xill[which].rb_ii);
+  A.rb_dd = reinterpret_cast<const double2 *>(T.xill[which].rb_dd);
+  A.xstride = T.xill[which].stride;
+  if (g_conv_minb == 1) k_conv<1><<<(unsigned) n, CONV_NT, sizeof(ConvSmem), st>>>(vps, T, S, A);
+  else k_conv<2><<<(unsigned) n, CONV_NT, sizeof(ConvSmem), st>>>(vps, T, S, A);
 }
 
 }  // namespace rx
