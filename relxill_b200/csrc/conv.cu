@@ -19,8 +19,6 @@
 // one point every 8, which makes every pass's gather and scatter bank-conflict free per quarter-warp.
 #include <cuda_runtime.h>
 
-#include <cstdlib>
-
 #include "common.h"
 #include "devutil.cuh"
 #include "kernels.h"
@@ -113,9 +111,10 @@ __device__ __forceinline__ void fft8(double (&r)[8], double (&i)[8]) {
 // Forward FFT of 4096 points; all CONV_NT threads call.  The input arrives in registers: thread j holds the points
 // j + 512 q, q = 0..7 (exactly what the first pass needs), so the packing code hands its values over without a
 // round trip through shared memory.  Result in the padded array z.
-// The twiddles of pass p are w^q with w = exp(-2 pi i k / (8 ns)), k = j mod ns: they depend on the thread only,
-// so the caller keeps the three w (one per pass) in registers for the whole kernel; w^2 and w^4 come from
-// squarings and the rest from products — no table reads inside the transform.
+// The twiddles of pass p are w^q with w = exp(-2 pi i k / (8 ns)), k = j mod ns: they depend on the thread only.
+// The last pass's w stays in registers for the whole kernel, the 8 + 64 distinct ones of passes 1 and 2 come from
+// a small shared table (tw12); w^2 and w^4 come from squarings and the rest from products — no global table
+// reads inside the transform.
 __device__ __forceinline__ void fft4096(double (&r)[8], double (&im)[8], double2 *z, const double2 *tw12, const double2 &w3) {
   const int j = threadIdx.x;
   fft8(r, im);
@@ -169,8 +168,9 @@ struct ConvArgs {
   int xstride;            // row stride of the zone spectra
 };
 
-template <int MINB>
-__global__ void __launch_bounds__(CONV_NT, MINB) k_conv(const VPar *__restrict__ vps, DevTables T, Scratch S, ConvArgs A) {
+// two CTAs per SM (64 registers): with one CTA and 128 registers nothing spills, but 16 warps hide too little
+// latency (13.4 ms against 10.5)
+__global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vps, DevTables T, Scratch S, ConvArgs A) {
   extern __shared__ __align__(16) unsigned char smraw[];
   ConvSmem &sm = *reinterpret_cast<ConvSmem *>(smraw);
   const int v = blockIdx.x, t = threadIdx.x;
@@ -431,16 +431,11 @@ __global__ void __launch_bounds__(CONV_NT, MINB) k_conv(const VPar *__restrict__
   }
 }
 
-static int g_conv_minb = 2;
-template <int MINB> static int conv_attr() {
-  cudaError_t e = cudaFuncSetAttribute(k_conv<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ConvSmem));
-  if (e != cudaSuccess) return 1;
-  e = cudaFuncSetAttribute(k_conv<MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
-  return e != cudaSuccess;
-}
 int conv_kernel_init() {
-  if (const char *env = getenv("RELXILL_B200_CONV_MINB")) g_conv_minb = atoi(env);
-  return conv_attr<1>() || conv_attr<2>();
+  cudaError_t e = cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ConvSmem));
+  if (e != cudaSuccess) return 1;
+  e = cudaFuncSetAttribute(k_conv, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
+  return e != cudaSuccess;
 }
 
 void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
@@ -451,8 +446,7 @@ void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
   A.rb_ii = reinterpret_cast<const int2 *>(T.xill[which].rb_ii);
   A.rb_dd = reinterpret_cast<const double2 *>(T.xill[which].rb_dd);
   A.xstride = T.xill[which].stride;
-  if (g_conv_minb == 1) k_conv<1><<<(unsigned) n, CONV_NT, sizeof(ConvSmem), st>>>(vps, T, S, A);
-  else k_conv<2><<<(unsigned) n, CONV_NT, sizeof(ConvSmem), st>>>(vps, T, S, A);
+  k_conv<<<(unsigned) n, CONV_NT, sizeof(ConvSmem), st>>>(vps, T, S, A);
 }
 
 }  // namespace rx
