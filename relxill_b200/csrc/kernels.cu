@@ -248,8 +248,10 @@ __global__ void __launch_bounds__(256) k_syspar(const VPar *__restrict__ vps, De
     __syncthreads();
   }
 
-  // ---- returning radiation
-  if (vp.return_rad != 0) {
+  // ---- returning radiation.  Pass 2 (with the correction factors) recomputes the whole emissivity, and between the
+  // passes only the alpha-disk ionisation gradient reads it (k_zone): every other vector that will get a second pass
+  // skips the uncorrected sum here
+  if (vp.return_rad != 0 && !(pass == 1 && vp.do_corr && vp.ion_grad_type != ION_ALPHA)) {
     const int is = vp.rr_spin;
     const size_t n2 = (size_t) RR_NR * RR_NR;
     const double *rlo_t = T.rr_rlo + (size_t) is * RR_NR, *rhi_t = T.rr_rhi + (size_t) is * RR_NR;
