@@ -61,6 +61,7 @@ struct Engine {
   size_t d_io_cap = 0;
   long max_chunk = 4096;
   long pipe_piece = 2072;     // vectors per pipelined piece of a host-buffer call (RELXILL_B200_PIPE)
+  long pipe_last = 888;       // ... and of the last piece, whose device->host copy nothing overlaps (RELXILL_B200_PIPE_LAST)
   cudaStream_t stream_c = nullptr, stream_d = nullptr;   // compute / copy streams of host-buffer calls
   bool profiling = false;
   bool keep_intermediates = false;   // store what only the test probes read (emission-angle tables)
@@ -172,6 +173,7 @@ int engine_init(Engine &E, const char *dir, int device) {
   if (const char *env = getenv("RELXILL_CONSTANT_DENSITY")) E.cfg.env_const_density = ((int) strtod(env, nullptr) == 1) ? 1 : 0;
   if (const char *env = getenv("RELXILL_B200_CHUNK")) E.max_chunk = std::max(1L, atol(env));
   if (const char *env = getenv("RELXILL_B200_PIPE")) E.pipe_piece = std::max(1L, atol(env));
+  if (const char *env = getenv("RELXILL_B200_PIPE_LAST")) E.pipe_last = std::max(0L, atol(env));
   if (!E.stream_c) cudaStreamCreateWithFlags(&E.stream_c, cudaStreamNonBlocking);
   if (!E.stream_d) cudaStreamCreateWithFlags(&E.stream_d, cudaStreamNonBlocking);
   if (kernels_init() != 0) {
@@ -274,11 +276,16 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
   const std::vector<double> &econv = E.tables->econv();
   std::vector<long> piece_n;
   {
-    long piece = S.cap;
-    if (pipe && b->n >= 2 * E.pipe_piece) piece = std::min(S.cap, E.pipe_piece);
-    long first = b->n % piece;
-    if (first == 0) first = std::min(piece, b->n);
-    for (long c0 = 0, nc = first; c0 < b->n; c0 += nc, nc = std::min(piece, b->n - c0)) piece_n.push_back(nc);
+    long piece = S.cap, last = 0;
+    if (pipe && b->n >= E.pipe_piece + E.pipe_last) {
+      piece = std::min(S.cap, E.pipe_piece);
+      last = std::min(E.pipe_last, piece);   // only the copy of the last piece is exposed: keep that piece short
+    }
+    const long body = b->n - last;
+    long first = body % piece;
+    if (first == 0) first = std::min(piece, body);
+    for (long c0 = 0, nc = first; c0 < body; c0 += nc, nc = std::min(piece, body - c0)) piece_n.push_back(nc);
+    if (last > 0) piece_n.push_back(last);
   }
   // ---- state cache: which vectors can keep the rows the arena still holds for them
   const bool one_piece = piece_n.size() == 1;

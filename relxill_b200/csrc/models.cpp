@@ -120,8 +120,9 @@ static void zone_grid(double rmin, double rmax, int nz, double h, double *rgrid)
   int indr = 0;
   if (h > rmin) {
     r_transition = h;
+    const double log_rmax = std::log(rmax), log_rmin = std::log(rmin);   // same bits as evaluating them per node
     for (int i = 0; i <= nz; i++) {
-      rgrid[i] = 1.0 * i / (nz) * (std::log(rmax) - std::log(rmin)) + std::log(rmin);
+      rgrid[i] = 1.0 * i / (nz) * (log_rmax - log_rmin) + log_rmin;
       rgrid[i] = std::exp(rgrid[i]);
     }
     indr = lower_index(rgrid, nz + 1, r_transition);
