@@ -1,9 +1,12 @@
 #!/bin/bash
 run() {
-  env "$@" python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
+  env "$@" python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
 d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); k=d['kernels_ms']
-print('$*', 'value %.0f e2e %.0f conv %.2f xill %.2f line %.2f' % (d['value'], d['e2e']['value'], k['k_conv'], k['k_xill'], k['k_line']))"
+print('$*', 'value %.0f ms/step %.3f e2e %.0f' % (d['value'], d['ms_per_step'], d['e2e']['value']))"
 }
-run RELXILL_B200_CONV_MINB=2
-run RELXILL_B200_CONV_MINB=1
+run RELXILL_B200_NO_AUX=1
+run RELXILL_B200_X=1
+run RELXILL_B200_NO_AUX=1
+run RELXILL_B200_X=1
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
