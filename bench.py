@@ -385,8 +385,21 @@ def run_ours(args):
         if same and dominant in prof["kernels"]:
             kk = prof["kernels"][dominant]
             traffic = kk["dram_bytes_read"] + kk["dram_bytes_write"]
+            # FP64 side of the roofline: flops counted by ncu (SASS thread instructions DADD/DMUL/DFMA of one launch of
+            # this kernel) over the launch time measured live above; peak = SMs x 64 FMA/clk x 2 x max SM clock
+            props = torch.cuda.get_device_properties(local)
+            fp64_peak = props.multi_processor_count * 128 * float((clocks or {}).get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+            fp64_rate = (kk["fp64_flop"] / (k_ms / max(k_cnt, 1) * 1e-3) / 1e12) if kk.get("fp64_flop") else None
             compute = {"fp64_pipe_pct": kk.get("fp64_pipe_pct"), "issue_active_pct": kk.get("issue_active_pct"),
+                       "fp64_tflops": fp64_rate, "fp64_peak_tflops": fp64_peak,
+                       "fp64_frac": (fp64_rate / fp64_peak) if fp64_rate else None,
+                       "fp64_peak_source": "nominal: SM count x 64 FMA/clk x 2 x max SM clock",
                        "source": prof.get("source")}
+            # the whole step: FP64 flops of all its kernels (same capture) over the measured step time
+            step_flop = sum(float(x.get("fp64_flop") or 0.0) for x in prof["kernels"].values())
+            if step_flop > 0:
+                compute["step_fp64_tflops"] = step_flop / (ms_total / args.steps * 1e-3) / 1e12
+                compute["step_fp64_frac"] = compute["step_fp64_tflops"] / fp64_peak
     except Exception:  # noqa: BLE001
         pass
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
