@@ -363,7 +363,7 @@ def run_ours(args):
     tot_k = sum(v[0] for v in ktimes.values()) or 1.0
     dominant = max(ktimes, key=lambda k: ktimes[k][0])
     nz = args.zones
-    nex = 2999
+    nex = ab.get("zone_spectrum_values") or 2999   # values per zone spectrum row as filed by k_xill / read by k_conv
     alg = {  # algorithmic bytes per launch of each kernel family
         "k_xill": ab["xillver"] + n * nz * nex * 8.0,                       # distinct table rows + zone spectra out
         "k_line": n * (1000 * 40 * 2 * 8.0 + 1000 * 5 * 8.0) + ab["line_profiles"],  # fine trff + radius scalars in, profiles out

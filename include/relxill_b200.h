@@ -110,7 +110,8 @@ void relxill_b200_free_batch(relxill_b200_batch *b);
  * rows per vector (U, host-counted from the zone indices the kernels produced) and the other
  * table/IO terms.  out[0]=bytes total, out[1]=sum of U over vectors, out[2]=xillver bytes,
  * out[3]=upper bound without cross-zone sharing, out[4]=bytes of the per-zone line profiles actually
- * produced (first to last non-zero bin of every zone), out[5..7] reserved (0). */
+ * produced (first to last non-zero bin of every zone), out[5]=values per zone spectrum row as filed by
+ * k_xill and read by k_conv, out[6..7] reserved (0). */
 int relxill_b200_algorithmic_bytes(relxill_b200_batch *b, double *out8);
 /* Number of kernel launches issued by the last relxill_b200_run of `b`. */
 long relxill_b200_last_launches(relxill_b200_batch *b);
@@ -119,6 +120,15 @@ long relxill_b200_last_launches(relxill_b200_batch *b);
  * Returns the number of entries written (<= max). */
 void relxill_b200_set_profiling(int on);
 int relxill_b200_kernel_times(relxill_b200_batch *b, const char **names, double *ms, long *launches, int max);
+
+/* Grid on which the per-zone xillver spectra are blended: 1 (default) = the convolution grid — every table
+ * row is rebinned once at load (the reference rebins every zone spectrum of every evaluation,
+ * _rebin_spectrum, src/Relxill.cpp:461-463; the map is linear, so it commutes with the interpolation) and
+ * kept in fp64 next to the fp32 table; 0 = the table grid, each zone spectrum rebinned inside k_conv.
+ * Same results to rounding.  The environment variable RELXILL_B200_XILL_GRID=table, read at
+ * initialisation, selects 0 and skips building the copy (1.7x the table's bytes). */
+void relxill_b200_set_xill_grid(int conv_grid);
+int relxill_b200_get_xill_grid(void);
 
 /* Keep the intermediates that only the probes read (the fine emission-angle tables are otherwise not stored
  * unless a limb law needs them).  Off by default. */

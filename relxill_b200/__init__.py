@@ -4,7 +4,8 @@ Python here is a thin host-side mirror of the reference's local-model interface;
 librelxill_b200.so (hand-written CUDA behind a C ABI, include/relxill_b200.h).
 """
 from .api import (Batch, LocalModel, ModelEvalFailed, ModelNotFound, PARAM_NAMES, batch_eval, default_energy_grid,
-                  default_params, init, lmod, num_params, set_cache, set_num_zones, shutdown)
+                  default_params, init, lmod, num_params, get_xill_grid, set_cache, set_num_zones, set_xill_grid, shutdown)
 
 __all__ = ["Batch", "LocalModel", "ModelEvalFailed", "ModelNotFound", "PARAM_NAMES", "batch_eval",
-           "default_energy_grid", "default_params", "init", "lmod", "num_params", "set_cache", "set_num_zones", "shutdown"]
+           "default_energy_grid", "default_params", "init", "lmod", "num_params", "get_xill_grid", "set_cache",
+           "set_num_zones", "set_xill_grid", "shutdown"]

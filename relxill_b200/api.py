@@ -69,6 +69,16 @@ def set_cache(on: bool) -> None:
     _lib.lib().relxill_b200_set_cache(1 if on else 0)
 
 
+def set_xill_grid(conv_grid: bool) -> None:
+    """Where the per-zone xillver spectra are filed: on the convolution grid (default) or on the table grid
+    (include/relxill_b200.h); the results agree to rounding."""
+    _lib.lib().relxill_b200_set_xill_grid(1 if conv_grid else 0)
+
+
+def get_xill_grid() -> bool:
+    return bool(_lib.lib().relxill_b200_get_xill_grid())
+
+
 def num_params(model: str) -> int:
     n = _lib.lib().relxill_b200_num_params(model.encode())
     if n < 0:
@@ -171,7 +181,7 @@ class Batch:
         out = np.zeros(8)
         _lib.lib().relxill_b200_algorithmic_bytes(self._h, out)
         return dict(total=out[0], distinct_rows=out[1], xillver=out[2], xillver_upper_bound=out[3],
-                    line_profiles=out[4])
+                    line_profiles=out[4], zone_spectrum_values=out[5])
 
     def kernel_times(self) -> dict:
         names = (C.c_char_p * 16)()

@@ -65,6 +65,10 @@ struct Engine {
   cudaStream_t stream_c = nullptr, stream_d = nullptr;   // compute / copy streams of host-buffer calls
   bool profiling = false;
   bool keep_intermediates = false;   // store what only the test probes read (emission-angle tables)
+  // k_xill blends the convolution-grid copy of the table (rows rebinned once at load, xill.cu) and k_conv reads the zone
+  // spectra with plain coalesced loads; off (RELXILL_B200_XILL_GRID=table): no such copy is built, zone spectra on the
+  // table grid, rebinned per zone in k_conv
+  bool xill_conv_grid = true;
   // device buffers recycled between batches (cudaMalloc/cudaFree synchronise and cost milliseconds)
   std::vector<std::pair<size_t, void *>> pool;
   // Device-resident state cache.  The scratch arena keeps the intermediates of the batch that
@@ -174,6 +178,7 @@ int engine_init(Engine &E, const char *dir, int device) {
   if (const char *env = getenv("RELXILL_B200_CHUNK")) E.max_chunk = std::max(1L, atol(env));
   if (const char *env = getenv("RELXILL_B200_PIPE")) E.pipe_piece = std::max(1L, atol(env));
   if (const char *env = getenv("RELXILL_B200_PIPE_LAST")) E.pipe_last = std::max(0L, atol(env));
+  if (const char *env = getenv("RELXILL_B200_XILL_GRID")) E.xill_conv_grid = std::string(env) != "table";
   if (!E.stream_c) cudaStreamCreateWithFlags(&E.stream_c, cudaStreamNonBlocking);
   if (!E.stream_d) cudaStreamCreateWithFlags(&E.stream_d, cudaStreamNonBlocking);
   if (kernels_init() != 0) {
@@ -181,6 +186,7 @@ int engine_init(Engine &E, const char *dir, int device) {
     return -1;
   }
   E.tables = new Tables();
+  E.tables->set_conv_grid_copy(E.xill_conv_grid);
   const std::string err = E.tables->load(d);
   if (!err.empty()) {
     set_err(err);
@@ -218,6 +224,7 @@ struct relxill_b200_batch {
   unsigned char *d_reuse = nullptr;
   long n_reuse_rel = 0, n_reuse_all = 0;
   std::vector<double> energy;   // host copy of the grid (retained batches compare it)
+  int xill_conv_grid = 0;       // the last run filed its zone spectra on the convolution grid
 };
 
 namespace {
@@ -262,7 +269,9 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
   const int which = xtab < 0 ? 0 : xtab;
   const bool relxill = (m.type == T_RELXILL);
   const int ne_line = (m.type == T_LINE) ? b->n_flux : NCONV;
-  const int nex_stride = (relxill || m.type == T_XILL) ? E.tables->xill_host(xtab).stride : 1;
+  const int nex_stride = (relxill || m.type == T_XILL) ? std::max(E.tables->xill_host(xtab).stride, E.tables->xill_host(xtab).xc_stride) : 1;
+  const int cgrid = (relxill && E.xill_conv_grid && E.tables->xill_host(xtab).has_conv_copy) ? 1 : 0;
+  b->xill_conv_grid = cgrid;
   const int n_incl = relxill ? E.tables->xill_host(xtab).n_incl : 0;
   const bool xillver = (m.type == T_XILL);
   const bool nth = (relxill || xillver) && m.prim == PRIM_NTHCOMP;
@@ -358,13 +367,13 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
     } else {
       tm.begin(); launch_line(vps, T, S, nc, T.econv, NCONV, 0, relxill ? b->nz_max : 1, st); tm.end(KF_LINE);
       if (relxill) {
-        tm.begin(); launch_xill(vps, T, S, nc, which, b->nz_max, E.tables->xill_host(xtab).n_ener, n_incl, st); tm.end(KF_XILL);
-        tm.begin(); launch_conv(vps, T, S, nc, b->d_energy, b->n_flux, out, E.d_total, which, 0, st); tm.end(KF_CONV);
+        tm.begin(); launch_xill(vps, T, S, nc, which, cgrid, st); tm.end(KF_XILL);
+        tm.begin(); launch_conv(vps, T, S, nc, b->d_energy, b->n_flux, out, E.d_total, which, 0, cgrid, st); tm.end(KF_CONV);
         if (nth) {
           tm.begin(); launch_prim_nth(vps, T, S, nc, E.d_total, b->d_energy, b->n_flux, out, st); tm.end(KF_PRIMNTH);
         }
       } else {
-        tm.begin(); launch_conv(vps, T, S, nc, b->d_energy, b->n_flux, out, nullptr, 0, 1, st); tm.end(KF_CONV);
+        tm.begin(); launch_conv(vps, T, S, nc, b->d_energy, b->n_flux, out, nullptr, 0, 1, 0, st); tm.end(KF_CONV);
       }
     }
     CK(cudaMemcpyAsync(b->status.data() + c0, S.status, nc * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -464,6 +473,8 @@ void relxill_b200_set_num_zones(int n) { g_eng.cfg.env_num_zones = n; }
 void relxill_b200_set_profiling(int on) { g_eng.profiling = on != 0; }
 void relxill_b200_keep_intermediates(int on) { g_eng.keep_intermediates = on != 0; }
 void relxill_b200_set_cache(int on) { g_eng.cache_on = on != 0; }
+void relxill_b200_set_xill_grid(int conv_grid) { g_eng.xill_conv_grid = conv_grid != 0; }
+int relxill_b200_get_xill_grid(void) { return g_eng.xill_conv_grid ? 1 : 0; }
 
 int relxill_b200_num_params(const char *model) {
   const ModelDef *m = find_model(model);
@@ -749,6 +760,10 @@ int relxill_b200_algorithmic_bytes(relxill_b200_batch *b, double *out8) {
   }
   out8[4] = prof;
   out8[5] = out8[6] = out8[7] = 0.0;
+  if (m.type == T_RELXILL) {   // values per zone spectrum as k_xill files them and k_conv reads them
+    const XillHost &xh = E.tables->xill_host(model_xtab(m));
+    out8[5] = b->xill_conv_grid ? xh.xc_n : xh.n_ener;
+  }
   return 0;
 }
 
@@ -781,12 +796,29 @@ int relxill_b200_probe(relxill_b200_batch *b, long iv, const char *what, double 
   else if (w == "corr_flux") { src = S.corr_flux + v * NZMAX; n = vp.nz; }
   else if (w == "corr_gshift") { src = S.corr_gshift + v * NZMAX; n = vp.nz; }
   else if (w == "total") { src = E.d_total + v * NCONV; n = NCONV; }
-  else if (w == "zone") {
+  else if (w == "xill_ener") {   // bin edges of the xillver table of this model
+    const std::vector<double> &xe = E.tables->xill_host(model_xtab(*b->m)).ener;
+    n = xe.size();
+    if ((long) n > max_len) return -1;
+    for (size_t i = 0; i < n; i++) out[i] = xe[i];
+    return (int) n;
+  } else if (w == "xillc") {       // zone spectra on the convolution grid (zero outside the table's range)
+    const XillHost &xh = E.tables->xill_host(model_xtab(*b->m));
+    if (!b->xill_conv_grid) { set_err("probe: zone spectra are on the table grid (probe \"xill\")"); return -1; }
+    const int nz = vp.nz;
+    if ((long) nz * NCONV > max_len) return -1;
+    for (long i = 0; i < (long) nz * NCONV; i++) out[i] = 0.0;
+    for (int z = 0; z < nz; z++)
+      cudaMemcpy(out + (size_t) z * NCONV + xh.xc_first, S.xillz + (v * S.nz_cap + z) * xh.xc_stride,
+                 xh.xc_n * sizeof(double), cudaMemcpyDeviceToHost);
+    return nz * NCONV;
+  } else if (w == "zone") {
     n = vp.nz + 1;
     if ((long) n > max_len) return -1;
     for (size_t i = 0; i < n; i++) out[i] = vp.zone[i];
     return (int) n;
   } else if (w == "relflux" || w == "xill" || w == "dist") {
+    if (w == "xill" && b->xill_conv_grid) { set_err("probe: zone spectra are on the convolution grid (probe \"xillc\")"); return -1; }
     const int nz = vp.nz;
     const size_t len = (w == "relflux") ? (size_t) ((b->m->type == T_LINE) ? b->n_flux : NCONV)
                        : (w == "xill")  ? (size_t) E.tables->xill_host(model_xtab(*b->m)).n_ener
@@ -794,7 +826,7 @@ int relxill_b200_probe(relxill_b200_batch *b, long iv, const char *what, double 
     if ((long) (len * nz) > max_len) return -1;
     for (int z = 0; z < nz; z++) {
       const double *p = (w == "relflux") ? S.relflux + (v * S.nz_cap + z) * S.ne_line_cap
-                        : (w == "xill")  ? S.xillz + (v * S.nz_cap + z) * S.nex_stride
+                        : (w == "xill")  ? S.xillz + (v * S.nz_cap + z) * E.tables->xill_host(model_xtab(*b->m)).stride
                                          : S.dist + (v * NZMAX + z) * MAX_INCL;
       cudaMemcpy(out + z * len, p, len * sizeof(double), cudaMemcpyDeviceToHost);
       if (w == "relflux") {  // rows are only written inside the zone's bin range

@@ -78,6 +78,11 @@ struct XillDev {
   // fixed rebin map xillver grid -> convolution grid (same imin/imax/weights as _rebin_spectrum)
   const int *rb_ii;      // [NCONV][2] (imin, imax) of the rebin onto the convolution grid; (0, 0) with zero weights outside the source grid
   const double *rb_dd;   // [NCONV][2] (dmin, dmax) partial-overlap fractions of the first and last source bin
+  // Convolution-grid copy of the table for the relxill models: every row rebinned at load onto the convolution bins
+  // that overlap the table grid, [xc_first, xc_first + xc_n), in fp64, rows of xc_stride doubles (null: not built;
+  // k_conv then rebins the zone spectra itself).  The rebin is linear, so it commutes with the blend (xill.cu)
+  int xc_first, xc_n, xc_stride;
+  const double *datac;   // [nnodes][n_incl][xc_stride]
 };
 
 struct DevTables {
@@ -136,7 +141,8 @@ struct Scratch {
   int *zrange;                                                // [cap][NZMAX][2] first/last bin written per zone (-1: none)
   double *dist;                                               // [cap][NZMAX][MAX_INCL]
   double *distpart;                                           // [cap][NR][10] per-radius parts of dist (k_fine -> k_dist)
-  double *xillz;                                              // [cap][nz_cap][nex_stride]
+  double *xillz;                                              // [cap][nz_cap][row]: zone spectra, rows of XillDev::xc_stride values on the
+                                                              // convolution grid (or of XillDev::stride on the table grid, see api.cu)
   int *status;                                                // [cap]
   // Re-use of the previous run's device-resident state (api.cu: the arena still holds this batch): per vector,
   // REUSE_REL = the relativistic half (k_syspar, k_fine, k_dist, k_line outputs) is still valid, REUSE_ALL = the

@@ -31,7 +31,8 @@ __device__ __forceinline__ int cv_pad(int i) { return i + (i >> 3); }
 
 struct ConvSmem {
   double2 z[CV_PADN];
-  double ar[NCONV / 2 + 1], ai[NCONV / 2 + 1];   // accumulated spectrum; reused as the final 4096-bin result
+  double2 acc[NCONV / 2 + 1];                    // accumulated half spectrum (one 128-bit access per bin); reused as
+                                                 // the final 4096-bin result (4098 doubles)
   double red[4 * (CONV_NT / 32)];
   double bc[8];
   double part[4 * (CONV_NT / 32)];   // per-warp partial sums of the packing phase, finished after the transform
@@ -115,6 +116,10 @@ __device__ __forceinline__ void fft8(double (&r)[8], double (&i)[8]) {
 // The last pass's w stays in registers for the whole kernel, the 8 + 64 distinct ones of passes 1 and 2 come from
 // a small shared table (tw12); w^2 and w^4 come from squarings and the rest from products — no global table
 // reads inside the transform.
+// UPPER: only the upper half of the result (points 2048..4095, the thread's q = 4..7) is written to z; the lower
+// half (points j + 512 q, q < 4) stays in r/im — all the split of two real transforms needs, since the partner of
+// point k is point 4096 - k.
+template <bool UPPER>
 __device__ __forceinline__ void fft4096(double (&r)[8], double (&im)[8], double2 *z, const double2 *tw12, const double2 &w3) {
   const int j = threadIdx.x;
   fft8(r, im);
@@ -149,7 +154,7 @@ __device__ __forceinline__ void fft4096(double (&r)[8], double (&im)[8], double2
     __syncthreads();
     const int j0 = ((j - k) << 3) + k;       // (j / ns) * ns * 8 + k
 #pragma unroll
-    for (int q = 0; q < 8; q++) z[cv_pad(j0 + q * ns)] = make_double2(r[q], im[q]);
+    for (int q = (UPPER && pass == 3) ? 4 : 0; q < 8; q++) z[cv_pad(j0 + q * ns)] = make_double2(r[q], im[q]);
     __syncthreads();
   }
 }
@@ -166,10 +171,13 @@ struct ConvArgs {
   const int2 *rb_ii;      // rebin map of the xillver table in use (XillDev::rb_ii / rb_dd)
   const double2 *rb_dd;
   int xstride;            // row stride of the zone spectra
+  int xc_first, xc_n;     // CG: the zone spectra are on the convolution grid, bins [xc_first, xc_first + xc_n) (xill.cu)
 };
 
 // two CTAs per SM (64 registers): with one CTA and 128 registers nothing spills, but 16 warps hide too little
 // latency (13.4 ms against 10.5)
+// CG: k_xill filed the zone spectra on the convolution grid already, the packing phase is a plain coalesced load
+template <bool CG>
 __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vps, DevTables T, Scratch S, ConvArgs A) {
   extern __shared__ __align__(16) unsigned char smraw[];
   ConvSmem &sm = *reinterpret_cast<ConvSmem *>(smraw);
@@ -187,7 +195,7 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
   const int i1 = T.conv_i1kev, b0 = T.conv_b0, b1 = T.conv_b1;
   const double2 *tw = reinterpret_cast<const double2 *>(T.tw);
   const double2 *cw = reinterpret_cast<const double2 *>(T.conv_w);
-  for (int k = t; k <= NCONV / 2; k += CONV_NT) { sm.ar[k] = 0.0; sm.ai[k] = 0.0; }
+  for (int k = t; k <= NCONV / 2; k += CONV_NT) sm.acc[k] = make_double2(0.0, 0.0);
   // tw[m] = exp(-2 pi i m / 4096): the last pass's twiddle of this thread stays in registers, the 8 + 64 distinct
   // ones of the two passes before it sit in shared memory (conflict-free: consecutive threads, consecutive entries)
   const double2 w3 = __ldg(tw + t);
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
       // the next zone's two rows are pulled into L2 while this zone is transformed: the packing loads are the
       // kernel's only DRAM accesses and there are too few warps to hide their latency (one 128-byte line per thread:
       // 188 lines of the zone spectrum, up to 256 of the written part of the line profile)
-      if (t < 188) {
+      if (t < (CG ? (A.xc_n + 15) >> 4 : 188)) {
         prefetch_l2(xz + A.xstride + t * 16);
       } else if (t >= 192 && t < 448) {
         const int nlo = zr_v[2 * z + 2], nhi = zr_v[2 * z + 3];
@@ -238,13 +246,18 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
 #pragma unroll
       for (int u = 0; u < 8; u++) {
         const int i = t + u * CONV_NT;
-        const int2 ii = __ldg(A.rb_ii + i);      // (0, 0) with zero weights outside the table grid
-        const double2 dd = __ldg(A.rb_dd + i);
         double f = 0.0;
-        f += xz[ii.x] * dd.x + xz[ii.y] * dd.y;
-        if (ii.y - ii.x >= 2) {
-          f += xz[ii.x + 1];
-          for (int jj = ii.x + 2; jj <= ii.y - 1; jj++) f += xz[jj];
+        if (CG) {
+          const int c = i - A.xc_first;
+          if ((unsigned) c < (unsigned) A.xc_n) f = xz[c];
+        } else {
+          const int2 ii = __ldg(A.rb_ii + i);      // (0, 0) with zero weights outside the table grid
+          const double2 dd = __ldg(A.rb_dd + i);
+          f += xz[ii.x] * dd.x + xz[ii.y] * dd.y;
+          if (ii.y - ii.x >= 2) {
+            f += xz[ii.x + 1];
+            for (int jj = ii.x + 2; jj <= ii.y - 1; jj++) f += xz[jj];
+          }
         }
         const int ku = ((c0 + u) & 7) << 9;
         const double r = ((unsigned) (r0 + ku - rjlo) <= (unsigned) rjw) ? relr[ku] : 0.0;
@@ -303,14 +316,19 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
     }
 #pragma unroll
     for (int u = 0; u < 8; u++) im[u] *= yscale;
-    fft4096(re, im, sm.z, sm.tw12, w3);
-    // ---- split, product spectrum, band sum of the convolved zone in the frequency domain
+    fft4096<true>(re, im, sm.z, sm.tw12, w3);
+    // ---- split, product spectrum, band sum of the convolved zone in the frequency domain.  Point k = t + 512 nk
+    // (nk < 4) is still in the thread's registers; its partner 4096 - k is point q = 7 - nk of thread 512 - t, in the
+    // stored upper half (k = 0 is its own partner; thread 0 also takes k = 2048, its own point q = 4)
     double dot[1] = {0.0};
     double pr_[5], pi_[5];
     int nk = 0;
+#pragma unroll
     for (int k = t; k <= NCONV / 2; k += CONV_NT, nk++) {
+      if (nk == 4 && t != 0) break;
       const int kk = (NCONV - k) & (NCONV - 1);
-      const double2 p = sm.z[cv_pad(k)], q = sm.z[cv_pad(kk)];
+      const double2 p = (nk < 4) ? make_double2(re[nk], im[nk]) : sm.z[cv_pad(k)];
+      const double2 q = (k == 0) ? p : sm.z[cv_pad(kk)];
       const double a = p.x, b = p.y, c = q.x, d = q.y;
       const double Xr = 0.5 * (a + c), Xi = 0.5 * (b - d);
       const double Yr = 0.5 * (b + d), Yi = 0.5 * (c - a);
@@ -347,8 +365,10 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
     const double norm = s_rel * s_xill / dot[0];
     nk = 0;
     for (int k = t; k <= NCONV / 2; k += CONV_NT, nk++) {
-      sm.ar[k] += norm * pr_[nk];
-      sm.ai[k] += norm * pi_[nk];
+      double2 a = sm.acc[k];
+      a.x += norm * pr_[nk];
+      a.y += norm * pi_[nk];
+      sm.acc[k] = a;
     }
     __syncthreads();
   }
@@ -359,13 +379,15 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
     for (int u = 0; u < 8; u++) {   // Hermitian extension of the accumulated half spectrum, conjugated
       const int i = t + u * CONV_NT;
       const int k = (i <= NCONV / 2) ? i : NCONV - i;
-      const double ai = (k == 0 || k == NCONV / 2) ? 0.0 : sm.ai[k];
-      re[u] = sm.ar[k];
+      const double2 a = sm.acc[k];
+      const double ai = (k == 0 || k == NCONV / 2) ? 0.0 : a.y;
+      re[u] = a.x;
       im[u] = (i <= NCONV / 2) ? -ai : ai;
     }
-    fft4096(re, im, sm.z, sm.tw12, w3);
+    fft4096<false>(re, im, sm.z, sm.tw12, w3);
   }
-  double *acc = sm.ar;   // ar and ai are contiguous: 4098 doubles
+  __syncthreads();       // every thread has taken its part of the accumulated spectrum
+  double *acc = reinterpret_cast<double *>(sm.acc);   // 4098 doubles
   if (reuse_all) {
     __syncthreads();
     for (int i = t; i < NCONV; i += CONV_NT) acc[i] = A.total[(size_t) v * NCONV + i];
@@ -432,21 +454,29 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
 }
 
 int conv_kernel_init() {
-  cudaError_t e = cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ConvSmem));
+  cudaError_t e = cudaFuncSetAttribute(k_conv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ConvSmem));
   if (e != cudaSuccess) return 1;
-  e = cudaFuncSetAttribute(k_conv, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
+  e = cudaFuncSetAttribute(k_conv<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return 1;
+  e = cudaFuncSetAttribute(k_conv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ConvSmem));
+  if (e != cudaSuccess) return 1;
+  e = cudaFuncSetAttribute(k_conv<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
   return e != cudaSuccess;
 }
 
 void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
-                 double *out, double *total, int which, int mode, cudaStream_t st) {
+                 double *out, double *total, int which, int mode, int conv_grid, cudaStream_t st) {
   ConvArgs A;
   A.user_e = user_e; A.n_flux = n_flux; A.out = out; A.total = total; A.which = which;
   A.nz_stride = S.nz_cap; A.ne_stride = S.ne_line_cap; A.mode = mode;
   A.rb_ii = reinterpret_cast<const int2 *>(T.xill[which].rb_ii);
   A.rb_dd = reinterpret_cast<const double2 *>(T.xill[which].rb_dd);
-  A.xstride = T.xill[which].stride;
-  k_conv<<<(unsigned) n, CONV_NT, sizeof(ConvSmem), st>>>(vps, T, S, A);
+  const bool cg = conv_grid && mode == 0;
+  A.xstride = cg ? T.xill[which].xc_stride : T.xill[which].stride;
+  A.xc_first = T.xill[which].xc_first;
+  A.xc_n = T.xill[which].xc_n;
+  if (cg) k_conv<true><<<(unsigned) n, CONV_NT, sizeof(ConvSmem), st>>>(vps, T, S, A);
+  else k_conv<false><<<(unsigned) n, CONV_NT, sizeof(ConvSmem), st>>>(vps, T, S, A);
 }
 
 }  // namespace rx

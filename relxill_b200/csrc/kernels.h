@@ -18,10 +18,10 @@ void launch_line(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
                  int grid_mode, int nz_max, cudaStream_t st);
 int line_max_bins();  // largest energy grid the line kernel handles in one pass
 void launch_linefinish(const VPar *vps, const Scratch &S, long n, int n_ener, double *out, cudaStream_t st);
-void launch_xill(const VPar *vps, const DevTables &T, const Scratch &S, long n, int which, int nz_max, int n_ener,
-                 int n_incl, cudaStream_t st);
+// conv_grid != 0: zone spectra are filed (k_xill) and read (k_conv) on the convolution grid, see xill.cu
+void launch_xill(const VPar *vps, const DevTables &T, const Scratch &S, long n, int which, int conv_grid, cudaStream_t st);
 void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
-                 double *out, double *total, int which, int mode, cudaStream_t st);
+                 double *out, double *total, int which, int mode, int conv_grid, cudaStream_t st);
 
 void launch_xillver(const VPar *vps, const DevTables &T, const Scratch &S, long n, int which, const double *user_e,
                     int n_flux, double *out, int stride, cudaStream_t st);

@@ -12,6 +12,7 @@
 //     (band energy flux, band photon flux before/after the g=2/3 shift) are reduced to three
 //     scalars per table node at load, so the kernels never re-read the spectra for them.
 #include "tables.h"
+#include "kernels.h"
 
 #include <cuda_runtime.h>
 
@@ -374,6 +375,52 @@ std::string Tables::load_xill(int which) {
   const double gref = 2. / 3.;
   for (int i = 0; i <= ne; i++) ez[i] = xh.ener[i] / gref;
 
+  // fixed rebin map xillver grid -> convolution grid
+  std::vector<int> imin_v(NCONV), imax_v(NCONV);
+  std::vector<double> dmin_v(NCONV), dmax_v(NCONV);
+  {
+    const double *e0 = xh.ener.data(), *e = econv_.data();
+    int imin = 0, imax = 0;
+    for (int ii = 0; ii < NCONV; ii++) {
+      imin_v[ii] = -1; imax_v[ii] = -1; dmin_v[ii] = 0; dmax_v[ii] = 0;
+      if ((e0[0] <= e[ii + 1]) && (e0[ne] >= e[ii])) {
+        while (imin <= ne && e0[imin] <= e[ii]) imin++;
+        if (imin > 0) imin--;
+        while (imax < ne && e0[imax] <= e[ii + 1]) imax++;
+        if (imax > 0) imax--;
+        double elo_ = e[ii], ehi_ = e[ii + 1];
+        if (elo_ < e0[imin]) elo_ = e0[imin];
+        if (ehi_ > e0[imax + 1]) ehi_ = e0[imax + 1];
+        imin_v[ii] = imin; imax_v[ii] = imax;
+        if (imax == imin) {
+          dmin_v[ii] = (ehi_ - elo_) / (e0[imin + 1] - e0[imin]);
+        } else {
+          dmin_v[ii] = (e0[imin + 1] - elo_) / (e0[imin + 1] - e0[imin]);
+          dmax_v[ii] = (ehi_ - e0[imax]) / (e0[imax + 1] - e0[imax]);
+        }
+      }
+    }
+  }
+  // the convolution bins that overlap the table grid form one interval [first, last]
+  int first = -1, last = -2;
+  for (int i = 0; i < NCONV; i++)
+    if (imin_v[i] >= 0) { if (first < 0) first = i; last = i; }
+  if (first < 0) { mf_close(f); return "xillver table: energy grid does not overlap the convolution grid"; }
+  for (int i = first; i <= last; i++)
+    if (imin_v[i] < 0) { mf_close(f); return "xillver table: energy grid is not monotone"; }
+  xh.xc_first = first;
+  xh.xc_n = last - first + 1;
+  xh.xc_stride = ((xh.xc_n + 31) / 32) * 32;
+  // Convolution-grid copy (relxill models only need it; standalone xillver models interpolate the table grid): every
+  // row rebinned exactly like _rebin_spectrum would rebin it (src/relutility.c:549-601), kept in fp64
+  const bool want_c = conv_grid_copy_ && (which == XT_STD || which == XT_CP || which == XT_NS || which == XT_CO);
+  double *d_datac = nullptr;
+  const size_t total_c = (size_t) S->nrows * xh.xc_stride;
+  if (want_c) {
+    if (cudaMalloc((void **) &d_datac, total_c * sizeof(double)) != cudaSuccess) { mf_close(f); return "out of device memory (xillver table, convolution-grid copy)"; }
+    allocs_.push_back(d_datac);
+    dev_bytes_ += total_c * sizeof(double);
+  }
   float *d_data = nullptr;
   const size_t total = (size_t) nrows * st;
   if (cudaMalloc((void **) &d_data, total * sizeof(float)) != cudaSuccess) { mf_close(f); return "out of device memory (xillver table)"; }
@@ -383,6 +430,7 @@ std::string Tables::load_xill(int which) {
   // stream node blocks through a staging buffer
   const long nodes_per_blk = 256;
   std::vector<float> stage((size_t) nodes_per_blk * ni * st, 0.f);
+  std::vector<double> stage_c(want_c ? (size_t) nodes_per_blk * ni * xh.xc_stride : 0, 0.0);
   for (long n0 = 0; n0 < xh.nnodes; n0 += nodes_per_blk) {
     const long nb = std::min(nodes_per_blk, xh.nnodes - n0);
     for (long nd = 0; nd < nb; nd++) {
@@ -416,35 +464,26 @@ std::string Tables::load_xill(int which) {
       ef[node] = s_ef; p1[node] = s_p1; p2[node] = s_p2;
     }
     cudaMemcpy(d_data + (size_t) n0 * ni * st, stage.data(), (size_t) nb * ni * st * sizeof(float), cudaMemcpyHostToDevice);
+    if (want_c) {
+      for (long r = 0; r < nb * ni; r++) {
+        const float *src = stage.data() + (size_t) r * st;
+        double *dst = stage_c.data() + (size_t) r * xh.xc_stride;
+        for (int c = 0; c < xh.xc_n; c++) {
+          const int i0 = imin_v[first + c], i1 = imax_v[first + c];
+          double v = (double) src[i0] * dmin_v[first + c] + (double) src[i1] * dmax_v[first + c];   // k_conv's order of operations
+          if (i1 - i0 >= 2) {
+            v += (double) src[i0 + 1];
+            for (int jj = i0 + 2; jj <= i1 - 1; jj++) v += (double) src[jj];
+          }
+          dst[c] = v;
+        }
+      }
+      cudaMemcpy(d_datac + (size_t) n0 * ni * xh.xc_stride, stage_c.data(), (size_t) nb * ni * xh.xc_stride * sizeof(double),
+                 cudaMemcpyHostToDevice);
+    }
   }
   mf_close(f);
 
-  // fixed rebin map xillver grid -> convolution grid
-  std::vector<int> imin_v(NCONV), imax_v(NCONV);
-  std::vector<double> dmin_v(NCONV), dmax_v(NCONV);
-  {
-    const double *e0 = xh.ener.data(), *e = econv_.data();
-    int imin = 0, imax = 0;
-    for (int ii = 0; ii < NCONV; ii++) {
-      imin_v[ii] = -1; imax_v[ii] = -1; dmin_v[ii] = 0; dmax_v[ii] = 0;
-      if ((e0[0] <= e[ii + 1]) && (e0[ne] >= e[ii])) {
-        while (imin <= ne && e0[imin] <= e[ii]) imin++;
-        if (imin > 0) imin--;
-        while (imax < ne && e0[imax] <= e[ii + 1]) imax++;
-        if (imax > 0) imax--;
-        double elo_ = e[ii], ehi_ = e[ii + 1];
-        if (elo_ < e0[imin]) elo_ = e0[imin];
-        if (ehi_ > e0[imax + 1]) ehi_ = e0[imax + 1];
-        imin_v[ii] = imin; imax_v[ii] = imax;
-        if (imax == imin) {
-          dmin_v[ii] = (ehi_ - elo_) / (e0[imin + 1] - e0[imin]);
-        } else {
-          dmin_v[ii] = (e0[imin + 1] - elo_) / (e0[imin + 1] - e0[imin]);
-          dmax_v[ii] = (ehi_ - e0[imax]) / (e0[imax + 1] - e0[imax]);
-        }
-      }
-    }
-  }
   XillDev &xd = dt_.xill[which];
   xd.npar = xh.npar;
   for (int i = 0; i < 6; i++) { xd.nvals[i] = xh.nvals[i]; xd.pindex[i] = xh.pindex[i]; xd.vals[i] = nullptr; }
@@ -465,6 +504,10 @@ std::string Tables::load_xill(int which) {
   xd.rb_ii = upload(ii_v);
   xd.rb_dd = upload(dd_v);
   if (!xd.rb_dd) return "out of device memory (xillver table)";
+  xd.xc_first = xh.xc_first; xd.xc_n = xh.xc_n; xd.xc_stride = xh.xc_stride;
+  xd.datac = d_datac;
+  xh.has_conv_copy = d_datac != nullptr;
+  xh.bytes_c = want_c ? total_c * sizeof(double) : 0;
   xh.loaded = true;
   return "";
 }

@@ -10,6 +10,9 @@ namespace rx {
 struct XillHost {
   bool loaded = false;
   int npar = 0, nvals[6] = {0}, pindex[6] = {0}, n_ener = 0, n_incl = 0, stride = 0;
+  int xc_first = 0, xc_n = 0, xc_stride = 0;   // convolution bins overlapping the table grid (XillDev)
+  bool has_conv_copy = false;                  // the fp64 convolution-grid copy of the rows is in HBM
+  size_t bytes_c = 0;
   long nnodes = 0;
   std::vector<float> vals[6];
   std::vector<double> ener;
@@ -30,7 +33,9 @@ class Tables {
   bool has_rel() const { return have_rel_; }
   const std::vector<double> &econv() const { return econv_; }
   size_t device_bytes() const { return dev_bytes_; }
-  double conv_cf_deviation() const { return conv_cf_dev_; }   // max |E_mid/dE / const - 1| on the convolution grid
+  double conv_cf_deviation() const { return conv_cf_dev_; }
+  // build the convolution-grid copy of the xillver tables that are loaded from now on (default on)
+  void set_conv_grid_copy(bool on) { conv_grid_copy_ = on; }   // max |E_mid/dE / const - 1| on the convolution grid
 
  private:
   std::string dir_;
@@ -41,6 +46,7 @@ class Tables {
   std::vector<void *> allocs_;
   size_t dev_bytes_ = 0;
   double conv_cf_dev_ = 0.0;
+  bool conv_grid_copy_ = true;
 
   template <class T> const T *upload(const std::vector<T> &v);
   template <class T> const T *upload(const T *p, size_t n);

@@ -21,6 +21,14 @@
 // shuffle-add per zone) to keep the same register footprint.
 // One CTA per (vector, tile of energy bins); table rows stream in as coalesced float loads, the zone spectra
 // leave as coalesced double stores.
+//  * CG (convolution-grid) variant.  The reference rebins every zone spectrum from the table grid onto the
+//    convolution grid (_rebin_spectrum, src/relutility.c:549-601, per zone in src/Relxill.cpp:461-463).  That map
+//    is linear and fixed, so it commutes with the blend: tables.cu applies it ONCE PER TABLE ROW at load and keeps
+//    the rebinned rows in fp64 (XillDev::datac; fp64 so that nothing is rounded that the reference does not
+//    round).  This kernel then blends straight on the convolution grid: same code, a thread owns a convolution
+//    bin, the rows are doubles (no float -> double conversions, which bound the corner refresh on the table
+//    grid), only the xc_n (about 2520 of 4096) bins that overlap the table exist, and k_conv reads its input with
+//    plain coalesced loads — no rebin map, no dependent gathers.
 #include <cuda_runtime.h>
 
 #include "common.h"
@@ -35,9 +43,15 @@ constexpr int XL_NI = 10;   // inclination nodes handled (all xillver tables hav
 // NS rest corners per zone, SPLIT lanes per energy bin; ST > 0: the table has XL_NI inclinations and rows of ST floats,
 // so the loads of a corner refresh address [pointer + immediate] (the refresh is a third of the kernel's instructions
 // when every row offset is 64-bit arithmetic on run-time strides); ST = 0: any table
-template <int NS, int SPLIT, int ST>
+template <bool CG> struct RowT { typedef float type; };
+template <> struct RowT<true> { typedef double type; };
+
+// ST > 0: row length of the table in use as a constant (3008 floats on the table grid, the xc_stride of the 2999-bin
+// xillver grid on the convolution grid)
+template <int NS, int SPLIT, int ST, bool CG>
 __global__ void __launch_bounds__(XL_NT, 4) k_xill(const VPar *__restrict__ vps, DevTables T, Scratch S, int which,
                                                    int nz_stride) {
+  typedef typename RowT<CG>::type row_t;
   constexpr int NIT = XL_NI / SPLIT;          // inclinations per lane
   constexpr int EPC = XL_NT / SPLIT;          // energy bins per CTA
   __shared__ __align__(16) double s_w[NZMAX * NS];
@@ -51,7 +65,8 @@ __global__ void __launch_bounds__(XL_NT, 4) k_xill(const VPar *__restrict__ vps,
   const int nz = vp.nz;
   const XillDev &X = T.xill[which];
   const int ni = ST ? XL_NI : X.n_incl;
-  const int st = ST ? ST : X.stride, ne = X.n_ener;
+  const int st = ST ? ST : (CG ? X.xc_stride : X.stride), ne = CG ? X.xc_n : X.n_ener;
+  const row_t *xdata = CG ? reinterpret_cast<const row_t *>(X.datac) : reinterpret_cast<const row_t *>(X.data);
   // lane -> (energy bin, inclination part): with SPLIT = 2 the two halves of a warp share 16 bins
   const int lane = t & 31, warp = t >> 5;
   const int part = (SPLIT == 2) ? (lane >> 4) : 0;
@@ -67,11 +82,11 @@ __global__ void __launch_bounds__(XL_NT, 4) k_xill(const VPar *__restrict__ vps,
     s_dist[q] = (m < ni) ? S.dist[((size_t) v * NZMAX + z) * MAX_INCL + m] : 0.0;
   }
   for (int z = t; z < nz; z += XL_NT) s_rn[z] = 1.0 / S.normch[(size_t) v * NZMAX + z];
-  const float *base[4];
+  const row_t *base[4];
   double gaw[4];
 #pragma unroll
   for (int q = 0; q < 4; q++) {
-    base[q] = X.data + (size_t) S.xga_off[(size_t) v * 4 + q] * ni * st + (live ? e : 0) + (size_t) (part * NIT) * st;
+    base[q] = xdata + (size_t) S.xga_off[(size_t) v * 4 + q] * ni * st + (live ? e : 0) + (size_t) (part * NIT) * st;
     gaw[q] = S.xga_w[(size_t) v * 4 + q];
   }
   __syncthreads();
@@ -92,7 +107,7 @@ __global__ void __launch_bounds__(XL_NT, 4) k_xill(const VPar *__restrict__ vps,
       if (off != cur[s]) {
         cur[s] = off;
         const size_t ro = (size_t) off * ni * st;
-        const float *p0 = base[0] + ro, *p1 = base[1] + ro, *p2 = base[2] + ro, *p3 = base[3] + ro;
+        const row_t *p0 = base[0] + ro, *p1 = base[1] + ro, *p2 = base[2] + ro, *p3 = base[3] + ro;
 #pragma unroll
         for (int m = 0; m < NIT; m++) {
           if (ST || part * NIT + m < ni) {
@@ -121,21 +136,32 @@ __global__ void __launch_bounds__(XL_NT, 4) k_xill(const VPar *__restrict__ vps,
 
 int xill_kernel_init() { return 0; }
 
-void launch_xill(const VPar *vps, const DevTables &T, const Scratch &S, long n, int which, int nz_max, int n_ener,
-                 int n_incl, cudaStream_t st) {
-  (void) nz_max;
-  (void) n_incl;   // tables with more than XL_NI inclinations are rejected at load (tables.cu)
+constexpr int XL_CST = 2528;   // xc_stride of the 2999-bin xillver grid (2521 convolution bins overlap it)
+
+template <bool CG>
+static void launch_xill_t(const VPar *vps, const DevTables &T, const Scratch &S, long n, int which, cudaStream_t st) {
   const XillDev &X = T.xill[which];
-  const bool std_rows = (X.stride == 3008 && X.n_incl == XL_NI);   // every table of the 2999-bin xillver grid
+  // every table of the 2999-bin xillver grid has these row lengths
+  const bool std_rows = (X.n_incl == XL_NI) && (CG ? X.xc_stride == XL_CST : X.stride == 3008);
+  constexpr int ST = CG ? XL_CST : 3008;
+  const int nb = CG ? X.xc_n : X.n_ener;   // bins a vector's CTAs cover
   if (X.npar == 6) {
-    dim3 grid((n_ener + XL_NT / 2 - 1) / (XL_NT / 2), (unsigned) n);
-    if (std_rows) k_xill<8, 2, 3008><<<grid, XL_NT, 0, st>>>(vps, T, S, which, S.nz_cap);
-    else k_xill<8, 2, 0><<<grid, XL_NT, 0, st>>>(vps, T, S, which, S.nz_cap);
+    dim3 grid((nb + XL_NT / 2 - 1) / (XL_NT / 2), (unsigned) n);
+    if (std_rows) k_xill<8, 2, ST, CG><<<grid, XL_NT, 0, st>>>(vps, T, S, which, S.nz_cap);
+    else k_xill<8, 2, 0, CG><<<grid, XL_NT, 0, st>>>(vps, T, S, which, S.nz_cap);
   } else {
-    dim3 grid((n_ener + XL_NT - 1) / XL_NT, (unsigned) n);
-    if (std_rows) k_xill<4, 1, 3008><<<grid, XL_NT, 0, st>>>(vps, T, S, which, S.nz_cap);
-    else k_xill<4, 1, 0><<<grid, XL_NT, 0, st>>>(vps, T, S, which, S.nz_cap);
+    dim3 grid((nb + XL_NT - 1) / XL_NT, (unsigned) n);
+    if (std_rows) k_xill<4, 1, ST, CG><<<grid, XL_NT, 0, st>>>(vps, T, S, which, S.nz_cap);
+    else k_xill<4, 1, 0, CG><<<grid, XL_NT, 0, st>>>(vps, T, S, which, S.nz_cap);
   }
+}
+
+// conv_grid: blend the rebinned rows (XillDev::datac) and file the zone spectra on the convolution grid (rows of
+// xc_stride) instead of the table grid (rows of stride); the caller checked that the table has them
+void launch_xill(const VPar *vps, const DevTables &T, const Scratch &S, long n, int which, int conv_grid, cudaStream_t st) {
+  // tables with more than XL_NI inclinations are rejected at load (tables.cu)
+  if (conv_grid) launch_xill_t<true>(vps, T, S, n, which, st);
+  else launch_xill_t<false>(vps, T, S, n, which, st);
 }
 
 }  // namespace rx
