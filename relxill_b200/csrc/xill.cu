@@ -58,7 +58,9 @@ __global__ void __launch_bounds__(XL_NT, 4) k_xill(const VPar *__restrict__ vps,
   __shared__ __align__(16) double s_dist[NZMAX * XL_NI];
   __shared__ double s_rn[NZMAX];
   __shared__ int s_off[NZMAX * NS];
-  const int v = blockIdx.y, t = threadIdx.x;
+  // tile-major launch order (blockIdx.x = vector): the CTAs resident on an SM at any time work on the SAME energy tile of
+  // different vectors, so the table rows that vectors share (MCMC walkers sit in the same table cell) hit in L1
+  const int v = blockIdx.x, tile = blockIdx.y, t = threadIdx.x;
   if (S.status[v] != ST_OK) return;
   if (S.reuse && (S.reuse[v] & REUSE_ALL)) return;
   const VPar &vp = vps[v];
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(XL_NT, 4) k_xill(const VPar *__restrict__ vps,
   // lane -> (energy bin, inclination part): with SPLIT = 2 the two halves of a warp share 16 bins
   const int lane = t & 31, warp = t >> 5;
   const int part = (SPLIT == 2) ? (lane >> 4) : 0;
-  const int e = blockIdx.x * EPC + ((SPLIT == 2) ? (warp * 16 + (lane & 15)) : t);
+  const int e = tile * EPC + ((SPLIT == 2) ? (warp * 16 + (lane & 15)) : t);
   const bool live = e < ne;
   for (int q = t; q < nz * NS; q += XL_NT) {
     const int z = q / NS, s = q - z * NS;
@@ -146,11 +148,11 @@ static void launch_xill_t(const VPar *vps, const DevTables &T, const Scratch &S,
   constexpr int ST = CG ? XL_CST : 3008;
   const int nb = CG ? X.xc_n : X.n_ener;   // bins a vector's CTAs cover
   if (X.npar == 6) {
-    dim3 grid((nb + XL_NT / 2 - 1) / (XL_NT / 2), (unsigned) n);
+    dim3 grid((unsigned) n, (nb + XL_NT / 2 - 1) / (XL_NT / 2));
     if (std_rows) k_xill<8, 2, ST, CG><<<grid, XL_NT, 0, st>>>(vps, T, S, which, S.nz_cap);
     else k_xill<8, 2, 0, CG><<<grid, XL_NT, 0, st>>>(vps, T, S, which, S.nz_cap);
   } else {
-    dim3 grid((nb + XL_NT - 1) / XL_NT, (unsigned) n);
+    dim3 grid((unsigned) n, (nb + XL_NT - 1) / XL_NT);
     if (std_rows) k_xill<4, 1, ST, CG><<<grid, XL_NT, 0, st>>>(vps, T, S, which, S.nz_cap);
     else k_xill<4, 1, 0, CG><<<grid, XL_NT, 0, st>>>(vps, T, S, which, S.nz_cap);
   }
