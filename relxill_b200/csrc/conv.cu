@@ -35,6 +35,7 @@ struct ConvSmem {
                                                  // the final 4096-bin result (4098 doubles)
   double red[4 * (CONV_NT / 32)];
   double bc[8];
+  double nyq;                        // product spectrum at the Nyquist bin (thread 0)
   double part[4 * (CONV_NT / 32)];   // per-warp partial sums of the packing phase, finished after the transform
   double2 tw12[8 + 64];              // twiddles of passes 1 and 2: exp(-2 pi i k / 64), k < 8; exp(-2 pi i k / 512), k < 64
 };
@@ -120,7 +121,7 @@ __device__ __forceinline__ void fft8(double (&r)[8], double (&i)[8]) {
 // half (points j + 512 q, q < 4) stays in r/im — all the split of two real transforms needs, since the partner of
 // point k is point 4096 - k.
 template <bool UPPER>
-__device__ __forceinline__ void fft4096(double (&r)[8], double (&im)[8], double2 *z, const double2 *tw12, const double2 &w3) {
+__device__ __forceinline__ void fft4096(double (&r)[8], double (&im)[8], double2 *z, const double2 *tw12, const double2 *tw3) {
   const int j = threadIdx.x;
   fft8(r, im);
 #pragma unroll
@@ -137,7 +138,7 @@ __device__ __forceinline__ void fft4096(double (&r)[8], double (&im)[8], double2
       im[q] = c.y;
     }
     {
-      const double2 w1 = (pass == 1) ? tw12[k] : (pass == 2) ? tw12[8 + k] : w3;
+      const double2 w1 = (pass == 1) ? tw12[k] : (pass == 2) ? tw12[8 + k] : __ldg(tw3 + j);
       const double2 w2 = make_double2(w1.x * w1.x - w1.y * w1.y, 2.0 * w1.x * w1.y);
       const double2 w4 = make_double2(w2.x * w2.x - w2.y * w2.y, 2.0 * w2.x * w2.y);
       const double2 w3 = cprod(w1, w2), w5 = cprod(w4, w1), w6 = cprod(w4, w2);
@@ -198,7 +199,6 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
   for (int k = t; k <= NCONV / 2; k += CONV_NT) sm.acc[k] = make_double2(0.0, 0.0);
   // tw[m] = exp(-2 pi i m / 4096): the last pass's twiddle of this thread stays in registers, the 8 + 64 distinct
   // ones of the two passes before it sit in shared memory (conflict-free: consecutive threads, consecutive entries)
-  const double2 w3 = __ldg(tw + t);
   if (t < 8) sm.tw12[t] = __ldg(tw + t * 64);
   else if (t < 72) sm.tw12[t] = __ldg(tw + (t - 8) * 8);
   double bal_prev = 0.0;   // ratio of the two input scales in the last zone that had one (0: none yet)
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
     //      both by E_mid/dE before the transform and divides the result by it afterwards (src/Relbase.cpp:93-103,
     //      186-190); on the logarithmic convolution grid that factor is one constant (to 1e-13, checked at load,
     //      tables.cu) and cancels against the normalisation, so it is left out
-    double sums[4] = {0.0, 0.0, 0.0, 0.0};   // all rel, |x|, band x, band rel
+    double sums[3] = {0.0, 0.0, 0.0};         // all rel, band x, band rel
     double re[8], im[8];                      // bins t + 512 u: the first FFT pass takes them from here
     if (A.mode == 0 && z + 1 < nz) {
       // the next zone's two rows are pulled into L2 while this zone is transformed: the packing loads are the
@@ -264,9 +264,8 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
         re[u] = f;
         im[u] = r;
         sums[0] += r;
-        sums[1] += fabs(f);
-        if (band & (1u << u)) sums[2] += f;
-        if (band & (0x100u << u)) sums[3] += r;
+        if (band & (1u << u)) sums[1] += f;
+        if (band & (0x100u << u)) sums[2] += r;
       }
     } else {
 #pragma unroll 1
@@ -276,9 +275,8 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
         const double r = ((unsigned) (ri - rjlo) <= (unsigned) rjw) ? relr[ri - r0] : 0.0;
         sm.z[cv_pad(i)] = make_double2(f, r);
         sums[0] += r;
-        sums[1] += fabs(f);
-        if (i >= b0 && i <= b1) sums[2] += f;
-        if (ri >= b0 && ri <= b1) sums[3] += r;
+        if (i >= b0 && i <= b1) sums[1] += f;
+        if (ri >= b0 && ri <= b1) sums[2] += r;
       }
 #pragma unroll
       for (int u = 0; u < 8; u++) {   // the thread's own values
@@ -294,61 +292,65 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
     const bool exact = (bal_prev == 0.0) || vp.renorm;   // uniform over the block
     double rscale = 1.0, s_xill = 0.0, s_rel = 0.0, yscale;
     if (exact) {
-      block_sum_n<4>(sums, sm);
+      block_sum_n<3>(sums, sm);
       const double srel_all = sums[0];
       if (vp.renorm) rscale = vp.relline_norm / srel_all;                  // renorm_relline_profile (one-zone models)
       const double srel_n = vp.renorm ? srel_all * rscale : srel_all;
       if (srel_n < 1e-12) { __syncthreads(); continue; }                   // src/Relxill.cpp:455-457
-      const double bal = (sums[1] > 0.0 && srel_n > 0.0) ? sums[1] / srel_n : 1.0;
-      s_xill = sums[2];
-      s_rel = vp.renorm ? sums[3] * rscale : sums[3];
+      // the scale of the spectrum: its band sum (spectra are non-negative; the band covers the whole table grid)
+      const double bal = (fabs(sums[1]) > 0.0 && srel_n > 0.0) ? fabs(sums[1]) / srel_n : 1.0;
+      s_xill = sums[1];
+      s_rel = vp.renorm ? sums[2] * rscale : sums[2];
       yscale = rscale * bal;
       if (!vp.renorm) bal_prev = bal;
     } else {
 #pragma unroll
-      for (int q = 0; q < 4; q++)
+      for (int q = 0; q < 3; q++)
         for (int o = 16; o > 0; o >>= 1) sums[q] += __shfl_xor_sync(0xffffffffu, sums[q], o);
       if ((t & 31) == 0) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) sm.part[q * (CONV_NT / 32) + (t >> 5)] = sums[q];
+        for (int q = 0; q < 3; q++) sm.part[q * (CONV_NT / 32) + (t >> 5)] = sums[q];
       }
       yscale = bal_prev;
     }
 #pragma unroll
     for (int u = 0; u < 8; u++) im[u] *= yscale;
-    fft4096<true>(re, im, sm.z, sm.tw12, w3);
+    fft4096<true>(re, im, sm.z, sm.tw12, tw);
     // ---- split, product spectrum, band sum of the convolved zone in the frequency domain.  Point k = t + 512 nk
     // (nk < 4) is still in the thread's registers; its partner 4096 - k is point q = 7 - nk of thread 512 - t, in the
     // stored upper half (k = 0 is its own partner; thread 0 also takes k = 2048, its own point q = 4)
     double dot[1] = {0.0};
-    double pr_[5], pi_[5];
-    int nk = 0;
+    double pr_[4], pi_[4];
 #pragma unroll
-    for (int k = t; k <= NCONV / 2; k += CONV_NT, nk++) {
-      if (nk == 4 && t != 0) break;
+    for (int nk = 0; nk < 4; nk++) {
+      const int k = t + nk * CONV_NT;
       const int kk = (NCONV - k) & (NCONV - 1);
-      const double2 p = (nk < 4) ? make_double2(re[nk], im[nk]) : sm.z[cv_pad(k)];
-      const double2 q = (k == 0) ? p : sm.z[cv_pad(kk)];
-      const double a = p.x, b = p.y, c = q.x, d = q.y;
+      const double2 q = (k == 0) ? make_double2(re[0], im[0]) : sm.z[cv_pad(kk)];
+      const double a = re[nk], b = im[nk], c = q.x, d = q.y;
       const double Xr = 0.5 * (a + c), Xi = 0.5 * (b - d);
       const double Yr = 0.5 * (b + d), Yi = 0.5 * (c - a);
       const double Pr = Xr * Yr - Xi * Yi, Pi = Xr * Yi + Xi * Yr;
       pr_[nk] = Pr;
       pi_[nk] = Pi;
-      const double wgt = (k == 0 || k == NCONV / 2) ? 1.0 : 2.0;
+      const double wgt = (k == 0) ? 1.0 : 2.0;
       const double2 w = __ldg(cw + k);
       dot[0] += wgt * (Pr * w.x + Pi * w.y);
+    }
+    if (t == 0) {   // the Nyquist bin (thread 0's own point q = 4; both spectra are real there) waits in shared memory
+      const double pn = re[4] * im[4];
+      sm.nyq = pn;
+      dot[0] += pn * __ldg(cw + NCONV / 2).x;
     }
     if (exact) {
       block_sum_n<1>(dot, sm);
     } else {
       // the band sum and, from the per-warp parts of the packing phase (visible: the transform's barriers lie in
-      // between), the four packing sums: five rows of 16 partials, one thread each
+      // between), the three packing sums: four rows of 16 partials, one thread each
       for (int o = 16; o > 0; o >>= 1) dot[0] += __shfl_xor_sync(0xffffffffu, dot[0], o);
       __syncthreads();
       if ((t & 31) == 0) sm.red[t >> 5] = dot[0];
       __syncthreads();
-      if (t < 5) {
+      if (t < 4) {
         const double *row = (t == 0) ? sm.red : sm.part + (t - 1) * (CONV_NT / 32);
         double a = 0.0;
         for (int i = 0; i < CONV_NT / 32; i++) a += row[i];
@@ -356,20 +358,22 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
       }
       __syncthreads();
       dot[0] = sm.bc[0];
-      const double srel_all = sm.bc[1], sabs = sm.bc[2];
+      const double srel_all = sm.bc[1];
       if (srel_all < 1e-12) { __syncthreads(); continue; }                 // src/Relxill.cpp:455-457
-      s_xill = sm.bc[3];
-      s_rel = sm.bc[4];
-      if (sabs > 0.0) bal_prev = sabs / srel_all;
+      s_xill = sm.bc[2];
+      s_rel = sm.bc[3];
+      if (fabs(s_xill) > 0.0) bal_prev = fabs(s_xill) / srel_all;
     }
     const double norm = s_rel * s_xill / dot[0];
-    nk = 0;
-    for (int k = t; k <= NCONV / 2; k += CONV_NT, nk++) {
+#pragma unroll
+    for (int nk = 0; nk < 4; nk++) {
+      const int k = t + nk * CONV_NT;
       double2 a = sm.acc[k];
       a.x += norm * pr_[nk];
       a.y += norm * pi_[nk];
       sm.acc[k] = a;
     }
+    if (t == 0) sm.acc[NCONV / 2].x += norm * sm.nyq;
     __syncthreads();
   }
   // ---- one inverse transform for the whole vector: out = Re(FFT(conj(A)))
@@ -384,7 +388,7 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
       re[u] = a.x;
       im[u] = (i <= NCONV / 2) ? -ai : ai;
     }
-    fft4096<false>(re, im, sm.z, sm.tw12, w3);
+    fft4096<false>(re, im, sm.z, sm.tw12, tw);
   }
   __syncthreads();       // every thread has taken its part of the accumulated spectrum
   double *acc = reinterpret_cast<double *>(sm.acc);   // 4098 doubles
