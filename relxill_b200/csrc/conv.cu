@@ -120,12 +120,17 @@ __device__ __forceinline__ void fft8(double (&r)[8], double (&i)[8]) {
 // UPPER: only the upper half of the result (points 2048..4095, the thread's q = 4..7) is written to z; the lower
 // half (points j + 512 q, q < 4) stays in r/im — all the split of two real transforms needs, since the partner of
 // point k is point 4096 - k.
-template <bool UPPER>
-__device__ __forceinline__ void fft4096(double (&r)[8], double (&im)[8], double2 *z, const double2 *tw12, const double2 *tw3) {
+// First pass of the transform: an 8-point DFT of the thread's own points, written to z (no twiddles, no barrier)
+__device__ __forceinline__ void fft4096_first(double (&r)[8], double (&im)[8], double2 *z) {
   const int j = threadIdx.x;
   fft8(r, im);
 #pragma unroll
   for (int q = 0; q < 8; q++) z[cv_pad((j << 3) + q)] = make_double2(r[q], im[q]);
+}
+// The three twiddled passes; starts with the barrier that publishes the first pass
+template <bool UPPER>
+__device__ __forceinline__ void fft4096_rest(double (&r)[8], double (&im)[8], double2 *z, const double2 *tw12, const double2 *tw3) {
+  const int j = threadIdx.x;
   __syncthreads();
 #pragma unroll
   for (int pass = 1; pass < 4; pass++) {
@@ -158,6 +163,11 @@ __device__ __forceinline__ void fft4096(double (&r)[8], double (&im)[8], double2
     for (int q = (UPPER && pass == 3) ? 4 : 0; q < 8; q++) z[cv_pad(j0 + q * ns)] = make_double2(r[q], im[q]);
     __syncthreads();
   }
+}
+template <bool UPPER>
+__device__ __forceinline__ void fft4096(double (&r)[8], double (&im)[8], double2 *z, const double2 *tw12, const double2 *tw3) {
+  fft4096_first(r, im, z);
+  fft4096_rest<UPPER>(r, im, z, tw12, tw3);
 }
 
 struct ConvArgs {
@@ -303,7 +313,16 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
       s_rel = vp.renorm ? sums[2] * rscale : sums[2];
       yscale = rscale * bal;
       if (!vp.renorm) bal_prev = bal;
+#pragma unroll
+      for (int u = 0; u < 8; u++) im[u] *= yscale;
+      fft4096_first(re, im, sm.z);
     } else {
+      // the first pass goes ahead of the warp reductions of the packing sums: the 16 packed values leave the registers
+      // before the shuffles need them (they were being spilled across the reduction)
+      yscale = bal_prev;
+#pragma unroll
+      for (int u = 0; u < 8; u++) im[u] *= yscale;
+      fft4096_first(re, im, sm.z);
 #pragma unroll
       for (int q = 0; q < 3; q++)
         for (int o = 16; o > 0; o >>= 1) sums[q] += __shfl_xor_sync(0xffffffffu, sums[q], o);
@@ -311,11 +330,8 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
 #pragma unroll
         for (int q = 0; q < 3; q++) sm.part[q * (CONV_NT / 32) + (t >> 5)] = sums[q];
       }
-      yscale = bal_prev;
     }
-#pragma unroll
-    for (int u = 0; u < 8; u++) im[u] *= yscale;
-    fft4096<true>(re, im, sm.z, sm.tw12, tw);
+    fft4096_rest<true>(re, im, sm.z, sm.tw12, tw);
     // ---- split, product spectrum, band sum of the convolved zone in the frequency domain.  Point k = t + 512 nk
     // (nk < 4) is still in the thread's registers; its partner 4096 - k is point q = 7 - nk of thread 512 - t, in the
     // stored upper half (k = 0 is its own partner; thread 0 also takes k = 2048, its own point q = 4)
