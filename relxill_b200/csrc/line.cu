@@ -52,6 +52,14 @@ struct RelbCtx {
 
 #define GS_C ((1.0 - 2 * GFAC_H) / (NG - 1))
 #define GS_INVC ((NG - 1) / (1.0 - 2 * GFAC_H))
+// An FP64 immediate whose low word is not zero costs two moves at every use (a tenth of this kernel's instructions
+// were such moves); as __constant__ data the same values ride in the instruction as constant-bank operands.
+struct LnConst {
+  double h, one_m_h, gs_c, gs_invc, prec, e95, sqrt_h;
+  double inv[7];   // 1 / (4^ii - 1) of the Richardson step
+};
+__constant__ LnConst LK = {GFAC_H, 1.0 - GFAC_H, GS_C, GS_INVC, 0.02, 1.0 * 0.95, 0.0,
+                           {0.0, 1.0 / 3.0, 1.0 / 15.0, 1.0 / 63.0, 1.0 / 255.0, 1.0 / 1023.0, 1.0 / 4095.0}};
 
 // limb darkening / brightening factor of relb_func (src/Relprofile.cpp:508-518); out of line: the default
 // law is isotropic and the logarithm would otherwise be replicated into every copy of the integrand
@@ -67,9 +75,9 @@ __device__ __noinline__ double2 relb2_limb(int ind, double inte, const double2 *
 // both branches of relb_func (src/Relprofile.cpp:489-521) at energy eg
 __device__ __forceinline__ void relb2(double eg, const RelbCtx &c, double &v0, double &v1) {
   const double egstar = (eg - c.gmin) * c.del_g;
-  int ind = (int) ((egstar - GFAC_H) * GS_INVC);
+  int ind = (int) ((egstar - LK.h) * LK.gs_invc);
   ind = ind < 0 ? 0 : (ind > NG - 2 ? NG - 2 : ind);
-  const double inte = (egstar - (GFAC_H + GS_C * (double) ind)) * GS_INVC;
+  const double inte = (egstar - (LK.h + LK.gs_c * (double) ind)) * LK.gs_invc;
   const double inte1 = 1.0 - inte;
   const double2 t0 = __ldg(c.trff + ind), t1 = __ldg(c.trff + ind + 1);
   const double common = (eg * eg * eg) * rsqrt(egstar - egstar * egstar) * c.scale;
@@ -85,7 +93,7 @@ __device__ __forceinline__ void relb2(double eg, const RelbCtx &c, double &v0, d
 // (obtprec > prec) of the reference, obtprec = fabs(t_new - t_old) / t_new  (src/Relprofile.cpp:575)
 __device__ __forceinline__ bool not_converged(double t_new, double t_old) {
   const double d = fabs(t_new - t_old);
-  if (t_new > 0.0) return d > 0.02 * t_new;
+  if (t_new > 0.0) return d > LK.prec * t_new;
   if (t_new == 0.0) return d > 0.0;   // x/0 = inf > prec;  0/0 = NaN compares false
   return false;                        // negative (or NaN) quotient ends the loop
 }
@@ -96,8 +104,7 @@ __device__ __forceinline__ double gstar2ener(double g, double gmin, double gmax)
 // divisions replaced by the tabulated reciprocals
 __device__ __forceinline__ double richardson(int ii, double cur_lo, double prev_lo) {
   const double r4[7] = {1.0, 4.0, 16.0, 64.0, 256.0, 1024.0, 4096.0};
-  const double inv[7] = {0.0, 1.0 / 3.0, 1.0 / 15.0, 1.0 / 63.0, 1.0 / 255.0, 1.0 / 1023.0, 1.0 / 4095.0};
-  return (r4[ii] * cur_lo - prev_lo) * inv[ii];
+  return (r4[ii] * cur_lo - prev_lo) * LK.inv[ii];
 }
 
 // grid_mode 0: the fixed convolution grid; 1: the caller's grid shifted by (1+z) and divided by lineE
@@ -182,22 +189,22 @@ __device__ __forceinline__ int bin_split(const LnRad &lr, double rlo0, double rh
   if (gbhi < 0.0) gbhi = 0.0; else if (gbhi > 1.0) gbhi = 1.0;
   if (gbhi == 0) return 0;
   rlo = rlo0; rhi = rhi0;
-  const bool at_lo = gblo <= GFAC_H, at_hi = gbhi >= (1.0 - GFAC_H);
-  double lo_hhi = GFAC_H, hi_hlo = 1.0 - GFAC_H;
+  const bool at_lo = gblo <= LK.h, at_hi = gbhi >= LK.one_m_h;
+  double lo_hhi = LK.h, hi_hlo = LK.one_m_h;
   if (at_lo) {
-    rlo = gstar2ener(GFAC_H, lr.gmin, lr.gmax);
-    if (gbhi <= GFAC_H) { lo_hhi = gbhi; rlo = -1.0; }
+    rlo = gstar2ener(LK.h, lr.gmin, lr.gmax);
+    if (gbhi <= LK.h) { lo_hhi = gbhi; rlo = -1.0; }
   }
   if (at_hi) {
-    rhi = gstar2ener(1 - GFAC_H, lr.gmin, lr.gmax);
-    if (gblo >= (1.0 - GFAC_H)) { hi_hlo = gblo; rhi = -1.0; }
+    rhi = gstar2ener(LK.one_m_h, lr.gmin, lr.gmax);
+    if (gblo >= LK.one_m_h) { hi_hlo = gblo; rhi = -1.0; }
   }
   if (EDGES && (at_lo || at_hi)) {   // lower-edge term first, like the reference; one call unless the bin spans both edges
     const double eb_lo = at_lo ? gblo : hi_hlo, eb_hi = at_lo ? lo_hhi : gbhi, e_norm = at_lo ? lr.nlo : lr.nhi;
     flu = flu + edge_term(eb_lo, eb_hi, e_norm, lr.gmin, lr.gmax);
     if (at_lo && at_hi) flu = flu + edge_term(hi_hlo, gbhi, lr.nhi, lr.gmin, lr.gmax);
   }
-  if ((rhi >= 0) && (rlo >= 0)) return (rlo >= 1.0 * 0.95) ? 2 : 1;
+  if ((rhi >= 0) && (rlo >= 0)) return (rlo >= LK.e95) ? 2 : 1;
   return 0;
 }
 
@@ -319,6 +326,13 @@ __global__ void __launch_bounds__(LN_NT, 8) k_line(const VPar *__restrict__ vps,
       }
     }
     __syncthreads();
+    if (t >= 32) {
+      // while warp 0 scans, the other warps request the transfer-function rows of the sub-batch's radii (640 bytes =
+      // five lines each): the integrand's table look-ups (data-dependent, one L2 round trip each) then hit in L1
+      const int nr = min(ib - cur, LN_MAXR);
+      for (int q = t - 32; q < nr * 5; q += LN_NT - 32)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(g_trff + (size_t) cur * NG) + (size_t) q * 128));
+    }
     if (t < 32) {   // offsets of the radii that fit the buffer: warp scan over the bin counts
       const int r = t;
       const bool valid = cur + r < ib;
