@@ -133,6 +133,7 @@ int ensure_scratch(Engine &E, long cap, int nz_cap, int ne_cap, int nex_stride, 
   ok &= salloc(E, S.zfirst, c * (NZMAX + 1)) && salloc(E, S.brk_i, c * 2) && salloc(E, S.brk_f, c * 2);
   ok &= salloc(E, S.it, c * NR) && salloc(E, S.izone, c * NR) && salloc(E, S.glim, c * 2) && salloc(E, S.reflfrac, c * 8);
   ok &= salloc(E, S.trff, c * NR * NG * 2) && salloc(E, S.cosne, c * NR * NG * 2);
+  ok &= salloc(E, S.relrow, c * REL_NRT * NG * 4);
   ok &= salloc(E, S.eshift, c * NZMAX) && salloc(E, S.zlxi, c * NZMAX) && salloc(E, S.zdens, c * NZMAX);
   ok &= salloc(E, S.zect, c * NZMAX) && salloc(E, S.normch, c * NZMAX) && salloc(E, S.corr_flux, c * NZMAX);
   ok &= salloc(E, S.corr_gshift, c * NZMAX) && salloc(E, S.nsrc, c);
@@ -358,6 +359,7 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
     tm.begin();
     launch_fine(vps, T, S, nc, relxill ? n_incl : 0, econv[0], econv[NCONV], (b->any_limb || E.keep_intermediates) ? 1 : 0, st);
     tm.end(KF_FINE);
+    b->launches++;   // launch_fine is two kernels (k_rows, k_fine) timed as one family
     if (relxill) {
       tm.begin(); launch_dist(vps, T, S, nc, n_incl, st); tm.end(KF_DIST);
     }

@@ -128,6 +128,7 @@ struct Scratch {
   double *glim;                                               // [cap][2] min gmin / max gmax over radii
   double *reflfrac;                                           // [cap][8]
   double *trff, *cosne;                                       // [cap][NR][NG][2]
+  double *relrow;                                             // [cap][REL_NRT][NG][4] table rows interpolated in (a, mu0): trff1,2, cosne1,2
   double *eshift, *zlxi, *zdens, *zect, *normch, *corr_flux, *corr_gshift;  // [cap][NZMAX]
   double *nsrc;                                               // [cap] source normalisation factor
   int *xrow;                                                  // [cap][NZMAX][32] node index of each corner

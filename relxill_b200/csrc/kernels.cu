@@ -681,6 +681,36 @@ __global__ void __launch_bounds__(128) k_zone(const VPar *__restrict__ vps, DevT
   }
 }
 
+// ---------------------------------------------------------------------------------- k_rows
+// The (a, mu0) half of the transfer-function interpolation (interpol_a_mu0, src/Relprofile.cpp:39-80), once per TABLE
+// radius: the fine grid has about ten radii per table interval, and every one of them needs the same two bilinearly
+// interpolated rows.  One thread per (table radius, g*): 16 table floats -> {trff1, trff2, cosne1, cosne2} in fp64
+// (exactly the values k_fine used to recompute per fine radius; the float -> double conversions of the 32 table
+// values per fine-grid point kept the XU pipe busier than the FP64 pipe).
+__global__ void __launch_bounds__(320) k_rows(const VPar *__restrict__ vps, DevTables T, Scratch S) {
+  const int v = blockIdx.y;
+  if (S.status[v] != ST_OK) return;
+  if (S.reuse && S.reuse[v]) return;
+  const int j = threadIdx.x % NG, it = blockIdx.x * 8 + threadIdx.x / NG;
+  if (it >= REL_NRT) return;
+  const int ia = S.brk_i[2 * v], im = S.brk_i[2 * v + 1];
+  const double fa = S.brk_f[2 * v], fm = S.brk_f[2 * v + 1];
+  const float4 *tc = reinterpret_cast<const float4 *>(T.rel_tc);
+  const size_t o00 = (((size_t) ia * REL_NMU + im) * REL_NRT + it) * NG + j;
+  const size_t o10 = (((size_t) (ia + 1) * REL_NMU + im) * REL_NRT + it) * NG + j;
+  const size_t o01 = (((size_t) ia * REL_NMU + im + 1) * REL_NRT + it) * NG + j;
+  const size_t o11 = (((size_t) (ia + 1) * REL_NMU + im + 1) * REL_NRT + it) * NG + j;
+  const float4 a00 = __ldg(tc + o00), a10 = __ldg(tc + o10), a01 = __ldg(tc + o01), a11 = __ldg(tc + o11);
+  double2 tr, co;
+  tr.x = lin2d_f(fa, fm, a00.x, a10.x, a01.x, a11.x);
+  tr.y = lin2d_f(fa, fm, a00.y, a10.y, a01.y, a11.y);
+  co.x = lin2d_f(fa, fm, a00.z, a10.z, a01.z, a11.z);
+  co.y = lin2d_f(fa, fm, a00.w, a10.w, a01.w, a11.w);
+  double2 *row = reinterpret_cast<double2 *>(S.relrow) + (((size_t) v * REL_NRT + it) * NG + j) * 2;
+  row[0] = tr;
+  row[1] = co;
+}
+
 // ---------------------------------------------------------------------------------- k_fine
 // The g*-dependent half of interpol_relTable (src/Relprofile.cpp:39-80,280-293): bilinear (a, mu0) blend of
 // the four table corners at the two bracketing table radii, then the radial lerp, for trff1/2 and cosne1/2.
@@ -709,22 +739,14 @@ __global__ void __launch_bounds__(320) k_fine(const VPar *__restrict__ vps, DevT
     s_rad[threadIdx.x][2] = ((gmax > e_first) && (gmin < e_last))
                                 ? r * (x1 * x1) * S.emis[(size_t) v * NR + i2] * (trapez_single(re, i2, NR) / 2) : -1.0;
   }
-  const int ia = S.brk_i[2 * v], im = S.brk_i[2 * v + 1];
-  const double fa = S.brk_f[2 * v], fm = S.brk_f[2 * v + 1];
   const int it = S.it[(size_t) v * NR + i];
   const double fr = S.fr[(size_t) v * NR + i];
-  const float4 *tc = reinterpret_cast<const float4 *>(T.rel_tc);
-  const size_t o00 = (((size_t) ia * REL_NMU + im) * REL_NRT + it) * NG + j;
-  const size_t o10 = (((size_t) (ia + 1) * REL_NMU + im) * REL_NRT + it) * NG + j;
-  const size_t o01 = (((size_t) ia * REL_NMU + im + 1) * REL_NRT + it) * NG + j;
-  const size_t o11 = (((size_t) (ia + 1) * REL_NMU + im + 1) * REL_NRT + it) * NG + j;
-  const float4 a00 = __ldg(tc + o00), a10 = __ldg(tc + o10), a01 = __ldg(tc + o01), a11 = __ldg(tc + o11);
-  const float4 b00 = __ldg(tc + o00 + NG), b10 = __ldg(tc + o10 + NG), b01 = __ldg(tc + o01 + NG), b11 = __ldg(tc + o11 + NG);
-  // row `it` (larger radius) and row `it+1` (smaller radius)
-  const double t1_hi = lin2d_f(fa, fm, a00.x, a10.x, a01.x, a11.x), t1_lo = lin2d_f(fa, fm, b00.x, b10.x, b01.x, b11.x);
-  const double t2_hi = lin2d_f(fa, fm, a00.y, a10.y, a01.y, a11.y), t2_lo = lin2d_f(fa, fm, b00.y, b10.y, b01.y, b11.y);
-  const double c1_hi = lin2d_f(fa, fm, a00.z, a10.z, a01.z, a11.z), c1_lo = lin2d_f(fa, fm, b00.z, b10.z, b01.z, b11.z);
-  const double c2_hi = lin2d_f(fa, fm, a00.w, a10.w, a01.w, a11.w), c2_lo = lin2d_f(fa, fm, b00.w, b10.w, b01.w, b11.w);
+  // the two table rows around this radius, already interpolated in (a, mu0) by k_rows: row `it` (larger radius) and
+  // row `it+1` (smaller radius)
+  const double2 *row = reinterpret_cast<const double2 *>(S.relrow) + (((size_t) v * REL_NRT + it) * NG + j) * 2;
+  const double2 thi = row[0], chi = row[1], tlo = row[2 * NG], clo = row[2 * NG + 1];
+  const double t1_hi = thi.x, t2_hi = thi.y, c1_hi = chi.x, c2_hi = chi.y;
+  const double t1_lo = tlo.x, t2_lo = tlo.y, c1_lo = clo.x, c2_lo = clo.y;
   double2 tr, co;
   tr.x = lin1d(fr, t1_lo, t1_hi);
   tr.y = lin1d(fr, t2_lo, t2_hi);
@@ -960,6 +982,8 @@ void launch_zone(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
 }
 void launch_fine(const VPar *vps, const DevTables &T, const Scratch &S, long n, int n_incl, double e_first,
                  double e_last, int store_cosne, cudaStream_t st) {
+  dim3 grid_rows((REL_NRT + 7) / 8, (unsigned) n);
+  k_rows<<<grid_rows, 320, 0, st>>>(vps, T, S);
   dim3 grid(NR / 8, (unsigned) n);
   k_fine<<<grid, 320, 0, st>>>(vps, T, S, n_incl, e_first, e_last, store_cosne);
 }
