@@ -251,10 +251,11 @@ __device__ __noinline__ double romberg_deep(double a, double pas, RelbCtx c, Dee
   return res[0] + res[1];
 }
 
-// 8 resident CTAs per SM (64 registers, 32 warps): the kernel is latency-bound on its dependent FP64 chains, and the
-// extra warps are worth more than the few spilled values (measured 11.8 ms at 6 CTAs / 80 registers, 10.0 ms at 8)
+// 9 resident CTAs per SM (56 registers, 36 warps): the kernel is latency-bound on its dependent FP64 chains, and the
+// extra warps are worth more than the few spilled values (measured 11.8 ms at 6 CTAs / 80 registers, 10.0 ms at 8 / 64,
+// 9.4 ms at 9 / 56; at 10 / 48 the spills win: 10.4 ms)
 template <int GRID_MODE>
-__global__ void __launch_bounds__(LN_NT, 8) k_line(const VPar *__restrict__ vps, DevTables T, Scratch S, LineGrid G,
+__global__ void __launch_bounds__(LN_NT, 9) k_line(const VPar *__restrict__ vps, DevTables T, Scratch S, LineGrid G,
                                                    int ne_stride, int nz_stride) {
   __shared__ __align__(16) LnSmem sm;
   const unsigned FULL = 0xffffffffu;
