@@ -406,12 +406,18 @@ def run_ours(args):
                 "frac": achieved / peak, "traffic": traffic, "compute": compute, "peak_source": peak_src,
                 "share_of_step": ktimes[dominant][0] / tot_k,
                 "algorithmic_bytes_per_launch": alg.get(dominant, 0.0)}
+    if roofline["frac"] > 1.0:
+        roofline["note"] = ("algorithmic bytes count every vector's distinct table rows (SURVEY 8d); MCMC walkers share them, the rows "
+                            "are served from L2/L1 and the figure exceeds the HBM peak: the kernel is not HBM-bound in this workload")
     xk = ktimes.get("k_xill", (0.0, 1))
     hbm_stage = {"kernel": "k_xill", "achieved": alg["k_xill"] / (xk[0] / max(xk[1], 1) * 1e-3) / 1e9 if xk[0] else None,
                  "unit": "GB/s", "peak": peak, "distinct_corner_rows_per_vector": ab["distinct_rows"] / n,
                  "xillver_bytes_distinct": ab["xillver"], "xillver_bytes_upper_bound": ab["xillver_upper_bound"]}
     if hbm_stage["achieved"]:
         hbm_stage["frac"] = hbm_stage["achieved"] / peak
+        hbm_stage["note"] = ("distinct rows are counted per vector; walkers share rows through L2/L1, so this is delivered table "
+                             "bandwidth, not DRAM traffic (see roofline.traffic / profiles/ncu_traffic.json; scripts/cfg4_probe.py is the "
+                             "HBM-bound case)")
         hbm_stage["frac_of_upper_bound_traffic"] = (ab["xillver_upper_bound"] + n * nz * nex * 8.0) / (xk[0] * 1e-3) / 1e9 / peak
 
     # ---- supplemental: the device-resident state cache on an MCMC-like sequence in which half of the walkers stay where
