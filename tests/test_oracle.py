@@ -21,6 +21,25 @@ def test_rebin_spectrum_kat(oracle):
     np.testing.assert_allclose(val, [0.5, 1.5, 2.0, 2.25, 0.25], atol=1e-12)
 
 
+def test_rebin_commutes_with_the_table_blend(oracle):
+    """What the convolution-grid copy of the xillver tables rests on (relxill_b200/csrc/tables.cu, xill.cu): _rebin_spectrum
+    (src/relutility.c:549-601) is a fixed linear map, so rebinning a weighted sum of table rows (what the reference
+    does per zone, src/Relxill.cpp:461-463) equals the weighted sum of the rebinned rows, to rounding."""
+    rng = np.random.default_rng(3)
+    src = np.exp(np.linspace(np.log(0.07), np.log(1000.1), 3000))     # a grid like the xillver tables' (2999 bins)
+    dst = oracle.conv_grid()
+    rows = rng.uniform(0.0, 1.0, (16, src.size - 1)).astype(np.float32).astype(np.float64) * src[:-1] ** -1.5
+    w = rng.uniform(0.0, 1.0, 16)
+    w /= w.sum()
+    blend_then_rebin = oracle.rebin(dst, src, w @ rows)
+    rebin_then_blend = w @ np.array([oracle.rebin(dst, src, r) for r in rows])
+    m = blend_then_rebin > 0
+    assert m.sum() > 2400 and not rebin_then_blend[~m].any()          # only the bins overlapping the table grid are non-zero
+    np.testing.assert_allclose(rebin_then_blend[m], blend_then_rebin[m], rtol=1e-13)
+    # and the rebin conserves the flux of the overlapping part
+    assert abs(blend_then_rebin.sum() / (w @ rows).sum() - 1) < 1e-12
+
+
 def test_default_grid_endpoints():
     # reference test/unit/tests-execmodel.cpp:44-61
     e = default_grid(100, 0.5, 10.0)
