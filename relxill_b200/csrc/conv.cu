@@ -17,6 +17,11 @@
 // The transform is a 4096-point radix-8 Stockham autosort FFT in shared memory: 4 passes, one butterfly per
 // thread per pass.  The work array is complex-interleaved (one 128-bit shared access per point) and padded by
 // one point every 8, which makes every pass's gather and scatter bank-conflict free per quarter-warp.
+// What bounds the kernel is the L1/shared-memory data pipe (ncu: wavefronts at ~70 % of peak, FP64 pipe 45 %), so the
+// zone loop is written to move as little as possible through it: the packing phase is a plain coalesced load
+// (k_xill files the zone spectra on the convolution grid), the last pass stores only the half of the result that
+// other threads need, the accumulators are 128-bit, and register spills (local memory rides the same pipe) are
+// kept out of the loop as far as 64 registers allow.
 #include <cuda_runtime.h>
 
 #include "common.h"
@@ -114,9 +119,11 @@ __device__ __forceinline__ void fft8(double (&r)[8], double (&i)[8]) {
 // j + 512 q, q = 0..7 (exactly what the first pass needs), so the packing code hands its values over without a
 // round trip through shared memory.  Result in the padded array z.
 // The twiddles of pass p are w^q with w = exp(-2 pi i k / (8 ns)), k = j mod ns: they depend on the thread only.
-// The last pass's w stays in registers for the whole kernel, the 8 + 64 distinct ones of passes 1 and 2 come from
-// a small shared table (tw12); w^2 and w^4 come from squarings and the rest from products — no global table
-// reads inside the transform.
+// The 8 + 64 distinct ones of passes 1 and 2 come from a small shared table (tw12), the last pass's w is re-read per
+// transform (one L1-resident 16-byte load: kept in registers it was spilled, the kernel runs at 64 registers per
+// thread); w^2 and w^4 come from squarings and the rest from products.
+// The transform comes in two pieces, the first pass and the three twiddled ones, so that the caller can put work that
+// needs registers (the warp reductions of the packing sums) between them, when the 16 packed values have left.
 // UPPER: only the upper half of the result (points 2048..4095, the thread's q = 4..7) is written to z; the lower
 // half (points j + 512 q, q < 4) stays in r/im — all the split of two real transforms needs, since the partner of
 // point k is point 4096 - k.
