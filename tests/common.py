@@ -103,3 +103,18 @@ def walker_ball(model, n, seed=4321):
         raise KeyError(model)
     p = c[None, :] + s[None, :] * rng.standard_normal((n, c.size))
     return np.clip(p, lo, hi)
+
+
+def config_cases():
+    """(key, model, zones, full parameter matrix, picked rows) of the BASELINE.json configurations 2-4 (config 5 is the
+    returning-radiation grid built in the tests).  tests/golden/make_golden.py evaluates the picked rows with the
+    unmodified reference (golden_v3_configs.npz); the GPU tests evaluate the FULL batches and compare those rows."""
+    cases = []
+    cases.append(("cfg2_relxill", "relxill", None, sample_params("relxill", 1024, seed=1234), [0, 17, 333, 640, 1023]))
+    cases.append(("cfg3_relxilllp", "relxilllp", 50, walker_ball("relxilllp", 4096), [0, 1, 1000, 2047, 4095]))
+    cases.append(("cfg3_relxilllpCp", "relxilllpCp", 50, walker_ball("relxilllpCp", 4096), [0, 1, 1000, 2047, 4095]))
+    cases.append(("cfg4_relxillCp", "relxillCp", None, sample_params("relxillCp", 5000, seed=99), [1, 1666, 2507, 4998]))
+    P = sample_params("relxilllpCp", 2500, seed=99)
+    P[:, 14] = 0
+    cases.append(("cfg4_relxilllpCp", "relxilllpCp", None, P, [1, 833, 1257, 2498]))
+    return cases

@@ -1,4 +1,4 @@
-"""Generates tests/golden/golden_v1.npz (and golden_v2_nsco.npz with `nsco` as argument) from the UNMODIFIED reference (oracle/_ref) on the synthetic
+"""Generates tests/golden/golden_v1.npz (golden_v2_nsco.npz with `nsco`, golden_v3_configs.npz with `configs` as argument) from the UNMODIFIED reference (oracle/_ref) on the synthetic
 'test' tables.  Run in the build container (needs /root/reference to have been compiled by
 `make -C oracle ref`):   python tests/golden/make_golden.py
 The fixture pins the oracle restatement and the CUDA path on machines without the reference."""
@@ -11,7 +11,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from common import MODELS, NSCO_MODELS, default_grid, sample_params  # noqa: E402
+from common import MODELS, NSCO_MODELS, config_cases, default_grid, sample_params  # noqa: E402
 from oracle.pyref import Ref  # noqa: E402  (process-isolated)
 from relxill_b200.tables import synth  # noqa: E402
 
@@ -71,8 +71,40 @@ def main_nsco():
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_v2_nsco.npz"), **out)
 
 
+def main_configs():
+    """golden_v3_configs.npz: the BASELINE.json configurations 2-5 (picked rows of the full batches the GPU tests run),
+    evaluated by the unmodified reference."""
+    tdir = synth.generate(synth.default_table_dir("test"), "test")
+    os.environ.pop("RELXILL_NUM_RZONES", None)
+    ref = Ref(tdir)
+    e = default_grid(600)
+    out = {"energy": e, "table_digest": np.array(table_digest(tdir))}
+    cases = config_cases()
+    # config 5: returning-radiation sweep over spin x height x inclination (the grid of tests/test_gpu_parity.py)
+    base = ref.default_params("relxilllp")
+    rows = []
+    for a in np.linspace(0.0, 0.998, 8):
+        for h in np.geomspace(2.0, 100.0, 8):
+            for inc in np.linspace(5.0, 80.0, 4):
+                p = base.copy()
+                p[0], p[2], p[3], p[12] = h, a, inc, 1
+                rows.append(p)
+    cases.append(("cfg5_relxilllp", "relxilllp", None, np.array(rows), [0, 37, 101, 200, 255]))
+    for key, model, zones, P, pick in cases:
+        ref.set_num_zones(zones)
+        F = ref.eval_batch(model, e, P[pick])
+        out[f"{key}_rows"] = np.array(pick)
+        out[f"{key}_params"] = P[pick]
+        out[f"{key}_flux"] = F
+        print(key, model, zones, F.shape, float(F.sum()))
+    ref.set_num_zones(None)
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_v3_configs.npz"), **out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "nsco":
+    if len(sys.argv) > 1 and sys.argv[1] == "configs":
+        main_configs()
+    elif len(sys.argv) > 1 and sys.argv[1] == "nsco":
         main_nsco()
     else:
         main()

@@ -8,11 +8,12 @@ import os
 import numpy as np
 import pytest
 
-from common import PEAK_FLOOR, RTOL, default_grid, relerr, sample_params, walker_ball
+from common import PEAK_FLOOR, RTOL, config_cases, default_grid, relerr, sample_params, walker_ball
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz")
 GOLDEN_NSCO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2_nsco.npz")
+GOLDEN_CFG = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v3_configs.npz")
 NSCO_MODELS = ["xillverNS", "relxillNS", "xillverCO", "relxillCO"]
 GPU_MODELS = ["relline", "relline_lp", "relconv", "relconv_lp", "relxill", "relxilllp", "relxillCp", "relxilllpCp",
               "xillver", "xillverCp"] + NSCO_MODELS
@@ -385,6 +386,43 @@ def test_state_cache_behind_the_xspec_symbols(rx):
 
 
 # ---------------------------------------------------------------- the other BASELINE.json configurations
+@pytest.mark.parametrize("key,model,zones", [("cfg2_relxill", "relxill", None), ("cfg3_relxilllp", "relxilllp", 50),
+                                              ("cfg3_relxilllpCp", "relxilllpCp", 50), ("cfg4_relxillCp", "relxillCp", None),
+                                              ("cfg4_relxilllpCp", "relxilllpCp", None), ("cfg5_relxilllp", "relxilllp", None)])
+def test_baseline_configs_vs_golden_reference_vectors(rx, key, model, zones):
+    """BASELINE.json configs 2-5 at their full batch sizes (1024 random relxill vectors; 4096 MCMC walkers with 50 zones;
+    the Cp shards streamed through several chunks; the returning-radiation sweep): the rows the fixture holds —
+    evaluated by the UNMODIFIED reference, tests/golden/make_golden.py configs — must come out of the full batch
+    within the north_star tolerance."""
+    g = np.load(GOLDEN_CFG)
+    e, rows, want = g["energy"], g[f"{key}_rows"], g[f"{key}_flux"]
+    if key == "cfg5_relxilllp":
+        P = _config5_grid(rx)
+    else:
+        P = next(c[3] for c in config_cases() if c[0] == key)
+    np.testing.assert_array_equal(P[rows], g[f"{key}_params"])     # the samplers still produce the fixture's vectors
+    rx.set_num_zones(zones)
+    try:
+        f, st = rx.batch_eval(model, e, P, return_status=True)
+    finally:
+        rx.set_num_zones(None)
+    assert (st[rows] == 0).all()
+    for i, w in zip(rows, want):
+        assert relerr(f[i], w) < RTOL, (key, int(i))
+
+
+def _config5_grid(rx):
+    base = rx.default_params("relxilllp")
+    rows = []
+    for a in np.linspace(0.0, 0.998, 8):
+        for h in np.geomspace(2.0, 100.0, 8):
+            for inc in np.linspace(5.0, 80.0, 4):
+                p = base.copy()
+                p[0], p[2], p[3], p[12] = h, a, inc, 1
+                rows.append(p)
+    return np.array(rows)
+
+
 def test_config2_relxill_1024_random(rx, oracle):
     """BASELINE config 2: relxill, 1024 random parameter vectors (seed 1234); a sample against the oracle, the
     whole batch for status / finiteness / batch-order invariance."""
@@ -423,15 +461,7 @@ def test_config4_cp_batch_streams_through_chunks(rx, oracle):
 def test_config5_returning_radiation_sweep(rx, oracle):
     """BASELINE config 5: relxilllp with returning radiation on a spin x height x inclination grid."""
     e = default_grid(1500)
-    base = rx.default_params("relxilllp")
-    rows = []
-    for a in np.linspace(0.0, 0.998, 8):
-        for h in np.geomspace(2.0, 100.0, 8):
-            for inc in np.linspace(5.0, 80.0, 4):
-                p = base.copy()
-                p[0], p[2], p[3], p[12] = h, a, inc, 1
-                rows.append(p)
-    P = np.array(rows)
+    P = _config5_grid(rx)
     f, st = rx.batch_eval("relxilllp", e, P, return_status=True)
     assert (st == 0).all() and np.isfinite(f).all() and (f.sum(axis=1) > 0).all()
     for i in (0, 37, 101, 200, 255):

@@ -9,6 +9,7 @@ from common import ALL_MODELS, MODELS, NSCO_MODELS, default_grid, relerr, sample
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz")
 GOLDEN_NSCO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2_nsco.npz")
+GOLDEN_CFG = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v3_configs.npz")
 
 
 # ---------------------------------------------------------------- table-independent KATs of the reference
@@ -103,6 +104,21 @@ def test_oracle_vs_golden_50_zones(oracle, model):
         oracle.set_num_zones(None)
 
 
+@pytest.mark.parametrize("key,model,zones", [("cfg2_relxill", "relxill", None), ("cfg3_relxilllp", "relxilllp", 50),
+                                              ("cfg3_relxilllpCp", "relxilllpCp", 50), ("cfg4_relxillCp", "relxillCp", None),
+                                              ("cfg4_relxilllpCp", "relxilllpCp", None), ("cfg5_relxilllp", "relxilllp", None)])
+def test_oracle_vs_golden_baseline_configs(oracle, key, model, zones):
+    """Rows of the BASELINE.json configurations 2-5 (random relxill vectors, 50-zone MCMC walkers, the Cp shards, the
+    returning-radiation sweep) evaluated by the unmodified reference: tests/golden/make_golden.py configs."""
+    g = np.load(GOLDEN_CFG)
+    oracle.set_num_zones(zones)
+    try:
+        for p, f in zip(g[f"{key}_params"], g[f"{key}_flux"]):
+            assert relerr(oracle.eval(model, g["energy"], p), f) < 1e-8, (key, p)
+    finally:
+        oracle.set_num_zones(None)
+
+
 def test_golden_tables_match(table_dir):
     import hashlib
     from relxill_b200.tables import synth
@@ -111,6 +127,7 @@ def test_golden_tables_match(table_dir):
         with open(os.path.join(table_dir, synth.FILES[key]), "rb") as f:
             h.update(f.read())
     assert h.hexdigest() == str(np.load(GOLDEN)["table_digest"]), "synthetic tables changed: regenerate the golden file"
+    assert h.hexdigest() == str(np.load(GOLDEN_CFG)["table_digest"]), "synthetic tables changed: regenerate golden_v3_configs.npz"
     h = hashlib.sha256()
     for key in ("rel", "xillns", "xillco"):
         with open(os.path.join(table_dir, synth.FILES[key]), "rb") as f:
