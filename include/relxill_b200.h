@@ -129,6 +129,10 @@ int relxill_b200_kernel_times(relxill_b200_batch *b, const char **names, double 
  * initialisation, selects 0 and skips building the copy (1.7x the table's bytes). */
 void relxill_b200_set_xill_grid(int conv_grid);
 int relxill_b200_get_xill_grid(void);
+/* Test hook: evaluate with the instantiation of the xillver blend kernel that takes the table's row length and
+ * inclination count at run time (what a table with another energy grid gets) even on the standard 2999-bin
+ * tables, whose strides are otherwise compile-time constants. */
+void relxill_b200_set_xill_generic(int on);
 
 /* Keep the intermediates that only the probes read (the fine emission-angle tables are otherwise not stored
  * unless a limb law needs them).  Off by default. */

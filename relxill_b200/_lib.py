@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "relxill_b200_prepare", "relxill_b200_run", "relxill_b200_batch_status", "relxill_b200_free_batch",
     "relxill_b200_algorithmic_bytes", "relxill_b200_last_launches", "relxill_b200_set_profiling", "relxill_b200_keep_intermediates",
     "relxill_b200_kernel_times", "relxill_b200_probe", "relxill_b200_update_params", "relxill_b200_update_energy",
-    "relxill_b200_reuse_counts", "relxill_b200_set_cache", "relxill_b200_set_xill_grid", "relxill_b200_get_xill_grid",
+    "relxill_b200_reuse_counts", "relxill_b200_set_cache", "relxill_b200_set_xill_grid", "relxill_b200_get_xill_grid", "relxill_b200_set_xill_generic",
 ] + sorted(LMOD_SYMBOLS.values())
 
 
@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
     L.relxill_b200_set_cache.argtypes = [C.c_int]
     L.relxill_b200_set_xill_grid.argtypes = [C.c_int]
     L.relxill_b200_get_xill_grid.restype = C.c_int
+    L.relxill_b200_set_xill_generic.argtypes = [C.c_int]
     for sym in LMOD_SYMBOLS.values():
         f = getattr(L, sym)
         f.argtypes = [_dp, C.c_int, _dp, C.c_int, _dp, C.c_void_p, C.c_char_p]

@@ -477,6 +477,7 @@ void relxill_b200_keep_intermediates(int on) { g_eng.keep_intermediates = on != 
 void relxill_b200_set_cache(int on) { g_eng.cache_on = on != 0; }
 void relxill_b200_set_xill_grid(int conv_grid) { g_eng.xill_conv_grid = conv_grid != 0; }
 int relxill_b200_get_xill_grid(void) { return g_eng.xill_conv_grid ? 1 : 0; }
+void relxill_b200_set_xill_generic(int on) { xill_force_generic(on); }
 
 int relxill_b200_num_params(const char *model) {
   const ModelDef *m = find_model(model);

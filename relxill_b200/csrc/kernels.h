@@ -20,6 +20,7 @@ int line_max_bins();  // largest energy grid the line kernel handles in one pass
 void launch_linefinish(const VPar *vps, const Scratch &S, long n, int n_ener, double *out, cudaStream_t st);
 // conv_grid != 0: zone spectra are filed (k_xill) and read (k_conv) on the convolution grid, see xill.cu
 void launch_xill(const VPar *vps, const DevTables &T, const Scratch &S, long n, int which, int conv_grid, cudaStream_t st);
+void xill_force_generic(int on);   // test hook: use k_xill's any-table instantiation (run-time row strides) on standard tables
 void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
                  double *out, double *total, int which, int mode, int conv_grid, cudaStream_t st);
 

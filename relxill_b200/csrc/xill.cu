@@ -138,13 +138,16 @@ __global__ void __launch_bounds__(XL_NT, 4) k_xill(const VPar *__restrict__ vps,
 
 int xill_kernel_init() { return 0; }
 
+static bool g_xill_generic = false;   // test hook: run the any-table instantiation (run-time strides) on standard tables too
+void xill_force_generic(int on) { g_xill_generic = on != 0; }
+
 constexpr int XL_CST = 2528;   // xc_stride of the 2999-bin xillver grid (2521 convolution bins overlap it)
 
 template <bool CG>
 static void launch_xill_t(const VPar *vps, const DevTables &T, const Scratch &S, long n, int which, cudaStream_t st) {
   const XillDev &X = T.xill[which];
   // every table of the 2999-bin xillver grid has these row lengths
-  const bool std_rows = (X.n_incl == XL_NI) && (CG ? X.xc_stride == XL_CST : X.stride == 3008);
+  const bool std_rows = !g_xill_generic && (X.n_incl == XL_NI) && (CG ? X.xc_stride == XL_CST : X.stride == 3008);
   constexpr int ST = CG ? XL_CST : 3008;
   const int nb = CG ? X.xc_n : X.n_ener;   // bins a vector's CTAs cover
   if (X.npar == 6) {

@@ -149,10 +149,13 @@ def test_stage_parity(rx, oracle):
 
 def test_xill_grid_variants_agree(rx, oracle):
     """The zone spectra filed on the convolution grid (rebin folded into the table-corner refresh of k_xill) and on
-    the table grid (rebinned per zone in k_conv) are the same linear map applied in a different order: the spectra
-    agree to rounding, for the 5-D and the 6-D table, and the table-grid path still matches the oracle."""
+    the table grid (rebinned per zone in k_conv) are the same linear map applied in a different order.  The zone spectra
+    differ in the last bit; behind the FFT that is 1e-16 of the spectrum's peak on every bin, i.e. up to ~1e-10 relative
+    on the faintest bins the parity metric looks at (1e-6 of the peak; measured 1.1e-10, the same floor as against the
+    reference).  Both paths match the oracle.  State cache off: every evaluation must run the kernels."""
     e = default_grid(3000)
     assert rx.get_xill_grid()
+    rx.set_cache(False)   # the second evaluation must run the kernels, not return the retained spectra
     try:
         for model in ("relxill", "relxilllp", "relxilllpCp", "relxillNS", "relxillCO"):
             P = sample_params(model, 6, seed=5)
@@ -160,10 +163,36 @@ def test_xill_grid_variants_agree(rx, oracle):
             rx.set_xill_grid(False)
             b = rx.batch_eval(model, e, P)
             rx.set_xill_grid(True)
-            assert max(relerr(x, y) for x, y in zip(a, b)) < 1e-12, model
+            assert max(relerr(x, y) for x, y in zip(a, b)) < 1e-8, model
+            assert relerr(a[0], oracle.eval(model, e, P[0])) < RTOL
             assert relerr(b[0], oracle.eval(model, e, P[0])) < RTOL
     finally:
         rx.set_xill_grid(True)
+        rx.set_cache(True)
+
+
+def test_xill_any_table_instantiation(rx):
+    """k_xill has its row length and inclination count as template constants for the 2999-bin xillver tables and an
+    instantiation with run-time strides for any other table; both must give the same spectra, on both zone-spectrum
+    grids and for the 5-D and 6-D tables."""
+    from relxill_b200 import _lib
+    e = default_grid(1200)
+    L = _lib.lib()
+    rx.set_cache(False)   # every evaluation runs the kernels
+    try:
+        for conv in (True, False):
+            rx.set_xill_grid(conv)
+            for model in ("relxilllp", "relxilllpCp", "relxillNS"):
+                P = sample_params(model, 5, seed=21)
+                a = rx.batch_eval(model, e, P)
+                L.relxill_b200_set_xill_generic(1)
+                b = rx.batch_eval(model, e, P)
+                L.relxill_b200_set_xill_generic(0)
+                assert max(relerr(x, y) for x, y in zip(a, b)) < 1e-13, (model, conv)
+    finally:
+        L.relxill_b200_set_xill_generic(0)
+        rx.set_xill_grid(True)
+        rx.set_cache(True)
 
 
 def test_lmod_symbols_match_batch(rx):
