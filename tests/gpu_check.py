@@ -1,4 +1,6 @@
-"""Stage-by-stage GPU vs oracle comparison (development aid; the parity tests proper live in tests/)."""
+"""Stage-by-stage GPU vs oracle comparison, printed as a table (development aid, run by hand on a GPU box:
+`python tests/gpu_check.py`; not collected by pytest — the parity tests proper are test_gpu_parity.py).  Lives under
+tests/ because it uses the oracle, which only the tests, smoke() and bench.py's CPU legs may touch."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
