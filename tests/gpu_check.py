@@ -61,7 +61,12 @@ for m in models:
                     line += f" {k} {relerr(b.probe(i, k), sg[k], 0):.1e}"
                 line += f" relflux {relerr(b.probe(i, 'relflux'), sg['relflux'].ravel()):.1e}"
                 line += f" dist {relerr(b.probe(i, 'dist'), sg['dist'].ravel()):.1e}"
-                line += f" xill {relerr(b.probe(i, 'xill'), sg['xill'].ravel()):.1e}"
+                if rx.get_xill_grid():   # zone spectra live on the convolution grid: rebin the oracle's like src/Relxill.cpp:461-463
+                    xe, ce = b.probe(i, 'xill_ener'), o.conv_grid()
+                    want = np.array([o.rebin(ce, xe, row) for row in sg['xill']])
+                    line += f" xillc {relerr(b.probe(i, 'xillc', max_len=50 * 4096), want.ravel()):.1e}"
+                else:
+                    line += f" xill {relerr(b.probe(i, 'xill'), sg['xill'].ravel()):.1e}"
                 line += f" total {relerr(b.probe(i, 'total'), sg['total']):.1e}"
             else:
                 line += f" emis {relerr(b.probe(i, 'emis'), sp['emis'], 0):.1e}"
