@@ -12,7 +12,10 @@ KEYS = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
         "smsp__inst_executed.sum", "smsp__average_warps_issue_stalled", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "sm__inst_executed_pipe_xu.avg.pct", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
-        "smsp__cycles_active.avg", "sm__cycles_elapsed.max"]
+        "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"]
 for r in rows[2:]:
     print("-" * 60)
     for h, u, v in zip(hdr, units, r):
