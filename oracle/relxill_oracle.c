@@ -4,11 +4,13 @@
  * of the product path.  Plain sequential C that follows the reference's arithmetic —
  * including its float/double mixing and its quirks — so that it agrees with the unmodified
  * reference (oracle/_ref) to rounding.  Every function names the reference code it restates
- * (paths relative to /root/reference).  Parity status: PINNED against oracle/_ref
- * (tests/test_oracle_vs_ref.py) and the golden vectors under tests/golden/.
+ * (paths relative to /root/reference).  Parity status: PINNED against fresh runs of oracle/_ref
+ * (tests/test_oracle.py::test_oracle_vs_reference_*, whole models and stage by stage) and against the
+ * golden vectors under tests/golden/ that were made with it (14 models, 50-zone cases, rows of the
+ * BASELINE configurations 2-5).
  *
- * Not restated (out of scope): relxillBB, NS/CO tables, alpha model,
- * extended jet, debug file writers, the caches (result-transparent).
+ * Not restated (out of scope): relxillBB, the alpha model, extended jet, debug file
+ * writers, the caches (result-transparent).
  */
 #include "relxill_oracle.h"
 
