@@ -40,6 +40,26 @@ def test_model_layout_matches_oracle(oracle):
         rx.num_params("relxillXX")
 
 
+def test_model_table_matches_the_reference_lmodel_dat():
+    """The drop-in boundary: for every model on the hot path the C symbol XSPEC resolves, the parameter order (with the
+    $switch entries) and the defaults are the ones of the reference's lmodel_relxill_public.dat / _devel.dat
+    (fixture tests/golden/lmodel_layout.json, made by tests/golden/make_lmodel_layout.py from the reference)."""
+    import json
+    import relxill_b200 as rx
+    from relxill_b200 import _lib
+    layout = json.load(open(os.path.join(ROOT, "tests", "golden", "lmodel_layout.json")))
+    out_of_scope = {"relxillBB", "relxilllpAlpha"}                 # SURVEY.md §2.2; INTEGRATION.md §1
+    assert set(layout) - out_of_scope == set(rx.PARAM_NAMES) == set(_lib.LMOD_SYMBOLS)
+    for m, ref in layout.items():
+        if m in out_of_scope:
+            assert ref["symbol"] not in _lib.ABI_SYMBOLS
+            continue
+        assert _lib.LMOD_SYMBOLS[m] == ref["symbol"], m
+        assert [p["name"] for p in ref["params"]] == rx.PARAM_NAMES[m], m
+        np.testing.assert_array_equal(rx.default_params(m), [p["default"] for p in ref["params"]], err_msg=m)
+        assert rx.num_params(m) == len(ref["params"])
+
+
 def test_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
