@@ -37,6 +37,10 @@ class Oracle:
         L.orc_relbase.argtypes = [C.c_char_p, _dp, _dp, C.c_int, _dp]
         L.orc_relxill_stages.argtypes = [C.c_char_p, _dp] + [_dp] * 8 + [_ip, _ip, _dp, _dp]
         L.orc_conv_grid.argtypes = [_dp]
+        L.orc_gshift_fluxboost.argtypes = [C.c_double] * 3
+        L.orc_gshift_fluxboost.restype = C.c_double
+        L.orc_lin2d_float.argtypes = [C.c_double, C.c_double, C.c_float, C.c_float, C.c_float, C.c_float]
+        L.orc_lin2d_float.restype = C.c_double
         L.orc_rebin.argtypes = [_dp, _dp, C.c_int, _dp, _dp, C.c_int]
         L.orc_fft_conv.argtypes = [_dp, _dp, _dp]
         L.orc_nthcomp.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_double, _dp]

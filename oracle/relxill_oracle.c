@@ -747,6 +747,10 @@ static double gshift_fluxboost(double xill_gshift_fac, double g, double gamma) {
   return fb;
 }
 
+/* exported for the reference's known-answer tests of these two helpers (tests/test_oracle.py) */
+double orc_gshift_fluxboost(double xill_gshift_fac, double g, double gamma) { return gshift_fluxboost(xill_gshift_fac, g, gamma); }
+double orc_lin2d_float(double f1, double f2, float r11, float r12, float r21, float r22) { return lin2d_f(f1, f2, r11, r12, r21, r22); }
+
 /* src/Relreturn_Corona.cpp:100-171,263-321 with the table handling of src/Relreturn_Table.cpp:396-611 */
 static int add_returnrad_emis(const Par *p, SysPar *sp) {
   if (!g_rr && load_rrad()) return 1;

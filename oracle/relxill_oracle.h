@@ -46,6 +46,9 @@ void orc_rebin(const double *ener, double *flu, int n, const double *ener0, cons
 void orc_fft_conv(const double *fxill, const double *frel, double *fout);
 void orc_nthcomp(const double *ener, int n, double gamma, double kte, double z, double *out);
 double orc_kerr_rms(double a);
+/* corrected_gshift_fluxboost_factor (src/Relreturn_Corona.cpp:39-83) and interp_lin_2d_float (src/relutility.c:53-58) */
+double orc_gshift_fluxboost(double xill_gshift_fac, double g, double gamma);
+double orc_lin2d_float(double f1, double f2, float r11, float r12, float r21, float r22);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,20 @@ def test_rebin_commutes_with_the_table_blend(oracle):
     assert abs(blend_then_rebin.sum() / (w @ rows).sum() - 1) < 1e-12
 
 
+def test_interp_2d_float_kat(oracle):
+    # reference test/unit/test-stdfunctions.cpp:192-211
+    assert abs(oracle.lib.orc_lin2d_float(0.4, 0.8, 1.0, 2.0, 2.0, 4.0) - 2.52) < 1e-6
+
+
+def test_gshift_fluxboost_factor_kat(oracle):
+    # reference test/unit/tests-returnrad.cpp:479-497 (corrected_gshift_fluxboost_factor)
+    f, gamma = oracle.lib.orc_gshift_fluxboost, 2.0
+    assert f(1.2, 1.5, gamma) > 1.5 ** gamma and f(1.2, 0.3, gamma) > 0.3 ** gamma
+    assert f(1.2, 1.5, gamma) > 1 and 0 < f(1.2, 0.3, gamma) < 1
+    assert f(0.9, 1.5, gamma) < 1.5 ** gamma and f(0.9, 0.3, gamma) < 0.3 ** gamma
+    assert f(0.9, 1.5, gamma) > 1 and 0 < f(0.9, 0.3, gamma) < 1
+
+
 def test_default_grid_endpoints():
     # reference test/unit/tests-execmodel.cpp:44-61
     e = default_grid(100, 0.5, 10.0)
