@@ -55,6 +55,22 @@ def test_gshift_fluxboost_factor_kat(oracle):
     assert f(0.9, 1.5, gamma) > 1 and 0 < f(0.9, 0.3, gamma) < 1
 
 
+def test_energy_grid_shifts(oracle):
+    """XspecSpectrum::shift_energy_grid_1keV / _redshift (src/XspecSpectrum.h:61-76; reference test
+    test/unit/test-cppspectrum.cpp:57-77), seen from outside: a line at lineE on the grid E is the line at 1 keV on
+    E / lineE, and a redshift z moves the grid to E (1 + z)."""
+    e = default_grid(800, 0.2, 20.0)
+    p = oracle.default_params("relline")
+    p[0], p[8] = 6.4, 0.0
+    base = oracle.eval("relline", e, p)
+    q = p.copy()
+    q[0] = 3.2
+    np.testing.assert_allclose(oracle.eval("relline", e / 2.0, q), base, rtol=1e-10, atol=1e-14)   # lineE halves with the grid
+    q = p.copy()
+    q[8] = 0.5
+    np.testing.assert_allclose(oracle.eval("relline", e / 1.5, q), base, rtol=1e-10, atol=1e-14)   # observed grid = rest grid / (1 + z)
+
+
 def test_default_grid_endpoints():
     # reference test/unit/tests-execmodel.cpp:44-61
     e = default_grid(100, 0.5, 10.0)
