@@ -46,14 +46,29 @@ RELXILL_B200_LMOD(lmodxillverco);            /* lmodel_relxill_devel.dat:1  xill
 RELXILL_B200_LMOD(lmodrelxillco);            /* lmodel_relxill_devel.dat:11 relxillCO (14) */
 
 /* ---------------------------------------------------------------- library state */
-/* Select the CUDA device and load the tables from `table_dir` (NULL: $RELXILL_TABLE_PATH or "./").
- * Optional: the first evaluation does it lazily on the current device.  Returns 0 on success. */
+/* Select the CUDA device (-1: the current one) and load the tables from `table_dir` (NULL: $RELXILL_TABLE_PATH or
+ * "./").  Optional: the first evaluation does it lazily on the current device — or, if the environment variable
+ * RELXILL_B200_DEVICES is set ("all" or a count), on that many devices.  Returns 0 on success. */
 int relxill_b200_init(const char *table_dir, int device);
-/* Free all device memory (tables, scratch). */
+/* Several devices in ONE process (north_star: "the parameter batch is sharded across the 8 GPUs of one box"): one
+ * engine — tables replicated, own scratch arena and streams — on each of the devices 0 .. n_devices-1 (n_devices < 1:
+ * all visible devices).  relxill_batch_eval and the lmod* symbols then shard every batch of >= 2 vectors per device
+ * over the engines, one host thread per device, and every device copies its rows straight into the caller's flux
+ * array: no collective is needed for host-buffer calls.  Prepared batches live on one engine
+ * (relxill_b200_prepare_on). */
+int relxill_b200_init_devices(const char *table_dir, int n_devices);
+int relxill_b200_num_devices(void);
+/* How relxill_batch_eval splits a batch over several devices: 0 (default) contiguous blocks, 1 round-robin rows — for
+ * structured batches (parameter-grid sweeps) whose cost varies systematically along the batch.  Also settable with the
+ * environment variable RELXILL_B200_INTERLEAVE=1. */
+void relxill_b200_set_sharding(int interleave);
+/* Free all device memory (tables, scratch) on every device. */
 void relxill_b200_shutdown(void);
-/* Equivalent of the reference's RELXILL_NUM_RZONES environment variable
- * (src/relutility.c:506-544); 0 restores the defaults (1 / 10 / 25).  The env var itself is read
- * once at init. */
+/* Programmatic override of the reference's RELXILL_NUM_RZONES environment variable (src/relutility.c:506-544):
+ * n > 0 takes precedence over the variable, 0 removes the override.  Without an override the variable is read on
+ * EVERY call, as are RELXILL_RETURNRAD_SWITCH, RELLINE_PHYSICAL_NORM, RELXILL_CONSTANT_DENSITY and
+ * RELXILL_RENORMALIZE — the reference re-reads all of them per evaluation (src/relutility.c:372-396,506-544;
+ * src/ModelDefinition.cpp:123-149; src/Relxill.cpp:241-278), and callers flip them mid-session. */
 void relxill_b200_set_num_zones(int n);
 /* Number of parameters of a model ("relxilllp", ...; XSPEC names), -1 if unknown. */
 int relxill_b200_num_params(const char *model);
@@ -85,6 +100,13 @@ int relxill_batch_eval_device(const char *model, const double *energy, int n_flu
 typedef struct relxill_b200_batch relxill_b200_batch;
 relxill_b200_batch *relxill_b200_prepare(const char *model, const double *energy, int n_flux,
                                          const double *params, long n_vec);
+/* ... on the engine with index `device_index` (0 .. relxill_b200_num_devices()-1); relxill_b200_prepare uses engine 0 */
+relxill_b200_batch *relxill_b200_prepare_on(int device_index, const char *model, const double *energy, int n_flux,
+                                            const double *params, long n_vec);
+/* Enqueues the kernels of the batch on `stream` (a cudaStream_t of the batch's device) and returns; d_flux is device
+ * memory of that device.  Asynchronous with respect to the host: synchronise the stream (or call
+ * relxill_b200_batch_status, which waits) before reading the result.  Runs that share an engine are ordered one after
+ * the other on the device whatever streams they are given (they share the engine's scratch arena). */
 int relxill_b200_run(relxill_b200_batch *b, double *d_flux, void *stream);
 /* Device-resident state cache (the reference's Relcache / specCache / RelxillCache, src/Relcache.cpp,
  * src/Relbase.cpp:143-168, src/Relxill.cpp:296-300,405, as a device-resident re-use of the previous run):
@@ -92,13 +114,17 @@ int relxill_b200_run(relxill_b200_batch *b, double *d_flux, void *stream);
  * same n_vec) and/or the energy grid in place and run again: a vector whose whole parameter set is unchanged
  * (z aside) only repeats the final rebin, one whose relativistic parameters are unchanged keeps its line
  * profiles and emission-angle distribution and repeats only the xillver half.  The results are bit-identical
- * to a fresh evaluation.  State survives only while no other batch has used the arena in between and the
- * batch ran in one piece (n_vec <= the chunk capacity).  relxill_batch_eval and the lmod* symbols keep their
- * last batch alive for the same purpose (an XSPEC fit varies one parameter at a time). */
+ * to a fresh evaluation.  State survives while no other batch has used the arena in between and the batch fits the
+ * arena (n_vec <= the chunk capacity, 4096 by default; RELXILL_B200_CHUNK) — also when a host-buffer call cuts it into
+ * pipelined pieces, each piece keeps its own slice of the arena.  relxill_batch_eval and the lmod* symbols keep their
+ * last batch alive for the same purpose (an XSPEC fit varies one parameter at a time; an MCMC step leaves the rejected
+ * walkers where they were). */
 int relxill_b200_update_params(relxill_b200_batch *b, const double *params /* [n_vec][npar] */);
 int relxill_b200_update_energy(relxill_b200_batch *b, const double *energy, int n_flux);
 /* vectors of the last run that were {recomputed, re-used the relativistic half, re-used everything} */
 int relxill_b200_reuse_counts(relxill_b200_batch *b, long *out3);
+/* the same counts for the batch(es) the last relxill_batch_eval / lmod* call retained (summed over the devices) */
+int relxill_b200_last_eval_reuse(long *out3);
 /* switch the re-use off (0) / on (1, default); measurements of the full path switch it off */
 void relxill_b200_set_cache(int on);
 /* per-vector status after prepare/run (host copy), length n_vec */

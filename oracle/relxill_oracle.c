@@ -247,10 +247,25 @@ static const ModelDef MODELS[] = {
 };
 #define N_MODELS ((int) (sizeof(MODELS) / sizeof(MODELS[0])))
 
+/* The reference reads its environment switches on every evaluation; so does the oracle.  orc_set_num_zones_env /
+ * orc_set_returnrad_env are programmatic overrides for the tests (0 / -1: no override, the environment decides). */
 static int g_env_num_zones = 0;
 static int g_env_returnrad = -1;
 void orc_set_num_zones_env(int n) { g_env_num_zones = n; }
 void orc_set_returnrad_env(int v) { g_env_returnrad = v; }
+static int env_is_one(const char *name) { /* is_env_set, src/ModelDefinition.cpp:123-137 */
+  const char *env = getenv(name);
+  return (env != NULL && (int) strtod(env, NULL) == 1) ? 1 : 0;
+}
+static int env_num_zones(void) { /* src/relutility.c:509-513 */
+  if (g_env_num_zones > 0) return g_env_num_zones;
+  const char *env = getenv("RELXILL_NUM_RZONES");
+  return env ? (int) atof(env) : 0;
+}
+static int env_returnrad(void) {
+  if (g_env_returnrad >= 0) return g_env_returnrad;
+  return getenv("RELXILL_RETURNRAD_SWITCH") ? env_is_one("RELXILL_RETURNRAD_SWITCH") : -1;
+}
 
 static const ModelDef *find_model(const char *name) {
   for (int i = 0; i < N_MODELS; i++)
@@ -270,7 +285,7 @@ int orc_default_params(const char *model, double *out) {
 
 /* zone count, src/relutility.c:506-544 */
 static int get_num_zones(int model_type, int emis_type, int ion_grad_type) {
-  int env = g_env_num_zones;
+  int env = env_num_zones();
   if (ion_grad_type != ION_CONST) {
     if (env != 0 && env > 9 && env <= ORC_NZMAX) return env;
     return 25;
@@ -326,7 +341,7 @@ static int interpret_params(const ModelDef *m, const double *par, Par *p) {
   p->limb = (int) lround(v[P_LIMB]);
   { /* get_returnrad_switch :139-149 */
     int def = (m->irrad == EMIS_LP) ? 1 : 0;
-    int sw = (g_env_returnrad == 1) ? 1 : def;
+    int sw = (env_returnrad() == 1) ? 1 : def;
     p->return_rad = (int) lround(has[P_SWRET] ? v[P_SWRET] : (double) sw);
   }
   /* check_parameter_bounds :168-273 */
@@ -1035,9 +1050,10 @@ static int relline_profile(const Par *p, const SysPar *sp, const double *ener, i
       flux[i * n_ener + j] /= 0.5 * (ener[j] + ener[j + 1]);
       sum += flux[i * n_ener + j];
     }
-  int renorm; /* do_renorm_model, relutility.c:603-623 (RELLINE_PHYSICAL_NORM unset) */
-  if (p->model_type < 0) renorm = (p->emis_type == EMIS_LP) ? 0 : 1;
-  else renorm = 1;
+  int renorm; /* do_renorm_model, relutility.c:603-623; do_not_normalize_relline, :386-396 */
+  const int phys_norm = env_is_one("RELLINE_PHYSICAL_NORM");
+  if (p->model_type < 0) renorm = (p->emis_type == EMIS_LP || phys_norm) ? 0 : 1;
+  else renorm = phys_norm ? 0 : 1;
   if (renorm) {
     double norm = 1;
     if (p->model_type < 0 && p->emis_type == EMIS_BKN) norm = 0.5 * cos((p->incl * 180.0 / M_PI) * M_PI / 180);
@@ -1683,6 +1699,16 @@ int orc_eval_model(const char *model, const double *energy, int n_flux, const do
     Stages st;
     memset(&st, 0, sizeof(st));
     rc = relxill_pipeline(&p, &st);
+    if (!rc && env_is_one("RELXILL_RENORMALIZE")) { /* renorm_relxill_spectrum_1keV, Relxill.cpp:241-259: 1 cts/s/keV/cm2 at 3 keV */
+      int klo = 0, khi = ORC_NCONV - 1; /* binary_search(energy, num_flux_bins, 3.0), relutility.c:155-171 */
+      while (khi - klo > 1) {
+        int k = (khi + klo) / 2;
+        if (g_econv[k] > 3.0) khi = k; else klo = k;
+      }
+      double dE = g_econv[klo + 1] - g_econv[klo];
+      double nf = 1.0 / (st.total[klo] / dE);
+      for (int i = 0; i < ORC_NCONV; i++) st.total[i] *= nf;
+    }
     if (!rc) orc_rebin(e, flux, n_flux, g_econv, st.total, ORC_NCONV); /* Relxill.cpp:261-278 */
     free_stages(&st);
   } else if (m->type == T_CONV) { /* LocalModel.cpp:82-98, Relbase.cpp:257-289 */

@@ -38,6 +38,7 @@ ABI_SYMBOLS = [
     "relxill_b200_algorithmic_bytes", "relxill_b200_last_launches", "relxill_b200_set_profiling", "relxill_b200_keep_intermediates",
     "relxill_b200_kernel_times", "relxill_b200_probe", "relxill_b200_update_params", "relxill_b200_update_energy",
     "relxill_b200_reuse_counts", "relxill_b200_set_cache", "relxill_b200_set_xill_grid", "relxill_b200_get_xill_grid", "relxill_b200_set_xill_generic",
+    "relxill_b200_last_eval_reuse", "relxill_b200_init_devices", "relxill_b200_num_devices", "relxill_b200_set_sharding", "relxill_b200_prepare_on",
 ] + sorted(LMOD_SYMBOLS.values())
 
 
@@ -62,6 +63,12 @@ def lib() -> C.CDLL:
     L.relxill_batch_eval_device.restype = C.c_int
     L.relxill_b200_prepare.argtypes = [C.c_char_p, _dp, C.c_int, _dp, C.c_long]
     L.relxill_b200_prepare.restype = C.c_void_p
+    L.relxill_b200_prepare_on.argtypes = [C.c_int, C.c_char_p, _dp, C.c_int, _dp, C.c_long]
+    L.relxill_b200_prepare_on.restype = C.c_void_p
+    L.relxill_b200_init_devices.argtypes = [C.c_char_p, C.c_int]
+    L.relxill_b200_init_devices.restype = C.c_int
+    L.relxill_b200_num_devices.restype = C.c_int
+    L.relxill_b200_set_sharding.argtypes = [C.c_int]
     L.relxill_b200_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.relxill_b200_run.restype = C.c_int
     L.relxill_b200_batch_status.argtypes = [C.c_void_p, _ip]
@@ -81,6 +88,8 @@ def lib() -> C.CDLL:
     L.relxill_b200_update_energy.restype = C.c_int
     L.relxill_b200_reuse_counts.argtypes = [C.c_void_p, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]
     L.relxill_b200_reuse_counts.restype = C.c_int
+    L.relxill_b200_last_eval_reuse.argtypes = [np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]
+    L.relxill_b200_last_eval_reuse.restype = C.c_int
     L.relxill_b200_set_cache.argtypes = [C.c_int]
     L.relxill_b200_set_xill_grid.argtypes = [C.c_int]
     L.relxill_b200_get_xill_grid.restype = C.c_int

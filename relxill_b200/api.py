@@ -69,6 +69,32 @@ def set_cache(on: bool) -> None:
     _lib.lib().relxill_b200_set_cache(1 if on else 0)
 
 
+def last_eval_reuse() -> dict:
+    """Vectors of the last `batch_eval` / `lmod` call that were recomputed / re-used their relativistic half / re-used
+    their whole spectrum (summed over the devices)."""
+    out = np.zeros(3, np.int64)
+    _lib.lib().relxill_b200_last_eval_reuse(out)
+    return dict(recomputed=int(out[0]), reused_rel=int(out[1]), reused_all=int(out[2]))
+
+
+def init_devices(table_dir: str | None = None, n_devices: int = 0) -> int:
+    """One engine per device 0..n_devices-1 (0: all visible) in this process; `batch_eval` then shards over them.
+    Returns the number of engines."""
+    rc = _lib.lib().relxill_b200_init_devices(table_dir.encode() if table_dir else None, int(n_devices))
+    if rc != 0:
+        raise RuntimeError("relxill_b200 initialisation failed: " + _lib.last_error())
+    return int(_lib.lib().relxill_b200_num_devices())
+
+
+def num_devices() -> int:
+    return int(_lib.lib().relxill_b200_num_devices())
+
+
+def set_sharding(interleave: bool) -> None:
+    """Multi-device split of `batch_eval`: contiguous blocks (default) or round-robin rows (parameter-grid sweeps)."""
+    _lib.lib().relxill_b200_set_sharding(1 if interleave else 0)
+
+
 def set_xill_grid(conv_grid: bool) -> None:
     """Where the per-zone xillver spectra are filed: on the convolution grid (default) or on the table grid
     (include/relxill_b200.h); the results agree to rounding."""

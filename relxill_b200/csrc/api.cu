@@ -1,8 +1,11 @@
 // api.cu — runtime + C ABI of librelxill_b200.so (see include/relxill_b200.h).
 //
-// Engine: one per process (one process per GPU); owns the HBM-resident tables, a scratch arena
-// sized for one chunk of parameter vectors, and the kernel sequence.  Batches larger than the
-// chunk capacity are streamed through the arena chunk by chunk on the caller's stream.
+// Runtime: process-wide switches (the reference's environment variables, the state-cache switch, ...) and the list
+// of engines.  Engine: one per CUDA device; owns that device's HBM-resident tables, a scratch arena sized for one
+// chunk of parameter vectors, its streams and staging buffers, and runs the kernel sequence.  Batches larger than the
+// chunk capacity stream through the arena chunk by chunk; a host-buffer call (relxill_batch_eval) is sharded over the
+// engines — one host thread per device, every device writes its rows straight into the caller's array — and inside a
+// device it is cut into pieces whose device->host copies overlap the kernels of the next piece.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -11,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <set>
 #include <string>
@@ -49,78 +53,139 @@ enum KFam { KF_SYSPAR, KF_ZONE, KF_FINE, KF_DIST, KF_LINE, KF_XILL, KF_CONV, KF_
 const char *KF_NAMES[KF_COUNT] = {"k_syspar", "k_zone", "k_fine", "k_dist", "k_line", "k_xill", "k_conv", "k_linefinish", "k_nth", "k_prim_nth", "k_xillver"};
 
 struct Engine {
-  std::mutex mu;
+  std::mutex mu;              // serialises the calls that use this device's arena
   bool inited = false;
   int device = 0;
   Tables *tables = nullptr;
-  HostConfig cfg;
   Scratch S{};
+  bool S_nth = false;         // the nthcomp work arrays of the arena are allocated
   std::vector<void *> scratch_allocs;
-  double *d_total = nullptr;  // [cap][NCONV]
-  double *d_io = nullptr;     // staging for host-buffer calls
+  double *d_io = nullptr;     // output staging of host-buffer calls
   size_t d_io_cap = 0;
+  double *h_io = nullptr;     // pinned staging for callers whose flux array is pageable memory
+  size_t h_io_cap = 0;
+  cudaStream_t stream_c = nullptr, stream_d = nullptr;   // compute / copy streams of host-buffer calls
+  cudaEvent_t arena_busy = nullptr;                      // recorded behind the last kernel that touches the arena
+  bool arena_busy_set = false;
+  cudaStream_t arena_stream = nullptr;                   // ... and the stream it was recorded on
+  // device / pinned buffers recycled between batches (cudaMalloc, cudaFree and cudaMallocHost synchronise and cost
+  // milliseconds).  A buffer only goes back to the pool once the work that uses it has been waited for (wait_arena).
+  std::vector<std::pair<size_t, void *>> pool, pool_pinned;
+  // Device-resident state cache (SURVEY.md §8f rank 3).  The scratch arena keeps the intermediates of the batch that
+  // ran last and fitted the arena (arena_owner = that batch's uid); when the same batch runs again with updated
+  // parameters, vectors whose relativistic half / whole parameter set is unchanged re-use their rows.
+  unsigned long arena_owner = 0;
+  relxill_b200_batch *retained = nullptr;   // the batch of the last host-buffer call (what an XSPEC fit re-evaluates)
+};
+
+struct Runtime {
+  std::mutex mu;              // guards the engine list and the switches below
+  std::vector<std::unique_ptr<Engine>> engines;
+  std::string table_dir;
+  HostConfig cfg;             // env-derived fields are refreshed per call (read_call_env)
   long max_chunk = 4096;
   long pipe_piece = 2072;     // vectors per pipelined piece of a host-buffer call (RELXILL_B200_PIPE)
   long pipe_last = 888;       // ... and of the last piece, whose device->host copy nothing overlaps (RELXILL_B200_PIPE_LAST)
-  cudaStream_t stream_c = nullptr, stream_d = nullptr;   // compute / copy streams of host-buffer calls
+  bool env_read = false;
   bool profiling = false;
   bool keep_intermediates = false;   // store what only the test probes read (emission-angle tables)
   // k_xill blends the convolution-grid copy of the table (rows rebinned once at load, xill.cu) and k_conv reads the zone
   // spectra with plain coalesced loads; off (RELXILL_B200_XILL_GRID=table): no such copy is built, zone spectra on the
   // table grid, rebinned per zone in k_conv
   bool xill_conv_grid = true;
-  // device buffers recycled between batches (cudaMalloc/cudaFree synchronise and cost milliseconds)
-  std::vector<std::pair<size_t, void *>> pool;
-  // Device-resident state cache (SURVEY.md §8f rank 3).  The scratch arena keeps the intermediates of the batch that
-  // ran last in one piece (arena_owner = that batch's uid); when the same batch runs again with updated parameters,
-  // vectors whose relativistic half / whole parameter set is unchanged re-use their rows instead of recomputing them.
   bool cache_on = true;
-  unsigned long arena_owner = 0, next_uid = 1;
-  relxill_b200_batch *retained = nullptr;   // the batch of the last host-buffer call (what an XSPEC fit re-evaluates)
+  int interleave = 0;         // multi-device sharding of host-buffer calls: 0 contiguous blocks, 1 round-robin rows
+  unsigned long next_uid = 1;
 };
-Engine g_eng;
+Runtime g_rt;
 
-void *pool_get(Engine &E, size_t bytes) {
-  for (size_t i = 0; i < E.pool.size(); i++) {
-    if (E.pool[i].first >= bytes && E.pool[i].first <= 2 * bytes + 4096) {
-      void *p = E.pool[i].second;
-      E.pool.erase(E.pool.begin() + i);
+// what one call needs of the process-wide switches, taken once under the runtime mutex
+struct CallCfg {
+  HostConfig cfg;
+  long max_chunk, pipe_piece, pipe_last;
+  bool profiling, keep_intermediates, xill_conv_grid, cache_on;
+};
+
+// The reference's environment switches, read per call like the reference does (a pyxspec session or the reference's own
+// e2e tests flip them between evaluations): get_num_zones (src/relutility.c:506-544), get_returnrad_switch / is_env_set
+// (src/ModelDefinition.cpp:123-149), do_not_normalize_relline (src/relutility.c:386-396), constantDiskDensity (:372-382),
+// do_renorm_relxill (src/Relxill.cpp:241-247).  Their values flow into every VPar (nz, return_rad, renorm,
+// const_density), so the state cache sees a change as a parameter change.
+void read_call_env_locked() {
+  auto is_one = [](const char *name) {
+    const char *env = getenv(name);
+    return (env && (int) strtod(env, nullptr) == 1) ? 1 : 0;
+  };
+  HostConfig &c = g_rt.cfg;
+  const char *nz = getenv("RELXILL_NUM_RZONES");
+  c.env_num_zones = nz ? (int) atof(nz) : 0;
+  c.env_returnrad = getenv("RELXILL_RETURNRAD_SWITCH") ? is_one("RELXILL_RETURNRAD_SWITCH") : -1;
+  c.env_phys_norm = is_one("RELLINE_PHYSICAL_NORM");
+  c.env_const_density = is_one("RELXILL_CONSTANT_DENSITY");
+  c.env_renorm_relxill = is_one("RELXILL_RENORMALIZE");
+  if (!g_rt.env_read) {   // this library's own tuning knobs are read once
+    g_rt.env_read = true;
+    // vectors per chunk / piece: the vector index rides in gridDim.y of several kernels (limit 65535)
+    if (const char *env = getenv("RELXILL_B200_CHUNK")) g_rt.max_chunk = std::min(65535L, std::max(1L, atol(env)));
+    if (const char *env = getenv("RELXILL_B200_PIPE")) g_rt.pipe_piece = std::min(65535L, std::max(1L, atol(env)));
+    if (const char *env = getenv("RELXILL_B200_PIPE_LAST")) g_rt.pipe_last = std::max(0L, atol(env));
+    if (const char *env = getenv("RELXILL_B200_XILL_GRID")) g_rt.xill_conv_grid = std::string(env) != "table";
+    if (const char *env = getenv("RELXILL_B200_INTERLEAVE")) g_rt.interleave = atoi(env) != 0;
+  }
+}
+
+CallCfg call_cfg(bool refresh_env) {
+  std::lock_guard<std::mutex> lk(g_rt.mu);
+  if (refresh_env || !g_rt.env_read) read_call_env_locked();
+  return CallCfg{g_rt.cfg, g_rt.max_chunk, g_rt.pipe_piece, g_rt.pipe_last, g_rt.profiling, g_rt.keep_intermediates,
+                 g_rt.xill_conv_grid, g_rt.cache_on};
+}
+
+// ---------------------------------------------------------------------------------- buffers
+void *pool_get(std::vector<std::pair<size_t, void *>> &pool, size_t bytes, bool pinned) {
+  for (size_t i = 0; i < pool.size(); i++) {
+    if (pool[i].first >= bytes && pool[i].first <= 2 * bytes + 4096) {
+      void *p = pool[i].second;
+      pool.erase(pool.begin() + i);
       return p;
     }
   }
   void *d = nullptr;
-  if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
+  const cudaError_t e = pinned ? cudaMallocHost(&d, bytes) : cudaMalloc(&d, bytes);
+  if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
   return d;
 }
-void pool_put(Engine &E, void *p, size_t bytes) {
+void pool_put(std::vector<std::pair<size_t, void *>> &pool, void *p, size_t bytes, bool pinned) {
   if (!p) return;
-  if (E.pool.size() >= 8) {
-    cudaFree(E.pool.front().second);
-    E.pool.erase(E.pool.begin());
+  if (pool.size() >= 8) {
+    if (pinned) cudaFreeHost(pool.front().second); else cudaFree(pool.front().second);
+    pool.erase(pool.begin());
   }
-  E.pool.emplace_back(bytes, p);
+  pool.emplace_back(bytes, p);
+}
+
+// Everything that was enqueued on this engine's arena (kernels of the last run, the status copy behind them) has
+// finished.  Called before host code overwrites what those kernels read (parameter upload, recycled buffers).
+void wait_arena(Engine &E) {
+  if (E.arena_busy_set) {
+    cudaEventSynchronize(E.arena_busy);
+    E.arena_busy_set = false;
+  }
 }
 
 void free_scratch(Engine &E) {
+  wait_arena(E);
   E.arena_owner = 0;   // whatever state the arena held is gone
   for (void *p : E.scratch_allocs) cudaFree(p);
   E.scratch_allocs.clear();
   E.S = Scratch{};
-  E.d_total = nullptr;
-}
-
-template <class T> bool salloc(Engine &E, T *&p, size_t n) {
-  void *d = nullptr;
-  if (cudaMalloc(&d, n * sizeof(T)) != cudaSuccess) return false;
-  E.scratch_allocs.push_back(d);
-  p = (T *) d;
-  return true;
+  E.S_nth = false;
 }
 
 int ensure_scratch(Engine &E, long cap, int nz_cap, int ne_cap, int nex_stride, bool nth) {
   Scratch &S = E.S;
-  if (S.cap >= cap && S.nz_cap >= nz_cap && S.ne_line_cap >= ne_cap && S.nex_stride >= nex_stride && (!nth || S.nth_spt)) return 0;
-  nth = nth || S.nth_spt != nullptr;
+  if (S.cap >= cap && S.nz_cap >= nz_cap && S.ne_line_cap >= ne_cap && S.nex_stride >= nex_stride && (!nth || E.S_nth)) return 0;
+  nth = nth || E.S_nth;
   cap = std::max(cap, S.cap);
   nz_cap = std::max(nz_cap, S.nz_cap);
   ne_cap = std::max(ne_cap, S.ne_line_cap);
@@ -128,67 +193,61 @@ int ensure_scratch(Engine &E, long cap, int nz_cap, int ne_cap, int nex_stride, 
   free_scratch(E);
   bool ok = true;
   const size_t c = (size_t) cap;
-  ok &= salloc(E, S.re, c * NR) && salloc(E, S.gmin, c * NR) && salloc(E, S.gmax, c * NR) && salloc(E, S.emis, c * NR);
-  ok &= salloc(E, S.del_emit, c * NR) && salloc(E, S.del_inc, c * NR) && salloc(E, S.fr, c * NR);
-  ok &= salloc(E, S.zfirst, c * (NZMAX + 1)) && salloc(E, S.brk_i, c * 2) && salloc(E, S.brk_f, c * 2);
-  ok &= salloc(E, S.it, c * NR) && salloc(E, S.izone, c * NR) && salloc(E, S.glim, c * 2) && salloc(E, S.reflfrac, c * 8);
-  ok &= salloc(E, S.trff, c * NR * NG * 2) && salloc(E, S.cosne, c * NR * NG * 2);
-  ok &= salloc(E, S.relrow, c * REL_NRT * NG * 4);
-  ok &= salloc(E, S.eshift, c * NZMAX) && salloc(E, S.zlxi, c * NZMAX) && salloc(E, S.zdens, c * NZMAX);
-  ok &= salloc(E, S.zect, c * NZMAX) && salloc(E, S.normch, c * NZMAX) && salloc(E, S.corr_flux, c * NZMAX);
-  ok &= salloc(E, S.corr_gshift, c * NZMAX) && salloc(E, S.nsrc, c);
-  ok &= salloc(E, S.xrow, c * NZMAX * 32) && salloc(E, S.xw, c * NZMAX * 32);
-  ok &= salloc(E, S.xkey, c * NZMAX * 32) && salloc(E, S.xwsort, c * NZMAX * 32) && salloc(E, S.xn, c);
-  ok &= salloc(E, S.xga_off, c * 4) && salloc(E, S.xga_w, c * 4) && salloc(E, S.zrange, c * NZMAX * 2);
-  ok &= salloc(E, S.relflux, c * nz_cap * ne_cap) && salloc(E, S.dist, c * NZMAX * MAX_INCL) && salloc(E, S.distpart, c * NR * 10);
-  ok &= salloc(E, S.xillz, c * nz_cap * (size_t) std::max(nex_stride, 1)) && salloc(E, S.status, c);
-  ok &= salloc(E, E.d_total, c * NCONV);
-  if (nth) {
-    ok &= salloc(E, S.nth_gam, c * NTH_MAX * NTH_SOL) && salloc(E, S.nth_g, c * NTH_MAX * NTH_SOL);
-    ok &= salloc(E, S.nth_spt, c * NTH_MAX * NTH_SOL) && salloc(E, S.nth_jmax, c * NTH_SOL);
-  }
+  const size_t nzc = (size_t) nz_cap, nec = (size_t) ne_cap, nxs = (size_t) std::max(nex_stride, 1);
+  auto alloc = [&](void **p, size_t bytes) {
+    if (!ok) return;
+    void *d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) { cudaGetLastError(); ok = false; return; }
+    E.scratch_allocs.push_back(d);
+    *p = d;
+  };
+#define RX_ALLOC(type, name, count) alloc((void **) &S.name, c * (size_t) (count) * sizeof(type));
+#define RX_ALLOC_NTH(type, name, count) if (nth) alloc((void **) &S.name, c * (size_t) (count) * sizeof(type));
+  SCRATCH_FIELDS(RX_ALLOC, RX_ALLOC_NTH)
+#undef RX_ALLOC
+#undef RX_ALLOC_NTH
+  (void) nzc; (void) nec; (void) nxs;
   if (!ok) {
     free_scratch(E);
     set_err("out of device memory for the scratch arena");
     return -2;
   }
   S.cap = cap; S.nz_cap = nz_cap; S.ne_line_cap = ne_cap; S.nex_stride = nex_stride;
+  E.S_nth = nth;
   return 0;
 }
 
-int engine_init(Engine &E, const char *dir, int device) {
+// The part of the arena that belongs to the vectors [c0, c0 + ...) of the batch that owns it
+Scratch scratch_slice(const Scratch &S, long c0, bool nth) {
+  if (c0 == 0) return S;
+  Scratch R = S;
+  const size_t o = (size_t) c0;
+  const size_t nzc = (size_t) S.nz_cap, nec = (size_t) S.ne_line_cap, nxs = (size_t) std::max(S.nex_stride, 1);
+#define RX_OFF(type, name, count) R.name = S.name + o * (size_t) (count);
+#define RX_OFF_NTH(type, name, count) if (nth) R.name = S.name + o * (size_t) (count);
+  SCRATCH_FIELDS(RX_OFF, RX_OFF_NTH)
+#undef RX_OFF
+#undef RX_OFF_NTH
+  (void) nzc; (void) nec; (void) nxs;
+  if (S.reuse) R.reuse = S.reuse + o;
+  R.cap = S.cap - c0;
+  return R;
+}
+
+int engine_init(Engine &E, const std::string &dir, int device, bool conv_grid) {
   if (E.inited) return 0;
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-    set_err("no CUDA device available (this library has no CPU fallback)");
-    return -1;
-  }
-  if (device < 0) {
-    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
-  }
   CK(cudaSetDevice(device));
   E.device = device;
-  std::string d;
-  if (dir && *dir) d = dir;
-  else if (const char *env = getenv("RELXILL_TABLE_PATH")) d = env;  // src/relutility.c:320-328
-  else d = "./";
-  if (const char *env = getenv("RELXILL_NUM_RZONES")) E.cfg.env_num_zones = (int) atof(env);
-  if (const char *env = getenv("RELXILL_RETURNRAD_SWITCH")) E.cfg.env_returnrad = (int) atof(env);
-  if (const char *env = getenv("RELLINE_PHYSICAL_NORM")) E.cfg.env_phys_norm = ((int) strtod(env, nullptr) == 1) ? 1 : 0;
-  if (const char *env = getenv("RELXILL_CONSTANT_DENSITY")) E.cfg.env_const_density = ((int) strtod(env, nullptr) == 1) ? 1 : 0;
-  if (const char *env = getenv("RELXILL_B200_CHUNK")) E.max_chunk = std::max(1L, atol(env));
-  if (const char *env = getenv("RELXILL_B200_PIPE")) E.pipe_piece = std::max(1L, atol(env));
-  if (const char *env = getenv("RELXILL_B200_PIPE_LAST")) E.pipe_last = std::max(0L, atol(env));
-  if (const char *env = getenv("RELXILL_B200_XILL_GRID")) E.xill_conv_grid = std::string(env) != "table";
-  if (!E.stream_c) cudaStreamCreateWithFlags(&E.stream_c, cudaStreamNonBlocking);
-  if (!E.stream_d) cudaStreamCreateWithFlags(&E.stream_d, cudaStreamNonBlocking);
+  if (!E.stream_c) CK(cudaStreamCreateWithFlags(&E.stream_c, cudaStreamNonBlocking));
+  if (!E.stream_d) CK(cudaStreamCreateWithFlags(&E.stream_d, cudaStreamNonBlocking));
+  if (!E.arena_busy) CK(cudaEventCreateWithFlags(&E.arena_busy, cudaEventDisableTiming));
   if (kernels_init() != 0) {
     set_err("kernel attribute setup failed (is this an sm_100a device?)");
     return -1;
   }
   E.tables = new Tables();
-  E.tables->set_conv_grid_copy(E.xill_conv_grid);
-  const std::string err = E.tables->load(d);
+  E.tables->set_conv_grid_copy(conv_grid);
+  const std::string err = E.tables->load(dir);
   if (!err.empty()) {
     set_err(err);
     delete E.tables;
@@ -199,22 +258,91 @@ int engine_init(Engine &E, const char *dir, int device) {
   return 0;
 }
 
+std::string resolve_table_dir(const char *dir) {
+  if (dir && *dir) return dir;
+  if (const char *env = getenv("RELXILL_TABLE_PATH")) return env;   // src/relutility.c:320-328
+  return "./";
+}
+
+// Engines for devices first .. first + n - 1 (n < 1: all visible devices from `first` on; first < 0: the current
+// device).  Idempotent when the set is unchanged.
+int runtime_init(const char *table_dir, int first, int n) {
+  std::lock_guard<std::mutex> lk(g_rt.mu);
+  if (!g_rt.env_read) read_call_env_locked();
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_err("no CUDA device available (this library has no CPU fallback)");
+    return -1;
+  }
+  if (first < 0) {
+    if (cudaGetDevice(&first) != cudaSuccess) first = 0;
+  }
+  if (n < 1) n = ndev - first;
+  if (n < 1 || first + n > ndev) {
+    set_err("requested devices " + std::to_string(first) + ".." + std::to_string(first + n - 1) + ", " + std::to_string(ndev) + " visible");
+    return -1;
+  }
+  if (!g_rt.engines.empty()) {
+    bool same = (int) g_rt.engines.size() == n;
+    for (int i = 0; same && i < n; i++) same = g_rt.engines[i]->device == first + i;
+    if (same) return 0;
+    set_err("already initialised on another device set: call relxill_b200_shutdown() first");
+    return -1;
+  }
+  g_rt.table_dir = resolve_table_dir(table_dir);
+  for (int i = 0; i < n; i++) {
+    std::unique_ptr<Engine> e(new Engine());
+    if (engine_init(*e, g_rt.table_dir, first + i, g_rt.xill_conv_grid)) {
+      g_rt.engines.clear();
+      return -1;
+    }
+    g_rt.engines.push_back(std::move(e));
+  }
+  cudaSetDevice(g_rt.engines[0]->device);
+  return 0;
+}
+
+Engine *engine_at(int idx) {
+  std::lock_guard<std::mutex> lk(g_rt.mu);
+  if (idx < 0 || idx >= (int) g_rt.engines.size()) return nullptr;
+  return g_rt.engines[idx].get();
+}
+int num_engines() {
+  std::lock_guard<std::mutex> lk(g_rt.mu);
+  return (int) g_rt.engines.size();
+}
+// lazily: the first evaluation initialises one engine on the current device (mirrors the reference's lazy table load),
+// or on the devices RELXILL_B200_DEVICES names ("all" or a count)
+int ensure_runtime() {
+  if (num_engines() > 0) return 0;
+  int n = 1, first = -1;
+  if (const char *env = getenv("RELXILL_B200_DEVICES")) {
+    first = 0;
+    n = (std::string(env) == "all") ? 0 : std::max(1, atoi(env));
+  }
+  return runtime_init(nullptr, first, n);
+}
+
 }  // namespace
 
 struct relxill_b200_batch {
+  Engine *eng = nullptr;
   const ModelDef *m = nullptr;
   long n = 0;
   int n_flux = 0;
   int nz_max = 1;
   bool any_corr = false;
   bool any_limb = false;      // some vector uses a limb law: k_fine must keep the emission angles for k_line
+  int renorm3 = 0;            // RELXILL_RENORMALIZE as read when the parameters were interpreted
   std::vector<VPar> vps;
-  std::vector<int> status;
+  int *status = nullptr;      // [n] pinned: the status copy of a run is asynchronous
   VPar *d_vps = nullptr;
   double *d_energy = nullptr;
   size_t vps_bytes = 0, energy_bytes = 0;
   long launches = 0;
   long last_chunk0 = 0, last_chunk_n = 0;
+  long arena_c0 = 0;          // arena slot of the first vector of the last chunk (0 unless the batch keeps its state)
   double kt_ms[KF_COUNT] = {0};
   long kt_n[KF_COUNT] = {0};
   // state cache: identity, the parameters the arena rows were computed from, per-vector re-use flags of the last run
@@ -231,21 +359,21 @@ struct relxill_b200_batch {
 namespace {
 
 struct Timer {
-  Engine &E;
+  bool on;
   relxill_b200_batch *b;
   cudaStream_t st;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  Timer(Engine &E_, relxill_b200_batch *b_, cudaStream_t s) : E(E_), b(b_), st(s) {
-    if (E.profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+  Timer(bool on_, relxill_b200_batch *b_, cudaStream_t s) : on(on_), b(b_), st(s) {
+    if (on) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
   }
   ~Timer() {
     if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
   }
-  void begin() { if (E.profiling) cudaEventRecord(e0, st); }
-  void end(int fam, bool is_kernel = true) {
-    if (is_kernel) b->launches++;
+  void begin() { if (on) cudaEventRecord(e0, st); }
+  void end(int fam, int kernels = 1) {
+    b->launches += kernels;
     b->kt_n[fam]++;
-    if (E.profiling) {
+    if (on) {
       cudaEventRecord(e1, st);
       cudaEventSynchronize(e1);
       float ms = 0;
@@ -257,13 +385,18 @@ struct Timer {
 
 // Host-buffer calls overlap the device->host copy of the spectra with the kernels of the next piece of the
 // batch: pieces of `pipe_piece` vectors (a whole number of waves of the one-CTA-per-vector kernels), the odd
-// remainder first, so that only the copy of the last piece is exposed.
+// remainder first, so that only the copy of the last piece is exposed.  A pageable destination goes through the
+// engine's pinned staging buffer (cudaMemcpyAsync into pageable memory blocks the host until the copy is done, which
+// would serialise the pieces): the device->host copies land there and the host moves each piece on while the GPU works
+// on the next ones.
 struct PipeOut {
-  double *h_flux;
+  double *h_flux;       // the caller's array
+  double *h_stage;      // pinned staging (null: h_flux is pinned or registered memory, copy straight into it)
   cudaStream_t copy_stream;
 };
 
-int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st, const PipeOut *pipe = nullptr) {
+int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st, const CallCfg &cc, const PipeOut *pipe = nullptr) {
+  CK(cudaSetDevice(E.device));
   const ModelDef &m = *b->m;
   const DevTables &T = E.tables->dev();
   const int xtab = model_xtab(m);
@@ -271,25 +404,29 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
   const bool relxill = (m.type == T_RELXILL);
   const int ne_line = (m.type == T_LINE) ? b->n_flux : NCONV;
   const int nex_stride = (relxill || m.type == T_XILL) ? std::max(E.tables->xill_host(xtab).stride, E.tables->xill_host(xtab).xc_stride) : 1;
-  const int cgrid = (relxill && E.xill_conv_grid && E.tables->xill_host(xtab).has_conv_copy) ? 1 : 0;
+  const int cgrid = (relxill && cc.xill_conv_grid && E.tables->xill_host(xtab).has_conv_copy) ? 1 : 0;
   b->xill_conv_grid = cgrid;
   const int n_incl = relxill ? E.tables->xill_host(xtab).n_incl : 0;
   const bool xillver = (m.type == T_XILL);
   const bool nth = (relxill || xillver) && m.prim == PRIM_NTHCOMP;
-  // the Kompaneets work arrays take 1.4 MB per vector: smaller chunks for the Cp models
-  const long cap = std::min(b->n, nth ? std::min<long>(E.max_chunk, 2048) : E.max_chunk);
+  const long cap = std::min(b->n, cc.max_chunk);
+  // the previous run on this arena may still be in flight on another stream
+  if (E.arena_busy_set && st != E.arena_stream) CK(cudaStreamWaitEvent(st, E.arena_busy, 0));
   if (ensure_scratch(E, cap, b->nz_max, ne_line, nex_stride, nth)) return -2;
-  Scratch S = E.S;
+  const Scratch S0 = E.S;
   b->launches = 0;
   for (int k = 0; k < KF_COUNT; k++) { b->kt_ms[k] = 0; b->kt_n[k] = 0; }
-  Timer tm(E, b, st);
+  Timer tm(cc.profiling, b, st);
   const std::vector<double> &econv = E.tables->econv();
+  // A batch that fits the arena keeps one arena slot per vector, whatever pieces it is cut into: its state survives the
+  // run.  A larger batch streams through the arena chunk by chunk (every chunk starts at slot 0) and leaves no state.
+  const bool resident = b->n <= S0.cap;
   std::vector<long> piece_n;
   {
-    long piece = S.cap, last = 0;
-    if (pipe && b->n >= E.pipe_piece + E.pipe_last) {
-      piece = std::min(S.cap, E.pipe_piece);
-      last = std::min(E.pipe_last, piece);   // only the copy of the last piece is exposed: keep that piece short
+    long piece = S0.cap, last = 0;
+    if (pipe && b->n >= cc.pipe_piece + cc.pipe_last) {
+      piece = std::min(S0.cap, cc.pipe_piece);
+      last = std::min(cc.pipe_last, piece);   // only the copy of the last piece is exposed: keep that piece short
     }
     const long body = b->n - last;
     long first = body % piece;
@@ -298,10 +435,9 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
     if (last > 0) piece_n.push_back(last);
   }
   // ---- state cache: which vectors can keep the rows the arena still holds for them
-  const bool one_piece = piece_n.size() == 1;
   b->n_reuse_rel = b->n_reuse_all = 0;
-  S.reuse = nullptr;
-  if (E.cache_on && one_piece && b->state_valid && E.arena_owner == b->uid && b->d_reuse && !E.keep_intermediates &&
+  const unsigned char *d_reuse = nullptr;
+  if (cc.cache_on && resident && b->state_valid && E.arena_owner == b->uid && b->d_reuse && !cc.keep_intermediates &&
       (m.type == T_RELXILL || m.type == T_CONV || m.type == T_LINE)) {
     b->reuse.resize(b->n);
     long any = 0;
@@ -314,40 +450,52 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
     }
     if (any) {
       CK(cudaMemcpyAsync(b->d_reuse, b->reuse.data(), b->n, cudaMemcpyHostToDevice, st));
-      S.reuse = b->d_reuse;
+      CK(cudaStreamSynchronize(st));   // b->reuse is pageable: the copy has left it when the host goes on
+      d_reuse = b->d_reuse;
     }
   }
   b->state_valid = false;   // until this run has been enqueued completely
   E.arena_owner = 0;
   std::vector<cudaEvent_t> ev(pipe ? piece_n.size() : 0);
   for (auto &e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  auto copy_piece = [&](size_t k, long c0, long nc) {
+  std::vector<cudaEvent_t> ev_copied((pipe && pipe->h_stage) ? piece_n.size() : 0);
+  for (auto &e : ev_copied) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  std::vector<long> piece_c0(piece_n.size());
+  auto copy_piece = [&](size_t k) {
+    const long c0 = piece_c0[k], nc = piece_n[k];
+    double *dst = (pipe->h_stage ? pipe->h_stage : pipe->h_flux) + (size_t) c0 * b->n_flux;
     CK(cudaStreamWaitEvent(pipe->copy_stream, ev[k], 0));
-    CK(cudaMemcpyAsync(pipe->h_flux + (size_t) c0 * b->n_flux, d_flux + (size_t) c0 * b->n_flux,
-                       (size_t) nc * b->n_flux * sizeof(double), cudaMemcpyDeviceToHost, pipe->copy_stream));
+    CK(cudaMemcpyAsync(dst, d_flux + (size_t) c0 * b->n_flux, (size_t) nc * b->n_flux * sizeof(double), cudaMemcpyDeviceToHost,
+                       pipe->copy_stream));
+    if (pipe->h_stage) CK(cudaEventRecord(ev_copied[k], pipe->copy_stream));
     return 0;
   };
-  long c0 = 0, prev_c0 = 0;
+  long c0 = 0;
   for (size_t ip = 0; ip < piece_n.size(); c0 += piece_n[ip], ip++) {
     const long nc = piece_n[ip];
+    piece_c0[ip] = c0;
     if (pipe && ip > 0) {   // the previous piece's kernels are enqueued behind it: its copy overlaps this piece
-      if (copy_piece(ip - 1, prev_c0, piece_n[ip - 1])) return -2;
+      if (copy_piece(ip - 1)) return -2;
     }
     struct AtEnd {   // record the piece's completion event however the body is left
-      std::vector<cudaEvent_t> &ev; size_t ip; cudaStream_t st; bool on; long &prev, c0;
-      ~AtEnd() { if (on) cudaEventRecord(ev[ip], st); prev = c0; }
-    } at_end{ev, ip, st, pipe != nullptr, prev_c0, c0};
+      std::vector<cudaEvent_t> &ev; size_t ip; cudaStream_t st; bool on;
+      ~AtEnd() { if (on) cudaEventRecord(ev[ip], st); }
+    } at_end{ev, ip, st, pipe != nullptr};
+    const long slot0 = resident ? c0 : 0;
+    Scratch S = scratch_slice(S0, slot0, nth);
+    S.reuse = d_reuse ? d_reuse + c0 : nullptr;
     const VPar *vps = b->d_vps + c0;
     double *out = d_flux + (size_t) c0 * b->n_flux;
+    b->last_chunk0 = c0;
+    b->last_chunk_n = nc;
+    b->arena_c0 = slot0;
     if (xillver) {
       tm.begin(); launch_xillver(vps, T, S, nc, which, b->d_energy, b->n_flux, out, nex_stride, st); tm.end(KF_XILLVER);
       if (nth) {
         tm.begin(); launch_nth(vps, T, S, nc, st); tm.end(KF_NTH);
         tm.begin(); launch_xillver_prim_nth(vps, T, S, nc, b->d_energy, b->n_flux, out, st); tm.end(KF_PRIMNTH);
       }
-      CK(cudaMemcpyAsync(b->status.data() + c0, S.status, nc * sizeof(int), cudaMemcpyDeviceToHost, st));
-      b->last_chunk0 = c0;
-      b->last_chunk_n = nc;
+      CK(cudaMemcpyAsync(b->status + c0, S.status, nc * sizeof(int), cudaMemcpyDeviceToHost, st));
       continue;
     }
     tm.begin(); launch_syspar(vps, T, S, nc, 1, st); tm.end(KF_SYSPAR);
@@ -357,9 +505,8 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
       if (b->any_corr) { tm.begin(); launch_syspar(vps, T, S, nc, 2, st); tm.end(KF_SYSPAR); }
     }
     tm.begin();
-    launch_fine(vps, T, S, nc, relxill ? n_incl : 0, econv[0], econv[NCONV], (b->any_limb || E.keep_intermediates) ? 1 : 0, st);
-    tm.end(KF_FINE);
-    b->launches++;   // launch_fine is two kernels (k_rows, k_fine) timed as one family
+    launch_fine(vps, T, S, nc, relxill ? n_incl : 0, econv[0], econv[NCONV], (b->any_limb || cc.keep_intermediates) ? 1 : 0, st);
+    tm.end(KF_FINE, 2);   // two kernels (k_rows, k_fine) timed as one family
     if (relxill) {
       tm.begin(); launch_dist(vps, T, S, nc, n_incl, st); tm.end(KF_DIST);
     }
@@ -370,26 +517,37 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
       tm.begin(); launch_line(vps, T, S, nc, T.econv, NCONV, 0, relxill ? b->nz_max : 1, st); tm.end(KF_LINE);
       if (relxill) {
         tm.begin(); launch_xill(vps, T, S, nc, which, cgrid, st); tm.end(KF_XILL);
-        tm.begin(); launch_conv(vps, T, S, nc, b->d_energy, b->n_flux, out, E.d_total, which, 0, cgrid, st); tm.end(KF_CONV);
+        tm.begin(); launch_conv(vps, T, S, nc, b->d_energy, b->n_flux, out, S.total, which, 0, cgrid, b->renorm3, st); tm.end(KF_CONV);
         if (nth) {
-          tm.begin(); launch_prim_nth(vps, T, S, nc, E.d_total, b->d_energy, b->n_flux, out, st); tm.end(KF_PRIMNTH);
+          tm.begin(); launch_prim_nth(vps, T, S, nc, S.total, b->d_energy, b->n_flux, out, b->renorm3, st); tm.end(KF_PRIMNTH);
         }
       } else {
-        tm.begin(); launch_conv(vps, T, S, nc, b->d_energy, b->n_flux, out, nullptr, 0, 1, 0, st); tm.end(KF_CONV);
+        tm.begin(); launch_conv(vps, T, S, nc, b->d_energy, b->n_flux, out, nullptr, 0, 1, 0, 0, st); tm.end(KF_CONV);
       }
     }
-    CK(cudaMemcpyAsync(b->status.data() + c0, S.status, nc * sizeof(int), cudaMemcpyDeviceToHost, st));
-    b->last_chunk0 = c0;
-    b->last_chunk_n = nc;
+    CK(cudaMemcpyAsync(b->status + c0, S.status, nc * sizeof(int), cudaMemcpyDeviceToHost, st));
   }
+  CK(cudaEventRecord(E.arena_busy, st));
+  E.arena_busy_set = true;
+  E.arena_stream = st;
   if (pipe) {
-    if (copy_piece(piece_n.size() - 1, prev_c0, piece_n.back())) return -2;
-    CK(cudaStreamSynchronize(pipe->copy_stream));
-    CK(cudaStreamSynchronize(st));
+    int rc = 0;
+    if (copy_piece(piece_n.size() - 1)) return -2;
+    if (pipe->h_stage) {   // pageable destination: move every piece on as soon as it has landed in the staging buffer
+      for (size_t k = 0; k < piece_n.size(); k++) {
+        if (cudaEventSynchronize(ev_copied[k]) != cudaSuccess) { rc = -2; break; }
+        const size_t off = (size_t) piece_c0[k] * b->n_flux;
+        memcpy(pipe->h_flux + off, pipe->h_stage + off, (size_t) piece_n[k] * b->n_flux * sizeof(double));
+      }
+    }
+    if (cudaStreamSynchronize(pipe->copy_stream) != cudaSuccess) rc = -2;
+    if (cudaStreamSynchronize(st) != cudaSuccess) rc = -2;
     for (auto &e : ev) cudaEventDestroy(e);
+    for (auto &e : ev_copied) cudaEventDestroy(e);
+    if (rc) { set_err(std::string("pipelined run: ") + cudaGetErrorString(cudaGetLastError())); return rc; }
   }
   CK(cudaGetLastError());
-  if (one_piece && !xillver) {   // the arena now holds this batch's state
+  if (resident && !xillver) {   // the arena now holds this batch's state
     b->state_vps = b->vps;
     b->state_valid = true;
     E.arena_owner = b->uid;
@@ -397,20 +555,16 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
   return 0;
 }
 
-}  // namespace
-
-namespace {
-
 // host-side interpretation of the raw parameter vectors (spread over a few threads for large batches) and the
 // batch-level switches derived from it
-void interpret_all(Engine &E, relxill_b200_batch *b, const double *params) {
+void interpret_all(Engine &E, relxill_b200_batch *b, const double *params, const CallCfg &cc) {
   const ModelDef *m = b->m;
   const long n_vec = b->n;
   const std::vector<double> &sp = E.tables->rr_spins();
   const int nthr = (int) std::max<long>(1, std::min<long>({(long) std::thread::hardware_concurrency(), 16L, n_vec / 256}));
   auto work = [&](long lo, long hi) {
     for (long i = lo; i < hi; i++)
-      interpret_params(*m, params + (size_t) i * m->npar, E.cfg, sp.empty() ? nullptr : sp.data(), (int) sp.size(), b->vps[i]);
+      interpret_params(*m, params + (size_t) i * m->npar, cc.cfg, sp.empty() ? nullptr : sp.data(), (int) sp.size(), b->vps[i]);
   };
   if (nthr <= 1) {
     work(0, n_vec);
@@ -421,6 +575,7 @@ void interpret_all(Engine &E, relxill_b200_batch *b, const double *params) {
   }
   b->nz_max = 1;
   b->any_corr = b->any_limb = false;
+  b->renorm3 = cc.cfg.env_renorm_relxill;
   for (long i = 0; i < n_vec; i++) {
     if (b->vps[i].status == ST_OK) {
       b->nz_max = std::max(b->nz_max, b->vps[i].nz);
@@ -430,18 +585,198 @@ void interpret_all(Engine &E, relxill_b200_batch *b, const double *params) {
   }
 }
 
-void read_call_env(Engine &E) {   // read per call, like the reference's constantDiskDensity() (src/relutility.c:372-382)
-  const char *env = getenv("RELXILL_CONSTANT_DENSITY");
-  E.cfg.env_const_density = (env && (int) strtod(env, nullptr) == 1) ? 1 : 0;
-}
-
 void free_batch_locked(Engine &E, relxill_b200_batch *b) {
   if (!b) return;
+  cudaSetDevice(E.device);
+  wait_arena(E);   // nothing in flight reads the buffers that go back to the pool
   if (E.arena_owner == b->uid) E.arena_owner = 0;
-  pool_put(E, b->d_vps, b->vps_bytes);
-  pool_put(E, b->d_energy, b->energy_bytes);
-  pool_put(E, b->d_reuse, (size_t) b->n);
+  pool_put(E.pool, b->d_vps, b->vps_bytes, false);
+  pool_put(E.pool, b->d_energy, b->energy_bytes, false);
+  pool_put(E.pool, b->d_reuse, (size_t) b->n, false);
+  pool_put(E.pool_pinned, b->status, (size_t) b->n * sizeof(int), true);
   delete b;
+}
+
+relxill_b200_batch *prepare_on(Engine &E, const char *model, const double *energy, int n_flux, const double *params,
+                               long n_vec, const CallCfg &cc) {
+  std::lock_guard<std::mutex> lk(E.mu);
+  g_err.clear();
+  if (cudaSetDevice(E.device) != cudaSuccess) { set_err("cannot select the engine's device"); return nullptr; }
+  const ModelDef *m = model ? find_model(model) : nullptr;
+  if (!m) { set_err(std::string("unknown model ") + (model ? model : "(null)")); return nullptr; }
+  if (n_vec < 1 || n_flux < 1 || !energy || !params) { set_err("empty batch or energy grid"); return nullptr; }
+  if (m->type == T_LINE && n_flux > line_max_bins()) {
+    set_err("line models: energy grids above " + std::to_string(line_max_bins()) + " bins are not supported yet");
+    return nullptr;
+  }
+  // tables this flavour needs; returning radiation can be switched per vector -> load if the table exists
+  bool want_rr = (m->irrad == EMIS_LP) || cc.cfg.env_returnrad == 1;
+  std::string err = (m->type == T_XILL)
+                        ? E.tables->require_xill_only(model_xtab(*m))
+                        : E.tables->require(m->irrad == EMIS_LP, false, model_xtab(*m));
+  if (!err.empty()) { set_err(err); return nullptr; }
+  if (want_rr) {
+    err = E.tables->require(false, true, XT_NONE);
+    // missing table is only an error for the vectors that switch returning radiation on
+  }
+  auto *b = new relxill_b200_batch();
+  b->eng = &E;
+  b->m = m;
+  b->n = n_vec;
+  b->n_flux = n_flux;
+  b->vps.resize(n_vec);
+  {
+    std::lock_guard<std::mutex> lr(g_rt.mu);
+    b->uid = g_rt.next_uid++;
+  }
+  b->energy.assign(energy, energy + n_flux + 1);
+  interpret_all(E, b, params, cc);
+  b->vps_bytes = n_vec * sizeof(VPar);
+  b->energy_bytes = (n_flux + 1) * sizeof(double);
+  b->d_vps = (VPar *) pool_get(E.pool, b->vps_bytes, false);
+  b->d_energy = (double *) pool_get(E.pool, b->energy_bytes, false);
+  b->d_reuse = (unsigned char *) pool_get(E.pool, (size_t) n_vec, false);
+  b->status = (int *) pool_get(E.pool_pinned, (size_t) n_vec * sizeof(int), true);
+  if (!b->d_vps || !b->d_energy || !b->d_reuse || !b->status) {
+    set_err("out of device memory (batch)");
+    free_batch_locked(E, b);
+    return nullptr;
+  }
+  for (long i = 0; i < n_vec; i++) b->status[i] = b->vps[i].status;
+  if (cudaMemcpy(b->d_vps, b->vps.data(), n_vec * sizeof(VPar), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(b->d_energy, energy, (n_flux + 1) * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_err(std::string("upload of the batch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    free_batch_locked(E, b);
+    return nullptr;
+  }
+  return b;
+}
+
+int update_params_locked(Engine &E, relxill_b200_batch *b, const double *params, const CallCfg &cc) {
+  CK(cudaSetDevice(E.device));
+  wait_arena(E);   // the kernels of the last run read d_vps
+  interpret_all(E, b, params, cc);
+  CK(cudaMemcpy(b->d_vps, b->vps.data(), b->n * sizeof(VPar), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int update_energy_locked(Engine &E, relxill_b200_batch *b, const double *energy, int n_flux) {
+  CK(cudaSetDevice(E.device));
+  wait_arena(E);
+  if (b->m->type == T_LINE) {
+    if (n_flux > line_max_bins()) { set_err("line models: energy grid too long"); return -1; }
+    b->state_valid = false;   // the line models integrate on the caller's grid: nothing survives a new grid
+  }
+  const size_t bytes = (size_t) (n_flux + 1) * sizeof(double);
+  if (bytes > b->energy_bytes) {
+    double *d = (double *) pool_get(E.pool, bytes, false);
+    if (!d) { set_err("out of device memory (energy grid)"); return -2; }
+    pool_put(E.pool, b->d_energy, b->energy_bytes, false);
+    b->d_energy = d;
+    b->energy_bytes = bytes;
+  }
+  b->n_flux = n_flux;
+  b->energy.assign(energy, energy + n_flux + 1);
+  CK(cudaMemcpy(b->d_energy, energy, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// One device's share of a host-buffer call: params [n_vec][npar], flux [n_vec][n_flux] and status [n_vec] are host
+// arrays of this shard only.
+int eval_on_engine(Engine &E, const char *model, const double *energy, int n_flux, const double *params, long n_vec,
+                   double *flux, int *status, const CallCfg &cc) {
+  static const bool dbg = getenv("RELXILL_B200_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t0 = now();
+  auto fail = [&](int rc) {
+    if (flux && n_vec > 0 && n_flux > 0) memset(flux, 0, sizeof(double) * (size_t) n_vec * n_flux);
+    if (status) for (long i = 0; i < n_vec; i++) status[i] = ST_BAD_PARAM;
+    return rc;
+  };
+  // An XSPEC fit (or any caller that re-evaluates the same vectors with a few parameters changed) comes back with the
+  // same model and batch size: the batch of the previous call was kept, so that the vectors whose relativistic half
+  // or whole parameter set is unchanged re-use the state still resident in the arena (run_batch).
+  relxill_b200_batch *b = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(E.mu);
+    relxill_b200_batch *r = E.retained;
+    E.retained = nullptr;
+    if (r && cc.cache_on && r->m == find_model(model) && r->n == n_vec && n_flux >= 1 && energy && params) {
+      int rc = 0;
+      if (n_flux != r->n_flux || memcmp(energy, r->energy.data(), sizeof(double) * (size_t) (n_flux + 1)) != 0)
+        rc = update_energy_locked(E, r, energy, n_flux);
+      if (rc == 0) rc = update_params_locked(E, r, params, cc);
+      if (rc == 0) b = r; else free_batch_locked(E, r);
+    } else {
+      free_batch_locked(E, r);
+    }
+  }
+  if (!b) b = prepare_on(E, model, energy, n_flux, params, n_vec, cc);
+  const auto t1 = now();
+  if (!b) return fail(-1);
+  std::lock_guard<std::mutex> lk(E.mu);
+  if (cudaSetDevice(E.device) != cudaSuccess) { free_batch_locked(E, b); return fail(-2); }
+  const size_t need = (size_t) n_vec * n_flux;
+  if (E.d_io_cap < need) {
+    wait_arena(E);
+    if (E.d_io) cudaFree(E.d_io);
+    E.d_io = nullptr;
+    E.d_io_cap = 0;
+    if (cudaMalloc((void **) &E.d_io, need * sizeof(double)) != cudaSuccess) {
+      cudaGetLastError();
+      set_err("out of device memory (output staging)");
+      free_batch_locked(E, b);
+      return fail(-2);
+    }
+    E.d_io_cap = need;
+  }
+  // is the caller's array page-locked?  (cudaMemcpyAsync into pageable memory is synchronous: stage those)
+  bool pageable = true;
+  {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, flux) == cudaSuccess) pageable = (at.type == cudaMemoryTypeUnregistered);
+    else cudaGetLastError();
+  }
+  const bool staged = pageable && n_vec >= cc.pipe_piece + cc.pipe_last;   // small batches run in one piece: nothing to overlap
+  if (staged && E.h_io_cap < need) {
+    if (E.h_io) cudaFreeHost(E.h_io);
+    E.h_io = nullptr;
+    E.h_io_cap = 0;
+    if (cudaMallocHost((void **) &E.h_io, need * sizeof(double)) == cudaSuccess) E.h_io_cap = need;
+    else cudaGetLastError();   // no pinned memory to be had: fall back to the direct (serialising) copy
+  }
+  if (b->m->type == T_CONV) {
+    // convolution models: flux is the input spectrum; a non-positive total is rejected (src/LocalModel.cpp:84-86)
+    bool changed = false;
+    for (long i = 0; i < n_vec; i++) {
+      double s = 0.0;
+      for (int j = 0; j < n_flux; j++) s += flux[(size_t) i * n_flux + j];
+      if (s <= 0.0 && b->vps[i].status == ST_OK) { b->vps[i].status = ST_CONV_INPUT; changed = true; }
+    }
+    wait_arena(E);
+    cudaError_t e = cudaSuccess;
+    if (changed) e = cudaMemcpy(b->d_vps, b->vps.data(), n_vec * sizeof(VPar), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(E.d_io, flux, need * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      set_err(std::string("upload of the input spectra failed: ") + cudaGetErrorString(e));
+      free_batch_locked(E, b);
+      return fail(-2);
+    }
+  }
+  const auto t2 = now();
+  PipeOut pipe{flux, (staged && E.h_io_cap >= need) ? E.h_io : nullptr, E.stream_d};
+  int rc = run_batch(E, b, E.d_io, E.stream_c, cc, &pipe);   // kernels + pipelined D2H; returns with both streams drained
+  if (rc != 0) { cudaStreamSynchronize(E.stream_c); cudaStreamSynchronize(E.stream_d); }
+  const auto t3 = now();
+  if (status) for (long i = 0; i < n_vec; i++) status[i] = b->status[i];
+  if (rc == 0 && b->state_valid && cc.cache_on) E.retained = b;
+  else free_batch_locked(E, b);
+  if (rc != 0) return fail(rc);
+  if (dbg)
+    fprintf(stderr, "relxill_batch_eval[dev %d] timing: prepare %.2f ms, staging %.2f ms, run + D2H (pipelined%s) %.2f ms, tail %.2f ms\n",
+            E.device, ms(t0, t1), ms(t1, t2), pipe.h_stage ? ", pageable destination staged" : "", ms(t2, t3), ms(t3, now()));
+  return 0;
 }
 
 }  // namespace
@@ -451,32 +786,41 @@ extern "C" {
 
 const char *relxill_b200_last_error(void) { return g_err.c_str(); }
 
-int relxill_b200_init(const char *table_dir, int device) {
-  std::lock_guard<std::mutex> lk(g_eng.mu);
-  return engine_init(g_eng, table_dir, device);
-}
+int relxill_b200_init(const char *table_dir, int device) { return runtime_init(table_dir, device, 1); }
+
+int relxill_b200_init_devices(const char *table_dir, int n_devices) { return runtime_init(table_dir, 0, n_devices); }
+
+int relxill_b200_num_devices(void) { return num_engines(); }
 
 void relxill_b200_shutdown(void) {
-  std::lock_guard<std::mutex> lk(g_eng.mu);
-  free_scratch(g_eng);
-  if (g_eng.d_io) cudaFree(g_eng.d_io);
-  g_eng.d_io = nullptr;
-  g_eng.d_io_cap = 0;
-  free_batch_locked(g_eng, g_eng.retained);
-  g_eng.retained = nullptr;
-  for (auto &pr : g_eng.pool) cudaFree(pr.second);
-  g_eng.pool.clear();
-  delete g_eng.tables;
-  g_eng.tables = nullptr;
-  g_eng.inited = false;
+  std::lock_guard<std::mutex> lk(g_rt.mu);
+  for (auto &ep : g_rt.engines) {
+    Engine &E = *ep;
+    std::lock_guard<std::mutex> le(E.mu);
+    cudaSetDevice(E.device);
+    free_batch_locked(E, E.retained);
+    E.retained = nullptr;
+    free_scratch(E);
+    if (E.d_io) cudaFree(E.d_io);
+    if (E.h_io) cudaFreeHost(E.h_io);
+    for (auto &pr : E.pool) cudaFree(pr.second);
+    for (auto &pr : E.pool_pinned) cudaFreeHost(pr.second);
+    if (E.stream_c) cudaStreamDestroy(E.stream_c);
+    if (E.stream_d) cudaStreamDestroy(E.stream_d);
+    if (E.arena_busy) cudaEventDestroy(E.arena_busy);
+    delete E.tables;
+  }
+  g_rt.engines.clear();
 }
 
-void relxill_b200_set_num_zones(int n) { g_eng.cfg.env_num_zones = n; }
-void relxill_b200_set_profiling(int on) { g_eng.profiling = on != 0; }
-void relxill_b200_keep_intermediates(int on) { g_eng.keep_intermediates = on != 0; }
-void relxill_b200_set_cache(int on) { g_eng.cache_on = on != 0; }
-void relxill_b200_set_xill_grid(int conv_grid) { g_eng.xill_conv_grid = conv_grid != 0; }
-int relxill_b200_get_xill_grid(void) { return g_eng.xill_conv_grid ? 1 : 0; }
+// the global switches are taken under the runtime mutex: a call in flight on another thread sees either the old or the new value
+void relxill_b200_set_num_zones(int n) { std::lock_guard<std::mutex> lk(g_rt.mu); g_rt.cfg.override_num_zones = n > 0 ? n : 0; }
+void relxill_b200_set_profiling(int on) { std::lock_guard<std::mutex> lk(g_rt.mu); g_rt.profiling = on != 0; }
+void relxill_b200_keep_intermediates(int on) { std::lock_guard<std::mutex> lk(g_rt.mu); g_rt.keep_intermediates = on != 0; }
+void relxill_b200_set_cache(int on) { std::lock_guard<std::mutex> lk(g_rt.mu); g_rt.cache_on = on != 0; }
+void relxill_b200_set_xill_grid(int conv_grid) { std::lock_guard<std::mutex> lk(g_rt.mu); g_rt.xill_conv_grid = conv_grid != 0; }
+int relxill_b200_get_xill_grid(void) { std::lock_guard<std::mutex> lk(g_rt.mu); return g_rt.xill_conv_grid ? 1 : 0; }
+void relxill_b200_set_sharding(int interleave) { std::lock_guard<std::mutex> lk(g_rt.mu); g_rt.interleave = interleave != 0; }
 void relxill_b200_set_xill_generic(int on) { xill_force_generic(on); }
 
 int relxill_b200_num_params(const char *model) {
@@ -490,90 +834,41 @@ int relxill_b200_default_params(const char *model, double *out) {
   return m->npar;
 }
 
+relxill_b200_batch *relxill_b200_prepare_on(int device_index, const char *model, const double *energy, int n_flux,
+                                            const double *params, long n_vec) {
+  g_err.clear();
+  if (ensure_runtime()) return nullptr;
+  Engine *E = engine_at(device_index);
+  if (!E) { set_err("prepare: no engine with index " + std::to_string(device_index)); return nullptr; }
+  const CallCfg cc = call_cfg(true);
+  return prepare_on(*E, model, energy, n_flux, params, n_vec, cc);
+}
+
 relxill_b200_batch *relxill_b200_prepare(const char *model, const double *energy, int n_flux, const double *params,
                                          long n_vec) {
-  Engine &E = g_eng;
-  std::lock_guard<std::mutex> lk(E.mu);
-  g_err.clear();
-  if (engine_init(E, nullptr, -1)) return nullptr;
-  const ModelDef *m = find_model(model);
-  if (!m) { set_err(std::string("unknown model ") + model); return nullptr; }
-  if (n_vec < 1 || n_flux < 1) { set_err("empty batch or energy grid"); return nullptr; }
-  if (m->type == T_LINE && n_flux > line_max_bins()) {
-    set_err("line models: energy grids above " + std::to_string(line_max_bins()) + " bins are not supported yet");
-    return nullptr;
-  }
-  // tables this flavour needs; returning radiation can be switched per vector -> load if the table exists
-  read_call_env(E);
-  bool want_rr = (m->irrad == EMIS_LP) || E.cfg.env_returnrad == 1;
-  std::string err = (m->type == T_XILL)
-                        ? E.tables->require_xill_only(model_xtab(*m))
-                        : E.tables->require(m->irrad == EMIS_LP, false, model_xtab(*m));
-  if (!err.empty()) { set_err(err); return nullptr; }
-  if (want_rr) {
-    err = E.tables->require(false, true, XT_NONE);
-    // missing table is only an error for the vectors that switch returning radiation on
-  }
-  auto *b = new relxill_b200_batch();
-  b->m = m;
-  b->n = n_vec;
-  b->n_flux = n_flux;
-  b->vps.resize(n_vec);
-  b->status.assign(n_vec, 0);
-  b->uid = E.next_uid++;
-  b->energy.assign(energy, energy + n_flux + 1);
-  interpret_all(E, b, params);
-  b->vps_bytes = n_vec * sizeof(VPar);
-  b->energy_bytes = (n_flux + 1) * sizeof(double);
-  b->d_vps = (VPar *) pool_get(E, b->vps_bytes);
-  b->d_energy = (double *) pool_get(E, b->energy_bytes);
-  b->d_reuse = (unsigned char *) pool_get(E, (size_t) n_vec);
-  if (!b->d_vps || !b->d_energy || !b->d_reuse) {
-    set_err("out of device memory (batch)");
-    free_batch_locked(E, b);
-    return nullptr;
-  }
-  cudaMemcpy(b->d_vps, b->vps.data(), n_vec * sizeof(VPar), cudaMemcpyHostToDevice);
-  cudaMemcpy(b->d_energy, energy, (n_flux + 1) * sizeof(double), cudaMemcpyHostToDevice);
-  return b;
+  return relxill_b200_prepare_on(0, model, energy, n_flux, params, n_vec);
 }
 
 void relxill_b200_free_batch(relxill_b200_batch *b) {
   if (!b) return;
-  std::lock_guard<std::mutex> lk(g_eng.mu);
-  free_batch_locked(g_eng, b);
+  Engine &E = *b->eng;
+  std::lock_guard<std::mutex> lk(E.mu);
+  free_batch_locked(E, b);
 }
 
 int relxill_b200_update_params(relxill_b200_batch *b, const double *params) {
-  Engine &E = g_eng;
+  if (!b || !params) { set_err("update_params: null argument"); return -1; }
+  const CallCfg cc = call_cfg(true);
+  Engine &E = *b->eng;
   std::lock_guard<std::mutex> lk(E.mu);
-  if (!b || !E.inited || !params) { set_err("update_params: library not initialised or null argument"); return -1; }
-  read_call_env(E);
-  interpret_all(E, b, params);
-  CK(cudaMemcpy(b->d_vps, b->vps.data(), b->n * sizeof(VPar), cudaMemcpyHostToDevice));
-  return 0;
+  return update_params_locked(E, b, params, cc);
 }
 
 int relxill_b200_update_energy(relxill_b200_batch *b, const double *energy, int n_flux) {
-  Engine &E = g_eng;
+  if (!b || !energy || n_flux < 1) { set_err("update_energy: bad argument"); return -1; }
+  Engine &E = *b->eng;
   std::lock_guard<std::mutex> lk(E.mu);
-  if (!b || !E.inited || !energy || n_flux < 1) { set_err("update_energy: library not initialised or bad argument"); return -1; }
-  if (b->m->type == T_LINE) {
-    if (n_flux > line_max_bins()) { set_err("line models: energy grid too long"); return -1; }
-    b->state_valid = false;   // the line models integrate on the caller's grid: nothing survives a new grid
-  }
-  const size_t bytes = (size_t) (n_flux + 1) * sizeof(double);
-  if (bytes > b->energy_bytes) {
-    double *d = (double *) pool_get(E, bytes);
-    if (!d) { set_err("out of device memory (energy grid)"); return -2; }
-    pool_put(E, b->d_energy, b->energy_bytes);
-    b->d_energy = d;
-    b->energy_bytes = bytes;
-  }
-  b->n_flux = n_flux;
-  b->energy.assign(energy, energy + n_flux + 1);
-  CK(cudaMemcpy(b->d_energy, energy, bytes, cudaMemcpyHostToDevice));
-  return 0;
+  return update_energy_locked(E, b, energy, n_flux);
 }
 
 int relxill_b200_reuse_counts(relxill_b200_batch *b, long *out3) {
@@ -584,16 +879,35 @@ int relxill_b200_reuse_counts(relxill_b200_batch *b, long *out3) {
   return 0;
 }
 
+int relxill_b200_last_eval_reuse(long *out3) {
+  if (!out3) return -1;
+  out3[0] = out3[1] = out3[2] = 0;
+  std::lock_guard<std::mutex> lk(g_rt.mu);
+  for (auto &ep : g_rt.engines) {
+    std::lock_guard<std::mutex> le(ep->mu);
+    const relxill_b200_batch *r = ep->retained;
+    if (!r) continue;
+    out3[0] += r->n - r->n_reuse_rel - r->n_reuse_all;
+    out3[1] += r->n_reuse_rel;
+    out3[2] += r->n_reuse_all;
+  }
+  return 0;
+}
+
 int relxill_b200_run(relxill_b200_batch *b, double *d_flux, void *stream) {
-  Engine &E = g_eng;
+  if (!b) { set_err("run: null batch"); return -1; }
+  const CallCfg cc = call_cfg(false);
+  Engine &E = *b->eng;
   std::lock_guard<std::mutex> lk(E.mu);
-  if (!b || !E.inited) { set_err("run: library not initialised or null batch"); return -1; }
-  return run_batch(E, b, d_flux, (cudaStream_t) stream);
+  return run_batch(E, b, d_flux, (cudaStream_t) stream, cc);
 }
 
 int relxill_b200_batch_status(relxill_b200_batch *b, int *status) {
   if (!b) return -1;
-  cudaDeviceSynchronize();
+  Engine &E = *b->eng;
+  std::lock_guard<std::mutex> lk(E.mu);
+  cudaSetDevice(E.device);
+  wait_arena(E);
   for (long i = 0; i < b->n; i++) status[i] = b->status[i];
   return 0;
 }
@@ -618,7 +932,7 @@ int relxill_batch_eval_device(const char *model, const double *energy, int n_flu
   relxill_b200_batch *b = relxill_b200_prepare(model, energy, n_flux, params, n_vec);
   if (!b) return -1;
   int rc = relxill_b200_run(b, d_flux, stream);
-  cudaStreamSynchronize((cudaStream_t) stream);
+  if (cudaStreamSynchronize((cudaStream_t) stream) != cudaSuccess && rc == 0) rc = -2;
   if (status) for (long i = 0; i < n_vec; i++) status[i] = b->status[i];
   relxill_b200_free_batch(b);
   return rc;
@@ -626,100 +940,82 @@ int relxill_batch_eval_device(const char *model, const double *energy, int n_flu
 
 int relxill_batch_eval(const char *model, const double *energy, int n_flux, const double *params, long n_vec,
                        double *flux, int *status) {
-  static const bool dbg = getenv("RELXILL_B200_TIMING") != nullptr;
-  auto now = [] { return std::chrono::steady_clock::now(); };
-  auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-  const auto t0 = now();
-  // An XSPEC fit (or any caller that re-evaluates the same vectors with a few parameters changed) comes back with the
-  // same model and batch size: the batch of the previous call was kept, so that the vectors whose relativistic half
-  // or whole parameter set is unchanged re-use the state still resident in the arena (run_batch).
-  relxill_b200_batch *b = nullptr;
-  {
-    std::lock_guard<std::mutex> lk(g_eng.mu);
-    relxill_b200_batch *r = g_eng.retained;
-    g_eng.retained = nullptr;
-    if (r && g_eng.cache_on && g_eng.inited && r->m == find_model(model) && r->n == n_vec && n_flux >= 1 && energy && params) b = r;
-    else free_batch_locked(g_eng, r);
-  }
-  if (b) {
-    int rc = 0;
-    if (n_flux != b->n_flux || memcmp(energy, b->energy.data(), sizeof(double) * (size_t) (n_flux + 1)) != 0)
-      rc = relxill_b200_update_energy(b, energy, n_flux);
-    if (rc == 0) rc = relxill_b200_update_params(b, params);
-    if (rc != 0) { relxill_b200_free_batch(b); b = nullptr; }
-  }
-  if (!b) b = relxill_b200_prepare(model, energy, n_flux, params, n_vec);
-  const auto t1 = now();
-  if (!b) {
+  g_err.clear();
+  auto fail = [&](int rc) {
     if (flux && n_vec > 0 && n_flux > 0) memset(flux, 0, sizeof(double) * (size_t) n_vec * n_flux);
     if (status) for (long i = 0; i < n_vec; i++) status[i] = ST_BAD_PARAM;
-    return -1;
-  }
-  Engine &E = g_eng;
-  const size_t need = (size_t) n_vec * n_flux;
-  bool io_ok = true;
+    return rc;
+  };
+  if (ensure_runtime()) return fail(-1);
+  const CallCfg cc = call_cfg(true);
+  const ModelDef *m = model ? find_model(model) : nullptr;
+  if (!m) { set_err(std::string("unknown model ") + (model ? model : "(null)")); return fail(-1); }
+  if (n_vec < 1 || n_flux < 1 || !energy || !params || !flux) { set_err("empty batch or energy grid"); return fail(-1); }
+  const int ndev = num_engines();
+  // ---- one device, or a batch too small to be worth sharding
+  if (ndev == 1 || n_vec < 2L * ndev) return eval_on_engine(*engine_at(0), model, energy, n_flux, params, n_vec, flux, status, cc);
+  // ---- the batch sharded over the devices of this process: contiguous blocks (each device writes its rows of the
+  // caller's arrays directly) or, for structured batches such as parameter-grid sweeps whose cost varies along the
+  // batch, round-robin rows.  No collective: the vectors are independent.
+  int interleave;
   {
-    std::lock_guard<std::mutex> lk(E.mu);
-    if (E.d_io_cap < need) {
-      if (E.d_io) cudaFree(E.d_io);
-      E.d_io = nullptr;
-      E.d_io_cap = 0;
-      if (cudaMalloc((void **) &E.d_io, need * sizeof(double)) != cudaSuccess) io_ok = false;
-      else E.d_io_cap = need;
-    }
+    std::lock_guard<std::mutex> lk(g_rt.mu);
+    interleave = g_rt.interleave;
   }
-  if (!io_ok) {
-    set_err("out of device memory (output staging)");
-    relxill_b200_free_batch(b);
-    return -2;
+  const int npar = m->npar;
+  std::vector<int> rcs(ndev, 0);
+  std::vector<std::string> errs(ndev);
+  std::vector<std::thread> th;
+  for (int d = 0; d < ndev; d++) {
+    th.emplace_back([&, d] {
+      Engine &E = *engine_at(d);
+      if (!interleave) {
+        const long base = n_vec / ndev, rem = n_vec % ndev;
+        const long lo = d * base + std::min<long>(d, rem), cnt = base + (d < rem ? 1 : 0);
+        rcs[d] = eval_on_engine(E, model, energy, n_flux, params + (size_t) lo * npar, cnt, flux + (size_t) lo * n_flux,
+                                status ? status + lo : nullptr, cc);
+      } else {
+        const long cnt = (n_vec - d + ndev - 1) / ndev;
+        std::vector<double> p((size_t) cnt * npar), f((size_t) cnt * n_flux);
+        std::vector<int> s(cnt);
+        for (long k = 0; k < cnt; k++) {
+          const long row = d + k * ndev;
+          memcpy(&p[(size_t) k * npar], params + (size_t) row * npar, npar * sizeof(double));
+          if (m->type == T_CONV) memcpy(&f[(size_t) k * n_flux], flux + (size_t) row * n_flux, n_flux * sizeof(double));
+        }
+        rcs[d] = eval_on_engine(E, model, energy, n_flux, p.data(), cnt, f.data(), s.data(), cc);
+        for (long k = 0; k < cnt; k++) {
+          const long row = d + k * ndev;
+          memcpy(flux + (size_t) row * n_flux, &f[(size_t) k * n_flux], n_flux * sizeof(double));
+          if (status) status[row] = s[k];
+        }
+      }
+      errs[d] = g_err;
+    });
   }
-  if (b->m->type == T_CONV) {
-    // convolution models: flux is the input spectrum; a non-positive total is rejected (src/LocalModel.cpp:84-86)
-    for (long i = 0; i < n_vec; i++) {
-      double s = 0.0;
-      for (int j = 0; j < n_flux; j++) s += flux[(size_t) i * n_flux + j];
-      if (s <= 0.0 && b->vps[i].status == ST_OK) b->vps[i].status = ST_CONV_INPUT;
-    }
-    cudaMemcpy(b->d_vps, b->vps.data(), n_vec * sizeof(VPar), cudaMemcpyHostToDevice);
-    cudaMemcpy(E.d_io, flux, need * sizeof(double), cudaMemcpyHostToDevice);
-  }
-  const auto t2 = now();
-  int rc;
-  {
-    std::lock_guard<std::mutex> lk(E.mu);
-    PipeOut pipe{flux, E.stream_d};
-    rc = run_batch(E, b, E.d_io, E.stream_c, &pipe);   // kernels + pipelined D2H; returns with both streams drained
-    if (rc != 0) { cudaStreamSynchronize(E.stream_c); cudaStreamSynchronize(E.stream_d); }
-  }
-  const auto t3 = now();
-  const auto t4 = now();
-  if (status) for (long i = 0; i < n_vec; i++) status[i] = b->status[i];
-  if (rc == 0 && b->state_valid && E.cache_on) {
-    std::lock_guard<std::mutex> lk(E.mu);
-    E.retained = b;
-  } else {
-    relxill_b200_free_batch(b);
-  }
-  if (dbg)
-    fprintf(stderr, "relxill_batch_eval timing: prepare %.2f ms, staging %.2f ms, run + D2H (pipelined) %.2f ms (+%.2f), free %.2f ms\n",
-            ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, now()));
-  return rc;
+  for (auto &x : th) x.join();
+  for (int d = 0; d < ndev; d++)
+    if (rcs[d] != 0) { g_err = errs[d]; return rcs[d]; }
+  return 0;
 }
 
 int relxill_b200_algorithmic_bytes(relxill_b200_batch *b, double *out8) {
   double *out4 = out8;
-  Engine &E = g_eng;
-  if (!b || !E.inited) return -1;
+  if (!b) return -1;
+  Engine &E = *b->eng;
+  std::lock_guard<std::mutex> lk(E.mu);
+  cudaSetDevice(E.device);
   cudaDeviceSynchronize();
   const ModelDef &m = *b->m;
   const long nc = b->last_chunk_n;
+  const Scratch S = scratch_slice(E.S, b->arena_c0, false);
   double sumU = 0, bound = 0;
   double xbytes = 0;
   if (m.type == T_RELXILL && nc > 0) {
     const XillHost &xh = E.tables->xill_host(model_xtab(m));
     const int ncorn = (xh.npar == 6) ? 32 : 16;
     std::vector<int> rows((size_t) nc * NZMAX * 32);
-    cudaMemcpy(rows.data(), E.S.xrow, rows.size() * sizeof(int), cudaMemcpyDeviceToHost);
+    if (cudaMemcpy(rows.data(), S.xrow, rows.size() * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
     const double row_bytes = (double) xh.n_incl * xh.n_ener * 4.0;
     for (long i = 0; i < nc; i++) {
       const VPar &vp = b->vps[b->last_chunk0 + i];
@@ -750,7 +1046,7 @@ int relxill_b200_algorithmic_bytes(relxill_b200_batch *b, double *out8) {
   double prof = 0;
   if (nc > 0 && (m.type == T_RELXILL || m.type == T_LINE || m.type == T_CONV)) {
     std::vector<int> zr((size_t) nc * NZMAX * 2);
-    cudaMemcpy(zr.data(), E.S.zrange, zr.size() * sizeof(int), cudaMemcpyDeviceToHost);
+    if (cudaMemcpy(zr.data(), S.zrange, zr.size() * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
     for (long i = 0; i < nc; i++) {
       const VPar &vp = b->vps[b->last_chunk0 + i];
       if (b->status[b->last_chunk0 + i] != ST_OK) continue;
@@ -771,12 +1067,14 @@ int relxill_b200_algorithmic_bytes(relxill_b200_batch *b, double *out8) {
 }
 
 int relxill_b200_probe(relxill_b200_batch *b, long iv, const char *what, double *out, long max_len) {
-  Engine &E = g_eng;
-  if (!b || !E.inited) return -1;
+  if (!b) return -1;
+  Engine &E = *b->eng;
+  std::lock_guard<std::mutex> lk(E.mu);
+  cudaSetDevice(E.device);
   cudaDeviceSynchronize();
   if (iv < b->last_chunk0 || iv >= b->last_chunk0 + b->last_chunk_n) { set_err("probe: vector not in the last chunk"); return -1; }
   const size_t v = (size_t) (iv - b->last_chunk0);
-  const Scratch &S = E.S;
+  const Scratch S = scratch_slice(E.S, b->arena_c0, false);
   const VPar &vp = b->vps[iv];
   const std::string w = what;
   const double *src = nullptr;
@@ -798,7 +1096,7 @@ int relxill_b200_probe(relxill_b200_batch *b, long iv, const char *what, double 
   else if (w == "normch") { src = S.normch + v * NZMAX; n = vp.nz; }
   else if (w == "corr_flux") { src = S.corr_flux + v * NZMAX; n = vp.nz; }
   else if (w == "corr_gshift") { src = S.corr_gshift + v * NZMAX; n = vp.nz; }
-  else if (w == "total") { src = E.d_total + v * NCONV; n = NCONV; }
+  else if (w == "total") { src = S.total + v * NCONV; n = NCONV; }
   else if (w == "xill_ener") {   // bin edges of the xillver table of this model
     const std::vector<double> &xe = E.tables->xill_host(model_xtab(*b->m)).ener;
     n = xe.size();
@@ -812,8 +1110,8 @@ int relxill_b200_probe(relxill_b200_batch *b, long iv, const char *what, double 
     if ((long) nz * NCONV > max_len) return -1;
     for (long i = 0; i < (long) nz * NCONV; i++) out[i] = 0.0;
     for (int z = 0; z < nz; z++)
-      cudaMemcpy(out + (size_t) z * NCONV + xh.xc_first, S.xillz + (v * S.nz_cap + z) * xh.xc_stride,
-                 xh.xc_n * sizeof(double), cudaMemcpyDeviceToHost);
+      if (cudaMemcpy(out + (size_t) z * NCONV + xh.xc_first, S.xillz + (v * S.nz_cap + z) * xh.xc_stride,
+                     xh.xc_n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
     return nz * NCONV;
   } else if (w == "zone") {
     n = vp.nz + 1;
@@ -831,10 +1129,10 @@ int relxill_b200_probe(relxill_b200_batch *b, long iv, const char *what, double 
       const double *p = (w == "relflux") ? S.relflux + (v * S.nz_cap + z) * S.ne_line_cap
                         : (w == "xill")  ? S.xillz + (v * S.nz_cap + z) * E.tables->xill_host(model_xtab(*b->m)).stride
                                          : S.dist + (v * NZMAX + z) * MAX_INCL;
-      cudaMemcpy(out + z * len, p, len * sizeof(double), cudaMemcpyDeviceToHost);
+      if (cudaMemcpy(out + z * len, p, len * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
       if (w == "relflux") {  // rows are only written inside the zone's bin range
         int rg[2];
-        cudaMemcpy(rg, S.zrange + (v * NZMAX + z) * 2, sizeof(rg), cudaMemcpyDeviceToHost);
+        if (cudaMemcpy(rg, S.zrange + (v * NZMAX + z) * 2, sizeof(rg), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
         for (long i = 0; i < (long) len; i++) if (i < rg[0] || i > rg[1]) out[z * len + i] = 0.0;
       }
     }
@@ -844,21 +1142,21 @@ int relxill_b200_probe(relxill_b200_batch *b, long iv, const char *what, double 
     return -1;
   }
   if ((long) n > max_len) return -1;
-  cudaMemcpy(out, src, n * sizeof(double), cudaMemcpyDeviceToHost);
+  if (cudaMemcpy(out, src, n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
   return (int) n;
 }
 
 // ---------------------------------------------------------------- XSPEC local-model entry points
+// The reference prints its error and leaves flux unspecified when an evaluation fails (src/LocalModel.cpp:149-158); here
+// flux is zeroed and EVERY failed call says so on stderr (a fit that silently received zeros would converge on nonsense).
 static void lmod_call(const char *name, const double *energy, int Nflux, const double *parameter, double *flux) {
-  static bool warned = false;
   int st = 0;
   const int rc = relxill_batch_eval(name, energy, Nflux, parameter, 1, flux, &st);
   if (rc != 0 || st != 0) {
     for (int i = 0; i < Nflux; i++) flux[i] = 0.0;
-    if (!warned) {
-      fprintf(stderr, " *** relxill_b200: evaluation of %s failed (rc=%d, status=%d); returning zeros\n", name, rc, st);
-      warned = true;
-    }
+    const std::string why = rc != 0 ? g_err : (st == ST_BAD_PARAM ? std::string("parameters outside the allowed range")
+                                                                  : "status " + std::to_string(st));
+    fprintf(stderr, " *** relxill_b200: evaluation of %s failed (%s); returning zeros\n", name, why.c_str());
   }
 }
 

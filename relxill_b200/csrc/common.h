@@ -102,6 +102,7 @@ struct DevTables {
   const double *conv_cf;    // [NCONV] E_mid / dE
   int conv_b0, conv_b1;     // the normalisation band as a bin interval: 0.01 <= E_lo and E_hi < 1000 for b0 <= i <= b1
   int conv_i1kev;
+  int conv_i3kev;           // convolution bin holding 3 keV (RELXILL_RENORMALIZE, src/Relxill.cpp:249-259)
   const double *ecoarse;    // [NCOARSE+1]
   const unsigned char *coarse_m1, *coarse_m2;  // masks of the two band conditions on the coarse grid
   const double *gstar, *d_gstar;  // [NG]
@@ -114,45 +115,54 @@ struct DevTables {
   double nth_xmin, nth_deltal;
 };
 
-// per-chunk device scratch (struct of arrays, vector-major)
+// per-chunk device scratch (struct of arrays, vector-major).  Every array is listed once in SCRATCH_FIELDS with its
+// element type and the number of elements per parameter vector (nzc / nec / nxs = the zone, line-grid and xillver-row
+// capacities of the arena): api.cu allocates from the list and offsets from it when a piece of a batch works on its own
+// slice of the arena, so the two cannot drift apart.
+//   X(type, name, elements per vector)            NTH_X: allocated only for the nthcomp (Cp) models
+#define SCRATCH_FIELDS(X, NTH_X)                                                                                          \
+  X(double, re, NR) X(double, gmin, NR) X(double, gmax, NR) X(double, emis, NR)     /* fine radial grid quantities */     \
+  X(double, del_emit, NR) X(double, del_inc, NR) X(double, fr, NR)                                                        \
+  X(int, it, NR) X(int, izone, NR)                                                                                        \
+  X(int, zfirst, NZMAX + 1)        /* first fine-grid index with zone < z */                                              \
+  X(int, brk_i, 2)                 /* rel-table bracket (spin, mu0) */                                                    \
+  X(double, brk_f, 2)              /* its interpolation factors */                                                        \
+  X(double, glim, 2)               /* min gmin / max gmax over radii */                                                   \
+  X(double, reflfrac, 8)                                                                                                  \
+  X(double, trff, (size_t) NR * NG * 2) X(double, cosne, (size_t) NR * NG * 2)      /* [NR][NG][2] */                     \
+  X(double, relrow, (size_t) REL_NRT * NG * 4)   /* table rows interpolated in (a, mu0): trff1,2, cosne1,2 */             \
+  X(double, eshift, NZMAX) X(double, zlxi, NZMAX) X(double, zdens, NZMAX) X(double, zect, NZMAX)                          \
+  X(double, normch, NZMAX) X(double, corr_flux, NZMAX) X(double, corr_gshift, NZMAX)                                      \
+  X(double, nsrc, 1)               /* source normalisation factor */                                                      \
+  X(int, xrow, NZMAX * 32)         /* node index of each corner */                                                        \
+  X(double, xw, NZMAX * 32)        /* corner weights */                                                                   \
+  X(int, xkey, NZMAX * 32)         /* rest-corner node offset per (zone, slot) */                                         \
+  X(int, xga_off, 4)               /* node offsets of the (Gamma, A_Fe) corners */                                        \
+  X(double, xga_w, 4)              /* their weights */                                                                    \
+  X(double, xwsort, NZMAX * 32)    /* weights in xkey order */                                                            \
+  X(int, xn, 1)                    /* number of rest corners per zone */                                                  \
+  X(double, relflux, (size_t) nzc * nec)   /* [nz_cap][ne_line_cap] (valid inside zrange only) */                         \
+  X(int, zrange, NZMAX * 2)        /* first/last bin written per zone (-1: none) */                                       \
+  X(double, dist, NZMAX * MAX_INCL)                                                                                       \
+  X(double, distpart, NR * 10)     /* per-radius parts of dist (k_fine -> k_dist) */                                      \
+  X(double, xillz, (size_t) nzc * nxs)     /* zone spectra: rows of XillDev::xc_stride (convolution grid) or ::stride */  \
+  X(int, status, 1)                                                                                                       \
+  X(double, total, NCONV)          /* convolution-grid spectrum of the vector (state cache, probes) */                    \
+  NTH_X(double, nth_gam, (size_t) NTH_MAX * NTH_SOL) NTH_X(double, nth_g, (size_t) NTH_MAX * NTH_SOL)                     \
+  NTH_X(double, nth_spt, (size_t) NTH_MAX * NTH_SOL) NTH_X(int, nth_jmax, NTH_SOL)
+
 struct Scratch {
   long cap;          // vectors
   int nz_cap;        // zones per vector allocated
   int ne_line_cap;   // bins of the line-profile grid allocated
   int nex_stride;    // xillver row stride
-  double *re, *gmin, *gmax, *emis, *del_emit, *del_inc, *fr;  // [cap][NR]
-  int *it, *izone;                                            // [cap][NR]
-  int *zfirst;                                                // [cap][NZMAX+1] first fine-grid index with zone < z
-  int *brk_i;                                                 // [cap][2] rel-table bracket (spin, mu0)
-  double *brk_f;                                              // [cap][2] its interpolation factors
-  double *glim;                                               // [cap][2] min gmin / max gmax over radii
-  double *reflfrac;                                           // [cap][8]
-  double *trff, *cosne;                                       // [cap][NR][NG][2]
-  double *relrow;                                             // [cap][REL_NRT][NG][4] table rows interpolated in (a, mu0): trff1,2, cosne1,2
-  double *eshift, *zlxi, *zdens, *zect, *normch, *corr_flux, *corr_gshift;  // [cap][NZMAX]
-  double *nsrc;                                               // [cap] source normalisation factor
-  int *xrow;                                                  // [cap][NZMAX][32] node index of each corner
-  double *xw;                                                 // [cap][NZMAX][32] corner weights
-  int *xkey;                                                  // [cap][NZMAX*32] (rest-corner node offset << 6 | zone), sorted
-  int *xga_off;                                               // [cap][4] node offsets of the (Gamma, A_Fe) corners
-  double *xga_w;                                              // [cap][4] their weights
-  double *xwsort;                                             // [cap][NZMAX*32] weights in xkey order
-  int *xn;                                                    // [cap] number of (zone, corner) pairs
-  double *relflux;                                            // [cap][nz_cap][ne_line_cap] (valid inside zrange only)
-  int *zrange;                                                // [cap][NZMAX][2] first/last bin written per zone (-1: none)
-  double *dist;                                               // [cap][NZMAX][MAX_INCL]
-  double *distpart;                                           // [cap][NR][10] per-radius parts of dist (k_fine -> k_dist)
-  double *xillz;                                              // [cap][nz_cap][row]: zone spectra, rows of XillDev::xc_stride values on the
-                                                              // convolution grid (or of XillDev::stride on the table grid, see api.cu)
-  int *status;                                                // [cap]
+#define RX_DECL(type, name, count) type *name;
+  SCRATCH_FIELDS(RX_DECL, RX_DECL)
+#undef RX_DECL
   // Re-use of the previous run's device-resident state (api.cu: the arena still holds this batch): per vector,
   // REUSE_REL = the relativistic half (k_syspar, k_fine, k_dist, k_line outputs) is still valid, REUSE_ALL = the
   // whole convolution-grid spectrum is.  Null when nothing can be re-used.
   const unsigned char *reuse;                                 // [cap]
-  // nthcomp (allocated only for Cp models): Kompaneets work arrays and solutions, [cap][NTH_MAX][NTH_SOL]
-  // with the solve index fastest (coalesced across the threads of a vector's block)
-  double *nth_gam, *nth_g, *nth_spt;
-  int *nth_jmax;                                              // [cap][NTH_SOL]
 };
 
 }  // namespace rx

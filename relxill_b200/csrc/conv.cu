@@ -190,6 +190,7 @@ struct ConvArgs {
   const double2 *rb_dd;
   int xstride;            // row stride of the zone spectra
   int xc_first, xc_n;     // CG: the zone spectra are on the convolution grid, bins [xc_first, xc_first + xc_n) (xill.cu)
+  int renorm3;            // RELXILL_RENORMALIZE=1: scale the spectrum to 1 cts/s/keV/cm2 at 3 keV before the final rebin
 };
 
 // two CTAs per SM (64 registers): with one CTA and 128 registers nothing spills, but 16 warps hide too little
@@ -471,12 +472,17 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
   }
   __syncthreads();
   // rebin to the caller's grid (shifted by 1+z), src/Relxill.cpp:261-278
+  double rn = 1.0;   // renorm_relxill_spectrum_1keV (src/Relxill.cpp:249-259); the Cp models get it in k_prim_nth, after their primary
+  if (A.renorm3 && A.mode == 0 && vp.prim_type != PRIM_NTHCOMP) {
+    const int i3 = T.conv_i3kev;
+    rn = 1.0 / (acc[i3] / (T.econv[i3 + 1] - T.econv[i3]));
+  }
   for (int j = t; j < A.n_flux; j += CONV_NT) {
     double elo = A.user_e[j], ehi = A.user_e[j + 1];
     if (A.mode == 0 && vp.z > 0) { elo *= (1 + vp.z); ehi *= (1 + vp.z); }
     double f = rebin_bin(elo, ehi, T.econv, acc, NCONV);
     if (A.mode == 1 && (ehi < 0.01 || elo > 1000.0)) f = 0;   // src/Relbase.cpp:233-246
-    o[j] = f;
+    o[j] = (A.renorm3 && A.mode == 0) ? f * rn : f;
   }
 }
 
@@ -492,8 +498,9 @@ int conv_kernel_init() {
 }
 
 void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
-                 double *out, double *total, int which, int mode, int conv_grid, cudaStream_t st) {
+                 double *out, double *total, int which, int mode, int conv_grid, int renorm3, cudaStream_t st) {
   ConvArgs A;
+  A.renorm3 = renorm3;
   A.user_e = user_e; A.n_flux = n_flux; A.out = out; A.total = total; A.which = which;
   A.nz_stride = S.nz_cap; A.ne_stride = S.ne_line_cap; A.mode = mode;
   A.rb_ii = reinterpret_cast<const int2 *>(T.xill[which].rb_ii);

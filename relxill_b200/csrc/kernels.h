@@ -22,7 +22,7 @@ void launch_linefinish(const VPar *vps, const Scratch &S, long n, int n_ener, do
 void launch_xill(const VPar *vps, const DevTables &T, const Scratch &S, long n, int which, int conv_grid, cudaStream_t st);
 void xill_force_generic(int on);   // test hook: use k_xill's any-table instantiation (run-time row strides) on standard tables
 void launch_conv(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
-                 double *out, double *total, int which, int mode, int conv_grid, cudaStream_t st);
+                 double *out, double *total, int which, int mode, int conv_grid, int renorm3, cudaStream_t st);
 
 void launch_xillver(const VPar *vps, const DevTables &T, const Scratch &S, long n, int which, const double *user_e,
                     int n_flux, double *out, int stride, cudaStream_t st);
@@ -30,6 +30,6 @@ void launch_xillver_prim_nth(const VPar *vps, const DevTables &T, const Scratch 
                              double *out, cudaStream_t st);
 void launch_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, cudaStream_t st);
 void launch_prim_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, double *total, const double *user_e,
-                     int n_flux, double *out, cudaStream_t st);
+                     int n_flux, double *out, int renorm3, cudaStream_t st);
 
 }  // namespace rx

@@ -1,8 +1,12 @@
 /* minifits.h — read-only FITS binary-table access (header-only, C99 / C++).
  *
  * Just enough of FITS to read the relxill tables: mmap the file, index the
- * HDUs, locate BINTABLE columns (TFORM rE / rD / rJ / rA, PCOUNT = 0) and copy
- * big-endian cells out as float / double / int / string.  No cfitsio in this
+ * HDUs, locate BINTABLE columns and copy big-endian cells out as float / double /
+ * int / string.  Every TFORM code of the FITS standard gets its true byte width, so
+ * that a column this reader cannot decode (bit, complex, variable-length P/Q) never
+ * shifts the columns behind it: reading such a column fails, reading its neighbours
+ * works.  A table whose column widths do not add up to NAXIS1 is rejected as a whole
+ * (every read fails).  TSCALn / TZEROn are applied like cfitsio does.  No cfitsio in this
  * image, so both the CUDA library's table loader and the oracle's cfitsio shim
  * sit on this reader (I/O only, no arithmetic).
  */
@@ -24,10 +28,11 @@
 
 typedef struct {
   char name[72];
-  char code;       /* 'E','D','J','A' */
+  char code;       /* TFORM data type: 'E','D','J','I','K','B','L' numeric; 'A' string; others: not decodable */
   long width;      /* repeat count */
   long offset;     /* byte offset inside a row */
-  int elsize;
+  int elsize;      /* bytes per element (0: unknown code, the whole table is rejected) */
+  double tscal, tzero;
 } mf_col;
 
 typedef struct {
@@ -35,9 +40,23 @@ typedef struct {
   int is_table;
   long nrows, rowbytes;
   int ncols;
+  int bad_layout;  /* column widths do not add up to NAXIS1 / unknown TFORM code: reads fail */
   mf_col *cols;
   const unsigned char *data;
 } mf_hdu;
+
+/* bytes per element of a TFORM data-type code (FITS standard 4.0, table 18); 0 = not a valid code */
+static inline int mf__elsize(char code) {
+  switch (code) {
+    case 'L': case 'B': case 'A': return 1;
+    case 'I': return 2;
+    case 'J': case 'E': return 4;
+    case 'K': case 'D': case 'C': case 'P': return 8;
+    case 'M': case 'Q': return 16;
+    case 'X': return -1;   /* bits: ceil(repeat / 8) bytes for the whole cell */
+    default: return 0;
+  }
+}
 
 typedef struct {
   const unsigned char *base;
@@ -114,6 +133,7 @@ static inline mf_file *mf_open(const char *path) {
           tfields = atol(val);
           if (tfields > MF_MAXCOLS) tfields = MF_MAXCOLS;
           cols = (mf_col *) calloc((size_t) (tfields > 0 ? tfields : 1), sizeof(mf_col));
+          for (long c = 0; c < tfields; c++) cols[c].tscal = 1.0;
         } else if (cols && (memcmp(card, "TTYPE", 5) == 0 || memcmp(card, "TFORM", 5) == 0)) {
           long idx = atol(card + 5);
           if (idx >= 1 && idx <= tfields) {
@@ -125,8 +145,14 @@ static inline mf_file *mf_open(const char *path) {
               if (e == val) rep = 1;
               cols[idx - 1].width = rep;
               cols[idx - 1].code = *e;
-              cols[idx - 1].elsize = (*e == 'D') ? 8 : (*e == 'A') ? 1 : 4;
+              cols[idx - 1].elsize = mf__elsize(*e);
             }
+          }
+        } else if (cols && (memcmp(card, "TSCAL", 5) == 0 || memcmp(card, "TZERO", 5) == 0)) {
+          long idx = atol(card + 5);
+          if (idx >= 1 && idx <= tfields) {
+            if (card[1] == 'S') cols[idx - 1].tscal = atof(val);
+            else cols[idx - 1].tzero = atof(val);
           }
         }
       }
@@ -146,8 +172,10 @@ static inline mf_file *mf_open(const char *path) {
       long off = 0;
       for (int c = 0; c < h->ncols; c++) {
         cols[c].offset = off;
-        off += cols[c].width * cols[c].elsize;
+        if (cols[c].elsize == 0) h->bad_layout = 1;
+        off += (cols[c].elsize < 0) ? (cols[c].width + 7) / 8 : cols[c].width * cols[c].elsize;
       }
+      if (off != h->rowbytes) h->bad_layout = 1;
       h->data = f->base + pos;
     } else {
       free(cols);
@@ -172,7 +200,19 @@ static inline int mf_find_col(const mf_hdu *h, const char *name) {
   return 0;
 }
 
+static inline int mf__numeric(char code) {
+  return code == 'E' || code == 'D' || code == 'J' || code == 'I' || code == 'K' || code == 'B' || code == 'L';
+}
+
 static inline double mf__cell(const mf_col *c, const unsigned char *p) {
+  if (c->code == 'I') return (double) (int16_t) (((uint16_t) p[0] << 8) | p[1]);
+  if (c->code == 'B') return (double) p[0];
+  if (c->code == 'L') return (p[0] == 'T') ? 1.0 : 0.0;
+  if (c->code == 'K') {
+    uint64_t u = 0;
+    for (int i = 0; i < 8; i++) u = (u << 8) | p[i];
+    return (double) (int64_t) u;
+  }
   if (c->code == 'E') {
     uint32_t u = ((uint32_t) p[0] << 24) | ((uint32_t) p[1] << 16) | ((uint32_t) p[2] << 8) | p[3];
     float v;
@@ -194,14 +234,15 @@ static inline double mf__cell(const mf_col *c, const unsigned char *p) {
  * 1-based, running on into the following rows.  out_kind: 'f','d','i'. */
 static inline int mf_read(const mf_hdu *h, int colnum, long firstrow, long firstelem, long nelem,
                           char out_kind, void *out) {
-  if (colnum < 1 || colnum > h->ncols) return 1;
+  if (colnum < 1 || colnum > h->ncols || h->bad_layout) return 1;
   const mf_col *c = &h->cols[colnum - 1];
-  if (c->code == 'A') return 1;
+  if (!mf__numeric(c->code) || c->width < 1 || firstrow < 1 || firstelem < 1) return 1;
   long idx = (firstrow - 1) * c->width + (firstelem - 1);
   for (long k = 0; k < nelem; k++, idx++) {
     long row = idx / c->width, el = idx % c->width;
     if (row >= h->nrows) return 2;
     double v = mf__cell(c, h->data + row * h->rowbytes + c->offset + el * c->elsize);
+    if (c->tscal != 1.0 || c->tzero != 0.0) v = v * c->tscal + c->tzero;
     if (out_kind == 'f') ((float *) out)[k] = (float) v;
     else if (out_kind == 'd') ((double *) out)[k] = v;
     else ((int *) out)[k] = (int) v;
@@ -211,7 +252,7 @@ static inline int mf_read(const mf_hdu *h, int colnum, long firstrow, long first
 
 /* string cell of row `row` (1-based), trailing blanks stripped, at most n-1 chars */
 static inline int mf_read_str(const mf_hdu *h, int colnum, long row, char *out, size_t n) {
-  if (colnum < 1 || colnum > h->ncols) return 1;
+  if (colnum < 1 || colnum > h->ncols || h->bad_layout) return 1;
   const mf_col *c = &h->cols[colnum - 1];
   if (c->code != 'A' || row < 1 || row > h->nrows) return 1;
   const unsigned char *p = h->data + (row - 1) * h->rowbytes + c->offset;

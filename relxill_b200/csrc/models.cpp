@@ -231,7 +231,7 @@ void interpret_params(const ModelDef &m, const double *par, const HostConfig &cf
     vp.status = ST_BAD_PARAM;
     return;
   }
-  vp.nz = zone_count(vp.model_type, vp.emis_type, vp.ion_grad_type, cfg.env_num_zones);
+  vp.nz = zone_count(vp.model_type, vp.emis_type, vp.ion_grad_type, cfg.num_zones());
 
   // energy shift source -> observer (src/Relphysics.cpp:217-255)
   vp.eshift_obs = 1.0;

@@ -21,11 +21,18 @@ struct ModelDef {
   double def[20];
 };
 
+// The reference reads its environment switches on EVERY evaluation (get_num_zones, src/relutility.c:506-544;
+// do_not_normalize_relline, :386-396; constantDiskDensity, :372-382; get_returnrad_switch, src/ModelDefinition.cpp:139-149;
+// do_renorm_relxill, src/Relxill.cpp:241-247), so api.cu refreshes this struct at the top of every call that interprets
+// parameters (read_call_env).
 struct HostConfig {
-  int env_num_zones = 0;     // RELXILL_NUM_RZONES (0 = unset)
-  int env_returnrad = -1;    // RELXILL_RETURNRAD_SWITCH (-1 = unset)
-  int env_phys_norm = 0;     // RELLINE_PHYSICAL_NORM
-  int env_const_density = 0; // RELXILL_CONSTANT_DENSITY (src/relutility.c:372-382)
+  int env_num_zones = 0;       // RELXILL_NUM_RZONES (0 = unset)
+  int override_num_zones = 0;  // relxill_b200_set_num_zones(n > 0): takes precedence over the environment variable
+  int env_returnrad = -1;      // RELXILL_RETURNRAD_SWITCH (-1 = unset)
+  int env_phys_norm = 0;       // RELLINE_PHYSICAL_NORM
+  int env_const_density = 0;   // RELXILL_CONSTANT_DENSITY
+  int env_renorm_relxill = 0;  // RELXILL_RENORMALIZE: relxill spectra rescaled to 1 cts/s/keV/cm2 at 3 keV before the final rebin
+  int num_zones() const { return override_num_zones > 0 ? override_num_zones : env_num_zones; }
 };
 
 const ModelDef *find_model(const char *name);

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(128) k_nth(const VPar *__restrict__ vps, DevTa
 // k_conv has already applied the reflection scaling and left the 4096-bin result in `total`; this kernel adds
 // the primary and rebins to the caller's grid.
 __global__ void __launch_bounds__(256) k_prim_nth(const VPar *__restrict__ vps, DevTables T, Scratch S, double *total,
-                                                  const double *__restrict__ user_e, int n_flux, double *out) {
+                                                  const double *__restrict__ user_e, int n_flux, double *out, int renorm3) {
   __shared__ double acc[NCONV];
   const int v = blockIdx.x, t = threadIdx.x;
   if (S.status[v] != ST_OK) return;
@@ -241,6 +241,11 @@ __global__ void __launch_bounds__(256) k_prim_nth(const VPar *__restrict__ vps, 
     tot[i] = val;
   }
   __syncthreads();
+  double rn = 1.0;   // RELXILL_RENORMALIZE: renorm_relxill_spectrum_1keV, src/Relxill.cpp:249-259
+  if (renorm3) {
+    const int i3 = T.conv_i3kev;
+    rn = 1.0 / (acc[i3] / (T.econv[i3 + 1] - T.econv[i3]));
+  }
   double *o = out + (size_t) v * n_flux;
   for (int j = t; j < n_flux; j += 256) {   // _rebin_spectrum (src/relutility.c:549-601), one output bin per thread
     double elo_o = user_e[j], ehi_o = user_e[j + 1];
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(256) k_prim_nth(const VPar *__restrict__ vps, 
         for (int jj = imin + 1; jj <= imax - 1; jj++) f += acc[jj];
       }
     }
-    o[j] = f;
+    o[j] = renorm3 ? f * rn : f;
   }
 }
 
@@ -298,8 +303,8 @@ void launch_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, c
   k_nth<<<(unsigned) n, 128, 0, st>>>(vps, T, S);
 }
 void launch_prim_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, double *total, const double *user_e,
-                     int n_flux, double *out, cudaStream_t st) {
-  k_prim_nth<<<(unsigned) n, 256, 0, st>>>(vps, T, S, total, user_e, n_flux, out);
+                     int n_flux, double *out, int renorm3, cudaStream_t st) {
+  k_prim_nth<<<(unsigned) n, 256, 0, st>>>(vps, T, S, total, user_e, n_flux, out, renorm3);
 }
 
 }  // namespace rx

@@ -37,8 +37,12 @@ Tables::~Tables() {
 
 template <class T> const T *Tables::upload(const T *p, size_t n) {
   void *d = nullptr;
-  if (cudaMalloc(&d, n * sizeof(T) + 256) != cudaSuccess) return nullptr;
-  cudaMemcpy(d, p, n * sizeof(T), cudaMemcpyHostToDevice);
+  if (cudaMalloc(&d, n * sizeof(T) + 256) != cudaSuccess) { upload_failed_ = true; return nullptr; }
+  if (cudaMemcpy(d, p, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {   // every loader checks upload_failed_ before it returns
+    cudaFree(d);
+    upload_failed_ = true;
+    return nullptr;
+  }
   allocs_.push_back(d);
   dev_bytes_ += n * sizeof(T);
   return (const T *) d;
@@ -148,6 +152,7 @@ void Tables::load_fixed() {
   dt_.conv_b0 = b0;
   dt_.conv_b1 = b1;
   dt_.conv_i1kev = lower_index(econv_.data(), NCONV + 1, 1.0);                      // src/Relbase.cpp:133-137
+  dt_.conv_i3kev = lower_index(econv_.data(), NCONV, 3.0);   // renorm_relxill_spectrum_1keV: binary_search(energy, num_flux_bins, 3.0), src/Relxill.cpp:252-253
   dt_.ecoarse = upload(ecoarse_);
   dt_.coarse_m1 = upload(m1);
   dt_.coarse_m2 = upload(m2);
@@ -172,8 +177,11 @@ std::string Tables::load_rel() {
   int h = mf_find_hdu(f, "a");
   int hm = mf_find_hdu(f, "mu0");
   if (!h || !hm || f->nhdu < 3 + REL_NA * REL_NMU) { mf_close(f); return "rel table: unexpected layout in " + path; }
-  mf_read(&f->hdus[h - 1], mf_find_col(&f->hdus[h - 1], "a"), 1, 1, REL_NA, 'f', a.data());
-  mf_read(&f->hdus[hm - 1], mf_find_col(&f->hdus[hm - 1], "mu0"), 1, 1, REL_NMU, 'f', mu.data());
+  if (mf_read(&f->hdus[h - 1], mf_find_col(&f->hdus[h - 1], "a"), 1, 1, REL_NA, 'f', a.data()) ||
+      mf_read(&f->hdus[hm - 1], mf_find_col(&f->hdus[hm - 1], "mu0"), 1, 1, REL_NMU, 'f', mu.data())) {
+    mf_close(f);
+    return "rel table: cannot read the spin / inclination axes of " + path;
+  }
   const size_t n1 = (size_t) REL_NA * REL_NMU * REL_NRT;
   std::vector<float> r(n1), gmin(n1), gmax(n1), tc(n1 * NG * 4), col((size_t) REL_NRT * NG);
   const char *names[4] = {"trff1", "trff2", "cosne1", "cosne2"};
@@ -198,7 +206,7 @@ std::string Tables::load_rel() {
   dt_.rel_gmin = upload(gmin);
   dt_.rel_gmax = upload(gmax);
   dt_.rel_tc = upload(tc);
-  if (!dt_.rel_tc) return "out of device memory (rel table)";
+  if (upload_failed_ || !dt_.rel_tc) return "out of device memory (rel table)";
   have_rel_ = true;
   return "";
 }
@@ -247,7 +255,7 @@ std::string Tables::load_lp() {
   dt_.lp_int = upload(in);
   dt_.lp_del = upload(de);
   dt_.lp_dinc = upload(di);
-  if (!dt_.lp_dinc) return "out of device memory (lp table)";
+  if (upload_failed_ || !dt_.lp_dinc) return "out of device memory (lp table)";
   have_lp_ = true;
   return "";
 }
@@ -261,7 +269,11 @@ std::string Tables::load_rrad() {
   if (!hs) { mf_close(f); return "returnRad table: no SPIN extension"; }
   const int ns = (int) f->hdus[hs - 1].nrows;
   rr_spin_.resize(ns);
-  mf_read(&f->hdus[hs - 1], mf_find_col(&f->hdus[hs - 1], "a"), 1, 1, ns, 'd', rr_spin_.data());
+  if (ns < 1 || mf_read(&f->hdus[hs - 1], mf_find_col(&f->hdus[hs - 1], "a"), 1, 1, ns, 'd', rr_spin_.data())) {
+    mf_close(f);
+    rr_spin_.clear();
+    return "returnRad table: cannot read the spin axis";
+  }
   const size_t n2 = (size_t) RR_NR * RR_NR;
   std::vector<double> rlo((size_t) ns * RR_NR), rhi((size_t) ns * RR_NR), tf(ns * n2), gmin(ns * n2), gmax(ns * n2),
       fg(ns * n2 * RR_NG), lng(ns * n2 * RR_NG);
@@ -304,7 +316,7 @@ std::string Tables::load_rrad() {
         }
     dt_.rr_fgl = upload(fgl);
   }
-  if (!dt_.rr_fgl) return "out of device memory (returnRad table)";
+  if (upload_failed_ || !dt_.rr_fgl) return "out of device memory (returnRad table)";
   have_rr_ = true;
   return "";
 }
@@ -335,16 +347,18 @@ std::string Tables::load_xill(int which) {
   const mf_hdu *P = &f->hdus[hp - 1], *E = &f->hdus[he - 1], *S = &f->hdus[hs - 1];
   xh.npar = (int) P->nrows;
   if (xh.npar != 5 && xh.npar != 6) { mf_close(f); return "xillver table: wrong dimensionality"; }
-  mf_read(P, 9, 1, 1, xh.npar, 'i', xh.nvals);
+  // XSPEC atable layout: column 1 NAME (string), 9 NUMBVALS, 10 VALUE (src/xilltable.c:169-238 reads them by number)
+  if (P->ncols < 10 || mf_read(P, 9, 1, 1, xh.npar, 'i', xh.nvals)) { mf_close(f); return "xillver table: cannot read NUMBVALS in " + path; }
   long nrows = 1;
   int ax_lxi = -1, ax_dns = -1;
   for (int i = 0; i < xh.npar; i++) {
     char nm[16];
-    mf_read_str(P, 1, i + 1, nm, 8);
+    if (mf_read_str(P, 1, i + 1, nm, sizeof(nm))) { mf_close(f); return "xillver table: cannot read the parameter names in " + path; }
     xh.pindex[i] = xill_param_id(nm);
     if (xh.pindex[i] < 0) { mf_close(f); return std::string("xillver table: unknown parameter ") + nm; }
+    if (xh.nvals[i] < 2) { mf_close(f); return std::string("xillver table: fewer than two values on axis ") + nm; }
     xh.vals[i].resize(xh.nvals[i]);
-    mf_read(P, 10, i + 1, 1, xh.nvals[i], 'f', xh.vals[i].data());
+    if (mf_read(P, 10, i + 1, 1, xh.nvals[i], 'f', xh.vals[i].data())) { mf_close(f); return std::string("xillver table: cannot read the values of axis ") + nm; }
     nrows *= xh.nvals[i];
     if (xh.pindex[i] == 2) ax_lxi = i;
     if (xh.pindex[i] == 4) ax_dns = i;
@@ -357,8 +371,10 @@ std::string Tables::load_xill(int which) {
   xh.stride = ((xh.n_ener + 31) / 32) * 32;
   xh.nnodes = nrows / xh.n_incl;
   std::vector<float> elo(xh.n_ener), ehi(xh.n_ener);
-  mf_read(E, 1, 1, 1, xh.n_ener, 'f', elo.data());
-  mf_read(E, 2, 1, 1, xh.n_ener, 'f', ehi.data());
+  if (xh.n_ener < 2 || mf_read(E, 1, 1, 1, xh.n_ener, 'f', elo.data()) || mf_read(E, 2, 1, 1, xh.n_ener, 'f', ehi.data())) {
+    mf_close(f);
+    return "xillver table: cannot read the energy grid of " + path;
+  }
   xh.ener.resize(xh.n_ener + 1);
   for (int i = 0; i < xh.n_ener; i++) xh.ener[i] = elo[i];                         // src/xilltable.c:1105-1109
   xh.ener[xh.n_ener] = ehi[xh.n_ener - 1];
@@ -463,7 +479,10 @@ std::string Tables::load_xill(int which) {
       }
       ef[node] = s_ef; p1[node] = s_p1; p2[node] = s_p2;
     }
-    cudaMemcpy(d_data + (size_t) n0 * ni * st, stage.data(), (size_t) nb * ni * st * sizeof(float), cudaMemcpyHostToDevice);
+    if (cudaMemcpy(d_data + (size_t) n0 * ni * st, stage.data(), (size_t) nb * ni * st * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+      mf_close(f);
+      return "xillver table: upload failed (" + path + ")";
+    }
     if (want_c) {
       for (long r = 0; r < nb * ni; r++) {
         const float *src = stage.data() + (size_t) r * st;
@@ -478,8 +497,11 @@ std::string Tables::load_xill(int which) {
           dst[c] = v;
         }
       }
-      cudaMemcpy(d_datac + (size_t) n0 * ni * xh.xc_stride, stage_c.data(), (size_t) nb * ni * xh.xc_stride * sizeof(double),
-                 cudaMemcpyHostToDevice);
+      if (cudaMemcpy(d_datac + (size_t) n0 * ni * xh.xc_stride, stage_c.data(), (size_t) nb * ni * xh.xc_stride * sizeof(double),
+                     cudaMemcpyHostToDevice) != cudaSuccess) {
+        mf_close(f);
+        return "xillver table: upload of the convolution-grid copy failed (" + path + ")";
+      }
     }
   }
   mf_close(f);
@@ -503,7 +525,7 @@ std::string Tables::load_xill(int which) {
   }
   xd.rb_ii = upload(ii_v);
   xd.rb_dd = upload(dd_v);
-  if (!xd.rb_dd) return "out of device memory (xillver table)";
+  if (upload_failed_ || !xd.rb_dd) return "out of device memory (xillver table)";
   xd.xc_first = xh.xc_first; xd.xc_n = xh.xc_n; xd.xc_stride = xh.xc_stride;
   xd.datac = d_datac;
   xh.has_conv_copy = d_datac != nullptr;
@@ -621,6 +643,7 @@ void Tables::load_nthcomp() {
 std::string Tables::load(const std::string &dir) {
   dir_ = dir;
   load_fixed();
+  if (upload_failed_) return "out of device memory (fixed grids)";
   if (conv_cf_dev_ > 1e-11) return "convolution grid: E_mid/dE is not constant (k_conv relies on it)";
   return "";   // the tables themselves are loaded on first use by the model flavour that needs them
 }
@@ -630,6 +653,7 @@ std::string Tables::require_xill_only(int xtab) {
   std::string err = load_xill(xtab);
   if (!err.empty()) return err;
   if (xtab == XT_CP) load_nthcomp();
+  if (upload_failed_) return "out of device memory (tables)";
   return "";
 }
 
@@ -640,6 +664,7 @@ std::string Tables::require(bool lp, bool rrad, int xtab) {
   if (rrad && !(err = load_rrad()).empty()) return err;
   if (xtab != XT_NONE && !(err = load_xill(xtab)).empty()) return err;
   if (xtab == XT_CP) load_nthcomp();
+  if (upload_failed_) return "out of device memory (tables)";
   return "";
 }
 

@@ -47,6 +47,7 @@ class Tables {
   size_t dev_bytes_ = 0;
   double conv_cf_dev_ = 0.0;
   bool conv_grid_copy_ = true;
+  bool upload_failed_ = false;   // a cudaMalloc / cudaMemcpy of a table array failed
 
   template <class T> const T *upload(const std::vector<T> &v);
   template <class T> const T *upload(const T *p, size_t n);

@@ -118,3 +118,37 @@ def config_cases():
     P[:, 14] = 0
     cases.append(("cfg4_relxilllpCp", "relxilllpCp", None, P, [1, 833, 1257, 2498]))
     return cases
+
+
+def edge_params(model):
+    """Parameter vectors that exercise the branches the random samplers never reach:
+    switch_returnrad in {-1, 2} (src/Rellp.cpp:483-509: -1 = reflection of the returning radiation only is NOT what it
+    means — 1 adds the returning emissivity, 2 / -1 replace the direct one), positive Rin / Rout (gravitational
+    radii instead of multiples of the ISCO), negative h (multiples of the event horizon) and negative Rbr
+    (src/ModelDefinition.cpp:202-226)."""
+    import relxill_b200 as rx   # only the default vectors (host-side table in the library)
+    base = rx.default_params(model)
+    names = [n.lower() for n in rx.PARAM_NAMES[model]]
+    rows = []
+
+    def row(**kw):
+        p = base.copy()
+        for k, v in kw.items():
+            p[names.index(k.lower())] = v
+        rows.append(p)
+
+    if "switch_returnrad" in names:
+        row(switch_returnrad=-1, a=0.9)
+        row(switch_returnrad=2, a=0.9)
+        row(switch_returnrad=2, a=-0.3)          # negative spin: no correction factors (src/Relxill.cpp:338-341)
+        row(switch_returnrad=0, a=0.9)
+    row(rin=6.5, rout=350.0, a=0.7)              # positive radii: used as given
+    row(rin=1.5, rout=80.0, a=0.5)               # positive Rin below the ISCO (4.23): clamped up to it
+    if "h" in names:
+        row(h=-2.5, a=0.95)                      # negative height: in units of the event horizon
+        row(h=-1.05, a=0.3)                      # below 1.1 r+: clamped
+    if "rbr" in names:
+        row(rbr=-3.0, index1=5.0, index2=2.0)    # negative break radius: in units of the ISCO
+        row(rbr=5000.0, index1=4.0)              # beyond Rout: clamped to Rout
+        row(rbr=0.5, index1=4.0)                 # inside Rin: clamped to Rin
+    return np.array(rows)

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from common import PEAK_FLOOR, RTOL, config_cases, default_grid, relerr, sample_params, walker_ball
+from common import PEAK_FLOOR, RTOL, config_cases, default_grid, edge_params, relerr, sample_params, walker_ball
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz")
@@ -414,6 +414,37 @@ def test_state_cache_behind_the_xspec_symbols(rx):
         np.testing.assert_array_equal(a, b)
 
 
+@pytest.mark.parametrize("model", ["relxilllp", "relxilllpCp"])
+def test_state_cache_survives_an_mcmc_sized_host_batch(rx, model):
+    """4096 walkers x 50 zones through the HOST API (relxill_batch_eval cuts the batch into pipelined
+    pieces; each piece keeps its slice of the arena), every second walker unchanged on the second call: 2048 whole
+    spectra are re-used, and the result carries the bits of a fresh evaluation.  relxilllpCp runs with the ionisation
+    gradient (its Kompaneets work arrays are part of the arena: one chunk of 4096)."""
+    e = default_grid(3000)
+    n = 4096
+    P0 = walker_ball(model, n)
+    if model == "relxilllpCp":
+        P0[:, 14] = 1
+    P1 = P0.copy()
+    P1[::2] = walker_ball(model, n, seed=991)[::2]
+    if model == "relxilllpCp":
+        P1[:, 14] = 1
+    rx.set_num_zones(50)
+    rx.set_cache(True)
+    try:
+        rx.batch_eval(model, e, P0)
+        assert rx.last_eval_reuse() == dict(recomputed=n, reused_rel=0, reused_all=0)
+        got = rx.batch_eval(model, e, P1)
+        cnt = rx.last_eval_reuse()
+        assert cnt["reused_all"] == n // 2 and cnt["recomputed"] + cnt["reused_rel"] == n // 2, cnt
+        rx.set_cache(False)
+        fresh = rx.batch_eval(model, e, P1)
+        np.testing.assert_array_equal(got, fresh)
+    finally:
+        rx.set_cache(True)
+        rx.set_num_zones(None)
+
+
 # ---------------------------------------------------------------- the other BASELINE.json configurations
 @pytest.mark.parametrize("key,model,zones", [("cfg2_relxill", "relxill", None), ("cfg3_relxilllp", "relxilllp", 50),
                                               ("cfg3_relxilllpCp", "relxilllpCp", 50), ("cfg4_relxillCp", "relxillCp", None),
@@ -495,3 +526,167 @@ def test_config5_returning_radiation_sweep(rx, oracle):
     assert (st == 0).all() and np.isfinite(f).all() and (f.sum(axis=1) > 0).all()
     for i in (0, 37, 101, 200, 255):
         assert relerr(f[i], oracle.eval("relxilllp", e, P[i])) < RTOL, i
+
+
+# ---------------------------------------------------------------- full batches against the unmodified reference
+@pytest.fixture(scope="module")
+def refpool_factory(table_dir):
+    from oracle import pyref
+    if not pyref.available():
+        pytest.skip("oracle/_ref/librelxill_ref.so not built")
+    from refpool import RefPool
+    pools = []
+
+    def make(zones):
+        pools.append(RefPool(table_dir, zones))
+        return pools[-1]
+    yield make
+    for p in pools:
+        p.close()
+
+
+def _census_report(name, c):
+    import json
+    print(f"\nPARITY-CENSUS {name}: {json.dumps(c)}")
+    out = os.environ.get("RELXILL_B200_CENSUS_OUT")
+    if out:
+        with open(out, "a") as f:
+            f.write(json.dumps({"case": name, **c}) + "\n")
+
+
+@pytest.mark.parametrize("model", ["relxilllp", "relxilllpCp"])
+def test_metric_batch_every_row_vs_reference(rx, refpool_factory, model):
+    """BASELINE config 3, all of it: every one of the 4096 MCMC walkers x 50 zones x 3000 bins against the UNMODIFIED
+    reference (oracle/_ref in a process pool on the host cores) — relxilllp, and relxilllpCp with the ionisation gradient
+    (iongrad_type 1 and 2 alternating).  SURVEY App. C.16 predicts a small rate of single-bin outliers from discrete
+    decisions that flip on a last-bit difference (Romberg exit, bin index, g* bracket): the census counts them.  No bin may
+    exceed the north_star tolerance."""
+    from refpool import census
+    e = default_grid(3000)
+    P = walker_ball(model, 4096)
+    if model == "relxilllpCp":
+        P[:, 14] = 1 + (np.arange(4096) % 2)
+    rx.set_num_zones(50)
+    try:
+        got, st = rx.batch_eval(model, e, P, return_status=True)
+    finally:
+        rx.set_num_zones(None)
+    assert (st == 0).all()
+    want, dt = refpool_factory(50).eval_rows(model, e, P)
+    c = census(got, want)
+    c["reference_seconds"] = round(dt, 1)
+    _census_report(f"cfg3_{model}_4096x50", c)
+    assert c["n_bins_over_1e-05"] == 0, c
+
+
+def test_config4_shard_vs_reference(rx, refpool_factory):
+    """BASELINE config 4 at its per-GPU size: 8192 uniform-random relxillCp vectors and 8192 relxilllpCp vectors
+    (iongrad_type 0, 10 zones) — one GPU's shard of the 65536 — with 256 randomly picked rows of each against the
+    unmodified reference."""
+    from refpool import census
+    e = default_grid(3000)
+    pool = refpool_factory(None)
+    for model in ("relxillCp", "relxilllpCp"):
+        P = sample_params(model, 8192, seed=99)
+        if model == "relxilllpCp":
+            P[:, 14] = 0
+        got, st = rx.batch_eval(model, e, P, return_status=True)
+        assert np.isfinite(got).all()
+        ok = np.flatnonzero(st == 0)
+        assert ok.size > 0.95 * 8192
+        pick = np.sort(np.random.default_rng(4).choice(ok, 256, replace=False))
+        want, _ = pool.eval_rows(model, e, P[pick])
+        c = census(got[pick], want)
+        _census_report(f"cfg4_{model}_8192_pick256", c)
+        assert c["n_bins_over_1e-05"] == 0, (model, c)
+
+
+def config5_grid_full(rx):
+    """BASELINE config 5 as stated: a in linspace(0, 0.998, 32) x h in geomspace(2, 100, 32) x Incl in linspace(5, 80, 16)."""
+    base = rx.default_params("relxilllp")
+    a, h, inc = np.meshgrid(np.linspace(0.0, 0.998, 32), np.geomspace(2.0, 100.0, 32), np.linspace(5.0, 80.0, 16), indexing="ij")
+    P = np.tile(base, (a.size, 1))
+    P[:, 2], P[:, 0], P[:, 3], P[:, 12] = a.ravel(), h.ravel(), inc.ravel(), 1
+    return P
+
+
+def test_config5_full_sweep_vs_reference(rx, refpool_factory):
+    """BASELINE config 5 at its stated size: the 32 x 32 x 16 = 16384-point returning-radiation sweep, 256 randomly
+    picked grid points against the unmodified reference."""
+    from refpool import census
+    e = default_grid(3000)
+    P = config5_grid_full(rx)
+    assert P.shape[0] == 16384
+    got, st = rx.batch_eval("relxilllp", e, P, return_status=True)
+    assert (st == 0).all() and np.isfinite(got).all() and (got.sum(axis=1) > 0).all()
+    pick = np.sort(np.random.default_rng(5).choice(16384, 256, replace=False))
+    want, _ = refpool_factory(None).eval_rows("relxilllp", e, P[pick])
+    c = census(got[pick], want)
+    _census_report("cfg5_relxilllp_16384_pick256", c)
+    assert c["n_bins_over_1e-05"] == 0, c
+
+
+# ---------------------------------------------------------------- edge-case parameters and environment switches
+@pytest.mark.parametrize("model", ["relxilllp", "relxilllpCp", "relline_lp", "relconv_lp", "relxill", "relline", "relxillCp"])
+def test_edge_case_parameters(rx, oracle, model):
+    """switch_returnrad in {-1, 2, 0}, positive Rin / Rout, negative h (x r+), negative / out-of-range Rbr
+    (src/Rellp.cpp:483-509, src/ModelDefinition.cpp:202-226; tests/common.py: edge_params); the oracle is pinned to the
+    reference on the same vectors in tests/test_oracle.py."""
+    e = default_grid(1500)
+    P = edge_params(model)
+    fin = _conv_input(e) if model.startswith("relconv") else None
+    rx.set_num_zones(None)
+    oracle.set_num_zones(None)
+    got, st = rx.batch_eval(model, e, P, fin, return_status=True)
+    assert (st == 0).all(), st
+    for a, p in zip(got, P):
+        b = oracle.eval_conv(model, e, p, fin) if fin is not None else oracle.eval(model, e, p)
+        assert relerr(a, b) < RTOL, (model, list(p))
+
+
+@pytest.mark.parametrize("env,model", [({"RELXILL_RENORMALIZE": "1"}, "relxilllp"), ({"RELXILL_RENORMALIZE": "1"}, "relxillCp"),
+                                       ({"RELXILL_RENORMALIZE": "1"}, "relxilllpCp"),
+                                       ({"RELLINE_PHYSICAL_NORM": "1"}, "relline"), ({"RELLINE_PHYSICAL_NORM": "1"}, "relconv"),
+                                       ({"RELLINE_PHYSICAL_NORM": "1"}, "relxill"),
+                                       ({"RELXILL_RETURNRAD_SWITCH": "1"}, "relline_lp"), ({"RELXILL_RETURNRAD_SWITCH": "0"}, "relxilllp"),
+                                       ({"RELXILL_NUM_RZONES": "17"}, "relxilllp"), ({"RELXILL_NUM_RZONES": "60"}, "relxilllp")])
+def test_environment_switches_are_read_per_call(rx, oracle, monkeypatch, env, model):
+    """The reference re-reads its environment switches on every evaluation (src/relutility.c:372-396,506-544,
+    src/ModelDefinition.cpp:123-149, src/Relxill.cpp:241-278) — a pyxspec session flips them between calls.  Evaluate,
+    set the variable, evaluate again (the retained batch of the first call must not leak its state), unset, evaluate
+    again: each result must be the oracle's under the same environment (the oracle is pinned to the reference under
+    these variables in tests/test_oracle.py)."""
+    e = default_grid(1200)
+    P = sample_params(model, 3, seed=77)
+    fin = _conv_input(e) if model == "relconv" else None
+    rx.set_num_zones(None)
+    oracle.set_num_zones(None)
+
+    def both():
+        got = rx.batch_eval(model, e, P, fin)
+        want = [oracle.eval_conv(model, e, p, fin) if fin is not None else oracle.eval(model, e, p) for p in P]
+        assert max(relerr(a, b) for a, b in zip(got, want)) < RTOL, (env, model)
+        return got
+    base = both()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    switched = both()
+    for k in env:
+        monkeypatch.delenv(k)
+    np.testing.assert_array_equal(both(), base)
+    if env in ({"RELXILL_RENORMALIZE": "1"}, {"RELLINE_PHYSICAL_NORM": "1"}, {"RELXILL_NUM_RZONES": "17"}):
+        assert max(relerr(a, b) for a, b in zip(switched, base)) > 1e-6      # the switch did something
+
+
+def test_num_zones_env_between_two_lmod_calls(rx, oracle, monkeypatch):
+    """RELXILL_NUM_RZONES flipped between two calls of the XSPEC symbol."""
+    e = default_grid(600)
+    p = rx.default_params("relxilllp")
+    rx.set_num_zones(None)
+    oracle.set_num_zones(None)
+    a10 = rx.lmod("relxilllp", e, p)
+    monkeypatch.setenv("RELXILL_NUM_RZONES", "35")
+    a35 = rx.lmod("relxilllp", e, p)
+    assert relerr(a35, oracle.eval("relxilllp", e, p)) < RTOL and relerr(a35, a10) > 1e-7
+    monkeypatch.delenv("RELXILL_NUM_RZONES")
+    np.testing.assert_array_equal(rx.lmod("relxilllp", e, p), a10)

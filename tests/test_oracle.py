@@ -221,3 +221,56 @@ def test_constant_density_env_vs_reference(oracle, ref, monkeypatch):
         ref.close()                     # workers spawned with the switch set must not outlive this test
     assert relerr(a, b) < 1e-8
     assert relerr(a, base) > 1e-4
+
+
+# ---------------------------------------------------------------- environment switches and edge-case parameters
+def _fresh_ref(table_dir):
+    from oracle import pyref
+    if not pyref.available():
+        pytest.skip("oracle/_ref/librelxill_ref.so not built")
+    return pyref.Ref(table_dir)      # workers are spawned on first use and inherit os.environ as it is then
+
+
+@pytest.mark.parametrize("env,model", [({"RELXILL_RENORMALIZE": "1"}, "relxilllp"), ({"RELXILL_RENORMALIZE": "1"}, "relxillCp"),
+                                       ({"RELLINE_PHYSICAL_NORM": "1"}, "relline"), ({"RELLINE_PHYSICAL_NORM": "1"}, "relconv"),
+                                       ({"RELLINE_PHYSICAL_NORM": "1"}, "relxill"),
+                                       ({"RELXILL_RETURNRAD_SWITCH": "1"}, "relline_lp"), ({"RELXILL_RETURNRAD_SWITCH": "0"}, "relxilllp"),
+                                       ({"RELXILL_NUM_RZONES": "17"}, "relxilllp"), ({"RELXILL_NUM_RZONES": "60"}, "relxilllp"),
+                                       ({"RELXILL_NUM_RZONES": "7"}, "relxilllpCp")])
+def test_env_switches_vs_reference(oracle, table_dir, monkeypatch, env, model):
+    """The reference reads RELXILL_RENORMALIZE (src/Relxill.cpp:241-278), RELLINE_PHYSICAL_NORM (src/relutility.c:386-396),
+    RELXILL_RETURNRAD_SWITCH (src/ModelDefinition.cpp:123-149) and RELXILL_NUM_RZONES (src/relutility.c:506-544) on every
+    evaluation; the oracle must do the same, including the out-of-range zone counts that fall back to the defaults."""
+    e = default_grid(500)
+    P = sample_params(model, 2, seed=77)
+    if model == "relxilllpCp":
+        P[:, 14] = [1, 2]     # ionisation gradient: zone counts below 10 are refused
+    fin = np.exp(-0.5 * ((np.log(0.5 * (e[1:] + e[:-1])) - np.log(6.4)) / 0.03) ** 2) + 1e-3
+    oracle.set_num_zones(None)
+    base = [oracle.eval_conv(model, e, p, fin) if model == "relconv" else oracle.eval(model, e, p) for p in P]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    ref = _fresh_ref(table_dir)
+    try:
+        changed = False
+        for p, b in zip(P, base):
+            got = oracle.eval_conv(model, e, p, fin) if model == "relconv" else oracle.eval(model, e, p)
+            want = ref.eval_conv(model, e, p, fin) if model == "relconv" else ref.eval(model, e, p)
+            assert relerr(got, want) < 1e-8, (env, model)
+            changed |= relerr(got, b) > 1e-6
+        expect_change = env not in ({"RELXILL_RETURNRAD_SWITCH": "0"}, {"RELXILL_NUM_RZONES": "60"}, {"RELXILL_NUM_RZONES": "7"})
+        if model == "relline_lp":
+            expect_change = False     # its lmodel.dat entry carries switch_returnrad, which takes precedence over the environment
+        assert changed == expect_change, (env, model)
+    finally:
+        ref.close()
+
+
+@pytest.mark.parametrize("model", ["relxilllp", "relxilllpCp", "relline_lp", "relxill", "relline", "relxillCp"])
+def test_edge_case_parameters_vs_reference(oracle, ref, model):
+    """switch_returnrad -1 / 2, positive Rin / Rout, negative h and Rbr (tests/common.py: edge_params)."""
+    from common import edge_params
+    e = default_grid(500)
+    oracle.set_num_zones(None)
+    for p in edge_params(model):
+        assert relerr(oracle.eval(model, e, p), ref.eval(model, e, p)) < 1e-8, (model, list(p))
