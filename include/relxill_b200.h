@@ -147,6 +147,10 @@ long relxill_b200_last_launches(relxill_b200_batch *b);
 void relxill_b200_set_profiling(int on);
 int relxill_b200_kernel_times(relxill_b200_batch *b, const char **names, double *ms, long *launches, int max);
 
+/* FP64 roofline denominator of the current device, measured on the spot: TFLOP/s of a DFMA microkernel (independent
+ * chains, no memory traffic, CUDA events, best of 5 after a warm-up launch).  < 0 on error. */
+double relxill_b200_measure_fp64_peak(void);
+
 /* Grid on which the per-zone xillver spectra are blended: 1 (default) = the convolution grid — every table
  * row is rebinned once at load (the reference rebins every zone spectrum of every evaluation,
  * _rebin_spectrum, src/Relxill.cpp:461-463; the map is linear, so it commutes with the interpolation) and

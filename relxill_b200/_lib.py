@@ -39,6 +39,7 @@ ABI_SYMBOLS = [
     "relxill_b200_kernel_times", "relxill_b200_probe", "relxill_b200_update_params", "relxill_b200_update_energy",
     "relxill_b200_reuse_counts", "relxill_b200_set_cache", "relxill_b200_set_xill_grid", "relxill_b200_get_xill_grid", "relxill_b200_set_xill_generic",
     "relxill_b200_last_eval_reuse", "relxill_b200_init_devices", "relxill_b200_num_devices", "relxill_b200_set_sharding", "relxill_b200_prepare_on",
+    "relxill_b200_measure_fp64_peak",
 ] + sorted(LMOD_SYMBOLS.values())
 
 
@@ -94,6 +95,7 @@ def lib() -> C.CDLL:
     L.relxill_b200_set_xill_grid.argtypes = [C.c_int]
     L.relxill_b200_get_xill_grid.restype = C.c_int
     L.relxill_b200_set_xill_generic.argtypes = [C.c_int]
+    L.relxill_b200_measure_fp64_peak.restype = C.c_double
     for sym in LMOD_SYMBOLS.values():
         f = getattr(L, sym)
         f.argtypes = [_dp, C.c_int, _dp, C.c_int, _dp, C.c_void_p, C.c_char_p]

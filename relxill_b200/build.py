@@ -9,9 +9,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librelxill_b200.so")
-SOURCES = ["models.cpp", "tables.cu", "kernels.cu", "line.cu", "xill.cu", "conv.cu", "nthcomp.cu", "api.cu"]
+SOURCES = ["models.cpp", "tables.cu", "kernels.cu", "line.cu", "xill.cu", "conv.cu", "nthcomp.cu", "peak.cu", "api.cu"]
 # translation units compiled with FMA contraction enabled (everything else: -fmad=false)
-FMAD_ON = {"line.cu", "xill.cu", "conv.cu"}
+FMAD_ON = {"line.cu", "xill.cu", "conv.cu", "peak.cu"}
 HEADERS = ["common.h", "devutil.cuh", "models.h", "tables.h", "kernels.h", "minifits.h", "../../include/relxill_b200.h"]
 
 NVCC_FLAGS = [
