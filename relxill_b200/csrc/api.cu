@@ -505,7 +505,8 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
       if (b->any_corr) { tm.begin(); launch_syspar(vps, T, S, nc, 2, st); tm.end(KF_SYSPAR); }
     }
     tm.begin();
-    launch_fine(vps, T, S, nc, relxill ? n_incl : 0, econv[0], econv[NCONV], (b->any_limb || cc.keep_intermediates) ? 1 : 0, st);
+    launch_fine(vps, T, S, nc, relxill ? n_incl : 0, econv[0], econv[NCONV], (b->any_limb || cc.keep_intermediates) ? 1 : 0,
+                cc.keep_intermediates ? 1 : 0, st);
     tm.end(KF_FINE, 2);   // two kernels (k_rows, k_fine) timed as one family
     if (relxill) {
       tm.begin(); launch_dist(vps, T, S, nc, n_incl, st); tm.end(KF_DIST);

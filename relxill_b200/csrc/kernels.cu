@@ -706,9 +706,11 @@ __global__ void __launch_bounds__(320) k_rows(const VPar *__restrict__ vps, DevT
   tr.y = lin2d_f(fa, fm, a00.y, a10.y, a01.y, a11.y);
   co.x = lin2d_f(fa, fm, a00.z, a10.z, a01.z, a11.z);
   co.y = lin2d_f(fa, fm, a00.w, a10.w, a01.w, a11.w);
-  double2 *row = reinterpret_cast<double2 *>(S.relrow) + (((size_t) v * REL_NRT + it) * NG + j) * 2;
+  // two planes per vector, [REL_NRT][NG] {branch 0, branch 1} each: the transfer functions (k_line stages runs of these
+  // rows with one bulk copy), then the emission angles
+  double2 *row = reinterpret_cast<double2 *>(S.relrow) + (size_t) v * REL_NRT * NG * 2 + (size_t) it * NG + j;
   row[0] = tr;
-  row[1] = co;
+  row[REL_NRT * NG] = co;
 }
 
 // ---------------------------------------------------------------------------------- k_fine
@@ -720,7 +722,7 @@ __global__ void __launch_bounds__(320) k_rows(const VPar *__restrict__ vps, DevT
 // them in the reference's order (g* ascending, branch 1 then 2).  The emission angles themselves are stored
 // only when a later stage needs them (limb darkening in k_line, or the test probes).
 __global__ void __launch_bounds__(320) k_fine(const VPar *__restrict__ vps, DevTables T, Scratch S, int n_incl,
-                                              double e_first, double e_last, int store_cosne) {
+                                              double e_first, double e_last, int store_cosne, int store_trff) {
   __shared__ __align__(16) double2 s_val[8][NG];   // the two branch contributions of every (radius, g*)
   __shared__ int s_bin[8][NG];                      // their angle bins, 16 bits each (0xffff: none)
   __shared__ double s_rad[8][3];                    // per radius: gmin, gmax - gmin, r (2 pi r)^2 emis weight (< 0: off the grid)
@@ -743,8 +745,8 @@ __global__ void __launch_bounds__(320) k_fine(const VPar *__restrict__ vps, DevT
   const double fr = S.fr[(size_t) v * NR + i];
   // the two table rows around this radius, already interpolated in (a, mu0) by k_rows: row `it` (larger radius) and
   // row `it+1` (smaller radius)
-  const double2 *row = reinterpret_cast<const double2 *>(S.relrow) + (((size_t) v * REL_NRT + it) * NG + j) * 2;
-  const double2 thi = row[0], chi = row[1], tlo = row[2 * NG], clo = row[2 * NG + 1];
+  const double2 *row = reinterpret_cast<const double2 *>(S.relrow) + (size_t) v * REL_NRT * NG * 2 + (size_t) it * NG + j;
+  const double2 thi = row[0], chi = row[REL_NRT * NG], tlo = row[NG], clo = row[REL_NRT * NG + NG];
   const double t1_hi = thi.x, t2_hi = thi.y, c1_hi = chi.x, c2_hi = chi.y;
   const double t1_lo = tlo.x, t2_lo = tlo.y, c1_lo = clo.x, c2_lo = clo.y;
   double2 tr, co;
@@ -753,7 +755,7 @@ __global__ void __launch_bounds__(320) k_fine(const VPar *__restrict__ vps, DevT
   co.x = lin1d(fr, c1_lo, c1_hi);
   co.y = lin1d(fr, c2_lo, c2_hi);
   const size_t o = ((size_t) v * NR + i) * NG + j;
-  reinterpret_cast<double2 *>(S.trff)[o] = tr;
+  if (store_trff) reinterpret_cast<double2 *>(S.trff)[o] = tr;   // probes only: k_line interpolates its own rows
   if (store_cosne) reinterpret_cast<double2 *>(S.cosne)[o] = co;
   if (n_incl <= 0) return;
   __syncthreads();
@@ -981,11 +983,11 @@ void launch_zone(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
   k_zone<<<(unsigned) n, 128, g_smem_zone, st>>>(vps, T, S);
 }
 void launch_fine(const VPar *vps, const DevTables &T, const Scratch &S, long n, int n_incl, double e_first,
-                 double e_last, int store_cosne, cudaStream_t st) {
+                 double e_last, int store_cosne, int store_trff, cudaStream_t st) {
   dim3 grid_rows((REL_NRT + 7) / 8, (unsigned) n);
   k_rows<<<grid_rows, 320, 0, st>>>(vps, T, S);
   dim3 grid(NR / 8, (unsigned) n);
-  k_fine<<<grid, 320, 0, st>>>(vps, T, S, n_incl, e_first, e_last, store_cosne);
+  k_fine<<<grid, 320, 0, st>>>(vps, T, S, n_incl, e_first, e_last, store_cosne, store_trff);
 }
 void launch_dist(const VPar *vps, const DevTables &T, const Scratch &S, long n, int n_incl, cudaStream_t st) {
   k_dist<<<(unsigned) n, 256, 0, st>>>(vps, T, S, n_incl);

@@ -12,7 +12,7 @@ void launch_syspar(const VPar *vps, const DevTables &T, const Scratch &S, long n
 void launch_zone(const VPar *vps, const DevTables &T, const Scratch &S, long n, cudaStream_t st);
 // n_incl > 0: also file the per-radius parts of the emission-angle distribution (relxill models)
 void launch_fine(const VPar *vps, const DevTables &T, const Scratch &S, long n, int n_incl, double e_first,
-                 double e_last, int store_cosne, cudaStream_t st);
+                 double e_last, int store_cosne, int store_trff, cudaStream_t st);
 void launch_dist(const VPar *vps, const DevTables &T, const Scratch &S, long n, int n_incl, cudaStream_t st);
 void launch_line(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *egrid, int n_ener,
                  int grid_mode, int nz_max, cudaStream_t st);

@@ -3,26 +3,31 @@
 // Romberg convergence test, which has a 2 % threshold.
 //
 // Replaces calc_relline_profile + integ_relline_bin + int_edge + int_romb + romberg_integration +
-// relb_func (src/Relprofile.cpp:489-726,835-905) and the division by the bin energy of
-// renorm_relline_profile (:757-762).
+// relb_func (src/Relprofile.cpp:489-726,835-905), the radial half of interpol_relTable (:280-293) and the division
+// by the bin energy of renorm_relline_profile (:757-762).
 //
-// Mapping.  One CTA (4 warps) per (vector, radial zone).  The zone's radii are processed in sub-batches; inside
-// a sub-batch all (radius, energy-bin) pairs that the reference's double loop visits are flattened into one
-// dense item list (the bins of one radius are contiguous: [ielo, iehi]), so lanes stay busy whatever the
-// line width is.  The work is sorted by cost so that the lanes of a warp do the same thing:
-//   set-up   lane = radius, one warp per task: first bin, last bin (closed-form index on the logarithmic
-//            convolution grid, corrected against the tabulated edges) and the integrand at the two edge
-//            nodes g* = h, 1-h that int_edge needs (once per radius instead of once per edge bin);
-//            offsets by a warp scan.
-//   pass A   one thread per item: analytic edge terms and the midpoint-rule bins (E < 0.95) are finished;
-//            the bins that take the Romberg path are gathered in a dense list.
-//   pass B   one thread per Romberg bin: two halvings (five abscissae) unconditionally; a bin that has not
-//            converged by then (the horns of the profile, a few per cent of the bins) goes on a work list.
-//   phase 2  one HALF WARP per listed bin: the 16 new abscissae of levels <= 4 are evaluated in parallel
-//            across the lanes, the level sums come from one xor-butterfly, and the tableaus of 32 bins are
-//            then built in parallel, one per lane.  Levels 5-6 (rare) are finished by the owning lane.
-//   phase 3  per energy bin, the sub-batch's contributions are added in ascending-radius order into the
-//            zone's output row -> no atomics on data, bit-reproducible, the reference's summation order.
+// Mapping.  One CTA (4 warps) per (vector, radial zone); the zone's radii are taken in sub-batches of <= LN_R.
+//   staging  the (a, mu0)-interpolated transfer-function rows of the TABLE radii that bracket the sub-batch (k_rows'
+//            output, contiguous) come in with ONE bulk asynchronous copy (cp.async.bulk + mbarrier: the TMA unit moves
+//            them while the threads compute bin ranges); the radial interpolation onto the sub-batch's fine radii is
+//            then done from shared memory into shared memory.  The fine transfer functions never exist in HBM.
+//   set-up   one thread per (radius, task): first bin | last bin (closed-form index on the logarithmic convolution
+//            grid, corrected against the tabulated edges) | the integrand at the edge nodes g* = h | g* = 1-h that
+//            int_edge needs (once per radius instead of once per edge bin).
+//   main     BIN-STATIONARY, no block barrier.  The sub-batch's bin range is cut into tiles of 15 bins anchored at
+//            the bin where the quadrature rule changes (E = 0.95, src/Relprofile.cpp:633), so a tile is all
+//            midpoint-rule or all Romberg.  A warp owns a tile; its two half-warps work on two consecutive radii at
+//            a time, lane = bin EDGE (16 edges = 15 bins), and walk the radii in ascending order with the bin's sum in
+//            a register -> the reference's summation order, no atomics, no contribution buffer.
+//              midpoint tiles: one evaluation of the integrand per bin.
+//              Romberg tiles:  the integrand at the bin edges is evaluated once per edge and shared by the two
+//                              neighbouring bins through a shuffle (the reference evaluates it twice); levels 1-2
+//                              (three more abscissae) for all lanes; the bins that have not converged by then (the
+//                              horns, ~13 %) are compacted across the warp: level 3 = 4 new abscissae of 8 bins per
+//                              pass, level 4 = 8 abscissae of 4 bins, summed by xor-butterflies and pulled back by
+//                              the owning lane, which keeps the tableau.  Levels 5-6 (~1e-4 of the bins) are
+//                              finished by the owning lane.
+//            The zone's row in HBM is the accumulator between sub-batches (read once, written once per sub-batch).
 //
 // Arithmetic.  The two branches k = 0, 1 of the transfer function share everything but the interpolated
 // trff value, so one evaluation of the integrand returns both (the reference calls relb_func twice).
@@ -35,6 +40,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdint>
 
 #include "common.h"
 #include "devutil.cuh"
@@ -42,24 +48,75 @@
 
 namespace rx {
 
-struct RelbCtx {
-  double gmin, gmax, del_g;
-  double scale;          // emis / (gmax - gmin)
-  const double2 *trff;   // [NG] {branch 0, branch 1} of this radius (global, L1-resident)
-  const double2 *cosne;
-  int limb;
-};
-
 #define GS_C ((1.0 - 2 * GFAC_H) / (NG - 1))
 #define GS_INVC ((NG - 1) / (1.0 - 2 * GFAC_H))
-// An FP64 immediate whose low word is not zero costs two moves at every use (a tenth of this kernel's instructions
-// were such moves); as __constant__ data the same values ride in the instruction as constant-bank operands.
+// An FP64 immediate whose low word is not zero costs two moves at every use; as __constant__ data the same values
+// ride in the instruction as constant-bank operands.
 struct LnConst {
   double h, one_m_h, gs_c, gs_invc, prec, e95, sqrt_h;
   double inv[7];   // 1 / (4^ii - 1) of the Richardson step
 };
 __constant__ LnConst LK = {GFAC_H, 1.0 - GFAC_H, GS_C, GS_INVC, 0.02, 1.0 * 0.95, 0.0,
                            {0.0, 1.0 / 3.0, 1.0 / 15.0, 1.0 / 63.0, 1.0 / 255.0, 1.0 / 1023.0, 1.0 / 4095.0}};
+
+constexpr int LN_NT = 128;
+constexpr int LN_NW = LN_NT / 32;
+constexpr int LN_R = 16;         // radii per sub-batch
+constexpr int LN_ROWS = 10;      // table rows staged per sub-batch (a sub-batch is cut where its bracket would not fit)
+constexpr int LN_TB = 15;        // bins per tile (16 edges: one half warp)
+constexpr int LN_FS = NG + 1;    // row stride of the fine rows in shared memory (padded: consecutive radii on different banks)
+
+struct LnRad {
+  double gmin, del_g, dgm;       // dgm = gmax - gmin
+  double scale;                  // emis / (gmax - gmin)
+  double weight;
+  double nlo, nhi;               // `norm` of int_edge (src/Relprofile.cpp:585-621) at g* = h and g* = 1-h
+  double ehlo, ehhi;             // gstar2ener(h), gstar2ener(1-h)
+  int ielo, iehi, gi, pad;
+};
+struct LnSmem {
+  double2 rows[LN_ROWS][NG];     // bulk-copy destination
+  double2 fine[LN_R][LN_FS];     // {branch 0, branch 1} of the sub-batch's radii
+  LnRad rad[LN_R + 2];
+  unsigned long long mbar;
+  int slot[LN_NW][8];
+  int jlo, jhi, zlo, zhi, zold_lo, zold_hi, j95;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ double2 lds_d2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+// ---- bulk asynchronous copy (TMA unit), completion on an mbarrier
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy reads of dst are done (after a barrier)
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t phase) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(a), "r"(phase) : "memory");
+  } while (!done);
+}
+
+struct RelbCtx {
+  double gmin, del_g;
+  double scale;          // emis / (gmax - gmin)
+  uint32_t row;          // shared-memory address of this radius' fine row: [NG] {branch 0, branch 1}
+  const double2 *cosne;  // global; only for limb != 0
+  int limb;
+};
 
 // limb darkening / brightening factor of relb_func (src/Relprofile.cpp:508-518); out of line: the default
 // law is isotropic and the logarithm would otherwise be replicated into every copy of the integrand
@@ -79,7 +136,7 @@ __device__ __forceinline__ void relb2(double eg, const RelbCtx &c, double &v0, d
   ind = ind < 0 ? 0 : (ind > NG - 2 ? NG - 2 : ind);
   const double inte = (egstar - (LK.h + LK.gs_c * (double) ind)) * LK.gs_invc;
   const double inte1 = 1.0 - inte;
-  const double2 t0 = __ldg(c.trff + ind), t1 = __ldg(c.trff + ind + 1);
+  const double2 t0 = lds_d2(c.row + ind * 16), t1 = lds_d2(c.row + ind * 16 + 16);
   const double common = (eg * eg * eg) * rsqrt(egstar - egstar * egstar) * c.scale;
   v0 = common * (inte * t0.x + inte1 * t1.x);   // (the reference's weights: inte on node ind, 1-inte on ind+1)
   v1 = common * (inte * t0.y + inte1 * t1.y);
@@ -97,8 +154,6 @@ __device__ __forceinline__ bool not_converged(double t_new, double t_old) {
   if (t_new == 0.0) return d > 0.0;   // x/0 = inf > prec;  0/0 = NaN compares false
   return false;                        // negative (or NaN) quotient ends the loop
 }
-
-__device__ __forceinline__ double gstar2ener(double g, double gmin, double gmax) { return (g * (gmax - gmin) + gmin) * 1.0; }
 
 // Richardson step of the Romberg tableau, t[ii] = (4^ii t[ii-1] - tprev[ii-1]) / (4^ii - 1), with the
 // divisions replaced by the tabulated reciprocals
@@ -143,74 +198,16 @@ __device__ int line_index(const LineGrid &G, double val, double z, double lineE)
   return klo;
 }
 
-constexpr int LN_NT = 128;
-constexpr int LN_BUF = 1024;     // contribution slots (items) per sub-batch
-constexpr int LN_MAXR = 32;      // radii per sub-batch: one lane each in the set-up warp
-constexpr int LN_MAXDEF = 256;   // work list of the deep Romberg bins
-struct LnRad {
-  double gmin, gmax, del_g, scale, weight;
-  double nlo, nhi;               // `norm` of int_edge (src/Relprofile.cpp:585-621) at g* = h and g* = 1-h
-  int ielo, iehi, off, gi;
-};
-struct LnSmem {
-  double contrib[LN_BUF];
-  double def_a[LN_MAXDEF], def_b[LN_MAXDEF];      // work list of phase 2: interval still to integrate
-  double def_f[LN_MAXDEF][2];                     // ... and the integrand at its lower end (both branches)
-  LnRad rad[LN_MAXR + 1];
-  unsigned short rlist[LN_BUF];                   // items that take the Romberg path
-  unsigned short def_item[LN_MAXDEF];
-  unsigned char item_rad[LN_BUF];                 // sub-batch radius of every item (bit 7: retry flag)
-  int nrad, nrom, ndef, overflow, cursor, jlo, jhi, resume;   // resume: first bin still to do of radius `cursor` (-1 = all)
-  int zjlo, zjhi;
-};
-
-__device__ __forceinline__ void ln_ctx(const LnRad &lr, const double2 *g_trff, const double2 *g_cosne, int limb, RelbCtx &c) {
-  c.gmin = lr.gmin; c.gmax = lr.gmax; c.del_g = lr.del_g; c.scale = lr.scale;
-  c.trff = g_trff + (size_t) lr.gi * NG; c.cosne = g_cosne + (size_t) lr.gi * NG; c.limb = limb;
-}
-
 // int_edge (src/Relprofile.cpp:585-621) with the integrand at the edge node already summed into `norm`
-__device__ __forceinline__ double edge_term(double blo, double bhi, double norm, double gmin, double gmax) {
+__device__ __forceinline__ double edge_term(double blo, double bhi, double norm, double dgm) {
   double lo, hi;
   if (blo <= 0.5) { lo = blo; hi = bhi; }
   else { lo = 1.0 - bhi; hi = 1.0 - blo; }
-  return 2 * norm * (sqrt(hi) - sqrt(lo)) * 1.0 * (gmax - gmin);
+  return 2 * norm * (sqrt(hi) - sqrt(lo)) * 1.0 * dgm;
 }
 
-// The decision part of integ_relline_bin (src/Relprofile.cpp:650-726): the analytic edge terms of the bin
-// (returned in flu when EDGES) and the interval [rlo, rhi] left for quadrature.  Returns 0: nothing left,
-// 1: midpoint rule, 2: Romberg (int_romb, :628-647).
-template <bool EDGES>
-__device__ __forceinline__ int bin_split(const LnRad &lr, double rlo0, double rhi0, double &rlo, double &rhi, double &flu) {
-  flu = 0.0;
-  double gblo = (rlo0 / 1.0 - lr.gmin) * lr.del_g;
-  if (gblo < 0.0) gblo = 0.0; else if (gblo > 1.0) gblo = 1.0;
-  double gbhi = (rhi0 / 1.0 - lr.gmin) * lr.del_g;
-  if (gbhi < 0.0) gbhi = 0.0; else if (gbhi > 1.0) gbhi = 1.0;
-  if (gbhi == 0) return 0;
-  rlo = rlo0; rhi = rhi0;
-  const bool at_lo = gblo <= LK.h, at_hi = gbhi >= LK.one_m_h;
-  double lo_hhi = LK.h, hi_hlo = LK.one_m_h;
-  if (at_lo) {
-    rlo = gstar2ener(LK.h, lr.gmin, lr.gmax);
-    if (gbhi <= LK.h) { lo_hhi = gbhi; rlo = -1.0; }
-  }
-  if (at_hi) {
-    rhi = gstar2ener(LK.one_m_h, lr.gmin, lr.gmax);
-    if (gblo >= LK.one_m_h) { hi_hlo = gblo; rhi = -1.0; }
-  }
-  if (EDGES && (at_lo || at_hi)) {   // lower-edge term first, like the reference; one call unless the bin spans both edges
-    const double eb_lo = at_lo ? gblo : hi_hlo, eb_hi = at_lo ? lo_hhi : gbhi, e_norm = at_lo ? lr.nlo : lr.nhi;
-    flu = flu + edge_term(eb_lo, eb_hi, e_norm, lr.gmin, lr.gmax);
-    if (at_lo && at_hi) flu = flu + edge_term(hi_hlo, gbhi, lr.nhi, lr.gmin, lr.gmax);
-  }
-  if ((rhi >= 0) && (rlo >= 0)) return (rlo >= LK.e95) ? 2 : 1;
-  return 0;
-}
-
-// Romberg levels 5 and 6 of one bin (rare: a fraction of a per cent of the listed bins), by the thread that owns
-// the bin's tableau.  The new abscissae of a level are summed in ascending order like the reference's loop.
-// Everything is passed by value so that the caller's tableau stays in registers.
+// Romberg levels 5 and 6 of one bin (rare: ~1e-4 of the Romberg bins), by the lane that owns the bin's tableau.
+// The new abscissae of a level are summed in ascending order like the reference's loop.
 struct DeepIn {
   double tp[2][5];   // tableau rows after level 4
   double res[2];
@@ -251,15 +248,78 @@ __device__ __noinline__ double romberg_deep(double a, double pas, RelbCtx c, Dee
   return res[0] + res[1];
 }
 
-// 9 resident CTAs per SM (56 registers, 36 warps): the kernel is latency-bound on its dependent FP64 chains, and the
-// extra warps are worth more than the few spilled values (measured 11.8 ms at 6 CTAs / 80 registers, 10.0 ms at 8 / 64,
-// 9.4 ms at 9 / 56; at 10 / 48 the spills win: 10.4 ms)
-template <int GRID_MODE>
-__global__ void __launch_bounds__(LN_NT, 9) k_line(const VPar *__restrict__ vps, DevTables T, Scratch S, LineGrid G,
-                                                   int ne_stride, int nz_stride) {
-  __shared__ __align__(16) LnSmem sm;
+__device__ __forceinline__ void ln_ctx(const LnSmem &sm, int r, const double2 *g_cosne, int limb, RelbCtx &c) {
+  const LnRad &lr = sm.rad[r];
+  c.gmin = lr.gmin; c.del_g = lr.del_g; c.scale = lr.scale;
+  c.row = smem_u32(&sm.fine[r][0]);
+  c.cosne = g_cosne + (size_t) lr.gi * NG; c.limb = limb;
+}
+
+// One Romberg level L (3 or 4) for the lanes of the warp that still need it (need == L), compacted: every such bin
+// gets NP = 2^(L-1) lanes, one per new abscissa a + (2p+1) pas / 2^L; an xor-butterfly sums them, the owning lane pulls
+// the two branch sums and advances its tableau (src/Relprofile.cpp:553-576).
+template <int L>
+__device__ __forceinline__ void romberg_level(const LnSmem &sm, int *slot, int lane, int rsel, const double2 *g_cosne, int limb,
+                                              double a, double pas, int &need, double (&sum)[2], double (&tp)[2][5],
+                                              double (&res)[2], bool (&done)[2]) {
   const unsigned FULL = 0xffffffffu;
-  const int v = blockIdx.y, z = blockIdx.x, t = threadIdx.x;
+  constexpr int NP = 1 << (L - 1), NB = 32 / NP;
+  unsigned pend = __ballot_sync(FULL, need == L);
+  while (pend) {
+    const int rank = __popc(pend & ((1u << lane) - 1));
+    const bool mine = (need == L) && rank < NB;
+    if (mine) slot[rank] = lane;
+    __syncwarp();
+    const int nb = min(NB, __popc(pend));
+    const int q = lane / NP, p = lane % NP;
+    const int src = (q < nb) ? slot[q] : lane;
+    __syncwarp();
+    const double a_s = __shfl_sync(FULL, a, src), pas_s = __shfl_sync(FULL, pas, src);
+    const int r_s = __shfl_sync(FULL, rsel, src);
+    RelbCtx c;
+    ln_ctx(sm, r_s, g_cosne, limb, c);
+    const double pasL = pas_s * (1.0 / (1 << L));
+    double w0, w1;
+    relb2(a_s + pasL * (double) (2 * p + 1), c, w0, w1);
+#pragma unroll
+    for (int o = 1; o < NP; o <<= 1) {
+      w0 += __shfl_xor_sync(FULL, w0, o);
+      w1 += __shfl_xor_sync(FULL, w1, o);
+    }
+    const int from = mine ? rank * NP : lane;
+    const double s0 = __shfl_sync(FULL, w0, from), s1 = __shfl_sync(FULL, w1, from);
+    if (mine) {
+      const double pasn = pas * (1.0 / (1 << L));
+      bool more = false;
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        sum[k] += k ? s1 : s0;
+        if (!done[k]) {
+          double cur[L + 1];
+          cur[0] = sum[k] * pasn;
+#pragma unroll
+          for (int ii = 1; ii <= L; ii++) cur[ii] = richardson(ii, cur[ii - 1], tp[k][ii - 1]);
+          if (!not_converged(cur[L], res[k])) done[k] = true;
+          res[k] = cur[L];
+#pragma unroll
+          for (int ii = 0; ii <= L; ii++) tp[k][ii] = cur[ii];
+          more |= !done[k];
+        }
+      }
+      need = more ? L + 1 : 0;
+    }
+    pend &= ~__ballot_sync(FULL, mine);
+  }
+}
+
+// 8 resident CTAs per SM (64 registers, 32 warps)
+template <int GRID_MODE>
+__global__ void __launch_bounds__(LN_NT, 8) k_line(const VPar *__restrict__ vps, DevTables T, Scratch S, LineGrid G,
+                                                   int ne_stride, int nz_stride) {
+  __shared__ __align__(128) LnSmem sm;
+  const unsigned FULL = 0xffffffffu;
+  const int v = blockIdx.x, z = blockIdx.y, t = threadIdx.x;
+  const int lane = t & 31, warp = t >> 5;
   if (S.status[v] != ST_OK) return;
   if (S.reuse && S.reuse[v]) return;   // the zone profiles of the previous run stand
   const VPar &vp = vps[v];
@@ -276,347 +336,257 @@ __global__ void __launch_bounds__(LN_NT, 9) k_line(const VPar *__restrict__ vps,
   const int ia = S.zfirst[(size_t) v * (NZMAX + 1) + z + 1], ib = S.zfirst[(size_t) v * (NZMAX + 1) + z];
   double *flux = S.relflux + ((size_t) v * nz_stride + z) * ne_stride;   // doubles as the zone accumulator
   const double *g_re = S.re + (size_t) v * NR;
-  const double2 *g_trff = reinterpret_cast<const double2 *>(S.trff) + (size_t) v * NR * NG;
+  const int *g_it = S.it + (size_t) v * NR;
+  const double2 *g_rows = reinterpret_cast<const double2 *>(S.relrow) + (size_t) v * REL_NRT * NG * 2;   // trff plane
   const double2 *g_cosne = reinterpret_cast<const double2 *>(S.cosne) + (size_t) v * NR * NG;
-  if (t == 0) { sm.cursor = ia; sm.resume = -1; sm.zjlo = n_ener; sm.zjhi = -1; }
+  if (t == 0) {
+    mbar_init(&sm.mbar, 1);
+    sm.zlo = n_ener; sm.zhi = -1;
+    // first bin of the Romberg rule: bins j >= j95 have E_lo >= 0.95 (src/Relprofile.cpp:633); tiles are anchored there
+    const int k = line_index<GRID_MODE>(G, LK.e95, zred, lineE);
+    sm.j95 = (line_edge(egrid, k, grid_mode, zred, lineE) >= LK.e95) ? k : k + 1;
+  }
   __syncthreads();
+  const int j95 = sm.j95;
 
-  while (true) {
-    const int cur = sm.cursor;
-    if (cur >= ib) break;
-    const int resume = sm.resume;
-    const int zjlo_old = sm.zjlo, zjhi_old = sm.zjhi;
-    // ---- sub-batch set-up: radius r = lane, one warp per task (first bin | last bin | edge norm at g* = h | at 1-h)
+  uint32_t phase = 0;
+  for (int cur = ia; cur < ib;) {
+    // ---- the sub-batch: as many radii as fit LN_R and whose table bracket fits LN_ROWS (every warp computes the same n)
+    int n, it0;
     {
-      const int r = t & 31, task = t >> 5;
-      const int i = cur + r;
+      const int i = min(cur + (lane & (LN_R - 1)), ib - 1);
+      const int it = g_it[i];
+      it0 = __shfl_sync(FULL, it, 0);
+      const unsigned ok = __ballot_sync(FULL, (lane < LN_R) && (cur + lane < ib) && (it + 2 - it0 <= LN_ROWS));
+      n = __ffs(~ok) - 1;   // ok is a prefix (it[] is non-decreasing); lane 0 always fits
+      const int it1 = __shfl_sync(FULL, it, n - 1);
+      if (t == 0) bulk_load(&sm.rows[0][0], g_rows + (size_t) it0 * NG, (uint32_t) (it1 + 2 - it0) * NG * 16, &sm.mbar);
+    }
+    const bool last_batch = cur + n >= ib;
+    // ---- set-up, part 1 (while the rows are in flight): thread = (radius, task 0: record + first bin | 1: last bin)
+    if (t < 2 * LN_R) {
+      const int r = t & (LN_R - 1), task = t / LN_R;
       LnRad &lr = sm.rad[r];
-      if (i < ib) {
+      const int i = cur + r;
+      if (r < n) {
         const double gmin = S.gmin[(size_t) v * NR + i], gmax = S.gmax[(size_t) v * NR + i];
-        const double del_g = 1. / (gmax - gmin);
-        const double scale = del_g * S.emis[(size_t) v * NR + i];
         const bool on_grid = (gmax > e_first) && (gmin < e_last);  // src/Relprofile.cpp:863-878
         if (task == 0) {
-          lr.gmin = gmin; lr.gmax = gmax; lr.del_g = del_g; lr.scale = scale;
+          const double del_g = 1. / (gmax - gmin);
+          lr.gmin = gmin; lr.del_g = del_g; lr.dgm = gmax - gmin;
+          lr.scale = del_g * S.emis[(size_t) v * NR + i];
           lr.weight = trapez_single(g_re, i, NR) / 2;
+          lr.ehlo = (GFAC_H * (gmax - gmin) + gmin) * 1.0;
+          lr.ehhi = ((1.0 - GFAC_H) * (gmax - gmin) + gmin) * 1.0;
           lr.gi = i;
-          int ielo = 0;
-          if (on_grid) {
-            ielo = line_index<GRID_MODE>(G, gmin < e_first ? e_first : gmin, zred, lineE);
-            if (r == 0 && resume >= 0) ielo = resume;   // rest of a radius wider than the buffer
-          }
-          lr.ielo = ielo;
-        } else if (task == 1) {
-          lr.iehi = on_grid ? line_index<GRID_MODE>(G, gmax > e_last ? e_last : gmax, zred, lineE) : -1;
+          lr.ielo = on_grid ? line_index<GRID_MODE>(G, gmin < e_first ? e_first : gmin, zred, lineE) : n_ener;
         } else {
-          RelbCtx c;
-          c.gmin = gmin; c.gmax = gmax; c.del_g = del_g; c.scale = scale;
-          c.trff = g_trff + (size_t) i * NG; c.cosne = g_cosne + (size_t) i * NG; c.limb = limb;
-          double n0, n1;
-          relb2(gstar2ener(task == 2 ? GFAC_H : 1.0 - GFAC_H, gmin, gmax), c, n0, n1);
-          double norm = 0.0;
-          norm = norm + n0;
-          norm = norm + n1;
-          norm = norm * sqrt(GFAC_H);
-          if (task == 2) lr.nlo = norm; else lr.nhi = norm;
+          lr.iehi = on_grid ? line_index<GRID_MODE>(G, gmax > e_last ? e_last : gmax, zred, lineE) : -1;
         }
-      } else if (task == 0) {
-        lr.gi = i; lr.ielo = 0;
-      } else if (task == 1) {
+      } else if (task == 0) {   // padding of an odd sub-batch: a radius without bins
+        lr.gmin = 0.0; lr.del_g = 1.0; lr.dgm = 1.0; lr.scale = 0.0; lr.weight = 0.0; lr.ehlo = 0.0; lr.ehhi = 1.0;
+        lr.nlo = 0.0; lr.nhi = 0.0; lr.gi = cur; lr.ielo = n_ener;
+      } else {
         lr.iehi = -1;
       }
     }
-    __syncthreads();
-    if (t >= 32) {
-      // while warp 0 scans, the other warps request the transfer-function rows of the sub-batch's radii (640 bytes =
-      // five lines each): the integrand's table look-ups (data-dependent, one L2 round trip each) then hit in L1
-      const int nr = min(ib - cur, LN_MAXR);
-      for (int q = t - 32; q < nr * 5; q += LN_NT - 32)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(g_trff + (size_t) cur * NG) + (size_t) q * 128));
+    // ---- radial interpolation of the staged rows onto the sub-batch's radii (src/Relprofile.cpp:280-293)
+    mbar_wait(&sm.mbar, phase);
+    phase ^= 1;
+    for (int q = t; q < n * NG; q += LN_NT) {
+      const int r = q / NG, jg = q - r * NG;
+      const int i = cur + r;
+      const int it = g_it[i] - it0;
+      const double fr = S.fr[(size_t) v * NR + i];
+      const double2 hi = sm.rows[it][jg], lo = sm.rows[it + 1][jg];   // row `it`: larger radius
+      double2 tr;
+      tr.x = __dadd_rn(__dmul_rn(fr, hi.x), __dmul_rn(1.0 - fr, lo.x));   // lin1d(fr, lo, hi), uncontracted like k_fine's
+      tr.y = __dadd_rn(__dmul_rn(fr, hi.y), __dmul_rn(1.0 - fr, lo.y));
+      sm.fine[r][jg] = tr;
     }
-    if (t < 32) {   // offsets of the radii that fit the buffer: warp scan over the bin counts
-      const int r = t;
-      const bool valid = cur + r < ib;
-      int ielo = sm.rad[r].ielo, iehi = sm.rad[r].iehi;
-      int w = valid ? max(iehi - ielo + 1, 0) : 0;
-      int next_resume = -1;
-      if (r == 0 && w > LN_BUF) {                       // a single radius wider than the buffer: take a piece
-        w = LN_BUF;
-        next_resume = ielo + w;
-        iehi = next_resume - 1;
-        sm.rad[0].iehi = iehi;
+    __syncthreads();
+    // ---- set-up, part 2: the integrand at the two edge nodes (threads 0..2 LN_R-1), the sub-batch's bin range (warp 2)
+    if (t < 2 * LN_R) {
+      const int r = t & (LN_R - 1), task = t / LN_R;
+      if (r < n) {
+        RelbCtx c;
+        ln_ctx(sm, r, g_cosne, limb, c);
+        const LnRad &lr = sm.rad[r];
+        double n0, n1;
+        relb2(task == 0 ? lr.ehlo : lr.ehhi, c, n0, n1);
+        double norm = 0.0;
+        norm = norm + n0;
+        norm = norm + n1;
+        norm = norm * sqrt(GFAC_H);
+        if (task == 0) sm.rad[r].nlo = norm; else sm.rad[r].nhi = norm;
       }
-      next_resume = __shfl_sync(FULL, next_resume, 0);
-      int cum = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int up = __shfl_up_sync(FULL, cum, o);
-        if (r >= o) cum += up;
-      }
-      const unsigned fits = __ballot_sync(FULL, valid && cum <= LN_BUF && (next_resume < 0 || r == 0));
-      const int n = __popc(fits);                       // `fits` is a prefix: cum is monotone, valid a prefix
-      const bool mine = r < n;
-      int jlo = (mine && w > 0) ? ielo : n_ener, jhi = (mine && w > 0) ? iehi : -1;
+    } else if (warp == 2) {
+      const bool valid = lane < n;
+      const int ielo = valid ? sm.rad[lane & (LN_R - 1)].ielo : n_ener, iehi = valid ? sm.rad[lane & (LN_R - 1)].iehi : -1;
+      int jlo = (iehi >= ielo) ? ielo : n_ener, jhi = (iehi >= ielo) ? iehi : -1;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         jlo = min(jlo, __shfl_xor_sync(FULL, jlo, o));
         jhi = max(jhi, __shfl_xor_sync(FULL, jhi, o));
       }
-      if (mine) sm.rad[r].off = cum - w;
-      if (r == n - 1) sm.rad[n].off = cum;
-      if (r == 0) {
-        sm.nrad = n;
-        sm.nrom = 0;
-        sm.ndef = 0;
-        sm.overflow = 0;
-        sm.jlo = jlo;
-        sm.jhi = jhi;
-        sm.zjlo = min(zjlo_old, jlo);
-        sm.zjhi = max(zjhi_old, jhi);
-        sm.resume = next_resume;
-        sm.cursor = (next_resume >= 0) ? cur + n - 1 : cur + n;
-      }
-    }
-    __syncthreads();
-    const int nrad = sm.nrad;
-    const int nitems = sm.rad[nrad].off;
-    for (int r = t >> 5; r < nrad; r += LN_NT / 32)   // item -> radius map, one warp per radius
-      for (int q = sm.rad[r].off + (t & 31); q < sm.rad[r + 1].off; q += 32) sm.item_rad[q] = (unsigned char) r;
-    __syncthreads();
-    // ---- pass A: one thread per item.  Edge terms and midpoint bins are finished here; the bins that take the
-    // Romberg path are gathered in a dense list (order irrelevant: every bin's value is computed on its own).
-    for (int base = 0; base < nitems; base += LN_NT) {
-      const int item = base + t;
-      int cls = 0;
-      if (item < nitems) {
-        const LnRad &lr = sm.rad[sm.item_rad[item]];
-        const int j = lr.ielo + (item - lr.off);
-        const double elo = line_edge(egrid, j, grid_mode, zred, lineE), ehi = line_edge(egrid, j + 1, grid_mode, zred, lineE);
-        double rlo, rhi, flu;
-        cls = bin_split<true>(lr, elo, ehi, rlo, rhi, flu);
-        if (cls == 1) {
-          RelbCtx c;
-          ln_ctx(lr, g_trff, g_cosne, limb, c);
-          double m0, m1;
-          relb2((rhi + rlo) / 2.0, c, m0, m1);
-          double f2 = 0.0;
-          f2 += m0 * (rhi - rlo);
-          f2 += m1 * (rhi - rlo);
-          flu = flu + f2;
+      if (lane == 0) {
+        const int zlo = sm.zlo, zhi = sm.zhi;
+        sm.zold_lo = zlo; sm.zold_hi = zhi;
+        if (jhi >= jlo && zhi >= zlo) {   // close a gap between the zone's range so far and this sub-batch's
+          if (zhi < jlo) jlo = zhi + 1;
+          if (zlo > jhi) jhi = zlo - 1;
         }
-        sm.contrib[item] = flu;
-      }
-      const unsigned rom = __ballot_sync(FULL, cls == 2);
-      if (rom) {
-        int pos = 0;
-        if ((t & 31) == 0) pos = atomicAdd(&sm.nrom, __popc(rom));
-        pos = __shfl_sync(FULL, pos, 0);
-        if (cls == 2) sm.rlist[pos + __popc(rom & ((1u << (t & 31)) - 1))] = (unsigned short) item;
+        const int nzlo = min(zlo, jlo), nzhi = max(zhi, jhi);
+        sm.zlo = nzlo; sm.zhi = nzhi;
+        // the last sub-batch visits the zone's whole range: it finishes the row (division by the bin energy)
+        sm.jlo = last_batch ? nzlo : jlo;
+        sm.jhi = last_batch ? nzhi : jhi;
       }
     }
     __syncthreads();
-    const int nrom = sm.nrom;
-    for (int round = 0;; round++) {
-      // ---- pass B: one thread per Romberg bin, two halvings (five abscissae) evaluated unconditionally.  A bin that
-      // has not converged by then (the horns of the profile) goes on the work list of phase 2; if the list is
-      // full the bin is flagged (bit 7 of item_rad) and retried after phase 2 has drained the list, so the
-      // result never depends on the order in which threads reach the list.
-      for (int base = 0; base < nrom; base += LN_NT) {
-        const int q = base + t;
-        bool defer = false;
-        int item = 0;
-        double ra = 0.0, rb = 0.0, fa0 = 0.0, fa1 = 0.0;
-        if (q < nrom) {
-          item = sm.rlist[q];
-          const int ir = sm.item_rad[item];
-          if (round == 0 || (ir & 0x80)) {
-            const LnRad &lr = sm.rad[ir & 0x7f];
-            const int j = lr.ielo + (item - lr.off);
-            const double elo = line_edge(egrid, j, grid_mode, zred, lineE), ehi = line_edge(egrid, j + 1, grid_mode, zred, lineE);
-            double flu;
-            bin_split<false>(lr, elo, ehi, ra, rb, flu);
+
+    // ---- main loop: warp = tile of 15 bins, half warp = radius, lane = bin edge
+    {
+      const int jlo = sm.jlo, jhi = sm.jhi, zold_lo = sm.zold_lo, zold_hi = sm.zold_hi;
+      const int half = lane >> 4, hl = lane & 15;
+      int *slot = sm.slot[warp];
+      if (jhi >= jlo) {
+        // tiles anchored at j95: tile k covers bins [j95 + k LN_TB, j95 + (k+1) LN_TB)
+        const int k_lo = (jlo - j95 >= 0) ? (jlo - j95) / LN_TB : -((j95 - jlo + LN_TB - 1) / LN_TB);
+        const int k_hi = (jhi - j95 >= 0) ? (jhi - j95) / LN_TB : -((j95 - jhi + LN_TB - 1) / LN_TB);
+        const int npair = (n + 1) >> 1;
+        for (int k = k_lo + warp; k <= k_hi; k += LN_NW) {
+          const int j = j95 + k * LN_TB + hl;                     // this lane's edge; its bin if hl < 15
+          const double Ea = line_edge(egrid, min(max(j, 0), n_ener), grid_mode, zred, lineE);
+          const double Eb = line_edge(egrid, min(max(j + 1, 0), n_ener), grid_mode, zred, lineE);
+          const bool binlane = (hl < LN_TB) && (j >= jlo) && (j <= jhi);
+          const bool was = binlane && (j >= zold_lo) && (j <= zold_hi);
+          double acc = was ? flux[j] : 0.0;
+          for (int pr = 0; pr < npair; pr++) {
+            const int rsel = 2 * pr + half;
+            const LnRad &lr = sm.rad[rsel];
+            const bool in = binlane && (j >= lr.ielo) && (j <= lr.iehi);
+            if (!__any_sync(FULL, in)) continue;
+            // ---- the decision part of integ_relline_bin (src/Relprofile.cpp:650-726)
+            const double gmin = lr.gmin, del_g = lr.del_g;
+            double ga = (Ea / 1.0 - gmin) * del_g;
+            if (ga < 0.0) ga = 0.0; else if (ga > 1.0) ga = 1.0;
+            double gb = (Eb / 1.0 - gmin) * del_g;
+            if (gb < 0.0) gb = 0.0; else if (gb > 1.0) gb = 1.0;
+            const bool live = in && !(gb == 0);
+            const bool a_lo = ga <= LK.h, a_hi = ga >= LK.one_m_h, b_lo = gb <= LK.h, b_hi = gb >= LK.one_m_h;
+            // abscissa of this lane's edge: the edge itself, or the end of the analytic edge interval it lies in
+            const double Xa = a_lo ? lr.ehlo : (a_hi ? lr.ehhi : Ea);
+            const double Xb = b_lo ? lr.ehlo : (b_hi ? lr.ehhi : Eb);
+            const bool quad = live && !b_lo && !a_hi;
+            double flu = 0.0;
+            if (live && (a_lo || b_hi)) {   // lower-edge term first, like the reference
+              const double dgm = lr.dgm;
+              if (a_lo) flu = flu + edge_term(ga, b_lo ? gb : LK.h, lr.nlo, dgm);
+              if (b_hi) flu = flu + edge_term(a_hi ? ga : LK.one_m_h, gb, lr.nhi, dgm);
+            }
+            const bool romb = quad && (Xa >= LK.e95);
+            const bool midp = quad && !romb;
             RelbCtx c;
-            ln_ctx(lr, g_trff, g_cosne, limb, c);
-            // Romberg on [ra, rb] for both branches (src/Relprofile.cpp:524-579), levels 0..2
-            const double pas = rb - ra, pas1 = pas / 2.0, pas2 = pas1 / 2.0;
-            // abscissae in the order a, b, a+pas/4, a+pas/2, a+3pas/4: the level-2 trapezoid sum is built as
-            // ((ta + f(q1)) + f(mid)) + f(q3), the reference's ascending order.  Rolled: one copy of the integrand.
-            double ta[2] = {0.0, 0.0}, fm[2] = {0.0, 0.0}, x2[2] = {0.0, 0.0};
-#pragma unroll 1
-            for (int pt = 0; pt < 5; pt++) {
-              const double eg = (pt == 0) ? ra : (pt == 1) ? rb : (pt == 2) ? ra + pas2 * 1 : (pt == 3) ? ra + pas1 * 1 : ra + pas2 * 3;
-              double w0, w1;
-              relb2(eg, c, w0, w1);
-              if (pt == 0) { fa0 = w0; fa1 = w1; }
-              else if (pt == 1) { ta[0] = (fa0 + w0) / 2.0; ta[1] = (fa1 + w1) / 2.0; x2[0] = ta[0]; x2[1] = ta[1]; }
-              else {
-                if (pt == 3) { fm[0] = w0; fm[1] = w1; }
-                x2[0] += w0;
-                x2[1] += w1;
+            c.gmin = gmin; c.del_g = del_g; c.scale = lr.scale;
+            c.row = smem_u32(&sm.fine[rsel][0]);
+            c.cosne = g_cosne + (size_t) lr.gi * NG; c.limb = limb;
+            if (__any_sync(FULL, midp)) {   // midpoint rule (int_romb, :628-647, lo < 0.95)
+              double m0, m1;
+              relb2((Xb + Xa) / 2.0, c, m0, m1);
+              if (midp) {
+                double f2 = 0.0;
+                f2 += m0 * (Xb - Xa);
+                f2 += m1 * (Xb - Xa);
+                flu = flu + f2;
               }
             }
-            double rsum = 0.0;
+            if (__any_sync(FULL, romb)) {   // Romberg on [Xa, Xb] for both branches (src/Relprofile.cpp:524-579)
+              double fa0, fa1;
+              relb2(Xa, c, fa0, fa1);       // every lane: its own lower edge = the neighbour's upper edge
+              const double fb0 = __shfl_down_sync(FULL, fa0, 1, 16), fb1 = __shfl_down_sync(FULL, fa1, 1, 16);
+              const double pas = Xb - Xa, pas1 = pas / 2.0, pas2 = pas1 / 2.0;
+              double fm0, fm1;
+              relb2(Xa + pas1 * 1, c, fm0, fm1);
+              double sum[2], tp[2][5], res[2];
+              bool done[2];
+              bool lvl2 = false;
 #pragma unroll
-            for (int k = 0; k < 2; k++) {
-              const double t00 = ta[k] * pas;
-              const double t01 = (ta[k] + fm[k]) * pas1;
-              const double t10 = richardson(1, t01, t00);
-              double r = t10;
-              if (not_converged(t10, t00)) {
-                const double t02 = x2[k] * pas2;
-                const double t11 = richardson(1, t02, t01);
-                const double t20 = richardson(2, t11, t10);
-                defer |= not_converged(t20, t10);
-                r = t20;
+              for (int kk = 0; kk < 2; kk++) {
+                const double ta = ((kk ? fa1 : fa0) + (kk ? fb1 : fb0)) / 2.0;
+                sum[kk] = ta;
+                const double t00 = ta * pas;
+                const double t01 = (ta + (kk ? fm1 : fm0)) * pas1;
+                const double t10 = richardson(1, t01, t00);
+                tp[kk][0] = t01; tp[kk][1] = t10;
+                res[kk] = t10;
+                done[kk] = !not_converged(t10, t00);
+                lvl2 |= !done[kk];
               }
-              rsum += r;
-            }
-            sm.item_rad[item] = (unsigned char) (ir & 0x7f);
-            if (!defer) sm.contrib[item] = sm.contrib[item] + rsum;
-          }
-        }
-        const unsigned dm = __ballot_sync(FULL, defer);
-        if (dm) {
-          int pos = 0;
-          if ((t & 31) == 0) pos = atomicAdd(&sm.ndef, __popc(dm));
-          pos = __shfl_sync(FULL, pos, 0);
-          if (defer) {
-            const int d = pos + __popc(dm & ((1u << (t & 31)) - 1));
-            if (d < LN_MAXDEF) {
-              sm.def_item[d] = (unsigned short) item;
-              sm.def_a[d] = ra;
-              sm.def_b[d] = rb;
-              sm.def_f[d][0] = fa0;
-              sm.def_f[d][1] = fa1;
-            } else {
-              sm.item_rad[item] |= 0x80;
-              sm.overflow = 1;
-            }
-          }
-        }
-      }
-      __syncthreads();
-      // ---- phase 2: the listed bins at full Romberg depth.  One HALF WARP evaluates the 16 new abscissae of levels
-      // 1..4 of a bin in parallel (lane h takes point h+1 of 16; f(a) comes from pass B); one xor-butterfly
-      // gives the sums of the points that are new at each level.  The lane whose index equals the iteration
-      // keeps them, so after 16 iterations every lane owns one bin and all tableaus are built in parallel.
-      {
-        const int ndef = min(sm.ndef, LN_MAXDEF);
-        constexpr int NH = LN_NT / 16;
-        const int half = t >> 4, h = t & 15, hb = t & 16;
-        for (int g0 = 0; g0 < ndef; g0 += 16 * NH) {
-          const int nit = min(16, (ndef - g0 + NH - 1) / NH);
-          double kn[2][4], kfb[2];
+              int need = 0;
+              if (__any_sync(FULL, romb && lvl2)) {
+                double q0, q1, u0, u1;
+                relb2(Xa + pas2 * 1, c, q0, q1);
+                relb2(Xa + pas2 * 3, c, u0, u1);
 #pragma unroll
-          for (int k = 0; k < 2; k++) { kfb[k] = 0.0; kn[k][0] = kn[k][1] = kn[k][2] = kn[k][3] = 0.0; }
-          for (int it = 0; it < nit; it++) {
-            const int d = g0 + it * NH + half;
-            double v0 = 0.0, v1 = 0.0;
-            if (d < ndef) {
-              RelbCtx c;
-              ln_ctx(sm.rad[sm.item_rad[sm.def_item[d]] & 0x7f], g_trff, g_cosne, limb, c);
-              const double a = sm.def_a[d], b = sm.def_b[d];
-              const double pas4 = (b - a) / 16.0;
-              relb2(h == 15 ? b : a + pas4 * (h + 1), c, v0, v1);
-            }
+                for (int kk = 0; kk < 2; kk++) {
+                  // ((ta + f(q1)) + f(mid)) + f(q3): the reference's ascending order
+                  sum[kk] = ((sum[kk] + (kk ? q1 : q0)) + (kk ? fm1 : fm0)) + (kk ? u1 : u0);
+                  if (!done[kk]) {
+                    const double t02 = sum[kk] * pas2;
+                    const double t11 = richardson(1, t02, tp[kk][0]);
+                    const double t20 = richardson(2, t11, tp[kk][1]);
+                    done[kk] = !not_converged(t20, res[kk]);
+                    res[kk] = t20;
+                    tp[kk][0] = t02; tp[kk][1] = t11; tp[kk][2] = t20;
+                    if (!done[kk]) need = 3;
+                  }
+                }
+                if (!romb) need = 0;
+              }
+              if (__any_sync(FULL, need == 3)) {
+                romberg_level<3>(sm, slot, lane, rsel, g_cosne, limb, Xa, pas, need, sum, tp, res, done);
+                if (__any_sync(FULL, need == 4)) {
+                  romberg_level<4>(sm, slot, lane, rsel, g_cosne, limb, Xa, pas, need, sum, tp, res, done);
+                  if (need == 5) {
+                    DeepIn in;
 #pragma unroll
-            for (int k = 0; k < 2; k++) {
-              const double vv = k ? v1 : v0;
-              const double fb = __shfl_sync(FULL, vv, hb + 15);
-              // class sums over the interior points p = 1..15 (lane h = p - 1): p = 8; p = 4 mod 8; p = 2 mod 4; odd p
-              double x = (h == 15) ? 0.0 : vv;
-              const double n1 = __shfl_sync(FULL, x, hb + 7);
-              x += __shfl_xor_sync(FULL, x, 8);
-              const double n2 = __shfl_sync(FULL, x, hb + 3);
-              x += __shfl_xor_sync(FULL, x, 4);
-              const double n3 = __shfl_sync(FULL, x, hb + 1);
-              x += __shfl_xor_sync(FULL, x, 2);
-              const double n4 = __shfl_sync(FULL, x, hb + 0);
-              if (h == it) { kfb[k] = fb; kn[k][0] = n1; kn[k][1] = n2; kn[k][2] = n3; kn[k][3] = n4; }
-            }
-          }
-          const int d = g0 + h * NH + half;   // the bin this lane kept
-          if (h < nit && d < ndef) {
-            const int item = sm.def_item[d];
-            const double a = sm.def_a[d], b = sm.def_b[d];
-            const double pas = b - a;
-            double tprev[2][5], res[2] = {0.0, 0.0};
-            bool done[2] = {false, false};
+                    for (int kk = 0; kk < 2; kk++) {
 #pragma unroll
-            for (int k = 0; k < 2; k++) {
-              const double ta = (sm.def_f[d][k] + kfb[k]) / 2.0;
-              tprev[k][0] = ta * pas;
-              double last = tprev[k][0], pasn = pas, sum = ta;
-#pragma unroll
-              for (int n = 1; n <= 4; n++) {
-                pasn = pasn * 0.5;
-                sum += kn[k][n - 1];
-                if (!done[k]) {
-                  double cur[5];
-                  cur[0] = sum * pasn;
-#pragma unroll
-                  for (int ii = 1; ii <= 4; ii++) if (ii <= n) cur[ii] = richardson(ii, cur[ii - 1], tprev[k][ii - 1]);
-                  res[k] = cur[n];
-                  if (!not_converged(cur[n], last)) done[k] = true;
-                  last = cur[n];
-#pragma unroll
-                  for (int ii = 0; ii <= 4; ii++) if (ii <= n) tprev[k][ii] = cur[ii];
+                      for (int ii = 0; ii < 5; ii++) in.tp[kk][ii] = tp[kk][ii];
+                      in.res[kk] = res[kk];
+                      in.done[kk] = done[kk] ? 1 : 0;
+                    }
+                    const double rt = romberg_deep(Xa, pas, c, in);
+                    res[0] = rt; res[1] = 0.0;
+                  }
                 }
               }
-            }
-            double rtot = res[0] + res[1];
-            if (!(done[0] && done[1])) {
-              RelbCtx c;
-              ln_ctx(sm.rad[sm.item_rad[item] & 0x7f], g_trff, g_cosne, limb, c);
-              DeepIn in;
-#pragma unroll
-              for (int k = 0; k < 2; k++) {
-#pragma unroll
-                for (int ii = 0; ii < 5; ii++) in.tp[k][ii] = tprev[k][ii];
-                in.res[k] = res[k];
-                in.done[k] = done[k] ? 1 : 0;
+              if (romb) {
+                double rsum = 0.0;
+                rsum += res[0];
+                rsum += res[1];
+                flu = flu + rsum;
               }
-              rtot = romberg_deep(a, pas, c, in);
             }
-            sm.contrib[item] = sm.contrib[item] + rtot;
+            // ---- ascending-radius accumulation: the lower half's radius first, then the upper half's
+            const double own = live ? flu * lr.weight : 0.0;
+            const double oth = __shfl_xor_sync(FULL, own, 16);
+            acc = (acc + (half ? oth : own)) + (half ? own : oth);
+          }
+          if (binlane && half == 0) {
+            // only the bins this zone touched are written; the range travels with the row
+            flux[j] = last_batch ? acc / (0.5 * (Ea + Eb)) : acc;
           }
         }
       }
-      const int again = sm.overflow;
-      __syncthreads();
-      if (!again) break;
-      if (t == 0) { sm.ndef = 0; sm.overflow = 0; }
-      __syncthreads();
     }
-    // ---- phase 3: ordered accumulation (ascending radius index = the reference's loop order) into the zone's
-    // row.  Bins joining the zone's range start from zero; bins the sub-batch does not touch stay as they are.
-    {
-      const int jlo = sm.jlo, jhi = sm.jhi;
-      const int nlo = min(zjlo_old, jlo), nhi = max(zjhi_old, jhi);
-      for (int j = nlo + t; j <= nhi; j += LN_NT) {
-        const bool was = (j >= zjlo_old && j <= zjhi_old), now = (j >= jlo && j <= jhi);
-        if (was && !now) continue;
-        double a = was ? flux[j] : 0.0;
-        if (now) {
-          for (int r = 0; r < nrad; r++) {
-            const LnRad &lr = sm.rad[r];
-            if (j >= lr.ielo && j <= lr.iehi) a += sm.contrib[lr.off + (j - lr.ielo)] * lr.weight;
-          }
-        }
-        flux[j] = a;
-      }
-    }
-    __syncthreads();
+    cur += n;
+    if (cur < ib) __syncthreads();   // the shared-memory stage and the row in HBM are taken over by the next sub-batch
   }
-  // only the bins this zone touched are written; the range travels with the row
-  const int zjlo = sm.zjlo, zjhi = sm.zjhi;
   if (t == 0) {
-    S.zrange[((size_t) v * NZMAX + z) * 2] = zjlo;
-    S.zrange[((size_t) v * NZMAX + z) * 2 + 1] = zjhi;
-  }
-  for (int j = zjlo + t; j <= zjhi; j += LN_NT) {
-    const double elo = line_edge(egrid, j, grid_mode, zred, lineE), ehi = line_edge(egrid, j + 1, grid_mode, zred, lineE);
-    flux[j] = flux[j] / (0.5 * (elo + ehi));
+    S.zrange[((size_t) v * NZMAX + z) * 2] = sm.zlo;
+    S.zrange[((size_t) v * NZMAX + z) * 2 + 1] = sm.zhi;
   }
 }
 
@@ -630,7 +600,7 @@ int line_kernel_init() {
 
 void launch_line(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *egrid, int n_ener,
                  int grid_mode, int nz_max, cudaStream_t st) {
-  dim3 grid(nz_max, (unsigned) n);
+  dim3 grid((unsigned) n, nz_max);   // zone-major launch order: the inner zones (most radii, widest profiles) first
   LineGrid G;
   G.e = egrid; G.n_ener = n_ener; G.mode = grid_mode;
   G.log_lo = std::log(CONV_EMIN);
