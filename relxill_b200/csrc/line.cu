@@ -41,6 +41,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 
 #include "common.h"
 #include "devutil.cuh"
@@ -61,6 +62,9 @@ __constant__ LnConst LK = {GFAC_H, 1.0 - GFAC_H, GS_C, GS_INVC, 0.02, 1.0 * 0.95
 
 constexpr int LN_NT = 128;
 constexpr int LN_NW = LN_NT / 32;
+#ifndef LN_MINB
+#define LN_MINB 8
+#endif
 constexpr int LN_R = 16;         // radii per sub-batch
 constexpr int LN_ROWS = 10;      // table rows staged per sub-batch (a sub-batch is cut where its bracket would not fit)
 constexpr int LN_TB = 15;        // bins per tile (16 edges: one half warp)
@@ -80,7 +84,7 @@ struct LnSmem {
   LnRad rad[LN_R + 2];
   unsigned long long mbar;
   int slot[LN_NW][8];
-  int jlo, jhi, zlo, zhi, zold_lo, zold_hi, j95;
+  int jlo, jhi, zlo, zhi, zold_lo, zold_hi, j95, next_tile;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -206,30 +210,31 @@ __device__ __forceinline__ double edge_term(double blo, double bhi, double norm,
   return 2 * norm * (sqrt(hi) - sqrt(lo)) * 1.0 * dgm;
 }
 
-// Romberg levels 5 and 6 of one bin (rare: ~1e-4 of the Romberg bins), by the lane that owns the bin's tableau.
-// The new abscissae of a level are summed in ascending order like the reference's loop.
-struct DeepIn {
-  double tp[2][5];   // tableau rows after level 4
-  double res[2];
+// Full Romberg integration of one bin by one lane (src/Relprofile.cpp:524-579, both branches sharing the abscissae).
+// Out of line and rare: (i) levels 5-6 of a bin whose first four were done cooperatively (`from` = 5: the tableau
+// rows after level 4 come in), ~1e-4 of the Romberg bins; (ii) from = 1: the bin below E = 0.95 whose lower limit is
+// raised to the analytic edge interval's end above 0.95 (a few per vector).  The new abscissae of a level are summed
+// in ascending order.
+struct RombIn {
+  double sum[2];     // trapezoid sums (in units of the level's step) after level from-1
+  double tp[2][5];   // tableau row of level from-1
+  double res[2];     // result of the branch's last level
   int done[2];
 };
-__device__ __noinline__ double romberg_deep(double a, double pas, RelbCtx c, DeepIn in) {
-  double tprev[2][7], res[2] = {in.res[0], in.res[1]};
+__device__ __noinline__ double romberg_serial(double a, double pas, RelbCtx c, RombIn in, int from) {
+  double tprev[2][7], res[2], sum[2] = {in.sum[0], in.sum[1]};
   bool done[2] = {in.done[0] != 0, in.done[1] != 0};
-  for (int k = 0; k < 2; k++)
+  for (int k = 0; k < 2; k++) {
     for (int ii = 0; ii < 5; ii++) tprev[k][ii] = in.tp[k][ii];
-  const double pas6 = pas / 64.0;
-  double pasn = pas / 16.0;
-  double sum[2] = {tprev[0][0] / pasn, tprev[1][0] / pasn};   // level-4 trapezoid sums, from cur[0] = sum * pasn
-  double last[2] = {res[0], res[1]};
-  for (int n = 5; n <= 6; n++) {
+    res[k] = in.res[k];
+  }
+  for (int n = from; n <= 6; n++) {
     if (done[0] && done[1]) break;
-    pasn = pasn * 0.5;
+    const double pasn = pas * (1.0 / (double) (1 << n));
     double o[2] = {0.0, 0.0};
-    const int step = (n == 5) ? 4 : 2, first = (n == 5) ? 2 : 1;   // level 5: p = 2 mod 4, level 6: odd p (of 64)
-    for (int p = first; p < 64; p += step) {
+    for (int p = 1; p < (1 << n); p += 2) {
       double w0, w1;
-      relb2(a + pas6 * p, c, w0, w1);
+      relb2(a + pasn * p, c, w0, w1);
       o[0] += w0;
       o[1] += w1;
     }
@@ -239,13 +244,29 @@ __device__ __noinline__ double romberg_deep(double a, double pas, RelbCtx c, Dee
       double cur[7];
       cur[0] = sum[k] * pasn;
       for (int ii = 1; ii <= n; ii++) cur[ii] = richardson(ii, cur[ii - 1], tprev[k][ii - 1]);
+      if (!not_converged(cur[n], res[k])) done[k] = true;
       res[k] = cur[n];
-      if (!not_converged(cur[n], last[k])) done[k] = true;
-      last[k] = cur[n];
       for (int ii = 0; ii <= n; ii++) tprev[k][ii] = cur[ii];
     }
   }
-  return res[0] + res[1];
+  double r = 0.0;
+  r += res[0];
+  r += res[1];
+  return r;
+}
+// the whole integration of [a, a + pas] from level 0
+__device__ __noinline__ double romberg_bin(double a, double pas, RelbCtx c) {
+  double fa0, fa1, fb0, fb1;
+  relb2(a, c, fa0, fa1);
+  relb2(a + pas, c, fb0, fb1);
+  RombIn in;
+  in.sum[0] = (fa0 + fb0) / 2.0; in.sum[1] = (fa1 + fb1) / 2.0;
+  for (int k = 0; k < 2; k++) {
+    in.tp[k][0] = in.sum[k] * pas;
+    in.res[k] = in.tp[k][0];
+    in.done[k] = 0;
+  }
+  return romberg_serial(a, pas, c, in, 1);
 }
 
 __device__ __forceinline__ void ln_ctx(const LnSmem &sm, int r, const double2 *g_cosne, int limb, RelbCtx &c) {
@@ -257,10 +278,11 @@ __device__ __forceinline__ void ln_ctx(const LnSmem &sm, int r, const double2 *g
 
 // One Romberg level L (3 or 4) for the lanes of the warp that still need it (need == L), compacted: every such bin
 // gets NP = 2^(L-1) lanes, one per new abscissa a + (2p+1) pas / 2^L; an xor-butterfly sums them, the owning lane pulls
-// the two branch sums and advances its tableau (src/Relprofile.cpp:553-576).
+// the two branch sums and advances its tableau (src/Relprofile.cpp:553-576).  Per branch the lane keeps the trapezoid
+// sum and the tableau row without its first entry (tq[i] = t[i+1]; the first one is sum * step).
 template <int L>
 __device__ __forceinline__ void romberg_level(const LnSmem &sm, int *slot, int lane, int rsel, const double2 *g_cosne, int limb,
-                                              double a, double pas, int &need, double (&sum)[2], double (&tp)[2][5],
+                                              double a, double pas, int &need, double (&sum)[2], double (&tq)[2][4],
                                               double (&res)[2], bool (&done)[2]) {
   const unsigned FULL = 0xffffffffu;
   constexpr int NP = 1 << (L - 1), NB = 32 / NP;
@@ -289,20 +311,22 @@ __device__ __forceinline__ void romberg_level(const LnSmem &sm, int *slot, int l
     const int from = mine ? rank * NP : lane;
     const double s0 = __shfl_sync(FULL, w0, from), s1 = __shfl_sync(FULL, w1, from);
     if (mine) {
-      const double pasn = pas * (1.0 / (1 << L));
+      const double pasn = pas * (1.0 / (1 << L)), pasp = pas * (2.0 / (1 << L));
       bool more = false;
 #pragma unroll
       for (int k = 0; k < 2; k++) {
+        const double t0p = sum[k] * pasp;   // first tableau entry of the previous level
         sum[k] += k ? s1 : s0;
         if (!done[k]) {
           double cur[L + 1];
           cur[0] = sum[k] * pasn;
+          cur[1] = richardson(1, cur[0], t0p);
 #pragma unroll
-          for (int ii = 1; ii <= L; ii++) cur[ii] = richardson(ii, cur[ii - 1], tp[k][ii - 1]);
+          for (int ii = 2; ii <= L; ii++) cur[ii] = richardson(ii, cur[ii - 1], tq[k][ii - 2]);
           if (!not_converged(cur[L], res[k])) done[k] = true;
           res[k] = cur[L];
 #pragma unroll
-          for (int ii = 0; ii <= L; ii++) tp[k][ii] = cur[ii];
+          for (int ii = 1; ii <= L; ii++) tq[k][ii - 1] = cur[ii];
           more |= !done[k];
         }
       }
@@ -312,9 +336,23 @@ __device__ __forceinline__ void romberg_level(const LnSmem &sm, int *slot, int l
   }
 }
 
+// analytic edge terms of a bin that reaches into [0, h] or [1-h, 1] (integ_relline_bin, src/Relprofile.cpp:650-726;
+// the decisions in g* like the reference's)
+__device__ __forceinline__ double edge_terms(double Ea, double Eb, double gmin, double del_g, double dgm, double nlo, double nhi) {
+  double ga = (Ea / 1.0 - gmin) * del_g;
+  if (ga < 0.0) ga = 0.0; else if (ga > 1.0) ga = 1.0;
+  double gb = (Eb / 1.0 - gmin) * del_g;
+  if (gb < 0.0) gb = 0.0; else if (gb > 1.0) gb = 1.0;
+  double flu = 0.0;
+  if (gb == 0) return flu;
+  if (ga <= LK.h) flu = flu + edge_term(ga, (gb <= LK.h) ? gb : LK.h, nlo, dgm);   // lower-edge term first, like the reference
+  if (gb >= LK.one_m_h) flu = flu + edge_term((ga >= LK.one_m_h) ? ga : LK.one_m_h, gb, nhi, dgm);
+  return flu;
+}
+
 // 8 resident CTAs per SM (64 registers, 32 warps)
-template <int GRID_MODE>
-__global__ void __launch_bounds__(LN_NT, 8) k_line(const VPar *__restrict__ vps, DevTables T, Scratch S, LineGrid G,
+template <int GRID_MODE, int MINB>
+__global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ vps, DevTables T, Scratch S, LineGrid G,
                                                    int ne_stride, int nz_stride) {
   __shared__ __align__(128) LnSmem sm;
   const unsigned FULL = 0xffffffffu;
@@ -329,13 +367,10 @@ __global__ void __launch_bounds__(LN_NT, 8) k_line(const VPar *__restrict__ vps,
   constexpr int grid_mode = GRID_MODE;
   const double zred = vp.z, lineE = vp.lineE;
   const int limb = vp.limb;
-  const double e_first = line_edge(egrid, 0, grid_mode, zred, lineE);
-  const double e_last = line_edge(egrid, n_ener, grid_mode, zred, lineE);
   // radii of this zone (izone[] is non-increasing along the descending-radius fine grid; k_syspar tabulated
   // the first index of every zone)
   const int ia = S.zfirst[(size_t) v * (NZMAX + 1) + z + 1], ib = S.zfirst[(size_t) v * (NZMAX + 1) + z];
   double *flux = S.relflux + ((size_t) v * nz_stride + z) * ne_stride;   // doubles as the zone accumulator
-  const double *g_re = S.re + (size_t) v * NR;
   const int *g_it = S.it + (size_t) v * NR;
   const double2 *g_rows = reinterpret_cast<const double2 *>(S.relrow) + (size_t) v * REL_NRT * NG * 2;   // trff plane
   const double2 *g_cosne = reinterpret_cast<const double2 *>(S.cosne) + (size_t) v * NR * NG;
@@ -369,13 +404,15 @@ __global__ void __launch_bounds__(LN_NT, 8) k_line(const VPar *__restrict__ vps,
       LnRad &lr = sm.rad[r];
       const int i = cur + r;
       if (r < n) {
+        const double e_first = line_edge(egrid, 0, grid_mode, zred, lineE);
+        const double e_last = line_edge(egrid, n_ener, grid_mode, zred, lineE);
         const double gmin = S.gmin[(size_t) v * NR + i], gmax = S.gmax[(size_t) v * NR + i];
         const bool on_grid = (gmax > e_first) && (gmin < e_last);  // src/Relprofile.cpp:863-878
         if (task == 0) {
           const double del_g = 1. / (gmax - gmin);
           lr.gmin = gmin; lr.del_g = del_g; lr.dgm = gmax - gmin;
           lr.scale = del_g * S.emis[(size_t) v * NR + i];
-          lr.weight = trapez_single(g_re, i, NR) / 2;
+          lr.weight = trapez_single(S.re + (size_t) v * NR, i, NR) / 2;
           lr.ehlo = (GFAC_H * (gmax - gmin) + gmin) * 1.0;
           lr.ehhi = ((1.0 - GFAC_H) * (gmax - gmin) + gmin) * 1.0;
           lr.gi = i;
@@ -441,89 +478,110 @@ __global__ void __launch_bounds__(LN_NT, 8) k_line(const VPar *__restrict__ vps,
         // the last sub-batch visits the zone's whole range: it finishes the row (division by the bin energy)
         sm.jlo = last_batch ? nzlo : jlo;
         sm.jhi = last_batch ? nzhi : jhi;
+        sm.next_tile = 0;
       }
     }
     __syncthreads();
 
-    // ---- main loop: warp = tile of 15 bins, half warp = radius, lane = bin edge
+    // ---- main loop: warp = tile of 15 bins, half warp = radius, lane = bin edge.  Tiles are handed out through a
+    // counter, the Romberg tiles (the expensive ones) first.
     {
       const int jlo = sm.jlo, jhi = sm.jhi, zold_lo = sm.zold_lo, zold_hi = sm.zold_hi;
       const int half = lane >> 4, hl = lane & 15;
       int *slot = sm.slot[warp];
-      if (jhi >= jlo) {
-        // tiles anchored at j95: tile k covers bins [j95 + k LN_TB, j95 + (k+1) LN_TB)
-        const int k_lo = (jlo - j95 >= 0) ? (jlo - j95) / LN_TB : -((j95 - jlo + LN_TB - 1) / LN_TB);
-        const int k_hi = (jhi - j95 >= 0) ? (jhi - j95) / LN_TB : -((j95 - jhi + LN_TB - 1) / LN_TB);
-        const int npair = (n + 1) >> 1;
-        for (int k = k_lo + warp; k <= k_hi; k += LN_NW) {
-          const int j = j95 + k * LN_TB + hl;                     // this lane's edge; its bin if hl < 15
-          const double Ea = line_edge(egrid, min(max(j, 0), n_ener), grid_mode, zred, lineE);
-          const double Eb = line_edge(egrid, min(max(j + 1, 0), n_ener), grid_mode, zred, lineE);
-          const bool binlane = (hl < LN_TB) && (j >= jlo) && (j <= jhi);
-          const bool was = binlane && (j >= zold_lo) && (j <= zold_hi);
-          double acc = was ? flux[j] : 0.0;
+      // tiles anchored at j95: tile k covers bins [j95 + k LN_TB, j95 + (k+1) LN_TB)
+      const int k_lo = (jlo - j95 >= 0) ? (jlo - j95) / LN_TB : -((j95 - jlo + LN_TB - 1) / LN_TB);
+      const int k_hi = (jhi - j95 >= 0) ? (jhi - j95) / LN_TB : -((j95 - jhi + LN_TB - 1) / LN_TB);
+      const int npair = (n + 1) >> 1;
+      while (jhi >= jlo) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(&sm.next_tile, 1);
+        k = k_hi - __shfl_sync(FULL, k, 0);
+        if (k < k_lo) break;
+        const int j = j95 + k * LN_TB + hl;                     // this lane's edge; its bin if hl < 15
+        const double Ea = line_edge(egrid, min(max(j, 0), n_ener), grid_mode, zred, lineE);
+        const double Eb = line_edge(egrid, min(max(j + 1, 0), n_ener), grid_mode, zred, lineE);
+        const bool binlane = (hl < LN_TB) && (j >= jlo) && (j <= jhi);
+        double acc = (binlane && (j >= zold_lo) && (j <= zold_hi)) ? flux[j] : 0.0;
+        if (k < 0) {
+          // ---------------- midpoint-rule tile (int_romb with lo < 0.95, src/Relprofile.cpp:628-647)
           for (int pr = 0; pr < npair; pr++) {
             const int rsel = 2 * pr + half;
             const LnRad &lr = sm.rad[rsel];
             const bool in = binlane && (j >= lr.ielo) && (j <= lr.iehi);
             if (!__any_sync(FULL, in)) continue;
-            // ---- the decision part of integ_relline_bin (src/Relprofile.cpp:650-726)
-            const double gmin = lr.gmin, del_g = lr.del_g;
-            double ga = (Ea / 1.0 - gmin) * del_g;
-            if (ga < 0.0) ga = 0.0; else if (ga > 1.0) ga = 1.0;
-            double gb = (Eb / 1.0 - gmin) * del_g;
-            if (gb < 0.0) gb = 0.0; else if (gb > 1.0) gb = 1.0;
-            const bool live = in && !(gb == 0);
-            const bool a_lo = ga <= LK.h, a_hi = ga >= LK.one_m_h, b_lo = gb <= LK.h, b_hi = gb >= LK.one_m_h;
-            // abscissa of this lane's edge: the edge itself, or the end of the analytic edge interval it lies in
-            const double Xa = a_lo ? lr.ehlo : (a_hi ? lr.ehhi : Ea);
-            const double Xb = b_lo ? lr.ehlo : (b_hi ? lr.ehhi : Eb);
-            const bool quad = live && !b_lo && !a_hi;
-            double flu = 0.0;
-            if (live && (a_lo || b_hi)) {   // lower-edge term first, like the reference
-              const double dgm = lr.dgm;
-              if (a_lo) flu = flu + edge_term(ga, b_lo ? gb : LK.h, lr.nlo, dgm);
-              if (b_hi) flu = flu + edge_term(a_hi ? ga : LK.one_m_h, gb, lr.nhi, dgm);
-            }
-            const bool romb = quad && (Xa >= LK.e95);
-            const bool midp = quad && !romb;
+            // limits of the quadrature: the bin, cut at the ends of the analytic edge intervals (the reference takes
+            // these decisions in g*; an ulp of difference moves the cut by an ulp)
+            const double ehlo = lr.ehlo, ehhi = lr.ehhi;
+            const bool e_lo = Ea < ehlo, e_hi = Eb > ehhi;
+            const double Xa = e_lo ? ehlo : Ea, Xb = e_hi ? ehhi : Eb;
+            const double w = Xb - Xa;
             RelbCtx c;
-            c.gmin = gmin; c.del_g = del_g; c.scale = lr.scale;
+            c.gmin = lr.gmin; c.del_g = lr.del_g; c.scale = lr.scale;
             c.row = smem_u32(&sm.fine[rsel][0]);
             c.cosne = g_cosne + (size_t) lr.gi * NG; c.limb = limb;
-            if (__any_sync(FULL, midp)) {   // midpoint rule (int_romb, :628-647, lo < 0.95)
-              double m0, m1;
-              relb2((Xb + Xa) / 2.0, c, m0, m1);
-              if (midp) {
+            double flu = 0.0;
+            if (in && (e_lo || e_hi)) flu = edge_terms(Ea, Eb, c.gmin, c.del_g, lr.dgm, lr.nlo, lr.nhi);
+            double m0, m1;
+            relb2((Xb + Xa) / 2.0, c, m0, m1);
+            if (in && w > 0.0) {
+              if (Xa >= LK.e95) {   // the lower limit was raised past 0.95: Romberg
+                flu = flu + romberg_bin(Xa, w, c);
+              } else {
                 double f2 = 0.0;
-                f2 += m0 * (Xb - Xa);
-                f2 += m1 * (Xb - Xa);
+                f2 += m0 * w;
+                f2 += m1 * w;
                 flu = flu + f2;
               }
             }
-            if (__any_sync(FULL, romb)) {   // Romberg on [Xa, Xb] for both branches (src/Relprofile.cpp:524-579)
-              double fa0, fa1;
-              relb2(Xa, c, fa0, fa1);       // every lane: its own lower edge = the neighbour's upper edge
+            // ascending-radius accumulation: the lower half's radius first, then the upper half's
+            const double own = in ? flu * lr.weight : 0.0;
+            const double oth = __shfl_xor_sync(FULL, own, 16);
+            acc = (acc + (half ? oth : own)) + (half ? own : oth);
+          }
+        } else {
+          // ---------------- Romberg tile (src/Relprofile.cpp:524-579), both branches
+          for (int pr = 0; pr < npair; pr++) {
+            const int rsel = 2 * pr + half;
+            const LnRad &lr = sm.rad[rsel];
+            const bool in = binlane && (j >= lr.ielo) && (j <= lr.iehi);
+            if (!__any_sync(FULL, in)) continue;
+            const double ehlo = lr.ehlo, ehhi = lr.ehhi;
+            // every lane evaluates the integrand at its own lower edge, clamped to the quadrature's range: that is
+            // the lower limit of its bin and the upper limit of the neighbour's
+            const double Xa = (Ea < ehlo) ? ehlo : ((Ea > ehhi) ? ehhi : Ea);
+            const double Xb = (Eb < ehlo) ? ehlo : ((Eb > ehhi) ? ehhi : Eb);
+            const double pas = Xb - Xa;
+            const bool romb = in && (pas > 0.0);
+            RelbCtx c;
+            c.gmin = lr.gmin; c.del_g = lr.del_g; c.scale = lr.scale;
+            c.row = smem_u32(&sm.fine[rsel][0]);
+            c.cosne = g_cosne + (size_t) lr.gi * NG; c.limb = limb;
+            double flu = 0.0;
+            if (in && (Ea < ehlo || Eb > ehhi)) flu = edge_terms(Ea, Eb, c.gmin, c.del_g, lr.dgm, lr.nlo, lr.nhi);
+            double sum[2], tq[2][4], res[2];
+            bool done[2];
+            int need = 0;
+            {
+              double fa0, fa1, fm0, fm1;
+              relb2(Xa, c, fa0, fa1);
               const double fb0 = __shfl_down_sync(FULL, fa0, 1, 16), fb1 = __shfl_down_sync(FULL, fa1, 1, 16);
-              const double pas = Xb - Xa, pas1 = pas / 2.0, pas2 = pas1 / 2.0;
-              double fm0, fm1;
+              const double pas1 = pas / 2.0, pas2 = pas1 / 2.0;
               relb2(Xa + pas1 * 1, c, fm0, fm1);
-              double sum[2], tp[2][5], res[2];
-              bool done[2];
+              double t01[2];
               bool lvl2 = false;
 #pragma unroll
               for (int kk = 0; kk < 2; kk++) {
                 const double ta = ((kk ? fa1 : fa0) + (kk ? fb1 : fb0)) / 2.0;
                 sum[kk] = ta;
                 const double t00 = ta * pas;
-                const double t01 = (ta + (kk ? fm1 : fm0)) * pas1;
-                const double t10 = richardson(1, t01, t00);
-                tp[kk][0] = t01; tp[kk][1] = t10;
+                t01[kk] = (ta + (kk ? fm1 : fm0)) * pas1;
+                const double t10 = richardson(1, t01[kk], t00);
+                tq[kk][0] = t10;
                 res[kk] = t10;
                 done[kk] = !not_converged(t10, t00);
                 lvl2 |= !done[kk];
               }
-              int need = 0;
               if (__any_sync(FULL, romb && lvl2)) {
                 double q0, q1, u0, u1;
                 relb2(Xa + pas2 * 1, c, q0, q1);
@@ -534,50 +592,51 @@ __global__ void __launch_bounds__(LN_NT, 8) k_line(const VPar *__restrict__ vps,
                   sum[kk] = ((sum[kk] + (kk ? q1 : q0)) + (kk ? fm1 : fm0)) + (kk ? u1 : u0);
                   if (!done[kk]) {
                     const double t02 = sum[kk] * pas2;
-                    const double t11 = richardson(1, t02, tp[kk][0]);
-                    const double t20 = richardson(2, t11, tp[kk][1]);
+                    const double t11 = richardson(1, t02, t01[kk]);
+                    const double t20 = richardson(2, t11, tq[kk][0]);
                     done[kk] = !not_converged(t20, res[kk]);
                     res[kk] = t20;
-                    tp[kk][0] = t02; tp[kk][1] = t11; tp[kk][2] = t20;
+                    tq[kk][0] = t11; tq[kk][1] = t20;
                     if (!done[kk]) need = 3;
                   }
                 }
                 if (!romb) need = 0;
               }
-              if (__any_sync(FULL, need == 3)) {
-                romberg_level<3>(sm, slot, lane, rsel, g_cosne, limb, Xa, pas, need, sum, tp, res, done);
-                if (__any_sync(FULL, need == 4)) {
-                  romberg_level<4>(sm, slot, lane, rsel, g_cosne, limb, Xa, pas, need, sum, tp, res, done);
-                  if (need == 5) {
-                    DeepIn in;
+            }
+            if (__any_sync(FULL, need == 3)) {
+              romberg_level<3>(sm, slot, lane, rsel, g_cosne, limb, Xa, pas, need, sum, tq, res, done);
+              if (__any_sync(FULL, need == 4)) {
+                romberg_level<4>(sm, slot, lane, rsel, g_cosne, limb, Xa, pas, need, sum, tq, res, done);
+                if (need == 5) {   // levels 5-6: by the owning lane
+                  RombIn in;
 #pragma unroll
-                    for (int kk = 0; kk < 2; kk++) {
+                  for (int kk = 0; kk < 2; kk++) {
+                    in.sum[kk] = sum[kk];
+                    in.tp[kk][0] = sum[kk] * (pas * (1.0 / 16.0));
 #pragma unroll
-                      for (int ii = 0; ii < 5; ii++) in.tp[kk][ii] = tp[kk][ii];
-                      in.res[kk] = res[kk];
-                      in.done[kk] = done[kk] ? 1 : 0;
-                    }
-                    const double rt = romberg_deep(Xa, pas, c, in);
-                    res[0] = rt; res[1] = 0.0;
+                    for (int ii = 0; ii < 4; ii++) in.tp[kk][ii + 1] = tq[kk][ii];
+                    in.res[kk] = res[kk];
+                    in.done[kk] = done[kk] ? 1 : 0;
                   }
+                  res[0] = romberg_serial(Xa, pas, c, in, 5);
+                  res[1] = 0.0;
                 }
               }
-              if (romb) {
-                double rsum = 0.0;
-                rsum += res[0];
-                rsum += res[1];
-                flu = flu + rsum;
-              }
             }
-            // ---- ascending-radius accumulation: the lower half's radius first, then the upper half's
-            const double own = live ? flu * lr.weight : 0.0;
+            if (romb) {
+              double rsum = 0.0;
+              rsum += res[0];
+              rsum += res[1];
+              flu = flu + rsum;
+            }
+            const double own = in ? flu * lr.weight : 0.0;
             const double oth = __shfl_xor_sync(FULL, own, 16);
             acc = (acc + (half ? oth : own)) + (half ? own : oth);
           }
-          if (binlane && half == 0) {
-            // only the bins this zone touched are written; the range travels with the row
-            flux[j] = last_batch ? acc / (0.5 * (Ea + Eb)) : acc;
-          }
+        }
+        if (binlane && half == 0) {
+          // only the bins this zone touched are written; the range travels with the row
+          flux[j] = last_batch ? acc / (0.5 * (Ea + Eb)) : acc;
         }
       }
     }
@@ -591,13 +650,25 @@ __global__ void __launch_bounds__(LN_NT, 8) k_line(const VPar *__restrict__ vps,
 }
 
 // ---------------------------------------------------------------------------------- launcher
-int line_kernel_init() {
-  cudaError_t e = cudaFuncSetAttribute(k_line<0>, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
+static int g_minb = 8;
+template <int MINB> static int line_init_one() {
+  // MINB CTAs x 18.6 KB of shared memory: the rest of the 256 KB stays L1 (energy grid, per-radius inputs, spills)
+  cudaError_t e = cudaFuncSetAttribute(k_line<0, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, MINB * 9);
   if (e != cudaSuccess) return 1;
-  e = cudaFuncSetAttribute(k_line<1>, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
+  e = cudaFuncSetAttribute(k_line<1, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, MINB * 9);
   return e == cudaSuccess ? 0 : 1;
 }
+int line_kernel_init() {
+  if (const char *s = getenv("RELXILL_B200_LINE_MINB")) g_minb = atoi(s);
+  return line_init_one<8>() | line_init_one<6>() | line_init_one<5>();
+}
 
+template <int MINB>
+static void launch_line_t(const VPar *vps, const DevTables &T, const Scratch &S, dim3 grid, const LineGrid &G, int grid_mode,
+                          cudaStream_t st) {
+  if (grid_mode == 0) k_line<0, MINB><<<grid, LN_NT, 0, st>>>(vps, T, S, G, S.ne_line_cap, S.nz_cap);
+  else k_line<1, MINB><<<grid, LN_NT, 0, st>>>(vps, T, S, G, S.ne_line_cap, S.nz_cap);
+}
 void launch_line(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *egrid, int n_ener,
                  int grid_mode, int nz_max, cudaStream_t st) {
   dim3 grid((unsigned) n, nz_max);   // zone-major launch order: the inner zones (most radii, widest profiles) first
@@ -605,8 +676,9 @@ void launch_line(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
   G.e = egrid; G.n_ener = n_ener; G.mode = grid_mode;
   G.log_lo = std::log(CONV_EMIN);
   G.inv_dlog = (double) NCONV / (std::log(CONV_EMAX) - std::log(CONV_EMIN));
-  if (grid_mode == 0) k_line<0><<<grid, LN_NT, 0, st>>>(vps, T, S, G, S.ne_line_cap, S.nz_cap);
-  else k_line<1><<<grid, LN_NT, 0, st>>>(vps, T, S, G, S.ne_line_cap, S.nz_cap);
+  if (g_minb == 6) launch_line_t<6>(vps, T, S, grid, G, grid_mode, st);
+  else if (g_minb == 5) launch_line_t<5>(vps, T, S, grid, G, grid_mode, st);
+  else launch_line_t<8>(vps, T, S, grid, G, grid_mode, st);
 }
 int line_max_bins() { return 1 << 24; }   // the zone accumulator lives in the output row: no shared-memory limit
 
