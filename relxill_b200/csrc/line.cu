@@ -60,13 +60,13 @@ struct LnConst {
 __constant__ LnConst LK = {GFAC_H, 1.0 - GFAC_H, GS_C, GS_INVC, 0.02, 1.0 * 0.95, 0.0,
                            {0.0, 1.0 / 3.0, 1.0 / 15.0, 1.0 / 63.0, 1.0 / 255.0, 1.0 / 1023.0, 1.0 / 4095.0}};
 
-constexpr int LN_NT = 128;
+constexpr int LN_NT = 32;      // one warp per CTA
 constexpr int LN_NW = LN_NT / 32;
 #ifndef LN_MINB
 #define LN_MINB 8
 #endif
-constexpr int LN_R = 16;         // radii per sub-batch
-constexpr int LN_ROWS = 10;      // table rows staged per sub-batch (a sub-batch is cut where its bracket would not fit)
+constexpr int LN_R = 8;          // radii per sub-batch
+constexpr int LN_ROWS = 5;       // table rows staged per sub-batch (a sub-batch is cut where its bracket would not fit)
 constexpr int LN_TB = 15;        // bins per tile (16 edges: one half warp)
 constexpr int LN_FS = NG + 1;    // row stride of the fine rows in shared memory (padded: consecutive radii on different banks)
 
@@ -78,13 +78,24 @@ struct LnRad {
   double ehlo, ehhi;             // gstar2ener(h), gstar2ener(1-h)
   int ielo, iehi, gi, pad;
 };
+// A Romberg bin that has not converged after level 2 waits here for levels 3+ (deep_flush)
+struct LnDeep {
+  double a, pas;                 // the bin's quadrature interval [a, a + pas]
+  double sum[2];                 // trapezoid sums (in units of the level's step) per branch; at the end sum[0] = the bin's result
+  double tq[2][3];               // tableau row without its first entry (= sum * step); a finished branch: [0] = its result
+  int rsel, hl;                  // radius of the sub-batch, owning lane
+  int flags, pad;                // bits 0-1: branch finished; bits 8-..: level still to do (1: all of it, 3, 4, 5; 0: done)
+};
+constexpr int LN_DQ = (LN_ROWS * NG * 16) / (int) sizeof(LnDeep);   // 26: the queue lives in the row stage, dead in the main loop
 struct LnSmem {
-  double2 rows[LN_ROWS][NG];     // bulk-copy destination
+  union {
+    double2 rows[LN_ROWS][NG];   // bulk-copy destination
+    LnDeep dq[LN_DQ];
+  };
   double2 fine[LN_R][LN_FS];     // {branch 0, branch 1} of the sub-batch's radii
   LnRad rad[LN_R + 2];
   unsigned long long mbar;
-  int slot[LN_NW][8];
-  int jlo, jhi, zlo, zhi, zold_lo, zold_hi, j95, next_tile;
+  int slot[32];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -185,7 +196,7 @@ struct LineGrid {
   double log_lo, inv_dlog;   // mode 0: edge[k] ~ exp(log_lo + k / inv_dlog)
 };
 template <int GRID_MODE>
-__device__ int line_index(const LineGrid &G, double val, double z, double lineE) {
+__device__ __noinline__ int line_index(const LineGrid &G, double val, double z, double lineE) {
   const int last = G.n_ener - 1;   // n_edges - 2
   if (GRID_MODE == 0) {
     int k = (int) floor((log(val) - G.log_lo) * G.inv_dlog);
@@ -210,63 +221,54 @@ __device__ __forceinline__ double edge_term(double blo, double bhi, double norm,
   return 2 * norm * (sqrt(hi) - sqrt(lo)) * 1.0 * dgm;
 }
 
-// Full Romberg integration of one bin by one lane (src/Relprofile.cpp:524-579, both branches sharing the abscissae).
-// Out of line and rare: (i) levels 5-6 of a bin whose first four were done cooperatively (`from` = 5: the tableau
-// rows after level 4 come in), ~1e-4 of the Romberg bins; (ii) from = 1: the bin below E = 0.95 whose lower limit is
-// raised to the analytic edge interval's end above 0.95 (a few per vector).  The new abscissae of a level are summed
-// in ascending order.
-struct RombIn {
-  double sum[2];     // trapezoid sums (in units of the level's step) after level from-1
-  double tp[2][5];   // tableau row of level from-1
-  double res[2];     // result of the branch's last level
-  int done[2];
-};
-__device__ __noinline__ double romberg_serial(double a, double pas, RelbCtx c, RombIn in, int from) {
-  double tprev[2][7], res[2], sum[2] = {in.sum[0], in.sum[1]};
-  bool done[2] = {in.done[0] != 0, in.done[1] != 0};
+// Full Romberg integration of [a, a + pas] by one lane (src/Relprofile.cpp:524-579, both branches sharing the abscissae).
+// Out of line and rare: (i) a bin that has not converged after the cooperative level 4, ~1e-4 of the Romberg bins;
+// (ii) the bin below E = 0.95 whose lower limit is raised to the analytic edge interval's end above 0.95 (a few per
+// vector).  The new abscissae of a level are summed in ascending order.
+__device__ __noinline__ double romberg_bin(double a, double pas, RelbCtx c) {
+  double fa0, fa1, fb0, fb1;
+  relb2(a, c, fa0, fa1);
+  relb2(a + pas, c, fb0, fb1);
+  double tprev[2][7], res[2], sum[2] = {(fa0 + fb0) / 2.0, (fa1 + fb1) / 2.0};
+  bool done[2] = {false, false};
+#pragma unroll 1
   for (int k = 0; k < 2; k++) {
-    for (int ii = 0; ii < 5; ii++) tprev[k][ii] = in.tp[k][ii];
-    res[k] = in.res[k];
+    tprev[k][0] = sum[k] * pas;
+    res[k] = tprev[k][0];
   }
-  for (int n = from; n <= 6; n++) {
+#pragma unroll 1
+  for (int n = 1; n <= 6; n++) {
     if (done[0] && done[1]) break;
     const double pasn = pas * (1.0 / (double) (1 << n));
     double o[2] = {0.0, 0.0};
+#pragma unroll 1
     for (int p = 1; p < (1 << n); p += 2) {
       double w0, w1;
       relb2(a + pasn * p, c, w0, w1);
       o[0] += w0;
       o[1] += w1;
     }
+#pragma unroll 1
     for (int k = 0; k < 2; k++) {
       sum[k] += o[k];
       if (done[k]) continue;
-      double cur[7];
-      cur[0] = sum[k] * pasn;
-      for (int ii = 1; ii <= n; ii++) cur[ii] = richardson(ii, cur[ii - 1], tprev[k][ii - 1]);
-      if (!not_converged(cur[n], res[k])) done[k] = true;
-      res[k] = cur[n];
-      for (int ii = 0; ii <= n; ii++) tprev[k][ii] = cur[ii];
+      double prev = tprev[k][0], cur = sum[k] * pasn, r4 = 1.0;
+      tprev[k][0] = cur;
+#pragma unroll 1
+      for (int ii = 1; ii <= n; ii++) {   // t[ii] = (4^ii t[ii-1] - tprev[ii-1]) / (4^ii - 1)
+        r4 *= 4.0;
+        cur = (r4 * cur - prev) * LK.inv[ii];
+        prev = tprev[k][ii];
+        tprev[k][ii] = cur;
+      }
+      if (!not_converged(cur, res[k])) done[k] = true;
+      res[k] = cur;
     }
   }
   double r = 0.0;
   r += res[0];
   r += res[1];
   return r;
-}
-// the whole integration of [a, a + pas] from level 0
-__device__ __noinline__ double romberg_bin(double a, double pas, RelbCtx c) {
-  double fa0, fa1, fb0, fb1;
-  relb2(a, c, fa0, fa1);
-  relb2(a + pas, c, fb0, fb1);
-  RombIn in;
-  in.sum[0] = (fa0 + fb0) / 2.0; in.sum[1] = (fa1 + fb1) / 2.0;
-  for (int k = 0; k < 2; k++) {
-    in.tp[k][0] = in.sum[k] * pas;
-    in.res[k] = in.tp[k][0];
-    in.done[k] = 0;
-  }
-  return romberg_serial(a, pas, c, in, 1);
 }
 
 __device__ __forceinline__ void ln_ctx(const LnSmem &sm, int r, const double2 *g_cosne, int limb, RelbCtx &c) {
@@ -276,69 +278,118 @@ __device__ __forceinline__ void ln_ctx(const LnSmem &sm, int r, const double2 *g
   c.cosne = g_cosne + (size_t) lr.gi * NG; c.limb = limb;
 }
 
-// One Romberg level L (3 or 4) for the lanes of the warp that still need it (need == L), compacted: every such bin
-// gets NP = 2^(L-1) lanes, one per new abscissa a + (2p+1) pas / 2^L; an xor-butterfly sums them, the owning lane pulls
-// the two branch sums and advances its tableau (src/Relprofile.cpp:553-576).  Per branch the lane keeps the trapezoid
-// sum and the tableau row without its first entry (tq[i] = t[i+1]; the first one is sum * step).
-template <int L>
-__device__ __forceinline__ void romberg_level(const LnSmem &sm, int *slot, int lane, int rsel, const double2 *g_cosne, int limb,
-                                              double a, double pas, int &need, double (&sum)[2], double (&tq)[2][4],
-                                              double (&res)[2], bool (&done)[2]) {
-  const unsigned FULL = 0xffffffffu;
-  constexpr int NP = 1 << (L - 1), NB = 32 / NP;
-  unsigned pend = __ballot_sync(FULL, need == L);
-  while (pend) {
-    const int rank = __popc(pend & ((1u << lane) - 1));
-    const bool mine = (need == L) && rank < NB;
-    if (mine) slot[rank] = lane;
-    __syncwarp();
-    const int nb = min(NB, __popc(pend));
-    const int q = lane / NP, p = lane % NP;
-    const int src = (q < nb) ? slot[q] : lane;
-    __syncwarp();
-    const double a_s = __shfl_sync(FULL, a, src), pas_s = __shfl_sync(FULL, pas, src);
-    const int r_s = __shfl_sync(FULL, rsel, src);
-    RelbCtx c;
-    ln_ctx(sm, r_s, g_cosne, limb, c);
-    const double pasL = pas_s * (1.0 / (1 << L));
-    double w0, w1;
-    relb2(a_s + pasL * (double) (2 * p + 1), c, w0, w1);
+// Levels 3+ of the queued bins, compacted over the warp (src/Relprofile.cpp:553-576): level 3 = 4 new abscissae
+// a + (2p+1) pas / 8 of 8 bins per pass, level 4 = 8 abscissae of 4 bins per pass, summed by xor-butterflies; the group's
+// first lane advances the bin's tableau in the queue entry.  What is left after level 4 (~1e-4 of the Romberg bins) and
+// the bins queued for a whole integration are finished by one lane each.  Returns, for lanes 0..14, what their bin
+// gains (already weighted with the radius' area weight); queue order = radius order, so the sum stays deterministic.
+__device__ __forceinline__ void deep_tableau(LnDeep &d, int L, double s0, double s1) {
+  const double pasn = d.pas * (1.0 / (double) (1 << L)), pasp = pasn * 2.0;
+  int flags = d.flags & 3;
+  bool more = false;
 #pragma unroll
-    for (int o = 1; o < NP; o <<= 1) {
+  for (int k = 0; k < 2; k++) {
+    const double t0p = d.sum[k] * pasp;   // first tableau entry of the previous level
+    const double sum = d.sum[k] + (k ? s1 : s0);
+    d.sum[k] = sum;
+    if (!(flags & (1 << k))) {
+      double cur[5];
+      cur[0] = sum * pasn;
+      cur[1] = richardson(1, cur[0], t0p);
+      cur[2] = richardson(2, cur[1], d.tq[k][0]);
+      cur[3] = richardson(3, cur[2], d.tq[k][1]);
+      double last = d.tq[k][1], res = cur[3];
+      if (L == 4) { cur[4] = richardson(4, cur[3], d.tq[k][2]); last = d.tq[k][2]; res = cur[4]; }
+      if (!not_converged(res, last)) {
+        flags |= 1 << k;
+        d.tq[k][0] = res;
+      } else if (L == 3) {
+        d.tq[k][0] = cur[1]; d.tq[k][1] = cur[2]; d.tq[k][2] = cur[3];
+        more = true;
+      } else {
+        more = true;
+      }
+    }
+  }
+  // not converged after level 4 (~1e-4 of the Romberg bins): the bin is integrated again as a whole by one lane
+  d.flags = flags | ((more ? (L == 3 ? 4 : 1) : 0) << 8);
+}
+__device__ __forceinline__ double deep_flush(LnSmem &sm, int ndq, int lane, const double2 *g_cosne, int limb) {
+  const unsigned FULL = 0xffffffffu;
+  // ---- level 3: 8 entries per pass, 4 lanes each
+  for (int b = 0; b < ndq; b += 8) {
+    const int e = min(b + (lane >> 2), ndq - 1), p = lane & 3;
+    LnDeep &d = sm.dq[e];
+    const bool act = (b + (lane >> 2) < ndq) && ((d.flags >> 8) == 3);
+    if (!__any_sync(FULL, act)) continue;
+    RelbCtx c;
+    ln_ctx(sm, d.rsel, g_cosne, limb, c);
+    double w0, w1;
+    relb2(d.a + d.pas * 0.125 * (double) (2 * p + 1), c, w0, w1);
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
       w0 += __shfl_xor_sync(FULL, w0, o);
       w1 += __shfl_xor_sync(FULL, w1, o);
     }
-    const int from = mine ? rank * NP : lane;
-    const double s0 = __shfl_sync(FULL, w0, from), s1 = __shfl_sync(FULL, w1, from);
-    if (mine) {
-      const double pasn = pas * (1.0 / (1 << L)), pasp = pas * (2.0 / (1 << L));
-      bool more = false;
-#pragma unroll
-      for (int k = 0; k < 2; k++) {
-        const double t0p = sum[k] * pasp;   // first tableau entry of the previous level
-        sum[k] += k ? s1 : s0;
-        if (!done[k]) {
-          double cur[L + 1];
-          cur[0] = sum[k] * pasn;
-          cur[1] = richardson(1, cur[0], t0p);
-#pragma unroll
-          for (int ii = 2; ii <= L; ii++) cur[ii] = richardson(ii, cur[ii - 1], tq[k][ii - 2]);
-          if (!not_converged(cur[L], res[k])) done[k] = true;
-          res[k] = cur[L];
-#pragma unroll
-          for (int ii = 1; ii <= L; ii++) tq[k][ii - 1] = cur[ii];
-          more |= !done[k];
-        }
-      }
-      need = more ? L + 1 : 0;
-    }
-    pend &= ~__ballot_sync(FULL, mine);
+    if (act && p == 0) deep_tableau(d, 3, w0, w1);
   }
+  __syncwarp();
+  // ---- level 4: the entries that go on, 4 per pass, 8 lanes each
+  int n4 = 0;
+  for (int b = 0; b < ndq; b += 32) {
+    const int e = b + lane;
+    const bool go = (e < ndq) && ((sm.dq[min(e, ndq - 1)].flags >> 8) == 4);
+    const unsigned m = __ballot_sync(FULL, go);
+    if (go) sm.slot[n4 + __popc(m & ((1u << lane) - 1))] = e;
+    n4 += __popc(m);
+  }
+  __syncwarp();
+  for (int b = 0; b < n4; b += 4) {
+    const int q = b + (lane >> 3), p = lane & 7;
+    const bool act = q < n4;
+    LnDeep &d = sm.dq[sm.slot[min(q, n4 - 1)]];
+    RelbCtx c;
+    ln_ctx(sm, d.rsel, g_cosne, limb, c);
+    double w0, w1;
+    relb2(d.a + d.pas * 0.0625 * (double) (2 * p + 1), c, w0, w1);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      w0 += __shfl_xor_sync(FULL, w0, o);
+      w1 += __shfl_xor_sync(FULL, w1, o);
+    }
+    if (act && p == 0) deep_tableau(d, 4, w0, w1);
+  }
+  __syncwarp();
+  // ---- the rest, one lane per entry: whole integrations (level code 1)
+  for (int b = 0; b < ndq; b += 32) {
+    const int e = b + lane;
+    if (e < ndq) {
+      LnDeep &d = sm.dq[e];
+      const int lvl = d.flags >> 8;
+      RelbCtx c;
+      ln_ctx(sm, d.rsel, g_cosne, limb, c);
+      double r;
+      if (lvl == 1) {
+        r = romberg_bin(d.a, d.pas, c);
+      } else {
+        r = 0.0;
+        r += d.tq[0][0];
+        r += d.tq[1][0];
+      }
+      d.sum[0] = r * sm.rad[d.rsel].weight;
+    }
+  }
+  __syncwarp();
+  double add = 0.0;
+  for (int e = 0; e < ndq; e++)
+    if (sm.dq[e].hl == lane) add += sm.dq[e].sum[0];
+  __syncwarp();
+  return add;
 }
 
 // analytic edge terms of a bin that reaches into [0, h] or [1-h, 1] (integ_relline_bin, src/Relprofile.cpp:650-726;
 // the decisions in g* like the reference's)
-__device__ __forceinline__ double edge_terms(double Ea, double Eb, double gmin, double del_g, double dgm, double nlo, double nhi) {
+__device__ __noinline__ double edge_terms(double Ea, double Eb, double gmin, double del_g, double dgm, double nlo, double nhi) {
   double ga = (Ea / 1.0 - gmin) * del_g;
   if (ga < 0.0) ga = 0.0; else if (ga > 1.0) ga = 1.0;
   double gb = (Eb / 1.0 - gmin) * del_g;
@@ -350,14 +401,14 @@ __device__ __forceinline__ double edge_terms(double Ea, double Eb, double gmin, 
   return flu;
 }
 
-// 8 resident CTAs per SM (64 registers, 32 warps)
+// One warp per CTA: no block barrier anywhere (the only synchronisation is the mbarrier of the bulk copy and
+// __syncwarp around the shared-memory stage).  24 resident CTAs per SM at 8.8 KB of shared memory and 80 registers.
 template <int GRID_MODE, int MINB>
 __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ vps, DevTables T, Scratch S, LineGrid G,
                                                    int ne_stride, int nz_stride) {
   __shared__ __align__(128) LnSmem sm;
   const unsigned FULL = 0xffffffffu;
-  const int v = blockIdx.x, z = blockIdx.y, t = threadIdx.x;
-  const int lane = t & 31, warp = t >> 5;
+  const int v = blockIdx.x, z = blockIdx.y, lane = threadIdx.x;
   if (S.status[v] != ST_OK) return;
   if (S.reuse && S.reuse[v]) return;   // the zone profiles of the previous run stand
   const VPar &vp = vps[v];
@@ -374,19 +425,19 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
   const int *g_it = S.it + (size_t) v * NR;
   const double2 *g_rows = reinterpret_cast<const double2 *>(S.relrow) + (size_t) v * REL_NRT * NG * 2;   // trff plane
   const double2 *g_cosne = reinterpret_cast<const double2 *>(S.cosne) + (size_t) v * NR * NG;
-  if (t == 0) {
+  int j95 = 0;
+  if (lane == 0) {
     mbar_init(&sm.mbar, 1);
-    sm.zlo = n_ener; sm.zhi = -1;
     // first bin of the Romberg rule: bins j >= j95 have E_lo >= 0.95 (src/Relprofile.cpp:633); tiles are anchored there
     const int k = line_index<GRID_MODE>(G, LK.e95, zred, lineE);
-    sm.j95 = (line_edge(egrid, k, grid_mode, zred, lineE) >= LK.e95) ? k : k + 1;
+    j95 = (line_edge(egrid, k, grid_mode, zred, lineE) >= LK.e95) ? k : k + 1;
   }
-  __syncthreads();
-  const int j95 = sm.j95;
+  j95 = __shfl_sync(FULL, j95, 0);
+  int zlo = n_ener, zhi = -1;   // bins of the zone's row written so far (the same in every lane)
 
   uint32_t phase = 0;
   for (int cur = ia; cur < ib;) {
-    // ---- the sub-batch: as many radii as fit LN_R and whose table bracket fits LN_ROWS (every warp computes the same n)
+    // ---- the sub-batch: as many radii as fit LN_R and whose table bracket fits LN_ROWS
     int n, it0;
     {
       const int i = min(cur + (lane & (LN_R - 1)), ib - 1);
@@ -395,15 +446,15 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
       const unsigned ok = __ballot_sync(FULL, (lane < LN_R) && (cur + lane < ib) && (it + 2 - it0 <= LN_ROWS));
       n = __ffs(~ok) - 1;   // ok is a prefix (it[] is non-decreasing); lane 0 always fits
       const int it1 = __shfl_sync(FULL, it, n - 1);
-      if (t == 0) bulk_load(&sm.rows[0][0], g_rows + (size_t) it0 * NG, (uint32_t) (it1 + 2 - it0) * NG * 16, &sm.mbar);
+      if (lane == 0) bulk_load(&sm.rows[0][0], g_rows + (size_t) it0 * NG, (uint32_t) (it1 + 2 - it0) * NG * 16, &sm.mbar);
     }
     const bool last_batch = cur + n >= ib;
-    // ---- set-up, part 1 (while the rows are in flight): thread = (radius, task 0: record + first bin | 1: last bin)
-    if (t < 2 * LN_R) {
-      const int r = t & (LN_R - 1), task = t / LN_R;
-      LnRad &lr = sm.rad[r];
-      const int i = cur + r;
-      if (r < n) {
+    // ---- set-up: lane = (radius, task).  While the rows are in flight, task 0: record + first bin | 1: last bin
+    const int r_su = lane & (LN_R - 1), task = lane / LN_R;
+    if (task < 2) {
+      LnRad &lr = sm.rad[r_su];
+      const int i = cur + r_su;
+      if (r_su < n) {
         const double e_first = line_edge(egrid, 0, grid_mode, zred, lineE);
         const double e_last = line_edge(egrid, n_ener, grid_mode, zred, lineE);
         const double gmin = S.gmin[(size_t) v * NR + i], gmax = S.gmax[(size_t) v * NR + i];
@@ -430,7 +481,8 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
     // ---- radial interpolation of the staged rows onto the sub-batch's radii (src/Relprofile.cpp:280-293)
     mbar_wait(&sm.mbar, phase);
     phase ^= 1;
-    for (int q = t; q < n * NG; q += LN_NT) {
+#pragma unroll 1
+    for (int q = lane; q < n * NG; q += 32) {
       const int r = q / NG, jg = q - r * NG;
       const int i = cur + r;
       const int it = g_it[i] - it0;
@@ -441,198 +493,197 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
       tr.y = __dadd_rn(__dmul_rn(fr, hi.y), __dmul_rn(1.0 - fr, lo.y));
       sm.fine[r][jg] = tr;
     }
-    __syncthreads();
-    // ---- set-up, part 2: the integrand at the two edge nodes (threads 0..2 LN_R-1), the sub-batch's bin range (warp 2)
-    if (t < 2 * LN_R) {
-      const int r = t & (LN_R - 1), task = t / LN_R;
-      if (r < n) {
-        RelbCtx c;
-        ln_ctx(sm, r, g_cosne, limb, c);
-        const LnRad &lr = sm.rad[r];
-        double n0, n1;
-        relb2(task == 0 ? lr.ehlo : lr.ehhi, c, n0, n1);
-        double norm = 0.0;
-        norm = norm + n0;
-        norm = norm + n1;
-        norm = norm * sqrt(GFAC_H);
-        if (task == 0) sm.rad[r].nlo = norm; else sm.rad[r].nhi = norm;
-      }
-    } else if (warp == 2) {
-      const bool valid = lane < n;
-      const int ielo = valid ? sm.rad[lane & (LN_R - 1)].ielo : n_ener, iehi = valid ? sm.rad[lane & (LN_R - 1)].iehi : -1;
-      int jlo = (iehi >= ielo) ? ielo : n_ener, jhi = (iehi >= ielo) ? iehi : -1;
+    __syncwarp();
+    // ---- set-up, tasks 2 and 3: the integrand at the two edge nodes g* = h, 1-h
+    if (task >= 2 && r_su < n) {
+      RelbCtx c;
+      ln_ctx(sm, r_su, g_cosne, limb, c);
+      const LnRad &lr = sm.rad[r_su];
+      double n0, n1;
+      relb2(task == 2 ? lr.ehlo : lr.ehhi, c, n0, n1);
+      double norm = 0.0;
+      norm = norm + n0;
+      norm = norm + n1;
+      norm = norm * sqrt(GFAC_H);
+      if (task == 2) sm.rad[r_su].nlo = norm; else sm.rad[r_su].nhi = norm;
+    }
+    // the sub-batch's bin range
+    int jlo, jhi;
+    {
+      const bool valid = r_su < n;
+      const int ielo = valid ? sm.rad[r_su].ielo : n_ener, iehi = valid ? sm.rad[r_su].iehi : -1;
+      jlo = (iehi >= ielo) ? ielo : n_ener; jhi = (iehi >= ielo) ? iehi : -1;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int o = LN_R / 2; o > 0; o >>= 1) {
         jlo = min(jlo, __shfl_xor_sync(FULL, jlo, o));
         jhi = max(jhi, __shfl_xor_sync(FULL, jhi, o));
       }
-      if (lane == 0) {
-        const int zlo = sm.zlo, zhi = sm.zhi;
-        sm.zold_lo = zlo; sm.zold_hi = zhi;
-        if (jhi >= jlo && zhi >= zlo) {   // close a gap between the zone's range so far and this sub-batch's
-          if (zhi < jlo) jlo = zhi + 1;
-          if (zlo > jhi) jhi = zlo - 1;
-        }
-        const int nzlo = min(zlo, jlo), nzhi = max(zhi, jhi);
-        sm.zlo = nzlo; sm.zhi = nzhi;
-        // the last sub-batch visits the zone's whole range: it finishes the row (division by the bin energy)
-        sm.jlo = last_batch ? nzlo : jlo;
-        sm.jhi = last_batch ? nzhi : jhi;
-        sm.next_tile = 0;
-      }
     }
-    __syncthreads();
+    const int zold_lo = zlo, zold_hi = zhi;
+    if (jhi >= jlo && zhi >= zlo) {   // close a gap between the zone's range so far and this sub-batch's
+      if (zhi < jlo) jlo = zhi + 1;
+      if (zlo > jhi) jhi = zlo - 1;
+    }
+    zlo = min(zlo, jlo); zhi = max(zhi, jhi);
+    // the last sub-batch visits the zone's whole range: it finishes the row (division by the bin energy)
+    if (last_batch) { jlo = zlo; jhi = zhi; }
+    __syncwarp();
 
-    // ---- main loop: warp = tile of 15 bins, half warp = radius, lane = bin edge.  Tiles are handed out through a
-    // counter, the Romberg tiles (the expensive ones) first.
-    {
-      const int jlo = sm.jlo, jhi = sm.jhi, zold_lo = sm.zold_lo, zold_hi = sm.zold_hi;
+    // ---- main loop: tile of 15 bins, half warp = radius, lane = bin edge; the Romberg tiles first
+    if (jhi >= jlo) {
       const int half = lane >> 4, hl = lane & 15;
-      int *slot = sm.slot[warp];
+      int ndq = 0;   // bins waiting in the deep queue
       // tiles anchored at j95: tile k covers bins [j95 + k LN_TB, j95 + (k+1) LN_TB)
       const int k_lo = (jlo - j95 >= 0) ? (jlo - j95) / LN_TB : -((j95 - jlo + LN_TB - 1) / LN_TB);
       const int k_hi = (jhi - j95 >= 0) ? (jhi - j95) / LN_TB : -((j95 - jhi + LN_TB - 1) / LN_TB);
       const int npair = (n + 1) >> 1;
-      while (jhi >= jlo) {
-        int k = 0;
-        if (lane == 0) k = atomicAdd(&sm.next_tile, 1);
-        k = k_hi - __shfl_sync(FULL, k, 0);
-        if (k < k_lo) break;
+      for (int k = k_hi; k >= k_lo; k--) {
         const int j = j95 + k * LN_TB + hl;                     // this lane's edge; its bin if hl < 15
         const double Ea = line_edge(egrid, min(max(j, 0), n_ener), grid_mode, zred, lineE);
         const double Eb = line_edge(egrid, min(max(j + 1, 0), n_ener), grid_mode, zred, lineE);
         const bool binlane = (hl < LN_TB) && (j >= jlo) && (j <= jhi);
         double acc = (binlane && (j >= zold_lo) && (j <= zold_hi)) ? flux[j] : 0.0;
-        if (k < 0) {
-          // ---------------- midpoint-rule tile (int_romb with lo < 0.95, src/Relprofile.cpp:628-647)
-          for (int pr = 0; pr < npair; pr++) {
-            const int rsel = 2 * pr + half;
-            const LnRad &lr = sm.rad[rsel];
-            const bool in = binlane && (j >= lr.ielo) && (j <= lr.iehi);
-            if (!__any_sync(FULL, in)) continue;
-            // limits of the quadrature: the bin, cut at the ends of the analytic edge intervals (the reference takes
-            // these decisions in g*; an ulp of difference moves the cut by an ulp)
-            const double ehlo = lr.ehlo, ehhi = lr.ehhi;
-            const bool e_lo = Ea < ehlo, e_hi = Eb > ehhi;
-            const double Xa = e_lo ? ehlo : Ea, Xb = e_hi ? ehhi : Eb;
-            const double w = Xb - Xa;
-            RelbCtx c;
-            c.gmin = lr.gmin; c.del_g = lr.del_g; c.scale = lr.scale;
-            c.row = smem_u32(&sm.fine[rsel][0]);
-            c.cosne = g_cosne + (size_t) lr.gi * NG; c.limb = limb;
-            double flu = 0.0;
-            if (in && (e_lo || e_hi)) flu = edge_terms(Ea, Eb, c.gmin, c.del_g, lr.dgm, lr.nlo, lr.nhi);
-            double m0, m1;
-            relb2((Xb + Xa) / 2.0, c, m0, m1);
-            if (in && w > 0.0) {
-              if (Xa >= LK.e95) {   // the lower limit was raised past 0.95: Romberg
-                flu = flu + romberg_bin(Xa, w, c);
-              } else {
+        // the radius pairs of the sub-batch; the bins that need Romberg levels 3+ wait in the queue, which is worked off
+        // (one copy of that code) when it cannot take another visit and at the end of the tile
+        for (int pr = 0;;) {
+          if (k < 0) {
+            // ---------------- midpoint-rule tile (int_romb with lo < 0.95, src/Relprofile.cpp:628-647)
+            for (; pr < npair; pr++) {
+              const int rsel = 2 * pr + half;
+              const LnRad &lr = sm.rad[rsel];
+              const bool in = binlane && (j >= lr.ielo) && (j <= lr.iehi);
+              if (!__any_sync(FULL, in)) continue;
+              // limits of the quadrature: the bin, cut at the ends of the analytic edge intervals (the reference takes
+              // these decisions in g*; an ulp of difference moves the cut by an ulp)
+              const double ehlo = lr.ehlo, ehhi = lr.ehhi;
+              const bool e_lo = Ea < ehlo, e_hi = Eb > ehhi;
+              const double Xa = e_lo ? ehlo : Ea, Xb = e_hi ? ehhi : Eb;
+              const double w = Xb - Xa;
+              RelbCtx c;
+              c.gmin = lr.gmin; c.del_g = lr.del_g; c.scale = lr.scale;
+              c.row = smem_u32(&sm.fine[rsel][0]);
+              c.cosne = g_cosne + (size_t) lr.gi * NG; c.limb = limb;
+              double flu = 0.0;
+              if (in && (e_lo || e_hi)) flu = edge_terms(Ea, Eb, c.gmin, c.del_g, lr.dgm, lr.nlo, lr.nhi);
+              double m0, m1;
+              relb2((Xb + Xa) / 2.0, c, m0, m1);
+              const bool quad = in && w > 0.0;
+              const bool hard = quad && (Xa >= LK.e95);   // the lower limit was raised past 0.95: Romberg, by deep_flush
+              if (quad && !hard) {
                 double f2 = 0.0;
                 f2 += m0 * w;
                 f2 += m1 * w;
                 flu = flu + f2;
               }
-            }
-            // ascending-radius accumulation: the lower half's radius first, then the upper half's
-            const double own = in ? flu * lr.weight : 0.0;
-            const double oth = __shfl_xor_sync(FULL, own, 16);
-            acc = (acc + (half ? oth : own)) + (half ? own : oth);
-          }
-        } else {
-          // ---------------- Romberg tile (src/Relprofile.cpp:524-579), both branches
-          for (int pr = 0; pr < npair; pr++) {
-            const int rsel = 2 * pr + half;
-            const LnRad &lr = sm.rad[rsel];
-            const bool in = binlane && (j >= lr.ielo) && (j <= lr.iehi);
-            if (!__any_sync(FULL, in)) continue;
-            const double ehlo = lr.ehlo, ehhi = lr.ehhi;
-            // every lane evaluates the integrand at its own lower edge, clamped to the quadrature's range: that is
-            // the lower limit of its bin and the upper limit of the neighbour's
-            const double Xa = (Ea < ehlo) ? ehlo : ((Ea > ehhi) ? ehhi : Ea);
-            const double Xb = (Eb < ehlo) ? ehlo : ((Eb > ehhi) ? ehhi : Eb);
-            const double pas = Xb - Xa;
-            const bool romb = in && (pas > 0.0);
-            RelbCtx c;
-            c.gmin = lr.gmin; c.del_g = lr.del_g; c.scale = lr.scale;
-            c.row = smem_u32(&sm.fine[rsel][0]);
-            c.cosne = g_cosne + (size_t) lr.gi * NG; c.limb = limb;
-            double flu = 0.0;
-            if (in && (Ea < ehlo || Eb > ehhi)) flu = edge_terms(Ea, Eb, c.gmin, c.del_g, lr.dgm, lr.nlo, lr.nhi);
-            double sum[2], tq[2][4], res[2];
-            bool done[2];
-            int need = 0;
-            {
-              double fa0, fa1, fm0, fm1;
-              relb2(Xa, c, fa0, fa1);
-              const double fb0 = __shfl_down_sync(FULL, fa0, 1, 16), fb1 = __shfl_down_sync(FULL, fa1, 1, 16);
-              const double pas1 = pas / 2.0, pas2 = pas1 / 2.0;
-              relb2(Xa + pas1 * 1, c, fm0, fm1);
-              double t01[2];
-              bool lvl2 = false;
-#pragma unroll
-              for (int kk = 0; kk < 2; kk++) {
-                const double ta = ((kk ? fa1 : fa0) + (kk ? fb1 : fb0)) / 2.0;
-                sum[kk] = ta;
-                const double t00 = ta * pas;
-                t01[kk] = (ta + (kk ? fm1 : fm0)) * pas1;
-                const double t10 = richardson(1, t01[kk], t00);
-                tq[kk][0] = t10;
-                res[kk] = t10;
-                done[kk] = !not_converged(t10, t00);
-                lvl2 |= !done[kk];
+              if (__any_sync(FULL, hard)) {
+                const unsigned dm = __ballot_sync(FULL, hard);
+                if (ndq + __popc(dm) > LN_DQ) break;   // no room: flush, then this visit again
+                if (hard) {
+                  LnDeep &d = sm.dq[ndq + __popc(dm & ((1u << lane) - 1))];
+                  d.a = Xa; d.pas = w; d.rsel = rsel; d.hl = hl; d.flags = 1 << 8;
+                }
+                ndq += __popc(dm);
+                __syncwarp();
               }
-              if (__any_sync(FULL, romb && lvl2)) {
-                double q0, q1, u0, u1;
-                relb2(Xa + pas2 * 1, c, q0, q1);
-                relb2(Xa + pas2 * 3, c, u0, u1);
-#pragma unroll
+              // ascending-radius accumulation: the lower half's radius first, then the upper half's
+              const double own = in ? flu * lr.weight : 0.0;
+              const double oth = __shfl_xor_sync(FULL, own, 16);
+              acc = (acc + (half ? oth : own)) + (half ? own : oth);
+            }
+          } else {
+            // ---------------- Romberg tile (src/Relprofile.cpp:524-579), both branches
+            for (; pr < npair; pr++) {
+              const int rsel = 2 * pr + half;
+              const LnRad &lr = sm.rad[rsel];
+              const bool in = binlane && (j >= lr.ielo) && (j <= lr.iehi);
+              if (!__any_sync(FULL, in)) continue;
+              const double ehlo = lr.ehlo, ehhi = lr.ehhi;
+              // every lane evaluates the integrand at its own lower edge, clamped to the quadrature's range: that is
+              // the lower limit of its bin and the upper limit of the neighbour's
+              const double Xa = (Ea < ehlo) ? ehlo : ((Ea > ehhi) ? ehhi : Ea);
+              const double Xb = (Eb < ehlo) ? ehlo : ((Eb > ehhi) ? ehhi : Eb);
+              const double pas = Xb - Xa;
+              const bool romb = in && (pas > 0.0);
+              RelbCtx c;
+              c.gmin = lr.gmin; c.del_g = lr.del_g; c.scale = lr.scale;
+              c.row = smem_u32(&sm.fine[rsel][0]);
+              c.cosne = g_cosne + (size_t) lr.gi * NG; c.limb = limb;
+              double flu = 0.0;
+              if (in && (Ea < ehlo || Eb > ehhi)) flu = edge_terms(Ea, Eb, c.gmin, c.del_g, lr.dgm, lr.nlo, lr.nhi);
+              double sum[2], tq[2][4], res[2];
+              bool done[2];
+              int need = 0;
+              {
+                double fa0, fa1, fm0, fm1;
+                relb2(Xa, c, fa0, fa1);
+                const double fb0 = __shfl_down_sync(FULL, fa0, 1, 16), fb1 = __shfl_down_sync(FULL, fa1, 1, 16);
+                const double pas1 = pas / 2.0, pas2 = pas1 / 2.0;
+                relb2(Xa + pas1 * 1, c, fm0, fm1);
+                double t01[2];
+                bool lvl2 = false;
+  #pragma unroll
                 for (int kk = 0; kk < 2; kk++) {
-                  // ((ta + f(q1)) + f(mid)) + f(q3): the reference's ascending order
-                  sum[kk] = ((sum[kk] + (kk ? q1 : q0)) + (kk ? fm1 : fm0)) + (kk ? u1 : u0);
-                  if (!done[kk]) {
-                    const double t02 = sum[kk] * pas2;
-                    const double t11 = richardson(1, t02, t01[kk]);
-                    const double t20 = richardson(2, t11, tq[kk][0]);
-                    done[kk] = !not_converged(t20, res[kk]);
-                    res[kk] = t20;
-                    tq[kk][0] = t11; tq[kk][1] = t20;
-                    if (!done[kk]) need = 3;
-                  }
+                  const double ta = ((kk ? fa1 : fa0) + (kk ? fb1 : fb0)) / 2.0;
+                  sum[kk] = ta;
+                  const double t00 = ta * pas;
+                  t01[kk] = (ta + (kk ? fm1 : fm0)) * pas1;
+                  const double t10 = richardson(1, t01[kk], t00);
+                  tq[kk][0] = t10;
+                  res[kk] = t10;
+                  done[kk] = !not_converged(t10, t00);
+                  lvl2 |= !done[kk];
                 }
-                if (!romb) need = 0;
-              }
-            }
-            if (__any_sync(FULL, need == 3)) {
-              romberg_level<3>(sm, slot, lane, rsel, g_cosne, limb, Xa, pas, need, sum, tq, res, done);
-              if (__any_sync(FULL, need == 4)) {
-                romberg_level<4>(sm, slot, lane, rsel, g_cosne, limb, Xa, pas, need, sum, tq, res, done);
-                if (need == 5) {   // levels 5-6: by the owning lane
-                  RombIn in;
-#pragma unroll
+                if (__any_sync(FULL, romb && lvl2)) {
+                  double q0, q1, u0, u1;
+                  relb2(Xa + pas2 * 1, c, q0, q1);
+                  relb2(Xa + pas2 * 3, c, u0, u1);
+  #pragma unroll
                   for (int kk = 0; kk < 2; kk++) {
-                    in.sum[kk] = sum[kk];
-                    in.tp[kk][0] = sum[kk] * (pas * (1.0 / 16.0));
-#pragma unroll
-                    for (int ii = 0; ii < 4; ii++) in.tp[kk][ii + 1] = tq[kk][ii];
-                    in.res[kk] = res[kk];
-                    in.done[kk] = done[kk] ? 1 : 0;
+                    // ((ta + f(q1)) + f(mid)) + f(q3): the reference's ascending order
+                    sum[kk] = ((sum[kk] + (kk ? q1 : q0)) + (kk ? fm1 : fm0)) + (kk ? u1 : u0);
+                    if (!done[kk]) {
+                      const double t02 = sum[kk] * pas2;
+                      const double t11 = richardson(1, t02, t01[kk]);
+                      const double t20 = richardson(2, t11, tq[kk][0]);
+                      done[kk] = !not_converged(t20, res[kk]);
+                      res[kk] = t20;
+                      tq[kk][0] = t11; tq[kk][1] = t20;
+                      if (!done[kk]) need = 3;
+                    }
                   }
-                  res[0] = romberg_serial(Xa, pas, c, in, 5);
-                  res[1] = 0.0;
+                  if (!romb) need = 0;
                 }
               }
+              if (__any_sync(FULL, need == 3)) {   // queue the bins that go on to level 3
+                const unsigned dm = __ballot_sync(FULL, need == 3);
+                if (ndq + __popc(dm) > LN_DQ) break;   // no room (a visit defers at most 30 bins): flush, then this visit again
+                if (need == 3) {
+                  LnDeep &d = sm.dq[ndq + __popc(dm & ((1u << lane) - 1))];
+                  d.a = Xa; d.pas = pas; d.rsel = rsel; d.hl = hl;
+  #pragma unroll
+                  for (int kk = 0; kk < 2; kk++) {
+                    d.sum[kk] = sum[kk];
+                    d.tq[kk][0] = done[kk] ? res[kk] : tq[kk][0];
+                    d.tq[kk][1] = tq[kk][1];
+                  }
+                  d.flags = (done[0] ? 1 : 0) | (done[1] ? 2 : 0) | (3 << 8);
+                }
+                ndq += __popc(dm);
+                __syncwarp();
+              }
+              if (romb && need == 0) {
+                double rsum = 0.0;
+                rsum += res[0];
+                rsum += res[1];
+                flu = flu + rsum;
+              }
+              const double own = in ? flu * lr.weight : 0.0;
+              const double oth = __shfl_xor_sync(FULL, own, 16);
+              acc = (acc + (half ? oth : own)) + (half ? own : oth);
             }
-            if (romb) {
-              double rsum = 0.0;
-              rsum += res[0];
-              rsum += res[1];
-              flu = flu + rsum;
-            }
-            const double own = in ? flu * lr.weight : 0.0;
-            const double oth = __shfl_xor_sync(FULL, own, 16);
-            acc = (acc + (half ? oth : own)) + (half ? own : oth);
           }
+          if (ndq) { acc += deep_flush(sm, ndq, lane, g_cosne, limb); ndq = 0; }
+          if (pr >= npair) break;
         }
         if (binlane && half == 0) {
           // only the bins this zone touched are written; the range travels with the row
@@ -641,26 +692,26 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
       }
     }
     cur += n;
-    if (cur < ib) __syncthreads();   // the shared-memory stage and the row in HBM are taken over by the next sub-batch
+    __syncwarp();   // the shared-memory stage and the row in HBM are taken over by the next sub-batch
   }
-  if (t == 0) {
-    S.zrange[((size_t) v * NZMAX + z) * 2] = sm.zlo;
-    S.zrange[((size_t) v * NZMAX + z) * 2 + 1] = sm.zhi;
+  if (lane == 0) {
+    S.zrange[((size_t) v * NZMAX + z) * 2] = zlo;
+    S.zrange[((size_t) v * NZMAX + z) * 2 + 1] = zhi;
   }
 }
 
 // ---------------------------------------------------------------------------------- launcher
-static int g_minb = 8;
+static int g_minb = 24;
 template <int MINB> static int line_init_one() {
   // MINB CTAs x 18.6 KB of shared memory: the rest of the 256 KB stays L1 (energy grid, per-radius inputs, spills)
-  cudaError_t e = cudaFuncSetAttribute(k_line<0, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, MINB * 9);
+  cudaError_t e = cudaFuncSetAttribute(k_line<0, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (e != cudaSuccess) return 1;
-  e = cudaFuncSetAttribute(k_line<1, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, MINB * 9);
+  e = cudaFuncSetAttribute(k_line<1, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   return e == cudaSuccess ? 0 : 1;
 }
 int line_kernel_init() {
   if (const char *s = getenv("RELXILL_B200_LINE_MINB")) g_minb = atoi(s);
-  return line_init_one<8>() | line_init_one<6>() | line_init_one<5>();
+  return line_init_one<24>() | line_init_one<20>() | line_init_one<16>();
 }
 
 template <int MINB>
@@ -676,9 +727,9 @@ void launch_line(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
   G.e = egrid; G.n_ener = n_ener; G.mode = grid_mode;
   G.log_lo = std::log(CONV_EMIN);
   G.inv_dlog = (double) NCONV / (std::log(CONV_EMAX) - std::log(CONV_EMIN));
-  if (g_minb == 6) launch_line_t<6>(vps, T, S, grid, G, grid_mode, st);
-  else if (g_minb == 5) launch_line_t<5>(vps, T, S, grid, G, grid_mode, st);
-  else launch_line_t<8>(vps, T, S, grid, G, grid_mode, st);
+  if (g_minb == 20) launch_line_t<20>(vps, T, S, grid, G, grid_mode, st);
+  else if (g_minb == 16) launch_line_t<16>(vps, T, S, grid, G, grid_mode, st);
+  else launch_line_t<24>(vps, T, S, grid, G, grid_mode, st);
 }
 int line_max_bins() { return 1 << 24; }   // the zone accumulator lives in the output row: no shared-memory limit
 
