@@ -144,22 +144,43 @@ __device__ __noinline__ double2 relb2_limb(int ind, double inte, const double2 *
   return make_double2(1.0, 1.0);
 }
 
-// both branches of relb_func (src/Relprofile.cpp:489-521) at energy eg
-__device__ __forceinline__ void relb2(double eg, const RelbCtx &c, double &v0, double &v1) {
-  const double egstar = (eg - c.gmin) * c.del_g;
+// both branches of relb_func (src/Relprofile.cpp:489-521) at energy eg.  ONE out-of-line copy, everything passed in
+// registers: the kernel's warps walk their zones independently, and with the integrand inlined at every quadrature
+// site the instruction cache was what bounded the kernel (ncu: stall_no_instruction 3.5 per issue).
+__device__ __forceinline__ double2 relb2_fi(double eg, double gmin, double del_g, double scale, uint32_t row, int limb,
+                                        const double2 *cosne) {
+  const double egstar = (eg - gmin) * del_g;
   int ind = (int) ((egstar - LK.h) * LK.gs_invc);
   ind = ind < 0 ? 0 : (ind > NG - 2 ? NG - 2 : ind);
   const double inte = (egstar - (LK.h + LK.gs_c * (double) ind)) * LK.gs_invc;
   const double inte1 = 1.0 - inte;
-  const double2 t0 = lds_d2(c.row + ind * 16), t1 = lds_d2(c.row + ind * 16 + 16);
-  const double common = (eg * eg * eg) * rsqrt(egstar - egstar * egstar) * c.scale;
-  v0 = common * (inte * t0.x + inte1 * t1.x);   // (the reference's weights: inte on node ind, 1-inte on ind+1)
-  v1 = common * (inte * t0.y + inte1 * t1.y);
-  if (c.limb != 0) {
-    const double2 f = relb2_limb(ind, inte, c.cosne, c.limb);
-    v0 *= f.x;
-    v1 *= f.y;
+  const double2 t0 = lds_d2(row + ind * 16), t1 = lds_d2(row + ind * 16 + 16);
+  const double common = (eg * eg * eg) * rsqrt(egstar - egstar * egstar) * scale;
+  double2 v;
+  v.x = common * (inte * t0.x + inte1 * t1.x);   // (the reference's weights: inte on node ind, 1-inte on ind+1)
+  v.y = common * (inte * t0.y + inte1 * t1.y);
+  if (limb != 0) {
+    const double2 f = relb2_limb(ind, inte, cosne, limb);
+    v.x *= f.x;
+    v.y *= f.y;
   }
+  return v;
+}
+// the out-of-line copy (set-up, deep levels, whole integrations)
+__device__ __noinline__ double2 relb2_f(double eg, double gmin, double del_g, double scale, uint32_t row, int limb,
+                                        const double2 *cosne) {
+  return relb2_fi(eg, gmin, del_g, scale, row, limb, cosne);
+}
+__device__ __forceinline__ void relb2(double eg, const RelbCtx &c, double &v0, double &v1) {
+  const double2 v = relb2_f(eg, c.gmin, c.del_g, c.scale, c.row, c.limb, c.cosne);
+  v0 = v.x;
+  v1 = v.y;
+}
+// inlined: the quadrature loops of the main loop (independent evaluations overlap)
+__device__ __forceinline__ void relb2i(double eg, const RelbCtx &c, double &v0, double &v1) {
+  const double2 v = relb2_fi(eg, c.gmin, c.del_g, c.scale, c.row, c.limb, c.cosne);
+  v0 = v.x;
+  v1 = v.y;
 }
 
 // (obtprec > prec) of the reference, obtprec = fabs(t_new - t_old) / t_new  (src/Relprofile.cpp:575)
@@ -278,37 +299,35 @@ __device__ __forceinline__ void ln_ctx(const LnSmem &sm, int r, const double2 *g
   c.cosne = g_cosne + (size_t) lr.gi * NG; c.limb = limb;
 }
 
-// Levels 3+ of the queued bins, compacted over the warp (src/Relprofile.cpp:553-576): level 3 = 4 new abscissae
-// a + (2p+1) pas / 8 of 8 bins per pass, level 4 = 8 abscissae of 4 bins per pass, summed by xor-butterflies; the group's
-// first lane advances the bin's tableau in the queue entry.  What is left after level 4 (~1e-4 of the Romberg bins) and
-// the bins queued for a whole integration are finished by one lane each.  Returns, for lanes 0..14, what their bin
-// gains (already weighted with the radius' area weight); queue order = radius order, so the sum stays deterministic.
+// Levels 3+ of the queued bins, compacted over the warp (src/Relprofile.cpp:553-576): level L takes NP = 2^(L-1) lanes
+// per bin, one per new abscissa a + (2p+1) pas / 2^L (level 3: 8 bins per pass, level 4: 4), an xor-butterfly sums them
+// and the group's first lane advances the bin's tableau in the queue entry.  What is left after level 4 (~1e-4 of the
+// Romberg bins) and the bins queued for a whole integration are finished by one lane each.  Returns, for lanes 0..14,
+// what their bin gains (already weighted with the radius' area weight); queue order = radius order, so the sum is
+// deterministic.  Written for size, not speed (rolled loops, one call site of the integrand): see relb2_f.
 __device__ __forceinline__ void deep_tableau(LnDeep &d, int L, double s0, double s1) {
   const double pasn = d.pas * (1.0 / (double) (1 << L)), pasp = pasn * 2.0;
   int flags = d.flags & 3;
   bool more = false;
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < 2; k++) {
-    const double t0p = d.sum[k] * pasp;   // first tableau entry of the previous level
+    double prev = d.sum[k] * pasp;   // first tableau entry of the previous level
     const double sum = d.sum[k] + (k ? s1 : s0);
     d.sum[k] = sum;
-    if (!(flags & (1 << k))) {
-      double cur[5];
-      cur[0] = sum * pasn;
-      cur[1] = richardson(1, cur[0], t0p);
-      cur[2] = richardson(2, cur[1], d.tq[k][0]);
-      cur[3] = richardson(3, cur[2], d.tq[k][1]);
-      double last = d.tq[k][1], res = cur[3];
-      if (L == 4) { cur[4] = richardson(4, cur[3], d.tq[k][2]); last = d.tq[k][2]; res = cur[4]; }
-      if (!not_converged(res, last)) {
-        flags |= 1 << k;
-        d.tq[k][0] = res;
-      } else if (L == 3) {
-        d.tq[k][0] = cur[1]; d.tq[k][1] = cur[2]; d.tq[k][2] = cur[3];
-        more = true;
-      } else {
-        more = true;
-      }
+    if (flags & (1 << k)) continue;
+    double cur = sum * pasn, r4 = 1.0, last = 0.0;
+#pragma unroll 1
+    for (int ii = 1; ii <= L; ii++) {   // t[ii] = (4^ii t[ii-1] - tprev[ii-1]) / (4^ii - 1); tq[ii-1] holds t[ii]
+      r4 *= 4.0;
+      cur = (r4 * cur - prev) * LK.inv[ii];
+      if (ii < L) { prev = d.tq[k][ii - 1]; d.tq[k][ii - 1] = cur; last = prev; }
+    }
+    if (!not_converged(cur, last)) {
+      flags |= 1 << k;
+      d.tq[k][0] = cur;
+    } else {
+      if (L == 3) d.tq[k][2] = cur;
+      more = true;
     }
   }
   // not converged after level 4 (~1e-4 of the Romberg bins): the bin is integrated again as a whole by one lane
@@ -316,60 +335,47 @@ __device__ __forceinline__ void deep_tableau(LnDeep &d, int L, double s0, double
 }
 __device__ __forceinline__ double deep_flush(LnSmem &sm, int ndq, int lane, const double2 *g_cosne, int limb) {
   const unsigned FULL = 0xffffffffu;
-  // ---- level 3: 8 entries per pass, 4 lanes each
-  for (int b = 0; b < ndq; b += 8) {
-    const int e = min(b + (lane >> 2), ndq - 1), p = lane & 3;
-    LnDeep &d = sm.dq[e];
-    const bool act = (b + (lane >> 2) < ndq) && ((d.flags >> 8) == 3);
-    if (!__any_sync(FULL, act)) continue;
-    RelbCtx c;
-    ln_ctx(sm, d.rsel, g_cosne, limb, c);
-    double w0, w1;
-    relb2(d.a + d.pas * 0.125 * (double) (2 * p + 1), c, w0, w1);
-#pragma unroll
-    for (int o = 1; o < 4; o <<= 1) {
-      w0 += __shfl_xor_sync(FULL, w0, o);
-      w1 += __shfl_xor_sync(FULL, w1, o);
+#pragma unroll 1
+  for (int L = 3; L <= 4; L++) {
+    // the entries that need level L, in queue order
+    int nl = 0;
+#pragma unroll 1
+    for (int b = 0; b < ndq; b += 32) {
+      const int e = b + lane;
+      const bool go = (e < ndq) && ((sm.dq[min(e, ndq - 1)].flags >> 8) == L);
+      const unsigned m = __ballot_sync(FULL, go);
+      if (go) sm.slot[nl + __popc(m & ((1u << lane) - 1))] = e;
+      nl += __popc(m);
     }
-    if (act && p == 0) deep_tableau(d, 3, w0, w1);
-  }
-  __syncwarp();
-  // ---- level 4: the entries that go on, 4 per pass, 8 lanes each
-  int n4 = 0;
-  for (int b = 0; b < ndq; b += 32) {
-    const int e = b + lane;
-    const bool go = (e < ndq) && ((sm.dq[min(e, ndq - 1)].flags >> 8) == 4);
-    const unsigned m = __ballot_sync(FULL, go);
-    if (go) sm.slot[n4 + __popc(m & ((1u << lane) - 1))] = e;
-    n4 += __popc(m);
-  }
-  __syncwarp();
-  for (int b = 0; b < n4; b += 4) {
-    const int q = b + (lane >> 3), p = lane & 7;
-    const bool act = q < n4;
-    LnDeep &d = sm.dq[sm.slot[min(q, n4 - 1)]];
-    RelbCtx c;
-    ln_ctx(sm, d.rsel, g_cosne, limb, c);
-    double w0, w1;
-    relb2(d.a + d.pas * 0.0625 * (double) (2 * p + 1), c, w0, w1);
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      w0 += __shfl_xor_sync(FULL, w0, o);
-      w1 += __shfl_xor_sync(FULL, w1, o);
+    __syncwarp();
+    const int lg = L - 1, np = 1 << lg, nb = 32 >> lg;
+#pragma unroll 1
+    for (int b = 0; b < nl; b += nb) {
+      const int q = b + (lane >> lg), p = lane & (np - 1);
+      LnDeep &d = sm.dq[sm.slot[min(q, nl - 1)]];
+      RelbCtx c;
+      ln_ctx(sm, d.rsel, g_cosne, limb, c);
+      double w0, w1;
+      relb2(d.a + d.pas * (1.0 / (double) (2 << lg)) * (double) (2 * p + 1), c, w0, w1);
+#pragma unroll 1
+      for (int o = 1; o < np; o <<= 1) {
+        w0 += __shfl_xor_sync(FULL, w0, o);
+        w1 += __shfl_xor_sync(FULL, w1, o);
+      }
+      if (q < nl && p == 0) deep_tableau(d, L, w0, w1);
     }
-    if (act && p == 0) deep_tableau(d, 4, w0, w1);
+    __syncwarp();
   }
-  __syncwarp();
   // ---- the rest, one lane per entry: whole integrations (level code 1)
+#pragma unroll 1
   for (int b = 0; b < ndq; b += 32) {
     const int e = b + lane;
     if (e < ndq) {
       LnDeep &d = sm.dq[e];
-      const int lvl = d.flags >> 8;
-      RelbCtx c;
-      ln_ctx(sm, d.rsel, g_cosne, limb, c);
       double r;
-      if (lvl == 1) {
+      if ((d.flags >> 8) == 1) {
+        RelbCtx c;
+        ln_ctx(sm, d.rsel, g_cosne, limb, c);
         r = romberg_bin(d.a, d.pas, c);
       } else {
         r = 0.0;
@@ -381,6 +387,7 @@ __device__ __forceinline__ double deep_flush(LnSmem &sm, int ndq, int lane, cons
   }
   __syncwarp();
   double add = 0.0;
+#pragma unroll 1
   for (int e = 0; e < ndq; e++)
     if (sm.dq[e].hl == lane) add += sm.dq[e].sum[0];
   __syncwarp();
@@ -566,7 +573,7 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
               double flu = 0.0;
               if (in && (e_lo || e_hi)) flu = edge_terms(Ea, Eb, c.gmin, c.del_g, lr.dgm, lr.nlo, lr.nhi);
               double m0, m1;
-              relb2((Xb + Xa) / 2.0, c, m0, m1);
+              relb2i((Xb + Xa) / 2.0, c, m0, m1);
               const bool quad = in && w > 0.0;
               const bool hard = quad && (Xa >= LK.e95);   // the lower limit was raised past 0.95: Romberg, by deep_flush
               if (quad && !hard) {
@@ -615,10 +622,10 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
               int need = 0;
               {
                 double fa0, fa1, fm0, fm1;
-                relb2(Xa, c, fa0, fa1);
+                relb2i(Xa, c, fa0, fa1);
                 const double fb0 = __shfl_down_sync(FULL, fa0, 1, 16), fb1 = __shfl_down_sync(FULL, fa1, 1, 16);
                 const double pas1 = pas / 2.0, pas2 = pas1 / 2.0;
-                relb2(Xa + pas1 * 1, c, fm0, fm1);
+                relb2i(Xa + pas1 * 1, c, fm0, fm1);
                 double t01[2];
                 bool lvl2 = false;
   #pragma unroll
@@ -635,8 +642,8 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
                 }
                 if (__any_sync(FULL, romb && lvl2)) {
                   double q0, q1, u0, u1;
-                  relb2(Xa + pas2 * 1, c, q0, q1);
-                  relb2(Xa + pas2 * 3, c, u0, u1);
+                  relb2i(Xa + pas2 * 1, c, q0, q1);
+                  relb2i(Xa + pas2 * 3, c, u0, u1);
   #pragma unroll
                   for (int kk = 0; kk < 2; kk++) {
                     // ((ta + f(q1)) + f(mid)) + f(q3): the reference's ascending order
@@ -701,7 +708,7 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
 }
 
 // ---------------------------------------------------------------------------------- launcher
-static int g_minb = 24;
+static int g_minb = 20;
 template <int MINB> static int line_init_one() {
   // MINB CTAs x 18.6 KB of shared memory: the rest of the 256 KB stays L1 (energy grid, per-radius inputs, spills)
   cudaError_t e = cudaFuncSetAttribute(k_line<0, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
