@@ -86,7 +86,8 @@ struct LnDeep {
   int rsel, hl;                  // radius of the sub-batch, owning lane
   int flags, pad;                // bits 0-1: branch finished; bits 8-..: level still to do (1: all of it, 3, 4, 5; 0: done)
 };
-constexpr int LN_DQ = (LN_ROWS * NG * 16) / (int) sizeof(LnDeep);   // 26: the queue lives in the row stage, dead in the main loop
+// the queue lives in the row stage, dead in the main loop; at most one entry per lane (deep_flush)
+constexpr int LN_DQ = ((LN_ROWS * NG * 16) / (int) sizeof(LnDeep)) < 32 ? ((LN_ROWS * NG * 16) / (int) sizeof(LnDeep)) : 32;
 struct LnSmem {
   union {
     double2 rows[LN_ROWS][NG];   // bulk-copy destination
@@ -335,61 +336,82 @@ __device__ __forceinline__ void deep_tableau(LnDeep &d, int L, double s0, double
 }
 __device__ __forceinline__ double deep_flush(LnSmem &sm, int ndq, int lane, const double2 *g_cosne, int limb) {
   const unsigned FULL = 0xffffffffu;
+  // ---- level 3, one lane per entry: its four new abscissae in ascending order, then the tableau
+  {
+    LnDeep &d = sm.dq[min(lane, ndq - 1)];
+    const bool go = (lane < ndq) && ((d.flags >> 8) == 3);
+    if (__any_sync(FULL, go)) {
+      RelbCtx c;
+      ln_ctx(sm, d.rsel, g_cosne, limb, c);
+      const double a = d.a, pas8 = d.pas * 0.125;
+      double s0 = 0.0, s1 = 0.0;
 #pragma unroll 1
-  for (int L = 3; L <= 4; L++) {
-    // the entries that need level L, in queue order
-    int nl = 0;
-#pragma unroll 1
-    for (int b = 0; b < ndq; b += 32) {
-      const int e = b + lane;
-      const bool go = (e < ndq) && ((sm.dq[min(e, ndq - 1)].flags >> 8) == L);
-      const unsigned m = __ballot_sync(FULL, go);
-      if (go) sm.slot[nl + __popc(m & ((1u << lane) - 1))] = e;
-      nl += __popc(m);
+      for (int p = 1; p < 8; p += 2) {
+        double w0, w1;
+        relb2(a + pas8 * (double) p, c, w0, w1);
+        s0 += w0;
+        s1 += w1;
+      }
+      if (go) deep_tableau(d, 3, s0, s1);
     }
+  }
+  __syncwarp();
+  // ---- level 4: the entries that go on, compacted, 4 per pass with 8 lanes each
+  {
+    const bool go = (lane < ndq) && ((sm.dq[min(lane, ndq - 1)].flags >> 8) == 4);
+    const unsigned m = __ballot_sync(FULL, go);
+    const int nl = __popc(m);
+    if (go) sm.slot[__popc(m & ((1u << lane) - 1))] = lane;
     __syncwarp();
-    const int lg = L - 1, np = 1 << lg, nb = 32 >> lg;
 #pragma unroll 1
-    for (int b = 0; b < nl; b += nb) {
-      const int q = b + (lane >> lg), p = lane & (np - 1);
+    for (int b = 0; b < nl; b += 4) {
+      const int q = b + (lane >> 3), p = lane & 7;
       LnDeep &d = sm.dq[sm.slot[min(q, nl - 1)]];
       RelbCtx c;
       ln_ctx(sm, d.rsel, g_cosne, limb, c);
       double w0, w1;
-      relb2(d.a + d.pas * (1.0 / (double) (2 << lg)) * (double) (2 * p + 1), c, w0, w1);
-#pragma unroll 1
-      for (int o = 1; o < np; o <<= 1) {
+      relb2(d.a + d.pas * 0.0625 * (double) (2 * p + 1), c, w0, w1);
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
         w0 += __shfl_xor_sync(FULL, w0, o);
         w1 += __shfl_xor_sync(FULL, w1, o);
       }
-      if (q < nl && p == 0) deep_tableau(d, L, w0, w1);
+      if (q < nl && p == 0) deep_tableau(d, 4, w0, w1);
     }
     __syncwarp();
   }
-  // ---- the rest, one lane per entry: whole integrations (level code 1)
-#pragma unroll 1
-  for (int b = 0; b < ndq; b += 32) {
-    const int e = b + lane;
-    if (e < ndq) {
-      LnDeep &d = sm.dq[e];
-      double r;
-      if ((d.flags >> 8) == 1) {
-        RelbCtx c;
-        ln_ctx(sm, d.rsel, g_cosne, limb, c);
-        r = romberg_bin(d.a, d.pas, c);
-      } else {
-        r = 0.0;
-        r += d.tq[0][0];
-        r += d.tq[1][0];
-      }
-      d.sum[0] = r * sm.rad[d.rsel].weight;
+  // ---- results, one lane per entry (whole integrations, level code 1, are done here); the owning lanes (0..14) pick
+  // them up through shared memory, entries of the same bin summed in queue order
+  double cwt = 0.0;
+  int hl = -1 - lane;
+  if (lane < ndq) {
+    LnDeep &d = sm.dq[lane];
+    hl = d.hl;
+    double r;
+    if ((d.flags >> 8) == 1) {
+      RelbCtx c;
+      ln_ctx(sm, d.rsel, g_cosne, limb, c);
+      r = romberg_bin(d.a, d.pas, c);
+    } else {
+      r = 0.0;
+      r += d.tq[0][0];
+      r += d.tq[1][0];
     }
+    cwt = r * sm.rad[d.rsel].weight;
+  }
+  const unsigned same = __match_any_sync(FULL, hl);
+  double *out = reinterpret_cast<double *>(&sm.slot[0]);   // 16 doubles
+  if (lane < ndq) sm.dq[lane].sum[0] = cwt;
+  if (lane < 16) out[lane] = 0.0;
+  __syncwarp();
+  if (lane < ndq && lane == __ffs(same) - 1) {
+    double tot = 0.0;
+#pragma unroll 1
+    for (unsigned mm = same; mm; mm &= mm - 1) tot += sm.dq[__ffs(mm) - 1].sum[0];   // ascending lanes = queue order
+    out[hl] = tot;
   }
   __syncwarp();
-  double add = 0.0;
-#pragma unroll 1
-  for (int e = 0; e < ndq; e++)
-    if (sm.dq[e].hl == lane) add += sm.dq[e].sum[0];
+  const double add = (lane < 16) ? out[lane] : 0.0;
   __syncwarp();
   return add;
 }
@@ -659,6 +681,9 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
                     }
                   }
                   if (!romb) need = 0;
+#ifdef EXP_NODEEP
+                need = 0;
+#endif
                 }
               }
               if (__any_sync(FULL, need == 3)) {   // queue the bins that go on to level 3
