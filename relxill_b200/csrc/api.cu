@@ -331,7 +331,7 @@ struct relxill_b200_batch {
   const ModelDef *m = nullptr;
   long n = 0;
   int n_flux = 0;
-  int nz_max = 1;
+  int nz_max = 1, nz_min = 1;
   bool any_corr = false;
   bool any_limb = false;      // some vector uses a limb law: k_fine must keep the emission angles for k_line
   int renorm3 = 0;            // RELXILL_RENORMALIZE as read when the parameters were interpreted
@@ -412,7 +412,9 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
   const long cap = std::min(b->n, cc.max_chunk);
   // the previous run on this arena may still be in flight on another stream
   if (E.arena_busy_set && st != E.arena_stream) CK(cudaStreamWaitEvent(st, E.arena_busy, 0));
-  if (ensure_scratch(E, cap, b->nz_max, ne_line, nex_stride, nth)) return -2;
+  const int nz_line_min = relxill ? b->nz_min : 1, nz_line_max = relxill ? b->nz_max : 1;
+  const int line_nk = line_launches(nz_line_min, nz_line_max);
+  if (ensure_scratch(E, cap, xillver ? b->nz_max : std::max(b->nz_max, line_rows(nz_line_min, nz_line_max)), ne_line, nex_stride, nth)) return -2;
   const Scratch S0 = E.S;
   b->launches = 0;
   for (int k = 0; k < KF_COUNT; k++) { b->kt_ms[k] = 0; b->kt_n[k] = 0; }
@@ -512,10 +514,10 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
       tm.begin(); launch_dist(vps, T, S, nc, n_incl, st); tm.end(KF_DIST);
     }
     if (m.type == T_LINE) {
-      tm.begin(); launch_line(vps, T, S, nc, b->d_energy, b->n_flux, 1, 1, st); tm.end(KF_LINE);
+      tm.begin(); launch_line(vps, T, S, nc, b->d_energy, b->n_flux, 1, 1, 1, st); tm.end(KF_LINE, line_nk);
       tm.begin(); launch_linefinish(vps, S, nc, b->n_flux, out, st); tm.end(KF_FINISH);
     } else {
-      tm.begin(); launch_line(vps, T, S, nc, T.econv, NCONV, 0, relxill ? b->nz_max : 1, st); tm.end(KF_LINE);
+      tm.begin(); launch_line(vps, T, S, nc, T.econv, NCONV, 0, nz_line_min, nz_line_max, st); tm.end(KF_LINE, line_nk);
       if (relxill) {
         tm.begin(); launch_xill(vps, T, S, nc, which, cgrid, st); tm.end(KF_XILL);
         tm.begin(); launch_conv(vps, T, S, nc, b->d_energy, b->n_flux, out, S.total, which, 0, cgrid, b->renorm3, st); tm.end(KF_CONV);
@@ -575,11 +577,13 @@ void interpret_all(Engine &E, relxill_b200_batch *b, const double *params, const
     for (auto &x : th) x.join();
   }
   b->nz_max = 1;
+  b->nz_min = NZMAX;
   b->any_corr = b->any_limb = false;
   b->renorm3 = cc.cfg.env_renorm_relxill;
   for (long i = 0; i < n_vec; i++) {
     if (b->vps[i].status == ST_OK) {
       b->nz_max = std::max(b->nz_max, b->vps[i].nz);
+      b->nz_min = std::min(b->nz_min, b->vps[i].nz);
       if (b->vps[i].do_corr) b->any_corr = true;
       if (b->vps[i].limb != 0) b->any_limb = true;
     }

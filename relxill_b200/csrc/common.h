@@ -10,6 +10,12 @@ constexpr int NR = 1000;       // fine radial grid
 constexpr int NG = 40;         // g* grid
 constexpr double CONV_EMIN = 0.00035, CONV_EMAX = 2000.0;   // convolution grid, src/Xillspec.h:36-38
 constexpr int NCONV = 4096;    // convolution grid bins
+constexpr int LINE_PARTS = 64; // partial rows of the line profile per vector at most (zones x runs, line.cu)
+// runs the radii of a zone are cut into for the line profile (line.cu), a function of the vector's zone count alone
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline int line_parts(int nz) { return nz == 1 ? 8 : (nz <= 8 ? 4 : 1); }
 constexpr int NCOARSE = 500;   // xillver-normalisation grid bins
 constexpr int NZMAX = 50;      // radial zones
 constexpr int REL_NA = 25, REL_NMU = 30, REL_NRT = 100;
@@ -143,6 +149,7 @@ struct DevTables {
   X(int, xn, 1)                    /* number of rest corners per zone */                                                  \
   X(double, relflux, (size_t) nzc * nec)   /* [nz_cap][ne_line_cap] (valid inside zrange only) */                         \
   X(int, zrange, NZMAX * 2)        /* first/last bin written per zone (-1: none) */                                       \
+  X(int, zrpart, LINE_PARTS * 2)   /* the same per partial row of a split zone (k_line -> k_linemerge) */                 \
   X(double, dist, NZMAX * MAX_INCL)                                                                                       \
   X(double, distpart, NR * 10)     /* per-radius parts of dist (k_fine -> k_dist) */                                      \
   X(double, xillz, (size_t) nzc * nxs)     /* zone spectra: rows of XillDev::xc_stride (convolution grid) or ::stride */  \

@@ -14,8 +14,12 @@ void launch_zone(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
 void launch_fine(const VPar *vps, const DevTables &T, const Scratch &S, long n, int n_incl, double e_first,
                  double e_last, int store_cosne, int store_trff, cudaStream_t st);
 void launch_dist(const VPar *vps, const DevTables &T, const Scratch &S, long n, int n_incl, cudaStream_t st);
+// nz_min, nz_max: zone counts in the batch.  Vectors with few zones have their radii cut into line_parts(nz) runs, summed
+// by a second kernel: the arena needs line_rows(nz_min, nz_max) profile rows per vector
+int line_rows(int nz_min, int nz_max);
+int line_launches(int nz_min, int nz_max);
 void launch_line(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *egrid, int n_ener,
-                 int grid_mode, int nz_max, cudaStream_t st);
+                 int grid_mode, int nz_min, int nz_max, cudaStream_t st);
 int line_max_bins();  // largest energy grid the line kernel handles in one pass
 void launch_linefinish(const VPar *vps, const Scratch &S, long n, int n_ener, double *out, cudaStream_t st);
 // conv_grid != 0: zone spectra are filed (k_xill) and read (k_conv) on the convolution grid, see xill.cu

@@ -449,8 +449,21 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
   const int limb = vp.limb;
   // radii of this zone (izone[] is non-increasing along the descending-radius fine grid; k_syspar tabulated
   // the first index of every zone)
-  const int ia = S.zfirst[(size_t) v * (NZMAX + 1) + z + 1], ib = S.zfirst[(size_t) v * (NZMAX + 1) + z];
-  double *flux = S.relflux + ((size_t) v * nz_stride + z) * ne_stride;   // doubles as the zone accumulator
+  int ia = S.zfirst[(size_t) v * (NZMAX + 1) + z + 1], ib = S.zfirst[(size_t) v * (NZMAX + 1) + z];
+  // Vectors with few zones (line and convolution models, the one-zone relxill flavours): the zone's radii are cut into
+  // line_parts(nz) runs, one CTA each, whose partial rows k_linemerge adds in ascending order; the division by the bin
+  // energy is left to it.  The cut depends on the vector's own zone count only, so a spectrum does not depend on the
+  // batch it is evaluated in.
+  const int nsplit = line_parts(vp.nz);
+  if ((int) blockIdx.z >= nsplit) return;
+  const bool whole = nsplit == 1;
+  const int row = whole ? z : z * nsplit + (int) blockIdx.z;
+  if (!whole) {
+    const int len = ((ib - ia + nsplit - 1) / nsplit + LN_R - 1) / LN_R * LN_R;
+    ia = min(ib, ia + (int) blockIdx.z * len);
+    ib = min(ib, ia + len);
+  }
+  double *flux = S.relflux + ((size_t) v * nz_stride + row) * ne_stride;   // doubles as the accumulator
   const int *g_it = S.it + (size_t) v * NR;
   const double2 *g_rows = reinterpret_cast<const double2 *>(S.relrow) + (size_t) v * REL_NRT * NG * 2;   // trff plane
   const double2 *g_cosne = reinterpret_cast<const double2 *>(S.cosne) + (size_t) v * NR * NG;
@@ -477,7 +490,7 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
       const int it1 = __shfl_sync(FULL, it, n - 1);
       if (lane == 0) bulk_load(&sm.rows[0][0], g_rows + (size_t) it0 * NG, (uint32_t) (it1 + 2 - it0) * NG * 16, &sm.mbar);
     }
-    const bool last_batch = cur + n >= ib;
+    const bool last_batch = whole && (cur + n >= ib);
     // ---- set-up: lane = (radius, task).  While the rows are in flight, task 0: record + first bin | 1: last bin
     const int r_su = lane & (LN_R - 1), task = lane / LN_R;
     if (task < 2) {
@@ -727,8 +740,47 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
     __syncwarp();   // the shared-memory stage and the row in HBM are taken over by the next sub-batch
   }
   if (lane == 0) {
-    S.zrange[((size_t) v * NZMAX + z) * 2] = zlo;
-    S.zrange[((size_t) v * NZMAX + z) * 2 + 1] = zhi;
+    int *zr = whole ? S.zrange + ((size_t) v * NZMAX + z) * 2 : S.zrpart + ((size_t) v * LINE_PARTS + row) * 2;
+    zr[0] = zlo;
+    zr[1] = zhi;
+  }
+}
+
+// Sum of the partial rows of a split zone (ascending runs = ascending radius index), division by the bin energy
+// (renorm_relline_profile, src/Relprofile.cpp:757-762) and the zone's range.  One CTA per vector, zones in ascending
+// order: the merged row z never lies behind a partial row that is still to be read (z <= z nsplit).
+template <int GRID_MODE>
+__global__ void __launch_bounds__(128) k_linemerge(const VPar *__restrict__ vps, Scratch S, LineGrid G, int ne_stride, int nz_stride,
+                                                   int nz_max) {
+  const int v = blockIdx.x, t = threadIdx.x;
+  if (S.status[v] != ST_OK) return;
+  if (S.reuse && S.reuse[v]) return;
+  const VPar &vp = vps[v];
+  const int nz = min(vp.nz, nz_max), nsplit = line_parts(vp.nz);
+  if (nsplit == 1) return;
+  double *base = S.relflux + (size_t) v * nz_stride * ne_stride;
+  const int *zp = S.zrpart + (size_t) v * LINE_PARTS * 2;
+  for (int z = 0; z < nz; z++) {
+    int lo = G.n_ener, hi = -1;
+    for (int s = 0; s < nsplit; s++) {
+      const int a = zp[(z * nsplit + s) * 2], b = zp[(z * nsplit + s) * 2 + 1];
+      if (b >= a) { lo = min(lo, a); hi = max(hi, b); }
+    }
+    double *out = base + (size_t) z * ne_stride;
+    for (int j = lo + t; j <= hi; j += 128) {
+      double a = 0.0;
+      for (int s = 0; s < nsplit; s++) {
+        const int r = z * nsplit + s;
+        if (j >= zp[r * 2] && j <= zp[r * 2 + 1]) a += base[(size_t) r * ne_stride + j];
+      }
+      const double elo = line_edge(G.e, j, GRID_MODE, vp.z, vp.lineE), ehi = line_edge(G.e, j + 1, GRID_MODE, vp.z, vp.lineE);
+      out[j] = a / (0.5 * (elo + ehi));
+    }
+    if (t == 0) {
+      S.zrange[((size_t) v * NZMAX + z) * 2] = lo;
+      S.zrange[((size_t) v * NZMAX + z) * 2 + 1] = hi;
+    }
+    __syncthreads();
   }
 }
 
@@ -752,16 +804,32 @@ static void launch_line_t(const VPar *vps, const DevTables &T, const Scratch &S,
   if (grid_mode == 0) k_line<0, MINB><<<grid, LN_NT, 0, st>>>(vps, T, S, G, S.ne_line_cap, S.nz_cap);
   else k_line<1, MINB><<<grid, LN_NT, 0, st>>>(vps, T, S, G, S.ne_line_cap, S.nz_cap);
 }
+// profile rows the arena needs per vector for zone counts in [nz_min, nz_max]
+int line_rows(int nz_min, int nz_max) {
+  int r = nz_max;
+  for (int nz = std::max(1, nz_min); nz <= nz_max; nz++) r = std::max(r, nz * line_parts(nz));
+  return r;
+}
 void launch_line(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *egrid, int n_ener,
-                 int grid_mode, int nz_max, cudaStream_t st) {
-  dim3 grid((unsigned) n, nz_max);   // zone-major launch order: the inner zones (most radii, widest profiles) first
+                 int grid_mode, int nz_min, int nz_max, cudaStream_t st) {
+  int parts = 1;
+  for (int nz = std::max(1, nz_min); nz <= nz_max; nz++) parts = std::max(parts, line_parts(nz));
+  dim3 grid((unsigned) n, nz_max, parts);   // zone-major launch order: the inner zones (most radii, widest profiles) first
   LineGrid G;
   G.e = egrid; G.n_ener = n_ener; G.mode = grid_mode;
   G.log_lo = std::log(CONV_EMIN);
   G.inv_dlog = (double) NCONV / (std::log(CONV_EMAX) - std::log(CONV_EMIN));
-  if (g_minb == 20) launch_line_t<20>(vps, T, S, grid, G, grid_mode, st);
+  if (g_minb == 24) launch_line_t<24>(vps, T, S, grid, G, grid_mode, st);
   else if (g_minb == 16) launch_line_t<16>(vps, T, S, grid, G, grid_mode, st);
-  else launch_line_t<24>(vps, T, S, grid, G, grid_mode, st);
+  else launch_line_t<20>(vps, T, S, grid, G, grid_mode, st);
+  if (parts > 1) {
+    if (grid_mode == 0) k_linemerge<0><<<(unsigned) n, 128, 0, st>>>(vps, S, G, S.ne_line_cap, S.nz_cap, nz_max);
+    else k_linemerge<1><<<(unsigned) n, 128, 0, st>>>(vps, S, G, S.ne_line_cap, S.nz_cap, nz_max);
+  }
+}
+int line_launches(int nz_min, int nz_max) {
+  for (int nz = std::max(1, nz_min); nz <= nz_max; nz++) if (line_parts(nz) > 1) return 2;
+  return 1;
 }
 int line_max_bins() { return 1 << 24; }   // the zone accumulator lives in the output row: no shared-memory limit
 
