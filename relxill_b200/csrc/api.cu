@@ -494,7 +494,7 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
     if (xillver) {
       tm.begin(); launch_xillver(vps, T, S, nc, which, b->d_energy, b->n_flux, out, nex_stride, st); tm.end(KF_XILLVER);
       if (nth) {
-        tm.begin(); launch_nth(vps, T, S, nc, st); tm.end(KF_NTH);
+        tm.begin(); launch_nth(vps, T, S, nc, 0, st); tm.end(KF_NTH, 2);
         tm.begin(); launch_xillver_prim_nth(vps, T, S, nc, b->d_energy, b->n_flux, out, st); tm.end(KF_PRIMNTH);
       }
       CK(cudaMemcpyAsync(b->status + c0, S.status, nc * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -503,7 +503,7 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
     tm.begin(); launch_syspar(vps, T, S, nc, 1, st); tm.end(KF_SYSPAR);
     if (relxill) {
       tm.begin(); launch_zone(vps, T, S, nc, st); tm.end(KF_ZONE);
-      if (nth) { tm.begin(); launch_nth(vps, T, S, nc, st); tm.end(KF_NTH); }
+      if (nth) { tm.begin(); launch_nth(vps, T, S, nc, b->nz_max, st); tm.end(KF_NTH, 2); }
       if (b->any_corr) { tm.begin(); launch_syspar(vps, T, S, nc, 2, st); tm.end(KF_SYSPAR); }
     }
     tm.begin();

@@ -117,6 +117,9 @@ struct DevTables {
   const double *conv_w;     // [NCONV/2+1][2] (re, im) DFT of the band mask (frequency-domain band sum of a convolution)
   // nthcomp: arrays that depend only on the photon grid (kT_bb is fixed at 0.05 keV)
   const double *nth_x, *nth_c2, *nth_rel, *nth_x3, *nth_w, *nth_dphdot;
+  const double *nth_w1, *nth_w2;   // weights of the two coarse-grid band integrals on the photon-grid nodes
+  int nth_ih1;                     // f_spp__ bracket at 1 keV, z = 0
+  double nth_xx1;
   int nth_jnr, nth_jrel, nth_jmaxth;
   double nth_xmin, nth_deltal;
 };
@@ -155,8 +158,8 @@ struct DevTables {
   X(double, xillz, (size_t) nzc * nxs)     /* zone spectra: rows of XillDev::xc_stride (convolution grid) or ::stride */  \
   X(int, status, 1)                                                                                                       \
   X(double, total, NCONV)          /* convolution-grid spectrum of the vector (state cache, probes) */                    \
-  NTH_X(double, nth_gam, (size_t) NTH_MAX * NTH_SOL) NTH_X(double, nth_g, (size_t) NTH_MAX * NTH_SOL)                     \
-  NTH_X(double, nth_spt, (size_t) NTH_MAX * NTH_SOL) NTH_X(int, nth_jmax, NTH_SOL)
+  NTH_X(double, nth_spt, NTH_MAX)  /* E F_E solution of the SOURCE (the zones' are consumed inside k_nth) */              \
+  NTH_X(int, nth_jmax, NTH_SOL) NTH_X(double, nth_nfac, NTH_SOL) NTH_X(double, nth_s2, NTH_SOL)
 
 struct Scratch {
   long cap;          // vectors

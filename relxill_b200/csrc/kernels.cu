@@ -959,6 +959,7 @@ __global__ void __launch_bounds__(256) k_xillver(const VPar *__restrict__ vps, D
 static size_t g_smem_sys = 0, g_smem_zone = 0;
 
 int line_kernel_init();
+int nth_kernel_init();
 int xill_kernel_init();
 int conv_kernel_init();
 
@@ -971,6 +972,7 @@ int kernels_init() {
   e = cudaFuncSetAttribute(k_zone, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) g_smem_zone);
   if (e != cudaSuccess) return 1;
   if (line_kernel_init() != 0) return 1;
+  if (nth_kernel_init() != 0) return 1;
   if (xill_kernel_init() != 0) return 1;
   if (conv_kernel_init() != 0) return 1;
   return 0;

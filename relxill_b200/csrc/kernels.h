@@ -32,7 +32,7 @@ void launch_xillver(const VPar *vps, const DevTables &T, const Scratch &S, long 
                     int n_flux, double *out, int stride, cudaStream_t st);
 void launch_xillver_prim_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, const double *user_e, int n_flux,
                              double *out, cudaStream_t st);
-void launch_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, cudaStream_t st);
+void launch_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, int nz_max, cudaStream_t st);   // 2 kernels
 void launch_prim_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, double *total, const double *user_e,
                      int n_flux, double *out, int renorm3, cudaStream_t st);
 

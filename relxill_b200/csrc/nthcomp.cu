@@ -8,10 +8,14 @@
 //
 // A relxilllpCp evaluation needs one Kompaneets solution per radial zone (kTe shifted into the zone's frame)
 // plus one for the source; the reference solves 3*Nz+3 times because every consumer calls c_donthcomp again
-// (SURVEY.md §3.5).  Here each distinct solution is computed once: one thread per solve runs the
-// tridiagonal recurrence (inherently sequential in the photon-energy index), the per-solve work arrays are
-// laid out [energy index][solve] so the threads of a block read and write them coalesced, and everything
-// that depends only on the photon grid was tabulated at load (tables.cu, load_nthcomp).
+// (SURVEY.md §3.5).  Here each distinct solution is computed once, one thread per solve (the tridiagonal recurrence is
+// sequential in the photon-energy index), 64 solves of consecutive vectors per CTA whatever the zone count is.
+// The elimination coefficients never leave the SM: the forward sweep keeps a checkpoint every 32 steps in shared
+// memory and the back substitution recomputes one 32-step segment at a time from its checkpoint (twice the flops of
+// the sweep instead of 1.4 MB of HBM scratch per vector written and read back: the kernel was bound by that traffic).
+// The zone solutions are not filed either: what is needed of them, two band integrals on the coarse grid and the
+// value at 1 keV, is linear in the solution and is accumulated while it is produced (weights tabulated at load,
+// tables.cu); only the source's solution goes to HBM for the primary spectrum.
 #include <cuda_runtime.h>
 
 #include "common.h"
@@ -21,84 +25,49 @@
 namespace rx {
 
 constexpr double LOG10E = 0.43429448190325182765;
+constexpr int NTH_NT = 64;     // solves per CTA
+constexpr int NTH_SEG = 32;    // steps between checkpoints
+constexpr int NTH_NSEG = (NTH_MAX + NTH_SEG - 1) / NTH_SEG;
 
-// f_thdscompton__ + f_thermlc__ for one (theta, gamma); arrays strided by NTH_SOL. returns jmax.
-__device__ int nth_solve(const DevTables &T, double theta, double gamma, double *gam, double *g, double *spt) {
-  const double *x = T.nth_x, *w = T.nth_w, *c2 = T.nth_c2, *rel = T.nth_rel, *x3 = T.nth_x3, *dph = T.nth_dphdot;
-  const double d1 = gamma + .5;
-  const double tautom = sqrt(3. / (theta * (d1 * d1 - 2.25)) + 2.25) - 1.5;
-  const double deltal = T.nth_deltal;
-  const double xmax = theta * 40.;
-  int jmax = (int) (LOG10E * log(xmax / T.nth_xmin) / .02) + 1;
-  if (jmax > 899) jmax = 899;
-  if (jmax < 4) jmax = 4;
-  int jnr = T.nth_jnr, jrel = T.nth_jrel;
-  if (jnr > jmax - 1) jnr = jmax - 1;
-  if (jrel > jmax) jrel = jmax;
-  const double xnr = x[jnr - 1], xr = x[jrel - 1];
-  auto bet = [&](int j) -> double {   // j 1-based
-    if (j > jrel) return 1 / tautom;
-    const double taukn = tautom * rel[j - 1];
-    if (j <= jnr - 1) return 1 / tautom / (taukn / 3 + 1);
-    const double arg = (x[j - 1] - xnr) / (xr - xnr);
-    const double flz = 1 - arg;
-    return 1 / tautom / (taukn / 3 * flz + 1);
-  };
-  const double c20 = tautom / deltal;
-  const double td = theta / deltal;
-  const double x32 = w[0];
-  const double aa = (td / x32 + .5) / (td / x32 - .5);
-  // forward elimination: gam[j-1], g[j-1] for j = 2 .. jmax-1 (1-based j as in the reference)
-  double gam_prev = 0.0, g_prev = 0.0;
-  for (int j = 2; j <= jmax - 1; j++) {
-    const double w1 = w[j - 1], w2 = w[j - 2];
-    const double a = -c20 * c2[j - 1] * (td / w1 + .5);
-    const double t1 = -c20 * c2[j - 1] * (.5 - td / w1);
-    const double t2 = c20 * c2[j - 2] * (td / w2 + .5);
-    const double t3 = x3[j - 1] * (tautom * bet(j));
-    const double b = t1 + t2 + t3;
-    const double c = c20 * c2[j - 2] * (.5 - td / w2);
-    const double d = x[j - 1] * dph[j - 1];
-    double alp, gg;
-    if (j == 2) {
-      alp = b + c * aa;
-      gg = d / alp;
-    } else {
-      alp = b - c * gam_prev;
-      // the last row also carries the (zero) boundary value u[jmax]: (d - a*0 - c*g)/alp
-      gg = (j == jmax - 1) ? (d - a * 0. - c * g_prev) / alp : (d - c * g_prev) / alp;
-    }
-    gam_prev = a / alp;
-    g_prev = gg;
-    gam[(size_t) (j - 1) * NTH_SOL] = gam_prev;
-    g[(size_t) (j - 1) * NTH_SOL] = gg;
+struct NthSolve {   // per-thread constants of one (theta, gamma)
+  double tautom, c20, td, aa, xnr, xr;
+  int jmax, jnr, jrel;
+};
+__device__ __forceinline__ double nth_bet(const DevTables &T, const NthSolve &q, int j) {   // j 1-based
+  if (j > q.jrel) return 1 / q.tautom;
+  const double taukn = q.tautom * T.nth_rel[j - 1];
+  if (j <= q.jnr - 1) return 1 / q.tautom / (taukn / 3 + 1);
+  const double arg = (T.nth_x[j - 1] - q.xnr) / (q.xr - q.xnr);
+  const double flz = 1 - arg;
+  return 1 / q.tautom / (taukn / 3 * flz + 1);
+}
+// one row of the forward elimination (f_thermlc__, src/donthcomp.c:200-301), j = 2 .. jmax-1 (1-based as in the reference)
+__device__ __forceinline__ void nth_step(const DevTables &T, const NthSolve &q, int j, double &gam_prev, double &g_prev) {
+  const double *x = T.nth_x, *w = T.nth_w, *c2 = T.nth_c2, *x3 = T.nth_x3, *dph = T.nth_dphdot;
+  const double w1 = w[j - 1], w2 = w[j - 2];
+  const double a = -q.c20 * c2[j - 1] * (q.td / w1 + .5);
+  const double t1 = -q.c20 * c2[j - 1] * (.5 - q.td / w1);
+  const double t2 = q.c20 * c2[j - 2] * (q.td / w2 + .5);
+  const double t3 = x3[j - 1] * (q.tautom * nth_bet(T, q, j));
+  const double b = t1 + t2 + t3;
+  const double c = q.c20 * c2[j - 2] * (.5 - q.td / w2);
+  const double d = x[j - 1] * dph[j - 1];
+  double alp, gg;
+  if (j == 2) {
+    alp = b + c * q.aa;
+    gg = d / alp;
+  } else {
+    alp = b - c * gam_prev;
+    // the last row also carries the (zero) boundary value u[jmax]: (d - a*0 - c*g)/alp
+    gg = (j == q.jmax - 1) ? (d - a * 0. - c * g_prev) / alp : (d - c * g_prev) / alp;
   }
-  // back substitution + escaping photon density -> E F_E
-  for (int j = 0; j < NTH_MAX; j++) { if (j >= jmax - 1) spt[(size_t) j * NTH_SOL] = 0.0; }
-  double u_next = g_prev;   // u[jmax-1] (1-based) = g[jmax-2]
-  {
-    const int j = jmax - 1;
-    const double dphesc = x[j - 1] * x[j - 1] * u_next * bet(j) * tautom;
-    spt[(size_t) (j - 1) * NTH_SOL] = dphesc * (x[j - 1] * x[j - 1]);
-  }
-  double u2 = u_next;   // will end as u of 1-based index 2
-  for (int jj = jmax - 2; jj >= 2; jj--) {
-    const double u = g[(size_t) (jj - 1) * NTH_SOL] - gam[(size_t) (jj - 1) * NTH_SOL] * u_next;
-    const double dphesc = x[jj - 1] * x[jj - 1] * u * bet(jj) * tautom;
-    spt[(size_t) (jj - 1) * NTH_SOL] = dphesc * (x[jj - 1] * x[jj - 1]);
-    u_next = u;
-    u2 = u;
-  }
-  {
-    const double u = aa * u2;
-    const double dphesc = x[0] * x[0] * u * bet(1) * tautom;
-    spt[0] = dphesc * (x[0] * x[0]);
-  }
-  return jmax;
+  gam_prev = a / alp;
+  g_prev = gg;
 }
 
 // value of the E F_E solution at photon energy e_kev (in the source frame after the redshift factor zfac =
 // 1 + z): the interpolation of c_donthcomp :759-780.  nth = jmax.
+// (the solution is contiguous: only the source's is filed)
 __device__ __forceinline__ double nth_prim(const DevTables &T, const double *spt, int nth, double e_kev, double zfac) {
   const double *xth = T.nth_x;
   const double target = e_kev * zfac;
@@ -112,7 +81,7 @@ __device__ __forceinline__ double nth_prim(const DevTables &T, const double *spt
   if (j > nth) return 0.0;
   if (j > 1) {
     const int jl = j - 1;
-    const double s0 = spt[(size_t) (jl - 1) * NTH_SOL], s1 = spt[(size_t) jl * NTH_SOL];
+    const double s0 = spt[jl - 1], s1 = spt[jl];
     return s0 + (e_kev / 511. * zfac - xth[jl - 1]) * (s1 - s0) / (xth[jl] - xth[jl - 1]);
   }
   return spt[0];
@@ -126,7 +95,7 @@ __device__ double nth_normfac(const DevTables &T, const double *spt, int nth, do
   int ih = 2;
   while (ih < nth && xx > xth[ih - 1]) ++ih;
   const int il = ih - 1;
-  const double s0 = spt[(size_t) (il - 1) * NTH_SOL], s1 = spt[(size_t) (ih - 1) * NTH_SOL];
+  const double s0 = spt[il - 1], s1 = spt[ih - 1];
   return 1 / (s0 + (s1 - s0) * (xx - xth[il - 1]) / (xth[ih - 1] - xth[il - 1]));
 }
 
@@ -138,51 +107,114 @@ __device__ __forceinline__ double nth_bin(const DevTables &T, const double *spt,
 }
 
 // ---------------------------------------------------------------------------------- k_nth
-// One CTA per vector of a Cp model, after k_zone: the Kompaneets solutions of the zones and the source,
-// their xillver-normalisation integrals on the coarse grid, the normalisation-change factors and the
-// returning-radiation flux-correction factors.
-__global__ void __launch_bounds__(128) k_nth(const VPar *__restrict__ vps, DevTables T, Scratch S) {
-  __shared__ double s_nfac[NZMAX + 1], s_s2[NZMAX + 1];
-  __shared__ int s_jmax[NZMAX + 1];
+// Thread = one Kompaneets solve: solve k of vector v (k < nz: zone k, kTe shifted into the zone's frame; k = nz: the
+// source), 64 consecutive (v, k) pairs per CTA.  f_thdscompton__ + f_thermlc__ (src/donthcomp.c:200-301,467-648).
+struct NthSmem {
+  double2 ck[NTH_NSEG][NTH_NT];    // (gam, g) entering each segment
+  double2 seg[NTH_SEG][NTH_NT];    // (gam, g) of the segment being back-substituted
+};
+__global__ void __launch_bounds__(NTH_NT) k_nth(const VPar *__restrict__ vps, DevTables T, Scratch S, long n, int per_vec) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  NthSmem &sm = *reinterpret_cast<NthSmem *>(smraw);
+  const int t = threadIdx.x;
+  const long gs = (long) blockIdx.x * NTH_NT + t;
+  const long v = gs / per_vec;
+  const int k = (int) (gs - v * per_vec);
+  bool on = v < n;
+  if (on) on = (S.status[v] == ST_OK) && !(S.reuse && (S.reuse[v] & REUSE_ALL)) && vps[v].prim_type == PRIM_NTHCOMP && k <= vps[v].nz;
+  NthSolve q;
+  q.jmax = 0;
+  bool source = false;
+  if (on) {
+    const VPar &vp = vps[v];
+    source = (k == vp.nz);
+    const double kte = source ? vp.ect : S.zect[(size_t) v * NZMAX + k];   // zone: kTe * energy shift; source: kTe
+    const double theta = kte / 511., gamma = vp.gam;
+    const double d1 = gamma + .5;
+    q.tautom = sqrt(3. / (theta * (d1 * d1 - 2.25)) + 2.25) - 1.5;
+    const double xmax = theta * 40.;
+    int jmax = (int) (LOG10E * log(xmax / T.nth_xmin) / .02) + 1;
+    if (jmax > 899) jmax = 899;
+    if (jmax < 4) jmax = 4;
+    q.jmax = jmax;
+    q.jnr = min(T.nth_jnr, jmax - 1);
+    q.jrel = min(T.nth_jrel, jmax);
+    q.xnr = T.nth_x[q.jnr - 1];
+    q.xr = T.nth_x[q.jrel - 1];
+    q.c20 = q.tautom / T.nth_deltal;
+    q.td = theta / T.nth_deltal;
+    const double x32 = T.nth_w[0];
+    q.aa = (q.td / x32 + .5) / (q.td / x32 - .5);
+  }
+  const int jmax = q.jmax;
+  // ---- forward elimination, checkpoints only: segment s covers the rows j = 2 + 32 s .. 33 + 32 s
+  double gam_prev = 0.0, g_prev = 0.0;
+  int jtop = 0;
+  for (int o = 16, m = jmax; o > 0; o >>= 1) { m = max(m, __shfl_xor_sync(0xffffffffu, m, o)); jtop = m; }
+  if (jtop == 0) return;   // (a whole warp without work)
+  for (int j = 2; j <= jtop - 1; j++) {
+    if (((j - 2) & (NTH_SEG - 1)) == 0) sm.ck[(j - 2) / NTH_SEG][t] = make_double2(gam_prev, g_prev);
+    if (j <= jmax - 1) nth_step(T, q, j, gam_prev, g_prev);
+  }
+  // ---- back substitution + escaping photon density -> E F_E, segment by segment from the top
+  const double *x = T.nth_x;
+  double *spt = S.nth_spt + (size_t) (on ? v : 0) * NTH_MAX;
+  if (on && source)
+    for (int j = jmax - 1; j < NTH_MAX; j++) spt[j] = 0.0;
+  const int ih1 = min(T.nth_ih1, jmax), il1 = ih1 - 1;   // f_spp__ bracket (1-based)
+  double a1 = 0.0, a2 = 0.0, s_il = 0.0, s_ih = 0.0;
+  auto emit = [&](int j, double u) {   // row j (1-based): E F_E at x_j
+    const double xj = x[j - 1];
+    const double dphesc = xj * xj * u * nth_bet(T, q, j) * q.tautom;
+    const double val = dphesc * (xj * xj);
+    if (source) spt[j - 1] = val;
+    a1 += T.nth_w1[j - 1] * val;
+    a2 += T.nth_w2[j - 1] * val;
+    if (j == il1) s_il = val;
+    if (j == ih1) s_ih = val;
+  };
+  double u_next = g_prev;   // u[jmax-1] (1-based) = g of the last row
+  if (on) emit(jmax - 1, u_next);
+  double u2 = u_next;       // will end as u of 1-based index 2
+  for (int s = (jtop - 3) / NTH_SEG; s >= 0; s--) {
+    const int j0 = 2 + s * NTH_SEG;
+    // the segment's rows again, from its checkpoint
+    double2 c = sm.ck[s][t];
+    for (int i = 0; i < NTH_SEG; i++) {
+      const int j = j0 + i;
+      if (j <= jmax - 1) nth_step(T, q, j, c.x, c.y);
+      sm.seg[i][t] = c;
+    }
+    for (int i = NTH_SEG - 1; i >= 0; i--) {
+      const int jj = j0 + i;
+      if (on && jj <= jmax - 2) {   // rows jmax-2 .. 2
+        const double2 gg = sm.seg[i][t];
+        const double u = gg.y - gg.x * u_next;
+        emit(jj, u);
+        u_next = u;
+        u2 = u;
+      }
+    }
+  }
+  if (!on) return;
+  emit(1, q.aa * u2);
+  // normalisation at 1 keV (f_spp__, src/donthcomp.c:651-681; z = 0) and the two band integrals
+  const double normfac = 1 / (s_il + (s_ih - s_il) * (T.nth_xx1 - x[il1 - 1]) / (x[ih1 - 1] - x[il1 - 1]));
+  S.nth_jmax[(size_t) v * NTH_SOL + k] = jmax;
+  S.nth_nfac[(size_t) v * NTH_SOL + k] = 1. / ((a1 * normfac) / (1e15 / 4.0 / PI));
+  S.nth_s2[(size_t) v * NTH_SOL + k] = a2 * normfac;
+}
+
+// per vector: source normalisation, normalisation-change factors and the returning-radiation flux-correction factors
+// (src/Xillspec.cpp:179-205,344-362,408-440,500-526, src/PrimarySource.h:279-293)
+__global__ void __launch_bounds__(64) k_nth_finish(const VPar *__restrict__ vps, DevTables T, Scratch S) {
   const int v = blockIdx.x, t = threadIdx.x;
   if (S.status[v] != ST_OK) return;
   if (S.reuse && (S.reuse[v] & REUSE_ALL)) return;
   const VPar &vp = vps[v];
   if (vp.prim_type != PRIM_NTHCOMP) return;
   const int nz = vp.nz;
-  double *gam = S.nth_gam + (size_t) v * NTH_MAX * NTH_SOL, *g = S.nth_g + (size_t) v * NTH_MAX * NTH_SOL;
-  double *spt = S.nth_spt + (size_t) v * NTH_MAX * NTH_SOL;
-  if (t <= nz) {
-    const double kte = (t < nz) ? S.zect[(size_t) v * NZMAX + t] : vp.ect;   // zone: kTe * energy shift; source: kTe
-    const int jm = nth_solve(T, kte / 511., vp.gam, gam + t, g + t, spt + t);
-    s_jmax[t] = jm;
-    S.nth_jmax[(size_t) v * NTH_SOL + t] = jm;
-  }
-  __syncthreads();
-  // band integrals on the coarse grid (z = 0: ener_shift = 1), one warp per solve
-  const int warp = t >> 5, lane = t & 31;
-  for (int job = warp; job <= nz; job += 4) {
-    const double *sp = spt + job;
-    const int nth = s_jmax[job];
-    const double normfac = nth_normfac(T, sp, nth, 1.0);
-    double a1 = 0.0, a2 = 0.0;
-    for (int i = lane; i < NCOARSE; i += 32) {
-      const double e0 = T.ecoarse[i], e1 = T.ecoarse[i + 1];
-      const double fl = nth_bin(T, sp, nth, e0, e1, 1.0, normfac);
-      const double wgt = fl * 0.5 * (e0 + e1);
-      if (T.coarse_m1[i]) a1 += wgt * 1e20 * 1.602177e-09;
-      if (T.coarse_m2[i]) a2 += wgt;
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-    }
-    if (lane == 0) {
-      s_nfac[job] = 1. / (a1 / (1e15 / 4.0 / PI));
-      s_s2[job] = a2;
-    }
-  }
-  __syncthreads();
+  const double *s_nfac = S.nth_nfac + (size_t) v * NTH_SOL, *s_s2 = S.nth_s2 + (size_t) v * NTH_SOL;
   if (t == 0) S.nsrc[v] = s_nfac[nz];
   if (t < nz) {
     S.normch[(size_t) v * NZMAX + t] = s_nfac[t] / s_nfac[nz];
@@ -216,7 +248,7 @@ __global__ void __launch_bounds__(256) k_prim_nth(const VPar *__restrict__ vps, 
   const VPar &vp = vps[v];
   const bool reuse_all = S.reuse && (S.reuse[v] & REUSE_ALL);   // `total` already holds reflection + primary
   const int nz = vp.nz;
-  const double *sp = S.nth_spt + (size_t) v * NTH_MAX * NTH_SOL + nz;
+  const double *sp = S.nth_spt + (size_t) v * NTH_MAX;
   const int nth = S.nth_jmax[(size_t) v * NTH_SOL + nz];
   const double zfac = 1 / vp.eshift_obs - 1 + 1;   // z + 1 with z = 1/shift - 1 (src/Xillspec.cpp:250)
   const double normfac = nth_normfac(T, sp, nth, zfac);
@@ -282,7 +314,7 @@ __global__ void __launch_bounds__(256) k_xillver_prim_nth(const VPar *__restrict
   if (S.status[v] != ST_OK) return;
   const VPar &vp = vps[v];
   if (!(vp.refl_frac >= 0)) return;
-  const double *sp = S.nth_spt + (size_t) v * NTH_MAX * NTH_SOL;
+  const double *sp = S.nth_spt + (size_t) v * NTH_MAX;
   const int nth = S.nth_jmax[(size_t) v * NTH_SOL];
   const double normfac = nth_normfac(T, sp, nth, 1.0);
   const double nsrc = S.nsrc[v];
@@ -299,8 +331,14 @@ void launch_xillver_prim_nth(const VPar *vps, const DevTables &T, const Scratch 
   k_xillver_prim_nth<<<(unsigned) n, 256, 0, st>>>(vps, T, S, user_e, n_flux, out);
 }
 
-void launch_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, cudaStream_t st) {
-  k_nth<<<(unsigned) n, 128, 0, st>>>(vps, T, S);
+int nth_kernel_init() {
+  return cudaFuncSetAttribute(k_nth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(NthSmem)) == cudaSuccess ? 0 : 1;
+}
+void launch_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, int nz_max, cudaStream_t st) {
+  const int per_vec = nz_max + 1;
+  const long total = n * per_vec;
+  k_nth<<<(unsigned) ((total + NTH_NT - 1) / NTH_NT), NTH_NT, sizeof(NthSmem), st>>>(vps, T, S, n, per_vec);
+  k_nth_finish<<<(unsigned) n, 64, 0, st>>>(vps, T, S);
 }
 void launch_prim_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, double *total, const double *user_e,
                      int n_flux, double *out, int renorm3, cudaStream_t st) {

@@ -637,6 +637,45 @@ void Tables::load_nthcomp() {
   dt_.nth_jmaxth = jmaxth;
   dt_.nth_xmin = xmin;
   dt_.nth_deltal = delta * std::log(10.);
+  // The two band integrals of a solution on the coarse grid (the xillver normalisation, src/Xillspec.cpp:179-205, and the
+  // returning-radiation flux, :344-362) are linear in the solution E F_E(x_j): photons per coarse bin are the trapezoid of
+  // the interpolated solution at the bin edges (c_donthcomp, src/donthcomp.c:759-786), so both are dot products with
+  // weights that depend on the two grids only.  k_nth takes them while it back-substitutes and never files the zone
+  // solutions.  (Beyond the last node of a solution the reference returns 0; the solution array is 0 there.)
+  {
+    std::vector<double> w1(N, 0.0), w2(N, 0.0);
+    auto edge = [&](double e, double coef, std::vector<double> &wv) {   // coef * p(e) as weights on the nodes
+      const double target = e * 1.0;
+      int lo = 0, hi = N;
+      while (lo < hi) { const int m = (lo + hi) >> 1; if (x[m] * 511. < target) lo = m + 1; else hi = m; }
+      const int j = lo + 1;   // first 1-based index with NOT (x[j-1] * 511 < target)
+      if (j > N) return;
+      if (j > 1) {
+        const int jl = j - 1;
+        const double fr = (e / 511. * 1.0 - x[jl - 1]) / (x[jl] - x[jl - 1]);
+        wv[jl - 1] += coef * (1.0 - fr);
+        wv[jl] += coef * fr;
+      } else {
+        wv[0] += coef;
+      }
+    };
+    for (int i = 0; i < NCOARSE; i++) {
+      const double e0 = ecoarse_[i], e1 = ecoarse_[i + 1];
+      const bool m1 = (e0 >= 0.1 && e0 <= 1000.0), m2 = (e0 >= 0.1 && e1 <= 1000);
+      const double base = .5 * (e1 - e0) * 0.5 * (e0 + e1);   // photons per bin -> energy per bin
+      if (m1) { edge(e1, base / (e1 * e1) * 1e20 * 1.602177e-09, w1); edge(e0, base / (e0 * e0) * 1e20 * 1.602177e-09, w1); }
+      if (m2) { edge(e1, base / (e1 * e1), w2); edge(e0, base / (e0 * e0), w2); }
+    }
+    dt_.nth_w1 = upload(w1);
+    dt_.nth_w2 = upload(w2);
+    // f_spp__ at 1 keV, z = 0 (src/donthcomp.c:651-681): the bracket on the photon grid
+    const double xn = 1.0 / 511.;
+    const double xx = 1 / (1 / xn);
+    int ih = 2;
+    while (ih < N && xx > x[ih - 1]) ++ih;
+    dt_.nth_ih1 = ih;
+    dt_.nth_xx1 = xx;
+  }
   have_nth_ = true;
 }
 
