@@ -117,6 +117,7 @@ struct DevTables {
   const double *conv_w;     // [NCONV/2+1][2] (re, im) DFT of the band mask (frequency-domain band sum of a convolution)
   // nthcomp: arrays that depend only on the photon grid (kT_bb is fixed at 0.05 keV)
   const double *nth_x, *nth_c2, *nth_rel, *nth_x3, *nth_w, *nth_dphdot;
+  const double *nth_rw, *nth_xd, *nth_x4;   // 1 / w, x dphdot, x^4 per node
   const double *nth_w1, *nth_w2;   // weights of the two coarse-grid band integrals on the photon-grid nodes
   int nth_ih1;                     // f_spp__ bracket at 1 keV, z = 0
   double nth_xx1;

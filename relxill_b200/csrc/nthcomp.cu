@@ -29,44 +29,58 @@ constexpr int NTH_NT = 64;     // solves per CTA
 constexpr int NTH_SEG = 32;    // steps between checkpoints
 constexpr int NTH_NSEG = (NTH_MAX + NTH_SEG - 1) / NTH_SEG;
 
+// Arithmetic.  The reference's rows cost six IEEE divisions each (td/w twice, taukn/3, 1/tautom/(...), a/alp, g/alp);
+// with 51 solves x 2 x 900 rows per vector that made the kernel instruction-bound.  Here the node-only quotients are
+// tabulated (tables.cu), td/w and the neighbouring row's coefficients are carried over instead of recomputed
+// (t2_j = -a_{j-1}, c_j = -t1_{j-1} exactly), and the two remaining quotients per row are reciprocals refined by two
+// Newton steps (~1 ulp).  The solution differs from the reference's by rounding only (measured against the golden
+// vectors: see tests), the recurrence and its order are the reference's.
+__device__ __forceinline__ double nth_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = r * (2.0 - x * r);
+  r = r * (2.0 - x * r);
+  return r;
+}
 struct NthSolve {   // per-thread constants of one (theta, gamma)
-  double tautom, c20, td, aa, xnr, xr;
+  double tautom, c20, td, aa, xnr, rxr;   // rxr = 1 / (xr - xnr)
   int jmax, jnr, jrel;
 };
-__device__ __forceinline__ double nth_bet(const DevTables &T, const NthSolve &q, int j) {   // j 1-based
-  if (j > q.jrel) return 1 / q.tautom;
-  const double taukn = q.tautom * T.nth_rel[j - 1];
-  if (j <= q.jnr - 1) return 1 / q.tautom / (taukn / 3 + 1);
-  const double arg = (T.nth_x[j - 1] - q.xnr) / (q.xr - q.xnr);
-  const double flz = 1 - arg;
-  return 1 / q.tautom / (taukn / 3 * flz + 1);
+// 1 / (tautom bet(j)) = taukn/3 * flz + 1, the scattering term's denominator (f_thermlc__: bet)
+__device__ __forceinline__ double nth_den(const DevTables &T, const NthSolve &q, int j) {   // j 1-based
+  if (j > q.jrel) return 1.0;
+  const double tk3 = q.tautom * T.nth_rel[j - 1] * (1.0 / 3.0);
+  if (j <= q.jnr - 1) return tk3 + 1;
+  const double flz = 1 - (T.nth_x[j - 1] - q.xnr) * q.rxr;
+  return tk3 * flz + 1;
 }
+// carried from row to row: (gam, g) of the recurrence, td/w and the two coefficients the next row shares
+struct NthRow { double gam, g, a, t1; };
 // one row of the forward elimination (f_thermlc__, src/donthcomp.c:200-301), j = 2 .. jmax-1 (1-based as in the reference)
-__device__ __forceinline__ void nth_step(const DevTables &T, const NthSolve &q, int j, double &gam_prev, double &g_prev) {
-  const double *x = T.nth_x, *w = T.nth_w, *c2 = T.nth_c2, *x3 = T.nth_x3, *dph = T.nth_dphdot;
-  const double w1 = w[j - 1], w2 = w[j - 2];
-  const double a = -q.c20 * c2[j - 1] * (q.td / w1 + .5);
-  const double t1 = -q.c20 * c2[j - 1] * (.5 - q.td / w1);
-  const double t2 = q.c20 * c2[j - 2] * (q.td / w2 + .5);
-  const double t3 = x3[j - 1] * (q.tautom * nth_bet(T, q, j));
+__device__ __forceinline__ void nth_step(const DevTables &T, const NthSolve &q, int j, NthRow &r) {
+  const double p = q.c20 * T.nth_c2[j - 1], qw = q.td * T.nth_rw[j - 1];
+  const double a = -p * (qw + .5);
+  const double t1 = -p * (.5 - qw);
+  const double t2 = -r.a;       // c20 c2[j-2] (td/w2 + .5)
+  const double c = -r.t1;       // c20 c2[j-2] (.5 - td/w2)
+  const double t3 = T.nth_x3[j - 1] * nth_rcp(nth_den(T, q, j));
   const double b = t1 + t2 + t3;
-  const double c = q.c20 * c2[j - 2] * (.5 - q.td / w2);
-  const double d = x[j - 1] * dph[j - 1];
-  double alp, gg;
-  if (j == 2) {
-    alp = b + c * q.aa;
-    gg = d / alp;
-  } else {
-    alp = b - c * gam_prev;
-    // the last row also carries the (zero) boundary value u[jmax]: (d - a*0 - c*g)/alp
-    gg = (j == q.jmax - 1) ? (d - a * 0. - c * g_prev) / alp : (d - c * g_prev) / alp;
-  }
-  gam_prev = a / alp;
-  g_prev = gg;
+  const double d = T.nth_xd[j - 1];
+  // row 2 closes on the boundary condition u[1] = aa u[2]; the last row also carries the (zero) boundary value u[jmax]
+  const double alp = (j == 2) ? b + c * q.aa : b - c * r.gam;
+  const double ra = nth_rcp(alp);
+  r.g = (j == 2) ? d * ra : (d - c * r.g) * ra;
+  r.gam = a * ra;
+  r.a = a;
+  r.t1 = t1;
+}
+// the coefficients a, t1 of row j (what row j + 1 takes over from it)
+__device__ __forceinline__ void nth_coef(const DevTables &T, const NthSolve &q, int j, NthRow &r) {
+  const double p = q.c20 * T.nth_c2[j - 1], qw = q.td * T.nth_rw[j - 1];
+  r.a = -p * (qw + .5);
+  r.t1 = -p * (.5 - qw);
 }
 
-// value of the E F_E solution at photon energy e_kev (in the source frame after the redshift factor zfac =
-// 1 + z): the interpolation of c_donthcomp :759-780.  nth = jmax.
 // (the solution is contiguous: only the source's is filed)
 __device__ __forceinline__ double nth_prim(const DevTables &T, const double *spt, int nth, double e_kev, double zfac) {
   const double *xth = T.nth_x;
@@ -140,7 +154,7 @@ __global__ void __launch_bounds__(NTH_NT) k_nth(const VPar *__restrict__ vps, De
     q.jnr = min(T.nth_jnr, jmax - 1);
     q.jrel = min(T.nth_jrel, jmax);
     q.xnr = T.nth_x[q.jnr - 1];
-    q.xr = T.nth_x[q.jrel - 1];
+    q.rxr = 1.0 / (T.nth_x[q.jrel - 1] - q.xnr);
     q.c20 = q.tautom / T.nth_deltal;
     q.td = theta / T.nth_deltal;
     const double x32 = T.nth_w[0];
@@ -148,13 +162,15 @@ __global__ void __launch_bounds__(NTH_NT) k_nth(const VPar *__restrict__ vps, De
   }
   const int jmax = q.jmax;
   // ---- forward elimination, checkpoints only: segment s covers the rows j = 2 + 32 s .. 33 + 32 s
-  double gam_prev = 0.0, g_prev = 0.0;
+  NthRow row;
+  nth_coef(T, q, 1, row);
+  row.gam = 0.0; row.g = 0.0;
   int jtop = 0;
   for (int o = 16, m = jmax; o > 0; o >>= 1) { m = max(m, __shfl_xor_sync(0xffffffffu, m, o)); jtop = m; }
   if (jtop == 0) return;   // (a whole warp without work)
   for (int j = 2; j <= jtop - 1; j++) {
-    if (((j - 2) & (NTH_SEG - 1)) == 0) sm.ck[(j - 2) / NTH_SEG][t] = make_double2(gam_prev, g_prev);
-    if (j <= jmax - 1) nth_step(T, q, j, gam_prev, g_prev);
+    if (((j - 2) & (NTH_SEG - 1)) == 0) sm.ck[(j - 2) / NTH_SEG][t] = make_double2(row.gam, row.g);
+    if (j <= jmax - 1) nth_step(T, q, j, row);
   }
   // ---- back substitution + escaping photon density -> E F_E, segment by segment from the top
   const double *x = T.nth_x;
@@ -164,26 +180,27 @@ __global__ void __launch_bounds__(NTH_NT) k_nth(const VPar *__restrict__ vps, De
   const int ih1 = min(T.nth_ih1, jmax), il1 = ih1 - 1;   // f_spp__ bracket (1-based)
   double a1 = 0.0, a2 = 0.0, s_il = 0.0, s_ih = 0.0;
   auto emit = [&](int j, double u) {   // row j (1-based): E F_E at x_j
-    const double xj = x[j - 1];
-    const double dphesc = xj * xj * u * nth_bet(T, q, j) * q.tautom;
-    const double val = dphesc * (xj * xj);
+    const double val = T.nth_x4[j - 1] * u * nth_rcp(nth_den(T, q, j));   // x^2 u bet tautom x^2
     if (source) spt[j - 1] = val;
     a1 += T.nth_w1[j - 1] * val;
     a2 += T.nth_w2[j - 1] * val;
     if (j == il1) s_il = val;
     if (j == ih1) s_ih = val;
   };
-  double u_next = g_prev;   // u[jmax-1] (1-based) = g of the last row
+  double u_next = row.g;    // u[jmax-1] (1-based) = g of the last row
   if (on) emit(jmax - 1, u_next);
   double u2 = u_next;       // will end as u of 1-based index 2
   for (int s = (jtop - 3) / NTH_SEG; s >= 0; s--) {
     const int j0 = 2 + s * NTH_SEG;
     // the segment's rows again, from its checkpoint
-    double2 c = sm.ck[s][t];
+    const double2 c2 = sm.ck[s][t];
+    NthRow c;
+    nth_coef(T, q, j0 - 1, c);   // the coefficients the segment's first row shares with the row before it
+    c.gam = c2.x; c.g = c2.y;
     for (int i = 0; i < NTH_SEG; i++) {
       const int j = j0 + i;
-      if (j <= jmax - 1) nth_step(T, q, j, c.x, c.y);
-      sm.seg[i][t] = c;
+      if (j <= jmax - 1) nth_step(T, q, j, c);
+      sm.seg[i][t] = make_double2(c.gam, c.g);
     }
     for (int i = NTH_SEG - 1; i >= 0; i--) {
       const int jj = j0 + i;
@@ -332,7 +349,9 @@ void launch_xillver_prim_nth(const VPar *vps, const DevTables &T, const Scratch 
 }
 
 int nth_kernel_init() {
-  return cudaFuncSetAttribute(k_nth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(NthSmem)) == cudaSuccess ? 0 : 1;
+  if (cudaFuncSetAttribute(k_nth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(NthSmem)) != cudaSuccess) return 1;
+  // three CTAs per SM: all of the shared-memory carve-out
+  return cudaFuncSetAttribute(k_nth, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared) == cudaSuccess ? 0 : 1;
 }
 void launch_nth(const VPar *vps, const DevTables &T, const Scratch &S, long n, int nz_max, cudaStream_t st) {
   const int per_vec = nz_max + 1;

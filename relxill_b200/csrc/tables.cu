@@ -632,6 +632,17 @@ void Tables::load_nthcomp() {
   dt_.nth_rel = upload(rel);
   dt_.nth_x3 = upload(x3);
   dt_.nth_dphdot = upload(dph);
+  {  // per-node products and reciprocals of k_nth's elimination rows
+    std::vector<double> rw(N), xd(N), x4(N);
+    for (int j = 0; j < N; j++) {
+      rw[j] = 1.0 / w[j];
+      xd[j] = x[j] * dph[j];
+      x4[j] = (x[j] * x[j]) * (x[j] * x[j]);
+    }
+    dt_.nth_rw = upload(rw);
+    dt_.nth_xd = upload(xd);
+    dt_.nth_x4 = upload(x4);
+  }
   dt_.nth_jnr = (int) (log10e * std::log(.1 / xmin) / delta + 1);
   dt_.nth_jrel = (int) (log10e * std::log(1. / xmin) / delta + 1);
   dt_.nth_jmaxth = jmaxth;
