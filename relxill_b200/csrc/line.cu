@@ -83,7 +83,7 @@ struct LnDeep {
   double a, pas;                 // the bin's quadrature interval [a, a + pas]
   double sum[2];                 // trapezoid sums (in units of the level's step) per branch; at the end sum[0] = the bin's result
   double tq[2][3];               // tableau row without its first entry (= sum * step); a finished branch: [0] = its result
-  int rsel, hl;                  // radius of the sub-batch, owning lane
+  int rsel, j;                   // radius of the sub-batch, energy bin
   int flags, pad;                // bits 0-1: branch finished; bits 8-..: level still to do (1: all of it, 3, 4, 5; 0: done)
 };
 // the queue lives in the row stage, dead in the main loop; at most one entry per lane (deep_flush)
@@ -303,9 +303,9 @@ __device__ __forceinline__ void ln_ctx(const LnSmem &sm, int r, const double2 *g
 // Levels 3+ of the queued bins, compacted over the warp (src/Relprofile.cpp:553-576): level L takes NP = 2^(L-1) lanes
 // per bin, one per new abscissa a + (2p+1) pas / 2^L (level 3: 8 bins per pass, level 4: 4), an xor-butterfly sums them
 // and the group's first lane advances the bin's tableau in the queue entry.  What is left after level 4 (~1e-4 of the
-// Romberg bins) and the bins queued for a whole integration are finished by one lane each.  Returns, for lanes 0..14,
-// what their bin gains (already weighted with the radius' area weight); queue order = radius order, so the sum is
-// deterministic.  Written for size, not speed (rolled loops, one call site of the integrand): see relb2_f.
+// Romberg bins) and the bins queued for a whole integration are finished by one lane each.  The results (weighted with
+// the radius' area weight) are added to the zone's row in HBM; queue order = radius order, so the sum is deterministic.
+// Written for size, not speed (rolled loops, one call site of the integrand): see relb2_f.
 __device__ __forceinline__ void deep_tableau(LnDeep &d, int L, double s0, double s1) {
   const double pasn = d.pas * (1.0 / (double) (1 << L)), pasp = pasn * 2.0;
   int flags = d.flags & 3;
@@ -334,7 +334,7 @@ __device__ __forceinline__ void deep_tableau(LnDeep &d, int L, double s0, double
   // not converged after level 4 (~1e-4 of the Romberg bins): the bin is integrated again as a whole by one lane
   d.flags = flags | ((more ? (L == 3 ? 4 : 1) : 0) << 8);
 }
-__device__ __forceinline__ double deep_flush(LnSmem &sm, int ndq, int lane, const double2 *g_cosne, int limb) {
+__device__ __forceinline__ void deep_flush(LnSmem &sm, int ndq, int lane, const double2 *g_cosne, int limb, double *flux) {
   const unsigned FULL = 0xffffffffu;
   // ---- level 3, one lane per entry: its four new abscissae in ascending order, then the tableau
   {
@@ -380,13 +380,14 @@ __device__ __forceinline__ double deep_flush(LnSmem &sm, int ndq, int lane, cons
     }
     __syncwarp();
   }
-  // ---- results, one lane per entry (whole integrations, level code 1, are done here); the owning lanes (0..14) pick
-  // them up through shared memory, entries of the same bin summed in queue order
+  // ---- results, one lane per entry (whole integrations, level code 1, are done here), added to the zone's row in
+  // HBM: the tiles the entries come from have been written.  Entries of the same bin (different radii) are summed in
+  // queue order by the first of them.
   double cwt = 0.0;
-  int hl = -1 - lane;
+  int j = -1 - lane;
   if (lane < ndq) {
     LnDeep &d = sm.dq[lane];
-    hl = d.hl;
+    j = d.j;
     double r;
     if ((d.flags >> 8) == 1) {
       RelbCtx c;
@@ -398,22 +399,17 @@ __device__ __forceinline__ double deep_flush(LnSmem &sm, int ndq, int lane, cons
       r += d.tq[1][0];
     }
     cwt = r * sm.rad[d.rsel].weight;
+    d.sum[0] = cwt;
   }
-  const unsigned same = __match_any_sync(FULL, hl);
-  double *out = reinterpret_cast<double *>(&sm.slot[0]);   // 16 doubles
-  if (lane < ndq) sm.dq[lane].sum[0] = cwt;
-  if (lane < 16) out[lane] = 0.0;
+  const unsigned same = __match_any_sync(FULL, j);
   __syncwarp();
   if (lane < ndq && lane == __ffs(same) - 1) {
     double tot = 0.0;
 #pragma unroll 1
     for (unsigned mm = same; mm; mm &= mm - 1) tot += sm.dq[__ffs(mm) - 1].sum[0];   // ascending lanes = queue order
-    out[hl] = tot;
+    flux[j] += tot;
   }
   __syncwarp();
-  const double add = (lane < 16) ? out[lane] : 0.0;
-  __syncwarp();
-  return add;
 }
 
 // analytic edge terms of a bin that reaches into [0, h] or [1-h, 1] (integ_relline_bin, src/Relprofile.cpp:650-726;
@@ -490,7 +486,6 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
       const int it1 = __shfl_sync(FULL, it, n - 1);
       if (lane == 0) bulk_load(&sm.rows[0][0], g_rows + (size_t) it0 * NG, (uint32_t) (it1 + 2 - it0) * NG * 16, &sm.mbar);
     }
-    const bool last_batch = whole && (cur + n >= ib);
     // ---- set-up: lane = (radius, task).  While the rows are in flight, task 0: record + first bin | 1: last bin
     const int r_su = lane & (LN_R - 1), task = lane / LN_R;
     if (task < 2) {
@@ -567,8 +562,6 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
       if (zlo > jhi) jhi = zlo - 1;
     }
     zlo = min(zlo, jlo); zhi = max(zhi, jhi);
-    // the last sub-batch visits the zone's whole range: it finishes the row (division by the bin energy)
-    if (last_batch) { jlo = zlo; jhi = zhi; }
     __syncwarp();
 
     // ---- main loop: tile of 15 bins, half warp = radius, lane = bin edge; the Romberg tiles first
@@ -579,15 +572,21 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
       const int k_lo = (jlo - j95 >= 0) ? (jlo - j95) / LN_TB : -((j95 - jlo + LN_TB - 1) / LN_TB);
       const int k_hi = (jhi - j95 >= 0) ? (jhi - j95) / LN_TB : -((j95 - jhi + LN_TB - 1) / LN_TB);
       const int npair = (n + 1) >> 1;
-      for (int k = k_hi; k >= k_lo; k--) {
+      // The bins that need Romberg levels 3+ wait in the queue; it is worked off (one copy of that code) when it cannot
+      // take another visit (`again`: the tile is written out, resumed afterwards at the same radius pair) and after the
+      // sub-batch's last tile.
+      for (int k = k_hi, pr = 0, again = 0;;) {
+        if (again || k < k_lo) {
+          __syncwarp();
+          if (ndq) { deep_flush(sm, ndq, lane, g_cosne, limb, flux); ndq = 0; }
+          if (k < k_lo) break;
+        }
         const int j = j95 + k * LN_TB + hl;                     // this lane's edge; its bin if hl < 15
         const double Ea = line_edge(egrid, min(max(j, 0), n_ener), grid_mode, zred, lineE);
         const double Eb = line_edge(egrid, min(max(j + 1, 0), n_ener), grid_mode, zred, lineE);
         const bool binlane = (hl < LN_TB) && (j >= jlo) && (j <= jhi);
-        double acc = (binlane && (j >= zold_lo) && (j <= zold_hi)) ? flux[j] : 0.0;
-        // the radius pairs of the sub-batch; the bins that need Romberg levels 3+ wait in the queue, which is worked off
-        // (one copy of that code) when it cannot take another visit and at the end of the tile
-        for (int pr = 0;;) {
+        double acc = (binlane && (again || ((j >= zold_lo) && (j <= zold_hi)))) ? flux[j] : 0.0;
+        {
           if (k < 0) {
             // ---------------- midpoint-rule tile (int_romb with lo < 0.95, src/Relprofile.cpp:628-647)
             for (; pr < npair; pr++) {
@@ -622,7 +621,7 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
                 if (ndq + __popc(dm) > LN_DQ) break;   // no room: flush, then this visit again
                 if (hard) {
                   LnDeep &d = sm.dq[ndq + __popc(dm & ((1u << lane) - 1))];
-                  d.a = Xa; d.pas = w; d.rsel = rsel; d.hl = hl; d.flags = 1 << 8;
+                  d.a = Xa; d.pas = w; d.rsel = rsel; d.j = j; d.flags = 1 << 8;
                 }
                 ndq += __popc(dm);
                 __syncwarp();
@@ -704,7 +703,7 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
                 if (ndq + __popc(dm) > LN_DQ) break;   // no room (a visit defers at most 30 bins): flush, then this visit again
                 if (need == 3) {
                   LnDeep &d = sm.dq[ndq + __popc(dm & ((1u << lane) - 1))];
-                  d.a = Xa; d.pas = pas; d.rsel = rsel; d.hl = hl;
+                  d.a = Xa; d.pas = pas; d.rsel = rsel; d.j = j;
   #pragma unroll
                   for (int kk = 0; kk < 2; kk++) {
                     d.sum[kk] = sum[kk];
@@ -727,17 +726,21 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
               acc = (acc + (half ? oth : own)) + (half ? own : oth);
             }
           }
-          if (ndq) { acc += deep_flush(sm, ndq, lane, g_cosne, limb); ndq = 0; }
-          if (pr >= npair) break;
         }
-        if (binlane && half == 0) {
-          // only the bins this zone touched are written; the range travels with the row
-          flux[j] = last_batch ? acc / (0.5 * (Ea + Eb)) : acc;
-        }
+        // only the bins this zone touched are written; the range travels with the row
+        if (binlane && half == 0) flux[j] = acc;
+        again = pr < npair;
+        if (!again) { k--; pr = 0; }
       }
     }
     cur += n;
     __syncwarp();   // the shared-memory stage and the row in HBM are taken over by the next sub-batch
+  }
+  if (whole) {   // division by the bin energy (renorm_relline_profile, src/Relprofile.cpp:757-762); k_linemerge's otherwise
+    for (int j = zlo + lane; j <= zhi; j += 32) {
+      const double elo = line_edge(egrid, j, grid_mode, zred, lineE), ehi = line_edge(egrid, j + 1, grid_mode, zred, lineE);
+      flux[j] = flux[j] / (0.5 * (elo + ehi));
+    }
   }
   if (lane == 0) {
     int *zr = whole ? S.zrange + ((size_t) v * NZMAX + z) * 2 : S.zrpart + ((size_t) v * LINE_PARTS + row) * 2;
