@@ -14,14 +14,17 @@
 //     load, so it is taken in the frequency domain and no per-zone inverse transform is needed;
 //   * the normalised product spectra of all zones are accumulated in the frequency domain and one inverse
 //     transform per vector brings the sum back (inverse = forward transform of the conjugate).
-// The transform is a 4096-point radix-8 Stockham autosort FFT in shared memory: 4 passes, one butterfly per
-// thread per pass.  The work array is complex-interleaved (one 128-bit shared access per point) and padded by
-// one point every 8, which makes every pass's gather and scatter bank-conflict free per quarter-warp.
-// What bounds the kernel is the L1/shared-memory data pipe (ncu: wavefronts at ~70 % of peak, FP64 pipe 45 %), so the
-// zone loop is written to move as little as possible through it: the packing phase is a plain coalesced load
-// (k_xill files the zone spectra on the convolution grid), the last pass stores only the half of the result that
-// other threads need, the accumulators are 128-bit, and register spills (local memory rides the same pipe) are
-// kept out of the loop as far as 64 registers allow.
+// The transform is a 4096-point radix-16 Stockham autosort FFT in shared memory: 3 passes (16^3 = 4096), one 16-point
+// butterfly per thread per pass, 256 threads with 16 points each.  The work array is complex-interleaved (one 128-bit
+// shared access per point) and padded by one point every 16, which makes every pass's gather and scatter
+// bank-conflict free per quarter-warp.
+// With the radix-8 transform of round 1 (4 passes, 512 threads at 64 registers) the L1/shared-memory data pipe bounded
+// the kernel (ncu: wavefronts at ~70 % of peak, FP64 pipe 45 %: 64 shared accesses per 8 points and zone, plus the
+// register spills, which ride the same pipe).  Radix 16 exchanges through shared memory twice instead of three times
+// (36 accesses per 8 points and zone), needs 6 block barriers per transform instead of 8 and, at 128 registers per
+// thread for the same register file per CTA, spills nothing.  The rest of the zone loop moves as little as possible
+// through that pipe too: the packing phase is a plain coalesced load (k_xill files the zone spectra on the convolution
+// grid), the last pass stores only the half of the result that other threads need, the accumulators are 128-bit.
 #include <cuda_runtime.h>
 
 #include "common.h"
@@ -30,9 +33,10 @@
 
 namespace rx {
 
-constexpr int CONV_NT = 512;
-constexpr int CV_PADN = NCONV + NCONV / 8;
-__device__ __forceinline__ int cv_pad(int i) { return i + (i >> 3); }
+constexpr int CONV_R = 16;                  // radix: points per thread
+constexpr int CONV_NT = NCONV / CONV_R;     // 256
+constexpr int CV_PADN = NCONV + NCONV / 16;
+__device__ __forceinline__ int cv_pad(int i) { return i + (i >> 4); }
 
 struct ConvSmem {
   double2 z[CV_PADN];
@@ -42,7 +46,7 @@ struct ConvSmem {
   double bc[8];
   double nyq;                        // product spectrum at the Nyquist bin (thread 0)
   double part[4 * (CONV_NT / 32)];   // per-warp partial sums of the packing phase, finished after the transform
-  double2 tw12[8 + 64];              // twiddles of passes 1 and 2: exp(-2 pi i k / 64), k < 8; exp(-2 pi i k / 512), k < 64
+  double2 tw1[16];                   // twiddles of pass 1: exp(-2 pi i k / 256), k < 16
 };
 
 // sums NV values over the block (fixed order: shuffle tree inside warps, then over the warps)
@@ -79,102 +83,127 @@ __device__ __forceinline__ double2 cprod(double2 a, double2 b) {
   return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// 8-point DFT (forward sign), decimation in frequency, outputs in natural order
-__device__ __forceinline__ void fft8(double (&r)[8], double (&i)[8]) {
-  const double h = 0.70710678118654752440;
-  double ar[8], ai[8];
+// 4-point DFT (forward sign) of (x0, x1, x2, x3) -> natural order, in place
+__device__ __forceinline__ void fft4(double &r0, double &i0, double &r1, double &i1, double &r2, double &i2, double &r3, double &i3) {
+  const double ar = r0 + r2, ai = i0 + i2, br = r0 - r2, bi = i0 - i2;
+  const double cr = r1 + r3, ci = i1 + i3, dr = r1 - r3, di = i1 - i3;
+  r0 = ar + cr; i0 = ai + ci;
+  r2 = ar - cr; i2 = ai - ci;
+  r1 = br + di; i1 = bi - dr;   // b - i d
+  r3 = br - di; i3 = bi + dr;   // b + i d
+}
+// 16-point DFT (forward sign), 4 x 4 decomposition (n = 4 n1 + n2 -> k = k1 + 4 k2), outputs in natural order
+__device__ __forceinline__ void fft16(double (&r)[16], double (&i)[16]) {
+  const double h = 0.70710678118654752440, c = 0.92387953251128675613, s = 0.38268343236508977173;
+  // step 1: for every n2, a 4-point DFT over n1 of x[4 n1 + n2]; the result y[n2][k1] stays at index 4 k1 + n2
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    ar[q] = r[q] + r[q + 4]; ai[q] = i[q] + i[q + 4];
-    ar[q + 4] = r[q] - r[q + 4]; ai[q + 4] = i[q] - i[q + 4];
+  for (int n2 = 0; n2 < 4; n2++) fft4(r[n2], i[n2], r[4 + n2], i[4 + n2], r[8 + n2], i[8 + n2], r[12 + n2], i[12 + n2]);
+  // step 2: twiddles W16^(n2 k1) on y[n2][k1] (index 4 k1 + n2)
+  {
+    double x, y;
+    // k1 = 1: W^1, W^2, W^3
+    x = r[5]; y = i[5]; r[5] = x * c + y * s; i[5] = y * c - x * s;
+    x = r[6]; y = i[6]; r[6] = (x + y) * h; i[6] = (y - x) * h;
+    x = r[7]; y = i[7]; r[7] = x * s + y * c; i[7] = y * s - x * c;
+    // k1 = 2: W^2, W^4 = -i, W^6
+    x = r[9]; y = i[9]; r[9] = (x + y) * h; i[9] = (y - x) * h;
+    x = r[10]; y = i[10]; r[10] = y; i[10] = -x;
+    x = r[11]; y = i[11]; r[11] = (y - x) * h; i[11] = (-x - y) * h;
+    // k1 = 3: W^3, W^6, W^9 = -W^1
+    x = r[13]; y = i[13]; r[13] = x * s + y * c; i[13] = y * s - x * c;
+    x = r[14]; y = i[14]; r[14] = (y - x) * h; i[14] = (-x - y) * h;
+    x = r[15]; y = i[15]; r[15] = -(x * c + y * s); i[15] = -(y * c - x * s);
   }
-  {  // twiddles w8^1, w8^2 = -i, w8^3 on the odd half
-    double x = ar[5], y = ai[5];
-    ar[5] = (x + y) * h; ai[5] = (y - x) * h;
-    x = ar[6]; y = ai[6];
-    ar[6] = y; ai[6] = -x;
-    x = ar[7]; y = ai[7];
-    ar[7] = (y - x) * h; ai[7] = (-x - y) * h;
-  }
-  double br[8], bi[8];
+  // step 3: for every k1, a 4-point DFT over n2 of y[n2][k1] -> X[k1 + 4 k2] at index 4 k1 + k2
 #pragma unroll
-  for (int g = 0; g < 8; g += 4) {
-    br[g] = ar[g] + ar[g + 2]; bi[g] = ai[g] + ai[g + 2];
-    br[g + 2] = ar[g] - ar[g + 2]; bi[g + 2] = ai[g] - ai[g + 2];
-    br[g + 1] = ar[g + 1] + ar[g + 3]; bi[g + 1] = ai[g + 1] + ai[g + 3];
-    const double dx = ar[g + 1] - ar[g + 3], dy = ai[g + 1] - ai[g + 3];
-    br[g + 3] = dy; bi[g + 3] = -dx;   // times -i
-  }
-  r[0] = br[0] + br[1]; i[0] = bi[0] + bi[1];
-  r[4] = br[0] - br[1]; i[4] = bi[0] - bi[1];
-  r[2] = br[2] + br[3]; i[2] = bi[2] + bi[3];
-  r[6] = br[2] - br[3]; i[6] = bi[2] - bi[3];
-  r[1] = br[4] + br[5]; i[1] = bi[4] + bi[5];
-  r[5] = br[4] - br[5]; i[5] = bi[4] - bi[5];
-  r[3] = br[6] + br[7]; i[3] = bi[6] + bi[7];
-  r[7] = br[6] - br[7]; i[7] = bi[6] - bi[7];
+  for (int k1 = 0; k1 < 4; k1++) fft4(r[4 * k1], i[4 * k1], r[4 * k1 + 1], i[4 * k1 + 1], r[4 * k1 + 2], i[4 * k1 + 2], r[4 * k1 + 3], i[4 * k1 + 3]);
+  // natural order: X[k1 + 4 k2] sits at 4 k1 + k2 -> transpose the 4 x 4 index
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b2 = a + 1; b2 < 4; b2++) {
+      double tt = r[4 * a + b2]; r[4 * a + b2] = r[4 * b2 + a]; r[4 * b2 + a] = tt;
+      tt = i[4 * a + b2]; i[4 * a + b2] = i[4 * b2 + a]; i[4 * b2 + a] = tt;
+    }
 }
 
 // Forward FFT of 4096 points; all CONV_NT threads call.  The input arrives in registers: thread j holds the points
-// j + 512 q, q = 0..7 (exactly what the first pass needs), so the packing code hands its values over without a
+// j + 256 q, q = 0..15 (exactly what the first pass needs), so the packing code hands its values over without a
 // round trip through shared memory.  Result in the padded array z.
-// The twiddles of pass p are w^q with w = exp(-2 pi i k / (8 ns)), k = j mod ns: they depend on the thread only.
-// The 8 + 64 distinct ones of passes 1 and 2 come from a small shared table (tw12), the last pass's w is re-read per
-// transform (one L1-resident 16-byte load: kept in registers it was spilled, the kernel runs at 64 registers per
-// thread); w^2 and w^4 come from squarings and the rest from products.
-// The transform comes in two pieces, the first pass and the three twiddled ones, so that the caller can put work that
-// needs registers (the warp reductions of the packing sums) between them, when the 16 packed values have left.
-// UPPER: only the upper half of the result (points 2048..4095, the thread's q = 4..7) is written to z; the lower
-// half (points j + 512 q, q < 4) stays in r/im — all the split of two real transforms needs, since the partner of
+// The twiddles of pass p are w^q with w = exp(-2 pi i k / (16 ns)), k = j mod ns: they depend on the thread only.
+// The 16 distinct ones of pass 1 come from a small shared table (tw1), the last pass's w is re-read per transform (one
+// L1-resident 16-byte load); the powers come from squarings and products, applied as soon as they exist.
+// The transform comes in two pieces, the first pass and the two twiddled ones, so that the caller can put work
+// between them when the 32 packed values have left the registers.
+// UPPER: only the upper half of the result (points 2048..4095, the thread's q = 8..15) is written to z; the lower
+// half (points j + 256 q, q < 8) stays in r/im — all the split of two real transforms needs, since the partner of
 // point k is point 4096 - k.
-// First pass of the transform: an 8-point DFT of the thread's own points, written to z (no twiddles, no barrier)
-__device__ __forceinline__ void fft4096_first(double (&r)[8], double (&im)[8], double2 *z) {
+// First pass of the transform: a 16-point DFT of the thread's own points, written to z (no twiddles, no barrier)
+__device__ __forceinline__ void fft4096_first(double (&r)[16], double (&im)[16], double2 *z) {
   const int j = threadIdx.x;
-  fft8(r, im);
+  fft16(r, im);
 #pragma unroll
-  for (int q = 0; q < 8; q++) z[cv_pad((j << 3) + q)] = make_double2(r[q], im[q]);
+  for (int q = 0; q < 16; q++) z[cv_pad((j << 4) + q)] = make_double2(r[q], im[q]);
 }
-// The three twiddled passes; starts with the barrier that publishes the first pass
+// The two twiddled passes; starts with the barrier that publishes the first pass
 template <bool UPPER>
-__device__ __forceinline__ void fft4096_rest(double (&r)[8], double (&im)[8], double2 *z, const double2 *tw12, const double2 *tw3) {
+__device__ __forceinline__ void fft4096_rest(double (&r)[16], double (&im)[16], double2 *z, const double2 *tw1, const double2 *tw2) {
   const int j = threadIdx.x;
   __syncthreads();
 #pragma unroll
-  for (int pass = 1; pass < 4; pass++) {
-    const int ns = 1 << (3 * pass);          // 8, 64, 512
+  for (int pass = 1; pass < 3; pass++) {
+    const int ns = 1 << (4 * pass);          // 16, 256
     const int k = j & (ns - 1);
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-      const double2 c = z[cv_pad(j + q * (NCONV / 8))];
+    for (int q = 0; q < 16; q++) {
+      const double2 c = z[cv_pad(j + q * (NCONV / 16))];
       r[q] = c.x;
       im[q] = c.y;
     }
     {
-      const double2 w1 = (pass == 1) ? tw12[k] : (pass == 2) ? tw12[8 + k] : __ldg(tw3 + j);
-      const double2 w2 = make_double2(w1.x * w1.x - w1.y * w1.y, 2.0 * w1.x * w1.y);
-      const double2 w4 = make_double2(w2.x * w2.x - w2.y * w2.y, 2.0 * w2.x * w2.y);
-      const double2 w3 = cprod(w1, w2), w5 = cprod(w4, w1), w6 = cprod(w4, w2);
-      const double2 w7 = cprod(w4, w3);
+      const double2 w1 = (pass == 1) ? tw1[k] : __ldg(tw2 + j);
       cmul(r[1], im[1], w1.x, w1.y);
+      const double2 w2 = make_double2(w1.x * w1.x - w1.y * w1.y, 2.0 * w1.x * w1.y);
       cmul(r[2], im[2], w2.x, w2.y);
+      const double2 w3 = cprod(w2, w1);
       cmul(r[3], im[3], w3.x, w3.y);
+      const double2 w4 = make_double2(w2.x * w2.x - w2.y * w2.y, 2.0 * w2.x * w2.y);
       cmul(r[4], im[4], w4.x, w4.y);
+      const double2 w5 = cprod(w4, w1);
       cmul(r[5], im[5], w5.x, w5.y);
+      const double2 w6 = cprod(w4, w2);
       cmul(r[6], im[6], w6.x, w6.y);
+      const double2 w7 = cprod(w4, w3);
       cmul(r[7], im[7], w7.x, w7.y);
+      const double2 w8 = make_double2(w4.x * w4.x - w4.y * w4.y, 2.0 * w4.x * w4.y);
+      cmul(r[8], im[8], w8.x, w8.y);
+      double2 w = cprod(w8, w1);
+      cmul(r[9], im[9], w.x, w.y);
+      w = cprod(w8, w2);
+      cmul(r[10], im[10], w.x, w.y);
+      w = cprod(w8, w3);
+      cmul(r[11], im[11], w.x, w.y);
+      w = cprod(w8, w4);
+      cmul(r[12], im[12], w.x, w.y);
+      w = cprod(w8, w5);
+      cmul(r[13], im[13], w.x, w.y);
+      w = cprod(w8, w6);
+      cmul(r[14], im[14], w.x, w.y);
+      w = cprod(w8, w7);
+      cmul(r[15], im[15], w.x, w.y);
     }
-    fft8(r, im);
+    fft16(r, im);
     __syncthreads();
-    const int j0 = ((j - k) << 3) + k;       // (j / ns) * ns * 8 + k
+    const int j0 = ((j - k) << 4) + k;       // (j / ns) * ns * 16 + k
 #pragma unroll
-    for (int q = (UPPER && pass == 3) ? 4 : 0; q < 8; q++) z[cv_pad(j0 + q * ns)] = make_double2(r[q], im[q]);
+    for (int q = (UPPER && pass == 2) ? 8 : 0; q < 16; q++) z[cv_pad(j0 + q * ns)] = make_double2(r[q], im[q]);
     __syncthreads();
   }
 }
 template <bool UPPER>
-__device__ __forceinline__ void fft4096(double (&r)[8], double (&im)[8], double2 *z, const double2 *tw12, const double2 *tw3) {
+__device__ __forceinline__ void fft4096(double (&r)[16], double (&im)[16], double2 *z, const double2 *tw1, const double2 *tw2) {
   fft4096_first(r, im, z);
-  fft4096_rest<UPPER>(r, im, z, tw12, tw3);
+  fft4096_rest<UPPER>(r, im, z, tw1, tw2);
 }
 
 struct ConvArgs {
@@ -193,8 +222,7 @@ struct ConvArgs {
   int renorm3;            // RELXILL_RENORMALIZE=1: scale the spectrum to 1 cts/s/keV/cm2 at 3 keV before the final rebin
 };
 
-// two CTAs per SM (64 registers): with one CTA and 128 registers nothing spills, but 16 warps hide too little
-// latency (13.4 ms against 10.5)
+// two CTAs of 256 threads per SM, 128 registers per thread
 // CG: k_xill filed the zone spectra on the convolution grid already, the packing phase is a plain coalesced load
 template <bool CG>
 __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vps, DevTables T, Scratch S, ConvArgs A) {
@@ -215,21 +243,20 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
   const double2 *tw = reinterpret_cast<const double2 *>(T.tw);
   const double2 *cw = reinterpret_cast<const double2 *>(T.conv_w);
   for (int k = t; k <= NCONV / 2; k += CONV_NT) sm.acc[k] = make_double2(0.0, 0.0);
-  // tw[m] = exp(-2 pi i m / 4096): the last pass's twiddle of this thread stays in registers, the 8 + 64 distinct
-  // ones of the two passes before it sit in shared memory (conflict-free: consecutive threads, consecutive entries)
-  if (t < 8) sm.tw12[t] = __ldg(tw + t * 64);
-  else if (t < 72) sm.tw12[t] = __ldg(tw + (t - 8) * 8);
+  // tw[m] = exp(-2 pi i m / 4096): the last pass's twiddle of this thread is re-read per transform, the 16 distinct ones
+  // of the pass before it sit in shared memory
+  if (t < 16) sm.tw1[t] = __ldg(tw + t * 16);
   double bal_prev = 0.0;   // ratio of the two input scales in the last zone that had one (0: none yet)
   // What does not change from zone to zone, per thread: the rotated bin of the line profile that goes with the
-  // thread's bin i(u) = t + 512 u is ri(u) = r0 + 512 ((c0 + u) mod 8), and whether i(u) (bits 0-7) and ri(u)
-  // (bits 8-15) lie in the normalisation band
-  const int r0 = (t + i1) & (CONV_NT - 1), c0 = (t + i1) >> 9;
+  // thread's bin i(u) = t + 256 u is ri(u) = r0 + 256 ((c0 + u) mod 16), and whether i(u) (bits 0-15) and ri(u)
+  // (bits 16-31) lie in the normalisation band
+  const int r0 = (t + i1) & (CONV_NT - 1), c0 = (t + i1) >> 8;
   unsigned band = 0u;
 #pragma unroll
-  for (int u = 0; u < 8; u++) {
-    const int i = t + u * CONV_NT, ri = r0 + (((c0 + u) & 7) << 9);
+  for (int u = 0; u < CONV_R; u++) {
+    const int i = t + u * CONV_NT, ri = r0 + (((c0 + u) & (CONV_R - 1)) << 8);
     if (i >= b0 && i <= b1) band |= 1u << u;
-    if (ri >= b0 && ri <= b1) band |= 0x100u << u;
+    if (ri >= b0 && ri <= b1) band |= 0x10000u << u;
   }
   const double *rel_v = S.relflux + (size_t) v * A.nz_stride * A.ne_stride + r0;
   const double *xz_v = S.xillz + (size_t) v * A.nz_stride * A.xstride;
@@ -245,16 +272,15 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
     //      186-190); on the logarithmic convolution grid that factor is one constant (to 1e-13, checked at load,
     //      tables.cu) and cancels against the normalisation, so it is left out
     double sums[3] = {0.0, 0.0, 0.0};         // all rel, band x, band rel
-    double re[8], im[8];                      // bins t + 512 u: the first FFT pass takes them from here
+    double re[CONV_R], im[CONV_R];            // bins t + 256 u: the first FFT pass takes them from here
     if (A.mode == 0 && z + 1 < nz) {
       // the next zone's two rows are pulled into L2 while this zone is transformed: the packing loads are the
       // kernel's only DRAM accesses and there are too few warps to hide their latency (one 128-byte line per thread:
       // 188 lines of the zone spectrum, up to 256 of the written part of the line profile)
-      if (t < (CG ? (A.xc_n + 15) >> 4 : 188)) {
-        prefetch_l2(xz + A.xstride + t * 16);
-      } else if (t >= 192 && t < 448) {
+      if (t < (CG ? (A.xc_n + 15) >> 4 : 188)) prefetch_l2(xz + A.xstride + t * 16);
+      {
         const int nlo = zr_v[2 * z + 2], nhi = zr_v[2 * z + 3];
-        const int l = (nlo & ~15) + (t - 192) * 16;
+        const int l = (nlo & ~15) + t * 16;
         if (l <= nhi) prefetch_l2(relr - r0 + A.ne_stride + l);
       }
     }
@@ -262,7 +288,7 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
       // all loads of the 8 bins are independent: bins outside the table grid carry zero weights, the common
       // spans (1-3 source bins) are branch-free
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
+      for (int u = 0; u < CONV_R; u++) {
         const int i = t + u * CONV_NT;
         double f = 0.0;
         if (CG) {
@@ -277,13 +303,13 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
             for (int jj = ii.x + 2; jj <= ii.y - 1; jj++) f += xz[jj];
           }
         }
-        const int ku = ((c0 + u) & 7) << 9;
+        const int ku = ((c0 + u) & (CONV_R - 1)) << 8;
         const double r = ((unsigned) (r0 + ku - rjlo) <= (unsigned) rjw) ? relr[ku] : 0.0;
         re[u] = f;
         im[u] = r;
         sums[0] += r;
         if (band & (1u << u)) sums[1] += f;
-        if (band & (0x100u << u)) sums[2] += r;
+        if (band & (0x10000u << u)) sums[2] += r;
       }
     } else {
 #pragma unroll 1
@@ -297,7 +323,7 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
         if (ri >= b0 && ri <= b1) sums[2] += r;
       }
 #pragma unroll
-      for (int u = 0; u < 8; u++) {   // the thread's own values
+      for (int u = 0; u < CONV_R; u++) {   // the thread's own values
         const double2 c = sm.z[cv_pad(t + u * CONV_NT)];
         re[u] = c.x;
         im[u] = c.y;
@@ -322,14 +348,14 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
       yscale = rscale * bal;
       if (!vp.renorm) bal_prev = bal;
 #pragma unroll
-      for (int u = 0; u < 8; u++) im[u] *= yscale;
+      for (int u = 0; u < CONV_R; u++) im[u] *= yscale;
       fft4096_first(re, im, sm.z);
     } else {
       // the first pass goes ahead of the warp reductions of the packing sums: the 16 packed values leave the registers
       // before the shuffles need them (they were being spilled across the reduction)
       yscale = bal_prev;
 #pragma unroll
-      for (int u = 0; u < 8; u++) im[u] *= yscale;
+      for (int u = 0; u < CONV_R; u++) im[u] *= yscale;
       fft4096_first(re, im, sm.z);
 #pragma unroll
       for (int q = 0; q < 3; q++)
@@ -339,14 +365,14 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
         for (int q = 0; q < 3; q++) sm.part[q * (CONV_NT / 32) + (t >> 5)] = sums[q];
       }
     }
-    fft4096_rest<true>(re, im, sm.z, sm.tw12, tw);
-    // ---- split, product spectrum, band sum of the convolved zone in the frequency domain.  Point k = t + 512 nk
-    // (nk < 4) is still in the thread's registers; its partner 4096 - k is point q = 7 - nk of thread 512 - t, in the
-    // stored upper half (k = 0 is its own partner; thread 0 also takes k = 2048, its own point q = 4)
+    fft4096_rest<true>(re, im, sm.z, sm.tw1, tw);
+    // ---- split, product spectrum, band sum of the convolved zone in the frequency domain.  Point k = t + 256 nk
+    // (nk < 8) is still in the thread's registers; its partner 4096 - k is point q = 15 - nk of thread 256 - t, in the
+    // stored upper half (k = 0 is its own partner; thread 0 also takes k = 2048, its own point q = 8)
     double dot[1] = {0.0};
-    double pr_[4], pi_[4];
+    double pr_[CONV_R / 2], pi_[CONV_R / 2];
 #pragma unroll
-    for (int nk = 0; nk < 4; nk++) {
+    for (int nk = 0; nk < CONV_R / 2; nk++) {
       const int k = t + nk * CONV_NT;
       const int kk = (NCONV - k) & (NCONV - 1);
       const double2 q = (k == 0) ? make_double2(re[0], im[0]) : sm.z[cv_pad(kk)];
@@ -360,8 +386,8 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
       const double2 w = __ldg(cw + k);
       dot[0] += wgt * (Pr * w.x + Pi * w.y);
     }
-    if (t == 0) {   // the Nyquist bin (thread 0's own point q = 4; both spectra are real there) waits in shared memory
-      const double pn = re[4] * im[4];
+    if (t == 0) {   // the Nyquist bin (thread 0's own point q = 8; both spectra are real there) waits in shared memory
+      const double pn = re[CONV_R / 2] * im[CONV_R / 2];
       sm.nyq = pn;
       dot[0] += pn * __ldg(cw + NCONV / 2).x;
     }
@@ -390,7 +416,7 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
     }
     const double norm = s_rel * s_xill / dot[0];
 #pragma unroll
-    for (int nk = 0; nk < 4; nk++) {
+    for (int nk = 0; nk < CONV_R / 2; nk++) {
       const int k = t + nk * CONV_NT;
       double2 a = sm.acc[k];
       a.x += norm * pr_[nk];
@@ -402,9 +428,9 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
   }
   // ---- one inverse transform for the whole vector: out = Re(FFT(conj(A)))
   if (!reuse_all) {
-    double re[8], im[8];
+    double re[CONV_R], im[CONV_R];
 #pragma unroll
-    for (int u = 0; u < 8; u++) {   // Hermitian extension of the accumulated half spectrum, conjugated
+    for (int u = 0; u < CONV_R; u++) {   // Hermitian extension of the accumulated half spectrum, conjugated
       const int i = t + u * CONV_NT;
       const int k = (i <= NCONV / 2) ? i : NCONV - i;
       const double2 a = sm.acc[k];
@@ -412,7 +438,7 @@ __global__ void __launch_bounds__(CONV_NT, 2) k_conv(const VPar *__restrict__ vp
       re[u] = a.x;
       im[u] = (i <= NCONV / 2) ? -ai : ai;
     }
-    fft4096<false>(re, im, sm.z, sm.tw12, tw);
+    fft4096<false>(re, im, sm.z, sm.tw1, tw);
   }
   __syncthreads();       // every thread has taken its part of the accumulated spectrum
   double *acc = reinterpret_cast<double *>(sm.acc);   // 4098 doubles
