@@ -6,28 +6,38 @@
 // relb_func (src/Relprofile.cpp:489-726,835-905), the radial half of interpol_relTable (:280-293) and the division
 // by the bin energy of renorm_relline_profile (:757-762).
 //
-// Mapping.  One CTA (4 warps) per (vector, radial zone); the zone's radii are taken in sub-batches of <= LN_R.
+// Mapping.  One CTA of ONE WARP per (vector, radial zone[, run of the zone's radii]); no block barrier anywhere.  The
+// warp takes the radii in sub-batches of <= LN_R = 8:
 //   staging  the (a, mu0)-interpolated transfer-function rows of the TABLE radii that bracket the sub-batch (k_rows'
 //            output, contiguous) come in with ONE bulk asynchronous copy (cp.async.bulk + mbarrier: the TMA unit moves
-//            them while the threads compute bin ranges); the radial interpolation onto the sub-batch's fine radii is
+//            them while the lanes compute bin ranges); the radial interpolation onto the sub-batch's fine radii is
 //            then done from shared memory into shared memory.  The fine transfer functions never exist in HBM.
-//   set-up   one thread per (radius, task): first bin | last bin (closed-form index on the logarithmic convolution
-//            grid, corrected against the tabulated edges) | the integrand at the edge nodes g* = h | g* = 1-h that
+//   set-up   lane = (radius, task): first bin | last bin (closed-form index on the logarithmic convolution grid,
+//            corrected against the tabulated edges) | the integrand at the edge nodes g* = h | g* = 1-h that
 //            int_edge needs (once per radius instead of once per edge bin).
-//   main     BIN-STATIONARY, no block barrier.  The sub-batch's bin range is cut into tiles of 15 bins anchored at
-//            the bin where the quadrature rule changes (E = 0.95, src/Relprofile.cpp:633), so a tile is all
-//            midpoint-rule or all Romberg.  A warp owns a tile; its two half-warps work on two consecutive radii at
-//            a time, lane = bin EDGE (16 edges = 15 bins), and walk the radii in ascending order with the bin's sum in
-//            a register -> the reference's summation order, no atomics, no contribution buffer.
+//   main     BIN-STATIONARY.  The sub-batch's bin range is cut into tiles of 15 bins anchored at the bin where the
+//            quadrature rule changes (E = 0.95, src/Relprofile.cpp:633), so a tile is all midpoint-rule or all
+//            Romberg.  The two half-warps work on two consecutive radii at a time, lane = bin EDGE (16 edges = 15
+//            bins), and walk the radii in ascending order with the bin's sum in a register: no atomics, no
+//            contribution buffer.
 //              midpoint tiles: one evaluation of the integrand per bin.
 //              Romberg tiles:  the integrand at the bin edges is evaluated once per edge and shared by the two
 //                              neighbouring bins through a shuffle (the reference evaluates it twice); levels 1-2
-//                              (three more abscissae) for all lanes; the bins that have not converged by then (the
-//                              horns, ~13 %) are compacted across the warp: level 3 = 4 new abscissae of 8 bins per
-//                              pass, level 4 = 8 abscissae of 4 bins, summed by xor-butterflies and pulled back by
-//                              the owning lane, which keeps the tableau.  Levels 5-6 (~1e-4 of the bins) are
-//                              finished by the owning lane.
-//            The zone's row in HBM is the accumulator between sub-batches (read once, written once per sub-batch).
+//                              (three more abscissae) for all lanes.  The bins that have not converged by then (the
+//                              horns, ~13 %) are QUEUED in shared memory with their tableau (the queue lives in the
+//                              row stage, dead by then) and worked off once per sub-batch, or when the queue is full:
+//                              level 3 one lane per queued bin, level 4 compacted (8 lanes per bin, xor-butterfly),
+//                              what is left after level 4 (~1e-4 of the bins) by one lane each (deep_flush).
+//            The zone's row in HBM is the accumulator between sub-batches (read once, written once per tile and
+//            sub-batch); the queued bins' results are added to it when the queue is worked off, so a bin's sum runs in
+//            ascending radius order except for those late terms: deterministic, a function of the vector alone.
+//   split    vectors with few zones (line and convolution models, one-zone relxill flavours) have every zone cut into
+//            line_parts(nz) runs of radii, one CTA each (a single XSPEC call of relline would otherwise be ONE warp
+//            walking 1000 radii); k_linemerge adds the partial rows in order.
+// What the measurements of round 2 taught (profiles/README.md): with the integrand inlined at every quadrature site
+// the kernel was bound by instruction fetch (independent warps, 90 KB of code: stall_no_instruction 3.5 per issue), so
+// everything outside the two tile loops is written for size (one out-of-line copy of the integrand, rolled loops);
+// Romberg state kept in registers across the deep levels spilled (local memory through a 28 KB L1), hence the queue.
 //
 // Arithmetic.  The two branches k = 0, 1 of the transfer function share everything but the interpolated
 // trff value, so one evaluation of the integrand returns both (the reference calls relb_func twice).
@@ -61,10 +71,7 @@ __constant__ LnConst LK = {GFAC_H, 1.0 - GFAC_H, GS_C, GS_INVC, 0.02, 1.0 * 0.95
                            {0.0, 1.0 / 3.0, 1.0 / 15.0, 1.0 / 63.0, 1.0 / 255.0, 1.0 / 1023.0, 1.0 / 4095.0}};
 
 constexpr int LN_NT = 32;      // one warp per CTA
-constexpr int LN_NW = LN_NT / 32;
-#ifndef LN_MINB
-#define LN_MINB 8
-#endif
+constexpr int LN_MINB = 20;     // resident CTAs per SM asked of the compiler: 96 registers (24 / 80 registers spills)
 constexpr int LN_R = 8;          // radii per sub-batch
 constexpr int LN_ROWS = 5;       // table rows staged per sub-batch (a sub-batch is cut where its bracket would not fit)
 constexpr int LN_TB = 15;        // bins per tile (16 edges: one half warp)
@@ -428,8 +435,8 @@ __device__ __noinline__ double edge_terms(double Ea, double Eb, double gmin, dou
 
 // One warp per CTA: no block barrier anywhere (the only synchronisation is the mbarrier of the bulk copy and
 // __syncwarp around the shared-memory stage).  24 resident CTAs per SM at 8.8 KB of shared memory and 80 registers.
-template <int GRID_MODE, int MINB>
-__global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ vps, DevTables T, Scratch S, LineGrid G,
+template <int GRID_MODE>
+__global__ void __launch_bounds__(LN_NT, LN_MINB) k_line(const VPar *__restrict__ vps, DevTables T, Scratch S, LineGrid G,
                                                    int ne_stride, int nz_stride) {
   __shared__ __align__(128) LnSmem sm;
   const unsigned FULL = 0xffffffffu;
@@ -693,9 +700,6 @@ __global__ void __launch_bounds__(LN_NT, MINB) k_line(const VPar *__restrict__ v
                     }
                   }
                   if (!romb) need = 0;
-#ifdef EXP_NODEEP
-                need = 0;
-#endif
                 }
               }
               if (__any_sync(FULL, need == 3)) {   // queue the bins that go on to level 3
@@ -788,25 +792,14 @@ __global__ void __launch_bounds__(128) k_linemerge(const VPar *__restrict__ vps,
 }
 
 // ---------------------------------------------------------------------------------- launcher
-static int g_minb = 20;
-template <int MINB> static int line_init_one() {
-  // MINB CTAs x 18.6 KB of shared memory: the rest of the 256 KB stays L1 (energy grid, per-radius inputs, spills)
-  cudaError_t e = cudaFuncSetAttribute(k_line<0, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+int line_kernel_init() {
+  // all of the carve-out as shared memory: 9.5 KB (+1 KB reserved) per one-warp CTA is what limits residency
+  cudaError_t e = cudaFuncSetAttribute(k_line<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (e != cudaSuccess) return 1;
-  e = cudaFuncSetAttribute(k_line<1, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  e = cudaFuncSetAttribute(k_line<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   return e == cudaSuccess ? 0 : 1;
 }
-int line_kernel_init() {
-  if (const char *s = getenv("RELXILL_B200_LINE_MINB")) g_minb = atoi(s);
-  return line_init_one<24>() | line_init_one<20>() | line_init_one<16>();
-}
 
-template <int MINB>
-static void launch_line_t(const VPar *vps, const DevTables &T, const Scratch &S, dim3 grid, const LineGrid &G, int grid_mode,
-                          cudaStream_t st) {
-  if (grid_mode == 0) k_line<0, MINB><<<grid, LN_NT, 0, st>>>(vps, T, S, G, S.ne_line_cap, S.nz_cap);
-  else k_line<1, MINB><<<grid, LN_NT, 0, st>>>(vps, T, S, G, S.ne_line_cap, S.nz_cap);
-}
 // profile rows the arena needs per vector for zone counts in [nz_min, nz_max]
 int line_rows(int nz_min, int nz_max) {
   int r = nz_max;
@@ -822,9 +815,8 @@ void launch_line(const VPar *vps, const DevTables &T, const Scratch &S, long n, 
   G.e = egrid; G.n_ener = n_ener; G.mode = grid_mode;
   G.log_lo = std::log(CONV_EMIN);
   G.inv_dlog = (double) NCONV / (std::log(CONV_EMAX) - std::log(CONV_EMIN));
-  if (g_minb == 24) launch_line_t<24>(vps, T, S, grid, G, grid_mode, st);
-  else if (g_minb == 16) launch_line_t<16>(vps, T, S, grid, G, grid_mode, st);
-  else launch_line_t<20>(vps, T, S, grid, G, grid_mode, st);
+  if (grid_mode == 0) k_line<0><<<grid, LN_NT, 0, st>>>(vps, T, S, G, S.ne_line_cap, S.nz_cap);
+  else k_line<1><<<grid, LN_NT, 0, st>>>(vps, T, S, G, S.ne_line_cap, S.nz_cap);
   if (parts > 1) {
     if (grid_mode == 0) k_linemerge<0><<<(unsigned) n, 128, 0, st>>>(vps, S, G, S.ne_line_cap, S.nz_cap, nz_max);
     else k_linemerge<1><<<(unsigned) n, 128, 0, st>>>(vps, S, G, S.ne_line_cap, S.nz_cap, nz_max);
