@@ -268,14 +268,16 @@ def _alg_bytes(ab, n, nz, nb):
     """Algorithmic bytes per launch of each kernel family (SURVEY.md §8d's per-vector figures x n)."""
     nex = ab.get("zone_spectrum_values") or 2999   # values per zone spectrum row as filed by k_xill / read by k_conv
     return {
-        "k_xill": ab["xillver"] + n * nz * nex * 8.0,                        # distinct table rows + zone spectra out
-        "k_line": n * (100 * 40 * 4 * 8.0 + 1000 * 5 * 8.0) + ab["line_profiles"],  # (a,mu0)-interpolated rows + radius scalars in, profiles out
+        # table rows that any vector of the launch reads, once (vectors share rows through L2; the per-vector count is in
+        # `table_rows_delivered`) + zone spectra out
+        "k_xill": (ab.get("xillver_union") or ab["xillver"]) + n * nz * nex * 8.0,
+        "k_line": n * (100 * 40 * 2 * 8.0 + 1000 * 6 * 8.0) + ab["line_profiles"],  # (a,mu0)-interpolated trff rows + radius scalars in, profiles out
         "k_conv": ab["line_profiles"] + n * (nz * nex * 8.0 + nb * 8.0),      # profiles + zone spectra in, spectrum out
         "k_fine": n * (2 * 4 * 40 * 16.0 * 100 + 1000 * 10 * 8.0),           # 4 corners x 100 radii x 40 g* float4 in, angle-distribution parts out
         "k_dist": n * (1000 * 10 * 8.0),
         "k_syspar": 2 * n * (4 * 3 * 100 * 4.0 + 2 * 2 * 3 * 100 * 4.0 + (3 * 2500 + 2 * 50000) * 8.0 + 7 * 1000 * 8.0),
         "k_zone": n * (4 * 1000 * 8.0),
-        "k_nth": n * (3 * 900 * 64 * 8.0),
+        "k_nth": n * ((nz + 1) * 4 * 8.0 + 900 * 8.0),                       # per solve kTe in, 3 numbers out; the source's solution out
         "k_prim_nth": n * (2 * 4096 * 8.0 + nb * 8.0),
     }
 

@@ -137,7 +137,8 @@ void relxill_b200_free_batch(relxill_b200_batch *b);
  * table/IO terms.  out[0]=bytes total, out[1]=sum of U over vectors, out[2]=xillver bytes,
  * out[3]=upper bound without cross-zone sharing, out[4]=bytes of the per-zone line profiles actually
  * produced (first to last non-zero bin of every zone), out[5]=values per zone spectrum row as filed by
- * k_xill and read by k_conv, out[6..7] reserved (0). */
+ * k_xill and read by k_conv, out[6]=bytes of the xillver rows that ANY vector of the batch reads, each counted once
+ * (what has to leave DRAM per launch at least; vectors share rows through L2), out[7] reserved (0). */
 int relxill_b200_algorithmic_bytes(relxill_b200_batch *b, double *out8);
 /* Number of kernel launches issued by the last relxill_b200_run of `b`. */
 long relxill_b200_last_launches(relxill_b200_batch *b);

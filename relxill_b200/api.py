@@ -207,7 +207,7 @@ class Batch:
         out = np.zeros(8)
         _lib.lib().relxill_b200_algorithmic_bytes(self._h, out)
         return dict(total=out[0], distinct_rows=out[1], xillver=out[2], xillver_upper_bound=out[3],
-                    line_profiles=out[4], zone_spectrum_values=out[5])
+                    line_profiles=out[4], zone_spectrum_values=out[5], xillver_union=out[6])
 
     def kernel_times(self) -> dict:
         names = (C.c_char_p * 16)()

@@ -1095,13 +1095,14 @@ int relxill_b200_algorithmic_bytes(relxill_b200_batch *b, double *out8) {
   const long nc = b->last_chunk_n;
   const Scratch S = scratch_slice(E.S, b->arena_c0, false);
   double sumU = 0, bound = 0;
-  double xbytes = 0;
+  double xbytes = 0, xbytes_union = 0;
   if (m.type == T_RELXILL && nc > 0) {
     const XillHost &xh = E.tables->xill_host(model_xtab(m));
     const int ncorn = (xh.npar == 6) ? 32 : 16;
     std::vector<int> rows((size_t) nc * NZMAX * 32);
     if (cudaMemcpy(rows.data(), S.xrow, rows.size() * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
     const double row_bytes = (double) xh.n_incl * xh.n_ener * 4.0;
+    std::set<int> all;   // rows any vector of the chunk reads: what has to come out of DRAM at least once per launch
     for (long i = 0; i < nc; i++) {
       const VPar &vp = b->vps[b->last_chunk0 + i];
       if (b->status[b->last_chunk0 + i] != ST_OK) continue;
@@ -1109,8 +1110,12 @@ int relxill_b200_algorithmic_bytes(relxill_b200_batch *b, double *out8) {
       for (int z = 0; z < vp.nz; z++)
         for (int c = 0; c < ncorn; c++) u.insert(rows[((size_t) i * NZMAX + z) * 32 + c]);
       sumU += (double) u.size();
+      all.insert(u.begin(), u.end());
       bound += (double) vp.nz * ncorn * row_bytes;
     }
+    // the rows k_xill actually reads: the fp64 convolution-grid copy (xc_n bins) or the f32 table rows
+    xbytes_union = (double) all.size() * (double) xh.n_incl * (b->xill_conv_grid ? xh.xc_n * 8.0 : xh.n_ener * 4.0)
+                   * ((double) b->n / (double) nc > 1.0 ? (double) b->n / (double) nc : 1.0);
     const double scale = (double) b->n / (double) nc;  // chunks beyond the last are assumed alike
     sumU *= scale;
     bound *= scale;
@@ -1148,6 +1153,7 @@ int relxill_b200_algorithmic_bytes(relxill_b200_batch *b, double *out8) {
     const XillHost &xh = E.tables->xill_host(model_xtab(m));
     out8[5] = b->xill_conv_grid ? xh.xc_n : xh.n_ener;
   }
+  out8[6] = xbytes_union;
   return 0;
 }
 
