@@ -6,9 +6,9 @@ timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -3
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k 'regex:k_' -s 9 -c 9 -f -o gpurun_out/prof_step \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_step.log 2>&1
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/ncu_step.log 2>&1
 tail -1 gpurun_out/ncu_step.log | cut -c1-200
 python bench.py --model relxilllpCp --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cp.json 2> gpurun_out/bench_cp.err
 python scripts/cfg4_probe.py 8192 > gpurun_out/cfg4.json 2> gpurun_out/cfg4.err
