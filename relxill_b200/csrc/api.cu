@@ -63,6 +63,7 @@ struct Engine {
   Tables *tables = nullptr;
   Scratch S{};
   bool S_nth = false;         // the nthcomp work arrays of the arena are allocated
+  bool S_fine = false;        // ... and the fine transfer-function / emission-angle arrays
   std::vector<void *> scratch_allocs;
   double *d_io = nullptr;     // output staging of host-buffer calls
   size_t d_io_cap = 0;
@@ -184,12 +185,15 @@ void free_scratch(Engine &E) {
   E.scratch_allocs.clear();
   E.S = Scratch{};
   E.S_nth = false;
+  E.S_fine = false;
 }
 
-int ensure_scratch(Engine &E, long cap, int nz_cap, int ne_cap, int nex_stride, bool nth) {
+int ensure_scratch(Engine &E, long cap, int nz_cap, int ne_cap, int nex_stride, bool nth, bool fine) {
   Scratch &S = E.S;
-  if (S.cap >= cap && S.nz_cap >= nz_cap && S.ne_line_cap >= ne_cap && S.nex_stride >= nex_stride && (!nth || E.S_nth)) return 0;
+  if (S.cap >= cap && S.nz_cap >= nz_cap && S.ne_line_cap >= ne_cap && S.nex_stride >= nex_stride && (!nth || E.S_nth) &&
+      (!fine || E.S_fine)) return 0;
   nth = nth || E.S_nth;
+  fine = fine || E.S_fine;
   cap = std::max(cap, S.cap);
   nz_cap = std::max(nz_cap, S.nz_cap);
   ne_cap = std::max(ne_cap, S.ne_line_cap);
@@ -207,7 +211,9 @@ int ensure_scratch(Engine &E, long cap, int nz_cap, int ne_cap, int nex_stride, 
   };
 #define RX_ALLOC(type, name, count) alloc((void **) &S.name, c * (size_t) (count) * sizeof(type));
 #define RX_ALLOC_NTH(type, name, count) if (nth) alloc((void **) &S.name, c * (size_t) (count) * sizeof(type));
-  SCRATCH_FIELDS(RX_ALLOC, RX_ALLOC_NTH)
+#define RX_ALLOC_FINE(type, name, count) if (fine) alloc((void **) &S.name, c * (size_t) (count) * sizeof(type));
+  SCRATCH_FIELDS(RX_ALLOC, RX_ALLOC_NTH, RX_ALLOC_FINE)
+#undef RX_ALLOC_FINE
 #undef RX_ALLOC
 #undef RX_ALLOC_NTH
   (void) nzc; (void) nec; (void) nxs;
@@ -218,6 +224,7 @@ int ensure_scratch(Engine &E, long cap, int nz_cap, int ne_cap, int nex_stride, 
   }
   S.cap = cap; S.nz_cap = nz_cap; S.ne_line_cap = ne_cap; S.nex_stride = nex_stride;
   E.S_nth = nth;
+  E.S_fine = fine;
   return 0;
 }
 
@@ -229,7 +236,9 @@ Scratch scratch_slice(const Scratch &S, long c0, bool nth) {
   const size_t nzc = (size_t) S.nz_cap, nec = (size_t) S.ne_line_cap, nxs = (size_t) std::max(S.nex_stride, 1);
 #define RX_OFF(type, name, count) R.name = S.name + o * (size_t) (count);
 #define RX_OFF_NTH(type, name, count) if (nth) R.name = S.name + o * (size_t) (count);
-  SCRATCH_FIELDS(RX_OFF, RX_OFF_NTH)
+#define RX_OFF_FINE(type, name, count) if (S.name) R.name = S.name + o * (size_t) (count);
+  SCRATCH_FIELDS(RX_OFF, RX_OFF_NTH, RX_OFF_FINE)
+#undef RX_OFF_FINE
 #undef RX_OFF
 #undef RX_OFF_NTH
   (void) nzc; (void) nec; (void) nxs;
@@ -418,7 +427,8 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
   if (E.arena_busy_set && st != E.arena_stream) CK(cudaStreamWaitEvent(st, E.arena_busy, 0));
   const int nz_line_min = relxill ? b->nz_min : 1, nz_line_max = relxill ? b->nz_max : 1;
   const int line_nk = line_launches(nz_line_min, nz_line_max);
-  if (ensure_scratch(E, cap, xillver ? b->nz_max : std::max(b->nz_max, line_rows(nz_line_min, nz_line_max)), ne_line, nex_stride, nth)) return -2;
+  const bool fine = !xillver && (b->any_limb || cc.keep_intermediates);   // the fine arrays are filed: probes, limb darkening
+  if (ensure_scratch(E, cap, xillver ? b->nz_max : std::max(b->nz_max, line_rows(nz_line_min, nz_line_max)), ne_line, nex_stride, nth, fine)) return -2;
   const Scratch S0 = E.S;
   b->launches = 0;
   for (int k = 0; k < KF_COUNT; k++) { b->kt_ms[k] = 0; b->kt_n[k] = 0; }
@@ -1177,8 +1187,11 @@ int relxill_b200_probe(relxill_b200_batch *b, long iv, const char *what, double 
   else if (w == "emis") { src = S.emis + v * NR; n = NR; }
   else if (w == "del_emit") { src = S.del_emit + v * NR; n = NR; }
   else if (w == "del_inc") { src = S.del_inc + v * NR; n = NR; }
-  else if (w == "trff") { src = S.trff + v * NR * NG * 2; n = (size_t) NR * NG * 2; }
-  else if (w == "cosne") { src = S.cosne + v * NR * NG * 2; n = (size_t) NR * NG * 2; }
+  else if (w == "trff" || w == "cosne") {
+    const double *base = (w == "trff") ? S.trff : S.cosne;
+    if (!base) { set_err("probe: the fine transfer functions are only filed with relxill_b200_keep_intermediates(1)"); return -1; }
+    src = base + v * NR * NG * 2; n = (size_t) NR * NG * 2;
+  }
   else if (w == "reflfrac") { src = S.reflfrac + v * 8; n = 5; }
   else if (w == "lxi") { src = S.zlxi + v * NZMAX; n = vp.nz; }
   else if (w == "dens") { src = S.zdens + v * NZMAX; n = vp.nz; }

@@ -130,7 +130,9 @@ struct DevTables {
 // capacities of the arena): api.cu allocates from the list and offsets from it when a piece of a batch works on its own
 // slice of the arena, so the two cannot drift apart.
 //   X(type, name, elements per vector)            NTH_X: allocated only for the nthcomp (Cp) models
-#define SCRATCH_FIELDS(X, NTH_X)                                                                                          \
+//                                                 FINE_X: only when a batch files the fine transfer functions / emission
+//                                                 angles (test probes, limb darkening): 1.3 MB per vector
+#define SCRATCH_FIELDS(X, NTH_X, FINE_X)                                                                                         \
   X(double, re, NR) X(double, gmin, NR) X(double, gmax, NR) X(double, emis, NR)     /* fine radial grid quantities */     \
   X(double, del_emit, NR) X(double, del_inc, NR) X(double, fr, NR)                                                        \
   X(int, it, NR) X(int, izone, NR)                                                                                        \
@@ -139,7 +141,7 @@ struct DevTables {
   X(double, brk_f, 2)              /* its interpolation factors */                                                        \
   X(double, glim, 2)               /* min gmin / max gmax over radii */                                                   \
   X(double, reflfrac, 8)                                                                                                  \
-  X(double, trff, (size_t) NR * NG * 2) X(double, cosne, (size_t) NR * NG * 2)      /* [NR][NG][2] */                     \
+  FINE_X(double, trff, (size_t) NR * NG * 2) FINE_X(double, cosne, (size_t) NR * NG * 2)   /* [NR][NG][2]: probes, limb */ \
   X(double, relrow, (size_t) REL_NRT * NG * 4)   /* table rows interpolated in (a, mu0): trff1,2, cosne1,2 */             \
   X(double, eshift, NZMAX) X(double, zlxi, NZMAX) X(double, zdens, NZMAX) X(double, zect, NZMAX)                          \
   X(double, normch, NZMAX) X(double, corr_flux, NZMAX) X(double, corr_gshift, NZMAX)                                      \
@@ -168,7 +170,7 @@ struct Scratch {
   int ne_line_cap;   // bins of the line-profile grid allocated
   int nex_stride;    // xillver row stride
 #define RX_DECL(type, name, count) type *name;
-  SCRATCH_FIELDS(RX_DECL, RX_DECL)
+  SCRATCH_FIELDS(RX_DECL, RX_DECL, RX_DECL)
 #undef RX_DECL
   // Re-use of the previous run's device-resident state (api.cu: the arena still holds this batch): per vector,
   // REUSE_REL = the relativistic half (k_syspar, k_fine, k_dist, k_line outputs) is still valid, REUSE_ALL = the
