@@ -690,3 +690,53 @@ def test_num_zones_env_between_two_lmod_calls(rx, oracle, monkeypatch):
     assert relerr(a35, oracle.eval("relxilllp", e, p)) < RTOL and relerr(a35, a10) > 1e-7
     monkeypatch.delenv("RELXILL_NUM_RZONES")
     np.testing.assert_array_equal(rx.lmod("relxilllp", e, p), a10)
+
+
+@pytest.mark.parametrize("zones", [2, 3, 8, 9])
+def test_few_zones_split_into_runs(rx, oracle, zones):
+    """Vectors with <= 8 zones have every zone's radii cut into runs (one CTA each) whose partial line profiles
+    k_linemerge adds in order (line.cu: line_parts); 9 zones is the first count that is not split."""
+    e = default_grid(900)
+    P = sample_params("relxilllp", 6, seed=300 + zones)
+    rx.set_num_zones(zones)
+    oracle.set_num_zones(zones)
+    try:
+        f, st = rx.batch_eval("relxilllp", e, P, return_status=True)
+        assert (st == 0).all()
+        for i in range(len(P)):
+            assert relerr(f[i], oracle.eval("relxilllp", e, P[i])) < RTOL, (zones, i)
+        # the zone profiles themselves, against the oracle's
+        import torch
+        b = rx.Batch("relxilllp", e, P[:2], keep_intermediates=True)
+        out = torch.zeros((2, e.size - 1), dtype=torch.float64, device="cuda")
+        b.run(out.data_ptr())
+        torch.cuda.synchronize()
+        for i in range(2):
+            assert relerr(b.probe(i, "relflux"), oracle.stages("relxilllp", P[i])["relflux"]) < 1e-11, (zones, i)
+        b.close()
+    finally:
+        rx.set_num_zones(None)
+        oracle.set_num_zones(None)
+
+
+def test_mixed_zone_counts_in_one_batch(rx, oracle, monkeypatch):
+    """relxilllpCp with RELXILL_NUM_RZONES=5: constant-ionisation vectors get 5 zones (split into runs), vectors with an
+    ionisation gradient ignore a value below 10 and get 25 (not split) — both kinds in one launch."""
+    e = default_grid(700)
+    P = sample_params("relxilllpCp", 8, seed=41)
+    names = rx.PARAM_NAMES["relxilllpCp"]
+    P[:, names.index("iongrad_type")] = [0, 1, 0, 2, 0, 1, 0, 0]
+    rx.set_num_zones(None)
+    oracle.set_num_zones(None)
+    monkeypatch.setenv("RELXILL_NUM_RZONES", "5")
+    try:
+        f, st = rx.batch_eval("relxilllpCp", e, P, return_status=True)
+        ok = st == 0
+        assert ok.sum() >= 6
+        for i in np.flatnonzero(ok):
+            assert relerr(f[i], oracle.eval("relxilllpCp", e, P[i])) < RTOL, i
+        # the same vectors one by one: a spectrum does not depend on its batch
+        for i in np.flatnonzero(ok)[:4]:
+            np.testing.assert_array_equal(rx.batch_eval("relxilllpCp", e, P[i : i + 1])[0], f[i])
+    finally:
+        monkeypatch.delenv("RELXILL_NUM_RZONES")
