@@ -71,7 +71,7 @@ __constant__ LnConst LK = {GFAC_H, 1.0 - GFAC_H, GS_C, GS_INVC, 0.02, 1.0 * 0.95
                            {0.0, 1.0 / 3.0, 1.0 / 15.0, 1.0 / 63.0, 1.0 / 255.0, 1.0 / 1023.0, 1.0 / 4095.0}};
 
 constexpr int LN_NT = 32;      // one warp per CTA
-constexpr int LN_MINB = 20;     // resident CTAs per SM asked of the compiler: 96 registers (24 / 80 registers spills)
+constexpr int LN_MINB = 20;     // resident CTAs per SM asked of the compiler: 96 registers (22 CTAs / 80 registers: spills, 9.2 ms against 8.6)
 constexpr int LN_R = 8;          // radii per sub-batch
 constexpr int LN_ROWS = 5;       // table rows staged per sub-batch (a sub-batch is cut where its bracket would not fit)
 constexpr int LN_TB = 15;        // bins per tile (16 edges: one half warp)
@@ -578,11 +578,11 @@ __global__ void __launch_bounds__(LN_NT, LN_MINB) k_line(const VPar *__restrict_
       // tiles anchored at j95: tile k covers bins [j95 + k LN_TB, j95 + (k+1) LN_TB)
       const int k_lo = (jlo - j95 >= 0) ? (jlo - j95) / LN_TB : -((j95 - jlo + LN_TB - 1) / LN_TB);
       const int k_hi = (jhi - j95 >= 0) ? (jhi - j95) / LN_TB : -((j95 - jhi + LN_TB - 1) / LN_TB);
-      const int npair = (n + 1) >> 1;
       // The bins that need Romberg levels 3+ wait in the queue; it is worked off (one copy of that code) when it cannot
       // take another visit (`again`: the tile is written out, resumed afterwards at the same radius pair) and after the
       // sub-batch's last tile.
-      for (int k = k_hi, pr = 0, again = 0;;) {
+      unsigned pm = 0;   // radius pairs of the current tile still to visit
+      for (int k = k_hi, again = 0;;) {
         if (again || k < k_lo) {
           __syncwarp();
           if (ndq) { deep_flush(sm, ndq, lane, g_cosne, limb, flux); ndq = 0; }
@@ -593,14 +593,19 @@ __global__ void __launch_bounds__(LN_NT, LN_MINB) k_line(const VPar *__restrict_
         const double Eb = line_edge(egrid, min(max(j + 1, 0), n_ener), grid_mode, zred, lineE);
         const bool binlane = (hl < LN_TB) && (j >= jlo) && (j <= jhi);
         double acc = (binlane && (again || ((j >= zold_lo) && (j <= zold_hi)))) ? flux[j] : 0.0;
+        if (!again) {   // the pairs with a radius whose bins reach into this tile (lane r < 8 looks at radius r)
+          const int tlo = max(j95 + k * LN_TB, jlo), thi = min(j95 + k * LN_TB + LN_TB - 1, jhi);
+          const LnRad &lq = sm.rad[lane & (LN_R - 1)];
+          const unsigned m = __ballot_sync(FULL, (lane < n) && (lq.iehi >= tlo) && (lq.ielo <= thi)) & 0xffu;
+          pm = (m | (m >> 1)) & 0x55u;
+        }
         {
           if (k < 0) {
             // ---------------- midpoint-rule tile (int_romb with lo < 0.95, src/Relprofile.cpp:628-647)
-            for (; pr < npair; pr++) {
-              const int rsel = 2 * pr + half;
+            for (; pm; pm &= pm - 1) {
+              const int rsel = (__ffs(pm) - 1) + half;
               const LnRad &lr = sm.rad[rsel];
               const bool in = binlane && (j >= lr.ielo) && (j <= lr.iehi);
-              if (!__any_sync(FULL, in)) continue;
               // limits of the quadrature: the bin, cut at the ends of the analytic edge intervals (the reference takes
               // these decisions in g*; an ulp of difference moves the cut by an ulp)
               const double ehlo = lr.ehlo, ehhi = lr.ehhi;
@@ -635,16 +640,15 @@ __global__ void __launch_bounds__(LN_NT, LN_MINB) k_line(const VPar *__restrict_
               }
               // ascending-radius accumulation: the lower half's radius first, then the upper half's
               const double own = in ? flu * lr.weight : 0.0;
-              const double oth = __shfl_xor_sync(FULL, own, 16);
-              acc = (acc + (half ? oth : own)) + (half ? own : oth);
+              const double oth = __shfl_down_sync(FULL, own, 16);   // the upper half's radius comes second
+              acc = (acc + own) + oth;                              // (only the lower half's sum is kept)
             }
           } else {
             // ---------------- Romberg tile (src/Relprofile.cpp:524-579), both branches
-            for (; pr < npair; pr++) {
-              const int rsel = 2 * pr + half;
+            for (; pm; pm &= pm - 1) {
+              const int rsel = (__ffs(pm) - 1) + half;
               const LnRad &lr = sm.rad[rsel];
               const bool in = binlane && (j >= lr.ielo) && (j <= lr.iehi);
-              if (!__any_sync(FULL, in)) continue;
               const double ehlo = lr.ehlo, ehhi = lr.ehhi;
               // every lane evaluates the integrand at its own lower edge, clamped to the quadrature's range: that is
               // the lower limit of its bin and the upper limit of the neighbour's
@@ -726,15 +730,15 @@ __global__ void __launch_bounds__(LN_NT, LN_MINB) k_line(const VPar *__restrict_
                 flu = flu + rsum;
               }
               const double own = in ? flu * lr.weight : 0.0;
-              const double oth = __shfl_xor_sync(FULL, own, 16);
-              acc = (acc + (half ? oth : own)) + (half ? own : oth);
+              const double oth = __shfl_down_sync(FULL, own, 16);   // the upper half's radius comes second
+              acc = (acc + own) + oth;                              // (only the lower half's sum is kept)
             }
           }
         }
         // only the bins this zone touched are written; the range travels with the row
         if (binlane && half == 0) flux[j] = acc;
-        again = pr < npair;
-        if (!again) { k--; pr = 0; }
+        again = pm != 0;
+        if (!again) k--;
       }
     }
     cur += n;
