@@ -1,17 +1,22 @@
 // kernels.cu — hand-written sm_100a kernels of the relxill spectrum-evaluation hot path.
 //
-// One batch chunk = C parameter vectors.  Kernel sequence (see DESIGN.md for the data flow):
-//   k_syspar   1 CTA / vector : (a,mu0) table interpolation of the 100 table radii, fine radial grid,
-//                               emissivity (broken power law | lamp post [+ returning radiation])
-//   k_zone     1 CTA / vector : per-zone ionisation / density / Ecut, xillver corner indices+weights,
+// One batch chunk = C parameter vectors.  Kernel sequence (see DESIGN.md §4 for the data flow and the measurements):
+//   k_syspar   1 CTA / vector   (this file)  (a,mu0) table interpolation of the 100 table radii, fine radial grid,
+//                               emissivity (broken power law | lamp post [+ returning radiation, second pass])
+//   k_zone     1 CTA / vector   (this file)  per-zone ionisation / density / Ecut, xillver corner slots + weights,
 //                               primary-spectrum normalisations, returning-radiation correction factors
-//   k_fine     (vector, 8 radii): transfer function + emission-angle tables on the fine radial grid
-//   k_dist     1 CTA / vector : emission-angle distribution per zone
-//   k_line     (vector, 256 energy bins): relline profile, bin-stationary: every thread owns one energy
-//                               bin and walks the 1000 radii -> no atomics, reference summation order
-//   k_xill     (vector, zone) : 16/32-corner xillver gather-blend, angle-weighted
-//   k_conv     1 CTA / vector : rebin, shared-memory FFT convolution per zone, primary spectrum,
+//   k_nth      64 solves / CTA  (nthcomp.cu) Kompaneets solutions of the zones and the source (Cp models)
+//   k_rows     (13, vector)     (this file)  (a,mu0) half of the transfer-function interpolation, per TABLE radius
+//   k_fine     (125, vector)    (this file)  per-radius parts of the emission-angle distribution (radial half of the
+//                               interpolation in registers; files the fine arrays only for probes / limb darkening)
+//   k_dist     1 CTA / vector   (this file)  emission-angle distribution per zone
+//   k_line     one WARP per (vector, zone[, run of radii]) (line.cu)  relline profile: table rows staged with one bulk
+//                               copy, bin-stationary tiles, Romberg levels 3+ through a shared-memory queue
+//   k_xill     (vector, energy tile) (xill.cu)  corner-stationary xillver blend on the convolution grid, angle-weighted
+//   k_conv     1 CTA / vector   (conv.cu)    radix-16 shared-memory FFT convolution per zone, primary spectrum,
 //                               rebin to the output grid
+//   k_linefinish / k_xillver / k_prim_nth: the line models' normalisation, the standalone xillver models, the nthcomp
+//                               primary
 // Reference code each kernel replaces is cited at the kernel.  FP64 throughout where the reference
 // uses double; float where it uses float (interpolation factors).  No tensor cores: no stage is a
 // dense contraction.
