@@ -317,15 +317,16 @@ __device__ __forceinline__ void deep_tableau(LnDeep &d, int L, double s0, double
   const double pasn = d.pas * (1.0 / (double) (1 << L)), pasp = pasn * 2.0;
   int flags = d.flags & 3;
   bool more = false;
-#pragma unroll 1
+#pragma unroll
   for (int k = 0; k < 2; k++) {
     double prev = d.sum[k] * pasp;   // first tableau entry of the previous level
     const double sum = d.sum[k] + (k ? s1 : s0);
     d.sum[k] = sum;
     if (flags & (1 << k)) continue;
     double cur = sum * pasn, r4 = 1.0, last = 0.0;
-#pragma unroll 1
-    for (int ii = 1; ii <= L; ii++) {   // t[ii] = (4^ii t[ii-1] - tprev[ii-1]) / (4^ii - 1); tq[ii-1] holds t[ii]
+#pragma unroll
+    for (int ii = 1; ii <= 4; ii++) {
+      if (ii > L) break;   // t[ii] = (4^ii t[ii-1] - tprev[ii-1]) / (4^ii - 1); tq[ii-1] holds t[ii]
       r4 *= 4.0;
       cur = (r4 * cur - prev) * LK.inv[ii];
       if (ii < L) { prev = d.tq[k][ii - 1]; d.tq[k][ii - 1] = cur; last = prev; }
@@ -343,6 +344,8 @@ __device__ __forceinline__ void deep_tableau(LnDeep &d, int L, double s0, double
 }
 __device__ __forceinline__ void deep_flush(LnSmem &sm, int ndq, int lane, const double2 *g_cosne, int limb, double *flux) {
   const unsigned FULL = 0xffffffffu;
+  // the bins' sums so far (the tiles they belong to have been written): fetched now, needed at the very end
+  const double before = (lane < ndq) ? flux[sm.dq[lane].j] : 0.0;
   // ---- level 3, one lane per entry: its four new abscissae in ascending order, then the tableau
   {
     LnDeep &d = sm.dq[min(lane, ndq - 1)];
@@ -414,7 +417,7 @@ __device__ __forceinline__ void deep_flush(LnSmem &sm, int ndq, int lane, const 
     double tot = 0.0;
 #pragma unroll 1
     for (unsigned mm = same; mm; mm &= mm - 1) tot += sm.dq[__ffs(mm) - 1].sum[0];   // ascending lanes = queue order
-    flux[j] += tot;
+    flux[j] = before + tot;
   }
   __syncwarp();
 }
