@@ -26,8 +26,8 @@
 //                              (three more abscissae) for all lanes.  The bins that have not converged by then (the
 //                              horns, ~13 %) are QUEUED in shared memory with their tableau (the queue lives in the
 //                              row stage, dead by then) and worked off once per sub-batch, or when the queue is full:
-//                              level 3 one lane per queued bin, level 4 compacted (8 lanes per bin, xor-butterfly),
-//                              what is left after level 4 (~1e-4 of the bins) by one lane each (deep_flush).
+//                              levels 3 and 4 one lane per queued bin, what is left after level 4 (~1e-4 of the
+//                              bins) by a whole new integration, one lane each (deep_flush).
 //            The zone's row in HBM is the accumulator between sub-batches (read once, written once per tile and
 //            sub-batch); the queued bins' results are added to it when the queue is worked off, so a bin's sum runs in
 //            ascending radius order except for those late terms: deterministic, a function of the vector alone.
@@ -103,7 +103,6 @@ struct LnSmem {
   double2 fine[LN_R][LN_FS];     // {branch 0, branch 1} of the sub-batch's radii
   LnRad rad[LN_R + 2];
   unsigned long long mbar;
-  int slot[32];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -307,10 +306,10 @@ __device__ __forceinline__ void ln_ctx(const LnSmem &sm, int r, const double2 *g
   c.cosne = g_cosne + (size_t) lr.gi * NG; c.limb = limb;
 }
 
-// Levels 3+ of the queued bins, compacted over the warp (src/Relprofile.cpp:553-576): level L takes NP = 2^(L-1) lanes
-// per bin, one per new abscissa a + (2p+1) pas / 2^L (level 3: 8 bins per pass, level 4: 4), an xor-butterfly sums them
-// and the group's first lane advances the bin's tableau in the queue entry.  What is left after level 4 (~1e-4 of the
-// Romberg bins) and the bins queued for a whole integration are finished by one lane each.  The results (weighted with
+// Levels 3+ of the queued bins (src/Relprofile.cpp:553-576), one lane per queued bin: the level's new abscissae, then
+// the bin's tableau in the queue entry.  (Level 4 compacted over the warp, 8 lanes per bin with an xor-butterfly, was
+// slower: 8.47 against 8.36 ms.)  What is left after level 4 (~1e-4 of the Romberg bins) and the bins queued for a whole
+// integration are finished by one lane each too.  The results (weighted with
 // the radius' area weight) are added to the zone's row in HBM; queue order = radius order, so the sum is deterministic.
 // Written for size, not speed (rolled loops, one call site of the integrand): see relb2_f.
 __device__ __forceinline__ void deep_tableau(LnDeep &d, int L, double s0, double s1) {
@@ -346,48 +345,25 @@ __device__ __forceinline__ void deep_flush(LnSmem &sm, int ndq, int lane, const 
   const unsigned FULL = 0xffffffffu;
   // the bins' sums so far (the tiles they belong to have been written): fetched now, needed at the very end
   const double before = (lane < ndq) ? flux[sm.dq[lane].j] : 0.0;
-  // ---- level 3, one lane per entry: its four new abscissae in ascending order, then the tableau
-  {
+  // ---- levels 3 and 4, one lane per entry: the level's new abscissae a + p pas / 2^L (p odd) in ascending order,
+  // then the tableau (src/Relprofile.cpp:553-576)
+#pragma unroll 1
+  for (int L = 3; L <= 4; L++) {
     LnDeep &d = sm.dq[min(lane, ndq - 1)];
-    const bool go = (lane < ndq) && ((d.flags >> 8) == 3);
-    if (__any_sync(FULL, go)) {
-      RelbCtx c;
-      ln_ctx(sm, d.rsel, g_cosne, limb, c);
-      const double a = d.a, pas8 = d.pas * 0.125;
-      double s0 = 0.0, s1 = 0.0;
+    const bool go = (lane < ndq) && ((d.flags >> 8) == L);
+    if (!__any_sync(FULL, go)) break;   // nothing goes on
+    RelbCtx c;
+    ln_ctx(sm, d.rsel, g_cosne, limb, c);
+    const double a = d.a, pasl = d.pas * (L == 3 ? 0.125 : 0.0625);
+    double s0 = 0.0, s1 = 0.0;
 #pragma unroll 1
-      for (int p = 1; p < 8; p += 2) {
-        double w0, w1;
-        relb2(a + pas8 * (double) p, c, w0, w1);
-        s0 += w0;
-        s1 += w1;
-      }
-      if (go) deep_tableau(d, 3, s0, s1);
-    }
-  }
-  __syncwarp();
-  // ---- level 4: the entries that go on, compacted, 4 per pass with 8 lanes each
-  {
-    const bool go = (lane < ndq) && ((sm.dq[min(lane, ndq - 1)].flags >> 8) == 4);
-    const unsigned m = __ballot_sync(FULL, go);
-    const int nl = __popc(m);
-    if (go) sm.slot[__popc(m & ((1u << lane) - 1))] = lane;
-    __syncwarp();
-#pragma unroll 1
-    for (int b = 0; b < nl; b += 4) {
-      const int q = b + (lane >> 3), p = lane & 7;
-      LnDeep &d = sm.dq[sm.slot[min(q, nl - 1)]];
-      RelbCtx c;
-      ln_ctx(sm, d.rsel, g_cosne, limb, c);
+    for (int p = 1; p < (1 << L); p += 2) {
       double w0, w1;
-      relb2(d.a + d.pas * 0.0625 * (double) (2 * p + 1), c, w0, w1);
-#pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {
-        w0 += __shfl_xor_sync(FULL, w0, o);
-        w1 += __shfl_xor_sync(FULL, w1, o);
-      }
-      if (q < nl && p == 0) deep_tableau(d, 4, w0, w1);
+      relb2(a + pasl * (double) p, c, w0, w1);
+      s0 += w0;
+      s1 += w1;
     }
+    if (go) { if (L == 3) deep_tableau(d, 3, s0, s1); else deep_tableau(d, 4, s0, s1); }
     __syncwarp();
   }
   // ---- results, one lane per entry (whole integrations, level code 1, are done here), added to the zone's row in
