@@ -27,4 +27,10 @@ for zones in (None, 50):
         P[1, 0] *= 1.01
         f2 = rx.batch_eval(m, e, P, fin if m.startswith("relconv") else None)
         print(m, zones, st.tolist(), float(np.nansum(f)), float(np.nansum(f2)))
+# a line model on a grid far finer than the profile: the deep queue of k_line fills inside a tile (resume path), wide zones
+ef = np.linspace(0.25, 1.45, 6001) * 6.4
+Pf = sample_params("relline", 2, seed=71)
+Pf[:, 0] = 6.4
+ff, stf = rx.batch_eval("relline", ef, Pf, return_status=True)
+print("relline fine grid", stf.tolist(), float(np.nansum(ff)))
 print("done")

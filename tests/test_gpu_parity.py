@@ -740,3 +740,26 @@ def test_mixed_zone_counts_in_one_batch(rx, oracle, monkeypatch):
             np.testing.assert_array_equal(rx.batch_eval("relxilllpCp", e, P[i : i + 1])[0], f[i])
     finally:
         monkeypatch.delenv("RELXILL_NUM_RZONES")
+
+
+def test_fine_grid_around_the_line_fills_the_deep_queue(rx, oracle):
+    """A line model on a grid much finer than the profile's structure: hundreds of Romberg bins per radius, many of them
+    past level 2, so the queue of k_line fills inside a tile (the resume path) and zones are wider than any tile."""
+    e = np.linspace(0.25, 1.45, 9001) * 6.4
+    P = sample_params("relline", 5, seed=71)
+    names = rx.PARAM_NAMES["relline"]
+    P[:, names.index("lineE")] = 6.4
+    P[:, names.index("z")] = [0.0, 0.0, 0.02, 0.0, 0.1]
+    P[:, names.index("limb")] = [0, 0, 0, 1, 2]
+    f, st = rx.batch_eval("relline", e, P, return_status=True)
+    assert (st == 0).all()
+    for i in range(len(P)):
+        want = oracle.eval("relline", e, P[i])
+        assert relerr(f[i], want) < RTOL, i
+        assert abs(f[i].sum() / want.sum() - 1) < 1e-9
+    # relline_lp through the same path
+    P2 = sample_params("relline_lp", 3, seed=72)
+    P2[:, rx.PARAM_NAMES["relline_lp"].index("lineE")] = 6.4
+    f2 = rx.batch_eval("relline_lp", e, P2)
+    for i in range(len(P2)):
+        assert relerr(f2[i], oracle.eval("relline_lp", e, P2[i])) < RTOL, i
