@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(320) k_rows(const VPar *__restrict__ vps, DevT
 // only when a later stage needs them (limb darkening in k_line, or the test probes).
 __global__ void __launch_bounds__(320) k_fine(const VPar *__restrict__ vps, DevTables T, Scratch S, int n_incl,
                                               double e_first, double e_last, int store_cosne, int store_trff) {
-  __shared__ __align__(16) double2 s_val[8][NG];   // the two branch contributions of every (radius, g*)
+  __shared__ double s_vx[8][NG], s_vy[8][NG];       // the two branch contributions of every (radius, g*)
   __shared__ int s_bin[8][NG];                      // their angle bins, 16 bits each (0xffff: none)
   __shared__ double s_rad[8][3];                    // per radius: gmin, gmax - gmin, r (2 pi r)^2 emis weight (< 0: off the grid)
   const int v = blockIdx.y;
@@ -781,7 +781,8 @@ __global__ void __launch_bounds__(320) k_fine(const VPar *__restrict__ vps, DevT
       else bins = i0 | (i1 << 16);
     }
     s_bin[rl][j] = bins;
-    s_val[rl][j] = val;
+    s_vx[rl][j] = val.x;
+    s_vy[rl][j] = val.y;
   }
   __syncthreads();
   {
@@ -793,9 +794,10 @@ __global__ void __launch_bounds__(320) k_fine(const VPar *__restrict__ vps, DevT
     for (int q = 0; q < NG / 4; q++) {
       const int jj = c * (NG / 4) + q;
       const int b = s_bin[r2][jj];
-      const double2 w = s_val[r2][jj];
-      if ((b & 0xffff) == m) s += w.x;
-      if ((b >> 16) == m) s += w.y;
+      // the values are read only where the bin matches (one or two of a thread's twenty candidates): the kernel runs the
+      // shared-memory data pipe, and an unconditional 128-bit read per candidate was most of its wavefronts
+      if ((b & 0xffff) == m) s += s_vx[r2][jj];
+      if ((b >> 16) == m) s += s_vy[r2][jj];
     }
     const double s1 = __shfl_down_sync(0xffffffffu, s, 1), s2 = __shfl_down_sync(0xffffffffu, s, 2),
                  s3 = __shfl_down_sync(0xffffffffu, s, 3);
