@@ -816,11 +816,48 @@ __global__ void __launch_bounds__(256) k_dist(const VPar *__restrict__ vps, DevT
   const double *part = S.distpart + (size_t) v * NR * 10;
   const int *zfirst = S.zfirst + (size_t) v * (NZMAX + 1);
   const int nz = vp.nz;
-  for (int job = t; job < nz * n_incl; job += 256) {
-    const int z = job / n_incl, m = job - z * n_incl;
-    double s = 0.0;
-    for (int i = zfirst[z + 1]; i < zfirst[z]; i++) s += part[(size_t) i * 10 + m];   // the zone's radii, ascending index
-    S.dist[((size_t) v * NZMAX + z) * MAX_INCL + m] = s;
+  // Zones of up to DIST_RUN radii: one thread per (zone, angle bin) adds the zone's radii in ascending index order.
+  // Longer zones (vectors with few zones: a one-zone model has 1000 radii, and ten threads of the block were walking
+  // them) are cut into runs of DIST_RUN radii, one thread per (bin, run), and the runs are added in order — a function of
+  // the zone's own length, so the result does not depend on the batch.
+  constexpr int DIST_RUN = 64, DIST_MAXRUN = NR / DIST_RUN + NZMAX + 1;
+  __shared__ double s_run[DIST_MAXRUN][MAX_INCL];
+  __shared__ short s_rz[DIST_MAXRUN], s_rb[NZMAX + 1];   // zone of every run, first run of every zone
+  int longest = 0;
+  for (int z = 0; z < nz; z++) longest = max(longest, zfirst[z] - zfirst[z + 1]);
+  if (longest <= DIST_RUN) {
+    for (int job = t; job < nz * n_incl; job += 256) {
+      const int z = job / n_incl, m = job - z * n_incl;
+      double s = 0.0;
+      for (int i = zfirst[z + 1]; i < zfirst[z]; i++) s += part[(size_t) i * 10 + m];   // the zone's radii, ascending index
+      S.dist[((size_t) v * NZMAX + z) * MAX_INCL + m] = s;
+    }
+  } else {
+    if (t == 0) {
+      int r = 0;
+      for (int z = 0; z < nz; z++) {
+        s_rb[z] = (short) r;
+        const int nrun = (zfirst[z] - zfirst[z + 1] + DIST_RUN - 1) / DIST_RUN;
+        for (int q = 0; q < nrun; q++) s_rz[r++] = (short) z;
+      }
+      s_rb[nz] = (short) r;
+    }
+    __syncthreads();
+    const int nrun = s_rb[nz];
+    for (int job = t; job < nrun * n_incl; job += 256) {
+      const int r = job / n_incl, m = job - r * n_incl;
+      const int z = s_rz[r], i0 = zfirst[z + 1] + (r - s_rb[z]) * DIST_RUN, i1 = min(zfirst[z], i0 + DIST_RUN);
+      double s = 0.0;
+      for (int i = i0; i < i1; i++) s += part[(size_t) i * 10 + m];
+      s_run[r][m] = s;
+    }
+    __syncthreads();
+    for (int job = t; job < nz * n_incl; job += 256) {
+      const int z = job / n_incl, m = job - z * n_incl;
+      double s = 0.0;
+      for (int r = s_rb[z]; r < s_rb[z + 1]; r++) s += s_run[r][m];
+      S.dist[((size_t) v * NZMAX + z) * MAX_INCL + m] = s;
+    }
   }
   __syncthreads();
   if (t < nz) {
