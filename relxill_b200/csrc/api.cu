@@ -437,12 +437,16 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
   // A batch that fits the arena keeps one arena slot per vector, whatever pieces it is cut into: its state survives the
   // run.  A larger batch streams through the arena chunk by chunk (every chunk starts at slot 0) and leaves no state.
   const bool resident = b->n <= S0.cap;
+  // Host-buffer call of a relxill flavour that fits the arena: everything up to the zone spectra runs on the WHOLE batch
+  // (full grids, no per-piece tails) and only the convolution, the last kernel, is cut into pieces whose device->host
+  // copies overlap the next piece's convolution.
+  const bool split_tail = pipe && resident && relxill && b->n >= cc.pipe_piece + cc.pipe_last;
   std::vector<long> piece_n;
   {
     long piece = S0.cap, last = 0;
     if (pipe && b->n >= cc.pipe_piece + cc.pipe_last) {
-      piece = std::min(S0.cap, cc.pipe_piece);
-      last = std::min(cc.pipe_last, piece);   // only the copy of the last piece is exposed: keep that piece short
+      piece = std::min(S0.cap, split_tail ? cc.pipe_piece / 2 : cc.pipe_piece);
+      last = std::min(split_tail ? cc.pipe_last / 2 : cc.pipe_last, piece);   // only the copy of the last piece is exposed: keep that piece short
     }
     const long body = b->n - last;
     long first = body % piece;
@@ -502,9 +506,37 @@ int run_batch(Engine &E, relxill_b200_batch *b, double *d_flux, cudaStream_t st,
     S.reuse = d_reuse ? d_reuse + c0 : nullptr;
     const VPar *vps = b->d_vps + c0;
     double *out = d_flux + (size_t) c0 * b->n_flux;
-    b->last_chunk0 = c0;
-    b->last_chunk_n = nc;
-    b->arena_c0 = slot0;
+    b->last_chunk0 = split_tail ? 0 : c0;
+    b->last_chunk_n = split_tail ? b->n : nc;
+    b->arena_c0 = split_tail ? 0 : slot0;
+    if (split_tail) {
+      if (ip == 0) {   // the stages before the convolution, once, on all vectors
+        Scratch Sa = S0;
+        Sa.reuse = d_reuse;
+        const VPar *va = b->d_vps;
+        const long na = b->n;
+        tm.begin(); launch_syspar(va, T, Sa, na, 1, st); tm.end(KF_SYSPAR);
+        tm.begin(); launch_zone(va, T, Sa, na, st); tm.end(KF_ZONE);
+        if (nth) { tm.begin(); launch_nth(va, T, Sa, na, b->nz_max, st); tm.end(KF_NTH, 2); }
+        if (b->any_corr) { tm.begin(); launch_syspar(va, T, Sa, na, 2, st); tm.end(KF_SYSPAR); }
+        tm.begin();
+        launch_fine(va, T, Sa, na, n_incl, econv[0], econv[NCONV], (b->any_limb || cc.keep_intermediates) ? 1 : 0,
+                    cc.keep_intermediates ? 1 : 0, st);
+        tm.end(KF_FINE, 2);
+        tm.begin(); launch_dist(va, T, Sa, na, n_incl, st); tm.end(KF_DIST);
+        tm.begin(); launch_line(va, T, Sa, na, T.econv, NCONV, 0, nz_line_min, nz_line_max, st); tm.end(KF_LINE, line_nk);
+        tm.begin(); launch_xill(va, T, Sa, na, which, cgrid, st); tm.end(KF_XILL);
+      }
+      // the zone spectra were filed by a launch over the whole batch: the kernels stride them by the row length in use
+      // (k_xill / k_conv: nz_cap x row stride per vector), not by the arena's allocation stride that scratch_slice applies
+      S.xillz = S0.xillz + (size_t) c0 * S0.nz_cap * (size_t) (cgrid ? E.tables->xill_host(xtab).xc_stride : E.tables->xill_host(xtab).stride);
+      tm.begin(); launch_conv(vps, T, S, nc, b->d_energy, b->n_flux, out, S.total, which, 0, cgrid, b->renorm3, st); tm.end(KF_CONV);
+      if (nth) {
+        tm.begin(); launch_prim_nth(vps, T, S, nc, S.total, b->d_energy, b->n_flux, out, b->renorm3, st); tm.end(KF_PRIMNTH);
+      }
+      CK(cudaMemcpyAsync(b->status + c0, S.status, nc * sizeof(int), cudaMemcpyDeviceToHost, st));
+      continue;
+    }
     if (xillver) {
       tm.begin(); launch_xillver(vps, T, S, nc, which, b->d_energy, b->n_flux, out, nex_stride, st); tm.end(KF_XILLVER);
       if (nth) {

@@ -763,3 +763,28 @@ def test_fine_grid_around_the_line_fills_the_deep_queue(rx, oracle):
     f2 = rx.batch_eval("relline_lp", e, P2)
     for i in range(len(P2)):
         assert relerr(f2[i], oracle.eval("relline_lp", e, P2[i])) < RTOL, i
+
+
+@pytest.mark.parametrize("model,zones", [("relxilllp", 50), ("relxilllpCp", None), ("relxill", None)])
+def test_pipelined_host_call_equals_the_resident_run(rx, model, zones):
+    """A host-buffer call above the pipeline threshold runs everything up to the zone spectra on the whole batch and cuts
+    only the convolution into pieces (api.cu: split_tail); the result must be the device-resident run's, bit for bit."""
+    import torch
+    e = default_grid(400)
+    n = 3100
+    P = walker_ball(model, n, seed=5) if model != "relxill" else sample_params(model, n, seed=5)
+    rx.set_cache(False)
+    rx.set_num_zones(zones)
+    try:
+        b = rx.Batch(model, e, P)
+        out = torch.zeros((n, e.size - 1), dtype=torch.float64, device="cuda")
+        b.run(out.data_ptr())
+        torch.cuda.synchronize()
+        want = out.cpu().numpy()
+        b.close()
+        got, st = rx.batch_eval(model, e, P, return_status=True)
+        assert (st == 0).mean() > 0.9
+        np.testing.assert_array_equal(got, want)
+    finally:
+        rx.set_cache(True)
+        rx.set_num_zones(None)
