@@ -139,7 +139,6 @@ struct DevTables {
   X(int, zfirst, NZMAX + 1)        /* first fine-grid index with zone < z */                                              \
   X(int, brk_i, 2)                 /* rel-table bracket (spin, mu0) */                                                    \
   X(double, brk_f, 2)              /* its interpolation factors */                                                        \
-  X(double, glim, 2)               /* min gmin / max gmax over radii */                                                   \
   X(double, reflfrac, 8)                                                                                                  \
   FINE_X(double, trff, (size_t) NR * NG * 2) FINE_X(double, cosne, (size_t) NR * NG * 2)   /* [NR][NG][2]: probes, limb */ \
   X(double, relrow, (size_t) REL_NRT * NG * 4)   /* table rows interpolated in (a, mu0): trff1,2, cosne1,2 */             \

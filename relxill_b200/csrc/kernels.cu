@@ -120,7 +120,6 @@ __global__ void __launch_bounds__(256) k_syspar(const VPar *__restrict__ vps, De
 
   // ---- fine radial grid + radial bracket in the table
   const double r1 = 1.0 / sqrt(rout), r2 = 1.0 / sqrt(rin);
-  double lmin = CUDART_INF, lmax = -CUDART_INF;
   for (int i = t; i < NR; i += 256) {
     double x = ((double) (i)) * (r2 - r1) / (NR - 1) + r1;
     x = 1.0 / x;
@@ -144,22 +143,8 @@ __global__ void __launch_bounds__(256) k_syspar(const VPar *__restrict__ vps, De
       S.it[(size_t) v * NR + i] = it;
       S.izone[(size_t) v * NR + i] = bsearch_asc<double>(vp.zone, vp.nz + 1, re);
     }
-    lmin = fmin(lmin, gmn);
-    lmax = fmax(lmax, gmx);
   }
   __syncthreads();
-  if (pass == 1) {  // extent of the line in energy (used to skip empty blocks of k_line)
-    sm.red[t] = lmin;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) { if (t < s) sm.red[t] = fmin(sm.red[t], sm.red[t + s]); __syncthreads(); }
-    if (t == 0) S.glim[2 * v] = sm.red[0];
-    __syncthreads();
-    sm.red[t] = lmax;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) { if (t < s) sm.red[t] = fmax(sm.red[t], sm.red[t + s]); __syncthreads(); }
-    if (t == 0) S.glim[2 * v + 1] = sm.red[0];
-    __syncthreads();
-  }
   if (sm.ints[1] != 0) {
     if (t == 0) S.status[v] = sm.ints[1];
     return;
