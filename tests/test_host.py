@@ -31,6 +31,16 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.ABI_SYMBOLS)
 
 
+def test_public_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/relxill_b200.h must compile as C99 (what a cgo / ctypes / Fortran-wrapper caller
+    sees) and as C++ (what XSPEC's generated wrapper sees), warnings as errors."""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "relxill_b200.h"\nint main(void) { return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)], check=True)
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)], check=True)
+
+
 def test_model_layout_matches_oracle(oracle):
     import relxill_b200 as rx
     for m in rx.PARAM_NAMES:
